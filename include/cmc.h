@@ -1,0 +1,180 @@
+/*
+ * cmc.h - C ABI of libcmc_b200.so: B200 (sm_100a) kernels for the cortico-muscular
+ * coherence hot path of paulruesing/multimodal-biosignal-analysis.
+ *
+ * The reference has no FFI: its boundary is the Python call surface of
+ *   src/pipeline/signal_features.py, data_surrogation.py and cbpa.py.
+ * Each entry point below cites the reference code whose arithmetic it replaces;
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative CMC_E* code; the message of
+ *     the last failure on the calling thread is returned by cmc_last_error();
+ *   - no exception crosses the boundary, nothing is allocated on behalf of the
+ *     caller: every buffer is caller-owned DEVICE memory (unless marked host), sized
+ *     as documented; scratch space is passed in explicitly and sized by the
+ *     matching *_workspace_bytes() function;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous with respect to the host and re-entrant per stream;
+ *   - complex values are interleaved float pairs (re, im) == numpy complex64.
+ */
+#ifndef CMC_B200_H
+#define CMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CMC_API __attribute__((visibility("default")))
+#else
+#define CMC_API
+#endif
+
+#define CMC_ABI_VERSION 1
+
+#define CMC_OK 0
+#define CMC_EINVAL (-1)      /* bad argument (shape, alignment, unsupported size) */
+#define CMC_ECUDA (-2)       /* CUDA runtime / driver error */
+#define CMC_EWORKSPACE (-3)  /* workspace too small */
+#define CMC_EUNSUPPORTED (-4)/* valid request outside the built kernel set */
+
+#define CMC_DETREND_NONE 0       /* multitaper MSC: signal_features.py:743-748 */
+#define CMC_DETREND_CONSTANT 1   /* segment mean removed before windowing (scipy Welch) */
+#define CMC_DETREND_POST_TAPER 2 /* mean of the tapered segment removed (periodogram, :419) */
+
+#define CMC_SURR_SHIFT 0
+#define CMC_SURR_PHASE 1
+#define CMC_PHASE_TABLE_BITS 12  /* phase surrogates index a 4096-entry TF32 table */
+#define CMC_FIX_SHIFT 30         /* cluster masses: int64 sums of rint(t * 2^30) */
+#define CMC_T_CLAMP 65536.0
+
+CMC_API int cmc_abi_version(void);
+CMC_API const char* cmc_last_error(void);
+/* number of kernels launched by this library in the calling process (bench bookkeeping) */
+CMC_API int64_t cmc_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1  fused detrend + taper + batched real FFT over segments.
+ * Replaces the per-window / per-taper `np.fft.rfft(window * taper)` of
+ * signal_features.py:743-748 (multitaper MSC), :412-420 (multitaper PSD) and the
+ * Welch segment transforms inside scipy.signal.coherence (preprocessing.py:1228).
+ *
+ *   x          [n_samples][ld]        float32, time-first, channel c at x[t*ld + c]
+ *   seg_starts [n_seg]                int64 (device) first sample of every segment
+ *   windows    [n_win][N]             float32 taper rows (DPSS, hann, ...)
+ *   spec       [n_seg][n_win][F][spec_ld] complex64, F = bin_hi - bin_lo + 1,
+ *              channel c at spec[...][c]; only columns [0, n_ch) are written
+ *   N          power of two in [128, 8192]
+ * ---------------------------------------------------------------------------------- */
+CMC_API int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int64_t ld,
+                     const int64_t* seg_starts, int n_seg,
+                     const float* windows, int n_win, int N, int detrend,
+                     int bin_lo, int bin_hi,
+                     float* spec, int64_t spec_ld, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2w  per-window multitaper magnitude-squared coherence with optional jackknife CI
+ * and independence-threshold mask.  Replaces signal_features.py:750-796 and
+ * jackknife_coherence_and_ci (:484-578) for all (EEG, EMG) pairs of every window.
+ *
+ *   X [W][K][F][ldx], Y [W][K][F][ldy]  complex64 spectra from cmc_fft_segments
+ *   window_mask [W] uint8 or NULL       0 = skip (outputs left untouched = zeros)
+ *   jackknife   0: coh = clip(|Sxy|^2 / (Sxx Syy), 0, 1)
+ *               1: coh = leave-one-taper-out mean, ci_lo / ci_hi = Student-t CI in
+ *                  Fisher-z space with critical value t_crit = t.ppf(1 - alpha/2, K-1)
+ *   it_threshold  >= 0: significant = coh > it_threshold;  < 0: `significant` unused
+ *   coh, ci_lo, ci_hi [W][F][Ne][Nm] float32;  significant [W][F][Ne][Nm] uint8
+ * ---------------------------------------------------------------------------------- */
+CMC_API int cmc_msc_windows(const float* X, const float* Y, int W, int K, int F, int Ne, int Nm,
+                    int64_t ldx, int64_t ldy, const uint8_t* window_mask,
+                    int jackknife, float t_crit, float it_threshold,
+                    float* coh, float* ci_lo, float* ci_hi, uint8_t* significant,
+                    void* stream);
+
+/* Same arithmetic fused with max_cmc_spectrograms_over_channels (:1132-1171): for every
+ * (window, frequency, EEG channel) the EMG channel with the largest value is selected
+ * (first index on ties, like np.argmax) and value / CI are gathered at that index, so the
+ * (W, F, Ne, Nm) tensor is never materialised.  zero_nonsignificant != 0 reproduces
+ * compute_task_wise_aggregated_cmc(enforce_independence_threshold=True) (:979-983).
+ *   out_* [W][F][Ne] float32, out_arg [W][F][Ne] int32 (may be NULL) */
+CMC_API int cmc_msc_windows_maxemg(const float* X, const float* Y, int W, int K, int F, int Ne, int Nm,
+                           int64_t ldx, int64_t ldy, const uint8_t* window_mask,
+                           int jackknife, float t_crit, float it_threshold,
+                           int zero_nonsignificant,
+                           float* out_coh, float* out_lo, float* out_hi, int32_t* out_arg,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  pooled cross-spectral density on the tensor cores (tcgen05, TF32 x3 split) fused
+ * with the auto-spectra normalisation into magnitude-squared coherence.  Replaces the
+ * averaged CSD / PSD / coherence arithmetic of signal_features.py:750-770 when the
+ * average runs over L = segments (Welch, scipy.signal.coherence) or windows x tapers.
+ *
+ *   X [L][F][ldx], Y [L][F][ldy] complex64 spectra
+ *   coh [F][Ne][Nm] float32 = clip(|sum_l conj(X) Y|^2 / (Sxx Syy), 0, 1)
+ *   sxx [F][Ne], syy [F][Nm] float32 = sum_l |.|^2           (may be NULL)
+ *   sxy [F][Ne][Nm] complex64 un-normalised cross spectrum    (may be NULL)
+ *   ws  scratch of cmc_csd_workspace_bytes(); on return it holds the whitened TF32
+ *       operands that cmc_surrogate_null() consumes.
+ * ---------------------------------------------------------------------------------- */
+CMC_API int64_t cmc_csd_workspace_bytes(int L, int F, int Ne, int Nm);
+CMC_API int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne, int Nm,
+                int64_t ldx, int64_t ldy,
+                float* coh, float* sxx, float* syy, float* sxy,
+                void* ws, int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3  surrogate null on the cached (whitened) spectra left in `ws` by cmc_csd_msc.
+ * New capability: the reference's stand-in is the analytic Beta(K-2,K-2) threshold of
+ * signal_features.py:470-481; the construction is defined in oracle/surrogate.py.
+ *
+ *   mode CMC_SURR_SHIFT: surrogate s rotates the EMG segment index by
+ *        shifts[s] * group (shifts int32 [s_end - s_begin], host-chosen, in [1, L/group))
+ *   mode CMC_SURR_PHASE: one Philox4x32-10(seed; s, l, f) phase per surrogate, segment
+ *        and frequency, shared by all EMG channels; s runs over GLOBAL indices
+ *        [s_begin, s_end) so results do not depend on how surrogates are sharded.
+ *   coh_obs  [F][Ne][Nm]  observed coherence to compare against
+ *   exceed   [F][Ne][Nm]  uint32, += #{s : C_s >= coh_obs}   (caller zero-initialises)
+ *   max_stat [s_end - s_begin] float32 max over (f, i, j) of C_s
+ *   ws2 scratch of cmc_surrogate_workspace_bytes()
+ * ---------------------------------------------------------------------------------- */
+CMC_API int64_t cmc_surrogate_workspace_bytes(int L, int F, int Ne, int Nm, int mode, int64_t n_surr);
+CMC_API int cmc_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, int mode, int group,
+                       const int32_t* shifts, uint64_t seed, int64_t s_begin, int64_t s_end,
+                       const float* coh_obs, uint32_t* exceed, float* max_stat,
+                       void* ws2, int64_t ws2_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  cluster-based permutation test: sign-flip t-map -> threshold -> connected-component
+ * labelling over a CSR adjacency -> cluster mass -> signed max statistic.  Replaces the
+ * body of mne.stats.permutation_cluster_1samp_test / spatio_temporal_cluster_1samp_test
+ * as called at cbpa.py:1027-1042 (algorithm restated in oracle/cbpa.py).
+ *
+ *   X      [n_subj][n_tests] float64, test index = t * n_ch + ch (C order)
+ *   signs  [n_perm][n_subj]  int8 in {-1,+1}, host-chosen
+ *   indptr [n_tests + 1], indices [nnz] int32 CSR adjacency (symmetric; diagonal ignored)
+ *   tail   0: clusters of t > thr and of t < -thr;  1: t > thr;  -1: t < thr
+ *   h0_fixed [p_end - p_begin] int64: signed cluster mass of largest magnitude (0 if no
+ *            cluster) as sum of rint(clamp(t) * 2^CMC_FIX_SHIFT) - exact and order-free
+ * cmc_cbpa_observed additionally returns the t-map, the label map (0 = no cluster,
+ * k = k-th cluster in MNE order: t > thr clusters first, each group by smallest flat
+ * index) and per-cluster masses (caller sizes mass_fixed / mass_f64 to n_tests).
+ * ---------------------------------------------------------------------------------- */
+CMC_API int64_t cmc_cbpa_workspace_bytes(int n_subj, int n_tests);
+CMC_API int cmc_cbpa_permute(const double* X, int n_subj, int n_tests,
+                     const int8_t* signs, int64_t p_begin, int64_t p_end,
+                     double thr, int tail, const int32_t* indptr, const int32_t* indices,
+                     int64_t* h0_fixed, void* ws, int64_t ws_bytes, void* stream);
+CMC_API int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, double thr, int tail,
+                      const int32_t* indptr, const int32_t* indices,
+                      double* t_obs, int32_t* labels, int64_t* mass_fixed, double* mass_f64,
+                      int32_t* n_clusters, void* ws, int64_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMC_B200_H */

@@ -1,0 +1,265 @@
+// K4: cluster-based permutation test.  One CTA per permutation: sign-flip t-map (fp64, numpy
+// operation order) -> threshold -> connected components over the CSR adjacency restricted to
+// supra-threshold nodes (lock-free union-find in shared memory, smaller index wins so every
+// cluster is rooted at its smallest flat index) -> order-free int64 fixed-point cluster
+// masses -> signed mass of largest magnitude.
+//
+// Replaces the body of mne.stats.permutation_cluster_1samp_test as called by the reference at
+// src/pipeline/cbpa.py:1027-1042; algorithm restated in oracle/cbpa.py.
+#include "common.cuh"
+
+namespace cmc {
+
+constexpr int kCbpaThreads = 256;
+constexpr int kCbpaMaxTests = 16384;
+
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        const int g = parent[p];
+        if (g != p) parent[x] = g;  // path halving; racing writers only ever store an ancestor
+        x = p;
+        p = g;
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    while (a != b) {
+        if (a < b) { int t = a; a = b; b = t; }   // hook the larger root under the smaller
+        const int old = atomicCAS(&parent[a], a, b);
+        if (old == a) break;
+        a = uf_find(parent, old);
+        b = uf_find(parent, b);
+    }
+}
+
+// t = mean / sqrt(var(ddof=1) / n) with numpy's evaluation order (oracle/cbpa.py:ttest_1samp_no_p):
+// sequential sums over subjects, no fused multiply-add.
+__device__ __forceinline__ double t_stat(const double* __restrict__ X, const double* sg, int n_subj,
+                                         int n_tests, int v) {
+    double sum = __dmul_rn(X[v], sg[0]);
+    for (int s = 1; s < n_subj; ++s) sum = __dadd_rn(sum, __dmul_rn(X[(int64_t)s * n_tests + v], sg[s]));
+    const double n = (double)n_subj;
+    const double mean = __ddiv_rn(sum, n);
+    double d = __dsub_rn(__dmul_rn(X[v], sg[0]), mean);
+    double ss = __dmul_rn(d, d);
+    for (int s = 1; s < n_subj; ++s) {
+        d = __dsub_rn(__dmul_rn(X[(int64_t)s * n_tests + v], sg[s]), mean);
+        ss = __dadd_rn(ss, __dmul_rn(d, d));
+    }
+    const double var = __ddiv_rn(ss, (double)(n_subj - 1));
+    return __ddiv_rn(mean, __dsqrt_rn(__ddiv_rn(var, n)));
+}
+
+__device__ __forceinline__ long long t_to_fixed(double t) {
+    t = fmin(fmax(t, -CMC_T_CLAMP), CMC_T_CLAMP);
+    return __double2ll_rn(t * (double)(1 << CMC_FIX_SHIFT));
+}
+
+template <bool OBSERVED>
+__global__ void __launch_bounds__(kCbpaThreads)
+cbpa_kernel(const double* __restrict__ X, int n_subj, int n_tests, const int8_t* __restrict__ signs,
+            int64_t n_perm, double thr, int tail, const int32_t* __restrict__ indptr,
+            const int32_t* __restrict__ indices, long long* __restrict__ h0,
+            double* __restrict__ t_obs, int32_t* __restrict__ root_out, long long* __restrict__ mass_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    long long* mass = reinterpret_cast<long long*>(smem_raw);                 // [n_tests]
+    int* parent = reinterpret_cast<int*>(mass + n_tests);                      // [n_tests]
+    double* sg = reinterpret_cast<double*>(parent + ((n_tests + 1) & ~1));      // [n_subj]
+    signed char* sgn = reinterpret_cast<signed char*>(sg + n_subj);            // [n_tests]
+    __shared__ long long red_abs[kCbpaThreads / 32];
+    __shared__ long long red_val[kCbpaThreads / 32];
+    const int tid = threadIdx.x;
+
+    for (int64_t p = blockIdx.x; p < n_perm; p += gridDim.x) {
+        __syncthreads();
+        for (int s = tid; s < n_subj; s += kCbpaThreads)
+            sg[s] = OBSERVED ? 1.0 : (double)signs[p * n_subj + s];
+        __syncthreads();
+        // ---- t-map, threshold, fixed-point image ----
+        for (int v = tid; v < n_tests; v += kCbpaThreads) {
+            const double t = t_stat(X, sg, n_subj, n_tests, v);
+            signed char s = 0;
+            if (tail == 0) s = (t > thr) ? 1 : ((t < -thr) ? -1 : 0);
+            else if (tail > 0) s = (t > thr) ? 1 : 0;
+            else s = (t < thr) ? -1 : 0;
+            sgn[v] = s;
+            parent[v] = s ? v : -1;
+            mass[v] = s ? t_to_fixed(t) : 0;
+            if (OBSERVED) t_obs[v] = t;
+        }
+        __syncthreads();
+        // ---- hook every supra-threshold edge once (u < v), same sign only ----
+        for (int v = tid; v < n_tests; v += kCbpaThreads) {
+            const signed char s = sgn[v];
+            if (!s) continue;
+            const int e1 = indptr[v + 1];
+            for (int e = indptr[v]; e < e1; ++e) {
+                const int u = indices[e];
+                if (u < v && sgn[u] == s) uf_union(parent, u, v);
+            }
+        }
+        __syncthreads();
+        // ---- cluster mass at the root (smallest index of the component) ----
+        for (int v = tid; v < n_tests; v += kCbpaThreads) {
+            if (!sgn[v]) { if (OBSERVED) root_out[v] = -1; continue; }
+            const int r = uf_find(parent, v);
+            if (r != v) atomicAdd(reinterpret_cast<unsigned long long*>(&mass[r]),
+                                  static_cast<unsigned long long>(mass[v]));
+            if (OBSERVED) root_out[v] = r;
+        }
+        __syncthreads();
+        // ---- signed mass of largest magnitude; a positive cluster wins an exact tie ----
+        long long best_abs = -1, best_val = 0;
+        for (int v = tid; v < n_tests; v += kCbpaThreads) {
+            if (sgn[v] && parent[v] == v) {
+                const long long m = mass[v];
+                const long long a = m < 0 ? -m : m;
+                if (a > best_abs || (a == best_abs && m > best_val)) { best_abs = a; best_val = m; }
+            }
+            if (OBSERVED) mass_out[v] = (sgn[v] && parent[v] == v) ? mass[v] : 0;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const long long oa = __shfl_xor_sync(0xffffffffu, best_abs, off);
+            const long long ov = __shfl_xor_sync(0xffffffffu, best_val, off);
+            if (oa > best_abs || (oa == best_abs && ov > best_val)) { best_abs = oa; best_val = ov; }
+        }
+        if ((tid & 31) == 0) { red_abs[tid >> 5] = best_abs; red_val[tid >> 5] = best_val; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kCbpaThreads / 32; ++w)
+                if (red_abs[w] > best_abs || (red_abs[w] == best_abs && red_val[w] > best_val)) {
+                    best_abs = red_abs[w];
+                    best_val = red_val[w];
+                }
+            h0[p] = best_abs < 0 ? 0 : best_val;
+        }
+    }
+}
+
+// Canonical cluster numbering of the observed map: t > thr clusters first, each group ordered by
+// root (= smallest flat index).  Single CTA; n_tests is small.
+__global__ void __launch_bounds__(1024)
+cbpa_label_kernel(const int32_t* __restrict__ root, const long long* __restrict__ mass_root, int n_tests,
+                  int32_t* __restrict__ labels, long long* __restrict__ mass_fixed,
+                  double* __restrict__ mass_f64, int32_t* __restrict__ n_clusters, int32_t* __restrict__ rank) {
+    __shared__ int warp_cnt[32];
+    __shared__ int running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {          // 0: positive roots, 1: negative roots
+        for (int base = 0; base < n_tests; base += 1024) {
+            const int v = base + tid;
+            bool is_root = false;
+            if (v < n_tests && root[v] == v) is_root = pass == 0 ? (mass_root[v] >= 0) : (mass_root[v] < 0);
+            const unsigned bal = __ballot_sync(0xffffffffu, is_root);
+            if (lane == 0) warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = running;
+            for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+            if (is_root) {
+                const int k = off + __popc(bal & ((1u << lane) - 1));
+                rank[v] = k;
+                mass_fixed[k] = mass_root[v];
+                mass_f64[k] = (double)mass_root[v] / (double)(1 << CMC_FIX_SHIFT);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < 32; ++w) tot += warp_cnt[w];
+                running += tot;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *n_clusters = running;
+    for (int v = tid; v < n_tests; v += 1024) labels[v] = root[v] >= 0 ? rank[root[v]] + 1 : 0;
+}
+
+static size_t cbpa_smem_bytes(int n_subj, int n_tests) {
+    return sizeof(long long) * n_tests + sizeof(int) * ((n_tests + 1) & ~1) + sizeof(double) * n_subj +
+           n_tests + 16;
+}
+
+static int cbpa_check(const double* X, int n_subj, int n_tests, const int32_t* indptr, const int32_t* indices,
+                      int tail, double thr) {
+    CMC_REQUIRE(X && indptr && indices, "cmc_cbpa: null pointer");
+    CMC_REQUIRE(n_subj >= 2, "cmc_cbpa: need at least 2 subjects");
+    CMC_REQUIRE(n_tests >= 1 && n_tests <= kCbpaMaxTests, "cmc_cbpa: n_tests=%d outside [1, %d]", n_tests,
+                kCbpaMaxTests);
+    CMC_REQUIRE(tail >= -1 && tail <= 1, "cmc_cbpa: tail must be -1, 0 or 1");
+    CMC_REQUIRE(!(tail == 0 && thr < 0), "cmc_cbpa: two-tailed test needs a non-negative threshold");
+    return CMC_OK;
+}
+
+}  // namespace cmc
+
+extern "C" int64_t cmc_cbpa_workspace_bytes(int n_subj, int n_tests) {
+    (void)n_subj;
+    // root int32 + rank int32 + mass_root int64 per test
+    return (int64_t)n_tests * 16 + 256;
+}
+
+extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const int8_t* signs,
+                                int64_t p_begin, int64_t p_end, double thr, int tail,
+                                const int32_t* indptr, const int32_t* indices, int64_t* h0_fixed,
+                                void* ws, int64_t ws_bytes, void* stream) {
+    using namespace cmc;
+    (void)ws; (void)ws_bytes;
+    int rc = cbpa_check(X, n_subj, n_tests, indptr, indices, tail, thr);
+    if (rc) return rc;
+    CMC_REQUIRE(signs && h0_fixed && p_end >= p_begin, "cmc_cbpa_permute: bad permutation range");
+    const int64_t n_perm = p_end - p_begin;
+    if (n_perm == 0) return CMC_OK;
+    const size_t smem = cbpa_smem_bytes(n_subj, n_tests);
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<false>), 227 * 1024);
+    if (rc) return rc;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbpa_kernel<false>, kCbpaThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t grid = n_perm < (int64_t)sms * per_sm ? n_perm : (int64_t)sms * per_sm;
+    cbpa_kernel<false><<<(unsigned)grid, kCbpaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        X, n_subj, n_tests, signs + p_begin * n_subj, n_perm, thr, tail, indptr, indices,
+        reinterpret_cast<long long*>(h0_fixed), nullptr, nullptr, nullptr);
+    CMC_CHECK_LAUNCH("cbpa_kernel<perm>");
+    return CMC_OK;
+}
+
+extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, double thr, int tail,
+                                 const int32_t* indptr, const int32_t* indices, double* t_obs,
+                                 int32_t* labels, int64_t* mass_fixed, double* mass_f64,
+                                 int32_t* n_clusters, void* ws, int64_t ws_bytes, void* stream) {
+    using namespace cmc;
+    int rc = cbpa_check(X, n_subj, n_tests, indptr, indices, tail, thr);
+    if (rc) return rc;
+    CMC_REQUIRE(t_obs && labels && mass_fixed && mass_f64 && n_clusters && ws, "cmc_cbpa_observed: null pointer");
+    if (ws_bytes < cmc_cbpa_workspace_bytes(n_subj, n_tests)) {
+        set_error("cmc_cbpa_observed: workspace %lld < %lld bytes", (long long)ws_bytes,
+                  (long long)cmc_cbpa_workspace_bytes(n_subj, n_tests));
+        return CMC_EWORKSPACE;
+    }
+    CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "cmc_cbpa_observed: workspace must be 8-byte aligned");
+    long long* mass_root = reinterpret_cast<long long*>(ws);
+    int32_t* root = reinterpret_cast<int32_t*>(mass_root + n_tests);
+    int32_t* rank = root + n_tests;
+    long long* h0_tmp = reinterpret_cast<long long*>(rank + n_tests + (n_tests & 1));
+    const size_t smem = cbpa_smem_bytes(n_subj, n_tests);
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true>), 227 * 1024);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cbpa_kernel<true><<<1, kCbpaThreads, smem, st>>>(X, n_subj, n_tests, nullptr, 1, thr, tail, indptr,
+                                                     indices, h0_tmp, t_obs, root, mass_root);
+    CMC_CHECK_LAUNCH("cbpa_kernel<observed>");
+    cbpa_label_kernel<<<1, 1024, 0, st>>>(root, mass_root, n_tests, labels,
+                                           reinterpret_cast<long long*>(mass_fixed), mass_f64, n_clusters, rank);
+    CMC_CHECK_LAUNCH("cbpa_label_kernel");
+    return CMC_OK;
+}

@@ -1,0 +1,319 @@
+// K1: fused detrend + taper + batched real FFT over Welch / multitaper segments.
+//
+// Replaces np.fft.rfft(window * taper) of the reference (signal_features.py:743-748,
+// :412-420; scipy Welch internals for preprocessing.py:1228).
+//
+// Layout ("batch fastest"): one CTA owns one segment and a tile of CT adjacent channels.
+// The time-first input x[t][c] makes the CT channels of one sample contiguous, so global
+// loads are sector-exact, the shared-memory work array buf[point][channel] is bank-conflict
+// free at every butterfly stride, and the twiddle of a butterfly is shared by the CT lanes
+// that process the same point for different channels.
+//
+// Real FFT of length N through a complex FFT of length M = N/2 on z[m] = x[2m] + i x[2m+1]
+// (Stockham autosort, radix 16/8 in registers, in-place in shared memory with register
+// staging), then the split X[b] = E[b] - i W_N^b O[b] for the requested bins only.
+#include "common.cuh"
+
+namespace cmc {
+
+// ---------------------------------------------------------------- small DFTs in registers
+template <int R> __device__ __forceinline__ void dft(float2 (&v)[R]);
+
+template <> __device__ __forceinline__ void dft<2>(float2 (&v)[2]) {
+    float2 a = v[0];
+    v[0] = cadd(a, v[1]);
+    v[1] = csub(a, v[1]);
+}
+template <> __device__ __forceinline__ void dft<4>(float2 (&v)[4]) {
+    float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    float2 t2 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+    float2 t3 = make_float2(d.y, -d.x);  // -i * d
+    v[0] = cadd(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[2] = csub(t0, t2);
+    v[3] = csub(t1, t3);
+}
+template <> __device__ __forceinline__ void dft<8>(float2 (&v)[8]) {
+    float2 e[4] = {v[0], v[2], v[4], v[6]};
+    float2 o[4] = {v[1], v[3], v[5], v[7]};
+    dft<4>(e);
+    dft<4>(o);
+    const float h = 0.70710678118654752f;
+    o[1] = make_float2((o[1].x + o[1].y) * h, (o[1].y - o[1].x) * h);
+    o[2] = make_float2(o[2].y, -o[2].x);
+    o[3] = make_float2((o[3].y - o[3].x) * h, -(o[3].x + o[3].y) * h);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = cadd(e[k], o[k]);
+        v[k + 4] = csub(e[k], o[k]);
+    }
+}
+template <> __device__ __forceinline__ void dft<16>(float2 (&v)[16]) {
+    float2 e[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        e[k] = v[2 * k];
+        o[k] = v[2 * k + 1];
+    }
+    dft<8>(e);
+    dft<8>(o);
+    // W16^k = (cos(pi k / 8), -sin(pi k / 8))
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
+    const float h = 0.70710678118654752f;
+    o[1] = cmul(o[1], make_float2(c1, -s1));
+    o[2] = make_float2((o[2].x + o[2].y) * h, (o[2].y - o[2].x) * h);
+    o[3] = cmul(o[3], make_float2(s1, -c1));
+    o[4] = make_float2(o[4].y, -o[4].x);
+    o[5] = cmul(o[5], make_float2(-s1, -c1));
+    o[6] = make_float2((o[6].y - o[6].x) * h, -(o[6].x + o[6].y) * h);
+    o[7] = cmul(o[7], make_float2(-c1, -s1));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[k] = cadd(e[k], o[k]);
+        v[k + 8] = csub(e[k], o[k]);
+    }
+}
+
+// twiddle powers w^1..w^(R-1) from a few table entries (<= 2 chained multiplies each)
+template <int R>
+__device__ __forceinline__ void apply_twiddles(float2 (&v)[R], const float2* __restrict__ tw, int base) {
+    // tw index of w^r is r * base
+    float2 w1 = __ldg(tw + base);
+    v[1] = cmul(v[1], w1);
+    if (R >= 4) {
+        float2 w2 = __ldg(tw + 2 * base);
+        v[2] = cmul(v[2], w2);
+        float2 w3 = cmul(w1, w2);
+        v[3] = cmul(v[3], w3);
+        if (R >= 8) {
+            float2 w4 = __ldg(tw + 4 * base);
+            v[4] = cmul(v[4], w4);
+            v[5] = cmul(v[5], cmul(w4, w1));
+            v[6] = cmul(v[6], cmul(w4, w2));
+            float2 w7 = cmul(w4, w3);
+            v[7] = cmul(v[7], w7);
+            if (R >= 16) {
+                float2 w8 = __ldg(tw + 8 * base);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));
+                v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3));
+                v[12] = cmul(v[12], cmul(w8, w4));
+                v[13] = cmul(v[13], cmul(w8, cmul(w4, w1)));
+                v[14] = cmul(v[14], cmul(w8, cmul(w4, w2)));
+                v[15] = cmul(v[15], cmul(w8, w7));
+            }
+        }
+    }
+}
+
+template <int M> struct Plan;
+template <> struct Plan<64>   { static constexpr int R0 = 8,  R1 = 8,  R2 = 1;  };
+template <> struct Plan<128>  { static constexpr int R0 = 16, R1 = 8,  R2 = 1;  };
+template <> struct Plan<256>  { static constexpr int R0 = 16, R1 = 16, R2 = 1;  };
+template <> struct Plan<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8;  };
+template <> struct Plan<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8;  };
+template <> struct Plan<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8;  };
+template <> struct Plan<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; };
+
+constexpr int kElemsPerThread = 32;
+
+// Stockham pass of radix R on buf[M][CT] where NS = product of the previous radices.
+template <int M, int CT, int NT, int R, int NS>
+__device__ __forceinline__ void pass_smem(float2* buf, const float2* __restrict__ twM, int tid) {
+    constexpr int B = kElemsPerThread / R;
+    constexpr int STRIDE = M / R;
+    float2 v[B][R];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const int q = tid + b * NT;
+        const int c = q % CT, j = q / CT;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[b][r] = buf[(j + r * STRIDE) * CT + c];
+        const int k = j % NS;
+        apply_twiddles<R>(v[b], twM, k * (M / (NS * R)));
+        dft<R>(v[b]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const int q = tid + b * NT;
+        const int c = q % CT, j = q / CT;
+        const int k = j % NS;
+        const int j0 = (j / NS) * (NS * R) + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[(j0 + r * NS) * CT + c] = v[b][r];
+    }
+    __syncthreads();
+}
+
+template <int M, int CT>
+__global__ void __launch_bounds__(M * CT / kElemsPerThread, (M * CT / kElemsPerThread) <= 256 ? 2 : 1)
+fft_segments_kernel(const float* __restrict__ x, int64_t n_samples, int n_ch, int64_t ld,
+                    const int64_t* __restrict__ seg_starts,
+                    const float* __restrict__ windows, int n_win, int detrend,
+                    int bin_lo, int F,
+                    float2* __restrict__ spec, int64_t spec_ld,
+                    const float2* __restrict__ twM, const float2* __restrict__ twN) {
+    constexpr int N = 2 * M;
+    constexpr int NT = M * CT / kElemsPerThread;
+    constexpr int R0 = Plan<M>::R0, R1 = Plan<M>::R1, R2 = Plan<M>::R2;
+    constexpr int B0 = kElemsPerThread / R0;
+    constexpr int S0 = M / R0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);
+    float* part = reinterpret_cast<float*>(smem_raw + sizeof(float2) * M * CT);  // [NT/32][32]
+    float* mean_s = part + NT;                                                    // [CT]
+
+    const int tid = threadIdx.x;
+    const int seg = blockIdx.x;
+    const int c0 = blockIdx.y * CT;
+    const int64_t start = seg_starts[seg];
+    const float* xs = x + start * ld + c0;
+
+    for (int kw = 0; kw < n_win; ++kw) {
+        const float* win = windows + (int64_t)kw * N;
+        float2 v[B0][R0];
+        // ---- load raw samples for this thread's first-pass butterflies ----
+#pragma unroll
+        for (int b = 0; b < B0; ++b) {
+            const int q = tid + b * NT;
+            const int c = q % CT, j = q / CT;
+            const bool ok = (c0 + c) < n_ch;
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const int n0 = 2 * (j + r * S0);
+                float a = 0.f, bb = 0.f;
+                if (ok) {
+                    a = __ldg(xs + (int64_t)n0 * ld + c);
+                    bb = __ldg(xs + (int64_t)(n0 + 1) * ld + c);
+                }
+                v[b][r] = make_float2(a, bb);
+            }
+        }
+        float mu = 0.f;
+        if (detrend == CMC_DETREND_CONSTANT) {
+            // deterministic per-channel mean: lane partials -> per-warp rows -> fixed-order sum
+            if (kw == 0) {
+                float s = 0.f;
+#pragma unroll
+                for (int b = 0; b < B0; ++b)
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) s += v[b][r].x + v[b][r].y;
+                // lanes with equal (lane % CT) hold the same channel (NT % CT == 0, CT | 32)
+#pragma unroll
+                for (int off = 16; off >= CT; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if ((tid & 31) < CT) part[(tid >> 5) * CT + (tid & 31)] = s;
+                __syncthreads();
+                if (tid < CT) {
+                    float t = 0.f;
+                    for (int w = 0; w < NT / 32; ++w) t += part[w * CT + tid];
+                    mean_s[tid] = t * (1.0f / N);
+                }
+                __syncthreads();
+            }
+            mu = mean_s[tid % CT];
+        }
+        // ---- taper and first Stockham pass (NS = 1: no twiddles) ----
+#pragma unroll
+        for (int b = 0; b < B0; ++b) {
+            const int q = tid + b * NT;
+            const int c = q % CT, j = q / CT;
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const int n0 = 2 * (j + r * S0);
+                const float2 w = __ldg(reinterpret_cast<const float2*>(win + n0));
+                v[b][r].x = (v[b][r].x - mu) * w.x;
+                v[b][r].y = (v[b][r].y - mu) * w.y;
+            }
+            dft<R0>(v[b]);
+#pragma unroll
+            for (int r = 0; r < R0; ++r) buf[(j * R0 + r) * CT + c] = v[b][r];
+        }
+        __syncthreads();
+        if (R1 > 1) pass_smem<M, CT, NT, (R1 > 1 ? R1 : 2), R0>(buf, twM, tid);
+        if (R2 > 1) pass_smem<M, CT, NT, (R2 > 1 ? R2 : 2), R0 * R1>(buf, twM, tid);
+
+        // ---- real-FFT split for the requested bins, coalesced over channels ----
+        float2* out = spec + ((int64_t)(seg * n_win + kw) * F) * spec_ld + c0;
+        for (int q = tid; q < F * CT; q += NT) {
+            const int c = q % CT, bi = q / CT;
+            const int b = bin_lo + bi;
+            if (c0 + c < n_ch) {
+                const float2 A = buf[(b & (M - 1)) * CT + c];
+                const float2 Bz = buf[((M - b) & (M - 1)) * CT + c];
+                const float2 E = make_float2(0.5f * (A.x + Bz.x), 0.5f * (A.y - Bz.y));
+                const float2 O = make_float2(0.5f * (A.x - Bz.x), 0.5f * (A.y + Bz.y));
+                const float2 T = cmul(__ldg(twN + b), O);
+                float2 X = make_float2(E.x + T.y, E.y - T.x);
+                if (b == 0 || b == M) X.y = 0.f;
+                if (detrend == CMC_DETREND_POST_TAPER && b == 0) X.x = 0.f;
+                out[(int64_t)bi * spec_ld + c] = X;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int M, int CT>
+static int launch_fft(const float* x, int64_t n_samples, int n_ch, int64_t ld,
+                      const int64_t* seg_starts, int n_seg, const float* windows, int n_win,
+                      int detrend, int bin_lo, int F, float2* spec, int64_t spec_ld,
+                      const float2* twM, const float2* twN, cudaStream_t st) {
+    constexpr int NT = M * CT / kElemsPerThread;
+    static_assert(NT >= 32 && NT <= 1024 && NT % 32 == 0, "bad CTA size");
+    static_assert(32 % CT == 0, "CT must divide the warp");
+    const size_t smem = sizeof(float2) * M * CT + sizeof(float) * (NT + CT);
+    auto kern = fft_segments_kernel<M, CT>;
+    int rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
+    if (rc) return rc;
+    dim3 grid(n_seg, (n_ch + CT - 1) / CT);
+    kern<<<grid, NT, smem, st>>>(x, n_samples, n_ch, ld, seg_starts, windows, n_win, detrend,
+                                 bin_lo, F, spec, spec_ld, twM, twN);
+    CMC_CHECK_LAUNCH("fft_segments_kernel");
+    return CMC_OK;
+}
+
+}  // namespace cmc
+
+extern "C" int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int64_t ld,
+                                const int64_t* seg_starts, int n_seg,
+                                const float* windows, int n_win, int N, int detrend,
+                                int bin_lo, int bin_hi,
+                                float* spec, int64_t spec_ld, void* stream) {
+    using namespace cmc;
+    CMC_REQUIRE(x && seg_starts && windows && spec, "cmc_fft_segments: null pointer");
+    CMC_REQUIRE(n_ch >= 1 && ld >= n_ch && spec_ld >= n_ch, "cmc_fft_segments: bad channel pitch");
+    CMC_REQUIRE(n_seg >= 0 && n_win >= 1, "cmc_fft_segments: bad segment/window count");
+    CMC_REQUIRE(detrend >= 0 && detrend <= 2, "cmc_fft_segments: detrend must be 0, 1 or 2");
+    CMC_REQUIRE(bin_lo >= 0 && bin_hi >= bin_lo && bin_hi <= N / 2,
+                "cmc_fft_segments: bins [%d, %d] outside [0, %d]", bin_lo, bin_hi, N / 2);
+    CMC_REQUIRE((reinterpret_cast<uintptr_t>(windows) & 7) == 0 && (reinterpret_cast<uintptr_t>(spec) & 7) == 0,
+                "cmc_fft_segments: windows/spec must be 8-byte aligned");
+    if (n_seg == 0) return CMC_OK;
+    if (N < 128 || N > 8192 || (N & (N - 1))) {
+        set_error("cmc_fft_segments: N=%d unsupported (power of two in [128, 8192])", N);
+        return CMC_EUNSUPPORTED;
+    }
+    const float2 *twM, *twN;
+    int rc = get_twiddles(N, &twM, &twN);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int F = bin_hi - bin_lo + 1;
+    float2* sp = reinterpret_cast<float2*>(spec);
+#define CMC_FFT_CASE(NN, CT)                                                                   \
+    case NN:                                                                                   \
+        return launch_fft<NN / 2, CT>(x, n_samples, n_ch, ld, seg_starts, n_seg, windows, n_win, \
+                                      detrend, bin_lo, F, sp, spec_ld, twM, twN, st)
+    switch (N) {
+        CMC_FFT_CASE(128, 32);
+        CMC_FFT_CASE(256, 32);
+        CMC_FFT_CASE(512, 32);
+        CMC_FFT_CASE(1024, 16);
+        CMC_FFT_CASE(2048, 8);
+        CMC_FFT_CASE(4096, 8);
+        CMC_FFT_CASE(8192, 4);
+    }
+#undef CMC_FFT_CASE
+    return CMC_EUNSUPPORTED;
+}

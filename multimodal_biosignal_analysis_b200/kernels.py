@@ -1,0 +1,242 @@
+"""Typed wrappers over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+This is the only module that touches ctypes pointers.  Every function enqueues on the
+current torch CUDA stream and never synchronises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+DETREND_NONE, DETREND_CONSTANT, DETREND_POST_TAPER = 0, 1, 2
+SURR_SHIFT, SURR_PHASE = 0, 1
+FIX_SHIFT = 30
+FIX_SCALE = float(1 << FIX_SHIFT)
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (this package has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+
+
+def fft_segments(x: torch.Tensor, seg_starts: torch.Tensor, windows: torch.Tensor, detrend: int = 0,
+                 bin_lo: int = 0, bin_hi: int | None = None, out: torch.Tensor | None = None,
+                 ch_offset: int = 0) -> torch.Tensor:
+    """Spectra of every (segment, window row, channel): complex64 (n_seg, K, F, C).
+
+    x (n_samples, n_ch) float32 with unit channel stride; seg_starts int64 (n_seg,);
+    windows float32 (K, N).  With ``out`` given (complex64 (n_seg, K, F, C_total)) the
+    channels are written at columns [ch_offset, ch_offset + n_ch).
+    """
+    _need_cuda(x, "x", torch.float32)
+    _need_cuda(seg_starts, "seg_starts", torch.int64)
+    _need_cuda(windows, "windows", torch.float32)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be (n_samples, n_ch) with contiguous channels")
+    windows = windows.contiguous()
+    seg_starts = seg_starts.contiguous()
+    n_samples, n_ch = x.shape
+    K, N = windows.shape
+    n_seg = seg_starts.numel()
+    if bin_hi is None:
+        bin_hi = N // 2
+    F = bin_hi - bin_lo + 1
+    if n_seg and (int(seg_starts.min()) < 0 or int(seg_starts.max()) + N > n_samples):
+        raise ValueError("segment outside the recording")
+    if out is None:
+        out = torch.empty((n_seg, K, F, n_ch), dtype=torch.complex64, device=x.device)
+        ch_offset = 0
+    else:
+        _need_cuda(out, "out", torch.complex64)
+        if out.shape[:3] != (n_seg, K, F) or not out.is_contiguous() or ch_offset + n_ch > out.shape[3]:
+            raise ValueError("out has the wrong shape")
+    lib = _lib.load()
+    rc = lib.cmc_fft_segments(x.data_ptr(), n_samples, n_ch, x.stride(0), seg_starts.data_ptr(), n_seg,
+                              windows.data_ptr(), K, N, detrend, bin_lo, bin_hi,
+                              out.data_ptr() + 8 * ch_offset, out.shape[3], _lib.current_stream())
+    _lib.check(rc, "cmc_fft_segments")
+    return out
+
+
+def _spectra_dims(X, Y):
+    _need_cuda(X, "X", torch.complex64)
+    _need_cuda(Y, "Y", torch.complex64)
+    if X.dim() != 4 or Y.dim() != 4 or X.shape[:3] != Y.shape[:3]:
+        raise ValueError("X, Y must be (W, K, F, channels) with equal leading dims")
+    if X.stride(3) != 1 or Y.stride(3) != 1:
+        raise ValueError("channel stride must be 1")
+    W, K, F, Ne = X.shape
+    Nm = Y.shape[3]
+    for t in (X, Y):
+        if t.stride(0) != K * F * t.stride(2) or t.stride(1) != F * t.stride(2):
+            raise ValueError("spectra must be dense in (W, K, F)")
+    return W, K, F, Ne, Nm, X.stride(2), Y.stride(2)
+
+
+def msc_windows(X: torch.Tensor, Y: torch.Tensor, window_mask: torch.Tensor | None = None,
+                jackknife: bool = False, t_crit: float = 0.0, it_threshold: float | None = None):
+    """Per-window MSC. Returns (coh, ci_lo, ci_hi, significant); absent outputs are None.
+    Outputs of masked-out windows are zero."""
+    W, K, F, Ne, Nm, ldx, ldy = _spectra_dims(X, Y)
+    dev = X.device
+    shape = (W, F, Ne, Nm)
+    alloc = torch.zeros if window_mask is not None else torch.empty
+    coh = alloc(shape, dtype=torch.float32, device=dev)
+    lo = alloc(shape, dtype=torch.float32, device=dev) if jackknife else None
+    hi = alloc(shape, dtype=torch.float32, device=dev) if jackknife else None
+    sig = alloc(shape, dtype=torch.uint8, device=dev) if it_threshold is not None else None
+    if window_mask is not None:
+        _need_cuda(window_mask, "window_mask", torch.uint8)
+        if window_mask.shape != (W,):
+            raise ValueError("window_mask must have shape (W,)")
+    lib = _lib.load()
+    rc = lib.cmc_msc_windows(X.data_ptr(), Y.data_ptr(), W, K, F, Ne, Nm, ldx, ldy, _lib.ptr(window_mask),
+                             int(jackknife), float(t_crit), -1.0 if it_threshold is None else float(it_threshold),
+                             coh.data_ptr(), _lib.ptr(lo), _lib.ptr(hi), _lib.ptr(sig), _lib.current_stream())
+    _lib.check(rc, "cmc_msc_windows")
+    return coh, lo, hi, sig
+
+
+def msc_windows_maxemg(X: torch.Tensor, Y: torch.Tensor, window_mask: torch.Tensor | None = None,
+                       jackknife: bool = False, t_crit: float = 0.0, it_threshold: float | None = None,
+                       zero_nonsignificant: bool = False, return_argmax: bool = False):
+    """Fused per-window MSC + EMG-argmax: returns (coh, lo, hi, argmax) of shape (W, F, Ne)."""
+    W, K, F, Ne, Nm, ldx, ldy = _spectra_dims(X, Y)
+    dev = X.device
+    shape = (W, F, Ne)
+    alloc = torch.zeros if window_mask is not None else torch.empty
+    coh = alloc(shape, dtype=torch.float32, device=dev)
+    lo = alloc(shape, dtype=torch.float32, device=dev) if jackknife else None
+    hi = alloc(shape, dtype=torch.float32, device=dev) if jackknife else None
+    arg = alloc(shape, dtype=torch.int32, device=dev) if return_argmax else None
+    if zero_nonsignificant and it_threshold is None:
+        raise ValueError("zero_nonsignificant needs it_threshold")
+    lib = _lib.load()
+    rc = lib.cmc_msc_windows_maxemg(X.data_ptr(), Y.data_ptr(), W, K, F, Ne, Nm, ldx, ldy,
+                                    _lib.ptr(window_mask), int(jackknife), float(t_crit),
+                                    -1.0 if it_threshold is None else float(it_threshold),
+                                    int(zero_nonsignificant), coh.data_ptr(), _lib.ptr(lo), _lib.ptr(hi),
+                                    _lib.ptr(arg), _lib.current_stream())
+    _lib.check(rc, "cmc_msc_windows_maxemg")
+    return coh, lo, hi, arg
+
+
+# ----------------------------------------------------------------------------- K2 / K3
+def _pooled_dims(X, Y):
+    _need_cuda(X, "X", torch.complex64)
+    _need_cuda(Y, "Y", torch.complex64)
+    if X.dim() != 3 or Y.dim() != 3 or X.shape[:2] != Y.shape[:2]:
+        raise ValueError("X, Y must be (L, F, channels)")
+    if X.stride(2) != 1 or Y.stride(2) != 1 or X.stride(0) != X.shape[1] * X.stride(1) or \
+            Y.stride(0) != Y.shape[1] * Y.stride(1):
+        raise ValueError("spectra must be dense in (L, F) with unit channel stride")
+    L, F, Ne = X.shape
+    return L, F, Ne, Y.shape[2], X.stride(1), Y.stride(1)
+
+
+class PooledCsd:
+    """Result of the tensor-core CSD pass; keeps the whitened operands for the surrogate null."""
+
+    def __init__(self, coh, sxx, syy, sxy, ws, dims):
+        self.coh, self.sxx, self.syy, self.sxy, self.ws, self.dims = coh, sxx, syy, sxy, ws, dims
+
+
+def csd_msc(X: torch.Tensor, Y: torch.Tensor, want_sxy: bool = False) -> PooledCsd:
+    """Pooled coherence over the leading axis on the tensor cores: coh (F, Ne, Nm)."""
+    L, F, Ne, Nm, ldx, ldy = _pooled_dims(X, Y)
+    dev = X.device
+    lib = _lib.load()
+    ws_bytes = int(lib.cmc_csd_workspace_bytes(L, F, Ne, Nm))
+    if ws_bytes < 0:
+        _lib.check(ws_bytes, "cmc_csd_workspace_bytes")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    coh = torch.empty((F, Ne, Nm), dtype=torch.float32, device=dev)
+    sxx = torch.empty((F, Ne), dtype=torch.float32, device=dev)
+    syy = torch.empty((F, Nm), dtype=torch.float32, device=dev)
+    sxy = torch.empty((F, Ne, Nm), dtype=torch.complex64, device=dev) if want_sxy else None
+    rc = lib.cmc_csd_msc(X.data_ptr(), Y.data_ptr(), L, F, Ne, Nm, ldx, ldy, coh.data_ptr(), sxx.data_ptr(),
+                         syy.data_ptr(), _lib.ptr(sxy), ws.data_ptr(), ws_bytes, _lib.current_stream())
+    _lib.check(rc, "cmc_csd_msc")
+    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm))
+
+
+def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: torch.Tensor | None = None,
+                   group: int = 1, seed: int = 0, exceed: torch.Tensor | None = None):
+    """Surrogates [s_begin, s_end) against csd.coh: returns (exceed uint32 (F,Ne,Nm) accumulated,
+    max_stat float32 (s_end - s_begin,))."""
+    L, F, Ne, Nm = csd.dims
+    dev = csd.coh.device
+    n = s_end - s_begin
+    lib = _lib.load()
+    if exceed is None:
+        exceed = torch.zeros((F, Ne, Nm), dtype=torch.int32, device=dev)
+    max_stat = torch.empty(n, dtype=torch.float32, device=dev)
+    if mode == SURR_SHIFT:
+        _need_cuda(shifts, "shifts", torch.int32)
+        if shifts.numel() != n:
+            raise ValueError("one shift per surrogate in [s_begin, s_end)")
+    ws2_bytes = int(lib.cmc_surrogate_workspace_bytes(L, F, Ne, Nm, mode, n))
+    if ws2_bytes < 0:
+        _lib.check(ws2_bytes, "cmc_surrogate_workspace_bytes")
+    ws2 = torch.empty(max(ws2_bytes, 16), dtype=torch.uint8, device=dev)
+    rc = lib.cmc_surrogate_null(csd.ws.data_ptr(), L, F, Ne, Nm, mode, group, _lib.ptr(shifts), seed, s_begin,
+                                s_end, csd.coh.data_ptr(), exceed.data_ptr(), max_stat.data_ptr(),
+                                ws2.data_ptr(), ws2_bytes, _lib.current_stream())
+    _lib.check(rc, "cmc_surrogate_null")
+    return exceed, max_stat
+
+
+# ----------------------------------------------------------------------------- K4
+def _cbpa_args(X, indptr, indices):
+    _need_cuda(X, "X", torch.float64)
+    _need_cuda(indptr, "indptr", torch.int32)
+    _need_cuda(indices, "indices", torch.int32)
+    if X.dim() != 2 or not X.is_contiguous():
+        raise ValueError("X must be contiguous (n_subj, n_tests)")
+    n_subj, n_tests = X.shape
+    if indptr.numel() != n_tests + 1:
+        raise ValueError("indptr must have n_tests + 1 entries")
+    return n_subj, n_tests
+
+
+def cbpa_observed(X: torch.Tensor, thr: float, tail: int, indptr: torch.Tensor, indices: torch.Tensor):
+    """Observed clustering: (t_obs f64 (n_tests,), labels int32, mass_fixed int64 (n_clusters,),
+    n_clusters).  Synchronises once to read the cluster count."""
+    n_subj, n_tests = _cbpa_args(X, indptr, indices)
+    dev = X.device
+    lib = _lib.load()
+    ws_bytes = int(lib.cmc_cbpa_workspace_bytes(n_subj, n_tests))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    t_obs = torch.empty(n_tests, dtype=torch.float64, device=dev)
+    labels = torch.empty(n_tests, dtype=torch.int32, device=dev)
+    mass_fixed = torch.zeros(n_tests, dtype=torch.int64, device=dev)
+    mass_f64 = torch.zeros(n_tests, dtype=torch.float64, device=dev)
+    n_clusters = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = lib.cmc_cbpa_observed(X.data_ptr(), n_subj, n_tests, float(thr), int(tail), indptr.data_ptr(),
+                               indices.data_ptr(), t_obs.data_ptr(), labels.data_ptr(), mass_fixed.data_ptr(),
+                               mass_f64.data_ptr(), n_clusters.data_ptr(), ws.data_ptr(), ws_bytes,
+                               _lib.current_stream())
+    _lib.check(rc, "cmc_cbpa_observed")
+    n = int(n_clusters.item())
+    return t_obs, labels, mass_fixed[:n], n
+
+
+def cbpa_permute(X: torch.Tensor, signs: torch.Tensor, p_begin: int, p_end: int, thr: float, tail: int,
+                 indptr: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+    """Max-cluster statistic (int64 fixed point) of permutations [p_begin, p_end) of the sign table."""
+    n_subj, n_tests = _cbpa_args(X, indptr, indices)
+    _need_cuda(signs, "signs", torch.int8)
+    if signs.dim() != 2 or signs.shape[1] != n_subj or not signs.is_contiguous():
+        raise ValueError("signs must be contiguous int8 (n_perm, n_subj)")
+    if not (0 <= p_begin <= p_end <= signs.shape[0]):
+        raise ValueError("permutation range outside the sign table")
+    h0 = torch.empty(p_end - p_begin, dtype=torch.int64, device=X.device)
+    lib = _lib.load()
+    rc = lib.cmc_cbpa_permute(X.data_ptr(), n_subj, n_tests, signs.data_ptr(), p_begin, p_end, float(thr),
+                              int(tail), indptr.data_ptr(), indices.data_ptr(), h0.data_ptr(), None, 0,
+                              _lib.current_stream())
+    _lib.check(rc, "cmc_cbpa_permute")
+    return h0

@@ -1,0 +1,108 @@
+"""GPU parity: K4 (CBPA) vs the MNE-algorithm oracle - t-map, label map, fixed-point masses, H0
+and p-values bit-exact for a host-supplied sign table."""
+import numpy as np
+import pytest
+import torch
+from scipy.stats import t as t_dist
+
+from oracle import cbpa as ocb
+from multimodal_biosignal_analysis_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _csr(adj):
+    a = adj.tocsr()
+    a.sort_indices()
+    return (torch.as_tensor(a.indptr.astype(np.int32)).cuda(), torch.as_tensor(a.indices.astype(np.int32)).cuda())
+
+
+def _run(X, signs, thr, tail, adj):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    n_subj = X.shape[0]
+    Xf = np.ascontiguousarray(X.reshape(n_subj, -1))
+    indptr, indices = _csr(adj)
+    Xd = torch.as_tensor(Xf).cuda()
+    t_obs, labels, mass, n = K.cbpa_observed(Xd, thr, tail, indptr, indices)
+    h0 = K.cbpa_permute(Xd, torch.as_tensor(signs).cuda(), 0, len(signs), thr, tail, indptr, indices)
+    return t_obs.cpu().numpy(), labels.cpu().numpy(), mass.cpu().numpy(), n, h0.cpu().numpy()
+
+
+@pytest.mark.parametrize("tail", [0, 1, -1])
+def test_cbpa_cfg4_small_permutation_set_bit_exact(cuda_device, tail):
+    pos = syn.sensor_positions(64)
+    adj = ocb.combine_adjacency(100, ocb.delaunay_adjacency(pos))
+    X = syn.make_cbpa_contrast(20, 100, 64)
+    if tail == -1:
+        X = -X
+    signs = syn.make_sign_table(48, 20, seed=42, tail=tail)
+    thr = t_dist.ppf(0.975 if tail == 0 else 0.95, 19)
+    if tail == -1:
+        thr = -thr
+    ref = ocb.permutation_cluster_1samp_test(X, signs, thr, tail, adj)
+    t_obs, labels, mass, n, h0 = _run(X, signs, thr, tail, adj)
+    np.testing.assert_array_equal(t_obs, ref["t_obs"].reshape(-1))       # fp64 bit-exact
+    assert n == len(ref["clusters"])
+    np.testing.assert_array_equal(labels, ref["labels"])
+    np.testing.assert_array_equal(mass, ref["mass_fixed"])
+    np.testing.assert_array_equal(h0, ref["H0_fixed"][1:])
+    h0_full = np.concatenate([[ref["H0_fixed"][0]], h0])
+    np.testing.assert_array_equal(ocb.pvalues_from_h0(mass, h0_full, tail), ref["cluster_pv"])
+
+
+def test_cbpa_production_shape_with_phase_wrap_and_nan(cuda_device):
+    rng = np.random.default_rng(9)
+    n_subj, n_times, n_ch = 13, 36, 11
+    pos = syn.sensor_positions(64)[:n_ch]
+    adj = ocb.add_phase_wraparound(ocb.combine_adjacency(n_times, ocb.delaunay_adjacency(pos)), n_times, n_ch)
+    X = rng.standard_normal((n_subj, n_times, n_ch))
+    X[:, 34:, :4] += 1.0
+    X[:, :2, :4] += 1.0          # cluster that only connects through the wrap-around edges
+    X[:, 10, 3] = np.nan          # all-NaN bin: t is NaN and must never enter a cluster
+    signs = syn.make_sign_table(64, n_subj, seed=1)
+    thr = t_dist.ppf(0.975, n_subj - 1)
+    ref = ocb.permutation_cluster_1samp_test(X, signs, thr, 0, adj)
+    t_obs, labels, mass, n, h0 = _run(X, signs, thr, 0, adj)
+    np.testing.assert_array_equal(np.isnan(t_obs), np.isnan(ref["t_obs"].reshape(-1)))
+    ok = ~np.isnan(t_obs)
+    np.testing.assert_array_equal(t_obs[ok], ref["t_obs"].reshape(-1)[ok])
+    np.testing.assert_array_equal(labels, ref["labels"])
+    np.testing.assert_array_equal(mass, ref["mass_fixed"])
+    np.testing.assert_array_equal(h0, ref["H0_fixed"][1:])
+    wrap_lab = labels.reshape(n_times, n_ch)
+    assert wrap_lab[35, 0] != 0 and wrap_lab[35, 0] == wrap_lab[0, 0]
+
+
+def test_cbpa_sign_symmetry_and_no_cluster(cuda_device):
+    """flipping every subject maps t -> -t and H0 -> -H0; a huge threshold gives H0 = 0."""
+    pos = syn.sensor_positions(64)[:16]
+    adj = ocb.combine_adjacency(12, ocb.delaunay_adjacency(pos))
+    X = syn.make_cbpa_contrast(10, 12, 16, seed=3)
+    signs = syn.make_sign_table(32, 10, seed=5)
+    thr = t_dist.ppf(0.975, 9)
+    _, _, _, _, h0 = _run(X, signs, thr, 0, adj)
+    _, _, _, _, h0_neg = _run(X, (-signs).astype(np.int8), thr, 0, adj)
+    np.testing.assert_array_equal(h0, -h0_neg)
+    t_obs, labels, mass, n, h0_big = _run(X, signs, 1e6, 0, adj)
+    assert n == 0 and np.all(labels == 0) and np.all(h0_big == 0)
+
+
+def test_cbpa_full_cfg4_properties(cuda_device):
+    """BASELINE config 4 at full size (1,024 permutations): checked through properties instead of the
+    (slow) oracle - sharding invariance and agreement of a subsample with the oracle."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    pos = syn.sensor_positions(64)
+    adj = ocb.combine_adjacency(100, ocb.delaunay_adjacency(pos))
+    X = syn.make_cbpa_contrast(20, 100, 64)
+    signs = syn.make_sign_table(1024, 20, seed=42)
+    thr = t_dist.ppf(0.975, 19)
+    indptr, indices = _csr(adj)
+    Xd = torch.as_tensor(np.ascontiguousarray(X.reshape(20, -1))).cuda()
+    sd = torch.as_tensor(signs).cuda()
+    whole = K.cbpa_permute(Xd, sd, 0, 1024, thr, 0, indptr, indices).cpu().numpy()
+    parts = np.concatenate([K.cbpa_permute(Xd, sd, a, a + 128, thr, 0, indptr, indices).cpu().numpy()
+                            for a in range(0, 1024, 128)])
+    np.testing.assert_array_equal(whole, parts)
+    pick = np.array([0, 17, 511, 1023])
+    ref = ocb.permutation_cluster_1samp_test(X, signs[pick], thr, 0, adj)
+    np.testing.assert_array_equal(whole[pick], ref["H0_fixed"][1:])

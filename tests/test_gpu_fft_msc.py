@@ -1,0 +1,157 @@
+"""GPU parity: K1 (segment spectra) and K2w (per-window MSC / jackknife) vs the fp64 oracle
+and the reference-generated golden vectors.  Tolerances: coherence and CI bounds 1e-4
+absolute (north star); spectra 2e-6 of the segment's spectral scale."""
+import numpy as np
+import pytest
+import torch
+from scipy import signal
+from scipy.stats import t as t_dist
+
+from conftest import golden
+from oracle import coherence as oc
+
+pytestmark = pytest.mark.gpu
+
+COH_TOL = 1e-4
+
+
+def _dev(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+@pytest.mark.parametrize("N", [128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("detrend", [0, 1, 2])
+def test_fft_segments_matches_numpy(cuda_device, N, detrend):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(N + detrend)
+    n_ch = 11 if N >= 2048 else 37
+    n = N * 3 + 17
+    x = (rng.standard_normal((n, n_ch)) + 0.7).astype(np.float32)
+    starts = np.array([0, 5, N // 2 + 3, n - N], dtype=np.int64)
+    wins = np.stack([signal.get_window("hann", N), signal.windows.dpss(N, 3, 2)[1]]).astype(np.float32)
+    ref = oc.segment_spectra(x.astype(np.float64), starts, wins.astype(np.float64), detrend)
+    got = K.fft_segments(_dev(x), _dev(starts), _dev(wins), detrend).cpu().numpy()
+    assert got.shape == ref.shape
+    scale = np.sqrt(np.mean(np.abs(ref) ** 2))
+    assert np.max(np.abs(got - ref)) < 2e-6 * scale * np.sqrt(N)
+
+
+def test_fft_segments_band_and_offsets(cuda_device):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(3)
+    N = 2048
+    eeg = rng.standard_normal((3 * N, 64)).astype(np.float32)
+    emg = rng.standard_normal((3 * N, 64)).astype(np.float32)
+    starts = np.arange(0, 2 * N + 1, N // 2, dtype=np.int64)
+    win = signal.get_window("hann", N).astype(np.float32)[None]
+    out = torch.zeros((len(starts), 1, 100, 128), dtype=torch.complex64, device="cuda")
+    K.fft_segments(_dev(eeg), _dev(starts), _dev(win), 1, 1, 100, out=out, ch_offset=0)
+    K.fft_segments(_dev(emg), _dev(starts), _dev(win), 1, 1, 100, out=out, ch_offset=64)
+    ref_e = oc.segment_spectra(eeg, starts, win, 1, 1, 100)
+    ref_m = oc.segment_spectra(emg, starts, win, 1, 1, 100)
+    got = out.cpu().numpy()
+    scale = np.sqrt(np.mean(np.abs(ref_e) ** 2))
+    assert np.max(np.abs(got[..., :64] - ref_e)) < 1e-4 * scale
+    assert np.max(np.abs(got[..., 64:] - ref_m)) < 1e-4 * scale
+
+
+def test_fft_rejects_bad_arguments(cuda_device):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    from multimodal_biosignal_analysis_b200._lib import CmcError
+    x = torch.zeros((4000, 4), device="cuda")
+    st = torch.zeros(1, dtype=torch.int64, device="cuda")
+    with pytest.raises(CmcError):
+        K.fft_segments(x, st, torch.ones((1, 1000), device="cuda"))         # not a power of two
+    with pytest.raises(ValueError):
+        K.fft_segments(x, st + 3000, torch.ones((1, 2048), device="cuda"))   # segment past the end
+    with pytest.raises(TypeError):
+        K.fft_segments(x.cpu(), st, torch.ones((1, 1024), device="cuda"))    # no CPU path
+
+
+def _spectra(x, fs, win_sec, overlap, tapers):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    N, hop = oc.window_params(fs, win_sec, overlap)
+    W = oc.n_windows_msc(x.shape[0], N, hop)
+    starts = np.arange(W, dtype=np.int64) * hop
+    return K.fft_segments(_dev(x, torch.float32), _dev(starts), _dev(tapers, torch.float32), 0)
+
+
+def test_msc_windows_nojk_matches_reference_golden(cuda_device):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    g = golden("msc_nojk.npz")
+    fs = float(g["fs"])
+    tapers, _ = oc.dpss_tapers(256, 3)
+    X = _spectra(g["eeg"], fs, 1.0, 0.5, tapers)
+    Y = _spectra(g["emg"], fs, 1.0, 0.5, tapers)
+    coh, lo, hi, sig = K.msc_windows(X, Y, None, False, 0.0, float(g["IT"]))
+    coh = coh.cpu().numpy()
+    assert lo is None and hi is None
+    assert coh.shape == g["coherence_raw"].shape
+    assert np.max(np.abs(coh - g["coherence_raw"])) < COH_TOL
+    diff = sig.cpu().numpy().astype(bool) != g["coherence_significant"]
+    assert np.all(np.abs(g["coherence_raw"][diff] - float(g["IT"])) <= COH_TOL)
+
+
+def test_msc_windows_jackknife_matches_reference_golden(cuda_device):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    g = golden("msc_jk.npz")
+    fs = float(g["fs"])
+    tapers, _ = oc.dpss_tapers(256, 3)
+    X = _spectra(g["eeg"], fs, 1.0, 0.5, tapers)
+    Y = _spectra(g["emg"], fs, 1.0, 0.5, tapers)
+    mask = _dev(g["window_mask"].astype(np.uint8))
+    t_crit = t_dist.ppf(1 - 0.05 / 2, 4)
+    coh, lo, hi, sig = K.msc_windows(X, Y, mask, True, t_crit, float(g["IT_bonferroni"]))
+    for got, key in ((coh, "coherence_raw"), (lo, "ci_lower"), (hi, "ci_upper")):
+        assert np.max(np.abs(got.cpu().numpy() - g[key])) < COH_TOL, key
+    assert np.all(coh.cpu().numpy()[~g["window_mask"]] == 0)
+    diff = sig.cpu().numpy().astype(bool) != g["coherence_significant"]
+    assert np.all(np.abs(g["coherence_raw"][diff] - float(g["IT_bonferroni"])) <= COH_TOL)
+    # fused EMG-argmax variant against the unfused result
+    c2, l2, h2, arg = K.msc_windows_maxemg(X, Y, mask, True, t_crit, None, False, True)
+    a, b, d = oc.max_over_emg(coh.cpu().numpy(), lo.cpu().numpy(), hi.cpu().numpy())
+    np.testing.assert_array_equal(c2.cpu().numpy(), a)
+    np.testing.assert_array_equal(l2.cpu().numpy(), b)
+    np.testing.assert_array_equal(h2.cpu().numpy(), d)
+    act = g["window_mask"]
+    np.testing.assert_array_equal(arg.cpu().numpy()[act], np.argmax(coh.cpu().numpy(), axis=3)[act])
+
+
+@pytest.mark.parametrize("K_tapers,nw", [(7, 4), (3, 2)])
+def test_msc_windows_other_taper_counts_vs_oracle(cuda_device, K_tapers, nw):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(K_tapers)
+    fs, N = 512.0, 512
+    n = N * 4
+    src = rng.standard_normal(n)
+    eeg = (rng.standard_normal((n, 5)) + src[:, None] * np.linspace(0, 2, 5)).astype(np.float32)
+    emg = (rng.standard_normal((n, 9)) + src[:, None] * np.linspace(2, 0, 9)).astype(np.float32)
+    ref = oc.multitaper_msc(eeg, emg, fs, nw=nw, use_jackknife=True, jackknife_alpha=0.1,
+                            apply_independence_threshold=False)
+    tapers, _ = oc.dpss_tapers(N, nw)
+    assert len(tapers) == K_tapers
+    X = _spectra(eeg, fs, 1.0, 0.5, tapers)
+    Y = _spectra(emg, fs, 1.0, 0.5, tapers)
+    coh, lo, hi, _ = K.msc_windows(X, Y, None, True, t_dist.ppf(0.95, K_tapers - 1), None)
+    assert np.max(np.abs(coh.cpu().numpy() - ref["coherence_raw"])) < COH_TOL
+    assert np.max(np.abs(lo.cpu().numpy() - ref["coherence_ci_lower"])) < COH_TOL
+    assert np.max(np.abs(hi.cpu().numpy() - ref["coherence_ci_upper"])) < COH_TOL
+
+
+def test_msc_identical_and_zero_channels(cuda_device):
+    """identical signals -> C = 1; an all-zero (bad) channel -> C = 0, never NaN."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(5)
+    n, N = 2048, 512
+    eeg = rng.standard_normal((n, 3)).astype(np.float32)
+    emg = eeg.copy()
+    emg[:, 2] = 0.0
+    tapers, _ = oc.dpss_tapers(N, 3)
+    X = _spectra(eeg, 512.0, 1.0, 0.5, tapers)
+    Y = _spectra(emg, 512.0, 1.0, 0.5, tapers)
+    coh, lo, hi, _ = K.msc_windows(X, Y, None, True, 2.776, None)
+    c = coh.cpu().numpy()
+    assert np.all(np.isfinite(c)) and np.all(np.isfinite(lo.cpu().numpy())) and np.all(np.isfinite(hi.cpu().numpy()))
+    assert np.max(np.abs(c[:, :, 0, 0] - 1.0)) < 1e-5
+    assert np.max(np.abs(c[:, :, 1, 1] - 1.0)) < 1e-5
+    assert np.all(c[:, :, :, 2] == 0)
