@@ -25,17 +25,18 @@ void set_error(const char* fmt, ...) {
 
 int ensure_smem_attr(const void* func, size_t bytes) {
     static std::mutex mu;
-    static std::set<std::pair<int, const void*>> done;
+    static std::map<std::pair<int, const void*>, size_t> done;
     int dev = 0;
     int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(mu);
     auto key = std::make_pair(dev, func);
-    if (done.count(key)) return CMC_OK;
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return CMC_OK;
     rc = check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
                     "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
     if (rc) return rc;
-    done.insert(key);
+    done[key] = bytes;
     return CMC_OK;
 }
 

@@ -218,7 +218,7 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
     const int64_t n_perm = p_end - p_begin;
     if (n_perm == 0) return CMC_OK;
     const size_t smem = cbpa_smem_bytes(n_subj, n_tests);
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<false>), 227 * 1024);
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<false>), smem);
     if (rc) return rc;
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
@@ -252,7 +252,7 @@ extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, doubl
     int32_t* rank = root + n_tests;
     long long* h0_tmp = reinterpret_cast<long long*>(rank + n_tests + (n_tests & 1));
     const size_t smem = cbpa_smem_bytes(n_subj, n_tests);
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true>), 227 * 1024);
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true>), smem);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cbpa_kernel<true><<<1, kCbpaThreads, smem, st>>>(X, n_subj, n_tests, nullptr, 1, thr, tail, indptr,

@@ -56,8 +56,8 @@ def test_cbpa_production_shape_with_phase_wrap_and_nan(cuda_device):
     pos = syn.sensor_positions(64)[:n_ch]
     adj = ocb.add_phase_wraparound(ocb.combine_adjacency(n_times, ocb.delaunay_adjacency(pos)), n_times, n_ch)
     X = rng.standard_normal((n_subj, n_times, n_ch))
-    X[:, 34:, :4] += 1.0
-    X[:, :2, :4] += 1.0          # cluster that only connects through the wrap-around edges
+    X[:, 34:, :4] += 4.0
+    X[:, :2, :4] += 4.0          # cluster that only connects through the wrap-around edges
     X[:, 10, 3] = np.nan          # all-NaN bin: t is NaN and must never enter a cluster
     signs = syn.make_sign_table(64, n_subj, seed=1)
     thr = t_dist.ppf(0.975, n_subj - 1)

@@ -1,0 +1,138 @@
+"""GPU parity: K2 (tcgen05 pooled CSD -> MSC) and K3 (shift-surrogate null) vs the fp64 oracle.
+Coherence tolerance 1e-4 absolute (north star); exceedance counts must lie inside the band obtained by
+moving the oracle's comparison by +-1e-5 (counts are exact whenever no surrogate falls that close)."""
+import numpy as np
+import pytest
+import torch
+from scipy import signal
+
+from oracle import coherence as oc
+from oracle import surrogate as osur
+from multimodal_biosignal_analysis_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+COH_TOL = 1e-4
+
+
+def _dev(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def _welch_spectra(eeg, emg, starts, N, lo, hi):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    win = signal.get_window("hann", N).astype(np.float32)[None]
+    X = K.fft_segments(_dev(eeg), _dev(starts), _dev(win), 1, lo, hi)[:, 0]
+    Y = K.fft_segments(_dev(emg), _dev(starts), _dev(win), 1, lo, hi)[:, 0]
+    return X, Y
+
+
+def _oracle_spectra(eeg, emg, starts, N, lo, hi):
+    win = signal.get_window("hann", N)[None]
+    X = oc.segment_spectra(eeg, starts, win, 1, lo, hi)[:, 0]
+    Y = oc.segment_spectra(emg, starts, win, 1, lo, hi)[:, 0]
+    return X, Y
+
+
+@pytest.mark.parametrize("n_epochs,ne,nm", [(6, 64, 64), (1, 11, 64), (3, 3, 70), (2, 70, 5), (5, 1, 1)])
+def test_pooled_welch_coherence_matches_oracle(cuda_device, n_epochs, ne, nm):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    N, hop, ep = 512, 256, 2048
+    eeg, emg = syn.make_epochs(n_epochs, ep, ne, nm, seed=100 + n_epochs)
+    starts = syn.epoch_segment_starts(n_epochs, ep, N, hop)
+    X, Y = _welch_spectra(eeg, emg, starts, N, 1, 100)
+    res = K.csd_msc(X, Y, want_sxy=True)
+    Xo, Yo = _oracle_spectra(eeg, emg, starts, N, 1, 100)
+    coh, sxx, syy, sxy = oc.msc_from_spectra(Xo, Yo)
+    assert np.max(np.abs(res.coh.cpu().numpy() - coh)) < COH_TOL
+    np.testing.assert_allclose(res.sxx.cpu().numpy(), sxx, rtol=2e-5)
+    np.testing.assert_allclose(res.syy.cpu().numpy(), syy, rtol=2e-5)
+    scale = np.sqrt(sxx[:, :, None] * syy[:, None, :])
+    assert np.max(np.abs(res.sxy.cpu().numpy() - sxy) / scale) < 1e-4
+
+
+def test_pooled_coherence_tighter_than_single_tf32(cuda_device):
+    """The 3xTF32 split must deliver far better than plain TF32 (~5e-5): check 2e-5 everywhere."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    N, hop, ep = 512, 256, 2048
+    eeg, emg = syn.make_epochs(8, ep, 64, 64, seed=7, )
+    emg[:, 0] = eeg[:, 0]                      # identical pair -> C = 1
+    starts = syn.epoch_segment_starts(8, ep, N, hop)
+    X, Y = _welch_spectra(eeg, emg, starts, N, 1, 100)
+    res = K.csd_msc(X, Y)
+    Xo, Yo = _oracle_spectra(eeg, emg, starts, N, 1, 100)
+    coh = oc.msc_from_spectra(Xo, Yo)[0]
+    got = res.coh.cpu().numpy()
+    assert np.max(np.abs(got - coh)) < 2e-5
+    assert np.max(np.abs(got[:, 0, 0] - 1.0)) < 2e-5
+
+
+def test_pooled_matches_scipy_coherence_cfg1(cuda_device):
+    """BASELINE config 1: one EEG x one bipolar EMG channel, 60 s @ 2048 Hz, nperseg 1024."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    eeg, emg = syn.make_recording(122880, 1, 2, seed=1)
+    bip = (emg[:, :1] - emg[:, 1:2]).astype(np.float32)
+    f, ref = signal.coherence(eeg[:, 0].astype(np.float64), bip[:, 0].astype(np.float64), fs=2048.0, nperseg=1024)
+    starts = oc.welch_segments(122880, 1024)
+    assert len(starts) == 239
+    X, Y = _welch_spectra(eeg, bip, starts, 1024, 0, 512)
+    got = K.csd_msc(X, Y).coh.cpu().numpy()[:, 0, 0]
+    assert np.max(np.abs(got - ref)) < COH_TOL
+
+
+def test_shift_surrogates_match_oracle(cuda_device):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    N, hop, ep, n_epochs = 512, 256, 2048, 6
+    eeg, emg = syn.make_epochs(n_epochs, ep, 20, 70, seed=11)
+    starts = syn.epoch_segment_starts(n_epochs, ep, N, hop)
+    L = len(starts)
+    X, Y = _welch_spectra(eeg, emg, starts, N, 1, 40)
+    res = K.csd_msc(X, Y)
+    rng = np.random.default_rng(3)
+    n_surr = 60
+    shifts = rng.integers(1, L, n_surr).astype(np.int32)
+    exceed, max_stat = K.surrogate_null(res, K.SURR_SHIFT, 0, n_surr, shifts=_dev(shifts))
+    Xo, Yo = _oracle_spectra(eeg, emg, starts, N, 1, 40)
+    Xw, _ = osur.whiten(Xo)
+    Yw, _ = osur.whiten(Yo)
+    cs = osur.surrogate_coherence(Xw, Yw, "shift", np.arange(n_surr), shifts=shifts)
+    coh_obs = res.coh.cpu().numpy().astype(np.float64)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+1e-5)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-1e-5)
+    got = exceed.cpu().numpy().astype(np.int64)
+    assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
+    assert np.mean(lo_cnt == hi_cnt) > 0.99                  # the band is tight almost everywhere
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 1e-4
+    # sharding invariance: two halves accumulate to the same counts
+    e2, m_a = K.surrogate_null(res, K.SURR_SHIFT, 0, 30, shifts=_dev(shifts[:30]))
+    e2, m_b = K.surrogate_null(res, K.SURR_SHIFT, 30, 60, shifts=_dev(shifts[30:]), exceed=e2)
+    np.testing.assert_array_equal(e2.cpu().numpy(), exceed.cpu().numpy())
+    np.testing.assert_array_equal(torch.cat([m_a, m_b]).cpu().numpy(), max_stat.cpu().numpy())
+
+
+def test_shift_surrogates_multitaper_groups(cuda_device):
+    """windows x tapers pooling: whole windows rotate, taper index stays aligned (group = K)."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(5)
+    N, W, Kt = 256, 9, 5
+    eeg, emg = syn.make_recording(N * (W + 1) // 2 + N, 7, 6, seed=21)
+    starts = (np.arange(W) * (N // 2)).astype(np.int64)
+    tapers, _ = oc.dpss_tapers(N, 3)
+    X = K.fft_segments(_dev(eeg), _dev(starts), _dev(tapers, torch.float32), 0, 2, 60)
+    Y = K.fft_segments(_dev(emg), _dev(starts), _dev(tapers, torch.float32), 0, 2, 60)
+    F = X.shape[2]
+    Xp, Yp = X.reshape(W * Kt, F, 7), Y.reshape(W * Kt, F, 6)
+    res = K.csd_msc(Xp, Yp)
+    Xo = oc.segment_spectra(eeg, starts, tapers, 0, 2, 60).reshape(W * Kt, F, 7)
+    Yo = oc.segment_spectra(emg, starts, tapers, 0, 2, 60).reshape(W * Kt, F, 6)
+    assert np.max(np.abs(res.coh.cpu().numpy() - oc.msc_from_spectra(Xo, Yo)[0])) < COH_TOL
+    shifts = rng.integers(1, W, 25).astype(np.int32)
+    exceed, max_stat = K.surrogate_null(res, K.SURR_SHIFT, 0, 25, shifts=_dev(shifts), group=Kt)
+    Xw, _ = osur.whiten(Xo)
+    Yw, _ = osur.whiten(Yo)
+    cs = osur.surrogate_coherence(Xw, Yw, "shift", np.arange(25), shifts=shifts, group=Kt)
+    coh_obs = res.coh.cpu().numpy().astype(np.float64)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+1e-5)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-1e-5)
+    got = exceed.cpu().numpy().astype(np.int64)
+    assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 1e-4
