@@ -78,7 +78,7 @@ template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                 const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-                const CsdParams p) {
+                const __grid_constant__ CUtensorMap mBodd, const CsdParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -123,7 +123,11 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
             for (long long t = t0; t < t1; ++t) {
                 const TileCoord c = decode_tile(t, p);
                 if (p.shift_mult && p.shift_mult[c.sh] == 0) continue;
-                const int off = p.shift_off ? p.shift_off[c.sh] : 0;
+                // TMA needs a 16-byte aligned box start: offsets = 2 (mod 4) floats read the copy of
+                // the B rows that is pre-shifted by one complex element
+                int off = p.shift_off ? p.shift_off[c.sh] : 0;
+                const bool odd = (off & 2) != 0;
+                off -= odd ? 2 : 0;
                 const int arow = (c.f * p.MT + c.mt) * kTileM;
                 const int brow = (c.f * p.NT + c.nt) * kTileN;
                 for (int v = 0; v < n_v; ++v) {
@@ -131,7 +135,7 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&bars->full[stage], kABytes + kBBytes);
                     tma_load_2d(sA + stage * kABytes, term == 2 ? &mAlo : &mAhi, &bars->full[stage], kb * kKBlock, arow);
-                    tma_load_2d(sB + stage * kBBytes, term == 1 ? &mBlo : &mBhi, &bars->full[stage],
+                    tma_load_2d(sB + stage * kBBytes, odd ? &mBodd : (term == 1 ? &mBlo : &mBhi), &bars->full[stage],
                                 off + kb * kKBlock, brow);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -282,12 +286,13 @@ power_kernel(const float2* __restrict__ S, int L, int F, int C, int64_t ld, floa
 //   MODE 0 (A operand): rows_per_f = MT * 128; row (mt*128 + r): r < 64 -> channel mt*64 + r (Xh),
 //                       r >= 64 -> i * Xh of channel mt*64 + r - 64; columns k >= 2L are zero.
 //   MODE 1 (B operand): rows_per_f = NT * 64; row = channel; columns [0,2L) and [2L,4L) both hold Yh,
-//                       columns >= 4L are zero.
+//                       columns >= 4L are zero; l_shift = 1 writes the same rows advanced by one
+//                       complex element (16-byte aligned access to odd segment shifts).
 // grid (F, rows_per_f / 32, ceil(row_len / 64)); block (32, 8)
 template <int MODE>
 __global__ void __launch_bounds__(256)
 pack_kernel(const float2* __restrict__ S, int L, int F, int C, int64_t ld, const float* __restrict__ P,
-            int rows_per_f, int row_len, float* __restrict__ hi, float* __restrict__ lo) {
+            int rows_per_f, int row_len, int l_shift, float* __restrict__ hi, float* __restrict__ lo) {
     __shared__ float2 tile[32][33];       // [l][row]
     const int f = blockIdx.x, r0 = blockIdx.y * 32, l0 = blockIdx.z * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -310,7 +315,7 @@ pack_kernel(const float2* __restrict__ S, int L, int F, int C, int64_t ld, const
         }
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-            const int lv = l0 + ty + 8 * n;        // virtual l (column pair index)
+            const int lv = l0 + ty + 8 * n + l_shift;   // virtual l (column pair index)
             int l = -1;
             if (lv < L) l = lv;
             else if (MODE == 1 && lv < 2 * L) l = lv - L;
@@ -344,7 +349,7 @@ pack_kernel(const float2* __restrict__ S, int L, int F, int C, int64_t ld, const
 struct CsdLayout {
     int L, F, Ne, Nm, MT, NT, KP, LB;
     int64_t a_elems, b_elems;          // floats per plane
-    int64_t off_pxx, off_pyy, off_ahi, off_alo, off_bhi, off_blo, total;
+    int64_t off_pxx, off_pyy, off_ahi, off_alo, off_bhi, off_blo, off_bodd, total;
 };
 
 static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -365,6 +370,7 @@ static CsdLayout csd_layout(int L, int F, int Ne, int Nm) {
     y.off_alo = o; o = align_up(o + y.a_elems * 4, 1024);
     y.off_bhi = o; o = align_up(o + y.b_elems * 4, 1024);
     y.off_blo = o; o = align_up(o + y.b_elems * 4, 1024);
+    y.off_bodd = o; o = align_up(o + y.b_elems * 4, 1024);
     y.total = o;
     return y;
 }
@@ -418,12 +424,13 @@ static size_t gemm_smem_bytes(int epi) {
 
 template <int EPI>
 static int launch_gemm(const CsdLayout& y, unsigned char* ws, CsdParams p, cudaStream_t st) {
-    CUtensorMap mAhi, mAlo, mBhi, mBlo;
+    CUtensorMap mAhi, mAlo, mBhi, mBlo, mBodd;
     int rc;
     if ((rc = make_operand_map(&mAhi, reinterpret_cast<float*>(ws + y.off_ahi), y.KP, (int64_t)y.F * y.MT * kTileM, kTileM))) return rc;
     if ((rc = make_operand_map(&mAlo, reinterpret_cast<float*>(ws + y.off_alo), y.KP, (int64_t)y.F * y.MT * kTileM, kTileM))) return rc;
     if ((rc = make_operand_map(&mBhi, reinterpret_cast<float*>(ws + y.off_bhi), y.LB, (int64_t)y.F * y.NT * kTileN, kTileN))) return rc;
     if ((rc = make_operand_map(&mBlo, reinterpret_cast<float*>(ws + y.off_blo), y.LB, (int64_t)y.F * y.NT * kTileN, kTileN))) return rc;
+    if ((rc = make_operand_map(&mBodd, reinterpret_cast<float*>(ws + y.off_bodd), y.LB, (int64_t)y.F * y.NT * kTileN, kTileN))) return rc;
     const size_t smem = gemm_smem_bytes(EPI);
     rc = ensure_smem_attr(reinterpret_cast<const void*>(csd_gemm_kernel<EPI>), smem);
     if (rc) return rc;
@@ -431,7 +438,7 @@ static int launch_gemm(const CsdLayout& y, unsigned char* ws, CsdParams p, cudaS
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long grid = p.total_tiles < sms ? p.total_tiles : sms;
-    csd_gemm_kernel<EPI><<<(unsigned)grid, kGemmThreads, smem, st>>>(mAhi, mAlo, mBhi, mBlo, p);
+    csd_gemm_kernel<EPI><<<(unsigned)grid, kGemmThreads, smem, st>>>(mAhi, mAlo, mBhi, mBlo, mBodd, p);
     CMC_CHECK_LAUNCH("csd_gemm_kernel");
     return CMC_OK;
 }
@@ -490,13 +497,16 @@ extern "C" int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne,
     power_kernel<<<dim3(F, (Nm + 31) / 32), dim3(32, 8), 0, st>>>(Yc, L, F, Nm, ldy, pyy);
     CMC_CHECK_LAUNCH("power_kernel(Y)");
     pack_kernel<0><<<dim3(F, y.MT * kTileM / 32, (y.KP + 63) / 64), dim3(32, 8), 0, st>>>(
-        Xc, L, F, Ne, ldx, pxx, y.MT * kTileM, y.KP, reinterpret_cast<float*>(w + y.off_ahi),
+        Xc, L, F, Ne, ldx, pxx, y.MT * kTileM, y.KP, 0, reinterpret_cast<float*>(w + y.off_ahi),
         reinterpret_cast<float*>(w + y.off_alo));
     CMC_CHECK_LAUNCH("pack_kernel<A>");
     pack_kernel<1><<<dim3(F, y.NT * kTileN / 32, (y.LB + 63) / 64), dim3(32, 8), 0, st>>>(
-        Yc, L, F, Nm, ldy, pyy, y.NT * kTileN, y.LB, reinterpret_cast<float*>(w + y.off_bhi),
+        Yc, L, F, Nm, ldy, pyy, y.NT * kTileN, y.LB, 0, reinterpret_cast<float*>(w + y.off_bhi),
         reinterpret_cast<float*>(w + y.off_blo));
     CMC_CHECK_LAUNCH("pack_kernel<B>");
+    pack_kernel<1><<<dim3(F, y.NT * kTileN / 32, (y.LB + 63) / 64), dim3(32, 8), 0, st>>>(
+        Yc, L, F, Nm, ldy, pyy, y.NT * kTileN, y.LB, 1, reinterpret_cast<float*>(w + y.off_bodd), nullptr);
+    CMC_CHECK_LAUNCH("pack_kernel<B odd>");
     if (sxx) {
         int rc = check_cuda(cudaMemcpyAsync(sxx, pxx, sizeof(float) * F * Ne, cudaMemcpyDeviceToDevice, st), "copy sxx");
         if (rc) return rc;
