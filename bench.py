@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the cortico-muscular coherence hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+Headline metric (BASELINE.json): EEG x EMG coherence pair-spectra/s on config 2 - one subject-
+condition = 64-ch EEG x 64-ch HD-EMG, 30 task epochs of 4 s at 2048 Hz, Welch segments of 2048
+samples / hop 1024 (L = 210), 1-100 Hz band (F = 100) -> 4,096 pair-spectra per step.
+One step = K1 (detrend + hann + rFFT of every segment of all 128 channels) + K2 (power, pack,
+tcgen05 CSD -> MSC).  Every rank processes its own subject-condition per step (weak scaling, no
+data-path collective).  ``value`` has the inputs resident in HBM; ``e2e`` goes through the public
+Python API with pinned host buffers (H2D of the recording and D2H of the coherence inside the
+timed region).  The surrogate-null and CBPA stages are timed separately and reported under
+``stages`` (they shard a fixed total over the ranks: strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 2048.0
+N_EPOCHS, EPOCH = 30, 8192
+NPERSEG, HOP = 2048, 1024
+BAND = (1.0, 100.0)
+NE = NM = 64
+N_ROTATE = 4                 # distinct resident recordings rotated per step (4 x 126 MB > 126 MB L2)
+N_SURR = 1000                # config 3
+N_PERM_TOTAL = 10000         # config 5 permutation count (sharded over ranks)
+CBPA_SHAPE = (20, 100, 64)   # config 4
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
+                              ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_fft_chunk(args):
+    from oracle import coherence as oc
+    x, starts, win, lo, hi = args
+    return oc.segment_spectra(x, starts, win, 1, lo, hi)[:, 0]
+
+
+def _cpu_csd_chunk(args):
+    from oracle import coherence as oc
+    X, Y = args
+    return oc.msc_from_spectra(X, Y)[0]
+
+
+def cpu_pooled_coherence(eeg, emg, starts, pool, n_workers):
+    """Oracle (numpy fp64) Welch all-pairs coherence, parallel over segments (FFT) and frequency
+    chunks (CSD) with ``n_workers`` processes."""
+    from scipy import signal
+    win = signal.get_window("hann", NPERSEG)[None]
+    freqs = np.fft.rfftfreq(NPERSEG, 1 / FS)
+    sel = np.flatnonzero((freqs >= BAND[0]) & (freqs <= BAND[1]))
+    lo, hi = int(sel[0]), int(sel[-1])
+    chunks = np.array_split(starts, min(n_workers, len(starts)))
+    jobs = [(eeg, c, win, lo, hi) for c in chunks] + [(emg, c, win, lo, hi) for c in chunks]
+    parts = pool.map(_cpu_fft_chunk, jobs) if pool else [_cpu_fft_chunk(j) for j in jobs]
+    X = np.concatenate(parts[:len(chunks)])
+    Y = np.concatenate(parts[len(chunks):])
+    fch = np.array_split(np.arange(X.shape[1]), min(n_workers, X.shape[1]))
+    jobs = [(X[:, f], Y[:, f]) for f in fch]
+    cs = pool.map(_cpu_csd_chunk, jobs) if pool else [_cpu_csd_chunk(j) for j in jobs]
+    return np.concatenate(cs)
+
+
+def run_cpu_reference(steps, warmup, sample_epochs=N_EPOCHS):
+    """Times the oracle port on the host cores; returns (pair-spectra/s, ms/step, cores, sample)."""
+    import multiprocessing as mp
+    from multimodal_biosignal_analysis_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    eeg, emg = syn.make_epochs(sample_epochs, EPOCH, NE, NM, seed=20260102)
+    eeg, emg = eeg.astype(np.float64), emg.astype(np.float64)
+    starts = syn.epoch_segment_starts(sample_epochs, EPOCH, NPERSEG, HOP)
+    ctx = mp.get_context("fork")
+    pool = ctx.Pool(cores) if cores > 1 else None
+    try:
+        for _ in range(warmup):
+            cpu_pooled_coherence(eeg, emg, starts, pool, cores)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_pooled_coherence(eeg, emg, starts, pool, cores)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    finally:
+        if pool:
+            pool.terminate()
+    # cost is linear in the number of segments: scale a sub-sampled run to the full L = 210
+    scale = N_EPOCHS / sample_epochs
+    ms = dt * 1e3 * scale
+    sample = (f"oracle port (numpy fp64 Welch all-pairs) on {sample_epochs}/{N_EPOCHS} epochs of config 2, "
+              f"{cores} worker processes" + (", time scaled linearly to 30 epochs" if scale != 1 else ""))
+    return NE * NM / (ms / 1e3), ms, cores, sample
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    val, ms, cores, sample = run_cpu_reference(steps, warmup)
+    line = {
+        "impl": "reference", "metric": "pair_spectra_per_s", "value": val, "unit": "pair-spectra/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": val, "unit": "pair-spectra/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pair-spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {"workload": "BASELINE config 2: 64x64 all-pairs Welch MSC, 30 epochs x 4 s @ 2048 Hz, nperseg 2048 "
+                        "hop 1024 (L=210 segments), 1-100 Hz (F=100) = 4096 pair-spectra per subject-condition "
+                        "per step per GPU",
+            "l2_policy": f"inputs larger than L2: {N_ROTATE} resident recordings (126 MB each) rotated per step",
+            "parallelism": "one subject-condition per rank per step, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from scipy import signal
+    from scipy.stats import t as t_dist
+    from multimodal_biosignal_analysis_b200 import _lib, kernels as K, synthetic as syn
+    from multimodal_biosignal_analysis_b200 import signal_features as sf
+    from multimodal_biosignal_analysis_b200 import data_surrogation as dsur
+    from multimodal_biosignal_analysis_b200 import cbpa as cb
+    from multimodal_biosignal_analysis_b200 import dist as cdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident synthetic inputs (different per rank and per rotation slot) ----
+    starts_h = syn.epoch_segment_starts(N_EPOCHS, EPOCH, NPERSEG, HOP)
+    starts = torch.from_numpy(starts_h).to(dev)
+    win = torch.from_numpy(signal.get_window("hann", NPERSEG).astype(np.float32)[None]).to(dev)
+    freqs = np.fft.rfftfreq(NPERSEG, 1 / FS)
+    sel = np.flatnonzero((freqs >= BAND[0]) & (freqs <= BAND[1]))
+    lo, hi = int(sel[0]), int(sel[-1])
+    F = hi - lo + 1
+    L = len(starts_h)
+    host_sets, dev_sets = [], []
+    for r in range(N_ROTATE):
+        eeg, emg = syn.make_epochs(N_EPOCHS, EPOCH, NE, NM, seed=20260102 + 97 * rank + r)
+        host_sets.append((eeg, emg))
+        dev_sets.append((torch.from_numpy(eeg).to(dev), torch.from_numpy(emg).to(dev)))
+    spec = torch.empty((L, 1, F, NE + NM), dtype=torch.complex64, device=dev)
+
+    def step(i):
+        eeg_d, emg_d = dev_sets[i % N_ROTATE]
+        K.fft_segments(eeg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=spec, ch_offset=0)
+        K.fft_segments(emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=spec, ch_offset=NE)
+        X = spec[:, 0, :, :NE]
+        Y = spec[:, 0, :, NE:]
+        return K.csd_msc(X, Y)
+
+    for i in range(warmup):
+        res = step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    launches0 = _lib.launch_count()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for i in range(steps):
+        eeg_d, emg_d = dev_sets[i % N_ROTATE]
+        ev[i][0].record()
+        K.fft_segments(eeg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=spec, ch_offset=0)
+        K.fft_segments(emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=spec, ch_offset=NE)
+        ev[i][1].record()
+        res = K.csd_msc(spec[:, 0, :, :NE], spec[:, 0, :, NE:])
+        ev[i][2].record()
+    t_end.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / steps
+    value = NE * NM * world / (ms_per_step / 1e3)
+    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev])) / 2.0      # per K1 launch
+    k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    n_samples = N_EPOCHS * EPOCH
+    k1_bytes = n_samples * NE * 4 + L * F * NE * 8                              # per launch (one modality)
+    hbm, bf16, peak_src = peaks()
+    k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API: pinned host buffers in, numpy coherence out ----
+    pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in host_sets]
+
+    def e2e_step(i):
+        eeg_h, emg_h = pinned[i % N_ROTATE]
+        pc = sf.welch_magnitude_squared_coherence(eeg_h, emg_h, FS, nperseg=NPERSEG, freq_band=BAND,
+                                                  segment_starts=starts_h)
+        return pc.coherence                                                  # D2H, synchronises
+
+    for i in range(2):
+        coh_e2e = e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        coh_e2e = e2e_step(i)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+    e2e = {"value": NE * NM * world / (e2e_ms / 1e3), "unit": "pair-spectra/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(n_samples * (NE + NM) * 4), "d2h_bytes_per_step": int(F * NE * NM * 4),
+           "api": "signal_features.welch_magnitude_squared_coherence(...).coherence"}
+
+    # ---- stage: surrogate null (config 3: 1,000 circular-shift surrogates on the cached spectra) ----
+    stages = {}
+    pooled = sf.PooledCoherence(res, freqs[lo:hi + 1], 1, False)
+    shifts = np.random.default_rng(3).integers(1, L, N_SURR).astype(np.int32)
+    for _ in range(2):
+        dsur.circular_shift_surrogate_null(pooled, N_SURR, shifts=shifts)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_rep = 3
+    e0.record()
+    for _ in range(n_rep):
+        null = dsur.circular_shift_surrogate_null(pooled, N_SURR, shifts=shifts)
+    e1.record()
+    barrier()
+    surr_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
+    n_distinct = len(np.unique(shifts))
+    flop = 2.0 * 128 * 64 * 2 * L * F * n_distinct / world              # executed TF32 flop per rank
+    stages["surrogate_null"] = {
+        "metric": "surrogates_per_s", "value": N_SURR / (surr_ms / 1e3), "unit": "surrogates/s",
+        "ms": surr_ms, "scaling": "strong",
+        "config": f"config 3: {N_SURR} circular-shift surrogates of one 64x64xF=100 subject-condition "
+                  f"({n_distinct} distinct shifts of L={L}, each one TF32 tcgen05 CSD pass; includes D2H of counts)",
+        "roofline": {"bound": "tensor", "achieved": flop / (surr_ms * 1e-3) / 1e12, "peak": bf16 / 2,
+                     "unit": "TFLOP/s", "frac": flop / (surr_ms * 1e-3) / 1e12 / (bf16 / 2),
+                     "note": "executed TF32 flop of the distinct-shift passes; TF32 peak taken as half the "
+                             "measured dense bf16 figure"},
+    }
+
+    # ---- stage: CBPA permutations (config 4 geometry, config 5 count sharded over the ranks) ----
+    from multimodal_biosignal_analysis_b200.cbpa import combine_adjacency, find_ch_adjacency_from_positions
+    adj = combine_adjacency(CBPA_SHAPE[1], find_ch_adjacency_from_positions(syn.sensor_positions(CBPA_SHAPE[2])))
+    adj.sort_indices()
+    Xc = syn.make_cbpa_contrast(*CBPA_SHAPE)
+    signs = syn.make_sign_table(N_PERM_TOTAL, CBPA_SHAPE[0], seed=42)
+    thr = float(t_dist.ppf(0.975, CBPA_SHAPE[0] - 1))
+    Xd = torch.from_numpy(np.ascontiguousarray(Xc.reshape(CBPA_SHAPE[0], -1))).to(dev)
+    indptr = torch.from_numpy(adj.indptr.astype(np.int32)).to(dev)
+    indices = torch.from_numpy(adj.indices.astype(np.int32)).to(dev)
+    sd = torch.from_numpy(signs).to(dev)
+    pb, pe = cdist.shard_range(N_PERM_TOTAL, rank, world)
+    for _ in range(2):
+        K.cbpa_permute(Xd, sd, pb, pe, thr, 0, indptr, indices)
+    barrier()
+    e0.record()
+    for _ in range(n_rep):
+        h0 = cdist.all_gather_ranges(K.cbpa_permute(Xd, sd, pb, pe, thr, 0, indptr, indices), N_PERM_TOTAL)
+    e1.record()
+    barrier()
+    cbpa_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
+    perm_bytes = CBPA_SHAPE[0] * CBPA_SHAPE[1] * CBPA_SHAPE[2] * 8 + CBPA_SHAPE[0] + 8
+    cbpa_gbs = perm_bytes * (pe - pb) / (cbpa_ms * 1e-3) / 1e9
+    stages["cbpa"] = {
+        "metric": "cbpa_permutations_per_s", "value": N_PERM_TOTAL / (cbpa_ms / 1e3), "unit": "permutations/s",
+        "ms": cbpa_ms, "scaling": "strong",
+        "config": f"config 4 geometry (20 subj x 100 x 64 = 6400 tests, {adj.nnz} nnz adjacency), "
+                  f"{N_PERM_TOTAL} sign-flip permutations sharded over {world} rank(s), H0 all-gathered",
+        "roofline": {"bound": "hbm", "achieved": cbpa_gbs, "peak": hbm, "unit": "GB/s", "frac": cbpa_gbs / hbm,
+                     "note": "algorithmic bytes = X (fp64) + sign row + H0 per permutation; X is L2 resident"},
+    }
+
+    # ---- CPU baseline (rank 0, N = 1): oracle port on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, ms, cores, sample = run_cpu_reference(steps=2, warmup=1, sample_epochs=10)
+        cpu = {"value": v, "unit": "pair-spectra/s", "cores": cores, "kind": "port", "sample": sample,
+               "ms_per_step": ms}
+
+    if rank == 0:
+        line = {
+            "metric": "pair_spectra_per_s", "value": value, "unit": "pair-spectra/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT), tf32x3 -> f32 accumulate (CSD)",
+            "data": "synthetic", "config": workload_config(),
+            "roofline": {"bound": "hbm", "kernel": "fft_segments_kernel<1024,8> (K1, one launch per modality)",
+                         "achieved": k1_gbs, "peak": hbm, "unit": "GB/s", "frac": k1_gbs / hbm,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": k1_ms,
+                         "k2_ms_per_step": k2_ms, "k1_share_of_step": 2 * k1_ms / (2 * k1_ms + k2_ms)},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "stages": stages,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,376 @@
+"""Drop-in for the cluster-based permutation analysis of the reference's ``src/pipeline/cbpa.py``.
+
+The reference delegates the arithmetic to ``mne.stats.spatio_temporal_cluster_1samp_test`` /
+``permutation_cluster_1samp_test`` (cbpa.py:1027-1042).  This module keeps ``CBPAConfig``,
+``run_cbpa`` / ``run_batch``, the adjacency builders and the result-dict contract
+(cbpa.py:1051-1056), and provides the two MNE-signature functions on top of the sm_100a CBPA
+kernels (``cmc_cbpa_observed`` / ``cmc_cbpa_permute``).  No MNE, no CPU fallback.
+
+Determinism: sign flips come from a host-side table (``make_sign_table``; pass ``signs=`` to supply
+your own), never from a library RNG stream; permutations shard across ranks by global index
+(``dist.shard_range``) and only the H0 slices are gathered.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Literal, Optional
+
+import numpy as np
+import torch
+from scipy import sparse
+from scipy.stats import t as t_dist
+
+from . import dist as cdist
+from . import file_management as filemgmt
+from . import kernels as K
+from .channel_layout import EEG_CHANNEL_IND_DICT
+
+EEG_CHANNELS: list[str] = list(EEG_CHANNEL_IND_DICT.keys())
+EEG_SFREQ: float = 2048
+
+# cbpa.py:36-43 - must match the feature-extraction workflow
+CMC_EEG_CHANNEL_SUBSET: list[str] = ["C5", "C3", "C1", "FC5", "FC3", "FC1", "F3", "CP5", "CP3", "CP1", "P3"]
+CMC_CHANNEL_FILE_SUFFIX: str = f"Channels_{'_'.join(CMC_EEG_CHANNEL_SUBSET)}"
+
+
+@dataclass
+class CBPAConfig:
+    """One CBPA run - same fields and defaults as the reference dataclass (cbpa.py:50-193)."""
+    # Feature
+    modality: Literal["PSD", "CMC"] = "PSD"
+    modality_file_id: str = "eeg"
+    freq_band: str = "alpha"
+    channels: Optional[list[str]] = None
+    # Contrast
+    condition_column: str = "Category or Silence"
+    condition_A: str = "Happy"
+    condition_B: str = "Silence"
+    # Segmentation
+    n_within_trial_segs: int = 1
+    # Subject subset
+    exclude_subjects: list[int] = None
+    # CBPA
+    alpha_cluster_forming: float = 0.05
+    n_permutations: int = 1000
+    tail: Literal[-1, 0, 1] = 0
+    use_spatio_temporal: bool = True
+    n_jobs: int = -1
+    seed: int = 42
+    # I/O
+    data_root: Path = field(default_factory=lambda: Path().resolve().parent)
+    psd_time_window_sec: float = 0.25
+    cmc_time_window_sec: float = 2.0
+    overlap_ratio: float = .5
+    psd_is_log_scaled: bool = True
+    output_dir: Path = field(
+        default_factory=lambda: Path().resolve().parent / "output" / "statistics_post_hoc_testing")
+    hypothesis_label: str = "cbpa_run"
+    save_plots: bool = True
+    show_plots: bool = False
+    # Phase normalisation (CMC only)
+    use_phase_normalization: bool = False
+    n_phase_bins: int = 36
+    min_samples_per_cycle: int = 2
+    min_cycles_per_condition: int = 3
+    # Plot options (consumed by the reference's plotting code only)
+    show_target_sine: bool | None = None
+    target_sine_min_pct_mvc: float = 7.5
+    target_sine_max_pct_mvc: float = 22.5
+    target_sine_frequency_hz: float = 0.1
+    include_dynamometer_force: bool = True
+    phase_start_offset_sec: float | None = None
+    force_phase_start_offset_sec: float | None = None
+    include_suptitle: bool = False
+    use_stretched_window_timestamps: bool = False
+
+
+# ----------------------------------------------------------------------------- adjacency (host, scipy.sparse)
+def combine_adjacency(n_times: int, spatial_adj) -> sparse.csr_matrix:
+    """Lattice-in-time x spatial adjacency with index ``t * n_ch + ch`` (what
+    ``mne.stats.combine_adjacency(n_times, spatial_adj)`` returns at cbpa.py:237): nodes are
+    neighbours when they differ in exactly one of (time by one step, channel by a spatial edge);
+    the diagonal is set."""
+    sp = sparse.coo_matrix(spatial_adj)
+    n_ch = sp.shape[0]
+    off = sp.row != sp.col
+    srow, scol = sp.row[off].astype(np.int64), sp.col[off].astype(np.int64)
+    t = np.arange(n_times, dtype=np.int64)
+    ch = np.arange(n_ch, dtype=np.int64)
+    lower = (t[:-1, None] * n_ch + ch[None, :]).ravel()
+    n = n_times * n_ch
+    rows = np.concatenate([(t[:, None] * n_ch + srow[None, :]).ravel(), lower, lower + n_ch, np.arange(n)])
+    cols = np.concatenate([(t[:, None] * n_ch + scol[None, :]).ravel(), lower + n_ch, lower, np.arange(n)])
+    m = sparse.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(n, n)).tocsr()
+    m.data[:] = 1.0
+    return m
+
+
+def find_ch_adjacency_from_positions(pos_2d: np.ndarray) -> sparse.csr_matrix:
+    """Delaunay-triangulation neighbours of 2-D sensor positions - the construction
+    ``mne.channels.find_ch_adjacency`` applies to a montage without template (cbpa.py:235)."""
+    from scipy.spatial import Delaunay
+    tri = Delaunay(np.asarray(pos_2d, dtype=np.float64))
+    n = len(pos_2d)
+    e = np.concatenate([tri.simplices[:, [a, b]] for a in range(3) for b in range(3) if a != b])
+    m = sparse.coo_matrix((np.ones(len(e)), (e[:, 0], e[:, 1])), shape=(n, n)).tocsr()
+    m.data[:] = 1.0
+    return m
+
+
+def _build_adjacency(info, n_times: int):
+    """cbpa.py:224-243.  ``info`` may be a spatial adjacency matrix, an (n_ch, 2) array of sensor
+    positions, or an ``mne.Info`` (only when MNE is installed)."""
+    if sparse.issparse(info) or (isinstance(info, np.ndarray) and info.ndim == 2 and info.shape[0] == info.shape[1]):
+        spatial_adj = sparse.csr_matrix(info)
+    elif isinstance(info, np.ndarray) and info.ndim == 2 and info.shape[1] == 2:
+        spatial_adj = find_ch_adjacency_from_positions(info)
+    else:
+        import mne  # noqa: F401 - optional; only needed for mne.Info inputs
+        spatial_adj, _ = mne.channels.find_ch_adjacency(info, ch_type="eeg")
+    combined = combine_adjacency(n_times, spatial_adj)
+    print(f"  [adjacency] spatial: {spatial_adj.shape}, combined (time×space): {combined.shape}, "
+          f"nnz edges: {combined.nnz}")
+    return combined
+
+
+def _add_phase_wraparound(adjacency, n_times: int, n_ch: int, time_grid: np.ndarray):
+    """(0, ch) <-> (n_times - 1, ch) edges for circular phase axes, cbpa.py:949-982."""
+    ch = np.arange(n_ch)
+    first, last = ch, (n_times - 1) * n_ch + ch
+    wrap = sparse.coo_matrix((np.ones(2 * n_ch, dtype=bool), (np.r_[first, last], np.r_[last, first])),
+                             shape=adjacency.shape).tocsr()
+    result = (adjacency.astype(bool) + wrap).astype(bool).tocsr()
+    print(f"  [adjacency] Phase wrap-around edges added (0°↔{int(time_grid[-1])}° for {n_ch} channels)")
+    return result
+
+
+# ----------------------------------------------------------------------------- permutation machinery
+def make_sign_table(n_permutations: int, n_subjects: int, seed=None, tail: int = 0) -> np.ndarray:
+    """int8 (n_rows, n_subjects) table of +-1.  Like MNE the observed ordering counts as one
+    permutation, so ``n_permutations - 1`` random rows are drawn; when all
+    ``2**(n_subjects - (tail == 0)) - 1`` distinct patterns fit, the test is exact and every
+    pattern is enumerated instead.  Two-tailed tests keep subject 0 fixed (t -> -t symmetry)."""
+    free = n_subjects - (1 if tail == 0 else 0)
+    max_perms = 2 ** free - 1 if free < 62 else np.inf
+    if n_permutations - 1 >= max_perms:
+        codes = np.arange(1, int(max_perms) + 1, dtype=np.int64)
+        bits = (codes[:, None] >> np.arange(free, dtype=np.int64)[None, :]) & 1
+    else:
+        rng = seed if isinstance(seed, np.random.Generator) else np.random.default_rng(seed)
+        bits = rng.integers(0, 2, size=(max(n_permutations - 1, 0), free), dtype=np.int8)
+    signs = np.ones((bits.shape[0], n_subjects), dtype=np.int8)
+    signs[:, n_subjects - free:] = 1 - 2 * bits.astype(np.int8)
+    return signs
+
+
+def _pvalues(stats_fixed: np.ndarray, h0_fixed: np.ndarray, tail: int) -> np.ndarray:
+    if tail == -1:
+        return np.array([np.mean(h0_fixed <= s) for s in stats_fixed], dtype=np.float64)
+    if tail == 1:
+        return np.array([np.mean(h0_fixed >= s) for s in stats_fixed], dtype=np.float64)
+    a = np.abs(h0_fixed)
+    return np.array([np.mean(a >= abs(int(s))) for s in stats_fixed], dtype=np.float64)
+
+
+def permutation_cluster_1samp_test(X, threshold=None, n_permutations: int = 1024, tail: int = 0,
+                                   adjacency=None, n_jobs=None, seed=None, out_type: str = "indices",
+                                   verbose=None, *, signs: np.ndarray | None = None, return_details: bool = False):
+    """GPU equivalent of ``mne.stats.permutation_cluster_1samp_test`` for the options the reference
+    uses (sparse adjacency, t_power=1, no TFCE / step-down).  X (n_subj, ...) float64; returns
+    ``(t_obs, clusters, cluster_pv, H0)``: t_obs shaped like one observation, clusters as boolean
+    masks (``out_type='mask'``) or index tuples, H0 = [observed] + one value per sign-table row.
+    ``n_jobs`` / ``verbose`` are accepted for signature compatibility."""
+    if adjacency is None:
+        raise ValueError("a sparse adjacency is required (the reference always passes one)")
+    Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
+    n_subj = Xh.shape[0]
+    sample_shape = Xh.shape[1:]
+    Xf = np.ascontiguousarray(Xh.reshape(n_subj, -1), dtype=np.float64)
+    n_tests = Xf.shape[1]
+    if tail not in (-1, 0, 1):
+        raise ValueError("tail must be -1, 0 or 1")
+    if threshold is None:
+        p = 0.05 / (1 + (tail == 0))
+        threshold = float(t_dist.ppf(1 - p, n_subj - 1)) * (-1 if tail == -1 else 1)
+    if (tail < 0 and threshold > 0) or (tail > 0 and threshold < 0) or (tail == 0 and threshold < 0):
+        raise ValueError(f"incompatible tail and threshold signs, got {tail} and {threshold}")
+    adj = sparse.csr_matrix(adjacency)
+    if adj.shape != (n_tests, n_tests):
+        raise ValueError(f"adjacency must be ({n_tests}, {n_tests}), got {adj.shape}")
+    adj.sort_indices()
+    if signs is None:
+        signs = make_sign_table(n_permutations, n_subj, seed, tail)
+    signs = np.ascontiguousarray(signs, dtype=np.int8)
+    if signs.ndim != 2 or signs.shape[1] != n_subj or not np.all(np.abs(signs) == 1):
+        raise ValueError("signs must be an (n_rows, n_subjects) table of +-1")
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Xd = torch.from_numpy(Xf).to(dev)
+    indptr = torch.from_numpy(adj.indptr.astype(np.int32)).to(dev)
+    indices = torch.from_numpy(adj.indices.astype(np.int32)).to(dev)
+    t_obs_d, labels_d, mass_d, n_clusters = K.cbpa_observed(Xd, threshold, tail, indptr, indices)
+    n_rows = signs.shape[0]
+    begin, end = cdist.shard_range(n_rows)
+    h0_local = K.cbpa_permute(Xd, torch.from_numpy(signs).to(dev), begin, end, threshold, tail, indptr, indices)
+    h0_perm = cdist.all_gather_ranges(h0_local, n_rows).cpu().numpy()
+    mass = mass_d.cpu().numpy()
+    if n_clusters:
+        orig = np.abs(mass).max() if tail == 0 else (mass.max() if tail == 1 else mass.min())
+    else:
+        orig = 0
+    h0_fixed = np.concatenate([[orig], h0_perm]).astype(np.int64)
+    cluster_pv = _pvalues(mass, h0_fixed, tail)
+    labels = labels_d.cpu().numpy()
+    t_obs = t_obs_d.cpu().numpy().reshape(sample_shape)
+    clusters = []
+    for k in range(1, n_clusters + 1):
+        m = labels == k
+        clusters.append(m.reshape(sample_shape) if out_type == "mask"
+                        else np.unravel_index(np.flatnonzero(m), sample_shape))
+    H0 = h0_fixed.astype(np.float64) / K.FIX_SCALE
+    if return_details:
+        return t_obs, clusters, cluster_pv, H0, dict(labels=labels.reshape(sample_shape), mass_fixed=mass,
+                                                     H0_fixed=h0_fixed, signs=signs)
+    return t_obs, clusters, cluster_pv, H0
+
+
+def spatio_temporal_cluster_1samp_test(X, threshold=None, n_permutations: int = 1024, tail: int = 0,
+                                       adjacency=None, n_jobs=None, seed=None, out_type: str = "indices",
+                                       verbose=None, **kwargs):
+    """X (n_subj, n_times, n_ch) with a combined (n_times * n_ch)^2 adjacency - the call the
+    reference makes at cbpa.py:1028-1032."""
+    if np.ndim(X) != 3:
+        raise ValueError("X must be (n_observations, n_times, n_vertices)")
+    return permutation_cluster_1samp_test(X, threshold=threshold, n_permutations=n_permutations, tail=tail,
+                                          adjacency=adjacency, n_jobs=n_jobs, seed=seed, out_type=out_type,
+                                          verbose=verbose, **kwargs)
+
+
+# ----------------------------------------------------------------------------- runner
+def build_contrast_array(cfg: CBPAConfig):
+    """Per-subject A - B contrast (n_subj, n_times, n_ch) from the stored spectrogram files
+    (cbpa.py:733-942).  The loaders are pandas / experiment-log glue of the reference
+     and are not rebuilt here: pass ``contrast=(X, ch_names, time_grid)``
+    to ``run_cbpa`` or assign a callable to ``cbpa.build_contrast_array``."""
+    raise NotImplementedError(
+        "build_contrast_array needs the reference's experiment-log loaders; pass contrast=(X, ch_names, "
+        "time_grid) to run_cbpa")
+
+
+def run_cbpa(cfg: CBPAConfig, cluster_rows_accumulator: list[dict] | None = None, *, contrast=None,
+             spatial_adjacency=None, signs: np.ndarray | None = None) -> dict:
+    """Full CBPA for one contrast, cbpa.py:985-1067.  Returns the reference's result dict
+    (keys t_obs, t_thresh, clusters, cluster_pv, H0, good_cluster_inds, ch_names, time_grid, cfg,
+    n_valid_subjects).  ``spatial_adjacency``: channel adjacency matrix or (n_ch, 2) positions."""
+    filemgmt.assert_dir(cfg.output_dir)
+    _print_header(cfg)
+    X, ch_names, time_grid = contrast if contrast is not None else build_contrast_array(cfg)
+    X = np.asarray(X, dtype=np.float64)
+    n_subj, n_times, n_ch = X.shape
+    df_stat = n_subj - 1
+    if cfg.tail == 0:
+        t_thresh = t_dist.ppf(1.0 - cfg.alpha_cluster_forming / 2, df=df_stat)
+    else:
+        t_thresh = t_dist.ppf(1.0 - cfg.alpha_cluster_forming, df=df_stat)
+    print(f"\n  Cluster-forming threshold  t({df_stat}) = ±{t_thresh:.4f}  "
+          f"(α = {cfg.alpha_cluster_forming}, tail = {cfg.tail})")
+    rng = np.random.default_rng(cfg.seed)
+    if spatial_adjacency is None:
+        raise ValueError("spatial_adjacency (matrix or 2-D sensor positions) is required without MNE")
+    adjacency = _build_adjacency(spatial_adjacency, n_times)
+    if cfg.use_phase_normalization:
+        adjacency = _add_phase_wraparound(adjacency, n_times, n_ch, np.asarray(time_grid))
+    if cfg.use_spatio_temporal:
+        t_obs, clusters, cluster_pv, H0 = spatio_temporal_cluster_1samp_test(
+            X, n_permutations=cfg.n_permutations, threshold=t_thresh, tail=cfg.tail, adjacency=adjacency,
+            n_jobs=cfg.n_jobs, seed=rng, out_type="mask", verbose=True, signs=signs)
+    else:
+        X_flat = X.reshape(n_subj, n_times * n_ch)
+        print(f"  [adjacency] flat: {adjacency.shape}, nnz edges: {adjacency.nnz}")
+        t_obs_flat, clusters, cluster_pv, H0 = permutation_cluster_1samp_test(
+            X_flat, n_permutations=cfg.n_permutations, threshold=t_thresh, tail=cfg.tail,
+            adjacency=adjacency, n_jobs=cfg.n_jobs, seed=rng, out_type="mask", verbose=True, signs=signs)
+        t_obs = t_obs_flat.reshape(n_times, n_ch)
+    alpha_cbpa = 0.05
+    good_cluster_inds = np.where(np.array(cluster_pv) < alpha_cbpa)[0]
+    print(f"\n  Clusters found: {len(clusters)} total, "
+          f"{len(good_cluster_inds)} significant (cluster p < {alpha_cbpa})")
+    for idx in good_cluster_inds:
+        print(f"    Cluster #{idx + 1:02d}:  p = {cluster_pv[idx]:.4f}")
+    results = dict(t_obs=t_obs, t_thresh=t_thresh, clusters=clusters, cluster_pv=np.array(cluster_pv), H0=H0,
+                   good_cluster_inds=good_cluster_inds, ch_names=ch_names, time_grid=time_grid, cfg=cfg,
+                   n_valid_subjects=n_subj)
+    _save_results(results, cfg, cluster_rows_accumulator=cluster_rows_accumulator,
+                  save_per_run_cluster_csv=(cluster_rows_accumulator is None))
+    return results
+
+
+def _cluster_mask(cluster, n_times: int, n_ch: int) -> np.ndarray:
+    if isinstance(cluster, np.ndarray) and cluster.dtype == bool:
+        return cluster.reshape(n_times, n_ch) if cluster.ndim == 1 else cluster
+    mask = np.zeros((n_times, n_ch), dtype=bool)
+    mask[cluster] = True
+    return mask
+
+
+def _save_results(results: dict, cfg: CBPAConfig, cluster_rows_accumulator: list[dict] | None = None,
+                  save_per_run_cluster_csv: bool = False) -> None:
+    """.npz archive, t_obs CSV and cluster summary rows with the reference's column names
+    (cbpa.py:1076-1185) so ``statistical_reporting._section_cbpa`` keeps reading them."""
+    import pandas as pd
+    stem = filemgmt.file_title(cfg.hypothesis_label, "")
+    out_dir = Path(cfg.output_dir)
+    np.savez(out_dir / (stem + ".npz"), t_obs=results["t_obs"], cluster_pv=results["cluster_pv"],
+             H0=results["H0"], ch_names=results["ch_names"], time_grid=results["time_grid"],
+             good_cluster_inds=results["good_cluster_inds"])
+    t_obs, time_grid, ch_names = results["t_obs"], results["time_grid"], list(results["ch_names"])
+    t_ax = np.asarray(time_grid) if time_grid is not None else np.arange(t_obs.shape[0])
+    pd.DataFrame(t_obs, index=pd.Index(np.round(t_ax, 4), name="time_s"), columns=ch_names).to_csv(
+        out_dir / (stem + "_t_obs.csv"))
+    n_times, n_ch = t_obs.shape
+    axis_label = "phase_deg" if cfg.use_phase_normalization else "time_s"
+    rows = []
+    for idx, (cluster, pv) in enumerate(zip(results["clusters"], results["cluster_pv"])):
+        mask = _cluster_mask(cluster, n_times, n_ch)
+        t_in = np.where(mask.any(axis=1))[0]
+        ch_in = np.where(mask.any(axis=0))[0]
+        rows.append({
+            "hypothesis": cfg.hypothesis_label, "modality": cfg.modality, "freq_band": cfg.freq_band,
+            "condition_column": cfg.condition_column, "condition_A": cfg.condition_A,
+            "condition_B": cfg.condition_B, "n_within_trial_segs": cfg.n_within_trial_segs,
+            "n_permutations": cfg.n_permutations, "alpha_cluster_forming": cfg.alpha_cluster_forming,
+            "tail": cfg.tail, "n_valid_subjects": results["n_valid_subjects"],
+            "cluster_index": idx + 1, "p_value": round(float(pv), 6),
+            "significant": bool(idx in results["good_cluster_inds"]),
+            "peak_t": round(float(np.abs(t_obs[mask]).max()) if mask.any() else 0.0, 4),
+            "t_thresh": round(float(results["t_thresh"]), 4), "n_time_points": int(len(t_in)),
+            f"{axis_label}_start": round(float(t_ax[t_in[0]]), 4) if len(t_in) > 0 else None,
+            f"{axis_label}_end": round(float(t_ax[t_in[-1]]), 4) if len(t_in) > 0 else None,
+            "n_channels": int(len(ch_in)), "channels": "; ".join(ch_names[i] for i in ch_in),
+        })
+    if cluster_rows_accumulator is not None:
+        cluster_rows_accumulator.extend(rows)
+    if save_per_run_cluster_csv:
+        pd.DataFrame(rows).to_csv(out_dir / (stem + "_cluster_summary.csv"), index=False)
+
+
+def _print_header(cfg: CBPAConfig) -> None:
+    bar = "═" * 70
+    print(f"\n{bar}\n  CBPA: {cfg.hypothesis_label}\n  Feature    : {cfg.modality} | {cfg.freq_band} band\n"
+          f"  Contrast   : '{cfg.condition_A}'  −  '{cfg.condition_B}'\n"
+          f"  Permutations: {cfg.n_permutations}  |  tail={cfg.tail}  |  α={cfg.alpha_cluster_forming}\n{bar}\n")
+
+
+def run_batch(configs: list[CBPAConfig], **run_kwargs):
+    """Sequential runs + one combined cluster-summary CSV, cbpa.py:1214-1250."""
+    import pandas as pd
+    all_results, rows = [], []
+    for i, cfg in enumerate(configs):
+        print(f"\n[{i + 1}/{len(configs)}] Starting: {cfg.hypothesis_label}")
+        all_results.append(run_cbpa(cfg, cluster_rows_accumulator=rows, **run_kwargs))
+    combined = pd.DataFrame(rows)
+    if not combined.empty:
+        out_path = Path(configs[0].output_dir) / filemgmt.file_title("CBPA Combined Cluster Summary", ".csv")
+        combined.to_csv(out_path, index=False)
+    return all_results, combined

@@ -1,0 +1,139 @@
+"""Drop-in for the reference's ``src/pipeline/data_surrogation.py`` plus the surrogate-null API.
+
+The reference module only holds test-data corrupters (``insert_bad_channels`` :19-65,
+``add_noise_to_channels`` :69-148, ``generate_noise`` :151-199); they are tiny host-side numpy
+helpers driven by the global ``random`` / ``np.random`` state and are kept with identical
+signatures and behaviour.  The statistical surrogates are NEW (the reference's stand-in is the
+analytic Beta threshold, signal_features.py:470-481): they reuse the whitened spectra cached by
+``signal_features.pooled_coherence`` so that a surrogate costs one cross-spectral contraction, shard
+across ranks by global surrogate index and exchange only counts and per-surrogate maxima.
+"""
+from __future__ import annotations
+
+import random
+from typing import Literal
+
+import numpy as np
+import torch
+
+from . import dist as cdist
+from . import kernels as K
+
+
+def check_2d_numpy_array(input_array: np.ndarray, axis: Literal[0, 1] = None):
+    if len(input_array.shape) == 1:
+        input_array = input_array[:, np.newaxis]
+        if axis is None:
+            axis = 0
+    else:
+        if axis is None:
+            raise AttributeError("For 2D signal arrays, axis needs to be defined!")
+    return input_array, axis
+
+
+def insert_bad_channels(input_array: np.ndarray, axis: Literal[0, 1] = None, n_channels: int = 5,
+                        scale_range: tuple[float, float] = (10.0, 15.0)) -> tuple[np.ndarray, list[int]]:
+    """Scale ``n_channels`` randomly chosen columns by U(scale_range); returns the copy and the
+    1-based indices of the amended channels (data_surrogation.py:19-65).  As in the reference,
+    channel 0 is never drawn (``range(1, ...)``) and the count comes from ``shape[axis + 1 % 2]``."""
+    input_array, axis = check_2d_numpy_array(input_array, axis)
+    output_array = input_array.copy()
+    lo, hi = scale_range
+    picked = random.sample(range(1, input_array.shape[axis + 1 % 2]), k=n_channels)
+    amended = []
+    for ch in picked:
+        factor = lo + np.random.rand() * (hi - lo)
+        output_array[:, ch] = input_array[:, ch] * factor
+        amended.append(ch + 1)
+    return output_array, amended
+
+
+def generate_noise(shape: tuple, noise_type: str, amplitude: float) -> np.ndarray:
+    """White or pink (white rFFT scaled by 1/sqrt(f)) noise with RMS ``amplitude``
+    (data_surrogation.py:151-199)."""
+    if noise_type == "white":
+        noise = np.random.normal(0, 1, shape)
+    elif noise_type == "pink":
+        n = shape[0]
+        spectrum = np.fft.rfft(np.random.normal(0, 1, n))
+        f = np.fft.rfftfreq(n)
+        f[0] = 1
+        noise = np.fft.irfft(spectrum / np.sqrt(f), n=n)
+        if len(shape) > 1:
+            noise = np.tile(noise[:, np.newaxis], (1, shape[1]))
+    else:
+        raise ValueError(f"Unknown noise_type: {noise_type}")
+    return noise * (amplitude / np.sqrt(np.mean(noise ** 2)))
+
+
+def add_noise_to_channels(input_array: np.ndarray, noise_db: float, channels: list[int],
+                          axis: Literal[0, 1] = 0, noise_type: Literal["white", "pink"] = "white",
+                          random_seed: int = None) -> np.ndarray:
+    """Add noise at a target SNR (dB) to the listed channels (data_surrogation.py:69-148)."""
+    if random_seed is not None:
+        np.random.seed(random_seed)
+    array, axis = check_2d_numpy_array(input_array, axis)
+    max_channels = array.shape[1 - axis]
+    if not all(0 <= ch < max_channels for ch in channels):
+        raise ValueError(f"Channel indices must be in range [0, {max_channels - 1}]")
+    noisy = array.copy()
+    for ch in channels:
+        sig = noisy[:, ch] if axis == 0 else noisy[ch, :]
+        noise_rms = np.sqrt(np.mean(sig ** 2) / 10 ** (noise_db / 10))
+        noise = generate_noise(sig.shape, noise_type, noise_rms)
+        if axis == 0:
+            noisy[:, ch] = sig + noise
+        else:
+            noisy[ch, :] = sig + noise
+    return noisy
+
+
+# ----------------------------------------------------------------------------- surrogate null (new)
+def _finish(pooled, exceed_d: torch.Tensor, max_local: torch.Tensor, n_surrogates: int, alpha: float):
+    cdist.all_reduce_sum_(exceed_d)
+    max_stat = cdist.all_gather_ranges(max_local, n_surrogates)
+    exceed = exceed_d.cpu().numpy().astype(np.int64)
+    ms = max_stat.cpu().numpy()
+    return {
+        "exceed": exceed,                                       # #{s : C_s >= C_obs} per (f, i, j)
+        "p_values": (1.0 + exceed) / (1.0 + n_surrogates),
+        "max_stat": ms,                                         # max over (f, i, j) per surrogate
+        "threshold_fwe": float(np.quantile(ms, 1.0 - alpha)) if n_surrogates else float("nan"),
+        "n_surrogates": n_surrogates,
+        "coherence": pooled.coherence,
+        "freqs": pooled.freqs,
+    }
+
+
+def circular_shift_surrogate_null(pooled, n_surrogates: int = 1000, seed: int | None = 0,
+                                  shifts: np.ndarray | None = None, alpha: float = 0.05) -> dict:
+    """Circular time-shift surrogates: surrogate s rotates the EMG segment (window) index by
+    ``shifts[s]`` in [1, n_positions - 1] (whole windows for multitaper pooling, tapers stay
+    aligned).  ``shifts`` is a host-supplied int32 table; by default it is drawn from
+    ``np.random.default_rng(seed)``.  Returns exceedance counts, p-values, the per-surrogate
+    max statistic and its (1 - alpha) quantile (family-wise threshold)."""
+    csd = pooled.device_result
+    L = csd.dims[0]
+    n_pos = L // pooled.group
+    if n_pos < 2:
+        raise ValueError("circular shift surrogates need at least two segments")
+    if shifts is None:
+        shifts = np.random.default_rng(seed).integers(1, n_pos, n_surrogates)
+    shifts = np.ascontiguousarray(shifts, dtype=np.int32)
+    if shifts.shape != (n_surrogates,):
+        raise ValueError("one shift per surrogate")
+    begin, end = cdist.shard_range(n_surrogates)
+    dev = csd.coh.device
+    exceed, max_local = K.surrogate_null(csd, K.SURR_SHIFT, begin, end,
+                                         shifts=torch.from_numpy(shifts[begin:end]).to(dev), group=pooled.group)
+    return _finish(pooled, exceed, max_local, n_surrogates, alpha)
+
+
+def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int = 0, alpha: float = 0.05) -> dict:
+    """Phase-randomised surrogates: every EMG spectrum is rotated by one random phase per
+    (surrogate, segment, frequency), shared by all EMG channels; phases come from
+    Philox4x32-10(seed; s, l, f) so any sharding of the surrogate index gives the same null."""
+    csd = pooled.device_result
+    begin, end = cdist.shard_range(n_surrogates)
+    exceed, max_local = K.surrogate_null(csd, K.SURR_PHASE, begin, end, seed=seed)
+    return _finish(pooled, exceed, max_local, n_surrogates, alpha)

@@ -1,0 +1,49 @@
+"""Sharding of surrogates / permutations across ranks (one process per GPU, torch.distributed).
+
+The path shards by index range with no data-path collective: every rank holds the (small)
+replicated inputs, computes a contiguous slice of the surrogate / permutation indices and only the
+per-index max-statistic vectors (all_gather) and the exceedance histograms (all_reduce) are
+exchanged - NCCL over NVLink on GPUs, gloo in the CPU tests.  Indices are global, so results do
+not depend on the number of ranks.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n: int, rank: int | None = None, world_size: int | None = None) -> tuple[int, int]:
+    """Contiguous slice [begin, end) of range(n) owned by ``rank`` (sizes differ by at most 1)."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, rem = divmod(n, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def all_gather_ranges(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Concatenate per-rank slices produced with ``shard_range`` into the full length-n vector."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    sizes = [shard_range(n_total, r, ws) for r in range(ws)]
+    width = max(e - b for b, e in sizes)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    gathered = [torch.empty_like(padded) for _ in range(ws)]
+    dist.all_gather(gathered, padded)
+    return torch.cat([g[: e - b] for g, (b, e) in zip(gathered, sizes)])
+
+
+def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
