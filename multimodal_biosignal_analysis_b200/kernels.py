@@ -22,6 +22,14 @@ def _need_cuda(t: torch.Tensor, name: str, dtype=None):
         raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
 
 
+def check_segments(seg_starts_host, N: int, n_samples: int) -> None:
+    """Host-side bounds check of a segment table (numpy / list)."""
+    import numpy as np
+    s = np.asarray(seg_starts_host)
+    if s.size and (int(s.min()) < 0 or int(s.max()) + N > n_samples):
+        raise ValueError("segment outside the recording")
+
+
 def fft_segments(x: torch.Tensor, seg_starts: torch.Tensor, windows: torch.Tensor, detrend: int = 0,
                  bin_lo: int = 0, bin_hi: int | None = None, out: torch.Tensor | None = None,
                  ch_offset: int = 0) -> torch.Tensor:
@@ -44,8 +52,8 @@ def fft_segments(x: torch.Tensor, seg_starts: torch.Tensor, windows: torch.Tenso
     if bin_hi is None:
         bin_hi = N // 2
     F = bin_hi - bin_lo + 1
-    if n_seg and (int(seg_starts.min()) < 0 or int(seg_starts.max()) + N > n_samples):
-        raise ValueError("segment outside the recording")
+    # bounds of seg_starts are the caller's contract (checked on the host by the public API):
+    # reading them back here would force a device synchronisation on every call
     if out is None:
         out = torch.empty((n_seg, K, F, n_ch), dtype=torch.complex64, device=x.device)
         ch_offset = 0

@@ -531,6 +531,7 @@ def pooled_coherence(eeg_array, emg_array, sampling_freq: float, segment_starts,
             raise ValueError(f"freq_band {freq_band} selects no frequency bin")
         lo, hi = int(sel[0]), int(sel[-1])
     dev = _device()
+    K.check_segments(segment_starts, N, eeg_array.shape[0])
     starts_d = torch.as_tensor(np.asarray(segment_starts, dtype=np.int64)).to(dev)
     wd = torch.from_numpy(windows).to(dev)
     X = K.fft_segments(_to_device_f32(eeg_array), starts_d, wd, detrend, lo, hi)

