@@ -48,7 +48,7 @@ extern "C" {
 
 #define CMC_SURR_SHIFT 0
 #define CMC_SURR_PHASE 1
-#define CMC_PHASE_TABLE_BITS 12  /* phase surrogates index a 4096-entry TF32 table */
+#define CMC_PHASE_TABLE_BITS 12  /* phase surrogates index a 4096-entry bf16 table */
 #define CMC_FIX_SHIFT 30         /* cluster masses: int64 sums of rint(t * 2^30) */
 #define CMC_T_CLAMP 65536.0
 
@@ -134,14 +134,18 @@ CMC_API int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne, in
  *
  *   mode CMC_SURR_SHIFT: surrogate s rotates the EMG segment index by
  *        shifts[s] * group (shifts int32 [s_end - s_begin], host-chosen, in [1, L/group))
- *   mode CMC_SURR_PHASE: one Philox4x32-10(seed; s, l, f) phase per surrogate, segment
- *        and frequency, shared by all EMG channels; s runs over GLOBAL indices
- *        [s_begin, s_end) so results do not depend on how surrogates are sharded.
+ *   mode CMC_SURR_PHASE: one phase per surrogate, segment and frequency, shared by all EMG
+ *        channels: table index = word (f & 3) of Philox4x32-10(key = seed, counter =
+ *        (s, l, f >> 2, s >> 32)) >> 20; s runs over GLOBAL indices [s_begin, s_end) so
+ *        results do not depend on how surrogates are sharded.  BF16 tensor-core GEMM with
+ *        the phase panel resident in shared memory: needs 2 L <= 512.
  *   coh_obs  [F][Ne][Nm]  observed coherence to compare against
  *   exceed   [F][Ne][Nm]  uint32, += #{s : C_s >= coh_obs}   (caller zero-initialises)
  *   max_stat [s_end - s_begin] float32 max over (f, i, j) of C_s
  *   ws2 scratch of cmc_surrogate_workspace_bytes()
  * ---------------------------------------------------------------------------------- */
+/* host copy of the phase table P[a] = (bf16(cos), bf16(sin)) of 2 pi a / 4096 as float pairs [4096][2] */
+CMC_API int cmc_phase_table(float* out_host);
 CMC_API int64_t cmc_surrogate_workspace_bytes(int L, int F, int Ne, int Nm, int mode, int64_t n_surr);
 CMC_API int cmc_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, int mode, int group,
                        const int32_t* shifts, uint64_t seed, int64_t s_begin, int64_t s_end,

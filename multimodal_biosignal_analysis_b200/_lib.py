@@ -27,6 +27,7 @@ _SIGNATURES = {
                                          _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cmc_csd_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "cmc_csd_msc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "cmc_phase_table": (C.c_int, [_vp]),
     "cmc_surrogate_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i64]),
     "cmc_surrogate_null": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _u64, _i64, _i64, _vp, _vp,
                                      _vp, _vp, _i64, _vp]),

@@ -1,0 +1,433 @@
+// K3 (phase mode): phase-randomised surrogate null as ONE dense GEMM per frequency on the tensor
+// cores (tcgen05.mma kind::f16, BF16 inputs, FP32 accumulation in TMEM).
+//
+// Surrogate s rotates every EMG spectrum by one phase per (segment l, frequency f), shared by all EMG
+// channels:  S_s[i][j] = sum_l conj(Xh[l][i]) Yh[l][j] P[s][l]  (Xh, Yh whitened, P on the unit circle).
+// With Z[l][(i,j)] = conj(Xh[l][i]) Yh[l][j] - computed ONCE - every surrogate is a row of
+//     D[s][n] = sum_k A[s][k] B[n][k],   K = (l, re/im),
+//     A[s]        = (P_re, P_im) interleaved                      M = surrogates
+//     B[re-form]  = (Z_re, -Z_im),  B[im-form] = (Z_im, Z_re)      N = 2 x pairs
+// so Re S and Im S of one pair land in the SAME accumulator lane (columns c and 128 + c of a
+// 128-pair tile) and the epilogue is lane-local: C = Re^2 + Im^2, compare with the observed
+// coherence (warp ballot -> per-pair exceedance count), running max per surrogate.
+//
+// CTA work unit = one (frequency, 128-surrogate panel): the A panel (128 x K) stays resident in
+// shared memory while the 256-row B tiles of all pair groups stream through a 3-stage TMA ring;
+// two 256-column TMEM accumulators overlap the epilogue with the next tile's MMAs.
+#include "csd_layout.cuh"
+
+#include <cuda_bf16.h>
+#include <math.h>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace cmc {
+
+using namespace tc;
+
+constexpr int kPhM = 128;            // surrogates per panel
+constexpr int kPhPairs = 128;        // pairs per B tile
+constexpr int kPhN = 2 * kPhPairs;   // B tile rows (re-forms then im-forms)
+constexpr int kPhKB = 64;            // bf16 per k-block = 128 bytes
+constexpr int kPhStages = 3;
+constexpr int kPhBBytes = kPhN * 128;   // 32 KB per stage
+constexpr int kPhThreads = 256;
+constexpr int kPhaseN = 1 << CMC_PHASE_TABLE_BITS;
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+static uint16_t host_bf16_rne(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// per-device table P[a] = (bf16(cos), bf16(sin)) of 2 pi a / 4096, packed as two bf16 in a uint32
+static int get_phase_table(const uint32_t** table) {
+    static std::mutex mu;
+    static std::map<int, uint32_t*> cache;
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(dev);
+    if (it == cache.end()) {
+        std::vector<uint32_t> h(kPhaseN);
+        for (int a = 0; a < kPhaseN; ++a) {
+            const double ang = 6.283185307179586476925286766559 * a / kPhaseN;
+            h[a] = (uint32_t)host_bf16_rne((float)cos(ang)) | ((uint32_t)host_bf16_rne((float)sin(ang)) << 16);
+        }
+        uint32_t* d = nullptr;
+        rc = check_cuda(cudaMalloc(&d, h.size() * 4), "cudaMalloc(phase table)");
+        if (rc) return rc;
+        rc = check_cuda(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice), "cudaMemcpy(phase table)");
+        if (rc) return rc;
+        it = cache.emplace(dev, d).first;
+    }
+    *table = it->second;
+    return CMC_OK;
+}
+
+// A operand: Phi[f][s_local][k] (bf16, K-major, row length KPb); one thread = (s, l, group of 4 frequencies)
+__global__ void __launch_bounds__(256)
+phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_begin, int n_local, int S_pad, int L,
+                 int F, int fg0, int KPb, __nv_bfloat16* __restrict__ A) {
+    const int lp = blockIdx.x * blockDim.x + threadIdx.x;      // complex column index, covers [0, KPb / 2)
+    const int s = blockIdx.y;                                   // local surrogate row, covers [0, S_pad)
+    const int fg = blockIdx.z;                                  // frequency group of 4
+    if (lp >= KPb / 2) return;
+    uint32_t vals[4] = {0u, 0u, 0u, 0u};
+    if (s < n_local && lp < L) {
+        const uint64_t sg = (uint64_t)(s_begin + s);
+        // counter = (surrogate, segment, GLOBAL frequency group, surrogate >> 32): word q is frequency 4 fg + q
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)sg, (uint32_t)lp, (uint32_t)(fg0 + fg), (uint32_t)(sg >> 32)),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        vals[0] = __ldg(table + (r.x >> (32 - CMC_PHASE_TABLE_BITS)));
+        vals[1] = __ldg(table + (r.y >> (32 - CMC_PHASE_TABLE_BITS)));
+        vals[2] = __ldg(table + (r.z >> (32 - CMC_PHASE_TABLE_BITS)));
+        vals[3] = __ldg(table + (r.w >> (32 - CMC_PHASE_TABLE_BITS)));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int f = fg * 4 + q;
+        if (f < F)
+            reinterpret_cast<uint32_t*>(A)[(((int64_t)f * S_pad + s) * KPb) / 2 + lp] = vals[q];
+    }
+}
+
+// B operand: Z re-/im-form rows (bf16, K-major) from the whitened 3xTF32 operands left by cmc_csd_msc.
+// grid (F, Ne); block 256: the thread block holds Xh row i in shared memory and sweeps j.
+__global__ void __launch_bounds__(256)
+z_gen_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo, const float* __restrict__ Bhi,
+             const float* __restrict__ Blo, int L, int Ne, int Nm, int MT, int NT, int KP, int LB, int KPb,
+             int R_pad, __nv_bfloat16* __restrict__ Z) {
+    extern __shared__ float2 xs[];                      // [KPb / 2] complex Xh[l][i]
+    const int f = blockIdx.x, i = blockIdx.y;
+    const int half = KPb / 2;
+    const float* ah = Ahi + ((int64_t)(f * MT + (i >> 6)) * kTileM + (i & 63)) * KP;
+    const float* al = Alo + ((int64_t)(f * MT + (i >> 6)) * kTileM + (i & 63)) * KP;
+    for (int l = threadIdx.x; l < half; l += blockDim.x) {
+        float2 v = make_float2(0.f, 0.f);
+        if (l < L) v = make_float2(ah[2 * l] + al[2 * l], ah[2 * l + 1] + al[2 * l + 1]);
+        xs[l] = v;
+    }
+    __syncthreads();
+    for (int j = 0; j < Nm; ++j) {
+        const float* bh = Bhi + ((int64_t)(f * NT + (j >> 6)) * kTileN + (j & 63)) * LB;
+        const float* bl = Blo + ((int64_t)(f * NT + (j >> 6)) * kTileN + (j & 63)) * LB;
+        const int p = i * Nm + j;
+        const int64_t row_re = (int64_t)f * R_pad + (p / kPhPairs) * kPhN + (p % kPhPairs);
+        uint32_t* zre = reinterpret_cast<uint32_t*>(Z + row_re * KPb);
+        uint32_t* zim = reinterpret_cast<uint32_t*>(Z + (row_re + kPhPairs) * KPb);
+        for (int l = threadIdx.x; l < half; l += blockDim.x) {
+            float zr = 0.f, zi = 0.f;
+            if (l < L) {
+                const float2 x = xs[l];
+                const float yr = bh[2 * l] + bl[2 * l], yi = bh[2 * l + 1] + bl[2 * l + 1];
+                zr = x.x * yr + x.y * yi;          // conj(x) * y
+                zi = x.x * yi - x.y * yr;
+            }
+            const __nv_bfloat162 re = __floats2bfloat162_rn(zr, -zi);
+            const __nv_bfloat162 im = __floats2bfloat162_rn(zi, zr);
+            zre[l] = *reinterpret_cast<const uint32_t*>(&re);
+            zim[l] = *reinterpret_cast<const uint32_t*>(&im);
+        }
+    }
+}
+
+struct PhaseParams {
+    int F, MT, NT, KB, n_local, n_pairs, S_pad, R_pad;
+    const float* coh_obs;      // [F][n_pairs]
+    uint32_t* exceed;          // [F][n_pairs]
+    uint32_t* max_u;           // [S_pad] float bits
+};
+
+struct __align__(8) PhaseBarriers {
+    uint64_t full[kPhStages];
+    uint64_t empty[kPhStages];
+    uint64_t a_full;
+    uint64_t a_empty;
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kPhThreads, 1)
+phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const PhaseParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = p.KB * kPhM * 128;                     // resident A panel: KB k-blocks of 16 KB
+    unsigned char* sA = base;
+    unsigned char* sB = base + a_bytes;                        // [kPhStages][32 KB]
+    float* cobs_s = reinterpret_cast<float*>(sB + kPhStages * kPhBBytes);   // [128]
+    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(cobs_s + kPhPairs);       // [128]
+    PhaseBarriers* bars = reinterpret_cast<PhaseBarriers*>(cnt_s + kPhPairs);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_panels = p.F * p.MT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPhStages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->a_empty, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars->tmem_full[a], 1);
+            mbar_init(&bars->tmem_empty[a], 4);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&mA);
+        tma_prefetch_desc(&mB);
+    }
+    if (warp == 2) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int pn = blockIdx.x; pn < n_panels; pn += gridDim.x) {
+                const int f = pn / p.MT, mt = pn - f * p.MT;
+                mbar_wait(&bars->a_empty, a_phase ^ 1);           // previous panel fully consumed
+                mbar_arrive_expect_tx(&bars->a_full, (uint32_t)a_bytes);
+                for (int kb = 0; kb < p.KB; ++kb)
+                    tma_load_2d(sA + kb * kPhM * 128, &mA, &bars->a_full, kb * kPhKB, f * p.S_pad + mt * kPhM);
+                a_phase ^= 1;
+                for (int nt = 0; nt < p.NT; ++nt)
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(&bars->empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&bars->full[stage], kPhBBytes);
+                        tma_load_2d(sB + stage * kPhBBytes, &mB, &bars->full[stage], kb * kPhKB,
+                                    f * p.R_pad + nt * kPhN);
+                        if (++stage == kPhStages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kPhM, kPhN);
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0, it = 0;
+            for (int pn = blockIdx.x; pn < n_panels; pn += gridDim.x) {
+                mbar_wait(&bars->a_full, a_phase);
+                a_phase ^= 1;
+                tc_fence_after();
+                for (int nt = 0; nt < p.NT; ++nt) {
+                    const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
+                    mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + acc * kPhN;
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(&bars->full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(sA + kb * kPhM * 128);
+                        const uint32_t b0 = smem_u32(sB + stage * kPhBBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d, make_smem_desc_k_sw128(a0 + k * 32), make_smem_desc_k_sw128(b0 + k * 32),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(&bars->empty[stage]);
+                        if (++stage == kPhStages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&bars->tmem_full[acc]);
+                    ++it;
+                }
+                umma_commit(&bars->a_empty);                      // A panel may be overwritten
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;
+        const int te = threadIdx.x - 128;                         // accumulator lane = surrogate row in the panel
+        uint32_t it = 0;
+        for (int pn = blockIdx.x; pn < n_panels; pn += gridDim.x) {
+            const int f = pn / p.MT, mt = pn - f * p.MT;
+            const int s_local = mt * kPhM + te;
+            const bool s_ok = s_local < p.n_local;
+            float vmax = 0.f;
+            for (int nt = 0; nt < p.NT; ++nt) {
+                const int pair_t = nt * kPhPairs + te;
+                cobs_s[te] = pair_t < p.n_pairs ? __ldg(p.coh_obs + (int64_t)f * p.n_pairs + pair_t) : 2.0f;
+                cnt_s[te] = 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
+                mbar_wait(&bars->tmem_full[acc], accphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * kPhN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t re[32], im[32];
+                    tmem_ld_32x32(taddr + ch * 32, re);
+                    tmem_ld_32x32(taddr + kPhPairs + ch * 32, im);
+                    tmem_ld_wait();
+                    uint32_t mine = 0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float a = __uint_as_float(re[c]), b = __uint_as_float(im[c]);
+                        const float cv = fminf(a * a + b * b, 1.0f);
+                        const bool hit = s_ok && (cv >= cobs_s[ch * 32 + c]);
+                        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                        mine = (lane == c) ? __popc(bal) : mine;
+                        vmax = fmaxf(vmax, cv);
+                    }
+                    if (mine) atomicAdd(&cnt_s[ch * 32 + lane], mine);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (cnt_s[te]) atomicAdd(&p.exceed[(int64_t)f * p.n_pairs + pair_t], cnt_s[te]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                ++it;
+            }
+            if (s_ok) atomicMax(&p.max_u[s_local], __float_as_uint(vmax));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void phase_gather_kernel(const uint32_t* __restrict__ max_u, int64_t n, float* __restrict__ max_stat) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) max_stat[i] = __uint_as_float(max_u[i]);
+}
+
+struct PhaseLayout {
+    int KPb, KB, S_pad, MT, n_pairs, n_pairs_pad, R_pad, NT, f_chunk;
+    int64_t off_max, off_A, off_Z, total;
+};
+
+static PhaseLayout phase_layout(int L, int F, int Ne, int Nm, int64_t n_surr) {
+    PhaseLayout y;
+    y.KPb = (int)align_up(2 * (int64_t)L, kPhKB);
+    y.KB = y.KPb / kPhKB;
+    y.S_pad = (int)align_up(n_surr > 0 ? n_surr : 1, kPhM);
+    y.MT = y.S_pad / kPhM;
+    y.n_pairs = Ne * Nm;
+    y.n_pairs_pad = (int)align_up(y.n_pairs, kPhPairs);
+    y.R_pad = 2 * y.n_pairs_pad;
+    y.NT = y.n_pairs_pad / kPhPairs;
+    // frequencies per launch: keep the generated operands of one chunk within ~3 GB
+    const int64_t per_f = ((int64_t)y.S_pad + y.R_pad) * y.KPb * 2;
+    int64_t fc = (3ll << 30) / (per_f > 0 ? per_f : 1);
+    fc = fc < 4 ? 4 : fc;
+    fc = fc / 4 * 4;                                            // Philox emits 4 frequencies per call
+    y.f_chunk = (int)(fc > F ? align_up(F, 4) : fc);
+    int64_t o = 0;
+    y.off_max = o; o = align_up(o + (int64_t)y.S_pad * 4, 1024);
+    y.off_A = o; o = align_up(o + (int64_t)y.f_chunk * y.S_pad * y.KPb * 2, 1024);
+    y.off_Z = o; o = align_up(o + (int64_t)y.f_chunk * y.R_pad * y.KPb * 2, 1024);
+    y.total = o;
+    return y;
+}
+
+int64_t phase_workspace_bytes(int L, int F, int Ne, int Nm, int64_t n_surr) {
+    return phase_layout(L, F, Ne, Nm, n_surr).total;
+}
+
+int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
+                         const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2, int64_t ws2_bytes,
+                         cudaStream_t st) {
+    const int64_t n = s_end - s_begin;
+    CMC_REQUIRE(n < (1ll << 31) - 256, "cmc_surrogate_null: too many surrogates in one call");
+    const CsdLayout cy = csd_layout(L, F, Ne, Nm);
+    const PhaseLayout y = phase_layout(L, F, Ne, Nm, n);
+    if (ws2_bytes < y.total) {
+        set_error("cmc_surrogate_null: workspace %lld < %lld bytes", (long long)ws2_bytes, (long long)y.total);
+        return CMC_EWORKSPACE;
+    }
+    CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws2) & 255) == 0, "cmc_surrogate_null: workspace must be 256-byte aligned");
+    const size_t smem = 1024 + (size_t)y.KB * kPhM * 128 + kPhStages * kPhBBytes + kPhPairs * 8 + sizeof(PhaseBarriers) + 16;
+    if (smem > 227 * 1024) {
+        set_error("cmc_surrogate_null: L=%d too long for the resident phase panel (2L <= 512)", L);
+        return CMC_EUNSUPPORTED;
+    }
+    const uint32_t* table;
+    int rc = get_phase_table(&table);
+    if (rc) return rc;
+    const unsigned char* w = static_cast<const unsigned char*>(ws);
+    unsigned char* w2 = static_cast<unsigned char*>(ws2);
+    uint32_t* max_u = reinterpret_cast<uint32_t*>(w2 + y.off_max);
+    __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(w2 + y.off_A);
+    __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w2 + y.off_Z);
+    rc = check_cuda(cudaMemsetAsync(max_u, 0, (size_t)y.S_pad * 4, st), "memset(max_u)");
+    if (rc) return rc;
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(phase_gemm_kernel), smem);
+    if (rc) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    for (int f0 = 0; f0 < F; f0 += y.f_chunk) {
+        const int fc = F - f0 < y.f_chunk ? F - f0 : y.f_chunk;
+        if (y.n_pairs_pad != y.n_pairs) {
+            rc = check_cuda(cudaMemsetAsync(Z, 0, (size_t)fc * y.R_pad * y.KPb * 2, st), "memset(Z)");
+            if (rc) return rc;
+        }
+        // Philox counters use GLOBAL frequency groups: shift the group index by f0 / 4
+        phase_gen_kernel<<<dim3((y.KPb / 2 + 255) / 256, y.S_pad, (fc + 3) / 4), 256, 0, st>>>(
+            table, seed, s_begin, (int)n, y.S_pad, L, fc, f0 / 4, y.KPb, A);
+        CMC_CHECK_LAUNCH("phase_gen_kernel");
+        z_gen_kernel<<<dim3(fc, Ne), 256, (size_t)y.KPb * 4, st>>>(
+            reinterpret_cast<const float*>(w + cy.off_ahi) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
+            reinterpret_cast<const float*>(w + cy.off_alo) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
+            reinterpret_cast<const float*>(w + cy.off_bhi) + (int64_t)f0 * cy.NT * kTileN * cy.LB,
+            reinterpret_cast<const float*>(w + cy.off_blo) + (int64_t)f0 * cy.NT * kTileN * cy.LB, L, Ne, Nm, cy.MT,
+            cy.NT, cy.KP, cy.LB, y.KPb, y.R_pad, Z);
+        CMC_CHECK_LAUNCH("z_gen_kernel");
+        CUtensorMap mA, mB;
+        if ((rc = make_kmajor_map(&mA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y.KPb, (int64_t)fc * y.S_pad, kPhM))) return rc;
+        if ((rc = make_kmajor_map(&mB, Z, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y.KPb, (int64_t)fc * y.R_pad, kPhN))) return rc;
+        PhaseParams p{};
+        p.F = fc; p.MT = y.MT; p.NT = y.NT; p.KB = y.KB; p.n_local = (int)n; p.n_pairs = y.n_pairs;
+        p.S_pad = y.S_pad; p.R_pad = y.R_pad;
+        p.coh_obs = coh_obs + (int64_t)f0 * y.n_pairs;
+        p.exceed = exceed + (int64_t)f0 * y.n_pairs;
+        p.max_u = max_u;
+        const int n_panels = fc * y.MT;
+        phase_gemm_kernel<<<n_panels < sms ? n_panels : sms, kPhThreads, smem, st>>>(mA, mB, p);
+        CMC_CHECK_LAUNCH("phase_gemm_kernel");
+    }
+    phase_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(max_u, n, max_stat);
+    CMC_CHECK_LAUNCH("phase_gather_kernel");
+    return CMC_OK;
+}
+
+}  // namespace cmc
+
+// host copy of the phase table as float pairs (cos, sin): lets callers / tests reproduce the surrogates
+extern "C" CMC_API int cmc_phase_table(float* out_host /* [4096][2] */) {
+    if (!out_host) return CMC_EINVAL;
+    for (int a = 0; a < cmc::kPhaseN; ++a) {
+        const double ang = 6.283185307179586476925286766559 * a / cmc::kPhaseN;
+        const uint32_t c = (uint32_t)cmc::host_bf16_rne((float)cos(ang)) << 16;
+        const uint32_t s = (uint32_t)cmc::host_bf16_rne((float)sin(ang)) << 16;
+        memcpy(out_host + 2 * a, &c, 4);
+        memcpy(out_host + 2 * a + 1, &s, 4);
+    }
+    return CMC_OK;
+}

@@ -23,15 +23,13 @@
 // overlaps the MMAs of tile t + 1.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "csd_layout.cuh"
 
 namespace cmc {
 
 using namespace tc;
 
 constexpr int kStages = 4;
-constexpr int kTileM = 128;
-constexpr int kTileN = 64;
-constexpr int kKBlock = 32;                     // floats per k-block = 128 bytes = one swizzle row
 constexpr int kABytes = kTileM * kKBlock * 4;   // 16 KB
 constexpr int kBBytes = kTileN * kKBlock * 4;   // 8 KB
 constexpr int kStagePitch = kTileN + 1;         // padded staging row (floats)
@@ -346,77 +344,6 @@ pack_kernel(const float2* __restrict__ S, int L, int F, int C, int64_t ld, const
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-struct CsdLayout {
-    int L, F, Ne, Nm, MT, NT, KP, LB;
-    int64_t a_elems, b_elems;          // floats per plane
-    int64_t off_pxx, off_pyy, off_ahi, off_alo, off_bhi, off_blo, off_bodd, total;
-};
-
-static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
-
-static CsdLayout csd_layout(int L, int F, int Ne, int Nm) {
-    CsdLayout y;
-    y.L = L; y.F = F; y.Ne = Ne; y.Nm = Nm;
-    y.MT = (Ne + 63) / 64;
-    y.NT = (Nm + 63) / 64;
-    y.KP = (int)align_up(2 * (int64_t)L, kKBlock);
-    y.LB = (int)align_up(2 * (int64_t)L + y.KP, kKBlock);
-    y.a_elems = (int64_t)F * y.MT * kTileM * y.KP;
-    y.b_elems = (int64_t)F * y.NT * kTileN * y.LB;
-    int64_t o = 0;
-    y.off_pxx = o; o = align_up(o + (int64_t)F * Ne * 4, 1024);
-    y.off_pyy = o; o = align_up(o + (int64_t)F * Nm * 4, 1024);
-    y.off_ahi = o; o = align_up(o + y.a_elems * 4, 1024);
-    y.off_alo = o; o = align_up(o + y.a_elems * 4, 1024);
-    y.off_bhi = o; o = align_up(o + y.b_elems * 4, 1024);
-    y.off_blo = o; o = align_up(o + y.b_elems * 4, 1024);
-    y.off_bodd = o; o = align_up(o + y.b_elems * 4, 1024);
-    y.total = o;
-    return y;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int get_encode_fn(EncodeTiledFn* fn) {
-    static EncodeTiledFn cached = nullptr;
-    if (!cached) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        int rc = check_cuda(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q),
-                            "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
-        if (rc) return rc;
-        if (q != cudaDriverEntryPointSuccess || !ptr) {
-            set_error("cuTensorMapEncodeTiled not available in this driver");
-            return CMC_ECUDA;
-        }
-        cached = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    *fn = cached;
-    return CMC_OK;
-}
-
-// 2-D K-major operand map: dim0 = row_len floats (contiguous), dim1 = rows; box = 32 floats x box_rows
-static int make_operand_map(CUtensorMap* m, const float* base, int64_t row_len, int64_t rows, int box_rows) {
-    EncodeTiledFn enc;
-    int rc = get_encode_fn(&enc);
-    if (rc) return rc;
-    cuuint64_t dims[2] = {(cuuint64_t)row_len, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)row_len * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d (row_len=%lld rows=%lld)", (int)r,
-                  (long long)row_len, (long long)rows);
-        return CMC_ECUDA;
-    }
-    return CMC_OK;
-}
-
 static size_t gemm_smem_bytes(int epi) {
     return 1024 + kStages * (kABytes + kBBytes) + sizeof(float) * kTileM * kStagePitch +
            (epi == 1 ? 64 * 64 * 4 : 0) + sizeof(GemmBarriers) + 16;
@@ -464,6 +391,11 @@ __global__ void shift_gather_kernel(const int32_t* __restrict__ shifts, int64_t 
         max_stat[i] = __uint_as_float(max_u[s]);
     }
 }
+
+int64_t phase_workspace_bytes(int L, int F, int Ne, int Nm, int64_t n_surr);
+int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
+                         const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2, int64_t ws2_bytes,
+                         cudaStream_t st);
 
 }  // namespace cmc
 
@@ -524,8 +456,10 @@ extern "C" int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne,
 
 extern "C" int64_t cmc_surrogate_workspace_bytes(int L, int F, int Ne, int Nm, int mode, int64_t n_surr) {
     (void)F; (void)Ne; (void)Nm; (void)n_surr;
+    if (L < 1 || F < 1 || Ne < 1 || Nm < 1 || n_surr < 0) return CMC_EINVAL;
     if (mode == CMC_SURR_SHIFT) return (int64_t)L * 12 + 256;
-    return CMC_EUNSUPPORTED;
+    if (mode == CMC_SURR_PHASE) return cmc::phase_workspace_bytes(L, F, Ne, Nm, n_surr);
+    return CMC_EINVAL;
 }
 
 extern "C" int cmc_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, int mode, int group,
@@ -533,15 +467,14 @@ extern "C" int cmc_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, 
                                   const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2,
                                   int64_t ws2_bytes, void* stream) {
     using namespace cmc;
-    (void)seed;
     CMC_REQUIRE(ws && coh_obs && exceed && max_stat && ws2, "cmc_surrogate_null: null pointer");
     CMC_REQUIRE(s_end >= s_begin, "cmc_surrogate_null: bad surrogate range");
     const int64_t n = s_end - s_begin;
     if (n == 0) return CMC_OK;
-    if (mode != CMC_SURR_SHIFT) {
-        set_error("cmc_surrogate_null: phase surrogates are not built yet");
-        return CMC_EUNSUPPORTED;
-    }
+    if (mode == CMC_SURR_PHASE)
+        return phase_surrogate_null(ws, L, F, Ne, Nm, seed, s_begin, s_end, coh_obs, exceed, max_stat, ws2, ws2_bytes,
+                                    static_cast<cudaStream_t>(stream));
+    CMC_REQUIRE(mode == CMC_SURR_SHIFT, "cmc_surrogate_null: unknown mode %d", mode);
     CMC_REQUIRE(shifts, "cmc_surrogate_null: shift mode needs a shift table");
     CMC_REQUIRE(group >= 1 && L % group == 0, "cmc_surrogate_null: group must divide L");
     const int n_pos = L / group;

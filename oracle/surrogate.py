@@ -14,8 +14,8 @@ cached spectra:
   phase  Y_s[l, f, :] = Y[l, f, :] * P[a(s, l, f)]    (one random phase per
          surrogate, segment and frequency, shared by all EMG channels, which
          preserves every auto-spectrum and the EMG inter-channel structure);
-         a = Philox4x32-10(key = seed, counter = (s, l, f, 0))[0] >> 20 indexes
-         a 4096-entry table P[a] = exp(2 pi i a / 4096) rounded to TF32.
+         a = Philox4x32-10(key = seed, counter = (s, l, f >> 2, 0))[f & 3] >> 20 indexes
+         a 4096-entry table P[a] = exp(2 pi i a / 4096) rounded to bfloat16.
 
   C_s = |sum_l conj(X) Y_s|^2 / (S_xx S_yy)   with the OBSERVED auto-spectra
   exceed[f,i,j] = #{s : C_s >= C_obs},  p = (1 + exceed) / (1 + n_surr)
@@ -64,21 +64,29 @@ def tf32_round(x: np.ndarray) -> np.ndarray:
     return u.astype(np.uint32).view(np.float32)
 
 
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even to bfloat16, returned as float32."""
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + np.uint64(0x7FFF) + ((u >> np.uint64(16)) & np.uint64(1))) & np.uint64(0xFFFF0000)
+    return u.astype(np.uint32).view(np.float32)
+
+
 def phase_table() -> np.ndarray:
-    """complex64 table P[a]; real and imaginary parts are TF32-representable."""
+    """complex64 table P[a]; real and imaginary parts are bfloat16-representable."""
     ang = 2.0 * np.pi * np.arange(N_PHASES) / N_PHASES
-    return (tf32_round(np.cos(ang).astype(np.float32))
-            + 1j * tf32_round(np.sin(ang).astype(np.float32))).astype(np.complex64)
+    return (bf16_round(np.cos(ang).astype(np.float32))
+            + 1j * bf16_round(np.sin(ang).astype(np.float32))).astype(np.complex64)
 
 
 def phase_indices(seed: int, s: np.ndarray, L: int, F: int) -> np.ndarray:
     """int32 (len(s), L, F) table indices for surrogates ``s`` (global indices)."""
     s = np.asarray(s, dtype=np.uint32)
-    S, Lg, Fg = np.meshgrid(s, np.arange(L, dtype=np.uint32), np.arange(F, dtype=np.uint32),
+    n_groups = (F + 3) // 4
+    S, Lg, Fg = np.meshgrid(s, np.arange(L, dtype=np.uint32), np.arange(n_groups, dtype=np.uint32),
                             indexing="ij")
-    r0, _, _, _ = philox4x32_10(S, Lg, Fg, np.zeros_like(S), seed & 0xFFFFFFFF,
-                                (seed >> 32) & 0xFFFFFFFF)
-    return (r0 >> np.uint32(32 - PHASE_BITS)).astype(np.int32)
+    words = philox4x32_10(S, Lg, Fg, np.zeros_like(S), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    idx = np.stack(words, axis=-1).reshape(len(s), L, n_groups * 4)[:, :, :F]
+    return (idx >> np.uint32(32 - PHASE_BITS)).astype(np.int32)
 
 
 def whiten(X: np.ndarray):
@@ -88,20 +96,34 @@ def whiten(X: np.ndarray):
     return X * scale[None], p
 
 
-def surrogate_coherence(Xw, Yw, mode: str, s_index, shifts=None, group: int = 1, seed: int = 0):
-    """fp64 coherence of the listed surrogates: (len(s_index), F, Ne, Nm)."""
+def surrogate_coherence(Xw, Yw, mode: str, s_index, shifts=None, group: int = 1, seed: int = 0, table=None,
+                        quantise_z: bool = False):
+    """fp64 coherence of the listed surrogates: (len(s_index), F, Ne, Nm).
+
+    ``quantise_z`` (phase mode): the cross-products Z[l,f,i,j] = conj(Xw) Yw are rounded to
+    bfloat16 before the phase-weighted sum - the operand precision of the tensor-core GEMM.  This is
+    part of the surrogate DEFINITION the CUDA path implements; against the unquantised sum it moves a
+    surrogate coherence by <~ 3e-3 |S| / sqrt(L)."""
     L, F, _ = Xw.shape
     out = []
-    table = phase_table().astype(np.complex128)
+    table = (phase_table() if table is None else np.asarray(table)).astype(np.complex128)
+    Z = None
+    if mode == "phase" and quantise_z:
+        Z = np.conj(Xw)[:, :, :, None] * Yw[:, :, None, :]
+        Z = bf16_round(Z.real.astype(np.float32)).astype(np.float64) + \
+            1j * bf16_round(Z.imag.astype(np.float32)).astype(np.float64)
     for s in np.asarray(s_index):
         if mode == "shift":
             Ys = np.roll(Yw, -int(shifts[s]) * group, axis=0)
+            sxy = np.einsum("lfi,lfj->fij", np.conj(Xw), Ys)
         elif mode == "phase":
             a = phase_indices(seed, np.array([s]), L, F)[0]
-            Ys = Yw * table[a][:, :, None]
+            if Z is not None:
+                sxy = np.einsum("lfij,lf->fij", Z, table[a])
+            else:
+                sxy = np.einsum("lfi,lfj->fij", np.conj(Xw), Yw * table[a][:, :, None])
         else:
             raise ValueError(mode)
-        sxy = np.einsum("lfi,lfj->fij", np.conj(Xw), Ys)
         out.append(np.minimum(np.abs(sxy) ** 2, 1.0))
     return np.stack(out)
 
