@@ -338,6 +338,32 @@ def main_gpu(args):
                              "measured dense bf16 figure"},
     }
 
+    # ---- stage: phase-randomised surrogates (config 3 count per rank-shard of config 5's 10,000) ----
+    n_phase = 10000
+    sb, se = cdist.shard_range(n_phase, rank, world)
+    for _ in range(1):
+        K.surrogate_null(res, K.SURR_PHASE, sb, se, seed=7)
+    barrier()
+    e0.record()
+    ex_p, ms_p = K.surrogate_null(res, K.SURR_PHASE, sb, se, seed=7)
+    cdist.all_reduce_sum_(ex_p)
+    ms_all = cdist.all_gather_ranges(ms_p, n_phase)
+    e1.record()
+    barrier()
+    ph_ms = max_over_ranks(e0.elapsed_time(e1))
+    kpb = ((2 * L + 63) // 64) * 64
+    ph_flop = 2.0 * (se - sb) * (2 * NE * NM) * kpb * F                    # executed bf16 flop on this rank
+    stages["surrogate_null_phase"] = {
+        "metric": "surrogates_per_s", "value": n_phase / (ph_ms / 1e3), "unit": "surrogates/s", "ms": ph_ms,
+        "scaling": "strong",
+        "config": f"config 5 count: {n_phase} phase-randomised surrogates of one 64x64xF=100 subject-condition "
+                  f"sharded over {world} rank(s) (Philox phases + bf16 Z operands generated in the timed region; "
+                  f"counts all-reduced, max-stat all-gathered)",
+        "roofline": {"bound": "tensor", "achieved": ph_flop / (ph_ms * 1e-3) / 1e12, "peak": bf16,
+                     "unit": "TFLOP/s", "frac": ph_flop / (ph_ms * 1e-3) / 1e12 / bf16,
+                     "note": "executed bf16 flop (K padded to 64) vs measured dense bf16 peak"},
+    }
+
     # ---- stage: CBPA permutations (config 4 geometry, config 5 count sharded over the ranks) ----
     from multimodal_biosignal_analysis_b200.cbpa import combine_adjacency, find_ch_adjacency_from_positions
     adj = combine_adjacency(CBPA_SHAPE[1], find_ch_adjacency_from_positions(syn.sensor_positions(CBPA_SHAPE[2])))

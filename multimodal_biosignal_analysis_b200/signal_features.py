@@ -348,11 +348,13 @@ def max_cmc_spectrograms_over_channels(cmc_array, cmc_array_lower_ci=None, cmc_a
 
 def _build_task_window_mask(time_centers_sec, log_frame, pre_buffer_sec: float, post_buffer_sec: float):
     """signal_features.py:842-895.  The trial-log parsing lives in the reference's pandas glue
-    (``data_integration`` / ``data_analysis``, out of scope); they are resolved lazily so that the
-    reference's own modules (or test doubles patched onto this module) supply them."""
+    (``data_integration``, out of scope); it is resolved lazily so that the reference's own module
+    (or test doubles patched onto this module) supplies it."""
     import pandas as pd
     measurement_start, _ = data_integration.get_qtc_measurement_start_end(log_frame)
-    measurement_start_aware = data_analysis.make_timezone_aware(pd.Timestamp(measurement_start))
+    measurement_start_aware = pd.Timestamp(measurement_start)
+    if measurement_start_aware.tzinfo is None:      # data_analysis.make_timezone_aware: naive -> UTC
+        measurement_start_aware = measurement_start_aware.tz_localize('utc')
     trial_start_ends = data_integration.get_all_task_start_ends(log_frame, output_type='list')
     mask = np.zeros(len(time_centers_sec), dtype=bool)
     for trial_start, trial_end in trial_start_ends:
@@ -366,39 +368,31 @@ def _build_task_window_mask(time_centers_sec, log_frame, pre_buffer_sec: float, 
     return mask
 
 
-class _LazyReferenceModule:
-    """Resolves ``src.pipeline.<name>`` of the reference on first attribute access."""
-
-    def __init__(self, name):
-        self.__dict__["_name"] = name
-        self.__dict__["_mod"] = None
-
-    def _resolve(self):
-        if self.__dict__["_mod"] is None:
-            import importlib
-            try:
-                self.__dict__["_mod"] = importlib.import_module(f"src.pipeline.{self._name}")
-            except Exception as exc:  # pragma: no cover - depends on the caller's environment
-                raise ImportError(
-                    f"log_frame handling needs the reference's src.pipeline.{self._name} "
-                    f"(pandas glue, out of scope of this package); pass window masks instead") from exc
-        return self.__dict__["_mod"]
-
-    def __getattr__(self, item):
-        return getattr(self._resolve(), item)
-
-    def __setattr__(self, key, value):       # lets tests monkeypatch functions without the reference
-        if self.__dict__["_mod"] is None:
-            try:
-                self._resolve()
-            except ImportError:
-                import types
-                self.__dict__["_mod"] = types.SimpleNamespace()
-        setattr(self.__dict__["_mod"], key, value)
+def _reference_glue(name: str):
+    """The trial-log parsers are pandas / experiment-log glue of the reference
+    (``src/pipeline/data_integration.py:717,766``), outside this package's scope: delegate to the
+    reference's module when it is importable, otherwise fail when CALLED (not at import)."""
+    def call(*args, **kwargs):
+        import importlib
+        try:
+            mod = importlib.import_module("src.pipeline.data_integration")
+        except Exception as exc:
+            raise ImportError(
+                f"log_frame handling needs the reference's src.pipeline.data_integration.{name} "
+                "(pandas glue, out of scope of this package); pass window masks instead") from exc
+        return getattr(mod, name)(*args, **kwargs)
+    call.__name__ = name
+    return call
 
 
-data_integration = _LazyReferenceModule("data_integration")
-data_analysis = _LazyReferenceModule("data_analysis")
+class _DataIntegrationShim:
+    """Namespace with the two functions ``_build_task_window_mask`` needs; tests and callers may
+    replace them (``monkeypatch.setattr(features.data_integration, ...)`` as the reference's tests do)."""
+    get_all_task_start_ends = staticmethod(_reference_glue("get_all_task_start_ends"))
+    get_qtc_measurement_start_end = staticmethod(_reference_glue("get_qtc_measurement_start_end"))
+
+
+data_integration = _DataIntegrationShim()
 
 
 def compute_task_wise_aggregated_cmc(
@@ -468,6 +462,16 @@ def compute_task_wise_aggregated_cmc(
     if use_jackknife:
         values_lower = output_dict['coherence_ci_lower']
         values_upper = output_dict['coherence_ci_upper']
+    if np.ndim(values) == 4:
+        # a caller-substituted MSC function returned the un-reduced (W, F, Ne, Nm) tensors:
+        # reduce them exactly like the reference does (:975-1002)
+        if enforce_independence_threshold:
+            values = np.where(output_dict['coherence_significant'], values, 0.0)
+        if use_jackknife:
+            values, values_lower, values_upper = max_cmc_spectrograms_over_channels(
+                values, values_lower, values_upper, channel_ax=3, verbose=True)
+        else:
+            values = max_cmc_spectrograms_over_channels(values, channel_ax=3, verbose=True)
 
     if save_dir is not None:
         channel_suffix = (f"Channels_{'_'.join(eeg_channel_subset)}" if eeg_channel_subset else "All_Channels")
