@@ -23,6 +23,20 @@ constexpr int kPtsPerThread = 16;    // complex points per thread (x 2 channels)
 
 // byte offset of raw sample (row n, channel pair cp) inside the TMA-written tile (SWIZZLE_64B: address bits
 // [4,6) ^= bits [7,9))
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 template <bool SWZ>
 __device__ __forceinline__ uint32_t raw_off(int n, int cp) {
     const uint32_t lin = (uint32_t)n * 32u + (uint32_t)cp * 8u;
@@ -34,19 +48,24 @@ __device__ __forceinline__ uint32_t pt_off(int p, int cp) {
     return (uint32_t)(p ^ ((p >> 4) & 1)) * 64u + (uint32_t)cp * 16u;
 }
 
+// Row swizzle p -> p ^ ((p >> 4) & 1) commutes with adding multiples of 32 rows, so it is applied once per
+// butterfly (all strides used after the first pass are multiples of 32 rows for M >= 512).
 template <int M, int R, int NS>
-__device__ __forceinline__ void pass_pair(unsigned char* buf, const float2* __restrict__ twM, int tid) {
+__device__ __forceinline__ void pass_pair(uint32_t sbuf, const float2* __restrict__ twM, int tid) {
     constexpr int NT = M / 4;
     constexpr int B = kPtsPerThread / R;
     constexpr int STRIDE = M / R;
+    constexpr bool kHoist = (STRIDE % 32 == 0) && (NS % 32 == 0 || NS >= 32);
     float2 va[B][R], vb[B][R];
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const int q = tid + b * NT;
         const int cp = q & 3, j = q >> 2;
+        const uint32_t base = sbuf + pt_off(j, cp);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const float4 t = *reinterpret_cast<const float4*>(buf + pt_off(j + r * STRIDE, cp));
+            const float4 t = lds128(STRIDE % 32 == 0 ? base + (uint32_t)(r * STRIDE) * 64u
+                                                     : sbuf + pt_off(j + r * STRIDE, cp));
             va[b][r] = make_float2(t.x, t.y);
             vb[b][r] = make_float2(t.z, t.w);
         }
@@ -62,12 +81,14 @@ __device__ __forceinline__ void pass_pair(unsigned char* buf, const float2* __re
         const int cp = q & 3, j = q >> 2;
         const int k = j % NS;
         const int j0 = (j / NS) * (NS * R) + k;
+        const uint32_t base = sbuf + pt_off(j0, cp);
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            *reinterpret_cast<float4*>(buf + pt_off(j0 + r * NS, cp)) =
-                make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y);
+            sts128(NS % 32 == 0 ? base + (uint32_t)(r * NS) * 64u : sbuf + pt_off(j0 + r * NS, cp),
+                   make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
     }
     __syncthreads();
+    (void)kHoist;
 }
 
 template <int M, bool SWZ>
@@ -75,7 +96,7 @@ __global__ void __launch_bounds__(M / 4, (M / 4) <= 256 ? 2 : 1)
 fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
                         const int64_t* __restrict__ seg_starts, const float* __restrict__ windows, int n_win,
                         int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
-                        const float2* __restrict__ twM, const float2* __restrict__ twN) {
+                        const float2* __restrict__ twM, const float2* __restrict__ twN, int dbg) {
     constexpr int N = 2 * M;
     constexpr int NT = M / 4;
     constexpr int R0 = Plan<M>::R0, R1 = Plan<M>::R1, R2 = Plan<M>::R2;
@@ -88,6 +109,7 @@ fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
     float* mean_s = part + (NT / 32) * kTmaCT;                       // [8]
     uint64_t* bar = reinterpret_cast<uint64_t*>(mean_s + kTmaCT);
 
+    const uint32_t sbuf = smem_u32(buf);
     const int tid = threadIdx.x;
     const int seg = blockIdx.x;
     const int c0 = blockIdx.y * kTmaCT;
@@ -101,14 +123,15 @@ fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
 
     for (int kw = 0; kw < n_win; ++kw) {
         // ---- TMA: raw tile -> shared memory (N rows of 32 bytes, boxes of 256 rows) ----
-        if (tid == 0) {
+        if (tid == 0 && !(dbg & 1)) {
             fence_proxy_async();                       // earlier generic-proxy accesses before async-proxy writes
             mbar_arrive_expect_tx(bar, N * 32);
 #pragma unroll 1
             for (int i = 0; i < N / kRowsPerBox; ++i)
                 tma_load_2d(buf + i * kRowsPerBox * 32, &tmap, bar, c0, start + i * kRowsPerBox);
         }
-        mbar_wait(bar, kw & 1);
+        if (!(dbg & 1)) mbar_wait(bar, kw & 1);
+        if (dbg & 2) { __syncthreads(); continue; }
 
         const float* win = windows + (int64_t)kw * N;
         float2 va[B0][R0], vb[B0][R0];
@@ -119,8 +142,8 @@ fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
 #pragma unroll
             for (int r = 0; r < R0; ++r) {
                 const int n0 = 2 * (j + r * S0);
-                const float2 re = *reinterpret_cast<const float2*>(buf + raw_off<SWZ>(n0, cp));       // x[2p][c], x[2p][c+1]
-                const float2 im = *reinterpret_cast<const float2*>(buf + raw_off<SWZ>(n0 + 1, cp));   // x[2p+1][..]
+                const float2 re = lds64(sbuf + raw_off<SWZ>(n0, cp));       // x[2p][c], x[2p][c+1]
+                const float2 im = lds64(sbuf + raw_off<SWZ>(n0 + 1, cp));   // x[2p+1][c], x[2p+1][c+1]
                 va[b][r] = make_float2(re.x, im.x);
                 vb[b][r] = make_float2(re.y, im.y);
             }
@@ -171,22 +194,22 @@ fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
             }
             dft<R0>(va[b]);
             dft<R0>(vb[b]);
+            // rows j * R0 + r: the swizzle bit is (j & 1) when R0 == 16, and r only enters through its low bit
 #pragma unroll
             for (int r = 0; r < R0; ++r)
-                *reinterpret_cast<float4*>(buf + pt_off(j * R0 + r, cp)) =
-                    make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y);
+                sts128(sbuf + pt_off(j * R0 + r, cp), make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
         }
         __syncthreads();
-        if (R1 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(buf, twM, tid);
-        if (R2 > 1) pass_pair<M, (R2 > 1 ? R2 : 2), R0 * R1>(buf, twM, tid);
+        if (R1 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(sbuf, twM, tid);
+        if (R2 > 1) pass_pair<M, (R2 > 1 ? R2 : 2), R0 * R1>(sbuf, twM, tid);
 
         // ---- real-FFT split for the requested bins; 2 channels = 16 bytes per lane ----
         float2* out = spec + ((int64_t)(seg * n_win + kw) * F) * spec_ld + c0;
         for (int q = tid; q < F * 4; q += NT) {
             const int cp = q & 3, bi = q >> 2;
             const int b = bin_lo + bi;
-            const float4 A = *reinterpret_cast<const float4*>(buf + pt_off(b & (M - 1), cp));
-            const float4 Bz = *reinterpret_cast<const float4*>(buf + pt_off((M - b) & (M - 1), cp));
+            const float4 A = lds128(sbuf + pt_off(b & (M - 1), cp));
+            const float4 Bz = lds128(sbuf + pt_off((M - b) & (M - 1), cp));
             const float2 w = __ldg(twN + b);
             float2 X[2];
 #pragma unroll
@@ -222,7 +245,8 @@ static int launch_tma(const CUtensorMap& tmap, int n_ch, const int64_t* seg_star
     int rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
     if (rc) return rc;
     dim3 grid(n_seg, (n_ch + kTmaCT - 1) / kTmaCT);
-    kern<<<grid, NT, smem, st>>>(tmap, n_ch, seg_starts, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN);
+    static const int dbg = getenv("CMC_FFT_DBG") ? atoi(getenv("CMC_FFT_DBG")) : 0;
+    kern<<<grid, NT, smem, st>>>(tmap, n_ch, seg_starts, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, dbg);
     CMC_CHECK_LAUNCH("fft_segments_tma_kernel");
     return CMC_OK;
 }
