@@ -118,8 +118,8 @@ CMC_API int cmc_msc_windows_maxemg(const float* X, const float* Y, int W, int K,
  *   coh [F][Ne][Nm] float32 = clip(|sum_l conj(X) Y|^2 / (Sxx Syy), 0, 1)
  *   sxx [F][Ne], syy [F][Nm] float32 = sum_l |.|^2           (may be NULL)
  *   sxy [F][Ne][Nm] complex64 un-normalised cross spectrum    (may be NULL)
- *   ws  scratch of cmc_csd_workspace_bytes(); on return it holds the whitened TF32
- *       operands that cmc_surrogate_null() consumes.
+ *   ws  scratch of cmc_csd_workspace_bytes(); on return it holds the TF32 operand planes and
+ *       auto-spectra that cmc_surrogate_null() consumes (and extends with shifted views).
  * ---------------------------------------------------------------------------------- */
 CMC_API int64_t cmc_csd_workspace_bytes(int L, int F, int Ne, int Nm);
 CMC_API int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne, int Nm,
@@ -147,7 +147,7 @@ CMC_API int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne, in
 /* host copy of the phase table P[a] = (bf16(cos), bf16(sin)) of 2 pi a / 4096 as float pairs [4096][2] */
 CMC_API int cmc_phase_table(float* out_host);
 CMC_API int64_t cmc_surrogate_workspace_bytes(int L, int F, int Ne, int Nm, int mode, int64_t n_surr);
-CMC_API int cmc_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, int mode, int group,
+CMC_API int cmc_surrogate_null(void* ws, int L, int F, int Ne, int Nm, int mode, int group,
                        const int32_t* shifts, uint64_t seed, int64_t s_begin, int64_t s_end,
                        const float* coh_obs, uint32_t* exceed, float* max_stat,
                        void* ws2, int64_t ws2_bytes, void* stream);

@@ -9,10 +9,16 @@ constexpr int kKBlock = 32;                     // floats per k-block = 128 byte
 constexpr int kTileM = 128;
 constexpr int kTileN = 64;
 
+// Workspace of one pooled-CSD problem.  Operands are K-major (K = (segment, re/im) contiguous), UNSCALED TF32
+// splits of the spectra; the normalisation by the auto-spectra happens in the GEMM epilogues.
+//   A_hi / A_lo [F][MT*128][KP]  rows r < 64: X of channel mt*64 + r, rows 64 + r: i * X
+//   B_hi / B_lo [F][NT*64][KP]   rows: Y
+//   B_dbl / B_odd [F][NT*64][LB] shift-surrogate views, built on demand: [Y | Y | 0..] and the same advanced by
+//                                one complex element (TMA boxes must start 16-byte aligned)
 struct CsdLayout {
     int L, F, Ne, Nm, MT, NT, KP, LB;
-    int64_t a_elems, b_elems;          // floats per plane
-    int64_t off_pxx, off_pyy, off_ahi, off_alo, off_bhi, off_blo, off_bodd, total;
+    int64_t a_elems, b_elems, bs_elems;          // floats per plane
+    int64_t off_pxx, off_pyy, off_ahi, off_alo, off_bhi, off_blo, off_bdbl, off_bodd, total;
 };
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -25,7 +31,8 @@ inline CsdLayout csd_layout(int L, int F, int Ne, int Nm) {
     y.KP = (int)align_up(2 * (int64_t)L, kKBlock);
     y.LB = (int)align_up(2 * (int64_t)L + y.KP, kKBlock);
     y.a_elems = (int64_t)F * y.MT * kTileM * y.KP;
-    y.b_elems = (int64_t)F * y.NT * kTileN * y.LB;
+    y.b_elems = (int64_t)F * y.NT * kTileN * y.KP;
+    y.bs_elems = (int64_t)F * y.NT * kTileN * y.LB;
     int64_t o = 0;
     y.off_pxx = o; o = align_up(o + (int64_t)F * Ne * 4, 1024);
     y.off_pyy = o; o = align_up(o + (int64_t)F * Nm * 4, 1024);
@@ -33,7 +40,8 @@ inline CsdLayout csd_layout(int L, int F, int Ne, int Nm) {
     y.off_alo = o; o = align_up(o + y.a_elems * 4, 1024);
     y.off_bhi = o; o = align_up(o + y.b_elems * 4, 1024);
     y.off_blo = o; o = align_up(o + y.b_elems * 4, 1024);
-    y.off_bodd = o; o = align_up(o + y.b_elems * 4, 1024);
+    y.off_bdbl = o; o = align_up(o + y.bs_elems * 4, 1024);
+    y.off_bodd = o; o = align_up(o + y.bs_elems * 4, 1024);
     y.total = o;
     return y;
 }

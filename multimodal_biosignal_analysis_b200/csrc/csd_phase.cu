@@ -112,22 +112,26 @@ phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_be
 // grid (F, Ne); block 256: the thread block holds Xh row i in shared memory and sweeps j.
 __global__ void __launch_bounds__(256)
 z_gen_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo, const float* __restrict__ Bhi,
-             const float* __restrict__ Blo, int L, int Ne, int Nm, int MT, int NT, int KP, int LB, int KPb,
-             int R_pad, __nv_bfloat16* __restrict__ Z) {
+             const float* __restrict__ Blo, const float* __restrict__ pxx, const float* __restrict__ pyy, int L, int Ne,
+             int Nm, int MT, int NT, int KP, int LB, int KPb, int R_pad, __nv_bfloat16* __restrict__ Z) {
     extern __shared__ float2 xs[];                      // [KPb / 2] complex Xh[l][i]
     const int f = blockIdx.x, i = blockIdx.y;
     const int half = KPb / 2;
     const float* ah = Ahi + ((int64_t)(f * MT + (i >> 6)) * kTileM + (i & 63)) * KP;
     const float* al = Alo + ((int64_t)(f * MT + (i >> 6)) * kTileM + (i & 63)) * KP;
+    const float px = pxx[(int64_t)f * Ne + i];
+    const float sx = px > 0.f ? rsqrtf(px) : 0.f;                // whitening: Xh = X / sqrt(Pxx)
     for (int l = threadIdx.x; l < half; l += blockDim.x) {
         float2 v = make_float2(0.f, 0.f);
-        if (l < L) v = make_float2(ah[2 * l] + al[2 * l], ah[2 * l + 1] + al[2 * l + 1]);
+        if (l < L) v = make_float2((ah[2 * l] + al[2 * l]) * sx, (ah[2 * l + 1] + al[2 * l + 1]) * sx);
         xs[l] = v;
     }
     __syncthreads();
     for (int j = 0; j < Nm; ++j) {
         const float* bh = Bhi + ((int64_t)(f * NT + (j >> 6)) * kTileN + (j & 63)) * LB;
         const float* bl = Blo + ((int64_t)(f * NT + (j >> 6)) * kTileN + (j & 63)) * LB;
+        const float py = pyy[(int64_t)f * Nm + j];
+        const float sy = py > 0.f ? rsqrtf(py) : 0.f;
         const int p = i * Nm + j;
         const int64_t row_re = (int64_t)f * R_pad + (p / kPhPairs) * kPhN + (p % kPhPairs);
         uint32_t* zre = reinterpret_cast<uint32_t*>(Z + row_re * KPb);
@@ -136,7 +140,7 @@ z_gen_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo, const
             float zr = 0.f, zi = 0.f;
             if (l < L) {
                 const float2 x = xs[l];
-                const float yr = bh[2 * l] + bl[2 * l], yi = bh[2 * l + 1] + bl[2 * l + 1];
+                const float yr = (bh[2 * l] + bl[2 * l]) * sy, yi = (bh[2 * l + 1] + bl[2 * l + 1]) * sy;
                 zr = x.x * yr + x.y * yi;          // conj(x) * y
                 zi = x.x * yi - x.y * yr;
             }
@@ -395,9 +399,11 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
         z_gen_kernel<<<dim3(fc, Ne), 256, (size_t)y.KPb * 4, st>>>(
             reinterpret_cast<const float*>(w + cy.off_ahi) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_alo) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
-            reinterpret_cast<const float*>(w + cy.off_bhi) + (int64_t)f0 * cy.NT * kTileN * cy.LB,
-            reinterpret_cast<const float*>(w + cy.off_blo) + (int64_t)f0 * cy.NT * kTileN * cy.LB, L, Ne, Nm, cy.MT,
-            cy.NT, cy.KP, cy.LB, y.KPb, y.R_pad, Z);
+            reinterpret_cast<const float*>(w + cy.off_bhi) + (int64_t)f0 * cy.NT * kTileN * cy.KP,
+            reinterpret_cast<const float*>(w + cy.off_blo) + (int64_t)f0 * cy.NT * kTileN * cy.KP,
+            reinterpret_cast<const float*>(w + cy.off_pxx) + (int64_t)f0 * Ne,
+            reinterpret_cast<const float*>(w + cy.off_pyy) + (int64_t)f0 * Nm, L, Ne, Nm, cy.MT, cy.NT, cy.KP, cy.KP,
+            y.KPb, y.R_pad, Z);
         CMC_CHECK_LAUNCH("z_gen_kernel");
         CUtensorMap mA, mB;
         if ((rc = make_kmajor_map(&mA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y.KPb, (int64_t)fc * y.S_pad, kPhM))) return rc;

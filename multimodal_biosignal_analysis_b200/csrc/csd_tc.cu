@@ -5,22 +5,24 @@
 //
 // Replaces signal_features.py:750-770 for averages over L segments / windows x tapers.
 //
-// Formulation.  Spectra are pre-whitened per (frequency, channel): Xh = X / sqrt(sum_l |X|^2), so
-// coherence is |sum_l conj(Xh) Yh|^2 and the TF32 inputs are scale free.  The complex contraction is
-// one real GEMM per frequency with K = (l, re/im) contiguous ("K-major" = complex64 memory order):
-//     A rows 0..63   = Xh            (re, im interleaved along K)
-//     A rows 64..127 = i * Xh        (-im, re)
-//     B rows         = Yh
+// Formulation.  The complex contraction is one real GEMM per frequency with K = (l, re/im) contiguous
+// ("K-major" = complex64 memory order along the segment axis):
+//     A rows 0..63   = X             (re, im interleaved along K)
+//     A rows 64..127 = i * X         (-im, re)
+//     B rows         = Y
 //     D[i][j] = Re S_ij,  D[64 + i][j] = Im S_ij            (M = 128, N = 64, K = 2L)
-// The observed pass is error-compensated 3xTF32 (hi*hi + hi*lo + lo*hi with hi = tf32(x),
-// lo = tf32(x - hi)), which keeps |dC| ~ 1e-6; it is HBM bound, so the extra MMAs are free.
-// Shift surrogates read the B operand at K offset 2 * shift * group from a doubled row
-// [Yh | Yh | 0...] - a TMA coordinate, no data movement - and use a single TF32 term.
+// and the epilogue normalises with the auto-spectra: C = |S / sqrt(Pxx) / sqrt(Pyy)|^2 (TF32 is a floating
+// format, so unscaled operands lose nothing).  One fused pack kernel transposes the spectra into the K-major
+// operand rows, splits them into TF32 hi/lo planes and accumulates Pxx / Pyy on the way (one read of the spectra).
+// The observed pass is error-compensated 3xTF32 (hi*hi + hi*lo + lo*hi with hi = tf32(x), lo = tf32(x - hi)):
+// every pipeline stage carries the four tiles A_hi, A_lo, B_hi, B_lo of one k-block, so each operand byte is
+// fetched once; |dC| ~ 2e-6 and the pass stays HBM bound.
+// Shift surrogates read the B operand at K offset 2 * shift * group from a doubled row [Y | Y | 0...] - a TMA
+// coordinate, no data movement - and use a single TF32 term.
 //
-// Pipeline per CTA (persistent over a contiguous tile range): warp 0 = TMA producer, warp 1 = MMA
-// issuer (one thread), warp 2 = TMEM allocator, warps 4-7 = epilogue.  4-stage smem ring
-// (full/empty mbarriers), 2 TMEM accumulators (tmem_full/tmem_empty) so the epilogue of tile t
-// overlaps the MMAs of tile t + 1.
+// Pipeline per CTA (persistent over a contiguous tile range): warp 0 = TMA producer, warp 1 = MMA issuer (one
+// thread), warp 2 = TMEM allocator, warps 4-7 = epilogue.  mbarrier ring of smem stages (full/empty), 2 TMEM
+// accumulators (tmem_full/tmem_empty) so the epilogue of tile t overlaps the MMAs of tile t + 1.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "csd_layout.cuh"
@@ -29,7 +31,7 @@ namespace cmc {
 
 using namespace tc;
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 constexpr int kABytes = kTileM * kKBlock * 4;   // 16 KB
 constexpr int kBBytes = kTileN * kKBlock * 4;   // 8 KB
 constexpr int kStagePitch = kTileN + 1;         // padded staging row (floats)
@@ -64,8 +66,8 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const CsdParams& p
 }
 
 struct __align__(8) GemmBarriers {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
@@ -80,9 +82,11 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    unsigned char* sA = base;                                   // [kStages][16 KB]
-    unsigned char* sB = base + kStages * kABytes;               // [kStages][8 KB]
-    float* stage_tile = reinterpret_cast<float*>(sB + kStages * kBBytes);          // [128][65]
+    // EPI 0 (3xTF32): 3 stages of {A_hi, A_lo, B_hi, B_lo} = 48 KB; EPI 1 (one term): 4 stages of {A_hi, B} = 24 KB
+    constexpr int kStages = EPI == 0 ? 3 : 4;
+    constexpr int kStageBytes = EPI == 0 ? 2 * (kABytes + kBBytes) : (kABytes + kBBytes);
+    unsigned char* sS = base;                                   // [kStages][kStageBytes]
+    float* stage_tile = reinterpret_cast<float*>(sS + kStages * kStageBytes);      // [128][65]
     uint32_t* cnt = reinterpret_cast<uint32_t*>(stage_tile + kTileM * kStagePitch);  // [64*64] (EPI 1)
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(cnt + (EPI == 1 ? 64 * 64 : 0));
 
@@ -91,7 +95,7 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
     const long long t1 = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
@@ -111,7 +115,6 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    const int n_v = p.nterms * p.KB;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -128,13 +131,18 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
                 off -= odd ? 2 : 0;
                 const int arow = (c.f * p.MT + c.mt) * kTileM;
                 const int brow = (c.f * p.NT + c.nt) * kTileN;
-                for (int v = 0; v < n_v; ++v) {
-                    const int term = v / p.KB, kb = v - term * p.KB;
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    unsigned char* st = sS + stage * kStageBytes;
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&bars->full[stage], kABytes + kBBytes);
-                    tma_load_2d(sA + stage * kABytes, term == 2 ? &mAlo : &mAhi, &bars->full[stage], kb * kKBlock, arow);
-                    tma_load_2d(sB + stage * kBBytes, odd ? &mBodd : (term == 1 ? &mBlo : &mBhi), &bars->full[stage],
-                                off + kb * kKBlock, brow);
+                    mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+                    tma_load_2d(st, &mAhi, &bars->full[stage], kb * kKBlock, arow);
+                    if (EPI == 0) {
+                        tma_load_2d(st + kABytes, &mAlo, &bars->full[stage], kb * kKBlock, arow);
+                        tma_load_2d(st + 2 * kABytes, &mBhi, &bars->full[stage], kb * kKBlock, brow);
+                        tma_load_2d(st + 2 * kABytes + kBBytes, &mBlo, &bars->full[stage], kb * kKBlock, brow);
+                    } else {
+                        tma_load_2d(st + kABytes, odd ? &mBodd : &mBhi, &bars->full[stage], off + kb * kKBlock, brow);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -153,15 +161,26 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
                 mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * kTileN;
-                for (int v = 0; v < n_v; ++v) {
+                for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA + stage * kABytes);
-                    const uint32_t b0 = smem_u32(sB + stage * kBBytes);
+                    const uint32_t s0 = smem_u32(sS + stage * kStageBytes);
+                    if (EPI == 0) {
+                        const uint32_t ahi = s0, alo = s0 + kABytes, bhi = s0 + 2 * kABytes, blo = bhi + kBBytes;
 #pragma unroll
-                    for (int k = 0; k < kKBlock / 8; ++k)
-                        umma_tf32(d, make_smem_desc_k_sw128(a0 + k * 32), make_smem_desc_k_sw128(b0 + k * 32), idesc,
-                                  (v | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kKBlock / 8; ++k) {
+                            const uint64_t dah = make_smem_desc_k_sw128(ahi + k * 32), dal = make_smem_desc_k_sw128(alo + k * 32);
+                            const uint64_t dbh = make_smem_desc_k_sw128(bhi + k * 32), dbl = make_smem_desc_k_sw128(blo + k * 32);
+                            umma_tf32(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);      // small terms first
+                            umma_tf32(d, dah, dbl, idesc, 1u);
+                            umma_tf32(d, dah, dbh, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kKBlock / 8; ++k)
+                            umma_tf32(d, make_smem_desc_k_sw128(s0 + k * 32), make_smem_desc_k_sw128(s0 + kABytes + k * 32),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit(&bars->empty[stage]);      // frees the smem slot when these MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -223,14 +242,15 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
                 if (i < p.Ne && j < p.Nm) {
                     const float re = stage_tile[il * kStagePitch + jl];
                     const float im = stage_tile[(64 + il) * kStagePitch + jl];
-                    const float cval = fminf(re * re + im * im, 1.0f);
+                    const float px = __ldg(p.pxx + c.f * p.Ne + i), py = __ldg(p.pyy + c.f * p.Nm + j);
+                    // |S|^2 / (Pxx Pyy) as |S / sqrt(Pxx) / sqrt(Pyy)|^2: no overflow, zero-power channels give 0
+                    const float sc = (px > 0.f && py > 0.f) ? rsqrtf(px) * rsqrtf(py) : 0.f;
+                    const float a = re * sc, b = im * sc;
+                    const float cval = fminf(a * a + b * b, 1.0f);
                     const long long o = ((long long)c.f * p.Ne + i) * p.Nm + j;
                     if (EPI == 0) {
                         p.coh[o] = cval;
-                        if (p.sxy) {
-                            const float s = sqrtf(p.pxx[c.f * p.Ne + i]) * sqrtf(p.pyy[c.f * p.Nm + j]);
-                            p.sxy[o] = make_float2(re * s, im * s);
-                        }
+                        if (p.sxy) p.sxy[o] = make_float2(re, im);
                     } else {
                         if (cval >= __ldg(p.coh_obs + o)) cnt[idx] += mult;
                         vmax = fmaxf(vmax, cval);
@@ -260,104 +280,116 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------
-// P[f][c] = sum_l |S[l][f][c]|^2, fixed summation order (deterministic)
+// Fused pack: transposes S[l][f][c] into K-major TF32 hi/lo operand rows (unscaled) and accumulates the
+// auto-spectra P[f][c] = sum_l |S|^2 in a fixed order (deterministic) - one read of the spectra.
+// grid (F, 2*MT + 2*NT): blockIdx.y < 2*MT -> 32 EEG channels (A rows: X and i*X), else 32 EMG channels (B rows).
+// block (32, 8).  Columns k >= 2L are written as zeros.
 __global__ void __launch_bounds__(256)
-power_kernel(const float2* __restrict__ S, int L, int F, int C, int64_t ld, float* __restrict__ P) {
+pack_fused_kernel(const float2* __restrict__ X, int64_t ldx, int Ne, const float2* __restrict__ Y, int64_t ldy, int Nm,
+                  int L, int F, int MT, int NT, int KP, float* __restrict__ Ahi, float* __restrict__ Alo,
+                  float* __restrict__ Bhi, float* __restrict__ Blo, float* __restrict__ pxx, float* __restrict__ pyy,
+                  float* __restrict__ sxx_out, float* __restrict__ syy_out) {
+    __shared__ float2 tile[32][33];       // [l][channel]
     __shared__ float part[8][33];
-    const int f = blockIdx.x, c = blockIdx.y * 32 + threadIdx.x, ly = threadIdx.y;
-    float acc = 0.f;
-    if (c < C)
-        for (int l = ly; l < L; l += 8) {
-            const float2 v = __ldg(S + ((int64_t)l * F + f) * ld + c);
-            acc += v.x * v.x + v.y * v.y;
+    const int f = blockIdx.x, tx = threadIdx.x, ty = threadIdx.y;
+    const bool is_a = (int)blockIdx.y < 2 * MT;
+    const int ct = is_a ? blockIdx.y : blockIdx.y - 2 * MT;      // 32-channel tile of this operand
+    const float2* S = is_a ? X : Y;
+    const int64_t ld = is_a ? ldx : ldy;
+    const int C = is_a ? Ne : Nm;
+    const int ch_ld = ct * 32 + tx;                               // channel loaded by this thread
+    float pw = 0.f;
+    for (int l0 = 0; l0 < KP / 2; l0 += 32) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const int l = l0 + ty + 8 * n;
+            float2 v = make_float2(0.f, 0.f);
+            if (l < L && ch_ld < C) v = __ldg(S + ((int64_t)l * F + f) * ld + ch_ld);
+            pw += v.x * v.x + v.y * v.y;
+            tile[ty + 8 * n][tx] = v;
         }
-    part[ly][threadIdx.x] = acc;
+        __syncthreads();
+        const int k = 2 * (l0 + tx);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            if (k >= KP) break;                                   // KP / 2 need not be a multiple of 32
+            const int cl = ty + 8 * n;                            // channel within the tile
+            const int ch = ct * 32 + cl;
+            const float2 v = tile[tx][cl];
+            const float2 h = make_float2(to_tf32(v.x), to_tf32(v.y));
+            const float2 lo = make_float2(to_tf32(v.x - h.x), to_tf32(v.y - h.y));
+            if (is_a) {
+                const int64_t row = ((int64_t)f * MT + (ch >> 6)) * kTileM + (ch & 63);
+                const int64_t o = row * KP + k;
+                *reinterpret_cast<float2*>(Ahi + o) = h;
+                *reinterpret_cast<float2*>(Alo + o) = lo;
+                const int64_t o2 = o + (int64_t)64 * KP;          // rows 64..127: i * X = (-im, re)
+                *reinterpret_cast<float2*>(Ahi + o2) = make_float2(-h.y, h.x);
+                *reinterpret_cast<float2*>(Alo + o2) = make_float2(-lo.y, lo.x);
+            } else {
+                const int64_t row = ((int64_t)f * NT + (ch >> 6)) * kTileN + (ch & 63);
+                const int64_t o = row * KP + k;
+                *reinterpret_cast<float2*>(Bhi + o) = h;
+                *reinterpret_cast<float2*>(Blo + o) = lo;
+            }
+        }
+        __syncthreads();
+    }
+    part[ty][tx] = pw;
     __syncthreads();
-    if (ly == 0 && c < C) {
+    if (ty == 0 && ch_ld < C) {
         float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
-        P[(int64_t)f * C + c] = t;
+        for (int w = 0; w < 8; ++w) t += part[w][tx];
+        if (is_a) {
+            pxx[(int64_t)f * Ne + ch_ld] = t;
+            if (sxx_out) sxx_out[(int64_t)f * Ne + ch_ld] = t;
+        } else {
+            pyy[(int64_t)f * Nm + ch_ld] = t;
+            if (syy_out) syy_out[(int64_t)f * Nm + ch_ld] = t;
+        }
     }
 }
 
-// Transposes S[l][f][c] into whitened K-major TF32 operand rows (hi and lo planes).
-//   MODE 0 (A operand): rows_per_f = MT * 128; row (mt*128 + r): r < 64 -> channel mt*64 + r (Xh),
-//                       r >= 64 -> i * Xh of channel mt*64 + r - 64; columns k >= 2L are zero.
-//   MODE 1 (B operand): rows_per_f = NT * 64; row = channel; columns [0,2L) and [2L,4L) both hold Yh,
-//                       columns >= 4L are zero; l_shift = 1 writes the same rows advanced by one
-//                       complex element (16-byte aligned access to odd segment shifts).
-// grid (F, rows_per_f / 32, ceil(row_len / 64)); block (32, 8)
-template <int MODE>
+// Shift-surrogate views of the B operand: Bdbl[k] = Bhi[k mod 2L] for k < 4L (else 0), Bodd[k] = Bdbl[k + 2].
+// One thread per complex column; grid (ceil(LB / 2 / 256), rows).
 __global__ void __launch_bounds__(256)
-pack_kernel(const float2* __restrict__ S, int L, int F, int C, int64_t ld, const float* __restrict__ P,
-            int rows_per_f, int row_len, int l_shift, float* __restrict__ hi, float* __restrict__ lo) {
-    __shared__ float2 tile[32][33];       // [l][row]
-    const int f = blockIdx.x, r0 = blockIdx.y * 32, l0 = blockIdx.z * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    // load: thread (tx = row, ty + 8n = l)
-    {
-        const int r = r0 + tx;
-        int ch;
-        bool rot = false;
-        if (MODE == 0) {
-            const int mt = r >> 7, rr = r & 127;
-            rot = rr >= 64;
-            ch = mt * 64 + (rr & 63);
-        } else {
-            ch = r;
-        }
-        float scale = 0.f;
-        if (ch < C) {
-            const float pw = P[(int64_t)f * C + ch];
-            scale = pw > 0.f ? rsqrtf(pw) : 0.f;
-        }
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-            const int lv = l0 + ty + 8 * n + l_shift;   // virtual l (column pair index)
-            int l = -1;
-            if (lv < L) l = lv;
-            else if (MODE == 1 && lv < 2 * L) l = lv - L;
-            float2 v = make_float2(0.f, 0.f);
-            if (l >= 0 && ch < C) {
-                const float2 s = __ldg(S + ((int64_t)l * F + f) * ld + ch);
-                v = rot ? make_float2(-s.y * scale, s.x * scale) : make_float2(s.x * scale, s.y * scale);
-            }
-            tile[ty + 8 * n][tx] = v;
-        }
-    }
-    __syncthreads();
-    // store: thread (tx = l, ty + 8n = row): 32 lanes write 256 contiguous bytes of one operand row
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-        const int r = r0 + ty + 8 * n;
-        const int k = 2 * (l0 + tx);
-        if (k < row_len) {
-            const float2 v = tile[tx][ty + 8 * n];
-            const float2 h = make_float2(to_tf32(v.x), to_tf32(v.y));
-            const int64_t o = ((int64_t)f * rows_per_f + r) * row_len + k;
-            *reinterpret_cast<float2*>(hi + o) = h;
-            if (lo) *reinterpret_cast<float2*>(lo + o) = make_float2(to_tf32(v.x - h.x), to_tf32(v.y - h.y));
-        }
-    }
+shift_operand_kernel(const float* __restrict__ Bhi, int L, int KP, int LB, float* __restrict__ Bdbl,
+                     float* __restrict__ Bodd) {
+    const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = blockIdx.y;
+    if (lp >= LB / 2) return;
+    const float2* src = reinterpret_cast<const float2*>(Bhi + row * KP);
+    const float2 z = make_float2(0.f, 0.f);
+    const float2 a = lp < 2 * L ? src[lp % L] : z;
+    const float2 b = lp + 1 < 2 * L ? src[(lp + 1) % L] : z;
+    reinterpret_cast<float2*>(Bdbl + row * LB)[lp] = a;
+    reinterpret_cast<float2*>(Bodd + row * LB)[lp] = b;
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static size_t gemm_smem_bytes(int epi) {
-    return 1024 + kStages * (kABytes + kBBytes) + sizeof(float) * kTileM * kStagePitch +
-           (epi == 1 ? 64 * 64 * 4 : 0) + sizeof(GemmBarriers) + 16;
+    const size_t stages = epi == 0 ? 3 * 2 * (kABytes + kBBytes) : 4 * (kABytes + kBBytes);
+    return 1024 + stages + sizeof(float) * kTileM * kStagePitch + (epi == 1 ? 64 * 64 * 4 : 0) + sizeof(GemmBarriers) + 16;
 }
 
 template <int EPI>
 static int launch_gemm(const CsdLayout& y, unsigned char* ws, CsdParams p, cudaStream_t st) {
     CUtensorMap mAhi, mAlo, mBhi, mBlo, mBodd;
     int rc;
-    if ((rc = make_operand_map(&mAhi, reinterpret_cast<float*>(ws + y.off_ahi), y.KP, (int64_t)y.F * y.MT * kTileM, kTileM))) return rc;
-    if ((rc = make_operand_map(&mAlo, reinterpret_cast<float*>(ws + y.off_alo), y.KP, (int64_t)y.F * y.MT * kTileM, kTileM))) return rc;
-    if ((rc = make_operand_map(&mBhi, reinterpret_cast<float*>(ws + y.off_bhi), y.LB, (int64_t)y.F * y.NT * kTileN, kTileN))) return rc;
-    if ((rc = make_operand_map(&mBlo, reinterpret_cast<float*>(ws + y.off_blo), y.LB, (int64_t)y.F * y.NT * kTileN, kTileN))) return rc;
-    if ((rc = make_operand_map(&mBodd, reinterpret_cast<float*>(ws + y.off_bodd), y.LB, (int64_t)y.F * y.NT * kTileN, kTileN))) return rc;
+    const int64_t arows = (int64_t)y.F * y.MT * kTileM, brows = (int64_t)y.F * y.NT * kTileN;
+    if ((rc = make_operand_map(&mAhi, reinterpret_cast<float*>(ws + y.off_ahi), y.KP, arows, kTileM))) return rc;
+    if ((rc = make_operand_map(&mAlo, reinterpret_cast<float*>(ws + y.off_alo), y.KP, arows, kTileM))) return rc;
+    if (EPI == 0) {
+        if ((rc = make_operand_map(&mBhi, reinterpret_cast<float*>(ws + y.off_bhi), y.KP, brows, kTileN))) return rc;
+        if ((rc = make_operand_map(&mBlo, reinterpret_cast<float*>(ws + y.off_blo), y.KP, brows, kTileN))) return rc;
+        mBodd = mBhi;
+    } else {
+        if ((rc = make_operand_map(&mBhi, reinterpret_cast<float*>(ws + y.off_bdbl), y.LB, brows, kTileN))) return rc;
+        if ((rc = make_operand_map(&mBodd, reinterpret_cast<float*>(ws + y.off_bodd), y.LB, brows, kTileN))) return rc;
+        mBlo = mBhi;
+    }
     const size_t smem = gemm_smem_bytes(EPI);
     rc = ensure_smem_attr(reinterpret_cast<const void*>(csd_gemm_kernel<EPI>), smem);
     if (rc) return rc;
@@ -372,7 +404,7 @@ static int launch_gemm(const CsdLayout& y, unsigned char* ws, CsdParams p, cudaS
 
 // shift-surrogate bookkeeping
 __global__ void shift_hist_kernel(const int32_t* __restrict__ shifts, int64_t n, int n_pos, int group,
-                                  uint32_t* __restrict__ mult, int32_t* __restrict__ off, uint32_t* __restrict__ max_u) {
+                                  uint32_t* __restrict__ mult, int32_t* __restrict__ off) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n_pos) off[i] = 2 * (int)i * group;
     if (i < n) {
@@ -380,7 +412,6 @@ __global__ void shift_hist_kernel(const int32_t* __restrict__ shifts, int64_t n,
         if (s < 0) s += n_pos;
         atomicAdd(&mult[s], 1u);
     }
-    (void)max_u;
 }
 __global__ void shift_gather_kernel(const int32_t* __restrict__ shifts, int64_t n, int n_pos,
                                     const uint32_t* __restrict__ max_u, float* __restrict__ max_stat) {
@@ -416,37 +447,17 @@ extern "C" int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne,
         return CMC_EWORKSPACE;
     }
     CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "cmc_csd_msc: workspace must be 256-byte aligned");
-    CMC_REQUIRE((int64_t)F * y.MT * kTileM < (1ll << 31) && (int64_t)F * y.NT * kTileN < (1ll << 31),
+    CMC_REQUIRE((int64_t)F * y.MT * kTileM < (1ll << 31) && (int64_t)F * y.NT * kTileN < (1ll << 31) && F <= 65535,
                 "cmc_csd_msc: operand too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned char* w = static_cast<unsigned char*>(ws);
     float* pxx = reinterpret_cast<float*>(w + y.off_pxx);
     float* pyy = reinterpret_cast<float*>(w + y.off_pyy);
-    const float2* Xc = reinterpret_cast<const float2*>(X);
-    const float2* Yc = reinterpret_cast<const float2*>(Y);
-    power_kernel<<<dim3(F, (Ne + 31) / 32), dim3(32, 8), 0, st>>>(Xc, L, F, Ne, ldx, pxx);
-    CMC_CHECK_LAUNCH("power_kernel(X)");
-    power_kernel<<<dim3(F, (Nm + 31) / 32), dim3(32, 8), 0, st>>>(Yc, L, F, Nm, ldy, pyy);
-    CMC_CHECK_LAUNCH("power_kernel(Y)");
-    pack_kernel<0><<<dim3(F, y.MT * kTileM / 32, (y.KP + 63) / 64), dim3(32, 8), 0, st>>>(
-        Xc, L, F, Ne, ldx, pxx, y.MT * kTileM, y.KP, 0, reinterpret_cast<float*>(w + y.off_ahi),
-        reinterpret_cast<float*>(w + y.off_alo));
-    CMC_CHECK_LAUNCH("pack_kernel<A>");
-    pack_kernel<1><<<dim3(F, y.NT * kTileN / 32, (y.LB + 63) / 64), dim3(32, 8), 0, st>>>(
-        Yc, L, F, Nm, ldy, pyy, y.NT * kTileN, y.LB, 0, reinterpret_cast<float*>(w + y.off_bhi),
-        reinterpret_cast<float*>(w + y.off_blo));
-    CMC_CHECK_LAUNCH("pack_kernel<B>");
-    pack_kernel<1><<<dim3(F, y.NT * kTileN / 32, (y.LB + 63) / 64), dim3(32, 8), 0, st>>>(
-        Yc, L, F, Nm, ldy, pyy, y.NT * kTileN, y.LB, 1, reinterpret_cast<float*>(w + y.off_bodd), nullptr);
-    CMC_CHECK_LAUNCH("pack_kernel<B odd>");
-    if (sxx) {
-        int rc = check_cuda(cudaMemcpyAsync(sxx, pxx, sizeof(float) * F * Ne, cudaMemcpyDeviceToDevice, st), "copy sxx");
-        if (rc) return rc;
-    }
-    if (syy) {
-        int rc = check_cuda(cudaMemcpyAsync(syy, pyy, sizeof(float) * F * Nm, cudaMemcpyDeviceToDevice, st), "copy syy");
-        if (rc) return rc;
-    }
+    pack_fused_kernel<<<dim3(F, 2 * y.MT + 2 * y.NT), dim3(32, 8), 0, st>>>(
+        reinterpret_cast<const float2*>(X), ldx, Ne, reinterpret_cast<const float2*>(Y), ldy, Nm, L, F, y.MT, y.NT, y.KP,
+        reinterpret_cast<float*>(w + y.off_ahi), reinterpret_cast<float*>(w + y.off_alo),
+        reinterpret_cast<float*>(w + y.off_bhi), reinterpret_cast<float*>(w + y.off_blo), pxx, pyy, sxx, syy);
+    CMC_CHECK_LAUNCH("pack_fused_kernel");
     CsdParams p{};
     p.F = F; p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock; p.nterms = 3; p.n_shift = 1;
     p.coh = coh; p.sxy = reinterpret_cast<float2*>(sxy); p.pxx = pxx; p.pyy = pyy;
@@ -455,14 +466,13 @@ extern "C" int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne,
 }
 
 extern "C" int64_t cmc_surrogate_workspace_bytes(int L, int F, int Ne, int Nm, int mode, int64_t n_surr) {
-    (void)F; (void)Ne; (void)Nm; (void)n_surr;
     if (L < 1 || F < 1 || Ne < 1 || Nm < 1 || n_surr < 0) return CMC_EINVAL;
     if (mode == CMC_SURR_SHIFT) return (int64_t)L * 12 + 256;
     if (mode == CMC_SURR_PHASE) return cmc::phase_workspace_bytes(L, F, Ne, Nm, n_surr);
     return CMC_EINVAL;
 }
 
-extern "C" int cmc_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, int mode, int group,
+extern "C" int cmc_surrogate_null(void* ws, int L, int F, int Ne, int Nm, int mode, int group,
                                   const int32_t* shifts, uint64_t seed, int64_t s_begin, int64_t s_end,
                                   const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2,
                                   int64_t ws2_bytes, void* stream) {
@@ -484,19 +494,27 @@ extern "C" int cmc_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, 
     }
     const CsdLayout y = csd_layout(L, F, Ne, Nm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char* w = static_cast<unsigned char*>(ws);
     uint32_t* mult = static_cast<uint32_t*>(ws2);
     uint32_t* max_u = mult + L;
     int32_t* off = reinterpret_cast<int32_t*>(max_u + L);
     int rc = check_cuda(cudaMemsetAsync(ws2, 0, (size_t)L * 8, st), "memset(shift tables)");
     if (rc) return rc;
     const int64_t nthreads = n > n_pos ? n : n_pos;
-    shift_hist_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(shifts, n, n_pos, group, mult, off, max_u);
+    shift_hist_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(shifts, n, n_pos, group, mult, off);
     CMC_CHECK_LAUNCH("shift_hist_kernel");
+    // doubled / advanced views of the B operand (rebuilt per call: ~10 us against milliseconds of GEMM)
+    shift_operand_kernel<<<dim3((y.LB / 2 + 255) / 256, (unsigned)((int64_t)F * y.NT * kTileN)), 256, 0, st>>>(
+        reinterpret_cast<const float*>(w + y.off_bhi), L, y.KP, y.LB, reinterpret_cast<float*>(w + y.off_bdbl),
+        reinterpret_cast<float*>(w + y.off_bodd));
+    CMC_CHECK_LAUNCH("shift_operand_kernel");
     CsdParams p{};
     p.F = F; p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock; p.nterms = 1; p.n_shift = n_pos;
     p.shift_off = off; p.shift_mult = mult; p.coh_obs = coh_obs; p.exceed = exceed; p.max_u = max_u;
+    p.pxx = reinterpret_cast<const float*>(w + y.off_pxx);
+    p.pyy = reinterpret_cast<const float*>(w + y.off_pyy);
     p.total_tiles = (long long)F * y.MT * y.NT * n_pos;
-    rc = launch_gemm<1>(y, const_cast<unsigned char*>(static_cast<const unsigned char*>(ws)), p, st);
+    rc = launch_gemm<1>(y, w, p, st);
     if (rc) return rc;
     shift_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shifts, n, n_pos, max_u, max_stat);
     CMC_CHECK_LAUNCH("shift_gather_kernel");

@@ -70,7 +70,8 @@ def _device():
 def _to_device_f32(a) -> torch.Tensor:
     """(n_samples, n_ch) float32 CUDA tensor with unit channel stride."""
     if isinstance(a, torch.Tensor):
-        t = a.to(device=_device(), dtype=torch.float32)
+        # pinned host tensors copy asynchronously, so consecutive uploads queue back to back
+        t = a.to(device=_device(), dtype=torch.float32, non_blocking=True)
     else:
         h = np.ascontiguousarray(a, dtype=np.float32)
         t = torch.from_numpy(h).to(_device(), non_blocking=True)

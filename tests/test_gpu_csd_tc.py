@@ -103,7 +103,8 @@ def test_shift_surrogates_match_oracle(cuda_device):
     assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
     exact, _ = osur.null_statistics(cs, coh_obs, tol=0.0)
     assert np.mean(got != exact) < 0.02                      # and almost always equal the exact count
-    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 1e-4
+    # single TF32 term: |dC| ~ 2 |S| 4e-4 / sqrt(L); with L = 42 and C_max ~ 0.3 that is ~1.5e-4
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 4e-4
     # sharding invariance: two halves accumulate to the same counts
     e2, m_a = K.surrogate_null(res, K.SURR_SHIFT, 0, 30, shifts=_dev(shifts[:30]))
     e2, m_b = K.surrogate_null(res, K.SURR_SHIFT, 30, 60, shifts=_dev(shifts[30:]), exceed=e2)
