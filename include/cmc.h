@@ -68,13 +68,23 @@ CMC_API int64_t cmc_launch_count(void);
  *   windows    [n_win][N]             float32 taper rows (DPSS, hann, ...)
  *   spec       [n_seg][n_win][F][spec_ld] complex64, F = bin_hi - bin_lo + 1,
  *              channel c at spec[...][c]; only columns [0, n_ch) are written
- *   N          power of two in [128, 8192]
+ *   N          powers of two in [128, 8192] run the shared-memory FFT kernels; any other length in
+ *              [2, 2^20] falls back to a direct O(N F) DFT kernel (validation-size calls)
  * ---------------------------------------------------------------------------------- */
 CMC_API int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int64_t ld,
                      const int64_t* seg_starts, int n_seg,
                      const float* windows, int n_win, int N, int detrend,
                      int bin_lo, int bin_hi,
                      float* spec, int64_t spec_ld, void* stream);
+
+/* Power spectra from segment spectra: out[w][f][c] = base_scale * dbl(f) * mean_k |spec[w][k][f][c]|^2, with
+ * dbl(f) = 2 for bins strictly inside (0, N/2) when one_sided != 0 (scipy density convention), optionally
+ * followed by log10(|.| + 1e-10).  Replaces signal.periodogram + mean over tapers of multitaper_psd
+ * (signal_features.py:417-437) and the segment average of signal.welch (signal_features.py:2116) with
+ * W = 1, K = segments.   spec [W][K][F][ld_in] complex64, out [W][F][ld_out] float32. */
+CMC_API int cmc_psd_from_spectra(const float* spec, int W, int K, int F, int n_ch, int64_t ld_in,
+                         float base_scale, int one_sided, int bin_lo, int N, int log_scale,
+                         float* out, int64_t ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K2w  per-window multitaper magnitude-squared coherence with optional jackknife CI

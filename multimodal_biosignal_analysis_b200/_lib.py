@@ -21,6 +21,7 @@ _SIGNATURES = {
     "cmc_launch_count": (_i64, []),
     "cmc_fft_segments": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32,
                                    _vp, _i64, _vp]),
+    "cmc_psd_from_spectra": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _f32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "cmc_msc_windows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i32, _f32, _f32,
                                   _vp, _vp, _vp, _vp, _vp]),
     "cmc_msc_windows_maxemg": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i32, _f32,

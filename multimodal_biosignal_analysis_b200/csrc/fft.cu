@@ -15,6 +15,11 @@
 #include "common.cuh"
 #include "fft_common.cuh"
 #include <stdlib.h>
+#include <math.h>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 namespace cmc {
 
@@ -176,6 +181,70 @@ static int launch_fft(const float* x, int64_t n_samples, int n_ch, int64_t ld,
     return CMC_OK;
 }
 
+// Arbitrary-length fallback (N not a supported power of two): direct O(N F) DFT per (segment, channel) with the
+// same detrend / taper semantics.  Used by validation-style calls (e.g. Welch PSDs with nperseg = 4 fs on
+// 500 Hz recordings); coalesced over channels, twiddles exp(-2 pi i q / N) from a per-device table.
+__global__ void __launch_bounds__(256)
+dft_direct_kernel(const float* __restrict__ x, int n_ch, int64_t ld, const int64_t* __restrict__ seg_starts,
+                  const float* __restrict__ windows, int n_win, int N, int detrend, int bin_lo, int F,
+                  float2* __restrict__ spec, int64_t spec_ld, const float2* __restrict__ twN) {
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    const int seg = blockIdx.x / n_win, kw = blockIdx.x % n_win;
+    if (c >= n_ch) return;
+    const float* xs = x + seg_starts[seg] * ld + c;
+    const float* win = windows + (int64_t)kw * N;
+    float mu = 0.f;
+    if (detrend == CMC_DETREND_CONSTANT) {
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) s += xs[(int64_t)n * ld];
+        mu = s / N;
+    }
+    float2* out = spec + ((int64_t)blockIdx.x * F) * spec_ld + c;
+    for (int bi = threadIdx.y; bi < F; bi += blockDim.y) {
+        const int b = bin_lo + bi;
+        float re = 0.f, im = 0.f;
+        int q = 0;                                   // (b * n) mod N
+        for (int n = 0; n < N; ++n) {
+            const float v = (xs[(int64_t)n * ld] - mu) * __ldg(win + n);
+            const float2 w = __ldg(twN + q);
+            re += v * w.x;
+            im += v * w.y;
+            q += b;
+            if (q >= N) q -= N;
+        }
+        if (detrend == CMC_DETREND_POST_TAPER && b == 0) re = 0.f;
+        if (b == 0 || 2 * b == N) im = 0.f;
+        out[(int64_t)bi * spec_ld] = make_float2(re, im);
+    }
+}
+
+// full-circle table exp(-2 pi i q / N), q in [0, N), for the direct kernel
+static int get_full_twiddles(int N, const float2** tw) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, float2*> cache;
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(dev, N);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::vector<float2> h(N);
+        for (int q = 0; q < N; ++q) {
+            const double a = -6.283185307179586476925286766559 * q / N;
+            h[q] = make_float2((float)cos(a), (float)sin(a));
+        }
+        float2* d = nullptr;
+        rc = check_cuda(cudaMalloc(&d, h.size() * sizeof(float2)), "cudaMalloc(dft table)");
+        if (rc) return rc;
+        rc = check_cuda(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice), "cudaMemcpy(dft table)");
+        if (rc) return rc;
+        it = cache.emplace(key, d).first;
+    }
+    *tw = it->second;
+    return CMC_OK;
+}
+
 int fft_segments_tma(const float* x, int64_t n_samples, int n_ch, int64_t ld, const int64_t* seg_starts, int n_seg,
                      const float* windows, int n_win, int N, int detrend, int bin_lo, int F, float2* spec,
                      int64_t spec_ld, const float2* twM, const float2* twN, cudaStream_t st);
@@ -198,8 +267,17 @@ extern "C" int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int
                 "cmc_fft_segments: windows/spec must be 8-byte aligned");
     if (n_seg == 0) return CMC_OK;
     if (N < 128 || N > 8192 || (N & (N - 1))) {
-        set_error("cmc_fft_segments: N=%d unsupported (power of two in [128, 8192])", N);
-        return CMC_EUNSUPPORTED;
+        CMC_REQUIRE(N >= 2 && N <= (1 << 20), "cmc_fft_segments: N=%d outside [2, 2^20]", N);
+        CMC_REQUIRE((int64_t)n_seg * n_win <= 2147483647ll, "cmc_fft_segments: too many segments");
+        const float2* tw;
+        int rc0 = get_full_twiddles(N, &tw);
+        if (rc0) return rc0;
+        dft_direct_kernel<<<dim3((unsigned)(n_seg * n_win), (n_ch + 31) / 32), dim3(32, 8), 0,
+                            static_cast<cudaStream_t>(stream)>>>(x, n_ch, ld, seg_starts, windows, n_win, N, detrend, bin_lo,
+                                                                 bin_hi - bin_lo + 1, reinterpret_cast<float2*>(spec),
+                                                                 spec_ld, tw);
+        CMC_CHECK_LAUNCH("dft_direct_kernel");
+        return CMC_OK;
     }
     const float2 *twM, *twN;
     int rc = get_twiddles(N, &twM, &twN);

@@ -69,6 +69,21 @@ def fft_segments(x: torch.Tensor, seg_starts: torch.Tensor, windows: torch.Tenso
     return out
 
 
+def psd_from_spectra(spec: torch.Tensor, base_scale: float, one_sided: bool, bin_lo: int, N: int,
+                     log_scale: bool) -> torch.Tensor:
+    """(W, K, F, C) complex64 spectra -> (W, F, C) float32 power spectra (mean over axis 1)."""
+    _need_cuda(spec, "spec", torch.complex64)
+    if spec.dim() != 4 or not spec.is_contiguous():
+        raise ValueError("spec must be contiguous (W, K, F, C)")
+    W, K, F, C = spec.shape
+    out = torch.empty((W, F, C), dtype=torch.float32, device=spec.device)
+    rc = _lib.load().cmc_psd_from_spectra(spec.data_ptr(), W, K, F, C, C, float(base_scale), int(one_sided),
+                                          int(bin_lo), int(N), int(log_scale), out.data_ptr(), C,
+                                          _lib.current_stream())
+    _lib.check(rc, "cmc_psd_from_spectra")
+    return out
+
+
 def _spectra_dims(X, Y):
     _need_cuda(X, "X", torch.complex64)
     _need_cuda(Y, "Y", torch.complex64)

@@ -88,6 +88,122 @@ def _out(t: torch.Tensor, host: bool):
     return t.cpu().numpy() if host else t
 
 
+def resample_data(data, original_sampling_freq, new_sampling_freq, axis: Literal[0, 1] = None):
+    """Linear-interpolation resampling helper, signal_features.py:40-56 (host utility)."""
+    from scipy.interpolate import interp1d
+    input_array, axis = check_2d_numpy_array(data, axis=axis)
+    n_timesteps = input_array.shape[axis]
+    duration = n_timesteps / original_sampling_freq
+    new_n = int(round(duration * new_sampling_freq))
+    f = interp1d(np.linspace(0, duration, n_timesteps), input_array, axis=axis, kind='linear',
+                 fill_value='extrapolate')
+    return f(np.linspace(0, duration, new_n))
+
+
+def mirror_eeg_channel_list(channels: list[str], input_is_left: bool = True) -> list[str]:
+    """Left/right mirror of 10-20 channel names, signal_features.py:59-76."""
+    out = []
+    for ch in channels:
+        if ch[-1] == 'z':
+            out.append(ch)
+            continue
+        if ch[-2:].isnumeric():
+            idx, area = int(ch[-2:]), ch[:-2]
+        elif ch[-1].isnumeric():
+            idx, area = int(ch[-1]), ch[:-1]
+        else:
+            raise ValueError("Unrecognizable EEG channel name: ", ch)
+        out.append(f"{area}{idx + (1 if input_is_left else -1)}")
+    return out
+
+
+# ----------------------------------------------------------------------------- PSD (SURVEY.md 8f row N3)
+def multitaper_psd(input_array, sampling_freq: float, nw: float = 3, window_length_sec: float = 1.0,
+                   overlap_frac: float = 0.5, axis: Literal[0, 1] = None, apply_log_scale: bool = True,
+                   psd_save_dir: str | Path | None = None, psd_file_suffix: str = "", plot_result: bool = False,
+                   **plot_kwargs):
+    """Sliding-window multitaper PSD, signal_features.py:80-454 (body :385-454): windows at
+    ``np.arange(0, n - N, hop)`` (:398 - one window fewer than the MSC grid when (n - N) % hop == 0),
+    un-renormalised DPSS tapers, ``signal.periodogram(window=None)`` conventions (mean of the TAPERED
+    window removed, density scaling 1 / (fs N), one-sided doubling), mean over tapers, optional
+    ``log10(|.| + 1e-10)``.  Returns (spectrograms (W, F, n_ch), time_centers, freqs).  ``plot_result`` needs the
+    reference's plotting module and is not supported here."""
+    host = _is_host(input_array)
+    input_array, axis = check_2d_numpy_array(input_array, axis=axis)
+    n_samples = input_array.shape[axis]
+    window_samples = int(window_length_sec * sampling_freq)
+    hop_samples = int(window_samples * (1 - overlap_frac))
+    k = int(2 * nw - 1)
+    tapers = signal.windows.dpss(M=window_samples, NW=nw, Kmax=k)
+    window_starts = np.arange(0, n_samples - window_samples, hop_samples)
+    time_centers = (window_starts + window_samples / 2) / sampling_freq
+    freqs = np.fft.rfftfreq(window_samples, d=1 / sampling_freq)
+    if axis == 1:
+        input_array = input_array.T
+    dev = _device()
+    x = _to_device_f32(input_array)
+    starts_d = torch.from_numpy(window_starts.astype(np.int64)).to(dev)
+    td = torch.from_numpy(np.ascontiguousarray(tapers, dtype=np.float32)).to(dev)
+    spec = K.fft_segments(x, starts_d, td, K.DETREND_POST_TAPER)
+    psd = K.psd_from_spectra(spec, 1.0 / (sampling_freq * window_samples), True, 0, window_samples, apply_log_scale)
+    spectrograms = _out(psd, host)
+    if host:
+        spectrograms = spectrograms.astype(np.float64)
+    if psd_save_dir is not None:
+        save_spectrograms(spectrograms, time_centers, freqs, "PSD", save_dir=psd_save_dir,
+                          identifier_suffix=psd_file_suffix)
+    if plot_result:
+        raise NotImplementedError("plot_result needs the reference's visualizations module (out of scope)")
+    return spectrograms, time_centers, freqs
+
+
+def welch_psd(input_array, sampling_freq: float, nperseg: int, noverlap: int | None = None, window: str = "hann",
+              axis: Literal[0, 1] = 0):
+    """``scipy.signal.welch(x, fs, nperseg=...)`` defaults (hann, 50 % overlap, constant detrend, density,
+    one-sided, mean over segments) for every channel: returns (freqs, psd (F, n_ch))."""
+    host = _is_host(input_array)
+    input_array, axis = check_2d_numpy_array(input_array, axis=axis)
+    if axis == 1:
+        input_array = input_array.T
+    n = input_array.shape[0]
+    nperseg = int(min(nperseg, n))                      # scipy clips nperseg to the input length
+    if noverlap is None:
+        noverlap = nperseg // 2
+    starts = np.arange(0, n - nperseg + 1, nperseg - noverlap, dtype=np.int64)
+    win = signal.get_window(window, nperseg)
+    dev = _device()
+    spec = K.fft_segments(_to_device_f32(input_array), torch.from_numpy(starts).to(dev),
+                          torch.from_numpy(win.astype(np.float32)[None]).to(dev), K.DETREND_CONSTANT)
+    L, _, F, C = spec.shape
+    psd = K.psd_from_spectra(spec.view(1, L, F, C), 1.0 / (sampling_freq * float(np.sum(win ** 2))), True, 0, nperseg,
+                             False)[0]
+    freqs = np.fft.rfftfreq(nperseg, d=1 / sampling_freq)
+    return freqs, (_out(psd, host).astype(np.float64) if host else psd)
+
+
+def compute_spectral_snr(input_array, sampling_freq: int, target_freq: float = 21.5, freq_window: float = 8.5,
+                         target_band_ratio: float = .5, axis: Literal[0, 1] = 0, return_psd: bool = False):
+    """Spectral SNR (dB) at a target frequency from a Welch PSD with 4-second segments,
+    signal_features.py:2069-2130: mean PSD in the narrow target band over mean PSD in the noise band
+    (means over bins AND channels, like the reference's boolean indexing of the (F, n_ch) array)."""
+    input_array, axis = check_2d_numpy_array(input_array, axis=axis)
+    freqs, psd = welch_psd(input_array, sampling_freq, nperseg=sampling_freq * 4, axis=axis)
+    if isinstance(psd, torch.Tensor):
+        psd = psd.cpu().numpy().astype(np.float64)
+    if axis == 1:
+        psd = psd.T                                     # scipy keeps the time axis in place
+    fax = freqs
+    target_freq_window = freq_window * target_band_ratio
+    target_band = (fax < target_freq + target_freq_window) & (fax > target_freq - target_freq_window)
+    noise_band = (fax >= target_freq - freq_window) & (fax <= target_freq + freq_window)
+    if axis == 1:
+        snr_linear = np.mean(psd[:, target_band]) / np.mean(psd[:, noise_band])
+    else:
+        snr_linear = np.mean(psd[target_band]) / np.mean(psd[noise_band])
+    snr_db = 10 * np.log10(snr_linear)
+    return snr_db if not return_psd else (snr_db, freqs, psd)
+
+
 # ----------------------------------------------------------------------------- scalar statistics
 def fisher_atanh_transform(coherence, eps: float = 1e-10):
     """signal_features.py:459-462."""

@@ -190,3 +190,50 @@ def test_cbpa_api_matches_oracle_and_result_dict(cuda_device, tmp_path):
     assert any(f.endswith("_cluster_summary.csv") for f in files)
     with pytest.raises(ValueError, match="incompatible tail"):
         cb.permutation_cluster_1samp_test(X, threshold=-2.0, tail=1, adjacency=adj)
+
+
+def test_multitaper_psd_matches_reference_golden(cuda_device):
+    from multimodal_biosignal_analysis_b200 import signal_features as sf
+    g = golden("psd.npz")
+    s_log, tc, fr = sf.multitaper_psd(g["x"], float(g["fs"]), nw=3, window_length_sec=0.5, overlap_frac=0.5, axis=0,
+                                      apply_log_scale=True)
+    s_lin, _, _ = sf.multitaper_psd(g["x"], float(g["fs"]), nw=3, window_length_sec=0.5, overlap_frac=0.5, axis=0,
+                                    apply_log_scale=False)
+    assert s_log.shape == g["s_log"].shape                     # the PSD grid has one window fewer than the MSC grid
+    np.testing.assert_array_equal(tc, g["time_centers"])
+    np.testing.assert_array_equal(fr, g["freqs"])
+    # DC is exactly 0 after the post-taper mean removal; elsewhere float32 relative accuracy
+    assert np.all(s_lin[:, 0] == 0)
+    np.testing.assert_allclose(s_lin[:, 1:], g["s_lin"][:, 1:], rtol=2e-4, atol=1e-9)
+    assert np.max(np.abs(s_log[:, 1:] - g["s_log"][:, 1:])) < 1e-4
+    with pytest.raises(AttributeError):
+        sf.multitaper_psd(g["x"], float(g["fs"]))             # 2-D input without axis
+
+
+def test_spectral_snr_and_welch_psd_vs_scipy(cuda_device):
+    """Includes the reference's tests/test_signal_features.py:14-24 (scale invariance) on its own shapes:
+    1000 samples at 500 Hz -> nperseg clipped to 1000, a non power-of-two length (direct DFT kernel)."""
+    from scipy import signal as ss
+    from multimodal_biosignal_analysis_b200 import signal_features as sf
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1000, 64))
+    a = sf.compute_spectral_snr(x, 500)
+    b = sf.compute_spectral_snr(x * .5, 500)
+    assert a == pytest.approx(b, abs=1e-4)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fr, ref = ss.welch(x, axis=0, fs=500, nperseg=2000)
+    snr, freqs, psd = sf.compute_spectral_snr(x, 500, return_psd=True)
+    np.testing.assert_allclose(freqs, fr)
+    np.testing.assert_allclose(psd, ref, rtol=3e-4, atol=1e-9)
+    tb = (fr < 21.5 + 4.25) & (fr > 21.5 - 4.25)
+    nb = (fr >= 13.0) & (fr <= 30.0)
+    assert snr == pytest.approx(10 * np.log10(np.mean(ref[tb]) / np.mean(ref[nb])), abs=1e-3)
+    # power-of-two path: 2048 Hz, 4-s segments of 8192 samples
+    y = rng.standard_normal((8192 * 3, 5)) + 0.3
+    f2, p2 = sf.welch_psd(y, 2048, 8192)
+    fr2, ref2 = ss.welch(y, axis=0, fs=2048, nperseg=8192)
+    np.testing.assert_allclose(p2, ref2, rtol=3e-4, atol=1e-12)
+    r = sf.resample_data(x, 500, 1000, axis=0)
+    assert r.shape == (2000, 64)
