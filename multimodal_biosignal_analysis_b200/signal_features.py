@@ -31,6 +31,20 @@ FREQUENCY_BANDS = {
     'gamma': (30, 100),
 }
 
+from . import spectrogram_aggregation as _agg
+from .spectrogram_aggregation import aggregate_psd_spectrogram  # noqa: E402,F401  (signal_features.py:1374-1502)
+
+
+def aggregate_spectrogram_over_frequency_band(spectrograms, freqs, behaviour='mean', frequency_bands=None,
+                                              log_transform=False, log_epsilon=1e-10, frequency_axis=1,
+                                              pre_aggregate_axis=None, lower_array=None, upper_array=None,
+                                              **kwargs):
+    """signal_features.py:1174-1371; see ``spectrogram_aggregation`` for the fidelity note on band selection."""
+    return _agg.aggregate_spectrogram_over_frequency_band(
+        spectrograms, freqs, behaviour, frequency_bands, log_transform, log_epsilon, frequency_axis,
+        pre_aggregate_axis, lower_array, upper_array, default_bands=FREQUENCY_BANDS, **kwargs)
+
+
 # budget (bytes) for the per-call (windows, F, Ne, Nm) device tensors; longer recordings are
 # processed in window chunks and streamed to the host arrays
 DEVICE_CHUNK_BYTES = 8 << 30

@@ -107,6 +107,28 @@ def main():
             f, coh[:, i, j] = signal.coherence(eeg[:, i], emg[:, j], fs=fs, nperseg=256)
     np.savez_compressed(os.path.join(OUT, "welch.npz"), eeg=eeg, emg=emg, fs=fs, freqs=f, coh=coh)
 
+    # ---- band / channel aggregation of stored spectrograms (host glue, N1) ----
+    rng = np.random.default_rng(18)
+    spec = rng.random((6, 129, 5))
+    fr = np.fft.rfftfreq(256, 1 / 256.0)
+    lo_a, hi_a = spec * 0.8, spec * 1.2
+    bands = {'alpha': (8, 12), 'beta': (13, 30)}
+    out = {}
+    for beh in ('mean', 'max'):
+        d = sf.aggregate_spectrogram_over_frequency_band(spec, fr, behaviour=beh, frequency_bands=bands,
+                                                         lower_array=lo_a, upper_array=hi_a)
+        for b in bands:
+            for k, nm in enumerate(('v', 'lo', 'hi')):
+                out[f"band_{beh}_{b}_{nm}"] = d[b][k]
+    d = sf.aggregate_spectrogram_over_frequency_band(spec, fr, behaviour='mean', frequency_bands=bands,
+                                                     log_transform=True, pre_aggregate_axis=(2, 'max'))
+    out["band_pre_alpha"] = d['alpha']
+    out["psd_agg_emg"] = sf.aggregate_psd_spectrogram(spec, fr, normalize_mvc=True, freq_slice='slow',
+                                                      aggregation_ops=[('mean', 1), ('max', 1)])
+    out["psd_agg_eeg"] = sf.aggregate_psd_spectrogram(spec, fr, channel_indices=[0, 1, 4], freq_slice=(8, 12),
+                                                      aggregation_ops=[('mean', 2), ('mean', 1)])
+    np.savez_compressed(os.path.join(OUT, "aggregation.npz"), spec=spec, freqs=fr, **out)
+
     # ---- scalars ----
     np.savez_compressed(
         os.path.join(OUT, "scalars.npz"),
