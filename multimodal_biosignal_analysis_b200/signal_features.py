@@ -697,6 +697,24 @@ def welch_magnitude_squared_coherence(eeg_array, emg_array, sampling_freq: float
                             eeg_axis, emg_axis)
 
 
+def local_neighbor_coherence(data, neighbor_mapping, sampling_freq: float, nperseg: int = 256) -> float:
+    """Average magnitude-squared coherence of every electrode with its neighbours - the quantity
+    ``BiosignalPreprocessor.validate_spatial_filtering`` evaluates before / after spatial filtering with one
+    ``scipy.signal.coherence`` call per neighbour pair ("~2-5 s per electrode", preprocessing.py:1214-1248;
+    SURVEY.md 8f row N4).  Here all pairs come from ONE batched K1 + K2 pass.  ``neighbor_mapping[ch]`` lists the
+    neighbour indices of channel ch; mean over frequencies, then neighbours, then electrodes (nan-aware).
+    The DC bin is numerically 0/0 after the per-segment detrend in both implementations; it carries 1/F of the
+    frequency mean."""
+    pc = welch_magnitude_squared_coherence(data, data, sampling_freq, nperseg=nperseg)
+    coh = pc.coherence
+    if isinstance(coh, torch.Tensor):
+        coh = coh.cpu().numpy()
+    mean_f = np.nanmean(coh, axis=0)                                  # (C, C)
+    per_ch = [np.nanmean([mean_f[ch, nb] for nb in nbs]) if len(nbs) else np.nan
+              for ch, nbs in enumerate(neighbor_mapping)]
+    return float(np.nanmean(per_ch))
+
+
 # ----------------------------------------------------------------------------- spectrogram files
 def save_spectrograms(spectrograms, time_centers, frequencies, modality: str, save_dir: str | Path,
                       identifier_suffix: str = ""):

@@ -237,3 +237,17 @@ def test_spectral_snr_and_welch_psd_vs_scipy(cuda_device):
     np.testing.assert_allclose(p2, ref2, rtol=3e-4, atol=1e-12)
     r = sf.resample_data(x, 500, 1000, axis=0)
     assert r.shape == (2000, 64)
+
+
+def test_local_neighbor_coherence_vs_scipy_loop(cuda_device):
+    from scipy import signal as ss
+    from multimodal_biosignal_analysis_b200 import signal_features as sf
+    rng = np.random.default_rng(2)
+    common = rng.standard_normal(6000)
+    data = rng.standard_normal((6000, 6)) + common[:, None] * np.array([0.0, 0.5, 1.0, 1.0, 0.2, 0.0])
+    mapping = [[1, 2], [0, 2], [1, 3], [2, 4], [3, 5], [4]]
+    ref = []
+    for ch, nbs in enumerate(mapping):
+        ref.append(np.nanmean([np.nanmean(ss.coherence(data[:, ch], data[:, nb], fs=512.0)[1]) for nb in nbs]))
+    got = sf.local_neighbor_coherence(data, mapping, 512.0)
+    assert got == pytest.approx(float(np.nanmean(ref)), abs=0.01)       # DC bin: 0/0 in both, 1/129 of the mean

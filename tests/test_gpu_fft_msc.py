@@ -36,6 +36,26 @@ def test_fft_segments_matches_numpy(cuda_device, N, detrend):
     assert np.max(np.abs(got - ref)) < 2e-6 * scale * np.sqrt(N)
 
 
+@pytest.mark.parametrize("N", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("n_ch,detrend", [(64, 1), (24, 0), (12, 2)])
+def test_fft_segments_tma_paths(cuda_device, N, n_ch, detrend):
+    """channel pitch multiple of 4 floats -> TMA-staged two-channel kernel; three tapers per segment, partial
+    last channel tile."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(N + n_ch)
+    n = N * 2 + 64
+    x = (rng.standard_normal((n, n_ch)) * np.linspace(0.5, 2.0, n_ch) + 0.4).astype(np.float32)
+    starts = np.array([0, 37, n - N], dtype=np.int64)
+    wins = np.concatenate([signal.get_window("hann", N)[None], signal.windows.dpss(N, 3, 2)]).astype(np.float32)
+    ref = oc.segment_spectra(x.astype(np.float64), starts, wins.astype(np.float64), detrend)
+    got = K.fft_segments(_dev(x), _dev(starts), _dev(wins), detrend).cpu().numpy()
+    scale = np.sqrt(np.mean(np.abs(ref) ** 2))
+    assert np.max(np.abs(got - ref)) < 2e-6 * scale * np.sqrt(N)
+    lo, hi = 3, min(100, N // 2)
+    got_b = K.fft_segments(_dev(x), _dev(starts), _dev(wins), detrend, lo, hi).cpu().numpy()
+    np.testing.assert_array_equal(got_b, got[:, :, lo:hi + 1])
+
+
 def test_fft_segments_band_and_offsets(cuda_device):
     from multimodal_biosignal_analysis_b200 import kernels as K
     rng = np.random.default_rng(3)
@@ -61,7 +81,7 @@ def test_fft_rejects_bad_arguments(cuda_device):
     x = torch.zeros((4000, 4), device="cuda")
     st = torch.zeros(1, dtype=torch.int64, device="cuda")
     with pytest.raises(CmcError):
-        K.fft_segments(x, st, torch.ones((1, 1000), device="cuda"))         # not a power of two
+        K.fft_segments(x, st, torch.ones((1, 1000), device="cuda"), 0, 0, 600)   # bin beyond N / 2
     with pytest.raises(ValueError):
         K.check_segments([3000], 2048, 4000)                                   # segment past the end
     with pytest.raises(TypeError):
@@ -159,3 +179,17 @@ def test_msc_identical_and_zero_channels(cuda_device):
     assert np.max(np.abs(c[:, :, 0, 0] - 1.0)) < 1e-5
     assert np.max(np.abs(c[:, :, 1, 1] - 1.0)) < 1e-5
     assert np.all(c[:, :, :, 2] == 0)
+
+
+@pytest.mark.parametrize("N", [100, 1000, 1536])
+def test_fft_segments_direct_dft_for_other_lengths(cuda_device, N):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(N)
+    x = (rng.standard_normal((2 * N + 10, 5)) + 0.2).astype(np.float32)
+    starts = np.array([0, N + 3], dtype=np.int64)
+    win = signal.get_window("hann", N).astype(np.float32)[None]
+    for detrend in (0, 1, 2):
+        ref = oc.segment_spectra(x.astype(np.float64), starts, win.astype(np.float64), detrend)
+        got = K.fft_segments(_dev(x), _dev(starts), _dev(win), detrend).cpu().numpy()
+        scale = np.sqrt(np.mean(np.abs(ref) ** 2))
+        assert np.max(np.abs(got - ref)) < 1e-5 * scale * np.sqrt(N)
