@@ -54,12 +54,39 @@ __device__ __forceinline__ double t_stat(const double* __restrict__ X, const dou
     return __ddiv_rn(mean, __dsqrt_rn(__ddiv_rn(var, n)));
 }
 
+// Same arithmetic with the subject column held in registers and the subject count known at compile time: the
+// NS loads are independent (one L2 latency instead of 2 NS dependent ones), the second pass re-uses them, and
+// the sign flip is an exact XOR of the sign bit (x * (+-1) == x with the sign bit flipped, NaNs included).
+// Evaluation order is unchanged, so t stays bit-identical to the oracle.  (profiles/r01c_cbpa.md)
+template <int NS>
+__device__ __forceinline__ double t_stat_regs(const double* __restrict__ X, const unsigned* flip, int n_tests, int v) {
+    double xs[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) xs[s] = X[(int64_t)s * n_tests + v];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        xs[s] = __hiloint2double(__double2hiint(xs[s]) ^ (int)flip[s], __double2loint(xs[s]));
+    double sum = xs[0];
+#pragma unroll
+    for (int s = 1; s < NS; ++s) sum = __dadd_rn(sum, xs[s]);
+    const double mean = __ddiv_rn(sum, (double)NS);
+    double d = __dsub_rn(xs[0], mean);
+    double ss = __dmul_rn(d, d);
+#pragma unroll
+    for (int s = 1; s < NS; ++s) {
+        d = __dsub_rn(xs[s], mean);
+        ss = __dadd_rn(ss, __dmul_rn(d, d));
+    }
+    const double var = __ddiv_rn(ss, (double)(NS - 1));
+    return __ddiv_rn(mean, __dsqrt_rn(__ddiv_rn(var, (double)NS)));
+}
+
 __device__ __forceinline__ long long t_to_fixed(double t) {
     t = fmin(fmax(t, -CMC_T_CLAMP), CMC_T_CLAMP);
     return __double2ll_rn(t * (double)(1 << CMC_FIX_SHIFT));
 }
 
-template <bool OBSERVED>
+template <bool OBSERVED, int NS>
 __global__ void __launch_bounds__(kCbpaThreads)
 cbpa_kernel(const double* __restrict__ X, int n_subj, int n_tests, const int8_t* __restrict__ signs,
             int64_t n_perm, double thr, int tail, const int32_t* __restrict__ indptr,
@@ -69,19 +96,24 @@ cbpa_kernel(const double* __restrict__ X, int n_subj, int n_tests, const int8_t*
     long long* mass = reinterpret_cast<long long*>(smem_raw);                 // [n_tests]
     int* parent = reinterpret_cast<int*>(mass + n_tests);                      // [n_tests]
     double* sg = reinterpret_cast<double*>(parent + ((n_tests + 1) & ~1));      // [n_subj]
-    signed char* sgn = reinterpret_cast<signed char*>(sg + n_subj);            // [n_tests]
+    unsigned* flip = reinterpret_cast<unsigned*>(sg + n_subj);                 // [n_subj] sign-bit masks
+    signed char* sgn = reinterpret_cast<signed char*>(flip + ((n_subj + 1) & ~1));   // [n_tests]
     __shared__ long long red_abs[kCbpaThreads / 32];
     __shared__ long long red_val[kCbpaThreads / 32];
     const int tid = threadIdx.x;
 
     for (int64_t p = blockIdx.x; p < n_perm; p += gridDim.x) {
         __syncthreads();
-        for (int s = tid; s < n_subj; s += kCbpaThreads)
-            sg[s] = OBSERVED ? 1.0 : (double)signs[p * n_subj + s];
+        for (int s = tid; s < n_subj; s += kCbpaThreads) {
+            const int sv = OBSERVED ? 1 : (int)signs[p * n_subj + s];
+            sg[s] = (double)sv;
+            flip[s] = sv < 0 ? 0x80000000u : 0u;
+        }
         __syncthreads();
         // ---- t-map, threshold, fixed-point image ----
         for (int v = tid; v < n_tests; v += kCbpaThreads) {
-            const double t = t_stat(X, sg, n_subj, n_tests, v);
+            const double t = NS > 0 ? t_stat_regs<(NS > 0 ? NS : 2)>(X, flip, n_tests, v)
+                                    : t_stat(X, sg, n_subj, n_tests, v);
             signed char s = 0;
             if (tail == 0) s = (t > thr) ? 1 : ((t < -thr) ? -1 : 0);
             else if (tail > 0) s = (t > thr) ? 1 : 0;
@@ -184,7 +216,7 @@ cbpa_label_kernel(const int32_t* __restrict__ root, const long long* __restrict_
 
 static size_t cbpa_smem_bytes(int n_subj, int n_tests) {
     return sizeof(long long) * n_tests + sizeof(int) * ((n_tests + 1) & ~1) + sizeof(double) * n_subj +
-           n_tests + 16;
+           sizeof(unsigned) * ((n_subj + 1) & ~1) + n_tests + 16;
 }
 
 static int cbpa_check(const double* X, int n_subj, int n_tests, const int32_t* indptr, const int32_t* indices,
@@ -218,15 +250,30 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
     const int64_t n_perm = p_end - p_begin;
     if (n_perm == 0) return CMC_OK;
     const size_t smem = cbpa_smem_bytes(n_subj, n_tests);
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<false>), smem);
+    // exact subject count as a template parameter for the usual group sizes, generic loop otherwise
+    using KernT = void (*)(const double*, int, int, const int8_t*, int64_t, double, int, const int32_t*,
+                           const int32_t*, long long*, double*, int32_t*, long long*);
+    KernT kern = cbpa_kernel<false, 0>;
+    switch (n_subj) {
+#define CMC_CBPA_CASE(n) case n: kern = cbpa_kernel<false, n>; break;
+        CMC_CBPA_CASE(2) CMC_CBPA_CASE(3) CMC_CBPA_CASE(4) CMC_CBPA_CASE(5) CMC_CBPA_CASE(6) CMC_CBPA_CASE(7)
+        CMC_CBPA_CASE(8) CMC_CBPA_CASE(9) CMC_CBPA_CASE(10) CMC_CBPA_CASE(11) CMC_CBPA_CASE(12) CMC_CBPA_CASE(13)
+        CMC_CBPA_CASE(14) CMC_CBPA_CASE(15) CMC_CBPA_CASE(16) CMC_CBPA_CASE(17) CMC_CBPA_CASE(18) CMC_CBPA_CASE(19)
+        CMC_CBPA_CASE(20) CMC_CBPA_CASE(21) CMC_CBPA_CASE(22) CMC_CBPA_CASE(23) CMC_CBPA_CASE(24) CMC_CBPA_CASE(25)
+        CMC_CBPA_CASE(26) CMC_CBPA_CASE(27) CMC_CBPA_CASE(28) CMC_CBPA_CASE(29) CMC_CBPA_CASE(30) CMC_CBPA_CASE(31)
+        CMC_CBPA_CASE(32)
+#undef CMC_CBPA_CASE
+        default: break;
+    }
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
     if (rc) return rc;
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbpa_kernel<false>, kCbpaThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCbpaThreads, smem);
     if (per_sm < 1) per_sm = 1;
     const int64_t grid = n_perm < (int64_t)sms * per_sm ? n_perm : (int64_t)sms * per_sm;
-    cbpa_kernel<false><<<(unsigned)grid, kCbpaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+    kern<<<(unsigned)grid, kCbpaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         X, n_subj, n_tests, signs + p_begin * n_subj, n_perm, thr, tail, indptr, indices,
         reinterpret_cast<long long*>(h0_fixed), nullptr, nullptr, nullptr);
     CMC_CHECK_LAUNCH("cbpa_kernel<perm>");
@@ -252,10 +299,10 @@ extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, doubl
     int32_t* rank = root + n_tests;
     long long* h0_tmp = reinterpret_cast<long long*>(rank + n_tests + (n_tests & 1));
     const size_t smem = cbpa_smem_bytes(n_subj, n_tests);
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true>), smem);
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true, 0>), smem);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cbpa_kernel<true><<<1, kCbpaThreads, smem, st>>>(X, n_subj, n_tests, nullptr, 1, thr, tail, indptr,
+    cbpa_kernel<true, 0><<<1, kCbpaThreads, smem, st>>>(X, n_subj, n_tests, nullptr, 1, thr, tail, indptr,
                                                      indices, h0_tmp, t_obs, root, mass_root);
     CMC_CHECK_LAUNCH("cbpa_kernel<observed>");
     cbpa_label_kernel<<<1, 1024, 0, st>>>(root, mass_root, n_tests, labels,
