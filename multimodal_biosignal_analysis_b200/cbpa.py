@@ -247,6 +247,82 @@ def spatio_temporal_cluster_1samp_test(X, threshold=None, n_permutations: int = 
                                           verbose=verbose, **kwargs)
 
 
+# ----------------------------------------------------------------------------- contrast front-end (row N2)
+def _get_task_freq_for_trial(log_df, t_start, t_end) -> float | None:
+    """Modal non-NaN 'Task Frequency' (Hz) inside [t_start, t_end), cbpa.py:250-279."""
+    col = log_df.loc[(log_df.index >= t_start) & (log_df.index < t_end), "Task Frequency"].dropna()
+    return None if col.empty else float(col.mode().iloc[0])
+
+
+def _extract_band_power(cfg: CBPAConfig, spectrogram: np.ndarray, freqs: np.ndarray,
+                        channel_indices: list[int] | None, freq_pooling: Literal["max", "mean"] = "max",
+                        channel_pooling: Literal["max", "mean"] = "max") -> np.ndarray:
+    """Stored spectrogram -> (n_windows, n_channels) band power, cbpa.py:564-649: CMC pools the EMG axis (if the
+    4-D tensor was stored) and then the band with ``freq_pooling``; PSD takes the band mean."""
+    from .spectrogram_aggregation import aggregate_psd_spectrogram
+    spec = spectrogram
+    if cfg.modality == "CMC":
+        if spec.ndim == 4:
+            spec = np.nanmean(spec, axis=3) if channel_pooling == "mean" else np.nanmax(spec, axis=3)
+        elif spec.ndim != 3:
+            raise ValueError(f"Unexpected CMC spectrogram shape {spec.shape}. "
+                             "Expected 3D (time,freq,eeg) or 4D (time,freq,eeg,emg).")
+    elif spec.ndim != 3:
+        raise ValueError(f"Unexpected PSD spectrogram shape {spec.shape}. Expected 3D (time,freq,channel).")
+    band_op = freq_pooling if cfg.modality == "CMC" else "mean"
+    return aggregate_psd_spectrogram(
+        spec, freqs, normalize_mvc=False, channel_indices=channel_indices,
+        is_log_scaled=cfg.psd_is_log_scaled if cfg.modality == "PSD" else False, freq_slice=cfg.freq_band,
+        aggregation_ops=[(band_op, 1)])
+
+
+def _band_power_per_phase(cfg: CBPAConfig, band_power: np.ndarray, timestamps, trial_spans: dict, trial_cond_map: dict,
+                          log_df, min_cycle_coverage_ratio: float = 0.8) -> dict[str, list[np.ndarray]]:
+    """Cycle-wise phase profiles of every trial grouped by condition, cbpa.py:651-725.  ``log_df`` is the enriched
+    log frame (DatetimeIndex, 'Task Frequency' column) or a mapping trial_id -> task frequency in Hz."""
+    import warnings
+    from .phase_normalization import phase_normalize_cycles
+    phase_grid = np.linspace(0, 360, cfg.n_phase_bins, endpoint=False)
+    out: dict[str, list[np.ndarray]] = {}
+    for trial_id, (t_start, t_end) in trial_spans.items():
+        condition = trial_cond_map.get(int(trial_id))
+        if condition is None:
+            continue
+        task_freq = (log_df.get(int(trial_id)) if isinstance(log_df, dict)
+                     else _get_task_freq_for_trial(log_df, t_start, t_end))
+        if task_freq is None or task_freq <= 0:
+            warnings.warn(f"  [phase] Trial {trial_id}: Task Frequency missing or zero. Skipping.")
+            continue
+        step = (cfg.cmc_time_window_sec if cfg.modality == "CMC" else cfg.psd_time_window_sec) * (1.0 - cfg.overlap_ratio)
+        samples_per_cycle = (1.0 / task_freq) / step
+        if samples_per_cycle < cfg.min_samples_per_cycle:
+            warnings.warn(f"  [phase] Trial {trial_id}: only {samples_per_cycle:.1f} CMC samples/cycle at "
+                          f"{task_freq} Hz — skipping (min={cfg.min_samples_per_cycle}).")
+            continue
+        mask = np.asarray((timestamps >= t_start) & (timestamps < t_end))
+        if not mask.any():
+            continue
+        t_rel = np.array([(ts - t_start).total_seconds() for ts in timestamps[mask]], dtype=float)
+        offset = float(cfg.phase_start_offset_sec) if cfg.phase_start_offset_sec is not None else float(1.0 / task_freq)
+        cycles = phase_normalize_cycles(
+            signal=band_power[mask], t_rel=t_rel, task_freq=task_freq,
+            trial_dur_sec=(t_end - t_start).total_seconds(), phase_grid=phase_grid,
+            min_samples_per_cycle=cfg.min_samples_per_cycle, min_cycle_coverage_ratio=min_cycle_coverage_ratio,
+            start_offset_sec=offset)
+        out.setdefault(condition, []).extend(cycles)
+    return out
+
+
+def phase_contrast_from_cycles(cfg: CBPAConfig, cycles_by_condition: dict) -> np.ndarray | None:
+    """Per-subject A - B profile (n_phase_bins, n_ch): nanmean over the valid cycles of each condition; ``None`` when
+    a condition has fewer than ``cfg.min_cycles_per_condition`` cycles (subject skipped), cbpa.py:858-879."""
+    a = cycles_by_condition.get(cfg.condition_A, [])
+    b = cycles_by_condition.get(cfg.condition_B, [])
+    if len(a) < cfg.min_cycles_per_condition or len(b) < cfg.min_cycles_per_condition:
+        return None
+    return np.nanmean(np.stack(a, axis=0), axis=0) - np.nanmean(np.stack(b, axis=0), axis=0)
+
+
 # ----------------------------------------------------------------------------- runner
 def build_contrast_array(cfg: CBPAConfig):
     """Per-subject A - B contrast (n_subj, n_times, n_ch) from the stored spectrogram files

@@ -129,6 +129,30 @@ def main():
                                                       aggregation_ops=[('mean', 2), ('mean', 1)])
     np.savez_compressed(os.path.join(OUT, "aggregation.npz"), spec=spec, freqs=fr, **out)
 
+    # ---- force-cycle phase normalisation (CBPA front-end, N2) ----
+    import src.pipeline.data_analysis as da
+    rng = np.random.default_rng(21)
+    t = np.sort(rng.uniform(0, 30, 150))
+    t[10] = t[11]                                            # duplicate time stamp
+    sig1 = np.sin(2 * np.pi * 0.1 * t) + 0.1 * rng.standard_normal(len(t))
+    sig2 = np.stack([sig1, np.cos(2 * np.pi * 0.1 * t), rng.standard_normal(len(t))], axis=1)
+    grid36 = np.linspace(0, 360, 36, endpoint=False)
+    gridc = np.linspace(0, 360, 13)
+    specs = [
+        ("a", sig1, t, 0.1, 30.0, grid36, 2, dict(start_offset_sec=10.0, verbose=False)),
+        ("b", sig2, t, 0.1, 30.0, grid36, 2, dict(start_offset_sec=0.0, min_cycle_coverage_ratio=0.5, verbose=False)),
+        ("c", sig2, t, 0.2, 29.0, gridc, 3, dict(interpolation_kind='nearest', verbose=False)),
+        ("d", sig2, t, 0.1, 30.0, grid36, 2, dict(use_interpolation=False, verbose=False)),
+        ("e", sig1[:40], t[:40], 0.15, 9.0, gridc, 2,
+         dict(min_cycle_coverage_ratio=0.0, phase_wraparound_coverage_threshold=0.95, verbose=False)),
+    ]
+    pn = {"t": t, "sig1": sig1, "sig2": sig2, "grid36": grid36, "gridc": gridc}
+    for name, sgl, tt, f0, dur, g, m, kw in specs:
+        cyc = da.phase_normalize_cycles(sgl, tt, f0, dur, g, m, **kw)
+        pn[f"n_{name}"] = len(cyc)
+        pn[f"cyc_{name}"] = np.stack(cyc) if len(cyc) else np.zeros(0)
+    np.savez_compressed(os.path.join(OUT, "phase_norm.npz"), **pn)
+
     # ---- scalars ----
     np.savez_compressed(
         os.path.join(OUT, "scalars.npz"),

@@ -231,3 +231,78 @@ def test_spectrogram_aggregation_matches_reference_golden():
         sf.aggregate_spectrogram_over_frequency_band(spec, fr[:-1])
     with pytest.raises(ValueError):
         sf.aggregate_psd_spectrogram(spec, None, freq_slice='alpha')
+
+
+def test_phase_normalize_cycles_matches_reference_golden():
+    from conftest import golden
+    from multimodal_biosignal_analysis_b200.phase_normalization import phase_normalize_cycles as pnc
+    g = golden("phase_norm.npz")
+    t, s1, s2, g36, gc = g["t"], g["sig1"], g["sig2"], g["grid36"], g["gridc"]
+    specs = [
+        ("a", s1, t, 0.1, 30.0, g36, 2, dict(start_offset_sec=10.0, verbose=False)),
+        ("b", s2, t, 0.1, 30.0, g36, 2, dict(start_offset_sec=0.0, min_cycle_coverage_ratio=0.5, verbose=False)),
+        ("c", s2, t, 0.2, 29.0, gc, 3, dict(interpolation_kind='nearest', verbose=False)),
+        ("d", s2, t, 0.1, 30.0, g36, 2, dict(use_interpolation=False, verbose=False)),
+        ("e", s1[:40], t[:40], 0.15, 9.0, gc, 2,
+         dict(min_cycle_coverage_ratio=0.0, phase_wraparound_coverage_threshold=0.95, verbose=False)),
+    ]
+    for name, sig, tt, f0, dur, grid, m, kw in specs:
+        cyc = pnc(sig, tt, f0, dur, grid, m, **kw)
+        assert len(cyc) == int(g[f"n_{name}"]) and len(cyc) > 0
+        np.testing.assert_array_equal(np.stack(cyc), g[f"cyc_{name}"])      # NaN positions included
+
+
+def test_phase_normalize_cycles_reference_behaviour_tests():
+    """Ports of the reference's tests/test_phase_normalization.py:6-75."""
+    from multimodal_biosignal_analysis_b200.phase_normalization import phase_normalize_cycles as pnc
+    t_rel = np.arange(0.0, 3.0, 0.1)
+    kw = dict(task_freq=1.0, trial_dur_sec=3.0, min_samples_per_cycle=2, min_cycle_coverage_ratio=0.0,
+              use_interpolation=True, verbose=False)
+    cycles = pnc(signal=t_rel.copy(), t_rel=t_rel, phase_grid=np.array([0.0, 90.0, 180.0, 270.0, 360.0]), **kw)
+    assert len(cycles) == 3
+    assert np.allclose([c[2] for c in cycles], [0.5, 1.5, 2.5], atol=1e-6)
+    cycles = pnc(signal=2.0 * t_rel + 3.0, t_rel=t_rel, phase_grid=np.array([0.0, 120.0, 240.0, 360.0]), **kw)
+    assert len(cycles) == 3 and all(c[0] == c[-1] for c in cycles)
+    t2 = np.array([0.0, 0.2, 0.4, 0.6, 0.8, 1.2, 1.4, 1.6, 1.8])
+    cycles = pnc(signal=np.sin(2.0 * np.pi * t2), t_rel=t2, task_freq=1.0, trial_dur_sec=2.0,
+                 phase_grid=np.array([0.0, 90.0, 180.0, 270.0]), min_samples_per_cycle=2,
+                 min_cycle_coverage_ratio=0.0, use_interpolation=True, verbose=False)
+    assert len(cycles) == 2 and np.isfinite(cycles[0][0]) and np.isnan(cycles[1][0])
+    avg = np.nanmean(np.stack(cycles, axis=0), axis=0)
+    assert np.isclose(avg[0], cycles[0][0], atol=1e-9)
+    assert pnc(t_rel, t_rel, 0.0, 3.0, np.arange(4.0), 2) == []
+    with pytest.raises(ValueError):
+        pnc(t_rel, t_rel[:-1], 1.0, 3.0, np.arange(4.0), 2)
+
+
+def test_cbpa_contrast_front_end():
+    """band power -> phase profiles per condition -> per-subject A - B contrast (cbpa.py:564-725, :858-879)."""
+    import pandas as pd
+    from multimodal_biosignal_analysis_b200 import cbpa as cb
+    cfg = cb.CBPAConfig(modality="CMC", freq_band="beta", condition_A="Happy", condition_B="Silence",
+                        use_phase_normalization=True, n_phase_bins=12, cmc_time_window_sec=2.0, overlap_ratio=0.5,
+                        min_cycles_per_condition=2)
+    rng = np.random.default_rng(0)
+    t0 = pd.Timestamp("2026-01-01 00:00:00", tz="UTC")
+    n_win = 140
+    stamps = pd.DatetimeIndex([t0 + pd.Timedelta(seconds=1.0 * i) for i in range(n_win)])
+    freqs = np.arange(0, 64, 0.5)
+    spec = rng.random((n_win, len(freqs), 3, 4))                       # stored 4-D CMC tensor
+    bp = cb._extract_band_power(cfg, spec, freqs, None)
+    band = (freqs >= 13) & (freqs <= 30)
+    np.testing.assert_array_equal(bp, np.nanmax(np.nanmax(spec, axis=3)[:, band], axis=1))
+    with pytest.raises(ValueError):
+        cb._extract_band_power(cfg, spec[0, :, 0], freqs, None)
+    spans = {1: (t0, t0 + pd.Timedelta(seconds=45)), 2: (t0 + pd.Timedelta(seconds=50), t0 + pd.Timedelta(seconds=95)),
+             3: (t0 + pd.Timedelta(seconds=100), t0 + pd.Timedelta(seconds=135))}
+    cond = {1: "Happy", 2: "Silence", 3: "Happy"}
+    cyc = cb._band_power_per_phase(cfg, bp, stamps, spans, cond, {1: 0.1, 2: 0.1, 3: 0.1})
+    assert set(cyc) == {"Happy", "Silence"} and len(cyc["Happy"]) == 5 and len(cyc["Silence"]) == 3
+    assert all(c.shape == (12, 3) for c in cyc["Happy"])
+    log_df = pd.DataFrame({"Task Frequency": [0.1] * n_win}, index=stamps)
+    cyc2 = cb._band_power_per_phase(cfg, bp, stamps, spans, cond, log_df)
+    np.testing.assert_array_equal(np.stack(cyc2["Silence"]), np.stack(cyc["Silence"]))
+    d = cb.phase_contrast_from_cycles(cfg, cyc)
+    np.testing.assert_allclose(d, np.nanmean(np.stack(cyc["Happy"]), 0) - np.nanmean(np.stack(cyc["Silence"]), 0))
+    cfg.min_cycles_per_condition = 4
+    assert cb.phase_contrast_from_cycles(cfg, cyc) is None
