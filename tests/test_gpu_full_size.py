@@ -1,0 +1,103 @@
+"""BASELINE.json configurations at FULL size, checked through size-independent properties and through the
+oracle on a channel subset (the coherence of a pair does not depend on the other channels)."""
+import numpy as np
+import pytest
+import torch
+from scipy import signal
+from scipy.stats import t as t_dist
+
+from oracle import coherence as oc
+from oracle import surrogate as osur
+from multimodal_biosignal_analysis_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg2(cuda_device):
+    from multimodal_biosignal_analysis_b200 import signal_features as sf
+    eeg, emg = syn.make_epochs(30, 8192, 64, 64, seed=20260102)
+    emg[:, 63] = eeg[:, 5]                         # one identical pair -> coherence 1 at every frequency
+    starts = syn.epoch_segment_starts(30, 8192, 2048, 1024)
+    pc = sf.welch_magnitude_squared_coherence(eeg, emg, 2048.0, nperseg=2048, freq_band=(1, 100), segment_starts=starts)
+    return eeg, emg, starts, pc
+
+
+def test_cfg2_full_size_subset_vs_oracle_and_properties(cfg2):
+    from multimodal_biosignal_analysis_b200 import signal_features as sf
+    eeg, emg, starts, pc = cfg2
+    coh = pc.coherence
+    assert coh.shape == (100, 64, 64) and pc.n_terms == 210
+    assert np.all(coh >= 0) and np.all(coh <= 1)
+    assert np.max(np.abs(coh[:, 5, 63] - 1.0)) < 2e-5
+    ie, im = [0, 5, 17, 40, 63], [1, 2, 31, 62, 63]
+    win = signal.get_window("hann", 2048)[None]
+    Xo = oc.segment_spectra(eeg[:, ie], starts, win, 1, 1, 100)[:, 0]
+    Yo = oc.segment_spectra(emg[:, im], starts, win, 1, 1, 100)[:, 0]
+    ref, sxx, syy, _ = oc.msc_from_spectra(Xo, Yo)
+    assert np.max(np.abs(coh[:, ie][:, :, im] - ref)) < 1e-4
+    np.testing.assert_allclose(pc.sxx[:, ie], sxx, rtol=5e-5)
+    np.testing.assert_allclose(pc.syy[:, im], syy, rtol=5e-5)
+    # scale invariance: coherence does not change when channels are rescaled (float32 exact powers of two)
+    pc2 = sf.welch_magnitude_squared_coherence(eeg * 4.0, emg * 0.25, 2048.0, nperseg=2048, freq_band=(1, 100),
+                                               segment_starts=starts)
+    assert np.max(np.abs(pc2.coherence - coh)) < 2e-6
+    # coupled pairs (common 20 / 40 Hz source) stand out at 20 Hz against the median pair
+    assert coh[19].max() > 10 * np.median(coh[19])
+
+
+def test_cfg3_full_size_surrogate_nulls(cfg2):
+    """1,000 surrogates per pair (config 3) in both modes: counts bounded, sharding-invariant, the identical and the
+    coupled pairs are significant, the null of uncoupled pairs is calibrated."""
+    from multimodal_biosignal_analysis_b200 import data_surrogation as ds, kernels as K
+    eeg, emg, starts, pc = cfg2
+    coh = pc.coherence
+    for mode in ("shift", "phase"):
+        null = (ds.circular_shift_surrogate_null(pc, 1000, seed=3) if mode == "shift"
+                else ds.phase_randomised_surrogate_null(pc, 1000, seed=3))
+        ex = null["exceed"]
+        assert ex.shape == coh.shape and ex.min() >= 0 and ex.max() <= 1000
+        assert np.all(ex[:, 5, 63] == 0)                       # C = 1 is never reached by a surrogate
+        p = null["p_values"]
+        strong = coh > 0.2
+        assert strong.sum() > 50 and np.all(p[strong] < 0.01)
+        # most pairs are uncoupled (8 x 16 of 64 x 64 carry the common source): their p-values stay ~uniform
+        assert 0.35 < p.mean() < 0.6 and np.mean(p < 0.05) < 0.2
+        assert null["max_stat"].shape == (1000,) and 0 < null["threshold_fwe"] < 1
+    # phase null: two shards with global indices reproduce the single run exactly
+    res = pc.device_result
+    e_all, m_all = K.surrogate_null(res, K.SURR_PHASE, 0, 1000, seed=3)
+    e_a, m_a = K.surrogate_null(res, K.SURR_PHASE, 0, 373, seed=3)
+    e_b, m_b = K.surrogate_null(res, K.SURR_PHASE, 373, 1000, seed=3, exceed=e_a)
+    np.testing.assert_array_equal(e_b.cpu().numpy(), e_all.cpu().numpy())
+    np.testing.assert_array_equal(torch.cat([m_a, m_b]).cpu().numpy(), m_all.cpu().numpy())
+    # spot-check 3 surrogates of the full-size problem against the fp64 definition on a channel subset
+    ie, im = [5, 17], [31, 63]
+    win = signal.get_window("hann", 2048)[None]
+    Xw, _ = osur.whiten(oc.segment_spectra(eeg[:, ie], starts, win, 1, 1, 100)[:, 0])
+    Yw, _ = osur.whiten(oc.segment_spectra(emg[:, im], starts, win, 1, 1, 100)[:, 0])
+    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(3), seed=3, quantise_z=True)
+    assert cs.max() < 0.2                                       # surrogates destroy the coupling
+    # the kernel's max over ALL pairs bounds the subset's max from above
+    assert np.all(m_all.cpu().numpy()[:3] >= cs.reshape(3, -1).max(axis=1) - 2e-5)
+
+
+def test_cfg5_cbpa_ten_thousand_permutations_properties(cuda_device):
+    """config 5 CBPA count: 10,000 sign-flip permutations; H0 symmetric in distribution, p-values monotone in
+    cluster mass, the planted effect is the significant cluster."""
+    from multimodal_biosignal_analysis_b200 import cbpa as cb
+    X = syn.make_cbpa_contrast(20, 100, 64)
+    adj = cb.combine_adjacency(100, cb.find_ch_adjacency_from_positions(syn.sensor_positions(64)))
+    thr = float(t_dist.ppf(0.975, 19))
+    t_obs, clusters, pv, H0, det = cb.permutation_cluster_1samp_test(
+        X, threshold=thr, n_permutations=10000, tail=0, adjacency=adj, seed=42, out_type="mask", return_details=True)
+    assert H0.shape == (10000,) and len(clusters) == len(pv)
+    mass = np.abs(det["mass_fixed"])
+    order = np.argsort(mass)
+    assert np.all(np.diff(pv[order]) <= 0)                      # larger |mass| -> smaller or equal p
+    best = int(np.argmax(mass))
+    assert pv[best] == 1.0 / 10000 or pv[best] < 0.001
+    t0 = 100 // 3
+    assert clusters[best][t0:t0 + 3, :10].mean() > 0.8          # the planted block
+    h = H0[1:]
+    assert abs(np.mean(h > 0) - 0.5) < 0.03                     # sign symmetry of the permutation distribution
