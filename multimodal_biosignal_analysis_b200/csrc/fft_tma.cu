@@ -37,6 +37,11 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// barrier over `n` threads with hardware barrier `id` (id 0, n = blockDim.x is __syncthreads)
+__device__ __forceinline__ void group_sync(int id, int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
 template <bool SWZ>
 __device__ __forceinline__ uint32_t raw_off(int n, int cp) {
     const uint32_t lin = (uint32_t)n * 32u + (uint32_t)cp * 8u;
@@ -51,7 +56,7 @@ __device__ __forceinline__ uint32_t pt_off(int p, int cp) {
 // Row swizzle p -> p ^ ((p >> 4) & 1) commutes with adding multiples of 32 rows, so it is applied once per
 // butterfly (all strides used after the first pass are multiples of 32 rows for M >= 512).
 template <int M, int R, int NS>
-__device__ __forceinline__ void pass_pair(uint32_t sbuf, const float2* __restrict__ twM, int tid) {
+__device__ __forceinline__ void pass_pair(uint32_t sbuf, const float2* __restrict__ twM, int tid, int bar_id) {
     constexpr int NT = M / 4;
     constexpr int B = kPtsPerThread / R;
     constexpr int STRIDE = M / R;
@@ -74,7 +79,7 @@ __device__ __forceinline__ void pass_pair(uint32_t sbuf, const float2* __restric
         dft<R>(va[b]);
         dft<R>(vb[b]);
     }
-    __syncthreads();
+    group_sync(bar_id, NT);
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const int q = tid + b * NT;
@@ -87,28 +92,154 @@ __device__ __forceinline__ void pass_pair(uint32_t sbuf, const float2* __restric
             sts128(NS % 32 == 0 ? base + (uint32_t)(r * NS) * 64u : sbuf + pt_off(j0 + r * NS, cp),
                    make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
     }
-    __syncthreads();
+    group_sync(bar_id, NT);
     (void)kHoist;
 }
 
-template <int M, bool SWZ>
-__global__ void __launch_bounds__(M / 4, (M / 4) <= 256 ? 2 : 1)
-fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
-                        const int64_t* __restrict__ seg_starts, const float* __restrict__ windows, int n_win,
-                        int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
-                        const float2* __restrict__ twM, const float2* __restrict__ twN, int dbg) {
+// Transforms the raw tile that sits at `sbuf` (N rows x 8 channels, written by TMA) in place and writes the
+// requested bins of window row `kw`.  Executed by the NT = M / 4 threads that synchronise on barrier `bar_id`.
+struct NoPoll {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+template <int M, bool SWZ, class Poll>
+__device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, float* part, float* mean_s, int tid, int bar_id, int kw,
+                                             int seg, int c0, int n_ch, const float* __restrict__ windows, int n_win,
+                                             int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
+                                             const float2* __restrict__ twM, const float2* __restrict__ twN) {
     constexpr int N = 2 * M;
     constexpr int NT = M / 4;
     constexpr int R0 = Plan<M>::R0, R1 = Plan<M>::R1, R2 = Plan<M>::R2;
     constexpr int B0 = kPtsPerThread / R0;
     constexpr int S0 = M / R0;
-    constexpr int kRowsPerBox = 256;
+    const float* win = windows + (int64_t)kw * N;
+    float2 va[B0][R0], vb[B0][R0];
+#pragma unroll
+    for (int b = 0; b < B0; ++b) {
+        const int q = tid + b * NT;
+        const int cp = q & 3, j = q >> 2;
+#pragma unroll
+        for (int r = 0; r < R0; ++r) {
+            const int n0 = 2 * (j + r * S0);
+            const float2 re = lds64(sbuf + raw_off<SWZ>(n0, cp));       // x[2p][c], x[2p][c+1]
+            const float2 im = lds64(sbuf + raw_off<SWZ>(n0 + 1, cp));   // x[2p+1][c], x[2p+1][c+1]
+            va[b][r] = make_float2(re.x, im.x);
+            vb[b][r] = make_float2(re.y, im.y);
+        }
+    }
+    float mua = 0.f, mub = 0.f;
+    if (detrend == CMC_DETREND_CONSTANT) {
+        if (kw == 0) {
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int b = 0; b < B0; ++b)
+#pragma unroll
+                for (int r = 0; r < R0; ++r) {
+                    sa += va[b][r].x + va[b][r].y;
+                    sb += vb[b][r].x + vb[b][r].y;
+                }
+            // lanes with equal (lane & 3) hold the same channel pair: fixed-order butterfly reduction
+#pragma unroll
+            for (int off = 16; off >= 4; off >>= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, off);
+                sb += __shfl_xor_sync(0xffffffffu, sb, off);
+            }
+            if ((tid & 31) < 4) {
+                part[(tid >> 5) * kTmaCT + 2 * (tid & 31)] = sa;
+                part[(tid >> 5) * kTmaCT + 2 * (tid & 31) + 1] = sb;
+            }
+            group_sync(bar_id, NT);
+            if (tid < kTmaCT) {
+                float t = 0.f;
+                for (int w = 0; w < NT / 32; ++w) t += part[w * kTmaCT + tid];
+                mean_s[tid] = t * (1.0f / N);
+            }
+            group_sync(bar_id, NT);
+        }
+        mua = mean_s[2 * (tid & 3)];
+        mub = mean_s[2 * (tid & 3) + 1];
+    }
+    // every thread has its raw samples in registers: the tile may now be overwritten in place
+    group_sync(bar_id, NT);
+    poll();
+#pragma unroll
+    for (int b = 0; b < B0; ++b) {
+        const int q = tid + b * NT;
+        const int cp = q & 3, j = q >> 2;
+#pragma unroll
+        for (int r = 0; r < R0; ++r) {
+            const float2 w = __ldg(reinterpret_cast<const float2*>(win + 2 * (j + r * S0)));
+            va[b][r] = make_float2((va[b][r].x - mua) * w.x, (va[b][r].y - mua) * w.y);
+            vb[b][r] = make_float2((vb[b][r].x - mub) * w.x, (vb[b][r].y - mub) * w.y);
+        }
+        dft<R0>(va[b]);
+        dft<R0>(vb[b]);
+#pragma unroll
+        for (int r = 0; r < R0; ++r)
+            sts128(sbuf + pt_off(j * R0 + r, cp), make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
+    }
+    group_sync(bar_id, NT);
+    poll();
+    if (R1 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(sbuf, twM, tid, bar_id);
+    poll();
+    if (R2 > 1) pass_pair<M, (R2 > 1 ? R2 : 2), R0 * R1>(sbuf, twM, tid, bar_id);
+    poll();
+
+    // ---- real-FFT split for the requested bins; 2 channels = 16 bytes per lane ----
+    float2* out = spec + ((int64_t)(seg * n_win + kw) * F) * spec_ld + c0;
+    for (int q = tid; q < F * 4; q += NT) {
+        const int cp = q & 3, bi = q >> 2;
+        const int b = bin_lo + bi;
+        const float4 A = lds128(sbuf + pt_off(b & (M - 1), cp));
+        const float4 Bz = lds128(sbuf + pt_off((M - b) & (M - 1), cp));
+        const float2 w = __ldg(twN + b);
+        float2 X[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float ax = h ? A.z : A.x, ay = h ? A.w : A.y, bx = h ? Bz.z : Bz.x, by = h ? Bz.w : Bz.y;
+            const float2 E = make_float2(0.5f * (ax + bx), 0.5f * (ay - by));
+            const float2 O = make_float2(0.5f * (ax - bx), 0.5f * (ay + by));
+            const float2 T = cmul(w, O);
+            X[h] = make_float2(E.x + T.y, E.y - T.x);
+            if (b == 0 || b == M) X[h].y = 0.f;
+            if (detrend == CMC_DETREND_POST_TAPER && b == 0) X[h].x = 0.f;
+        }
+        float2* o = out + (int64_t)bi * spec_ld + 2 * cp;
+        const int c = c0 + 2 * cp;
+        if (c + 1 < n_ch && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            *reinterpret_cast<float4*>(o) = make_float4(X[0].x, X[0].y, X[1].x, X[1].y);
+        } else {
+            if (c < n_ch) o[0] = X[0];
+            if (c + 1 < n_ch) o[1] = X[1];
+        }
+    }
+    group_sync(bar_id, NT);
+}
+
+// one thread: raw tile of (segment start, channel tile) -> shared memory, N rows of 32 bytes in boxes of 256 rows
+template <int M>
+__device__ __forceinline__ void issue_tile_tma(unsigned char* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int start) {
+    constexpr int N = 2 * M;
+    fence_proxy_async();                       // earlier generic-proxy accesses before async-proxy writes
+    mbar_arrive_expect_tx(bar, N * 32);
+#pragma unroll 1
+    for (int i = 0; i < N / 256; ++i) tma_load_2d(dst + i * 256 * 32, tmap, bar, c0, start + i * 256);
+}
+
+// Basic kernel: one CTA per (segment, channel tile), 2 CTAs per SM.
+template <int M, bool SWZ>
+__global__ void __launch_bounds__(M / 4, (M / 4) <= 256 ? 2 : 1)
+fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
+                        const int64_t* __restrict__ seg_starts, const float* __restrict__ windows, int n_win,
+                        int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
+                        const float2* __restrict__ twM, const float2* __restrict__ twN) {
+    constexpr int N = 2 * M;
+    constexpr int NT = M / 4;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* buf = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     float* part = reinterpret_cast<float*>(buf + N * 32);            // [NT / 32][8]
     float* mean_s = part + (NT / 32) * kTmaCT;                       // [8]
     uint64_t* bar = reinterpret_cast<uint64_t*>(mean_s + kTmaCT);
-
     const uint32_t sbuf = smem_u32(buf);
     const int tid = threadIdx.x;
     const int seg = blockIdx.x;
@@ -120,118 +251,134 @@ fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
         tma_prefetch_desc(&tmap);
     }
     __syncthreads();
-
     for (int kw = 0; kw < n_win; ++kw) {
-        // ---- TMA: raw tile -> shared memory (N rows of 32 bytes, boxes of 256 rows) ----
-        if (tid == 0 && !(dbg & 1)) {
-            fence_proxy_async();                       // earlier generic-proxy accesses before async-proxy writes
-            mbar_arrive_expect_tx(bar, N * 32);
-#pragma unroll 1
-            for (int i = 0; i < N / kRowsPerBox; ++i)
-                tma_load_2d(buf + i * kRowsPerBox * 32, &tmap, bar, c0, start + i * kRowsPerBox);
-        }
-        if (!(dbg & 1)) mbar_wait(bar, kw & 1);
-        if (dbg & 2) { __syncthreads(); continue; }
+        if (tid == 0) issue_tile_tma<M>(buf, &tmap, bar, c0, start);
+        mbar_wait(bar, kw & 1);
+        process_tile<M, SWZ>(NoPoll(), sbuf, part, mean_s, tid, 0, kw, seg, c0, n_ch, windows, n_win, detrend, bin_lo, F,
+                             spec, spec_ld, twM, twN);
+    }
+}
 
-        const float* win = windows + (int64_t)kw * N;
-        float2 va[B0][R0], vb[B0][R0];
-#pragma unroll
-        for (int b = 0; b < B0; ++b) {
-            const int q = tid + b * NT;
-            const int cp = q & 3, j = q >> 2;
-#pragma unroll
-            for (int r = 0; r < R0; ++r) {
-                const int n0 = 2 * (j + r * S0);
-                const float2 re = lds64(sbuf + raw_off<SWZ>(n0, cp));       // x[2p][c], x[2p][c+1]
-                const float2 im = lds64(sbuf + raw_off<SWZ>(n0 + 1, cp));   // x[2p+1][c], x[2p+1][c+1]
-                va[b][r] = make_float2(re.x, im.x);
-                vb[b][r] = make_float2(re.y, im.y);
-            }
+// Pipelined kernel: one persistent CTA per SM with TWO workers of NT threads and THREE tile buffers.  Each worker
+// transforms its current tile while the free buffer receives the next tile of whichever worker claims it first;
+// when a worker moves on to its prefetched buffer it hands the old one back.  The basic kernel serialises the
+// TMA wait and the butterflies inside a CTA (53.9 us = 0.75 x (40.6 compute + 25.4 load), profiles/r01b); here the
+// load of tile t + 1 overlaps the transform of tile t.  At most one prefetch is outstanding at any time (3 buffers,
+// 2 in use), so a single-slot free list suffices.
+struct PipeCtrl {
+    uint64_t full[3];
+    int free_buf;            // index of the idle buffer or -1
+    unsigned fills[3];       // number of TMA fills issued into each buffer (parity of the next wait)
+    int next_buf[2];         // per worker: prefetched buffer or -1
+    unsigned next_parity[2];
+};
+
+template <int M>
+__global__ void __launch_bounds__(M / 2, 1)
+fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch, int n_seg,
+                             const int64_t* __restrict__ seg_starts, const float* __restrict__ windows, int n_win,
+                             int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
+                             const float2* __restrict__ twM, const float2* __restrict__ twN) {
+    constexpr int N = 2 * M;
+    constexpr int NT = M / 4;                  // threads per worker
+    constexpr int kTileBytes = N * 32;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    float* part_all = reinterpret_cast<float*>(base + 3 * kTileBytes);          // [2][NT / 32][8]
+    float* mean_all = part_all + 2 * (NT / 32) * kTmaCT;                        // [2][8]
+    PipeCtrl* ctl = reinterpret_cast<PipeCtrl*>(mean_all + 2 * kTmaCT);
+    const int worker = threadIdx.x / NT;
+    const int tid = threadIdx.x - worker * NT;
+    const int bar_id = 1 + worker;
+    float* part = part_all + worker * (NT / 32) * kTmaCT;
+    float* mean_s = mean_all + worker * kTmaCT;
+    const int n_ct = (n_ch + kTmaCT - 1) / kTmaCT;
+    const long long total = (long long)n_seg * n_ct;
+    const long long stride = 2ll * gridDim.x;
+    long long t = 2ll * blockIdx.x + worker;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 3; ++b) {
+            mbar_init(&ctl->full[b], 1);
+            ctl->fills[b] = 0;
         }
-        float mua = 0.f, mub = 0.f;
-        if (detrend == CMC_DETREND_CONSTANT) {
-            if (kw == 0) {
-                float sa = 0.f, sb = 0.f;
-#pragma unroll
-                for (int b = 0; b < B0; ++b)
-#pragma unroll
-                    for (int r = 0; r < R0; ++r) {
-                        sa += va[b][r].x + va[b][r].y;
-                        sb += vb[b][r].x + vb[b][r].y;
+        ctl->free_buf = 2;
+        ctl->next_buf[0] = ctl->next_buf[1] = -1;
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap);
+    }
+    __syncthreads();
+    if (t >= total) return;                    // this worker has no tile; buffer 2 stays with the other worker
+
+    int cur = worker;
+    unsigned cur_parity = 0;
+    if (tid == 0) {
+        issue_tile_tma<M>(base + cur * kTileBytes, &tmap, &ctl->full[cur], (int)(t % n_ct) * kTmaCT,
+                          (int)seg_starts[t / n_ct]);
+        ctl->fills[cur] = 1;
+    }
+    while (true) {
+        const int seg = (int)(t / n_ct), c0 = (int)(t % n_ct) * kTmaCT;
+        const long long tn = t + stride;
+        for (int kw = 0; kw < n_win; ++kw) {
+            if (kw > 0 && tid == 0) {          // the in-place transform consumed the raw tile: fetch it again
+                cur_parity = ctl->fills[cur] & 1;
+                ctl->fills[cur] += 1;
+                issue_tile_tma<M>(base + cur * kTileBytes, &tmap, &ctl->full[cur], c0, (int)seg_starts[seg]);
+            }
+            if (kw > 0) {
+                group_sync(bar_id, NT);
+                cur_parity = (ctl->fills[cur] - 1) & 1;
+            }
+            mbar_wait(&ctl->full[cur], cur_parity);
+            // thread 0 of the worker tries to claim the idle buffer for the worker's next tile - here and again after
+            // every pass barrier, so that a buffer released by the other worker mid-tile is picked up at once
+            auto poll = [&]() {
+                if (tid == 0 && kw == n_win - 1 && tn < total && ctl->next_buf[worker] < 0) {
+                    const int fb = atomicExch(&ctl->free_buf, -1);
+                    if (fb >= 0) {
+                        ctl->next_parity[worker] = ctl->fills[fb] & 1;
+                        ctl->fills[fb] += 1;
+                        issue_tile_tma<M>(base + fb * kTileBytes, &tmap, &ctl->full[fb], (int)(tn % n_ct) * kTmaCT,
+                                          (int)seg_starts[tn / n_ct]);
+                        ctl->next_buf[worker] = fb;
                     }
-                // lanes with equal (lane & 3) hold the same channel pair: fixed-order butterfly reduction
-#pragma unroll
-                for (int off = 16; off >= 4; off >>= 1) {
-                    sa += __shfl_xor_sync(0xffffffffu, sa, off);
-                    sb += __shfl_xor_sync(0xffffffffu, sb, off);
                 }
-                if ((tid & 31) < 4) {
-                    part[(tid >> 5) * kTmaCT + 2 * (tid & 31)] = sa;
-                    part[(tid >> 5) * kTmaCT + 2 * (tid & 31) + 1] = sb;
-                }
-                __syncthreads();
-                if (tid < kTmaCT) {
-                    float t = 0.f;
-                    for (int w = 0; w < NT / 32; ++w) t += part[w * kTmaCT + tid];
-                    mean_s[tid] = t * (1.0f / N);
-                }
-                __syncthreads();
-            }
-            mua = mean_s[2 * (tid & 3)];
-            mub = mean_s[2 * (tid & 3) + 1];
+            };
+            poll();
+            process_tile<M, false>(poll, smem_u32(base + cur * kTileBytes), part, mean_s, tid, bar_id, kw, seg, c0, n_ch,
+                                   windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN);
         }
-        // every thread has its raw samples in registers: the tile may now be overwritten in place
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < B0; ++b) {
-            const int q = tid + b * NT;
-            const int cp = q & 3, j = q >> 2;
-#pragma unroll
-            for (int r = 0; r < R0; ++r) {
-                const float2 w = __ldg(reinterpret_cast<const float2*>(win + 2 * (j + r * S0)));
-                va[b][r] = make_float2((va[b][r].x - mua) * w.x, (va[b][r].y - mua) * w.y);
-                vb[b][r] = make_float2((vb[b][r].x - mub) * w.x, (vb[b][r].y - mub) * w.y);
+        // process_tile ended with a worker barrier: the buffer is no longer read and ctl->next_* is visible
+        t = tn;
+        if (t >= total) {
+            if (tid == 0) {
+                __threadfence_block();
+                atomicCAS(&ctl->free_buf, -1, cur);                // let the other worker prefetch into it
             }
-            dft<R0>(va[b]);
-            dft<R0>(vb[b]);
-            // rows j * R0 + r: the swizzle bit is (j & 1) when R0 == 16, and r only enters through its low bit
-#pragma unroll
-            for (int r = 0; r < R0; ++r)
-                sts128(sbuf + pt_off(j * R0 + r, cp), make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
+            break;
         }
-        __syncthreads();
-        if (R1 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(sbuf, twM, tid);
-        if (R2 > 1) pass_pair<M, (R2 > 1 ? R2 : 2), R0 * R1>(sbuf, twM, tid);
-
-        // ---- real-FFT split for the requested bins; 2 channels = 16 bytes per lane ----
-        float2* out = spec + ((int64_t)(seg * n_win + kw) * F) * spec_ld + c0;
-        for (int q = tid; q < F * 4; q += NT) {
-            const int cp = q & 3, bi = q >> 2;
-            const int b = bin_lo + bi;
-            const float4 A = lds128(sbuf + pt_off(b & (M - 1), cp));
-            const float4 Bz = lds128(sbuf + pt_off((M - b) & (M - 1), cp));
-            const float2 w = __ldg(twN + b);
-            float2 X[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float ax = h ? A.z : A.x, ay = h ? A.w : A.y, bx = h ? Bz.z : Bz.x, by = h ? Bz.w : Bz.y;
-                const float2 E = make_float2(0.5f * (ax + bx), 0.5f * (ay - by));
-                const float2 O = make_float2(0.5f * (ax - bx), 0.5f * (ay + by));
-                const float2 T = cmul(w, O);
-                X[h] = make_float2(E.x + T.y, E.y - T.x);
-                if (b == 0 || b == M) X[h].y = 0.f;
-                if (detrend == CMC_DETREND_POST_TAPER && b == 0) X[h].x = 0.f;
+        const int nb = ctl->next_buf[worker];
+        if (nb >= 0) {
+            const unsigned np = ctl->next_parity[worker];
+            group_sync(bar_id, NT);                                 // everyone has read next_* before it is reset
+            if (tid == 0) {
+                ctl->next_buf[worker] = -1;
+                __threadfence_block();
+                atomicCAS(&ctl->free_buf, -1, cur);                // hand the old buffer back
             }
-            float2* o = out + (int64_t)bi * spec_ld + 2 * cp;
-            const int c = c0 + 2 * cp;
-            if (c + 1 < n_ch && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                *reinterpret_cast<float4*>(o) = make_float4(X[0].x, X[0].y, X[1].x, X[1].y);
-            } else {
-                if (c < n_ch) o[0] = X[0];
-                if (c + 1 < n_ch) o[1] = X[1];
+            cur = nb;
+            cur_parity = np;
+        } else {
+            // no prefetch happened (the other worker held the idle buffer): reload in place
+            if (tid == 0) {
+                ctl->fills[cur] += 1;
+                issue_tile_tma<M>(base + cur * kTileBytes, &tmap, &ctl->full[cur], (int)(t % n_ct) * kTmaCT,
+                                  (int)seg_starts[t / n_ct]);
             }
+            group_sync(bar_id, NT);
+            cur_parity = (ctl->fills[cur] - 1) & 1;
         }
-        __syncthreads();
     }
 }
 
@@ -245,9 +392,28 @@ static int launch_tma(const CUtensorMap& tmap, int n_ch, const int64_t* seg_star
     int rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
     if (rc) return rc;
     dim3 grid(n_seg, (n_ch + kTmaCT - 1) / kTmaCT);
-    static const int dbg = getenv("CMC_FFT_DBG") ? atoi(getenv("CMC_FFT_DBG")) : 0;
-    kern<<<grid, NT, smem, st>>>(tmap, n_ch, seg_starts, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, dbg);
+    kern<<<grid, NT, smem, st>>>(tmap, n_ch, seg_starts, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN);
     CMC_CHECK_LAUNCH("fft_segments_tma_kernel");
+    return CMC_OK;
+}
+
+template <int M>
+static int launch_tma_pipe(const CUtensorMap& tmap, int n_ch, const int64_t* seg_starts, int n_seg, const float* windows,
+                           int n_win, int detrend, int bin_lo, int F, float2* spec, int64_t spec_ld, const float2* twM,
+                           const float2* twN, cudaStream_t st) {
+    constexpr int NT = M / 4;
+    const size_t smem = 1024 + 3 * (size_t)M * 64 + sizeof(float) * 2 * ((NT / 32) * kTmaCT + kTmaCT) + sizeof(PipeCtrl) + 16;
+    auto kern = fft_segments_tma_pipe_kernel<M>;
+    int rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
+    if (rc) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT);
+    const long long grid = (tiles + 1) / 2 < sms ? (tiles + 1) / 2 : sms;
+    kern<<<(unsigned)grid, 2 * NT, smem, st>>>(tmap, n_ch, n_seg, seg_starts, windows, n_win, detrend, bin_lo, F, spec,
+                                               spec_ld, twM, twN);
+    CMC_CHECK_LAUNCH("fft_segments_tma_pipe_kernel");
     return CMC_OK;
 }
 
@@ -276,6 +442,16 @@ int fft_segments_tma(const float* x, int64_t n_samples, int n_ch, int64_t ld, co
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(recording) failed with CUresult %d", (int)r);
         return CMC_ECUDA;
+    }
+    // pipelined persistent kernel whenever three tiles fit into shared memory (N <= 2048) and there is enough work
+    static const bool no_pipe = getenv("CMC_FFT_NO_PIPE") != nullptr;
+    if (!no_pipe && (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT) >= 64) {
+        switch (N) {
+            case 512:  return launch_tma_pipe<256>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            case 1024: return launch_tma_pipe<512>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            case 2048: return launch_tma_pipe<1024>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            default: break;
+        }
     }
     switch (N) {
         case 512: return launch_tma<256, false>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);

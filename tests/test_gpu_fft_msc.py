@@ -193,3 +193,26 @@ def test_fft_segments_direct_dft_for_other_lengths(cuda_device, N):
         got = K.fft_segments(_dev(x), _dev(starts), _dev(win), detrend).cpu().numpy()
         scale = np.sqrt(np.mean(np.abs(ref) ** 2))
         assert np.max(np.abs(got - ref)) < 1e-5 * scale * np.sqrt(N)
+
+
+@pytest.mark.parametrize("N", [512, 1024, 2048])
+def test_fft_segments_pipelined_kernel_many_tiles(cuda_device, N):
+    """>= 64 (segment, channel-tile) units -> the persistent two-worker / three-buffer kernel, with several window
+    rows per segment (tile re-fetch path) and more tiles than workers (prefetch hand-over path)."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(N)
+    n_seg, n_ch = 500, 20                                   # 1500 tiles over 296 workers
+    hop = N // 4
+    n = hop * (n_seg - 1) + N
+    x = (rng.standard_normal((n, n_ch)) + 0.1).astype(np.float32)
+    starts = (np.arange(n_seg) * hop).astype(np.int64)
+    wins = signal.windows.dpss(N, 3, 3).astype(np.float32)
+    for detrend, nw in ((1, 1), (0, 3)):
+        ref = oc.segment_spectra(x.astype(np.float64), starts, wins[:nw].astype(np.float64), detrend, 2, 90)
+        got = K.fft_segments(_dev(x), _dev(starts), _dev(wins[:nw]), detrend, 2, 90).cpu().numpy()
+        scale = np.sqrt(np.mean(np.abs(ref) ** 2))
+        assert np.max(np.abs(got - ref)) < 2e-6 * scale * np.sqrt(N)
+    # determinism: repeated launches give bit-identical spectra
+    a = K.fft_segments(_dev(x), _dev(starts), _dev(wins[:1]), 1, 2, 90)
+    b = K.fft_segments(_dev(x), _dev(starts), _dev(wins[:1]), 1, 2, 90)
+    assert torch.equal(torch.view_as_real(a), torch.view_as_real(b))
