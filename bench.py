@@ -444,9 +444,10 @@ def main_gpu(args):
             "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT), tf32x3 -> f32 accumulate (CSD)",
             "data": "synthetic", "config": workload_config(),
-            "roofline": {"bound": "hbm", "kernel": "fft_segments_kernel<1024,8> (K1, one launch per modality)",
+            "roofline": {"bound": "hbm", "kernel": "fft_segments_tma_pipe_kernel<1024> (K1, one launch per modality)",
                          "achieved": k1_gbs, "peak": hbm, "unit": "GB/s", "frac": k1_gbs / hbm,
-                         "traffic": None, "peak_source": peak_src,
+                         # dram__bytes_read + dram__bytes_write of one K1 launch, ncu --set full (profiles/r01b_k1_tma.md)
+                         "traffic": 70.5e6, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": k1_ms,
                          "k2_ms_per_step": k2_ms, "k1_share_of_step": 2 * k1_ms / (2 * k1_ms + k2_ms)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "stages": stages,

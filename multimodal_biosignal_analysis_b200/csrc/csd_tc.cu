@@ -82,7 +82,8 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    // EPI 0 (3xTF32): 3 stages of {A_hi, A_lo, B_hi, B_lo} = 48 KB; EPI 1 (one term): 4 stages of {A_hi, B} = 24 KB
+    // EPI 0 (3xTF32): 3 stages of {A_hi, A_lo, B_hi, B_lo} = 48 KB (a 4th stage measured no gain); EPI 1 (one term):
+    // 4 stages of {A_hi, B} = 24 KB
     constexpr int kStages = EPI == 0 ? 3 : 4;
     constexpr int kStageBytes = EPI == 0 ? 2 * (kABytes + kBBytes) : (kABytes + kBBytes);
     unsigned char* sS = base;                                   // [kStages][kStageBytes]
