@@ -15,6 +15,8 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE]
+# developer hook for instrumented builds (e.g. CMC_NVCC_EXTRA="-DCMC_CBPA_PROFILE"); use with --force
+NVCC_FLAGS += os.environ.get("CMC_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -10,8 +10,17 @@
 
 namespace cmc {
 
-constexpr int kCbpaThreads = 256;
+constexpr int kCbpaThreads = 512;
 constexpr int kCbpaMaxTests = 16384;
+
+#ifdef CMC_CBPA_PROFILE
+// instrumented build only: per-phase clock64() totals of thread 0 of every CTA
+__device__ unsigned long long g_cbpa_cycles[8];
+#define CBPA_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); \
+    atomicAdd(&g_cbpa_cycles[i], (unsigned long long)(now_ - tick_)); tick_ = now_; } } while (0)
+#else
+#define CBPA_TICK(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ int uf_find(int* parent, int x) {
     int p = parent[x];
@@ -58,6 +67,22 @@ __device__ __forceinline__ double t_stat(const double* __restrict__ X, const dou
 // NS loads are independent (one L2 latency instead of 2 NS dependent ones), the second pass re-uses them, and
 // the sign flip is an exact XOR of the sign bit (x * (+-1) == x with the sign bit flipped, NaNs included).
 // Evaluation order is unchanged, so t stays bit-identical to the oracle.  (profiles/r01c_cbpa.md)
+// a / B for a compile-time integer B without the generic division sequence: q = RN(a * RN(1/B)) is within one
+// ulp of a / B, and one exact-remainder correction r = a - B q (an FMA), q' = RN(q + r * RN(1/B)) then yields
+// the correctly rounded quotient (Markstein's theorem), i.e. exactly what __ddiv_rn returns.  Outside a safe
+// exponent band (zeros, subnormals, huge values, Inf/NaN) the generic division is used.
+template <int B>
+__device__ __forceinline__ double div_const(double a) {
+    constexpr double y = 1.0 / (double)B;
+    const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+    if (e - 100u < 1800u) {
+        const double q = __dmul_rn(a, y);
+        const double r = __fma_rn(-(double)B, q, a);
+        return __fma_rn(r, y, q);
+    }
+    return __ddiv_rn(a, (double)B);
+}
+
 template <int NS>
 __device__ __forceinline__ double t_stat_regs(const double* __restrict__ X, const unsigned* flip, int n_tests, int v) {
     double xs[NS];
@@ -69,7 +94,7 @@ __device__ __forceinline__ double t_stat_regs(const double* __restrict__ X, cons
     double sum = xs[0];
 #pragma unroll
     for (int s = 1; s < NS; ++s) sum = __dadd_rn(sum, xs[s]);
-    const double mean = __ddiv_rn(sum, (double)NS);
+    const double mean = div_const<NS>(sum);
     double d = __dsub_rn(xs[0], mean);
     double ss = __dmul_rn(d, d);
 #pragma unroll
@@ -77,8 +102,8 @@ __device__ __forceinline__ double t_stat_regs(const double* __restrict__ X, cons
         d = __dsub_rn(xs[s], mean);
         ss = __dadd_rn(ss, __dmul_rn(d, d));
     }
-    const double var = __ddiv_rn(ss, (double)(NS - 1));
-    return __ddiv_rn(mean, __dsqrt_rn(__ddiv_rn(var, (double)NS)));
+    const double var = div_const<NS - 1>(ss);
+    return __ddiv_rn(mean, __dsqrt_rn(div_const<NS>(var)));
 }
 
 __device__ __forceinline__ long long t_to_fixed(double t) {
@@ -86,29 +111,43 @@ __device__ __forceinline__ long long t_to_fixed(double t) {
     return __double2ll_rn(t * (double)(1 << CMC_FIX_SHIFT));
 }
 
+// Permutation CTAs (OBSERVED == false) keep a compact list of the supra-threshold nodes (a few per cent of the
+// map under H0): the t-map pass appends to it, and the hook / mass / max passes then walk the list instead of
+// the whole map - eight lanes per listed node over its CSR row, next row prefetched - so their cost follows the
+// number of supra-threshold nodes and every lane has work.  If the list overflows its capacity the CTA falls
+// back to the whole-map passes for that permutation; results are identical either way (unions and the integer
+// masses are order-free).  (profiles/r01c_cbpa.md)
 template <bool OBSERVED, int NS>
 __global__ void __launch_bounds__(kCbpaThreads)
 cbpa_kernel(const double* __restrict__ X, int n_subj, int n_tests, const int8_t* __restrict__ signs,
             int64_t n_perm, double thr, int tail, const int32_t* __restrict__ indptr,
             const int32_t* __restrict__ indices, long long* __restrict__ h0,
-            double* __restrict__ t_obs, int32_t* __restrict__ root_out, long long* __restrict__ mass_out) {
+            double* __restrict__ t_obs, int32_t* __restrict__ root_out, long long* __restrict__ mass_out,
+            int list_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     long long* mass = reinterpret_cast<long long*>(smem_raw);                 // [n_tests]
     int* parent = reinterpret_cast<int*>(mass + n_tests);                      // [n_tests]
     double* sg = reinterpret_cast<double*>(parent + ((n_tests + 1) & ~1));      // [n_subj]
     unsigned* flip = reinterpret_cast<unsigned*>(sg + n_subj);                 // [n_subj] sign-bit masks
     signed char* sgn = reinterpret_cast<signed char*>(flip + ((n_subj + 1) & ~1));   // [n_tests]
+    unsigned short* list = reinterpret_cast<unsigned short*>(sgn + ((n_tests + 1) & ~1));   // [list_cap]
     __shared__ long long red_abs[kCbpaThreads / 32];
     __shared__ long long red_val[kCbpaThreads / 32];
+    __shared__ int n_supra;
     const int tid = threadIdx.x;
 
+#ifdef CMC_CBPA_PROFILE
+    long long tick_ = clock64();
+#endif
     for (int64_t p = blockIdx.x; p < n_perm; p += gridDim.x) {
         __syncthreads();
+        CBPA_TICK(0);
         for (int s = tid; s < n_subj; s += kCbpaThreads) {
             const int sv = OBSERVED ? 1 : (int)signs[p * n_subj + s];
             sg[s] = (double)sv;
             flip[s] = sv < 0 ? 0x80000000u : 0u;
         }
+        if (tid == 0) n_supra = 0;
         __syncthreads();
         // ---- t-map, threshold, fixed-point image ----
         for (int v = tid; v < n_tests; v += kCbpaThreads) {
@@ -122,38 +161,86 @@ cbpa_kernel(const double* __restrict__ X, int n_subj, int n_tests, const int8_t*
             parent[v] = s ? v : -1;
             mass[v] = s ? t_to_fixed(t) : 0;
             if (OBSERVED) t_obs[v] = t;
-        }
-        __syncthreads();
-        // ---- hook every supra-threshold edge once (u < v), same sign only ----
-        for (int v = tid; v < n_tests; v += kCbpaThreads) {
-            const signed char s = sgn[v];
-            if (!s) continue;
-            const int e1 = indptr[v + 1];
-            for (int e = indptr[v]; e < e1; ++e) {
-                const int u = indices[e];
-                if (u < v && sgn[u] == s) uf_union(parent, u, v);
+            if (!OBSERVED && s) {
+                const int k = atomicAdd(&n_supra, 1);
+                if (k < list_cap) list[k] = (unsigned short)v;
             }
         }
         __syncthreads();
-        // ---- cluster mass at the root (smallest index of the component) ----
-        for (int v = tid; v < n_tests; v += kCbpaThreads) {
-            if (!sgn[v]) { if (OBSERVED) root_out[v] = -1; continue; }
-            const int r = uf_find(parent, v);
-            if (r != v) atomicAdd(reinterpret_cast<unsigned long long*>(&mass[r]),
-                                  static_cast<unsigned long long>(mass[v]));
-            if (OBSERVED) root_out[v] = r;
-        }
-        __syncthreads();
-        // ---- signed mass of largest magnitude; a positive cluster wins an exact tie ----
+        CBPA_TICK(1);
+        const int ns = OBSERVED ? 0 : n_supra;
+        const bool compact = !OBSERVED && ns <= list_cap;     // CTA-uniform
         long long best_abs = -1, best_val = 0;
-        for (int v = tid; v < n_tests; v += kCbpaThreads) {
-            if (sgn[v] && parent[v] == v) {
-                const long long m = mass[v];
-                const long long a = m < 0 ? -m : m;
-                if (a > best_abs || (a == best_abs && m > best_val)) { best_abs = a; best_val = m; }
+        if (compact) {
+            // ---- hook: eight lanes per listed node, one CSR row each; the next row is fetched ahead ----
+            const int sub = tid & 7, grp = tid >> 3;
+            constexpr int kGroups = kCbpaThreads >> 3;
+            int i = grp;
+            int v = 0, e0 = 0, e1 = 0;
+            if (i < ns) { v = list[i]; e0 = indptr[v]; e1 = indptr[v + 1]; }
+            while (i < ns) {
+                const int inext = i + kGroups;
+                int vn = 0, e0n = 0, e1n = 0;
+                if (inext < ns) { vn = list[inext]; e0n = indptr[vn]; e1n = indptr[vn + 1]; }
+                const signed char s = sgn[v];
+                for (int e = e0 + sub; e < e1; e += 8) {
+                    const int u = indices[e];
+                    if (u < v && sgn[u] == s) uf_union(parent, u, v);
+                }
+                i = inext; v = vn; e0 = e0n; e1 = e1n;
             }
-            if (OBSERVED) mass_out[v] = (sgn[v] && parent[v] == v) ? mass[v] : 0;
+            __syncthreads();
+            CBPA_TICK(2);
+            // ---- cluster mass at the root ----
+            for (int k = tid; k < ns; k += kCbpaThreads) {
+                const int w = list[k];
+                const int r = uf_find(parent, w);
+                if (r != w) atomicAdd(reinterpret_cast<unsigned long long*>(&mass[r]),
+                                      static_cast<unsigned long long>(mass[w]));
+            }
+            __syncthreads();
+            CBPA_TICK(3);
+            for (int k = tid; k < ns; k += kCbpaThreads) {
+                const int w = list[k];
+                if (parent[w] == w) {
+                    const long long m = mass[w];
+                    const long long a = m < 0 ? -m : m;
+                    if (a > best_abs || (a == best_abs && m > best_val)) { best_abs = a; best_val = m; }
+                }
+            }
+        } else {
+            // ---- hook every supra-threshold edge once (u < v), same sign only ----
+            for (int v = tid; v < n_tests; v += kCbpaThreads) {
+                const signed char s = sgn[v];
+                if (!s) continue;
+                const int e1 = indptr[v + 1];
+                for (int e = indptr[v]; e < e1; ++e) {
+                    const int u = indices[e];
+                    if (u < v && sgn[u] == s) uf_union(parent, u, v);
+                }
+            }
+            __syncthreads();
+            CBPA_TICK(2);
+            // ---- cluster mass at the root (smallest index of the component) ----
+            for (int v = tid; v < n_tests; v += kCbpaThreads) {
+                if (!sgn[v]) { if (OBSERVED) root_out[v] = -1; continue; }
+                const int r = uf_find(parent, v);
+                if (r != v) atomicAdd(reinterpret_cast<unsigned long long*>(&mass[r]),
+                                      static_cast<unsigned long long>(mass[v]));
+                if (OBSERVED) root_out[v] = r;
+            }
+            __syncthreads();
+            CBPA_TICK(3);
+            for (int v = tid; v < n_tests; v += kCbpaThreads) {
+                if (sgn[v] && parent[v] == v) {
+                    const long long m = mass[v];
+                    const long long a = m < 0 ? -m : m;
+                    if (a > best_abs || (a == best_abs && m > best_val)) { best_abs = a; best_val = m; }
+                }
+                if (OBSERVED) mass_out[v] = (sgn[v] && parent[v] == v) ? mass[v] : 0;
+            }
         }
+        // ---- signed mass of largest magnitude; a positive cluster wins an exact tie ----
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const long long oa = __shfl_xor_sync(0xffffffffu, best_abs, off);
@@ -170,6 +257,7 @@ cbpa_kernel(const double* __restrict__ X, int n_subj, int n_tests, const int8_t*
                 }
             h0[p] = best_abs < 0 ? 0 : best_val;
         }
+        CBPA_TICK(4);
     }
 }
 
@@ -214,9 +302,22 @@ cbpa_label_kernel(const int32_t* __restrict__ root, const long long* __restrict_
     for (int v = tid; v < n_tests; v += 1024) labels[v] = root[v] >= 0 ? rank[root[v]] + 1 : 0;
 }
 
-static size_t cbpa_smem_bytes(int n_subj, int n_tests) {
+static size_t cbpa_smem_bytes(int n_subj, int n_tests, int list_cap) {
     return sizeof(long long) * n_tests + sizeof(int) * ((n_tests + 1) & ~1) + sizeof(double) * n_subj +
-           sizeof(unsigned) * ((n_subj + 1) & ~1) + n_tests + 16;
+           sizeof(unsigned) * ((n_subj + 1) & ~1) + ((n_tests + 1) & ~1) + sizeof(unsigned short) * list_cap + 16;
+}
+
+// Capacity of the supra-threshold list: the whole map when two CTAs still fit on one SM, else what is left of
+// the 227 KB a CTA may use (the kernel falls back to whole-map passes when a permutation overflows it).
+static int cbpa_list_cap(int n_subj, int n_tests) {
+    const size_t base = cbpa_smem_bytes(n_subj, n_tests, 0);
+    const size_t two_per_sm = 112 * 1024, one_per_sm = 226 * 1024;
+    size_t room = 0;
+    if (base + 2 * (size_t)n_tests <= two_per_sm) room = 2 * (size_t)n_tests;
+    else if (base < two_per_sm && (two_per_sm - base) / 2 >= (size_t)n_tests / 4) room = two_per_sm - base;
+    else if (base < one_per_sm) room = one_per_sm - base;
+    const size_t cap = room / 2;
+    return (int)(cap < (size_t)n_tests ? cap : (size_t)n_tests);
 }
 
 static int cbpa_check(const double* X, int n_subj, int n_tests, const int32_t* indptr, const int32_t* indices,
@@ -231,6 +332,14 @@ static int cbpa_check(const double* X, int n_subj, int n_tests, const int32_t* i
 }
 
 }  // namespace cmc
+
+#ifdef CMC_CBPA_PROFILE
+extern "C" CMC_API int cmc_dbg_cbpa_cycles(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, cmc::g_cbpa_cycles, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(cmc::g_cbpa_cycles, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" int64_t cmc_cbpa_workspace_bytes(int n_subj, int n_tests) {
     (void)n_subj;
@@ -249,10 +358,11 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
     CMC_REQUIRE(signs && h0_fixed && p_end >= p_begin, "cmc_cbpa_permute: bad permutation range");
     const int64_t n_perm = p_end - p_begin;
     if (n_perm == 0) return CMC_OK;
-    const size_t smem = cbpa_smem_bytes(n_subj, n_tests);
+    const int list_cap = cbpa_list_cap(n_subj, n_tests);
+    const size_t smem = cbpa_smem_bytes(n_subj, n_tests, list_cap);
     // exact subject count as a template parameter for the usual group sizes, generic loop otherwise
     using KernT = void (*)(const double*, int, int, const int8_t*, int64_t, double, int, const int32_t*,
-                           const int32_t*, long long*, double*, int32_t*, long long*);
+                           const int32_t*, long long*, double*, int32_t*, long long*, int);
     KernT kern = cbpa_kernel<false, 0>;
     switch (n_subj) {
 #define CMC_CBPA_CASE(n) case n: kern = cbpa_kernel<false, n>; break;
@@ -275,7 +385,7 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
     const int64_t grid = n_perm < (int64_t)sms * per_sm ? n_perm : (int64_t)sms * per_sm;
     kern<<<(unsigned)grid, kCbpaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         X, n_subj, n_tests, signs + p_begin * n_subj, n_perm, thr, tail, indptr, indices,
-        reinterpret_cast<long long*>(h0_fixed), nullptr, nullptr, nullptr);
+        reinterpret_cast<long long*>(h0_fixed), nullptr, nullptr, nullptr, list_cap);
     CMC_CHECK_LAUNCH("cbpa_kernel<perm>");
     return CMC_OK;
 }
@@ -298,12 +408,12 @@ extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, doubl
     int32_t* root = reinterpret_cast<int32_t*>(mass_root + n_tests);
     int32_t* rank = root + n_tests;
     long long* h0_tmp = reinterpret_cast<long long*>(rank + n_tests + (n_tests & 1));
-    const size_t smem = cbpa_smem_bytes(n_subj, n_tests);
+    const size_t smem = cbpa_smem_bytes(n_subj, n_tests, 0);
     rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true, 0>), smem);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cbpa_kernel<true, 0><<<1, kCbpaThreads, smem, st>>>(X, n_subj, n_tests, nullptr, 1, thr, tail, indptr,
-                                                     indices, h0_tmp, t_obs, root, mass_root);
+                                                     indices, h0_tmp, t_obs, root, mass_root, 0);
     CMC_CHECK_LAUNCH("cbpa_kernel<observed>");
     cbpa_label_kernel<<<1, 1024, 0, st>>>(root, mass_root, n_tests, labels,
                                            reinterpret_cast<long long*>(mass_fixed), mass_f64, n_clusters, rank);

@@ -12,4 +12,19 @@ thr = float(t_dist.ppf(0.975, 19))
 for _ in range(3):
     h0 = K.cbpa_permute(X, signs, 0, 10000, thr, 0, ip, ix)
 torch.cuda.synchronize()
-print("ok", int(h0.abs().max()))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    h0 = K.cbpa_permute(X, signs, 0, 10000, thr, 0, ip, ix)
+e1.record(); torch.cuda.synchronize()
+print("ok", int(h0.abs().max()), "ms/10000 perms", e0.elapsed_time(e1) / 10, "checksum", int(h0.sum()))
+import ctypes
+from multimodal_biosignal_analysis_b200 import _lib
+lib = _lib.load()
+if hasattr(lib, "cmc_dbg_cbpa_cycles"):
+    buf = (ctypes.c_ulonglong * 8)()
+    lib.cmc_dbg_cbpa_cycles(buf, 1)
+    h0 = K.cbpa_permute(X, signs, 0, 10000, thr, 0, ip, ix); torch.cuda.synchronize()
+    lib.cmc_dbg_cbpa_cycles(buf, 0)
+    tot = sum(buf)
+    print("phase cycles per perm [signs, tmap, hook, mass, max]:", [round(b / 10000) for b in buf[:5]], "share", [round(b / tot, 3) for b in buf[:5]])

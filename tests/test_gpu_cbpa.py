@@ -106,3 +106,26 @@ def test_cbpa_full_cfg4_properties(cuda_device):
     pick = np.array([0, 17, 511, 1023])
     ref = ocb.permutation_cluster_1samp_test(X, signs[pick], thr, 0, adj)
     np.testing.assert_array_equal(whole[pick], ref["H0_fixed"][1:])
+
+
+def test_cbpa_max_map_size_supra_list_overflow_and_compact_paths(cuda_device):
+    """n_tests = 16384 (the ABI maximum): the supra-threshold list holds only part of the map, so a strong
+    effect (most nodes supra-threshold) takes the whole-map fallback and a null map takes the compact path;
+    both must match the oracle bit for bit."""
+    rng = np.random.default_rng(31)
+    n_subj, n_times, n_ch = 9, 256, 64
+    adj = ocb.combine_adjacency(n_times, ocb.delaunay_adjacency(syn.sensor_positions(n_ch)))
+    signs = syn.make_sign_table(6, n_subj, seed=3)
+    all_minus = -np.ones((1, n_subj), dtype=signs.dtype)        # as many supra-threshold nodes as the observed map
+    one_flip = np.ones((1, n_subj), dtype=signs.dtype)
+    one_flip[0, 4] = -1
+    signs = np.concatenate([signs[:3], all_minus, signs[3:], one_flip])
+    thr = t_dist.ppf(0.975, n_subj - 1)
+    for shift in (0.0, 1.5):
+        X = rng.standard_normal((n_subj, n_times, n_ch)) + shift
+        ref = ocb.permutation_cluster_1samp_test(X, signs, thr, 0, adj)
+        t_obs, labels, mass, n, h0 = _run(X, signs, thr, 0, adj)
+        np.testing.assert_array_equal(t_obs, ref["t_obs"].reshape(-1))
+        np.testing.assert_array_equal(labels, ref["labels"])
+        np.testing.assert_array_equal(mass, ref["mass_fixed"])
+        np.testing.assert_array_equal(h0, ref["H0_fixed"][1:])
