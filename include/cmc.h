@@ -177,6 +177,9 @@ CMC_API int cmc_surrogate_null(void* ws, int L, int F, int Ne, int Nm, int mode,
  * cmc_cbpa_observed additionally returns the t-map, the label map (0 = no cluster,
  * k = k-th cluster in MNE order: t > thr clusters first, each group by smallest flat
  * index) and per-cluster masses (caller sizes mass_fixed / mass_f64 to n_tests).
+ *   ws     scratch of cmc_cbpa_workspace_bytes() for BOTH calls, 16-byte aligned: labelling
+ *          scratch plus a re-tiled copy of X (rebuilt on every call; calls sharing a stream
+ *          may share one workspace)
  * ---------------------------------------------------------------------------------- */
 CMC_API int64_t cmc_cbpa_workspace_bytes(int n_subj, int n_tests);
 CMC_API int cmc_cbpa_permute(const double* X, int n_subj, int n_tests,

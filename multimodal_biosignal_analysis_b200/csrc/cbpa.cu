@@ -45,56 +45,100 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
+// The data are re-laid once per call as XT[test / 32][subject][test % 32] (tests padded to a multiple of 32):
+// the subject column of 32 consecutive tests is then NS coalesced 256-byte rows at compile-time offsets from one
+// base address - no per-load address arithmetic in the t-map loop.
+__global__ void __launch_bounds__(256)
+cbpa_tile_kernel(const double* __restrict__ X, int n_subj, int n_tests, double* __restrict__ XT) {
+    const int64_t n_pad = ((int64_t)n_tests + 31) & ~31LL;
+    const int64_t total = n_pad * n_subj;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int lane = (int)(i & 31);
+        const int64_t rest = i >> 5;
+        const int s = (int)(rest % n_subj);
+        const int64_t v = (rest / n_subj) * 32 + lane;
+        XT[i] = v < n_tests ? X[(int64_t)s * n_tests + v] : 0.0;
+    }
+}
+
+__device__ __forceinline__ const double* tile_column(const double* __restrict__ XT, int n_subj, int v) {
+    return XT + (int64_t)(v >> 5) * n_subj * 32 + (v & 31);
+}
+
 // t = mean / sqrt(var(ddof=1) / n) with numpy's evaluation order (oracle/cbpa.py:ttest_1samp_no_p):
-// sequential sums over subjects, no fused multiply-add.
-__device__ __forceinline__ double t_stat(const double* __restrict__ X, const double* sg, int n_subj,
-                                         int n_tests, int v) {
-    double sum = __dmul_rn(X[v], sg[0]);
-    for (int s = 1; s < n_subj; ++s) sum = __dadd_rn(sum, __dmul_rn(X[(int64_t)s * n_tests + v], sg[s]));
+// sequential sums over subjects, no fused multiply-add.  Generic subject count.
+__device__ __forceinline__ double t_stat(const double* __restrict__ XT, const double* sg, int n_subj, int v) {
+    const double* col = tile_column(XT, n_subj, v);
+    double sum = __dmul_rn(col[0], sg[0]);
+    for (int s = 1; s < n_subj; ++s) sum = __dadd_rn(sum, __dmul_rn(col[s * 32], sg[s]));
     const double n = (double)n_subj;
     const double mean = __ddiv_rn(sum, n);
-    double d = __dsub_rn(__dmul_rn(X[v], sg[0]), mean);
+    double d = __dsub_rn(__dmul_rn(col[0], sg[0]), mean);
     double ss = __dmul_rn(d, d);
     for (int s = 1; s < n_subj; ++s) {
-        d = __dsub_rn(__dmul_rn(X[(int64_t)s * n_tests + v], sg[s]), mean);
+        d = __dsub_rn(__dmul_rn(col[s * 32], sg[s]), mean);
         ss = __dadd_rn(ss, __dmul_rn(d, d));
     }
     const double var = __ddiv_rn(ss, (double)(n_subj - 1));
     return __ddiv_rn(mean, __dsqrt_rn(__ddiv_rn(var, n)));
 }
 
-// Same arithmetic with the subject column held in registers and the subject count known at compile time: the
-// NS loads are independent (one L2 latency instead of 2 NS dependent ones), the second pass re-uses them, and
-// the sign flip is an exact XOR of the sign bit (x * (+-1) == x with the sign bit flipped, NaNs included).
-// Evaluation order is unchanged, so t stays bit-identical to the oracle.  (profiles/r01c_cbpa.md)
 // a / B for a compile-time integer B without the generic division sequence: q = RN(a * RN(1/B)) is within one
 // ulp of a / B, and one exact-remainder correction r = a - B q (an FMA), q' = RN(q + r * RN(1/B)) then yields
-// the correctly rounded quotient (Markstein's theorem), i.e. exactly what __ddiv_rn returns.  Outside a safe
-// exponent band (zeros, subnormals, huge values, Inf/NaN) the generic division is used.
+// the correctly rounded quotient (Markstein's theorem), i.e. exactly what __ddiv_rn returns - provided a sits
+// in a safe exponent band (no zeros, subnormals, huge values, Inf/NaN), which div_safe() tests.
 template <int B>
-__device__ __forceinline__ double div_const(double a) {
+__device__ __forceinline__ double div_fast(double a) {
     constexpr double y = 1.0 / (double)B;
-    const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
-    if (e - 100u < 1800u) {
-        const double q = __dmul_rn(a, y);
-        const double r = __fma_rn(-(double)B, q, a);
-        return __fma_rn(r, y, q);
-    }
-    return __ddiv_rn(a, (double)B);
+    const double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-(double)B, q, a);
+    return __fma_rn(r, y, q);
+}
+__device__ __forceinline__ bool div_safe(double a) {
+    return (((unsigned)__double2hiint(a) & 0x7fffffffu) - (100u << 20)) < (1800u << 20);
 }
 
+// Out-of-line form of t_stat with sign-bit masks, for the rare columns t_stat_regs hands over.
+__device__ __noinline__ double t_stat_flip(const double* __restrict__ XT, const unsigned* flip, int n_subj, int v) {
+    const double* col = tile_column(XT, n_subj, v);
+    auto x = [&](int s) {
+        const double a = col[s * 32];
+        return __hiloint2double(__double2hiint(a) ^ (int)flip[s], __double2loint(a));
+    };
+    double sum = x(0);
+    for (int s = 1; s < n_subj; ++s) sum = __dadd_rn(sum, x(s));
+    const double n = (double)n_subj;
+    const double mean = __ddiv_rn(sum, n);
+    double d = __dsub_rn(x(0), mean);
+    double ss = __dmul_rn(d, d);
+    for (int s = 1; s < n_subj; ++s) {
+        d = __dsub_rn(x(s), mean);
+        ss = __dadd_rn(ss, __dmul_rn(d, d));
+    }
+    const double var = __ddiv_rn(ss, (double)(n_subj - 1));
+    return __ddiv_rn(mean, __dsqrt_rn(__ddiv_rn(var, n)));
+}
+
+// Same arithmetic as t_stat with the subject column held in registers and the subject count known at compile
+// time: the NS loads are independent (one L2 latency), the second pass re-uses them, and the sign flip is an
+// exact XOR of the sign bit (x * (+-1) == x with the sign bit flipped, NaNs included).  The three divisions by
+// constants take the two-FMA form; one range test covers all three and falls back to the generic divisions.
+// Evaluation order is unchanged, so t stays bit-identical to the oracle.  (profiles/r01c_cbpa.md)
+// Returns mean and var / n (t = mean / sqrt(var / n)); false = outside the safe band, use t_stat_flip.
 template <int NS>
-__device__ __forceinline__ double t_stat_regs(const double* __restrict__ X, const unsigned* flip, int n_tests, int v) {
+__device__ __forceinline__ bool t_moments_regs(const double* __restrict__ XT, const unsigned* flip, int v,
+                                               double& mean_out, double& vn_out) {
+    const double* col = tile_column(XT, NS, v);
     double xs[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) xs[s] = X[(int64_t)s * n_tests + v];
+    for (int s = 0; s < NS; ++s) xs[s] = col[s * 32];
 #pragma unroll
     for (int s = 0; s < NS; ++s)
         xs[s] = __hiloint2double(__double2hiint(xs[s]) ^ (int)flip[s], __double2loint(xs[s]));
     double sum = xs[0];
 #pragma unroll
     for (int s = 1; s < NS; ++s) sum = __dadd_rn(sum, xs[s]);
-    const double mean = div_const<NS>(sum);
+    const double mean = div_fast<NS>(sum);
     double d = __dsub_rn(xs[0], mean);
     double ss = __dmul_rn(d, d);
 #pragma unroll
@@ -102,8 +146,17 @@ __device__ __forceinline__ double t_stat_regs(const double* __restrict__ X, cons
         d = __dsub_rn(xs[s], mean);
         ss = __dadd_rn(ss, __dmul_rn(d, d));
     }
-    const double var = div_const<NS - 1>(ss);
-    return __ddiv_rn(mean, __dsqrt_rn(div_const<NS>(var)));
+    const double var = div_fast<NS - 1>(ss);
+    const double vn = div_fast<NS>(var);
+    mean_out = mean;
+    vn_out = vn;
+    return div_safe(sum) && div_safe(ss) && div_safe(var);
+}
+
+__device__ __forceinline__ signed char supra_sign(double t, double thr, int tail) {
+    if (tail == 0) return (t > thr) ? 1 : ((t < -thr) ? -1 : 0);
+    if (tail > 0) return (t > thr) ? 1 : 0;
+    return (t < thr) ? -1 : 0;
 }
 
 __device__ __forceinline__ long long t_to_fixed(double t) {
@@ -119,7 +172,7 @@ __device__ __forceinline__ long long t_to_fixed(double t) {
 // masses are order-free).  (profiles/r01c_cbpa.md)
 template <bool OBSERVED, int NS>
 __global__ void __launch_bounds__(kCbpaThreads)
-cbpa_kernel(const double* __restrict__ X, int n_subj, int n_tests, const int8_t* __restrict__ signs,
+cbpa_kernel(const double* __restrict__ XT, int n_subj, int n_tests, const int8_t* __restrict__ signs,
             int64_t n_perm, double thr, int tail, const int32_t* __restrict__ indptr,
             const int32_t* __restrict__ indices, long long* __restrict__ h0,
             double* __restrict__ t_obs, int32_t* __restrict__ root_out, long long* __restrict__ mass_out,
@@ -149,22 +202,30 @@ cbpa_kernel(const double* __restrict__ X, int n_subj, int n_tests, const int8_t*
         }
         if (tid == 0) n_supra = 0;
         __syncthreads();
-        // ---- t-map, threshold, fixed-point image ----
+        // ---- t-map, threshold, fixed-point image (parent / mass are only ever read at supra-threshold nodes) ----
         for (int v = tid; v < n_tests; v += kCbpaThreads) {
-            const double t = NS > 0 ? t_stat_regs<(NS > 0 ? NS : 2)>(X, flip, n_tests, v)
-                                    : t_stat(X, sg, n_subj, n_tests, v);
+            double t = 0.0;
             signed char s = 0;
-            if (tail == 0) s = (t > thr) ? 1 : ((t < -thr) ? -1 : 0);
-            else if (tail > 0) s = (t > thr) ? 1 : 0;
-            else s = (t < thr) ? -1 : 0;
-            sgn[v] = s;
-            parent[v] = s ? v : -1;
-            mass[v] = s ? t_to_fixed(t) : 0;
-            if (OBSERVED) t_obs[v] = t;
-            if (!OBSERVED && s) {
-                const int k = atomicAdd(&n_supra, 1);
-                if (k < list_cap) list[k] = (unsigned short)v;
+            if (NS > 0) {
+                constexpr int NSX = NS > 0 ? NS : 2;
+                double mean, vn;
+                const bool ok = t_moments_regs<NSX>(XT, flip, v, mean, vn);
+                t = ok ? __ddiv_rn(mean, __dsqrt_rn(vn)) : t_stat_flip(XT, flip, n_subj, v);
+                s = supra_sign(t, thr, tail);
+            } else {
+                t = t_stat(XT, sg, n_subj, v);
+                s = supra_sign(t, thr, tail);
             }
+            sgn[v] = s;
+            if (s) {
+                parent[v] = v;
+                mass[v] = t_to_fixed(t);
+                if (!OBSERVED) {
+                    const int k = atomicAdd(&n_supra, 1);
+                    if (k < list_cap) list[k] = (unsigned short)v;
+                }
+            }
+            if (OBSERVED) t_obs[v] = t;
         }
         __syncthreads();
         CBPA_TICK(1);
@@ -341,10 +402,32 @@ extern "C" CMC_API int cmc_dbg_cbpa_cycles(unsigned long long* out, int reset) {
 }
 #endif
 
+namespace cmc {
+static int64_t cbpa_labels_bytes(int n_tests) {
+    return ((int64_t)n_tests * 16 + 256 + 255) & ~255LL;           // root int32 + rank int32 + mass_root int64 per test
+}
+// Re-tiles X into the workspace (after the labelling scratch) and returns the tiled copy.
+static int cbpa_tile(const double* X, int n_subj, int n_tests, void* ws, int64_t ws_bytes, cudaStream_t st,
+                     const double** XT, const char* who) {
+    if (!ws || ws_bytes < cmc_cbpa_workspace_bytes(n_subj, n_tests)) {
+        set_error("%s: workspace %lld < %lld bytes", who, (long long)ws_bytes,
+                  (long long)cmc_cbpa_workspace_bytes(n_subj, n_tests));
+        return CMC_EWORKSPACE;
+    }
+    CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "%s: workspace must be 16-byte aligned", who);
+    double* xt = reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + cbpa_labels_bytes(n_tests));
+    const int64_t total = (((int64_t)n_tests + 31) & ~31LL) * n_subj;
+    const int64_t blocks = (total + 255) / 256;
+    cbpa_tile_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(X, n_subj, n_tests, xt);
+    CMC_CHECK_LAUNCH("cbpa_tile_kernel");
+    *XT = xt;
+    return CMC_OK;
+}
+}  // namespace cmc
+
 extern "C" int64_t cmc_cbpa_workspace_bytes(int n_subj, int n_tests) {
-    (void)n_subj;
-    // root int32 + rank int32 + mass_root int64 per test
-    return (int64_t)n_tests * 16 + 256;
+    // labelling scratch + the tiled copy of X (tests padded to a multiple of 32)
+    return cmc::cbpa_labels_bytes(n_tests) + (((int64_t)n_tests + 31) & ~31LL) * n_subj * 8;
 }
 
 extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const int8_t* signs,
@@ -352,12 +435,17 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
                                 const int32_t* indptr, const int32_t* indices, int64_t* h0_fixed,
                                 void* ws, int64_t ws_bytes, void* stream) {
     using namespace cmc;
-    (void)ws; (void)ws_bytes;
     int rc = cbpa_check(X, n_subj, n_tests, indptr, indices, tail, thr);
     if (rc) return rc;
     CMC_REQUIRE(signs && h0_fixed && p_end >= p_begin, "cmc_cbpa_permute: bad permutation range");
     const int64_t n_perm = p_end - p_begin;
     if (n_perm == 0) return CMC_OK;
+    const double* XT = nullptr;
+    rc = cbpa_tile(X, n_subj, n_tests, ws, ws_bytes, static_cast<cudaStream_t>(stream), &XT, "cmc_cbpa_permute");
+    if (rc) return rc;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int list_cap = cbpa_list_cap(n_subj, n_tests);
     const size_t smem = cbpa_smem_bytes(n_subj, n_tests, list_cap);
     // exact subject count as a template parameter for the usual group sizes, generic loop otherwise
@@ -377,14 +465,11 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
     }
     rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
     if (rc) return rc;
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCbpaThreads, smem);
     if (per_sm < 1) per_sm = 1;
     const int64_t grid = n_perm < (int64_t)sms * per_sm ? n_perm : (int64_t)sms * per_sm;
     kern<<<(unsigned)grid, kCbpaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        X, n_subj, n_tests, signs + p_begin * n_subj, n_perm, thr, tail, indptr, indices,
+        XT, n_subj, n_tests, signs + p_begin * n_subj, n_perm, thr, tail, indptr, indices,
         reinterpret_cast<long long*>(h0_fixed), nullptr, nullptr, nullptr, list_cap);
     CMC_CHECK_LAUNCH("cbpa_kernel<perm>");
     return CMC_OK;
@@ -397,13 +482,11 @@ extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, doubl
     using namespace cmc;
     int rc = cbpa_check(X, n_subj, n_tests, indptr, indices, tail, thr);
     if (rc) return rc;
-    CMC_REQUIRE(t_obs && labels && mass_fixed && mass_f64 && n_clusters && ws, "cmc_cbpa_observed: null pointer");
-    if (ws_bytes < cmc_cbpa_workspace_bytes(n_subj, n_tests)) {
-        set_error("cmc_cbpa_observed: workspace %lld < %lld bytes", (long long)ws_bytes,
-                  (long long)cmc_cbpa_workspace_bytes(n_subj, n_tests));
-        return CMC_EWORKSPACE;
-    }
-    CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "cmc_cbpa_observed: workspace must be 8-byte aligned");
+    CMC_REQUIRE(t_obs && labels && mass_fixed && mass_f64 && n_clusters, "cmc_cbpa_observed: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double* XT = nullptr;
+    rc = cbpa_tile(X, n_subj, n_tests, ws, ws_bytes, st, &XT, "cmc_cbpa_observed");
+    if (rc) return rc;
     long long* mass_root = reinterpret_cast<long long*>(ws);
     int32_t* root = reinterpret_cast<int32_t*>(mass_root + n_tests);
     int32_t* rank = root + n_tests;
@@ -411,8 +494,7 @@ extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, doubl
     const size_t smem = cbpa_smem_bytes(n_subj, n_tests, 0);
     rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true, 0>), smem);
     if (rc) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cbpa_kernel<true, 0><<<1, kCbpaThreads, smem, st>>>(X, n_subj, n_tests, nullptr, 1, thr, tail, indptr,
+    cbpa_kernel<true, 0><<<1, kCbpaThreads, smem, st>>>(XT, n_subj, n_tests, nullptr, 1, thr, tail, indptr,
                                                      indices, h0_tmp, t_obs, root, mass_root, 0);
     CMC_CHECK_LAUNCH("cbpa_kernel<observed>");
     cbpa_label_kernel<<<1, 1024, 0, st>>>(root, mass_root, n_tests, labels,

@@ -258,8 +258,10 @@ def cbpa_permute(X: torch.Tensor, signs: torch.Tensor, p_begin: int, p_end: int,
         raise ValueError("permutation range outside the sign table")
     h0 = torch.empty(p_end - p_begin, dtype=torch.int64, device=X.device)
     lib = _lib.load()
+    ws_bytes = int(lib.cmc_cbpa_workspace_bytes(n_subj, n_tests))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
     rc = lib.cmc_cbpa_permute(X.data_ptr(), n_subj, n_tests, signs.data_ptr(), p_begin, p_end, float(thr),
-                              int(tail), indptr.data_ptr(), indices.data_ptr(), h0.data_ptr(), None, 0,
-                              _lib.current_stream())
+                              int(tail), indptr.data_ptr(), indices.data_ptr(), h0.data_ptr(), ws.data_ptr(),
+                              ws_bytes, _lib.current_stream())
     _lib.check(rc, "cmc_cbpa_permute")
     return h0
