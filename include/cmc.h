@@ -148,7 +148,8 @@ CMC_API int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne, in
  *        channels: table index = word (f & 3) of Philox4x32-10(key = seed, counter =
  *        (s, l, f >> 2, s >> 32)) >> 20; s runs over GLOBAL indices [s_begin, s_end) so
  *        results do not depend on how surrogates are sharded.  BF16 tensor-core GEMM with
- *        the phase panel resident in shared memory: needs 2 L <= 512.
+ *        the phase panel resident in shared memory for 2 L <= 512, streamed with the B
+ *        tiles for longer segment axes (2 L <= 12288).
  *   coh_obs  [F][Ne][Nm]  observed coherence to compare against
  *   exceed   [F][Ne][Nm]  uint32, += #{s : C_s >= coh_obs}   (caller zero-initialises)
  *   max_stat [s_end - s_begin] float32 max over (f, i, j) of C_s

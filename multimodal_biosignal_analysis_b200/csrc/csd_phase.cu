@@ -30,8 +30,10 @@ constexpr int kPhM = 128;            // surrogates per panel
 constexpr int kPhPairs = 128;        // pairs per B tile
 constexpr int kPhN = 2 * kPhPairs;   // B tile rows (re-forms then im-forms)
 constexpr int kPhKB = 64;            // bf16 per k-block = 128 bytes
-constexpr int kPhStages = 3;
-constexpr int kPhBBytes = kPhN * 128;   // 32 KB per stage
+constexpr int kPhStages = 3;             // B ring of the resident-panel variant
+constexpr int kPhStagesStream = 4;       // (A block + B block) ring of the streamed-panel variant
+constexpr int kPhABytes = kPhM * 128;    // 16 KB: one k-block of the A panel
+constexpr int kPhBBytes = kPhN * 128;    // 32 KB: one k-block of a B tile
 constexpr int kPhThreads = 256;
 constexpr int kPhaseN = 1 << CMC_PHASE_TABLE_BITS;
 
@@ -160,8 +162,8 @@ struct PhaseParams {
 };
 
 struct __align__(8) PhaseBarriers {
-    uint64_t full[kPhStages];
-    uint64_t empty[kPhStages];
+    uint64_t full[kPhStagesStream];
+    uint64_t empty[kPhStagesStream];
     uint64_t a_full;
     uint64_t a_empty;
     uint64_t tmem_full[2];
@@ -170,14 +172,21 @@ struct __align__(8) PhaseBarriers {
     uint32_t pad;
 };
 
+// STREAM_A = false: the A panel of the CTA's (frequency, surrogate panel) is resident (2L <= 512).
+// STREAM_A = true : long segment axes - every ring stage carries the A k-block next to the B k-block, the panel
+//                   is re-read from L2 for each pair tile (1.5 x the operand traffic, no limit on L).
+template <bool STREAM_A>
 __global__ void __launch_bounds__(kPhThreads, 1)
 phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const PhaseParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const int a_bytes = p.KB * kPhM * 128;                     // resident A panel: KB k-blocks of 16 KB
+    constexpr int kStages = STREAM_A ? kPhStagesStream : kPhStages;
+    constexpr int kStageBytes = STREAM_A ? kPhABytes + kPhBBytes : kPhBBytes;
+    constexpr int kBOff = STREAM_A ? kPhABytes : 0;            // B block inside a stage
+    const int a_bytes = STREAM_A ? 0 : p.KB * kPhABytes;       // resident A panel: KB k-blocks of 16 KB
     unsigned char* sA = base;
-    unsigned char* sB = base + a_bytes;                        // [kPhStages][32 KB]
-    float* cobs_s = reinterpret_cast<float*>(sB + kPhStages * kPhBBytes);   // [128]
+    unsigned char* sB = base + a_bytes;                        // [kStages][kStageBytes]
+    float* cobs_s = reinterpret_cast<float*>(sB + kStages * kStageBytes);   // [128]
     uint32_t* cnt_s = reinterpret_cast<uint32_t*>(cobs_s + kPhPairs);       // [128]
     PhaseBarriers* bars = reinterpret_cast<PhaseBarriers*>(cnt_s + kPhPairs);
 
@@ -185,7 +194,7 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     const int n_panels = p.F * p.MT;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kPhStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
@@ -215,18 +224,22 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             uint32_t phase = 0, a_phase = 0;
             for (int pn = blockIdx.x; pn < n_panels; pn += gridDim.x) {
                 const int f = pn / p.MT, mt = pn - f * p.MT;
-                mbar_wait(&bars->a_empty, a_phase ^ 1);           // previous panel fully consumed
-                mbar_arrive_expect_tx(&bars->a_full, (uint32_t)a_bytes);
-                for (int kb = 0; kb < p.KB; ++kb)
-                    tma_load_2d(sA + kb * kPhM * 128, &mA, &bars->a_full, kb * kPhKB, f * p.S_pad + mt * kPhM);
-                a_phase ^= 1;
+                if (!STREAM_A) {
+                    mbar_wait(&bars->a_empty, a_phase ^ 1);       // previous panel fully consumed
+                    mbar_arrive_expect_tx(&bars->a_full, (uint32_t)a_bytes);
+                    for (int kb = 0; kb < p.KB; ++kb)
+                        tma_load_2d(sA + kb * kPhABytes, &mA, &bars->a_full, kb * kPhKB, f * p.S_pad + mt * kPhM);
+                    a_phase ^= 1;
+                }
                 for (int nt = 0; nt < p.NT; ++nt)
                     for (int kb = 0; kb < p.KB; ++kb) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&bars->full[stage], kPhBBytes);
-                        tma_load_2d(sB + stage * kPhBBytes, &mB, &bars->full[stage], kb * kPhKB,
-                                    f * p.R_pad + nt * kPhN);
-                        if (++stage == kPhStages) { stage = 0; phase ^= 1; }
+                        mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+                        unsigned char* st = sB + stage * kStageBytes;
+                        if (STREAM_A)
+                            tma_load_2d(st, &mA, &bars->full[stage], kb * kPhKB, f * p.S_pad + mt * kPhM);
+                        tma_load_2d(st + kBOff, &mB, &bars->full[stage], kb * kPhKB, f * p.R_pad + nt * kPhN);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
             }
         }
@@ -237,9 +250,11 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0, a_phase = 0, it = 0;
             for (int pn = blockIdx.x; pn < n_panels; pn += gridDim.x) {
-                mbar_wait(&bars->a_full, a_phase);
-                a_phase ^= 1;
-                tc_fence_after();
+                if (!STREAM_A) {
+                    mbar_wait(&bars->a_full, a_phase);
+                    a_phase ^= 1;
+                    tc_fence_after();
+                }
                 for (int nt = 0; nt < p.NT; ++nt) {
                     const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
                     mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
@@ -248,19 +263,19 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                     for (int kb = 0; kb < p.KB; ++kb) {
                         mbar_wait(&bars->full[stage], phase);
                         tc_fence_after();
-                        const uint32_t a0 = smem_u32(sA + kb * kPhM * 128);
-                        const uint32_t b0 = smem_u32(sB + stage * kPhBBytes);
+                        const uint32_t a0 = smem_u32(STREAM_A ? sB + stage * kStageBytes : sA + kb * kPhABytes);
+                        const uint32_t b0 = smem_u32(sB + stage * kStageBytes + kBOff);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16(d, make_smem_desc_k_sw128(a0 + k * 32), make_smem_desc_k_sw128(b0 + k * 32),
                                       idesc, (kb | k) != 0 ? 1u : 0u);
                         umma_commit(&bars->empty[stage]);
-                        if (++stage == kPhStages) { stage = 0; phase ^= 1; }
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(&bars->tmem_full[acc]);
                     ++it;
                 }
-                umma_commit(&bars->a_empty);                      // A panel may be overwritten
+                if (!STREAM_A) umma_commit(&bars->a_empty);       // A panel may be overwritten
             }
         }
     } else if (warp >= 4) {
@@ -366,11 +381,11 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
         return CMC_EWORKSPACE;
     }
     CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws2) & 255) == 0, "cmc_surrogate_null: workspace must be 256-byte aligned");
-    const size_t smem = 1024 + (size_t)y.KB * kPhM * 128 + kPhStages * kPhBBytes + kPhPairs * 8 + sizeof(PhaseBarriers) + 16;
-    if (smem > 227 * 1024) {
-        set_error("cmc_surrogate_null: L=%d too long for the resident phase panel (2L <= 512)", L);
-        return CMC_EUNSUPPORTED;
-    }
+    const size_t tail_bytes = kPhPairs * 8 + sizeof(PhaseBarriers) + 16;
+    size_t smem = 1024 + (size_t)y.KB * kPhABytes + kPhStages * kPhBBytes + tail_bytes;
+    const bool stream_a = smem > 227 * 1024;                    // 2L > 512: the panel no longer fits next to the ring
+    if (stream_a) smem = 1024 + (size_t)kPhStagesStream * (kPhABytes + kPhBBytes) + tail_bytes;
+    CMC_REQUIRE((size_t)y.KPb * 4 <= 48 * 1024, "cmc_surrogate_null: L=%d too long (2L <= 12288)", L);
     const uint32_t* table;
     int rc = get_phase_table(&table);
     if (rc) return rc;
@@ -381,7 +396,8 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
     __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w2 + y.off_Z);
     rc = check_cuda(cudaMemsetAsync(max_u, 0, (size_t)y.S_pad * 4, st), "memset(max_u)");
     if (rc) return rc;
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(phase_gemm_kernel), smem);
+    auto gemm = stream_a ? phase_gemm_kernel<true> : phase_gemm_kernel<false>;
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(gemm), smem);
     if (rc) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -415,7 +431,7 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
         p.exceed = exceed + (int64_t)f0 * y.n_pairs;
         p.max_u = max_u;
         const int n_panels = fc * y.MT;
-        phase_gemm_kernel<<<n_panels < sms ? n_panels : sms, kPhThreads, smem, st>>>(mA, mB, p);
+        gemm<<<n_panels < sms ? n_panels : sms, kPhThreads, smem, st>>>(mA, mB, p);
         CMC_CHECK_LAUNCH("phase_gemm_kernel");
     }
     phase_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(max_u, n, max_stat);

@@ -35,11 +35,15 @@ def all_gather_ranges(local: torch.Tensor, n_total: int) -> torch.Tensor:
         return local
     sizes = [shard_range(n_total, r, ws) for r in range(ws)]
     width = max(e - b for b, e in sizes)
+    if n_total == width * ws:                                    # equal slices: one collective, no repacking
+        out = torch.empty(n_total, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
     padded = torch.zeros(width, dtype=local.dtype, device=local.device)
     padded[: local.numel()] = local
-    gathered = [torch.empty_like(padded) for _ in range(ws)]
-    dist.all_gather(gathered, padded)
-    return torch.cat([g[: e - b] for g, (b, e) in zip(gathered, sizes)])
+    out = torch.empty(width * ws, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    return torch.cat([out[r * width: r * width + (e - b)] for r, (b, e) in enumerate(sizes)])
 
 
 def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:

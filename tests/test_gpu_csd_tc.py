@@ -200,3 +200,35 @@ def test_phase_surrogate_null_is_calibrated(cuda_device):
     assert abs(p.mean() - 0.5) < 0.03
     assert abs(np.mean(p < 0.05) - 0.05) < 0.02
     assert np.all(max_stat.cpu().numpy() > 0) and np.all(max_stat.cpu().numpy() <= 1)
+
+
+def test_phase_surrogates_long_segment_axis_streams_the_panel(cuda_device):
+    """L = 300 segments (2L = 600 > 512): the phase panel no longer fits in shared memory and is streamed with
+    the B tiles; same definition, same tolerances, and shards still reproduce the unsharded run."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(77)
+    N, L, ne, nm, n_surr = 64, 300, 5, 70, 150
+    t = np.arange(N * L)
+    common = np.sin(2 * np.pi * 0.11 * t)
+    eeg = (rng.standard_normal((N * L, ne)) + 0.5 * common[:, None]).astype(np.float32)
+    emg = (rng.standard_normal((N * L, nm)) + 0.5 * np.roll(common, 2)[:, None]).astype(np.float32)
+    starts = (np.arange(L) * N).astype(np.int64)
+    X, Y = _welch_spectra(eeg, emg, starts, N, 2, 10)
+    res = K.csd_msc(X, Y)
+    seed = 99
+    exceed, max_stat = K.surrogate_null(res, K.SURR_PHASE, 0, n_surr, seed=seed)
+    table = _phase_table_from_lib()
+    Xo, Yo = _oracle_spectra(eeg, emg, starts, N, 2, 10)
+    Xw, _ = osur.whiten(Xo)
+    Yw, _ = osur.whiten(Yo)
+    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed, table=table, quantise_z=True)
+    coh_obs = res.coh.cpu().numpy().astype(np.float64)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+2e-5)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-2e-5)
+    got = exceed.cpu().numpy().astype(np.int64)
+    assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 2e-5
+    e2, m_a = K.surrogate_null(res, K.SURR_PHASE, 0, 70, seed=seed)
+    e2, m_b = K.surrogate_null(res, K.SURR_PHASE, 70, n_surr, seed=seed, exceed=e2)
+    np.testing.assert_array_equal(e2.cpu().numpy(), exceed.cpu().numpy())
+    np.testing.assert_array_equal(torch.cat([m_a, m_b]).cpu().numpy(), max_stat.cpu().numpy())
