@@ -669,10 +669,11 @@ def pooled_coherence(eeg_array, emg_array, sampling_freq: float, segment_starts,
     K.check_segments(segment_starts, N, eeg_array.shape[0])
     starts_d = torch.as_tensor(np.asarray(segment_starts, dtype=np.int64)).to(dev)
     wd = torch.from_numpy(windows).to(dev)
-    X = K.fft_segments(_to_device_f32(eeg_array), starts_d, wd, detrend, lo, hi)
-    Y = K.fft_segments(_to_device_f32(emg_array), starts_d, wd, detrend, lo, hi)
-    L = X.shape[0] * X.shape[1]
-    csd = K.csd_msc(X.view(L, X.shape[2], X.shape[3]), Y.view(L, Y.shape[2], Y.shape[3]))
+    # K1 writes K-major rows (bin, channel, segment x taper) that the fused K2 kernel contracts as they lie:
+    # no pack pass; the operand planes of the surrogate nulls are built on demand
+    Xk, L = K.fft_segments_kmajor(_to_device_f32(eeg_array), starts_d, wd, detrend, lo, hi)
+    Yk, _ = K.fft_segments_kmajor(_to_device_f32(emg_array), starts_d, wd, detrend, lo, hi)
+    csd = K.csd_msc_kmajor(Xk, Yk, L)
     return PooledCoherence(csd, freqs[lo:hi + 1], n_win, host)
 
 
