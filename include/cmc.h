@@ -147,6 +147,21 @@ CMC_API int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne, in
                 float* coh, float* sxx, float* syy, float* sxy,
                 void* ws, int64_t ws_bytes, void* stream);
 
+/* Coherence only, straight from the spectra (same arguments and results as cmc_csd_msc): the spectra are
+ * staged by TMA as MN-major operands (M = (channel, re/im), K = segment), split into TF32 hi/lo and reduced
+ * to auto-spectra in shared memory - one read of X and Y, no pack pass, no operand planes.  ws only receives
+ * the auto-spectra: cmc_csd_workspace_bytes_min(F, Ne, Nm) bytes suffice when ldx and ldy are even and X, Y
+ * are 16-byte aligned; other layouts fall back to cmc_csd_msc and need its full workspace.
+ * cmc_csd_operands fills the operand planes (and auto-spectra) of a full-size workspace for
+ * cmc_surrogate_null without computing the coherence again. */
+CMC_API int64_t cmc_csd_workspace_bytes_min(int F, int Ne, int Nm);
+CMC_API int cmc_csd_coherence(const float* X, const float* Y, int L, int F, int Ne, int Nm,
+                      int64_t ldx, int64_t ldy,
+                      float* coh, float* sxx, float* syy, float* sxy,
+                      void* ws, int64_t ws_bytes, void* stream);
+CMC_API int cmc_csd_operands(const float* X, const float* Y, int L, int F, int Ne, int Nm,
+                     int64_t ldx, int64_t ldy, void* ws, int64_t ws_bytes, void* stream);
+
 /* K2 from K-major rows (cmc_fft_segments_kmajor): Xk [F][Ne][pitch_x], Yk [F][Nm][pitch_y]
  * complex64, pitches in complex elements (even, >= L), 16-byte aligned; same outputs and
  * arithmetic as cmc_csd_msc.  The TF32 split, the i*X rows and the auto-spectra are derived in
@@ -156,7 +171,6 @@ CMC_API int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne, in
  *                       be as small as cmc_csd_workspace_bytes_min(F, Ne, Nm).
  * cmc_csd_operands_kmajor fills the planes later (ws must then have the full size and hold the
  * auto-spectra of the cmc_csd_msc_kmajor call). */
-CMC_API int64_t cmc_csd_workspace_bytes_min(int F, int Ne, int Nm);
 CMC_API int cmc_csd_msc_kmajor(const float* Xk, const float* Yk, int L, int F, int Ne, int Nm,
                        int64_t pitch_x, int64_t pitch_y,
                        float* coh, float* sxx, float* syy, float* sxy,

@@ -30,6 +30,8 @@ _SIGNATURES = {
                                           _vp, _i64, _vp]),
     "cmc_csd_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "cmc_csd_workspace_bytes_min": (_i64, [_i32, _i32, _i32]),
+    "cmc_csd_coherence": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "cmc_csd_operands": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i64, _vp]),
     "cmc_csd_msc_kmajor": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
                                      _i32, _vp]),
     "cmc_csd_operands_kmajor": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i64, _vp]),

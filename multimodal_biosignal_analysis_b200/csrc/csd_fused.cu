@@ -347,10 +347,6 @@ static int launch_planes(const float* Xk, const float* Yk, const CsdLayout& y, i
 }
 }  // namespace cmc
 
-extern "C" int64_t cmc_csd_workspace_bytes_min(int F, int Ne, int Nm) {
-    return cmc::csd_layout(1, F, Ne, Nm).off_ahi;                   // auto-spectra only
-}
-
 extern "C" int cmc_csd_operands_kmajor(const float* Xk, const float* Yk, int L, int F, int Ne, int Nm, int64_t pitch_x,
                                        int64_t pitch_y, void* ws, int64_t ws_bytes, void* stream) {
     using namespace cmc;

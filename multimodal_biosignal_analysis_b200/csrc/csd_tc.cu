@@ -424,6 +424,32 @@ __global__ void shift_gather_kernel(const int32_t* __restrict__ shifts, int64_t 
     }
 }
 
+bool csd_direct_ok(const float* X, const float* Y, int64_t ldx, int64_t ldy);
+int csd_msc_direct(const float* X, const float* Y, int L, int F, int Ne, int Nm, int64_t ldx, int64_t ldy, float* coh,
+                   float* sxx, float* syy, float* sxy, unsigned char* w, const CsdLayout& y, cudaStream_t st);
+
+static int csd_common_check(const float* X, const float* Y, int L, int F, int Ne, int Nm, int64_t ldx, int64_t ldy,
+                            const void* ws, const CsdLayout& y) {
+    CMC_REQUIRE(X && Y && ws, "cmc_csd_*: null pointer");
+    CMC_REQUIRE(L >= 1 && F >= 1 && Ne >= 1 && Nm >= 1 && ldx >= Ne && ldy >= Nm, "cmc_csd_*: bad shape");
+    CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "cmc_csd_*: workspace must be 256-byte aligned");
+    CMC_REQUIRE((int64_t)F * y.MT * kTileM < (1ll << 31) && (int64_t)F * y.NT * kTileN < (1ll << 31) && F <= 65535,
+                "cmc_csd_*: operand too large");
+    return CMC_OK;
+}
+
+// pack pass alone: operand planes + auto-spectra into the workspace
+static int launch_pack(const float* X, const float* Y, int L, int F, int Ne, int Nm, int64_t ldx, int64_t ldy,
+                       float* sxx, float* syy, unsigned char* w, const CsdLayout& y, cudaStream_t st) {
+    pack_fused_kernel<<<dim3(F, 2 * y.MT + 2 * y.NT), dim3(32, 8), 0, st>>>(
+        reinterpret_cast<const float2*>(X), ldx, Ne, reinterpret_cast<const float2*>(Y), ldy, Nm, L, F, y.MT, y.NT, y.KP,
+        reinterpret_cast<float*>(w + y.off_ahi), reinterpret_cast<float*>(w + y.off_alo),
+        reinterpret_cast<float*>(w + y.off_bhi), reinterpret_cast<float*>(w + y.off_blo),
+        reinterpret_cast<float*>(w + y.off_pxx), reinterpret_cast<float*>(w + y.off_pyy), sxx, syy);
+    CMC_CHECK_LAUNCH("pack_fused_kernel");
+    return CMC_OK;
+}
+
 int64_t phase_workspace_bytes(int L, int F, int Ne, int Nm, int64_t n_surr);
 int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
                          const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2, int64_t ws2_bytes,
@@ -464,6 +490,44 @@ extern "C" int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne,
     p.coh = coh; p.sxy = reinterpret_cast<float2*>(sxy); p.pxx = pxx; p.pyy = pyy;
     p.total_tiles = (long long)F * y.MT * y.NT;
     return launch_gemm<0>(y, w, p, st);
+}
+
+extern "C" int64_t cmc_csd_workspace_bytes_min(int F, int Ne, int Nm) {
+    if (F < 1 || Ne < 1 || Nm < 1) return CMC_EINVAL;
+    return cmc::csd_layout(1, F, Ne, Nm).off_ahi;                   // auto-spectra only
+}
+
+extern "C" int cmc_csd_coherence(const float* X, const float* Y, int L, int F, int Ne, int Nm, int64_t ldx, int64_t ldy,
+                                 float* coh, float* sxx, float* syy, float* sxy, void* ws, int64_t ws_bytes,
+                                 void* stream) {
+    using namespace cmc;
+    const CsdLayout y = csd_layout(L, F, Ne, Nm);
+    int rc = csd_common_check(X, Y, L, F, Ne, Nm, ldx, ldy, ws, y);
+    if (rc) return rc;
+    CMC_REQUIRE(coh, "cmc_csd_coherence: null pointer");
+    static const bool no_direct = getenv("CMC_CSD_NO_DIRECT") != nullptr;
+    if (no_direct || !csd_direct_ok(X, Y, ldx, ldy))     // odd channel pitch: TMA cannot address the rows
+        return cmc_csd_msc(X, Y, L, F, Ne, Nm, ldx, ldy, coh, sxx, syy, sxy, ws, ws_bytes, stream);
+    if (ws_bytes < y.off_ahi) {
+        set_error("cmc_csd_coherence: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)y.off_ahi);
+        return CMC_EWORKSPACE;
+    }
+    return csd_msc_direct(X, Y, L, F, Ne, Nm, ldx, ldy, coh, sxx, syy, sxy, static_cast<unsigned char*>(ws), y,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cmc_csd_operands(const float* X, const float* Y, int L, int F, int Ne, int Nm, int64_t ldx, int64_t ldy,
+                                void* ws, int64_t ws_bytes, void* stream) {
+    using namespace cmc;
+    const CsdLayout y = csd_layout(L, F, Ne, Nm);
+    int rc = csd_common_check(X, Y, L, F, Ne, Nm, ldx, ldy, ws, y);
+    if (rc) return rc;
+    if (ws_bytes < y.total) {
+        set_error("cmc_csd_operands: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)y.total);
+        return CMC_EWORKSPACE;
+    }
+    return launch_pack(X, Y, L, F, Ne, Nm, ldx, ldy, nullptr, nullptr, static_cast<unsigned char*>(ws), y,
+                       static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int64_t cmc_surrogate_workspace_bytes(int L, int F, int Ne, int Nm, int mode, int64_t n_surr) {

@@ -64,6 +64,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM / tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -138,6 +145,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_k_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(1) << 46;                             // descriptor version (Blackwell)
     d |= static_cast<uint64_t>(2) << 61;                             // SWIZZLE_128B
     return d;
+}
+// UMMA shared-memory descriptor, MN-major 32-bit operand tile.  TF32 operands that are contiguous along M/N must
+// use the 128-byte swizzle with a 32-byte base (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; 32-byte chunk index
+// XOR (k-row & 3)): k-rows of 128 bytes (32 fp32 along M/N), swizzle atoms of 4 k-rows = 512 bytes apart along K
+// (SBO), 32-element M/N atoms `atom_pitch` bytes apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128_b32(uint32_t smem_addr, uint32_t atom_pitch) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);          // start address  [0,14)
+    d |= static_cast<uint64_t>(atom_pitch >> 4) << 16;               // leading byte offset [16,30)
+    d |= static_cast<uint64_t>(512 >> 4) << 32;                      // stride byte offset [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                             // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(1) << 61;                             // SWIZZLE_128B_BASE32B
+    return d;
+}
+// instruction descriptor: TF32 x TF32 -> FP32, both operands MN-major (bits 15 / 16), dense
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
 }
 // instruction descriptor: TF32 x TF32 -> FP32, both operands K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {

@@ -192,32 +192,45 @@ def _pooled_dims(X, Y):
 class PooledCsd:
     """Result of the tensor-core CSD pass; keeps (or can rebuild) the operands of the surrogate null."""
 
-    def __init__(self, coh, sxx, syy, sxy, ws, dims, kmajor=None):
+    def __init__(self, coh, sxx, syy, sxy, ws, dims, pending=None):
         self.coh, self.sxx, self.syy, self.sxy, self.ws, self.dims = coh, sxx, syy, sxy, ws, dims
-        self._kmajor = kmajor           # (Xk, Yk) while the operand planes of ws are not filled yet
+        # ("std", X, Y, ldx, ldy) or ("kmajor", Xk, Yk) while the operand planes of ws are not filled yet
+        self._pending = pending
 
     def ensure_operands(self) -> None:
         """Fill the TF32 operand planes the surrogate kernels read (no-op when already present)."""
-        if self._kmajor is None:
+        if self._pending is None:
             return
-        Xk, Yk = self._kmajor
         L, F, Ne, Nm = self.dims
         lib = _lib.load()
         ws_bytes = int(lib.cmc_csd_workspace_bytes(L, F, Ne, Nm))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.coh.device)
-        ws[: self.ws.numel()].copy_(self.ws)                      # auto-spectra of the coherence pass
-        rc = lib.cmc_csd_operands_kmajor(Xk.data_ptr(), Yk.data_ptr(), L, F, Ne, Nm, Xk.shape[2], Yk.shape[2],
-                                         ws.data_ptr(), ws_bytes, _lib.current_stream())
-        _lib.check(rc, "cmc_csd_operands_kmajor")
-        self.ws, self._kmajor = ws, None
+        if self._pending[0] == "std":
+            _, X, Y, ldx, ldy = self._pending
+            rc = lib.cmc_csd_operands(X.data_ptr(), Y.data_ptr(), L, F, Ne, Nm, ldx, ldy, ws.data_ptr(), ws_bytes,
+                                      _lib.current_stream())
+            _lib.check(rc, "cmc_csd_operands")
+        else:
+            _, Xk, Yk = self._pending
+            ws[: self.ws.numel()].copy_(self.ws)                  # auto-spectra of the coherence pass
+            rc = lib.cmc_csd_operands_kmajor(Xk.data_ptr(), Yk.data_ptr(), L, F, Ne, Nm, Xk.shape[2], Yk.shape[2],
+                                             ws.data_ptr(), ws_bytes, _lib.current_stream())
+            _lib.check(rc, "cmc_csd_operands_kmajor")
+        self.ws, self._pending = ws, None
 
 
-def csd_msc(X: torch.Tensor, Y: torch.Tensor, want_sxy: bool = False) -> PooledCsd:
-    """Pooled coherence over the leading axis on the tensor cores: coh (F, Ne, Nm)."""
+def csd_msc(X: torch.Tensor, Y: torch.Tensor, want_sxy: bool = False, keep_operands: bool = False) -> PooledCsd:
+    """Pooled coherence over the leading axis on the tensor cores: coh (F, Ne, Nm).
+
+    By default only the coherence pass runs (the spectra are read once, straight from their (L, F, C) layout);
+    the operand planes of the surrogate nulls are built on the first :func:`surrogate_null` call, or right away
+    with ``keep_operands=True`` (pack + GEMM path)."""
     L, F, Ne, Nm, ldx, ldy = _pooled_dims(X, Y)
     dev = X.device
     lib = _lib.load()
-    ws_bytes = int(lib.cmc_csd_workspace_bytes(L, F, Ne, Nm))
+    direct = (not keep_operands and ldx % 2 == 0 and ldy % 2 == 0 and X.data_ptr() % 16 == 0
+              and Y.data_ptr() % 16 == 0)
+    ws_bytes = int(lib.cmc_csd_workspace_bytes_min(F, Ne, Nm) if direct else lib.cmc_csd_workspace_bytes(L, F, Ne, Nm))
     if ws_bytes < 0:
         _lib.check(ws_bytes, "cmc_csd_workspace_bytes")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -225,10 +238,11 @@ def csd_msc(X: torch.Tensor, Y: torch.Tensor, want_sxy: bool = False) -> PooledC
     sxx = torch.empty((F, Ne), dtype=torch.float32, device=dev)
     syy = torch.empty((F, Nm), dtype=torch.float32, device=dev)
     sxy = torch.empty((F, Ne, Nm), dtype=torch.complex64, device=dev) if want_sxy else None
-    rc = lib.cmc_csd_msc(X.data_ptr(), Y.data_ptr(), L, F, Ne, Nm, ldx, ldy, coh.data_ptr(), sxx.data_ptr(),
-                         syy.data_ptr(), _lib.ptr(sxy), ws.data_ptr(), ws_bytes, _lib.current_stream())
-    _lib.check(rc, "cmc_csd_msc")
-    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm))
+    fn = lib.cmc_csd_coherence if direct else lib.cmc_csd_msc
+    rc = fn(X.data_ptr(), Y.data_ptr(), L, F, Ne, Nm, ldx, ldy, coh.data_ptr(), sxx.data_ptr(), syy.data_ptr(),
+            _lib.ptr(sxy), ws.data_ptr(), ws_bytes, _lib.current_stream())
+    _lib.check(rc, "cmc_csd_coherence" if direct else "cmc_csd_msc")
+    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm), pending=("std", X, Y, ldx, ldy) if direct else None)
 
 
 def csd_msc_kmajor(Xk: torch.Tensor, Yk: torch.Tensor, L: int, want_sxy: bool = False,
@@ -259,7 +273,7 @@ def csd_msc_kmajor(Xk: torch.Tensor, Yk: torch.Tensor, L: int, want_sxy: bool = 
                                 syy.data_ptr(), _lib.ptr(sxy), ws.data_ptr(), ws_bytes, int(keep_operands),
                                 _lib.current_stream())
     _lib.check(rc, "cmc_csd_msc_kmajor")
-    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm), kmajor=None if keep_operands else (Xk, Yk))
+    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm), pending=None if keep_operands else ("kmajor", Xk, Yk))
 
 
 def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: torch.Tensor | None = None,

@@ -669,11 +669,16 @@ def pooled_coherence(eeg_array, emg_array, sampling_freq: float, segment_starts,
     K.check_segments(segment_starts, N, eeg_array.shape[0])
     starts_d = torch.as_tensor(np.asarray(segment_starts, dtype=np.int64)).to(dev)
     wd = torch.from_numpy(windows).to(dev)
-    # K1 writes K-major rows (bin, channel, segment x taper) that the fused K2 kernel contracts as they lie:
-    # no pack pass; the operand planes of the surrogate nulls are built on demand
-    Xk, L = K.fft_segments_kmajor(_to_device_f32(eeg_array), starts_d, wd, detrend, lo, hi)
-    Yk, _ = K.fft_segments_kmajor(_to_device_f32(emg_array), starts_d, wd, detrend, lo, hi)
-    csd = K.csd_msc_kmajor(Xk, Yk, L)
+    # K2 contracts the spectra as K1 writes them (no pack pass); its TMA needs an even channel pitch, so odd
+    # channel counts get one padding column.  The operand planes of the surrogate nulls are built on demand.
+    def spectra(sig):
+        n_ch = sig.shape[1]
+        out = torch.empty((len(segment_starts), n_win, hi - lo + 1, n_ch + (n_ch & 1)), dtype=torch.complex64,
+                          device=dev)
+        K.fft_segments(sig, starts_d, wd, detrend, lo, hi, out=out, ch_offset=0)
+        return out.view(-1, out.shape[2], out.shape[3])[:, :, :n_ch]
+
+    csd = K.csd_msc(spectra(_to_device_f32(eeg_array)), spectra(_to_device_f32(emg_array)))
     return PooledCoherence(csd, freqs[lo:hi + 1], n_win, host)
 
 

@@ -269,3 +269,31 @@ def test_fused_kmajor_path_matches_packed_path_and_oracle(cuda_device, n_epochs,
         e_ref, m_ref = K.surrogate_null(ref, K.SURR_SHIFT, 0, len(shifts), shifts=shifts)
         e_got, m_got = K.surrogate_null(got, K.SURR_SHIFT, 0, len(shifts), shifts=shifts)
         assert np.max(np.abs(m_got.cpu().numpy() - m_ref.cpu().numpy())) < 2e-6
+
+
+@pytest.mark.parametrize("n_epochs,ne,nm,N", [(6, 64, 64, 512), (1, 12, 64, 512), (3, 4, 70, 256), (2, 70, 6, 512),
+                                                (5, 2, 2, 128), (9, 38, 20, 1024), (3, 11, 64, 256)])
+def test_direct_path_matches_packed_path_and_oracle(cuda_device, n_epochs, ne, nm, N):
+    """Direct K2 kernel (spectra staged as MN-major operands, 2 x 2 fold in the epilogue) against the packed-
+    operand path and the fp64 oracle; odd channel pitches (11) take the packed path inside cmc_csd_coherence."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    ep = 4 * N
+    eeg, emg = syn.make_epochs(n_epochs, ep, ne, nm, seed=6)
+    starts = syn.epoch_segment_starts(n_epochs, ep, N, N // 2)
+    lo, hi = 1, min(40, N // 2)
+    X, Y = _welch_spectra(eeg, emg, starts, N, lo, hi)
+    ref = K.csd_msc(X, Y, want_sxy=True, keep_operands=True)
+    got = K.csd_msc(X, Y, want_sxy=True)
+    np.testing.assert_allclose(got.sxx.cpu().numpy(), ref.sxx.cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(got.syy.cpu().numpy(), ref.syy.cpu().numpy(), rtol=2e-6)
+    scale = np.sqrt(ref.sxx.cpu().numpy()[:, :, None] * ref.syy.cpu().numpy()[:, None, :])
+    assert np.max(np.abs(got.sxy.cpu().numpy() - ref.sxy.cpu().numpy()) / scale) < 1e-6
+    assert np.max(np.abs(got.coh.cpu().numpy() - ref.coh.cpu().numpy())) < 2e-6
+    Xo, Yo = _oracle_spectra(eeg, emg, starts, N, lo, hi)
+    assert np.max(np.abs(got.coh.cpu().numpy() - oc.msc_from_spectra(Xo, Yo)[0])) < 2e-5
+    L = len(starts)
+    if L > 2:
+        shifts = torch.arange(1, min(L, 9), dtype=torch.int32).cuda()
+        e_ref, m_ref = K.surrogate_null(ref, K.SURR_SHIFT, 0, len(shifts), shifts=shifts)
+        e_got, m_got = K.surrogate_null(got, K.SURR_SHIFT, 0, len(shifts), shifts=shifts)
+        assert np.max(np.abs(m_got.cpu().numpy() - m_ref.cpu().numpy())) < 2e-6
