@@ -77,16 +77,6 @@ CMC_API int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int64_
                      int bin_lo, int bin_hi,
                      float* spec, int64_t spec_ld, void* stream);
 
-/* Same transform, output as K-major rows: spec_k [F][n_ch][row_pitch] complex64 with the
- * segment index l = seg * n_win + taper contiguous (row_pitch >= n_seg * n_win, even for
- * cmc_csd_msc_kmajor) - the operand order of the pooled contraction, so K2 needs no pack pass.
- * Elements l >= n_seg * n_win of a row are not written. */
-CMC_API int cmc_fft_segments_kmajor(const float* x, int64_t n_samples, int n_ch, int64_t ld,
-                            const int64_t* seg_starts, int n_seg,
-                            const float* windows, int n_win, int N, int detrend,
-                            int bin_lo, int bin_hi,
-                            float* spec_k, int64_t row_pitch, void* stream);
-
 /* Power spectra from segment spectra: out[w][f][c] = base_scale * dbl(f) * mean_k |spec[w][k][f][c]|^2, with
  * dbl(f) = 2 for bins strictly inside (0, N/2) when one_sided != 0 (scipy density convention), optionally
  * followed by log10(|.| + 1e-10).  Replaces signal.periodogram + mean over tapers of multitaper_psd
@@ -161,22 +151,6 @@ CMC_API int cmc_csd_coherence(const float* X, const float* Y, int L, int F, int 
                       void* ws, int64_t ws_bytes, void* stream);
 CMC_API int cmc_csd_operands(const float* X, const float* Y, int L, int F, int Ne, int Nm,
                      int64_t ldx, int64_t ldy, void* ws, int64_t ws_bytes, void* stream);
-
-/* K2 from K-major rows (cmc_fft_segments_kmajor): Xk [F][Ne][pitch_x], Yk [F][Nm][pitch_y]
- * complex64, pitches in complex elements (even, >= L), 16-byte aligned; same outputs and
- * arithmetic as cmc_csd_msc.  The TF32 split, the i*X rows and the auto-spectra are derived in
- * shared memory between the TMA and the MMAs, so the spectra are read once and nothing is packed.
- *   keep_operands != 0: also fill the operand planes of `ws` for cmc_surrogate_null (ws of
- *                       cmc_csd_workspace_bytes()); 0: ws only receives the auto-spectra and may
- *                       be as small as cmc_csd_workspace_bytes_min(F, Ne, Nm).
- * cmc_csd_operands_kmajor fills the planes later (ws must then have the full size and hold the
- * auto-spectra of the cmc_csd_msc_kmajor call). */
-CMC_API int cmc_csd_msc_kmajor(const float* Xk, const float* Yk, int L, int F, int Ne, int Nm,
-                       int64_t pitch_x, int64_t pitch_y,
-                       float* coh, float* sxx, float* syy, float* sxy,
-                       void* ws, int64_t ws_bytes, int keep_operands, void* stream);
-CMC_API int cmc_csd_operands_kmajor(const float* Xk, const float* Yk, int L, int F, int Ne, int Nm,
-                            int64_t pitch_x, int64_t pitch_y, void* ws, int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K3  surrogate null on the cached (whitened) spectra left in `ws` by cmc_csd_msc.

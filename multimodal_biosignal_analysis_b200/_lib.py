@@ -26,15 +26,10 @@ _SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _vp]),
     "cmc_msc_windows_maxemg": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i32, _f32,
                                          _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "cmc_fft_segments_kmajor": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32,
-                                          _vp, _i64, _vp]),
     "cmc_csd_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "cmc_csd_workspace_bytes_min": (_i64, [_i32, _i32, _i32]),
     "cmc_csd_coherence": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cmc_csd_operands": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i64, _vp]),
-    "cmc_csd_msc_kmajor": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
-                                     _i32, _vp]),
-    "cmc_csd_operands_kmajor": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i64, _vp]),
     "cmc_csd_msc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cmc_phase_table": (C.c_int, [_vp]),
     "cmc_surrogate_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i64]),

@@ -14,7 +14,7 @@
 // hi*hi) and accumulate Pxx / Pyy in a fixed order.  HBM traffic = the spectra, once.
 //
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue,
-// warps 8-11 converters.  Stage ring: full (TMA bytes) -> conv (128 converter arrivals) -> MMAs -> empty.
+// warps 8-15 converters.  Stage ring: full (TMA bytes) -> conv (256 converter arrivals) -> MMAs -> empty.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "csd_layout.cuh"
@@ -23,7 +23,8 @@ namespace cmc {
 
 using namespace tc;
 
-constexpr int kMnThreads = 384;
+constexpr int kMnThreads = 512;
+constexpr int kMnConvThreads = 256;                        // warps 8-15
 constexpr int kMnStages = 3;
 constexpr int kMnKBlock = 32;                             // segments per stage
 constexpr int kMnAtomBytes = kMnKBlock * 128;             // 4 KB: 32 k-rows of one 32-float M/N atom
@@ -54,6 +55,21 @@ struct __align__(8) MnBarriers {
     uint32_t pad;
 };
 
+#ifdef CMC_K2_TRACE
+// instrumented build only: globaltimer stamps of CTA 0 (ns), slot = event id
+__device__ unsigned long long g_k2_trace[64];
+__device__ __forceinline__ void k2_stamp(int slot) {
+    if (blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_k2_trace[slot] = t;
+    }
+}
+#define K2_STAMP(slot) k2_stamp(slot)
+#else
+#define K2_STAMP(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ float4 mn_lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -69,23 +85,25 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* sS = base;                                                         // [kMnStages][64 KB]
     float* stage_tile = reinterpret_cast<float*>(sS + kMnStages * kMnStageBytes);     // [64][65] coherence tile
-    float* pw = stage_tile + 64 * kMnPitch;                                            // [2][128]: Pxx rows, Pyy rows
-    MnBarriers* bars = reinterpret_cast<MnBarriers*>(pw + 2 * 128);
+    float* pw = stage_tile + 64 * kMnPitch;            // [2][256]: Pxx, Pyy, 1/sqrt(Pxx), 1/sqrt(Pyy) of the tile's channels
+    float* pw_part = pw + 2 * 256;                     // [128] partial auto-spectra of the second converter warp per atom
+    MnBarriers* bars = reinterpret_cast<MnBarriers*>(pw_part + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) K2_STAMP(0);
     const long long t0 = p.total_tiles * blockIdx.x / gridDim.x;
     const long long t1 = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMnStages; ++s) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->conv[s], 128);
+            mbar_init(&bars->conv[s], kMnConvThreads);
             mbar_init(&bars->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tmem_full[a], 1);
             mbar_init(&bars->tmem_empty[a], 4);
-            mbar_init(&bars->pw_full[a], 128);
+            mbar_init(&bars->pw_full[a], kMnConvThreads);
             mbar_init(&bars->pw_empty[a], 128);
         }
         fence_barrier_init();
@@ -100,28 +118,30 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    if (threadIdx.x == 0) K2_STAMP(1);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (long long t = t0; t < t1; ++t) {
-                const int nt = (int)(t % p.NT);
-                const long long r = t / p.NT;
-                const int mt = (int)(r % p.MT), f = (int)(r / p.MT);
-                for (int kb = 0; kb < p.KB; ++kb) {
-                    unsigned char* st = sS + stage * kMnStageBytes;
+        // ===================== TMA producer: lane 0 owns the barriers, lanes 0-7 each issue one box =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const int a = lane & 3;                      // 32-float atom of the 128-float operand row
+        const bool is_y = (lane & 4) != 0;
+        for (long long t = t0; t < t1; ++t) {
+            const int nt = (int)(t % p.NT);
+            const long long r = t / p.NT;
+            const int mt = (int)(r % p.MT), f = (int)(r / p.MT);
+            for (int kb = 0; kb < p.KB; ++kb) {
+                unsigned char* st = sS + stage * kMnStageBytes;
+                if (lane == 0) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
+                    if (t == t0) K2_STAMP(2 + kb);
                     mbar_arrive_expect_tx(&bars->full[stage], 2 * kMnOpBytes);
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        tma_load_3d(st + a * kMnAtomBytes, &mX, &bars->full[stage], mt * 128 + a * 32, f, kb * kMnKBlock);
-                        tma_load_3d(st + 2 * kMnOpBytes + a * kMnAtomBytes, &mY, &bars->full[stage], nt * 128 + a * 32, f,
-                                    kb * kMnKBlock);
-                    }
-                    if (++stage == kMnStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (lane < 8)
+                    tma_load_3d(st + (is_y ? 2 * kMnOpBytes : 0) + a * kMnAtomBytes, is_y ? &mY : &mX, &bars->full[stage],
+                                (is_y ? nt : mt) * 128 + a * 32, f, kb * kMnKBlock);
+                if (++stage == kMnStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -137,6 +157,7 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
                 const uint32_t d = tmem_base + acc * 128;
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(&bars->conv[stage], phase);
+                    if (t == t0) K2_STAMP(30 + kb);
                     tc_fence_after();
                     const uint32_t ahi = smem_u32(sS + stage * kMnStageBytes), alo = ahi + kMnOpBytes;
                     const uint32_t bhi = ahi + 2 * kMnOpBytes, blo = bhi + kMnOpBytes;
@@ -159,20 +180,21 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
         }
     } else if (warp >= 8) {
         // ===================== converters: TF32 hi/lo split and auto-spectra =====================
-        // thread -> atom a (32 floats = 16 channels), 16-byte chunk cc (2 channels), rows rg, rg + 4, ...
-        const int tc_ = threadIdx.x - 256;           // 0..127
-        const int a = tc_ >> 5, cc = tc_ & 7, rg = (tc_ >> 3) & 3;
+        // thread -> atom a (32 floats = 16 channels), 16-byte chunk cc (2 channels), rows rg, rg + 8, rg + 16, rg + 24
+        const int tc_ = threadIdx.x - 256;           // 0..255
+        const int a = tc_ >> 6, cc = tc_ & 7, rg = (tc_ >> 3) & 7;
         int stage = 0;
         uint32_t phase = 0, it = 0;
         for (long long t = t0; t < t1; ++t) {
             float px0 = 0.f, px1 = 0.f, py0 = 0.f, py1 = 0.f;
             for (int kb = 0; kb < p.KB; ++kb) {
                 mbar_wait(&bars->full[stage], phase);
+                if (t == t0 && tc_ == 0) K2_STAMP(10 + kb);
                 const uint32_t ahi = smem_u32(sS + stage * kMnStageBytes) + a * kMnAtomBytes;
                 const uint32_t alo = ahi + kMnOpBytes, bhi = ahi + 2 * kMnOpBytes, blo = bhi + kMnOpBytes;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = rg + 4 * j;                                      // segment row of the k-block
+                for (int j = 0; j < 4; ++j) {
+                    const int k = rg + 8 * j;                                      // segment row of the k-block
                     // 128-byte swizzle with 32-byte base: 32-byte chunk index XOR (row & 3)
                     const uint32_t off = (uint32_t)(k * 128 + ((((cc >> 1) ^ (k & 3)) << 5) | ((cc & 1) << 4)));
                     const float4 x = mn_lds128(ahi + off);
@@ -192,22 +214,36 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
                 }
                 fence_proxy_async();                 // generic-proxy writes -> visible to the MMA's async-proxy reads
                 mbar_arrive(&bars->conv[stage]);
+                if (t == t0 && tc_ == 0) K2_STAMP(20 + kb);
                 if (++stage == kMnStages) { stage = 0; phase ^= 1; }
             }
-            // fold the four row groups (lanes differing in bits 3 and 4) in a fixed order
+            // fold the eight row groups: four inside the warp (lanes differing in bits 3 and 4), then the two warps
+            // of an atom through shared memory - a fixed order
             px0 += __shfl_xor_sync(0xffffffffu, px0, 8);  px0 += __shfl_xor_sync(0xffffffffu, px0, 16);
             px1 += __shfl_xor_sync(0xffffffffu, px1, 8);  px1 += __shfl_xor_sync(0xffffffffu, px1, 16);
             py0 += __shfl_xor_sync(0xffffffffu, py0, 8);  py0 += __shfl_xor_sync(0xffffffffu, py0, 16);
             py1 += __shfl_xor_sync(0xffffffffu, py1, 8);  py1 += __shfl_xor_sync(0xffffffffu, py1, 16);
             const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
             mbar_wait(&bars->pw_empty[acc], accphase ^ 1);
-            if (rg == 0) {
-                const int ch = a * 16 + cc * 2;
-                pw[acc * 128 + ch] = px0;
-                pw[acc * 128 + ch + 1] = px1;
-                pw[acc * 128 + 64 + ch] = py0;
-                pw[acc * 128 + 64 + ch + 1] = py1;
+            const int ch = a * 16 + cc * 2;
+            const bool upper = (rg & 4) != 0;        // second warp of the atom
+            if ((rg & 3) == 0 && upper) {
+                pw_part[ch] = px0;  pw_part[ch + 1] = px1;
+                pw_part[64 + ch] = py0;  pw_part[64 + ch + 1] = py1;
             }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if ((rg & 3) == 0 && !upper) {
+                float* o = pw + acc * 256;
+                px0 += pw_part[ch];  px1 += pw_part[ch + 1];
+                py0 += pw_part[64 + ch];  py1 += pw_part[64 + ch + 1];
+                o[ch] = px0;  o[ch + 1] = px1;  o[64 + ch] = py0;  o[64 + ch + 1] = py1;
+                // normalisation factors 1 / sqrt(P), 0 for a silent channel
+                o[128 + ch] = px0 > 0.f ? rsqrtf(px0) : 0.f;
+                o[128 + ch + 1] = px1 > 0.f ? rsqrtf(px1) : 0.f;
+                o[192 + ch] = py0 > 0.f ? rsqrtf(py0) : 0.f;
+                o[192 + ch + 1] = py1 > 0.f ? rsqrtf(py1) : 0.f;
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");        // pw_part is free again
             mbar_arrive(&bars->pw_full[acc]);
             ++it;
         }
@@ -216,7 +252,6 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
         const int q = warp - 4;                  // TMEM lane quadrant of this warp
         const int te = threadIdx.x - 128;        // 0..127 = accumulator row (i, ci)
         const int il = te >> 1;                  // EEG channel of this lane pair
-        const bool even = (te & 1) == 0;         // even lane: re parts of X, odd lane: im parts
         uint32_t it = 0;
         for (long long t = t0; t < t1; ++t) {
             const int nt = (int)(t % p.NT);
@@ -225,42 +260,52 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
             const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
             mbar_wait(&bars->pw_full[acc], accphase);
             mbar_wait(&bars->tmem_full[acc], accphase);
+            if (t == t0 && te == 0) K2_STAMP(40);
             tc_fence_after();
-            const float* pwa = pw + acc * 128;
-            const float pxv = pwa[il];
-            const float sx = pxv > 0.f ? rsqrtf(pxv) : 0.f;
+            const float* pwa = pw + acc * 256;
+            const uint32_t sy_addr = smem_u32(pwa + 192);
+            const float sx = pwa[128 + il];
             const int i = mt * 64 + il;
+            const int odd = te & 1;
             const uint32_t taddr = tmem_base + acc * 128 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {     // 32 accumulator columns = 16 EMG channels
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + ch * 32, v);
+                float sy[16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 w = mn_lds128(sy_addr + (uint32_t)(ch * 64 + g * 16));
+                    sy[4 * g] = w.x; sy[4 * g + 1] = w.y; sy[4 * g + 2] = w.z; sy[4 * g + 3] = w.w;
+                }
                 tmem_ld_wait();
+                // Both lanes of a channel pair fetch the partner's row (two independent shuffles per column pair);
+                // the even lane then finishes the even EMG channels, the odd lane the odd ones.
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
-                    const int jl = ch * 16 + jj;
                     const float e = __uint_as_float(v[2 * jj]), o = __uint_as_float(v[2 * jj + 1]);
-                    const float po = __shfl_xor_sync(0xffffffffu, o, 1);
-                    // even lane: Re S = xr yr + xi yi;  odd lane: Im S = xr yi - xi yr
-                    const float val = even ? e + po : po - e;
-                    const float pyv = pwa[64 + jl];
-                    // |S|^2 / (Pxx Pyy) as |S / sqrt(Pxx) / sqrt(Pyy)|^2: no overflow, zero-power channels give 0
-                    const float sc = (pxv > 0.f && pyv > 0.f) ? sx * rsqrtf(pyv) : 0.f;
-                    const float sv = val * sc;
-                    const float sq = sv * sv;
-                    const float other = __shfl_xor_sync(0xffffffffu, sq, 1);
-                    const float pv = __shfl_xor_sync(0xffffffffu, val, 1);
-                    if (even) {
-                        stage_tile[il * kMnPitch + jl] = fminf(sq + other, 1.0f);
-                        const int j = nt * 64 + jl;
-                        if (p.sxy && i < p.Ne && j < p.Nm)
-                            p.sxy[((long long)f * p.Ne + i) * p.Nm + j] = make_float2(val, pv);
+                    const float ep = __shfl_xor_sync(0xffffffffu, e, 1);
+                    const float op = __shfl_xor_sync(0xffffffffu, o, 1);
+                    if ((jj & 1) == odd) {
+                        // rows (i, re) / (i, im): Re S = xr yr + xi yi, Im S = xr yi - xi yr
+                        const float re = odd ? ep + o : e + op;
+                        const float im = odd ? op - e : o - ep;
+                        const int jl = ch * 16 + jj;
+                        // |S|^2 / (Pxx Pyy) as |S / sqrt(Pxx) / sqrt(Pyy)|^2: no overflow, silent channels give 0
+                        const float sc = sx * sy[jj];
+                        const float ar = re * sc, ai = im * sc;
+                        stage_tile[il * kMnPitch + jl] = fminf(ar * ar + ai * ai, 1.0f);
+                        if (p.sxy) {
+                            const int j = nt * 64 + jl;
+                            if (i < p.Ne && j < p.Nm) p.sxy[((long long)f * p.Ne + i) * p.Nm + j] = make_float2(re, im);
+                        }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);   // accumulator may be overwritten
+            if (t == t0 && te == 0) K2_STAMP(41);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             {   // auto-spectra outputs (every pair tile of a row block carries the same values)
                 const bool is_x = te < 64;
@@ -281,13 +326,23 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
             }
             mbar_arrive(&bars->pw_empty[acc]);
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t == t0 && te == 0) K2_STAMP(42);
             ++it;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 256);
+    if (threadIdx.x == 0) K2_STAMP(43);
 }
+
+#ifdef CMC_K2_TRACE
+}  // namespace cmc
+extern "C" CMC_API int cmc_dbg_k2_trace(unsigned long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, cmc::g_k2_trace, sizeof(unsigned long long) * 64);
+}
+namespace cmc {
+#endif
 
 // Spectra [L][F][ld] complex64 as a 3-D fp32 tensor: dim0 = 2 * n_ch floats of one (l, f), dim1 = F, dim2 = L;
 // box = 32 floats x 1 bin x 32 segments.  Out-of-range channels / segments read as zeros.
@@ -332,7 +387,7 @@ int csd_msc_direct(const float* X, const float* Y, int L, int F, int Ne, int Nm,
     p.sxx_out = sxx;
     p.syy_out = syy;
     p.total_tiles = (long long)F * y.MT * y.NT;
-    const size_t smem = 1024 + (size_t)kMnStages * kMnStageBytes + (size_t)64 * kMnPitch * 4 + 2 * 128 * 4 +
+    const size_t smem = 1024 + (size_t)kMnStages * kMnStageBytes + (size_t)64 * kMnPitch * 4 + (2 * 256 + 128) * 4 +
                         sizeof(MnBarriers) + 16;
     rc = ensure_smem_attr(reinterpret_cast<const void*>(csd_mn_kernel), smem);
     if (rc) return rc;

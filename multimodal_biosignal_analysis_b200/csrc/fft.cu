@@ -155,8 +155,7 @@ fft_segments_kernel(const float* __restrict__ x, int64_t n_samples, int n_ch, in
                 float2 X = make_float2(E.x + T.y, E.y - T.x);
                 if (b == 0 || b == M) X.y = 0.f;
                 if (detrend == CMC_DETREND_POST_TAPER && b == 0) X.x = 0.f;
-                if (spec_ld > 0) out[(int64_t)bi * spec_ld + c] = X;
-                else *spec_ptr(spec, spec_ld, n_ch, F, (int64_t)seg * n_win + kw, bi, c0 + c) = X;
+                out[(int64_t)bi * spec_ld + c] = X;
             }
         }
         __syncthreads();
@@ -215,8 +214,7 @@ dft_direct_kernel(const float* __restrict__ x, int n_ch, int64_t ld, const int64
         }
         if (detrend == CMC_DETREND_POST_TAPER && b == 0) re = 0.f;
         if (b == 0 || 2 * b == N) im = 0.f;
-        if (spec_ld > 0) out[(int64_t)bi * spec_ld] = make_float2(re, im);
-        else *spec_ptr(spec, spec_ld, n_ch, F, (int64_t)blockIdx.x, bi, c) = make_float2(re, im);
+        out[(int64_t)bi * spec_ld] = make_float2(re, im);
     }
 }
 
@@ -253,44 +251,14 @@ int fft_segments_tma(const float* x, int64_t n_samples, int n_ch, int64_t ld, co
 
 }  // namespace cmc
 
-namespace cmc {
-int fft_segments_impl(const float* x, int64_t n_samples, int n_ch, int64_t ld, const int64_t* seg_starts, int n_seg,
-                      const float* windows, int n_win, int N, int detrend, int bin_lo, int bin_hi, float* spec,
-                      int64_t spec_ld, void* stream);
-}
-
-extern "C" int cmc_fft_segments_kmajor(const float* x, int64_t n_samples, int n_ch, int64_t ld,
-                                       const int64_t* seg_starts, int n_seg,
-                                       const float* windows, int n_win, int N, int detrend,
-                                       int bin_lo, int bin_hi,
-                                       float* spec_k, int64_t row_pitch, void* stream) {
-    using namespace cmc;
-    CMC_REQUIRE(row_pitch >= (int64_t)n_seg * n_win && row_pitch >= 1,
-                "cmc_fft_segments_kmajor: row_pitch %lld < n_seg * n_win", (long long)row_pitch);
-    // internal convention (fft_common.cuh: spec_ptr): a negative pitch selects the K-major rows
-    return fft_segments_impl(x, n_samples, n_ch, ld, seg_starts, n_seg, windows, n_win, N, detrend, bin_lo, bin_hi, spec_k,
-                             -row_pitch, stream);
-}
-
 extern "C" int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int64_t ld,
                                 const int64_t* seg_starts, int n_seg,
                                 const float* windows, int n_win, int N, int detrend,
                                 int bin_lo, int bin_hi,
                                 float* spec, int64_t spec_ld, void* stream) {
     using namespace cmc;
-    CMC_REQUIRE(spec_ld >= n_ch, "cmc_fft_segments: bad channel pitch");
-    return fft_segments_impl(x, n_samples, n_ch, ld, seg_starts, n_seg, windows, n_win, N, detrend, bin_lo, bin_hi, spec,
-                             spec_ld, stream);
-}
-
-namespace cmc {
-int fft_segments_impl(const float* x, int64_t n_samples, int n_ch, int64_t ld,
-                      const int64_t* seg_starts, int n_seg,
-                      const float* windows, int n_win, int N, int detrend,
-                      int bin_lo, int bin_hi,
-                      float* spec, int64_t spec_ld, void* stream) {
     CMC_REQUIRE(x && seg_starts && windows && spec, "cmc_fft_segments: null pointer");
-    CMC_REQUIRE(n_ch >= 1 && ld >= n_ch, "cmc_fft_segments: bad channel pitch");
+    CMC_REQUIRE(n_ch >= 1 && ld >= n_ch && spec_ld >= n_ch, "cmc_fft_segments: bad channel pitch");
     CMC_REQUIRE(n_seg >= 0 && n_win >= 1, "cmc_fft_segments: bad segment/window count");
     CMC_REQUIRE(detrend >= 0 && detrend <= 2, "cmc_fft_segments: detrend must be 0, 1 or 2");
     CMC_REQUIRE(bin_lo >= 0 && bin_hi >= bin_lo && bin_hi <= N / 2,
@@ -340,4 +308,3 @@ int fft_segments_impl(const float* x, int64_t n_samples, int n_ch, int64_t ld,
 #undef CMC_FFT_CASE
     return CMC_EUNSUPPORTED;
 }
-}  // namespace cmc

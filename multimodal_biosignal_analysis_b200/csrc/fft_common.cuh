@@ -132,13 +132,4 @@ __device__ __forceinline__ void apply_twiddles2(float2 (&v)[R], float2 (&u)[R], 
     }
 }
 
-// Output addressing shared by the K1 kernels.
-//   spec_ld > 0: spectra [segment * n_win + taper][bin][channel], channel pitch spec_ld (complex elements)
-//   spec_ld < 0: K-major rows [bin][channel][segment * n_win + taper], -spec_ld complex elements per row - the
-//                operand order of the pooled-CSD contraction, read by cmc_csd_msc_kmajor without a pack pass
-__device__ __forceinline__ float2* spec_ptr(float2* spec, int64_t spec_ld, int n_ch, int F, int64_t lk, int bi, int c) {
-    return spec_ld > 0 ? spec + (lk * F + bi) * spec_ld + c
-                       : spec + ((int64_t)bi * n_ch + c) * (-spec_ld) + lk;
-}
-
 }  // namespace cmc

@@ -204,19 +204,13 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
             if (b == 0 || b == M) X[h].y = 0.f;
             if (detrend == CMC_DETREND_POST_TAPER && b == 0) X[h].x = 0.f;
         }
+        float2* o = out + (int64_t)bi * spec_ld + 2 * cp;
         const int c = c0 + 2 * cp;
-        if (spec_ld > 0) {
-            float2* o = out + (int64_t)bi * spec_ld + 2 * cp;
-            if (c + 1 < n_ch && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                *reinterpret_cast<float4*>(o) = make_float4(X[0].x, X[0].y, X[1].x, X[1].y);
-            } else {
-                if (c < n_ch) o[0] = X[0];
-                if (c + 1 < n_ch) o[1] = X[1];
-            }
-        } else {                                   // K-major rows: one complex element per (bin, channel) row
-            const int64_t lk = (int64_t)seg * n_win + kw;
-            if (c < n_ch) *spec_ptr(spec, spec_ld, n_ch, F, lk, bi, c) = X[0];
-            if (c + 1 < n_ch) *spec_ptr(spec, spec_ld, n_ch, F, lk, bi, c + 1) = X[1];
+        if (c + 1 < n_ch && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            *reinterpret_cast<float4*>(o) = make_float4(X[0].x, X[0].y, X[1].x, X[1].y);
+        } else {
+            if (c < n_ch) o[0] = X[0];
+            if (c + 1 < n_ch) o[1] = X[1];
         }
     }
     group_sync(bar_id, NT);

@@ -69,35 +69,6 @@ def fft_segments(x: torch.Tensor, seg_starts: torch.Tensor, windows: torch.Tenso
     return out
 
 
-def fft_segments_kmajor(x: torch.Tensor, seg_starts: torch.Tensor, windows: torch.Tensor, detrend: int = 0,
-                        bin_lo: int = 0, bin_hi: int | None = None) -> tuple[torch.Tensor, int]:
-    """Same transform as :func:`fft_segments`, written as K-major rows for :func:`csd_msc_kmajor`:
-    returns (spec_k complex64 (F, n_ch, pitch), L) with L = n_seg * K valid elements per row
-    (l = segment * K + window row); the pitch is L rounded up to an even count, the tail is
-    uninitialised and never read."""
-    _need_cuda(x, "x", torch.float32)
-    _need_cuda(seg_starts, "seg_starts", torch.int64)
-    _need_cuda(windows, "windows", torch.float32)
-    if x.dim() != 2 or x.stride(1) != 1:
-        raise ValueError("x must be (n_samples, n_ch) with contiguous channels")
-    windows = windows.contiguous()
-    seg_starts = seg_starts.contiguous()
-    n_samples, n_ch = x.shape
-    K, N = windows.shape
-    n_seg = seg_starts.numel()
-    if bin_hi is None:
-        bin_hi = N // 2
-    F = bin_hi - bin_lo + 1
-    L = n_seg * K
-    pitch = max(2, (L + 1) // 2 * 2)
-    out = torch.empty((F, n_ch, pitch), dtype=torch.complex64, device=x.device)
-    rc = _lib.load().cmc_fft_segments_kmajor(x.data_ptr(), n_samples, n_ch, x.stride(0), seg_starts.data_ptr(), n_seg,
-                                             windows.data_ptr(), K, N, detrend, bin_lo, bin_hi, out.data_ptr(),
-                                             pitch, _lib.current_stream())
-    _lib.check(rc, "cmc_fft_segments_kmajor")
-    return out, L
-
-
 def psd_from_spectra(spec: torch.Tensor, base_scale: float, one_sided: bool, bin_lo: int, N: int,
                      log_scale: bool) -> torch.Tensor:
     """(W, K, F, C) complex64 spectra -> (W, F, C) float32 power spectra (mean over axis 1)."""
@@ -194,7 +165,7 @@ class PooledCsd:
 
     def __init__(self, coh, sxx, syy, sxy, ws, dims, pending=None):
         self.coh, self.sxx, self.syy, self.sxy, self.ws, self.dims = coh, sxx, syy, sxy, ws, dims
-        # ("std", X, Y, ldx, ldy) or ("kmajor", Xk, Yk) while the operand planes of ws are not filled yet
+        # (X, Y, ldx, ldy) while the operand planes of ws are not filled yet
         self._pending = pending
 
     def ensure_operands(self) -> None:
@@ -205,17 +176,10 @@ class PooledCsd:
         lib = _lib.load()
         ws_bytes = int(lib.cmc_csd_workspace_bytes(L, F, Ne, Nm))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.coh.device)
-        if self._pending[0] == "std":
-            _, X, Y, ldx, ldy = self._pending
-            rc = lib.cmc_csd_operands(X.data_ptr(), Y.data_ptr(), L, F, Ne, Nm, ldx, ldy, ws.data_ptr(), ws_bytes,
-                                      _lib.current_stream())
-            _lib.check(rc, "cmc_csd_operands")
-        else:
-            _, Xk, Yk = self._pending
-            ws[: self.ws.numel()].copy_(self.ws)                  # auto-spectra of the coherence pass
-            rc = lib.cmc_csd_operands_kmajor(Xk.data_ptr(), Yk.data_ptr(), L, F, Ne, Nm, Xk.shape[2], Yk.shape[2],
-                                             ws.data_ptr(), ws_bytes, _lib.current_stream())
-            _lib.check(rc, "cmc_csd_operands_kmajor")
+        X, Y, ldx, ldy = self._pending
+        rc = lib.cmc_csd_operands(X.data_ptr(), Y.data_ptr(), L, F, Ne, Nm, ldx, ldy, ws.data_ptr(), ws_bytes,
+                                  _lib.current_stream())
+        _lib.check(rc, "cmc_csd_operands")
         self.ws, self._pending = ws, None
 
 
@@ -242,38 +206,7 @@ def csd_msc(X: torch.Tensor, Y: torch.Tensor, want_sxy: bool = False, keep_opera
     rc = fn(X.data_ptr(), Y.data_ptr(), L, F, Ne, Nm, ldx, ldy, coh.data_ptr(), sxx.data_ptr(), syy.data_ptr(),
             _lib.ptr(sxy), ws.data_ptr(), ws_bytes, _lib.current_stream())
     _lib.check(rc, "cmc_csd_coherence" if direct else "cmc_csd_msc")
-    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm), pending=("std", X, Y, ldx, ldy) if direct else None)
-
-
-def csd_msc_kmajor(Xk: torch.Tensor, Yk: torch.Tensor, L: int, want_sxy: bool = False,
-                   keep_operands: bool = False) -> PooledCsd:
-    """Pooled coherence from the K-major rows of :func:`fft_segments_kmajor` (F, channels, pitch): the
-    spectra are read once, nothing is packed.  The operand planes for surrogate nulls are built on the
-    first :func:`surrogate_null` call unless ``keep_operands`` asks for them right away."""
-    _need_cuda(Xk, "Xk", torch.complex64)
-    _need_cuda(Yk, "Yk", torch.complex64)
-    if Xk.dim() != 3 or Yk.dim() != 3 or Xk.shape[0] != Yk.shape[0] or not Xk.is_contiguous() or not Yk.is_contiguous():
-        raise ValueError("Xk, Yk must be contiguous (F, channels, pitch) with equal F")
-    F, Ne, px = Xk.shape
-    Nm, py = Yk.shape[1], Yk.shape[2]
-    if not (1 <= L <= min(px, py)):
-        raise ValueError("L outside the row pitch")
-    dev = Xk.device
-    lib = _lib.load()
-    ws_bytes = int(lib.cmc_csd_workspace_bytes(L, F, Ne, Nm) if keep_operands else
-                   lib.cmc_csd_workspace_bytes_min(F, Ne, Nm))
-    if ws_bytes < 0:
-        _lib.check(ws_bytes, "cmc_csd_workspace_bytes")
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    coh = torch.empty((F, Ne, Nm), dtype=torch.float32, device=dev)
-    sxx = torch.empty((F, Ne), dtype=torch.float32, device=dev)
-    syy = torch.empty((F, Nm), dtype=torch.float32, device=dev)
-    sxy = torch.empty((F, Ne, Nm), dtype=torch.complex64, device=dev) if want_sxy else None
-    rc = lib.cmc_csd_msc_kmajor(Xk.data_ptr(), Yk.data_ptr(), L, F, Ne, Nm, px, py, coh.data_ptr(), sxx.data_ptr(),
-                                syy.data_ptr(), _lib.ptr(sxy), ws.data_ptr(), ws_bytes, int(keep_operands),
-                                _lib.current_stream())
-    _lib.check(rc, "cmc_csd_msc_kmajor")
-    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm), pending=None if keep_operands else ("kmajor", Xk, Yk))
+    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm), pending=(X, Y, ldx, ldy) if direct else None)
 
 
 def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: torch.Tensor | None = None,

@@ -234,43 +234,6 @@ def test_phase_surrogates_long_segment_axis_streams_the_panel(cuda_device):
     np.testing.assert_array_equal(torch.cat([m_a, m_b]).cpu().numpy(), max_stat.cpu().numpy())
 
 
-@pytest.mark.parametrize("n_epochs,ne,nm,N", [(6, 64, 64, 512), (1, 11, 64, 512), (3, 3, 70, 256), (2, 70, 5, 512),
-                                                (5, 1, 1, 128), (9, 37, 20, 1024)])
-def test_fused_kmajor_path_matches_packed_path_and_oracle(cuda_device, n_epochs, ne, nm, N):
-    """K1 writing K-major rows + the fused K2 kernel (TF32 split, i*X rows and auto-spectra derived in shared
-    memory) against the packed-operand path (same arithmetic: coherence within 2e-6, identical up to the
-    summation order of the auto-spectra) and against the fp64 oracle (1e-4 gate, 2e-5 observed)."""
-    from multimodal_biosignal_analysis_b200 import kernels as K
-    ep = 4 * N
-    eeg, emg = syn.make_epochs(n_epochs, ep, ne, nm, seed=5)
-    starts = syn.epoch_segment_starts(n_epochs, ep, N, N // 2)
-    lo, hi = 1, min(40, N // 2)
-    win = _dev(signal.get_window("hann", N).astype(np.float32)[None])
-    Xk, L = K.fft_segments_kmajor(_dev(eeg), _dev(starts), win, 1, lo, hi)
-    Yk, L2 = K.fft_segments_kmajor(_dev(emg), _dev(starts), win, 1, lo, hi)
-    assert L == L2 == len(starts)
-    X, Y = _welch_spectra(eeg, emg, starts, N, lo, hi)
-    # K1: the K-major rows hold exactly the spectra of the standard layout
-    np.testing.assert_array_equal(Xk[:, :, :L].permute(2, 0, 1).cpu().numpy(), X.cpu().numpy())
-    np.testing.assert_array_equal(Yk[:, :, :L].permute(2, 0, 1).cpu().numpy(), Y.cpu().numpy())
-    ref = K.csd_msc(X, Y, want_sxy=True)
-    got = K.csd_msc_kmajor(Xk, Yk, L, want_sxy=True)
-    np.testing.assert_allclose(got.sxx.cpu().numpy(), ref.sxx.cpu().numpy(), rtol=2e-6)
-    np.testing.assert_allclose(got.syy.cpu().numpy(), ref.syy.cpu().numpy(), rtol=2e-6)
-    scale = np.sqrt(ref.sxx.cpu().numpy()[:, :, None] * ref.syy.cpu().numpy()[:, None, :])
-    assert np.max(np.abs(got.sxy.cpu().numpy() - ref.sxy.cpu().numpy()) / scale) < 1e-6
-    assert np.max(np.abs(got.coh.cpu().numpy() - ref.coh.cpu().numpy())) < 2e-6
-    Xo, Yo = _oracle_spectra(eeg, emg, starts, N, lo, hi)
-    coh_o = oc.msc_from_spectra(Xo, Yo)[0]
-    assert np.max(np.abs(got.coh.cpu().numpy() - coh_o)) < 2e-5
-    # surrogate nulls work from the lazily built operand planes and agree with the packed path
-    shifts = torch.arange(1, min(L, 9), dtype=torch.int32).cuda()
-    if L > 2:
-        e_ref, m_ref = K.surrogate_null(ref, K.SURR_SHIFT, 0, len(shifts), shifts=shifts)
-        e_got, m_got = K.surrogate_null(got, K.SURR_SHIFT, 0, len(shifts), shifts=shifts)
-        assert np.max(np.abs(m_got.cpu().numpy() - m_ref.cpu().numpy())) < 2e-6
-
-
 @pytest.mark.parametrize("n_epochs,ne,nm,N", [(6, 64, 64, 512), (1, 12, 64, 512), (3, 4, 70, 256), (2, 70, 6, 512),
                                                 (5, 2, 2, 128), (9, 38, 20, 1024), (3, 11, 64, 256)])
 def test_direct_path_matches_packed_path_and_oracle(cuda_device, n_epochs, ne, nm, N):
