@@ -8,7 +8,9 @@ restates the published algorithm of ``mne.stats.permutation_cluster_1samp_test``
 (``mne/stats/cluster_level.py``: ``_find_clusters``, ``_get_components``,
 ``_do_1samp_permutations``, ``_pval_from_histogram``; ``mne/stats/parametric.py``:
 ``ttest_1samp_no_p``) for the options the reference uses: sparse adjacency,
-t_power=1, no TFCE, no step-down, out_type='mask'.
+t_power=1, no TFCE, no step-down, out_type='mask'.  Cross-checked against an
+independent scipy implementation (``scipy.stats.ttest_1samp`` +
+``scipy.ndimage.label``) in ``tests/test_oracle_golden.py``.
 
 Determinism contract shared with the CUDA path:
   * the sign-flip table is HOST-SUPPLIED (int8 in {-1,+1}, one row per

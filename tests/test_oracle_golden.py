@@ -99,3 +99,61 @@ def test_dpss_eigenvalues_known_answer():
     _, eigs = oc.dpss_tapers(4096, 3)
     np.testing.assert_allclose(eigs, [0.99999987, 0.99999075, 0.99971499, 0.99491441, 0.946138],
                                atol=2e-6)
+
+
+def test_cbpa_oracle_against_independent_scipy_implementation():
+    """MNE is not installed here, so the CBPA restatement is cross-checked against a second, independent
+    implementation assembled from scipy: scipy.stats.ttest_1samp for the t-map and scipy.ndimage.label
+    (4-connectivity on a time x channel lattice) for the clusters, with the cluster statistics, the
+    max-statistic null and MNE's p-value rule re-derived here from their definitions."""
+    from scipy import ndimage, sparse, stats
+    from oracle import cbpa as ocb
+    rng = np.random.default_rng(2024)
+    n_subj, n_times, n_ch = 11, 24, 9
+    X = rng.standard_normal((n_subj, n_times, n_ch))
+    X[:, 5:12, 2:6] += 1.1
+    X[:, 15:20, 6:9] -= 1.2
+    chain = sparse.diags([np.ones(n_ch - 1), np.ones(n_ch - 1)], [-1, 1], format="csr")    # channel c ~ c +- 1
+    adj = ocb.combine_adjacency(n_times, chain)
+    thr = stats.t.ppf(0.975, n_subj - 1)
+    signs = np.where(rng.random((40, n_subj)) < 0.5, -1, 1).astype(np.int8)
+    cross = ndimage.generate_binary_structure(2, 1)
+
+    def independent(Xs, tail):
+        t = stats.ttest_1samp(Xs, 0.0, axis=0).statistic
+        tf = np.rint(np.clip(t, -ocb.T_CLAMP, ocb.T_CLAMP) * ocb.FIX_SCALE).astype(np.int64)
+        masks = [t > thr, t < -thr] if tail == 0 else ([t > thr] if tail == 1 else [t < -thr])
+        label_map = np.zeros(t.shape, dtype=np.int32)
+        fixed, flt = [], []
+        for m in masks:
+            lab, n = ndimage.label(m, structure=cross)       # numbered in raster order of the first element
+            for k in range(1, n + 1):
+                sel = lab == k
+                fixed.append(int(tf[sel].sum()))
+                flt.append(float(t[sel].sum()))
+                label_map[sel] = len(fixed)
+        return t, label_map, np.array(fixed, dtype=np.int64), np.array(flt)
+
+    for tail in (0, 1, -1):
+        thr_call = -thr if tail == -1 else thr
+        ref = ocb.permutation_cluster_1samp_test(X, signs, thr_call, tail, adj)
+        t, label_map, fixed, flt = independent(X, tail)
+        np.testing.assert_allclose(ref["t_obs"], t, rtol=1e-12)
+        assert len(ref["clusters"]) == len(fixed) >= 1
+        np.testing.assert_array_equal(ref["labels"].reshape(n_times, n_ch), label_map)     # same clusters, same order
+        np.testing.assert_array_equal(ref["mass_fixed"], fixed)
+        np.testing.assert_allclose(ref["mass_float"], flt, rtol=1e-12)
+        h0 = np.zeros(1 + len(signs), dtype=np.int64)
+        pick = {0: lambda v: v[np.argmax(np.abs(v))], 1: lambda v: v.max(), -1: lambda v: v.min()}[tail]
+        h0[0] = abs(pick(fixed)) if tail == 0 else pick(fixed)
+        for p, s in enumerate(signs):
+            _, _, fx, _ = independent(X * s[:, None, None], tail)
+            h0[1 + p] = 0 if len(fx) == 0 else fx[np.argmax(np.abs(fx))]
+        np.testing.assert_array_equal(ref["H0_fixed"], h0)
+        if tail == 0:
+            pv = [(np.abs(h0) >= abs(v)).mean() for v in fixed]
+        elif tail == 1:
+            pv = [(h0 >= v).mean() for v in fixed]
+        else:
+            pv = [(h0 <= v).mean() for v in fixed]
+        np.testing.assert_array_equal(ref["cluster_pv"], np.array(pv))
