@@ -341,11 +341,13 @@ def main_gpu(args):
 
     # ---- stage: phase-randomised surrogates (config 3 count per rank-shard of config 5's 10,000) ----
     n_phase = 10000
-    sb, se = cdist.shard_range(n_phase, rank, world)
+    # one null shared by the ranks: every rank runs all surrogates on its slice of the frequency axis, so
+    # operand generation, phases and contraction all shrink with the rank count (data_surrogation._plan)
+    fb, fe = cdist.shard_range(F, rank, world)
     def phase_null():
-        ex_p, ms_p = K.surrogate_null(res, K.SURR_PHASE, sb, se, seed=7)
-        cdist.all_reduce_sum_(ex_p)                                # exceedance histogram
-        return ex_p, cdist.all_gather_ranges(ms_p, n_phase)        # per-surrogate max statistic
+        ex_p, ms_p = K.surrogate_null(res, K.SURR_PHASE, 0, n_phase, seed=7, f_range=(fb, fe))
+        cdist.all_reduce_sum_(ex_p)                                # exceedance histogram (disjoint bins)
+        return ex_p, cdist.all_reduce_max_(ms_p)                   # per-surrogate max statistic
 
     for _ in range(2):                                             # warm-up includes the collectives
         phase_null()
@@ -357,13 +359,14 @@ def main_gpu(args):
     barrier()
     ph_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
     kpb = ((2 * L + 63) // 64) * 64
-    ph_flop = 2.0 * (se - sb) * (2 * NE * NM) * kpb * F                    # executed bf16 flop on this rank
+    ph_flop = 2.0 * n_phase * (2 * NE * NM) * kpb * (fe - fb)              # executed bf16 flop on this rank
     stages["surrogate_null_phase"] = {
         "metric": "surrogates_per_s", "value": n_phase / (ph_ms / 1e3), "unit": "surrogates/s", "ms": ph_ms,
         "scaling": "strong",
         "config": f"config 5 count: {n_phase} phase-randomised surrogates of one 64x64xF=100 subject-condition "
-                  f"sharded over {world} rank(s) (Philox phases + bf16 Z operands generated in the timed region; "
-                  f"counts all-reduced, max-stat all-gathered)",
+                  f"with the frequency axis sharded over {world} rank(s) (Philox phases + bf16 Z operands generated in "
+                  f"the timed region; "
+                  f"counts summed, max-stat max-reduced over ranks)",
         "roofline": {"bound": "tensor", "achieved": ph_flop / (ph_ms * 1e-3) / 1e12, "peak": bf16,
                      "unit": "TFLOP/s", "frac": ph_flop / (ph_ms * 1e-3) / 1e12 / bf16,
                      "note": "executed bf16 flop (K padded to 64) vs measured dense bf16 peak"},

@@ -177,6 +177,16 @@ CMC_API int cmc_surrogate_null(void* ws, int L, int F, int Ne, int Nm, int mode,
                        const int32_t* shifts, uint64_t seed, int64_t s_begin, int64_t s_end,
                        const float* coh_obs, uint32_t* exceed, float* max_stat,
                        void* ws2, int64_t ws2_bytes, void* stream);
+/* Same, restricted to the frequency bins [f_begin, f_end) of the F-bin problem (all pointers still
+ * address the full arrays): exceed is only touched inside the range and max_stat is the maximum over
+ * the range, so ranks that split the FREQUENCY axis combine with a sum and a max.  Every kernel of the
+ * null (operand generation included) then shrinks with the range, which is what scales a single null
+ * over GPUs; phases are indexed by the global bin, so the result does not depend on the split. */
+CMC_API int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, int mode, int group,
+                             const int32_t* shifts, uint64_t seed, int64_t s_begin, int64_t s_end,
+                             int f_begin, int f_end,
+                             const float* coh_obs, uint32_t* exceed, float* max_stat,
+                             void* ws2, int64_t ws2_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K4  cluster-based permutation test: sign-flip t-map -> threshold -> connected-component

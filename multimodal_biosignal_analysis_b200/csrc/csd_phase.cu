@@ -86,10 +86,12 @@ static int get_phase_table(const uint32_t** table) {
 // A operand: Phi[f][s_local][k] (bf16, K-major, row length KPb); one thread = (s, l, group of 4 frequencies)
 __global__ void __launch_bounds__(256)
 phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_begin, int n_local, int S_pad, int L,
-                 int F, int fg0, int KPb, __nv_bfloat16* __restrict__ A) {
+                 int F, int f_lo, int KPb, __nv_bfloat16* __restrict__ A) {
+    // frequencies [f_lo, f_lo + F) of the GLOBAL axis land in rows [0, F) of A; f_lo need not be a multiple of 4
     const int lp = blockIdx.x * blockDim.x + threadIdx.x;      // complex column index, covers [0, KPb / 2)
     const int s = blockIdx.y;                                   // local surrogate row, covers [0, S_pad)
-    const int fg = blockIdx.z;                                  // frequency group of 4
+    const int fg0 = f_lo >> 2;
+    const int fg = blockIdx.z;                                  // frequency group of 4, relative to fg0
     if (lp >= KPb / 2) return;
     uint32_t vals[4] = {0u, 0u, 0u, 0u};
     if (s < n_local && lp < L) {
@@ -104,8 +106,8 @@ phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_be
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int f = fg * 4 + q;
-        if (f < F)
+        const int f = (fg0 + fg) * 4 + q - f_lo;                // row of A
+        if (f >= 0 && f < F)
             reinterpret_cast<uint32_t*>(A)[(((int64_t)f * S_pad + s) * KPb) / 2 + lp] = vals[q];
     }
 }
@@ -370,8 +372,8 @@ int64_t phase_workspace_bytes(int L, int F, int Ne, int Nm, int64_t n_surr) {
 }
 
 int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
-                         const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2, int64_t ws2_bytes,
-                         cudaStream_t st) {
+                         int f_begin, int f_end, const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2,
+                         int64_t ws2_bytes, cudaStream_t st) {
     const int64_t n = s_end - s_begin;
     CMC_REQUIRE(n < (1ll << 31) - 256, "cmc_surrogate_null: too many surrogates in one call");
     const CsdLayout cy = csd_layout(L, F, Ne, Nm);
@@ -402,15 +404,15 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    for (int f0 = 0; f0 < F; f0 += y.f_chunk) {
-        const int fc = F - f0 < y.f_chunk ? F - f0 : y.f_chunk;
+    for (int f0 = f_begin; f0 < f_end; f0 += y.f_chunk) {
+        const int fc = f_end - f0 < y.f_chunk ? f_end - f0 : y.f_chunk;
         if (y.n_pairs_pad != y.n_pairs) {
             rc = check_cuda(cudaMemsetAsync(Z, 0, (size_t)fc * y.R_pad * y.KPb * 2, st), "memset(Z)");
             if (rc) return rc;
         }
-        // Philox counters use GLOBAL frequency groups: shift the group index by f0 / 4
-        phase_gen_kernel<<<dim3((y.KPb / 2 + 255) / 256, y.S_pad, (fc + 3) / 4), 256, 0, st>>>(
-            table, seed, s_begin, (int)n, y.S_pad, L, fc, f0 / 4, y.KPb, A);
+        // Philox counters use GLOBAL frequency groups of 4; a chunk may start inside a group
+        phase_gen_kernel<<<dim3((y.KPb / 2 + 255) / 256, y.S_pad, ((f0 + fc - 1) >> 2) - (f0 >> 2) + 1), 256, 0, st>>>(
+            table, seed, s_begin, (int)n, y.S_pad, L, fc, f0, y.KPb, A);
         CMC_CHECK_LAUNCH("phase_gen_kernel");
         z_gen_kernel<<<dim3(fc, Ne), 256, (size_t)y.KPb * 4, st>>>(
             reinterpret_cast<const float*>(w + cy.off_ahi) + (int64_t)f0 * cy.MT * kTileM * cy.KP,

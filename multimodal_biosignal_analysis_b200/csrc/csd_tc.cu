@@ -39,6 +39,7 @@ constexpr int kGemmThreads = 256;
 
 struct CsdParams {
     int F, MT, NT, Ne, Nm, KB, nterms, n_shift;
+    int f0;                       // first frequency of the processed range (tiles cover [f0, f0 + F))
     const int32_t* shift_off;     // [n_shift] K offset (floats) into the doubled B rows, or null
     const uint32_t* shift_mult;   // [n_shift] surrogates that use this shift (0 = skip), or null
     float* coh;                   // EPI 0 out [F][Ne][Nm]
@@ -61,7 +62,7 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const CsdParams& p
     c.nt = (int)(r % p.NT);
     r /= p.NT;
     c.mt = (int)(r % p.MT);
-    c.f = (int)(r / p.MT);
+    c.f = p.f0 + (int)(r / p.MT);
     return c;
 }
 
@@ -452,8 +453,8 @@ static int launch_pack(const float* X, const float* Y, int L, int F, int Ne, int
 
 int64_t phase_workspace_bytes(int L, int F, int Ne, int Nm, int64_t n_surr);
 int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
-                         const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2, int64_t ws2_bytes,
-                         cudaStream_t st);
+                         int f_begin, int f_end, const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2,
+                         int64_t ws2_bytes, cudaStream_t st);
 
 }  // namespace cmc
 
@@ -541,14 +542,28 @@ extern "C" int cmc_surrogate_null(void* ws, int L, int F, int Ne, int Nm, int mo
                                   const int32_t* shifts, uint64_t seed, int64_t s_begin, int64_t s_end,
                                   const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2,
                                   int64_t ws2_bytes, void* stream) {
+    return cmc_surrogate_null_range(ws, L, F, Ne, Nm, mode, group, shifts, seed, s_begin, s_end, 0, F, coh_obs, exceed,
+                                    max_stat, ws2, ws2_bytes, stream);
+}
+
+extern "C" int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, int mode, int group,
+                                        const int32_t* shifts, uint64_t seed, int64_t s_begin, int64_t s_end,
+                                        int f_begin, int f_end, const float* coh_obs, uint32_t* exceed,
+                                        float* max_stat, void* ws2, int64_t ws2_bytes, void* stream) {
     using namespace cmc;
     CMC_REQUIRE(ws && coh_obs && exceed && max_stat && ws2, "cmc_surrogate_null: null pointer");
     CMC_REQUIRE(s_end >= s_begin, "cmc_surrogate_null: bad surrogate range");
+    CMC_REQUIRE(0 <= f_begin && f_begin <= f_end && f_end <= F, "cmc_surrogate_null: bad frequency range [%d, %d)",
+                f_begin, f_end);
     const int64_t n = s_end - s_begin;
     if (n == 0) return CMC_OK;
+    if (f_begin == f_end) {                      // nothing to compare against: every max statistic is 0
+        return check_cuda(cudaMemsetAsync(max_stat, 0, (size_t)n * 4, static_cast<cudaStream_t>(stream)),
+                          "memset(max_stat)");
+    }
     if (mode == CMC_SURR_PHASE)
-        return phase_surrogate_null(ws, L, F, Ne, Nm, seed, s_begin, s_end, coh_obs, exceed, max_stat, ws2, ws2_bytes,
-                                    static_cast<cudaStream_t>(stream));
+        return phase_surrogate_null(ws, L, F, Ne, Nm, seed, s_begin, s_end, f_begin, f_end, coh_obs, exceed, max_stat,
+                                    ws2, ws2_bytes, static_cast<cudaStream_t>(stream));
     CMC_REQUIRE(mode == CMC_SURR_SHIFT, "cmc_surrogate_null: unknown mode %d", mode);
     CMC_REQUIRE(shifts, "cmc_surrogate_null: shift mode needs a shift table");
     CMC_REQUIRE(group >= 1 && L % group == 0, "cmc_surrogate_null: group must divide L");
@@ -574,11 +589,12 @@ extern "C" int cmc_surrogate_null(void* ws, int L, int F, int Ne, int Nm, int mo
         reinterpret_cast<float*>(w + y.off_bodd));
     CMC_CHECK_LAUNCH("shift_operand_kernel");
     CsdParams p{};
-    p.F = F; p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock; p.nterms = 1; p.n_shift = n_pos;
+    p.F = f_end - f_begin; p.f0 = f_begin;
+    p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock; p.nterms = 1; p.n_shift = n_pos;
     p.shift_off = off; p.shift_mult = mult; p.coh_obs = coh_obs; p.exceed = exceed; p.max_u = max_u;
     p.pxx = reinterpret_cast<const float*>(w + y.off_pxx);
     p.pyy = reinterpret_cast<const float*>(w + y.off_pyy);
-    p.total_tiles = (long long)F * y.MT * y.NT * n_pos;
+    p.total_tiles = (long long)(f_end - f_begin) * y.MT * y.NT * n_pos;
     rc = launch_gemm<1>(y, w, p, st);
     if (rc) return rc;
     shift_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shifts, n, n_pos, max_u, max_stat);

@@ -89,9 +89,31 @@ def add_noise_to_channels(input_array: np.ndarray, noise_db: float, channels: li
 
 
 # ----------------------------------------------------------------------------- surrogate null (new)
-def _finish(pooled, exceed_d: torch.Tensor, max_local: torch.Tensor, n_surrogates: int, alpha: float):
-    cdist.all_reduce_sum_(exceed_d)
-    max_stat = cdist.all_gather_ranges(max_local, n_surrogates)
+def _plan(n_surrogates: int, n_freqs: int, shard: str):
+    """Work split of one null over the ranks: ``(s_begin, s_end, f_range, by_frequency)``.
+
+    "frequency" (default when every rank can get a bin): each rank runs ALL surrogates on its own slice of the
+    frequency axis, so operand generation, phases and contraction all shrink with the rank count (a shift null
+    costs at most n_positions - 1 passes however the surrogates are split, so only this split scales it);
+    "surrogate": each rank runs a slice of the surrogate index on all bins.  Indices are global either way, the
+    null does not depend on the split."""
+    rank, world = cdist.world()
+    if shard not in ("auto", "frequency", "surrogate"):
+        raise ValueError("shard must be 'auto', 'frequency' or 'surrogate'")
+    by_freq = world > 1 and (shard == "frequency" or (shard == "auto" and n_freqs >= world))
+    if by_freq:
+        return 0, n_surrogates, cdist.shard_range(n_freqs, rank, world), True
+    begin, end = cdist.shard_range(n_surrogates, rank, world)
+    return begin, end, None, False
+
+
+def _finish(pooled, exceed_d: torch.Tensor, max_local: torch.Tensor, n_surrogates: int, alpha: float,
+            by_frequency: bool = False):
+    cdist.all_reduce_sum_(exceed_d)                              # disjoint bins (or disjoint surrogates): a sum
+    if by_frequency:
+        max_stat = cdist.all_reduce_max_(max_local)              # every rank holds all surrogates of its bins
+    else:
+        max_stat = cdist.all_gather_ranges(max_local, n_surrogates)
     exceed = exceed_d.cpu().numpy().astype(np.int64)
     ms = max_stat.cpu().numpy()
     return {
@@ -106,7 +128,8 @@ def _finish(pooled, exceed_d: torch.Tensor, max_local: torch.Tensor, n_surrogate
 
 
 def circular_shift_surrogate_null(pooled, n_surrogates: int = 1000, seed: int | None = 0,
-                                  shifts: np.ndarray | None = None, alpha: float = 0.05) -> dict:
+                                  shifts: np.ndarray | None = None, alpha: float = 0.05,
+                                  shard: str = "auto") -> dict:
     """Circular time-shift surrogates: surrogate s rotates the EMG segment (window) index by
     ``shifts[s]`` in [1, n_positions - 1] (whole windows for multitaper pooling, tapers stay
     aligned).  ``shifts`` is a host-supplied int32 table; by default it is drawn from
@@ -122,18 +145,20 @@ def circular_shift_surrogate_null(pooled, n_surrogates: int = 1000, seed: int | 
     shifts = np.ascontiguousarray(shifts, dtype=np.int32)
     if shifts.shape != (n_surrogates,):
         raise ValueError("one shift per surrogate")
-    begin, end = cdist.shard_range(n_surrogates)
+    begin, end, f_range, by_freq = _plan(n_surrogates, csd.dims[1], shard)
     dev = csd.coh.device
     exceed, max_local = K.surrogate_null(csd, K.SURR_SHIFT, begin, end,
-                                         shifts=torch.from_numpy(shifts[begin:end]).to(dev), group=pooled.group)
-    return _finish(pooled, exceed, max_local, n_surrogates, alpha)
+                                         shifts=torch.from_numpy(shifts[begin:end]).to(dev), group=pooled.group,
+                                         f_range=f_range)
+    return _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq)
 
 
-def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int = 0, alpha: float = 0.05) -> dict:
+def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int = 0, alpha: float = 0.05,
+                                    shard: str = "auto") -> dict:
     """Phase-randomised surrogates: every EMG spectrum is rotated by one random phase per
     (surrogate, segment, frequency), shared by all EMG channels; phases come from
     Philox4x32-10(seed; s, l, f) so any sharding of the surrogate index gives the same null."""
     csd = pooled.device_result
-    begin, end = cdist.shard_range(n_surrogates)
-    exceed, max_local = K.surrogate_null(csd, K.SURR_PHASE, begin, end, seed=seed)
-    return _finish(pooled, exceed, max_local, n_surrogates, alpha)
+    begin, end, f_range, by_freq = _plan(n_surrogates, csd.dims[1], shard)
+    exceed, max_local = K.surrogate_null(csd, K.SURR_PHASE, begin, end, seed=seed, f_range=f_range)
+    return _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq)

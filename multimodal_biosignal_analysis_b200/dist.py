@@ -51,3 +51,10 @@ def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+def all_reduce_max_(t: torch.Tensor) -> torch.Tensor:
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t

@@ -210,9 +210,11 @@ def csd_msc(X: torch.Tensor, Y: torch.Tensor, want_sxy: bool = False, keep_opera
 
 
 def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: torch.Tensor | None = None,
-                   group: int = 1, seed: int = 0, exceed: torch.Tensor | None = None):
+                   group: int = 1, seed: int = 0, exceed: torch.Tensor | None = None,
+                   f_range: tuple[int, int] | None = None):
     """Surrogates [s_begin, s_end) against csd.coh: returns (exceed uint32 (F,Ne,Nm) accumulated,
-    max_stat float32 (s_end - s_begin,))."""
+    max_stat float32 (s_end - s_begin,)).  ``f_range = (f_begin, f_end)`` restricts the null to those
+    frequency bins: exceed is only updated there and max_stat is the maximum over the range."""
     L, F, Ne, Nm = csd.dims
     dev = csd.coh.device
     n = s_end - s_begin
@@ -229,10 +231,11 @@ def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: 
     if ws2_bytes < 0:
         _lib.check(ws2_bytes, "cmc_surrogate_workspace_bytes")
     ws2 = torch.empty(max(ws2_bytes, 16), dtype=torch.uint8, device=dev)
-    rc = lib.cmc_surrogate_null(csd.ws.data_ptr(), L, F, Ne, Nm, mode, group, _lib.ptr(shifts), seed, s_begin,
-                                s_end, csd.coh.data_ptr(), exceed.data_ptr(), max_stat.data_ptr(),
-                                ws2.data_ptr(), ws2_bytes, _lib.current_stream())
-    _lib.check(rc, "cmc_surrogate_null")
+    f_begin, f_end = (0, F) if f_range is None else (int(f_range[0]), int(f_range[1]))
+    rc = lib.cmc_surrogate_null_range(csd.ws.data_ptr(), L, F, Ne, Nm, mode, group, _lib.ptr(shifts), seed, s_begin,
+                                      s_end, f_begin, f_end, csd.coh.data_ptr(), exceed.data_ptr(),
+                                      max_stat.data_ptr(), ws2.data_ptr(), ws2_bytes, _lib.current_stream())
+    _lib.check(rc, "cmc_surrogate_null_range")
     return exceed, max_stat
 
 

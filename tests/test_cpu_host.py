@@ -98,7 +98,14 @@ def _gloo_worker(rank, world, port, q):
     full = cd.all_gather_ranges(local, n)
     cnt = torch.full((4,), rank + 1, dtype=torch.int32)
     cd.all_reduce_sum_(cnt)
-    q.put((rank, full.tolist(), cnt.tolist()))
+    # frequency-sharded null: every rank holds all surrogates of its own bins -> max over ranks, sum of counts
+    from multimodal_biosignal_analysis_b200 import data_surrogation as ds
+    s0, s1, f_range, by_freq = ds._plan(7, 5, "auto")
+    mx = torch.tensor([0.1 * (rank + 1), 0.5 - 0.1 * rank], dtype=torch.float32)
+    cd.all_reduce_max_(mx)
+    s0b, s1b, f_range_b, by_freq_b = ds._plan(7, 1, "auto")          # fewer bins than ranks: split the surrogates
+    q.put((rank, full.tolist(), cnt.tolist(), (s0, s1, f_range, by_freq), [round(float(v), 6) for v in mx],
+           (s0b, s1b, f_range_b, by_freq_b)))
     dist.destroy_process_group()
 
 
@@ -114,9 +121,12 @@ def test_two_rank_sharding_over_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, full, cnt in out:
+    for rank, full, cnt, plan, mx, plan_b in out:
         assert full == [10 * i for i in range(11)]
         assert cnt == [3, 3, 3, 3]
+        assert plan == (0, 7, (0, 3) if rank == 0 else (3, 5), True)
+        assert mx == [0.2, 0.5]
+        assert plan_b == ((0, 4, None, False) if rank == 0 else (4, 7, None, False))
 
 
 def test_file_naming_and_spectrogram_roundtrip(tmp_path):

@@ -260,3 +260,27 @@ def test_direct_path_matches_packed_path_and_oracle(cuda_device, n_epochs, ne, n
         e_ref, m_ref = K.surrogate_null(ref, K.SURR_SHIFT, 0, len(shifts), shifts=shifts)
         e_got, m_got = K.surrogate_null(got, K.SURR_SHIFT, 0, len(shifts), shifts=shifts)
         assert np.max(np.abs(m_got.cpu().numpy() - m_ref.cpu().numpy())) < 2e-6
+
+
+@pytest.mark.parametrize("mode", ["phase", "shift"])
+def test_surrogate_null_frequency_ranges_reproduce_the_full_null(cuda_device, mode):
+    """Splitting the FREQUENCY axis (how ranks share one null) gives the same counts as the unsplit call and
+    the per-surrogate max statistic is the max over the pieces - for ranges that do not align with the
+    groups of four bins one Philox call covers."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    N, hop, ep, n_epochs, ne, nm, n_surr = 256, 128, 1024, 4, 6, 9, 96
+    eeg, emg = syn.make_epochs(n_epochs, ep, ne, nm, seed=41)
+    starts = syn.epoch_segment_starts(n_epochs, ep, N, hop)
+    X, Y = _welch_spectra(eeg, emg, starts, N, 2, 24)            # F = 23 bins
+    res = K.csd_msc(X, Y)
+    F = res.coh.shape[0]
+    kw = dict(seed=5) if mode == "phase" else dict(
+        shifts=torch.as_tensor(np.random.default_rng(1).integers(1, len(starts), n_surr).astype(np.int32)).cuda())
+    m = K.SURR_PHASE if mode == "phase" else K.SURR_SHIFT
+    full_e, full_m = K.surrogate_null(res, m, 0, n_surr, **kw)
+    exceed, pieces = None, []
+    for f0, f1 in ((0, 5), (5, 6), (6, 6), (6, 17), (17, F)):
+        exceed, mx = K.surrogate_null(res, m, 0, n_surr, exceed=exceed, f_range=(f0, f1), **kw)
+        pieces.append(mx)
+    np.testing.assert_array_equal(exceed.cpu().numpy(), full_e.cpu().numpy())
+    np.testing.assert_array_equal(torch.stack(pieces).max(dim=0).values.cpu().numpy(), full_m.cpu().numpy())
