@@ -487,10 +487,10 @@ extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, doubl
     const double* XT = nullptr;
     rc = cbpa_tile(X, n_subj, n_tests, ws, ws_bytes, st, &XT, "cmc_cbpa_observed");
     if (rc) return rc;
-    long long* mass_root = reinterpret_cast<long long*>(ws);
-    int32_t* root = reinterpret_cast<int32_t*>(mass_root + n_tests);
+    long long* mass_root = reinterpret_cast<long long*>(ws);                    // 8-byte items first
+    long long* h0_tmp = mass_root + n_tests;
+    int32_t* root = reinterpret_cast<int32_t*>(h0_tmp + 1);
     int32_t* rank = root + n_tests;
-    long long* h0_tmp = reinterpret_cast<long long*>(rank + n_tests + (n_tests & 1));
     const size_t smem = cbpa_smem_bytes(n_subj, n_tests, 0);
     rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true, 0>), smem);
     if (rc) return rc;

@@ -129,3 +129,32 @@ def test_cbpa_max_map_size_supra_list_overflow_and_compact_paths(cuda_device):
         np.testing.assert_array_equal(labels, ref["labels"])
         np.testing.assert_array_equal(mass, ref["mass_fixed"])
         np.testing.assert_array_equal(h0, ref["H0_fixed"][1:])
+
+
+@pytest.mark.parametrize("n_subj,n_times,n_ch", [(2, 10, 7), (3, 9, 5), (32, 12, 6), (35, 11, 9), (21, 33, 1)])
+def test_cbpa_subject_counts_and_ragged_maps(cuda_device, n_subj, n_times, n_ch):
+    """Smallest, template-boundary (32) and generic (> 32) subject counts, maps whose size is not a multiple of
+    the 32-test tile of the re-laid data, exact zeros / constant columns (t = NaN) and huge / tiny magnitudes that
+    leave the fast constant-division band: everything bit-identical to the oracle."""
+    rng = np.random.default_rng(100 + n_subj)
+    pos = syn.sensor_positions(64)[:max(n_ch, 3)]
+    sp = ocb.delaunay_adjacency(pos)[:n_ch][:, :n_ch] if n_ch >= 3 else None
+    if sp is None:
+        from scipy import sparse
+        sp = sparse.csr_matrix((n_ch, n_ch))
+    adj = ocb.combine_adjacency(n_times, sp)
+    X = rng.standard_normal((n_subj, n_times, n_ch)) + 0.6
+    X[:, 0, 0] = 0.0                    # all-zero column: t = 0/0
+    X[:, 1, 0] = 3.25                   # constant column: zero variance
+    X[:, 2, 0] *= 1e200                 # outside the fast-division exponent band
+    X[:, 3, 0] *= 1e-200
+    signs = syn.make_sign_table(24, n_subj, seed=n_subj)
+    thr = t_dist.ppf(0.975, n_subj - 1)
+    with np.errstate(all="ignore"):
+        ref = ocb.permutation_cluster_1samp_test(X, signs, thr, 0, adj)
+    t_obs, labels, mass, n, h0 = _run(X, signs, thr, 0, adj)
+    np.testing.assert_array_equal(t_obs, ref["t_obs"].reshape(-1))       # NaNs compare equal position-wise
+    assert n == len(ref["clusters"])
+    np.testing.assert_array_equal(labels, ref["labels"])
+    np.testing.assert_array_equal(mass, ref["mass_fixed"])
+    np.testing.assert_array_equal(h0, ref["H0_fixed"][1:])

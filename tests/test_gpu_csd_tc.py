@@ -284,3 +284,27 @@ def test_surrogate_null_frequency_ranges_reproduce_the_full_null(cuda_device, mo
         pieces.append(mx)
     np.testing.assert_array_equal(exceed.cpu().numpy(), full_e.cpu().numpy())
     np.testing.assert_array_equal(torch.stack(pieces).max(dim=0).values.cpu().numpy(), full_m.cpu().numpy())
+
+
+@pytest.mark.parametrize("ne,nm,N", [(64, 64, 1024), (70, 40, 2048), (8, 8, 4096)])
+def test_direct_path_many_tiles_per_cta(cuda_device, ne, nm, N):
+    """Full-band spectra: 513 - 2049 bins x channel tiles = several tiles per persistent CTA, which exercises the
+    accumulator double buffering and the barrier phase wrap-around of the direct kernel."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    ep = 4 * N
+    eeg, emg = syn.make_epochs(3, ep, ne, nm, seed=8)
+    starts = syn.epoch_segment_starts(3, ep, N, N // 2)
+    X, Y = _welch_spectra(eeg, emg, starts, N, 0, N // 2)
+    ref = K.csd_msc(X, Y, want_sxy=True, keep_operands=True)
+    got = K.csd_msc(X, Y, want_sxy=True)
+    assert got.coh.shape[0] * ((ne + 63) // 64) * ((nm + 63) // 64) > 2 * 148
+    np.testing.assert_allclose(got.sxx.cpu().numpy(), ref.sxx.cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(got.syy.cpu().numpy(), ref.syy.cpu().numpy(), rtol=2e-6)
+    scale = np.sqrt(ref.sxx.cpu().numpy()[:, :, None] * ref.syy.cpu().numpy()[:, None, :]) + 1e-30
+    assert np.max(np.abs(got.sxy.cpu().numpy() - ref.sxy.cpu().numpy()) / scale) < 1e-6
+    # bins 0 and N/2 carry (numerically) zero power after the per-segment detrend: compare away from 0/0
+    ok = (ref.sxx.cpu().numpy()[:, :, None] > 1e-6) & (ref.syy.cpu().numpy()[:, None, :] > 1e-6)
+    assert np.max(np.abs(got.coh.cpu().numpy() - ref.coh.cpu().numpy())[ok]) < 2e-6
+    # and a second call on the same stream gives the same bits (no state left behind)
+    again = K.csd_msc(X, Y)
+    np.testing.assert_array_equal(again.coh.cpu().numpy(), got.coh.cpu().numpy())
