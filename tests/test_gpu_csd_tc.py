@@ -308,3 +308,24 @@ def test_direct_path_many_tiles_per_cta(cuda_device, ne, nm, N):
     # and a second call on the same stream gives the same bits (no state left behind)
     again = K.csd_msc(X, Y)
     np.testing.assert_array_equal(again.coh.cpu().numpy(), got.coh.cpu().numpy())
+
+
+@pytest.mark.parametrize("L", [1, 2, 31, 32, 33, 65])
+@pytest.mark.parametrize("ne,nm,F", [(2, 2, 3), (66, 4, 5)])
+def test_direct_path_segment_count_edges(cuda_device, L, ne, nm, F):
+    """Segment counts around the 32-segment k-block of the direct kernel (TMA zero-fills the tail) on random
+    spectra, against a float64 contraction."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(1000 + L)
+    X = torch.randn((L, F, ne), dtype=torch.complex64, device="cuda", generator=g)
+    Y = torch.randn((L, F, nm), dtype=torch.complex64, device="cuda", generator=g) + 0.3 * X[:, :, :1]
+    got = K.csd_msc(X, Y, want_sxy=True)
+    Xd, Yd = X.to(torch.complex128), Y.to(torch.complex128)
+    sxy = torch.einsum("lfi,lfj->fij", Xd.conj(), Yd)
+    sxx = (Xd.abs() ** 2).sum(0)
+    syy = (Yd.abs() ** 2).sum(0)
+    coh = (sxy.abs() ** 2 / (sxx[:, :, None] * syy[:, None, :])).clamp(0, 1)
+    assert torch.max(torch.abs(got.coh.double() - coh)).item() < 2e-5
+    assert torch.max(torch.abs(got.sxy.to(torch.complex128) - sxy) / torch.sqrt(sxx[:, :, None] * syy[:, None, :])).item() < 1e-5
+    torch.testing.assert_close(got.sxx.double(), sxx, rtol=1e-5, atol=0)
+    torch.testing.assert_close(got.syy.double(), syy, rtol=1e-5, atol=0)
