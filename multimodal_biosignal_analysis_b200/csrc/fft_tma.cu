@@ -10,6 +10,8 @@
 //     arithmetic are shared by both, shared-memory accesses are LDS.128 / STS.128, output stores 16 bytes.
 // Shared-memory rows are XOR-swizzled so that all butterfly strides are bank-conflict free.
 #include "fft_common.cuh"
+
+#include <atomic>
 #include "tc_common.cuh"
 #include "csd_layout.cuh"
 #include <stdlib.h>
@@ -271,14 +273,37 @@ struct PipeCtrl {
     unsigned fills[3];       // number of TMA fills issued into each buffer (parity of the next wait)
     int next_buf[2];         // per worker: prefetched buffer or -1
     unsigned next_parity[2];
+    long long next_tile[2];  // per worker: tile claimed for the next round
 };
+
+// Tiles beyond the first one of every worker are claimed from a device-wide counter, so workers that start late
+// (their SM was still busy with another kernel) or run slower simply take fewer tiles.  One slot per launch in
+// flight; the last worker to leave resets its slot, so a slot is reusable by the next stream-ordered launch (and by
+// CUDA-graph replays, whose kernel arguments are frozen).
+struct TileCounter {
+    unsigned next;           // tiles claimed so far beyond the 2 * gridDim.x initial ones
+    unsigned done;           // workers that have left the kernel
+};
+constexpr int kTileCounterSlots = 64;
+__device__ TileCounter g_tile_counters[kTileCounterSlots];
+
+__device__ __forceinline__ void worker_leave(TileCounter* ctr, int tid) {
+    if (tid == 0 && ctr) {
+        __threadfence();
+        if (atomicAdd(&ctr->done, 1u) == 2u * gridDim.x - 1u) {   // every worker has claimed its last tile
+            ctr->next = 0u;
+            ctr->done = 0u;
+            __threadfence();
+        }
+    }
+}
 
 template <int M>
 __global__ void __launch_bounds__(M / 2, 1)
 fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch, int n_seg,
                              const int64_t* __restrict__ seg_starts, const float* __restrict__ windows, int n_win,
                              int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
-                             const float2* __restrict__ twM, const float2* __restrict__ twN) {
+                             const float2* __restrict__ twM, const float2* __restrict__ twN, TileCounter* ctr) {
     constexpr int N = 2 * M;
     constexpr int NT = M / 4;                  // threads per worker
     constexpr int kTileBytes = N * 32;
@@ -294,8 +319,7 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
     float* mean_s = mean_all + worker * kTmaCT;
     const int n_ct = (n_ch + kTmaCT - 1) / kTmaCT;
     const long long total = (long long)n_seg * n_ct;
-    const long long stride = 2ll * gridDim.x;
-    long long t = 2ll * blockIdx.x + worker;
+    long long t = 2ll * blockIdx.x + worker;   // first tile is static, the rest come from the counter
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < 3; ++b) {
@@ -308,18 +332,27 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
         tma_prefetch_desc(&tmap);
     }
     __syncthreads();
-    if (t >= total) return;                    // this worker has no tile; buffer 2 stays with the other worker
+    if (t >= total) {                          // this worker has no tile; buffer 2 stays with the other worker
+        worker_leave(ctr, tid);
+        return;
+    }
 
     int cur = worker;
     unsigned cur_parity = 0;
+    long long tn = total, tnn = total;         // thread 0 of the worker: tiles claimed for the next two rounds
     if (tid == 0) {
         issue_tile_tma<M>(base + cur * kTileBytes, &tmap, &ctl->full[cur], (int)(t % n_ct) * kTmaCT,
                           (int)seg_starts[t / n_ct]);
         ctl->fills[cur] = 1;
+        tn = ctr ? 2ll * gridDim.x + atomicAdd(&ctr->next, 1u) : t + 2ll * gridDim.x;
     }
     while (true) {
         const int seg = (int)(t / n_ct), c0 = (int)(t % n_ct) * kTmaCT;
-        const long long tn = t + stride;
+        if (tid == 0) {
+            ctl->next_tile[worker] = tn;       // read by the whole worker after the tile's last barrier
+            // claim one round ahead: the atomic's round trip hides behind this tile
+            tnn = !ctr ? tn + 2ll * gridDim.x : (tn < total ? 2ll * gridDim.x + atomicAdd(&ctr->next, 1u) : total);
+        }
         for (int kw = 0; kw < n_win; ++kw) {
             if (kw > 0 && tid == 0) {          // the in-place transform consumed the raw tile: fetch it again
                 cur_parity = ctl->fills[cur] & 1;
@@ -350,14 +383,16 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
                                    windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN);
         }
         // process_tile ended with a worker barrier: the buffer is no longer read and ctl->next_* is visible
-        t = tn;
+        t = ctl->next_tile[worker];
         if (t >= total) {
             if (tid == 0) {
                 __threadfence_block();
                 atomicCAS(&ctl->free_buf, -1, cur);                // let the other worker prefetch into it
             }
+            worker_leave(ctr, tid);
             break;
         }
+        tn = tnn;
         const int nb = ctl->next_buf[worker];
         if (nb >= 0) {
             const unsigned np = ctl->next_parity[worker];
@@ -411,8 +446,15 @@ static int launch_tma_pipe(const CUtensorMap& tmap, int n_ch, const int64_t* seg
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT);
     const long long grid = (tiles + 1) / 2 < sms ? (tiles + 1) / 2 : sms;
+    // one counter slot per launch in flight (round robin; zero-initialised device memory, reset by the kernel)
+    static std::atomic<unsigned> next_slot{0};
+    TileCounter* slots = nullptr;
+    rc = check_cuda(cudaGetSymbolAddress(reinterpret_cast<void**>(&slots), g_tile_counters), "cudaGetSymbolAddress");
+    if (rc) return rc;
+    static const bool static_tiles = getenv("CMC_FFT_STATIC_TILES") != nullptr;      // fixed stride instead of claims
+    TileCounter* ctr = static_tiles ? nullptr : slots + next_slot.fetch_add(1) % kTileCounterSlots;
     kern<<<(unsigned)grid, 2 * NT, smem, st>>>(tmap, n_ch, n_seg, seg_starts, windows, n_win, detrend, bin_lo, F, spec,
-                                               spec_ld, twM, twN);
+                                               spec_ld, twM, twN, ctr);
     CMC_CHECK_LAUNCH("fft_segments_tma_pipe_kernel");
     return CMC_OK;
 }
