@@ -703,6 +703,123 @@ def welch_magnitude_squared_coherence(eeg_array, emg_array, sampling_freq: float
                             eeg_axis, emg_axis)
 
 
+def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, noverlap: int | None = None,
+                          window: str = "hann", detrend: str | bool = "constant",
+                          freq_band: tuple[float, float] | None = None, segment_starts=None):
+    """Welch coherence of MANY recordings of equal shape (the subject-condition sweep of the workflows): a
+    generator that yields ``(coherence (F, Ne, Nm) float32 numpy, freqs)`` per ``(eeg, emg)`` item, in order.
+
+    Same arithmetic as :func:`welch_magnitude_squared_coherence` item by item, but the items are pipelined over
+    three CUDA streams - upload of item i + 1, K1 + K2 of item i and download of item i - 1 overlap - so a sweep runs
+    at the speed of the PCIe upload instead of the sum of the three.  Items must be time-first
+    ``(n_samples, n_channels)`` float32; pinned host tensors (``torch.Tensor.pin_memory()``) upload asynchronously,
+    anything else is staged through a pinned buffer first (one extra host copy).  The yielded coherence array is
+    only valid until the next-but-one item is requested (two host buffers rotate); copy it to keep it."""
+    it = iter(recordings)
+    try:
+        first = next(it)
+    except StopIteration:
+        return
+    dev = _device()
+    eeg0, emg0 = first
+    n, ne, nm = int(eeg0.shape[0]), int(eeg0.shape[1]), int(emg0.shape[1])
+    if int(emg0.shape[0]) != n:
+        raise ValueError("EEG and EMG must have same number of samples")
+    if noverlap is None:
+        noverlap = nperseg // 2
+    if segment_starts is None:
+        segment_starts = np.arange(0, n - nperseg + 1, nperseg - noverlap, dtype=np.int64)
+    if detrend not in ("constant", False, None):
+        raise ValueError("only detrend='constant' or False are supported")
+    dmode = K.DETREND_CONSTANT if detrend == "constant" else K.DETREND_NONE
+    freqs = np.fft.rfftfreq(nperseg, d=1 / sampling_freq)
+    lo, hi = 0, len(freqs) - 1
+    if freq_band is not None:
+        sel = np.flatnonzero((freqs >= freq_band[0]) & (freqs <= freq_band[1]))
+        if len(sel) == 0:
+            raise ValueError(f"freq_band {freq_band} selects no frequency bin")
+        lo, hi = int(sel[0]), int(sel[-1])
+    F = hi - lo + 1
+    K.check_segments(segment_starts, nperseg, n)
+    starts_d = torch.as_tensor(np.asarray(segment_starts, dtype=np.int64)).to(dev)
+    wd = torch.from_numpy(signal.get_window(window, nperseg).astype(np.float32)[None]).to(dev)
+    L = len(segment_starts)
+    ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)                    # even channel pitch for K2's TMA
+    slots = []
+    for _ in range(2):
+        slots.append(dict(
+            eeg=torch.empty((n, ne), dtype=torch.float32, device=dev),
+            emg=torch.empty((n, nm), dtype=torch.float32, device=dev),
+            X=torch.empty((L, 1, F, ne_p), dtype=torch.complex64, device=dev),
+            Y=torch.empty((L, 1, F, nm_p), dtype=torch.complex64, device=dev),
+            out=torch.empty((F, ne, nm), dtype=torch.float32).pin_memory(),
+            stage=None, h2d=None, comp=None, d2h=None, res=None))
+    s_up, s_comp, s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+    for st in (s_up, s_comp, s_down):
+        st.wait_stream(cur)
+
+    def host_f32(a, slot, key):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a
+            if a.dtype == torch.float32 and a.is_pinned() and a.is_contiguous():
+                return a
+            a = a.numpy()
+        if slot["stage"] is None:
+            slot["stage"] = {"eeg": torch.empty((n, ne), dtype=torch.float32).pin_memory(),
+                             "emg": torch.empty((n, nm), dtype=torch.float32).pin_memory()}
+        buf = slot["stage"][key]
+        np.copyto(buf.numpy(), np.asarray(a), casting="same_kind")
+        return buf
+
+    def submit(item, i):
+        slot = slots[i % 2]
+        eeg, emg = item
+        if tuple(eeg.shape) != (n, ne) or tuple(emg.shape) != (n, nm):
+            raise ValueError("all recordings of a sweep must have the shape of the first one")
+        if slot["comp"] is not None:                              # the slot's previous item has been transformed
+            s_up.wait_event(slot["comp"])
+        if slot["stage"] is not None and slot["h2d"] is not None:
+            slot["h2d"].synchronize()                             # staging buffer still being read by the copy engine
+        with torch.cuda.stream(s_up):
+            slot["eeg"].copy_(host_f32(eeg, slot, "eeg"), non_blocking=True)
+            slot["emg"].copy_(host_f32(emg, slot, "emg"), non_blocking=True)
+            slot["h2d"] = torch.cuda.Event()
+            slot["h2d"].record()
+        with torch.cuda.stream(s_comp):
+            s_comp.wait_event(slot["h2d"])
+            if slot["d2h"] is not None:
+                s_comp.wait_event(slot["d2h"])                    # previous result of this slot has left the device
+            K.fft_segments(slot["eeg"], starts_d, wd, dmode, lo, hi, out=slot["X"], ch_offset=0)
+            K.fft_segments(slot["emg"], starts_d, wd, dmode, lo, hi, out=slot["Y"], ch_offset=0)
+            res = K.csd_msc(slot["X"].view(L, F, ne_p)[:, :, :ne], slot["Y"].view(L, F, nm_p)[:, :, :nm])
+            slot["comp"] = torch.cuda.Event()
+            slot["comp"].record()
+        with torch.cuda.stream(s_down):
+            s_down.wait_event(slot["comp"])
+            slot["out"].copy_(res.coh, non_blocking=True)
+            res.coh.record_stream(s_down)
+            slot["d2h"] = torch.cuda.Event()
+            slot["d2h"].record()
+        slot["res"] = res
+
+    def collect(i):
+        slot = slots[i % 2]
+        slot["d2h"].synchronize()
+        return slot["out"].numpy(), freqs[lo:hi + 1]
+
+    submit(first, 0)
+    i = 0
+    for item in it:
+        i += 1
+        submit(item, i)                                           # item i is in flight while item i - 1 is handed out
+        yield collect(i - 1)
+    yield collect(i)
+    cur.wait_stream(s_comp)
+    cur.wait_stream(s_down)
+
+
 def local_neighbor_coherence(data, neighbor_mapping, sampling_freq: float, nperseg: int = 256) -> float:
     """Average magnitude-squared coherence of every electrode with its neighbours - the quantity
     ``BiosignalPreprocessor.validate_spatial_filtering`` evaluates before / after spatial filtering with one

@@ -251,3 +251,27 @@ def test_local_neighbor_coherence_vs_scipy_loop(cuda_device):
         ref.append(np.nanmean([np.nanmean(ss.coherence(data[:, ch], data[:, nb], fs=512.0)[1]) for nb in nbs]))
     got = sf.local_neighbor_coherence(data, mapping, 512.0)
     assert got == pytest.approx(float(np.nanmean(ref)), abs=0.01)       # DC bin: 0/0 in both, 1/129 of the mean
+
+
+def test_welch_coherence_sweep_matches_item_by_item(cuda_device):
+    """The three-stream sweep (upload / K1 + K2 / download overlapped across recordings) returns, item by item,
+    exactly what welch_magnitude_squared_coherence returns - for pinned tensors, plain numpy arrays and a
+    single-item sweep, with odd channel counts."""
+    import torch
+    from multimodal_biosignal_analysis_b200 import signal_features as sf, synthetic as syn
+    fs, nper = 512.0, 256
+    recs = []
+    for k in range(5):
+        eeg, emg = syn.make_epochs(2, 2048, 7, 10, seed=60 + k)
+        recs.append((eeg, emg))
+    ref = [sf.welch_magnitude_squared_coherence(e, m, fs, nperseg=nper, freq_band=(2, 60)).coherence for e, m in recs]
+    pinned = [(torch.from_numpy(e).pin_memory(), torch.from_numpy(m).pin_memory()) for e, m in recs]
+    for items in (pinned, recs, recs[:1], (r for r in pinned[:2])):
+        got = []
+        for coh, freqs in sf.welch_coherence_sweep(items, fs, nperseg=nper, freq_band=(2, 60)):
+            got.append(coh.copy())
+            assert freqs[0] >= 2 and freqs[-1] <= 60 and coh.shape == (len(freqs), 7, 10)
+        assert len(got) >= 1
+        for g, r in zip(got, ref):
+            np.testing.assert_array_equal(g, r)
+    assert list(sf.welch_coherence_sweep([], fs)) == []
