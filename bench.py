@@ -390,13 +390,13 @@ def main_gpu(args):
         "metric": "surrogates_per_s", "value": N_SURR / (surr_ms / 1e3), "unit": "surrogates/s",
         "ms": surr_ms, "scaling": "replicated",
         "config": f"config 3: {N_SURR} circular-shift surrogates of one 64x64xF=100 subject-condition; distinct shifts are "
-                  f"deduplicated on the device ({n_distinct} of L={L}), each is one TF32 tcgen05 CSD pass, so the cost "
-                  f"does not grow beyond {L - 1} passes (10,000 surrogates take the same time); every rank runs it "
-                  f"for its own subject-condition",
+                  f"deduplicated on the device ({n_distinct} of L={L}), four of them share one TF32 tcgen05 tile "
+                  f"(N = 256), so the cost does not grow beyond {L - 1} CSD passes (10,000 surrogates take the same "
+                  f"time); every rank runs it for its own subject-condition",
         "roofline": {"bound": "tensor", "achieved": flop / (surr_ms * 1e-3) / 1e12, "peak": bf16 / 2,
                      "unit": "TFLOP/s", "frac": flop / (surr_ms * 1e-3) / 1e12 / (bf16 / 2),
-                     "note": "executed TF32 flop of the distinct-shift passes (M=128 x N=64 tiles, operand-fetch "
-                             "bound); TF32 peak taken as half the measured dense bf16 figure"},
+                     "note": "executed TF32 flop of the distinct-shift passes (M=128 x N=256 tiles; bound by the "
+                             "per-output epilogue on 4 warps); TF32 peak taken as half the measured dense bf16 figure"},
     }
 
     # ---- stage: phase-randomised surrogates (config 3 count per rank-shard of config 5's 10,000) ----

@@ -425,6 +425,9 @@ __global__ void shift_gather_kernel(const int32_t* __restrict__ shifts, int64_t 
     }
 }
 
+int launch_shift4(const CsdLayout& y, unsigned char* ws, int f_begin, int f_end, int Ne, int Nm, int n_pos,
+                  const int32_t* shift_off, const uint32_t* shift_mult, const float* coh_obs, uint32_t* exceed,
+                  uint32_t* max_u, cudaStream_t st);
 bool csd_direct_ok(const float* X, const float* Y, int64_t ldx, int64_t ldy);
 int csd_msc_direct(const float* X, const float* Y, int L, int F, int Ne, int Nm, int64_t ldx, int64_t ldy, float* coh,
                    float* sxx, float* syy, float* sxy, unsigned char* w, const CsdLayout& y, cudaStream_t st);
@@ -588,14 +591,20 @@ extern "C" int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, 
         reinterpret_cast<const float*>(w + y.off_bhi), L, y.KP, y.LB, reinterpret_cast<float*>(w + y.off_bdbl),
         reinterpret_cast<float*>(w + y.off_bodd));
     CMC_CHECK_LAUNCH("shift_operand_kernel");
-    CsdParams p{};
-    p.F = f_end - f_begin; p.f0 = f_begin;
-    p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock; p.nterms = 1; p.n_shift = n_pos;
-    p.shift_off = off; p.shift_mult = mult; p.coh_obs = coh_obs; p.exceed = exceed; p.max_u = max_u;
-    p.pxx = reinterpret_cast<const float*>(w + y.off_pxx);
-    p.pyy = reinterpret_cast<const float*>(w + y.off_pyy);
-    p.total_tiles = (long long)(f_end - f_begin) * y.MT * y.NT * n_pos;
-    rc = launch_gemm<1>(y, w, p, st);
+    static const bool one_per_tile = getenv("CMC_SHIFT_NO_BATCH") != nullptr;
+    if (!one_per_tile) {
+        // four shifts share one staged A tile (csd_shift.cu)
+        rc = launch_shift4(y, w, f_begin, f_end, Ne, Nm, n_pos, off, mult, coh_obs, exceed, max_u, st);
+    } else {
+        CsdParams p{};
+        p.F = f_end - f_begin; p.f0 = f_begin;
+        p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock; p.nterms = 1; p.n_shift = n_pos;
+        p.shift_off = off; p.shift_mult = mult; p.coh_obs = coh_obs; p.exceed = exceed; p.max_u = max_u;
+        p.pxx = reinterpret_cast<const float*>(w + y.off_pxx);
+        p.pyy = reinterpret_cast<const float*>(w + y.off_pyy);
+        p.total_tiles = (long long)(f_end - f_begin) * y.MT * y.NT * n_pos;
+        rc = launch_gemm<1>(y, w, p, st);
+    }
     if (rc) return rc;
     shift_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shifts, n, n_pos, max_u, max_stat);
     CMC_CHECK_LAUNCH("shift_gather_kernel");
