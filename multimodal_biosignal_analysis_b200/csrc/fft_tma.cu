@@ -100,6 +100,17 @@ __device__ __forceinline__ void pass_pair(uint32_t sbuf, const float2* __restric
 
 // Transforms the raw tile that sits at `sbuf` (N rows x 8 channels, written by TMA) in place and writes the
 // requested bins of window row `kw`.  Executed by the NT = M / 4 threads that synchronise on barrier `bar_id`.
+#ifdef CMC_K1_PROFILE
+// instrumented build only: per-phase clock64() totals of thread 0 of worker 0 of every CTA
+__device__ unsigned long long g_k1_cycles[8];
+#define K1_TICK(i) do { if (tid == 0 && bar_id == 1) { const long long now_ = clock64(); \
+    atomicAdd(&g_k1_cycles[i], (unsigned long long)(now_ - tick_)); tick_ = now_; } } while (0)
+#define K1_TICK_INIT long long tick_ = clock64()
+#else
+#define K1_TICK(i) do { } while (0)
+#define K1_TICK_INIT do { } while (0)
+#endif
+
 struct NoPoll {
     __device__ __forceinline__ void operator()() const {}
 };
@@ -115,6 +126,7 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
     constexpr int B0 = kPtsPerThread / R0;
     constexpr int S0 = M / R0;
     const float* win = windows + (int64_t)kw * N;
+    K1_TICK_INIT;
     float2 va[B0][R0], vb[B0][R0];
 #pragma unroll
     for (int b = 0; b < B0; ++b) {
@@ -163,6 +175,7 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
     }
     // every thread has its raw samples in registers: the tile may now be overwritten in place
     group_sync(bar_id, NT);
+    K1_TICK(1);
     poll();
 #pragma unroll
     for (int b = 0; b < B0; ++b) {
@@ -181,10 +194,13 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
             sts128(sbuf + pt_off(j * R0 + r, cp), make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
     }
     group_sync(bar_id, NT);
+    K1_TICK(2);
     poll();
     if (R1 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(sbuf, twM, tid, bar_id);
+    K1_TICK(3);
     poll();
     if (R2 > 1) pass_pair<M, (R2 > 1 ? R2 : 2), R0 * R1>(sbuf, twM, tid, bar_id);
+    K1_TICK(4);
     poll();
 
     // ---- real-FFT split for the requested bins; 2 channels = 16 bytes per lane ----
@@ -216,7 +232,18 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
         }
     }
     group_sync(bar_id, NT);
+    K1_TICK(5);
 }
+
+#ifdef CMC_K1_PROFILE
+}  // namespace cmc
+extern "C" CMC_API int cmc_dbg_k1_cycles(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, cmc::g_k1_cycles, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(cmc::g_k1_cycles, z, sizeof(z)); }
+    return 0;
+}
+namespace cmc {
+#endif
 
 // one thread: raw tile of (segment start, channel tile) -> shared memory, N rows of 32 bytes in boxes of 256 rows
 template <int M>
@@ -363,7 +390,13 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
                 group_sync(bar_id, NT);
                 cur_parity = (ctl->fills[cur] - 1) & 1;
             }
+#ifdef CMC_K1_PROFILE
+            long long w0_ = clock64();
+#endif
             mbar_wait(&ctl->full[cur], cur_parity);
+#ifdef CMC_K1_PROFILE
+            if (tid == 0 && worker == 0) atomicAdd(&g_k1_cycles[0], (unsigned long long)(clock64() - w0_));
+#endif
             // thread 0 of the worker tries to claim the idle buffer for the worker's next tile - here and again after
             // every pass barrier, so that a buffer released by the other worker mid-tile is picked up at once
             auto poll = [&]() {
