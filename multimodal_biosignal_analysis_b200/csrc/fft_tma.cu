@@ -132,11 +132,16 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
     for (int b = 0; b < B0; ++b) {
         const int q = tid + b * NT;
         const int cp = q & 3, j = q >> 2;
+        // rows are 32 bytes and a lane group of four owns one row, so a half-warp that read the even rows of four
+        // consecutive points would hit only half of the banks; every other point pair reads its odd row first
+        const int sw = (j >> 1) & 1;
 #pragma unroll
         for (int r = 0; r < R0; ++r) {
             const int n0 = 2 * (j + r * S0);
-            const float2 re = lds64(sbuf + raw_off<SWZ>(n0, cp));       // x[2p][c], x[2p][c+1]
-            const float2 im = lds64(sbuf + raw_off<SWZ>(n0 + 1, cp));   // x[2p+1][c], x[2p+1][c+1]
+            const float2 first = lds64(sbuf + raw_off<SWZ>(n0 + sw, cp));
+            const float2 second = lds64(sbuf + raw_off<SWZ>(n0 + 1 - sw, cp));
+            const float2 re = sw ? second : first;                      // x[2p][c], x[2p][c+1]
+            const float2 im = sw ? first : second;                      // x[2p+1][c], x[2p+1][c+1]
             va[b][r] = make_float2(re.x, im.x);
             vb[b][r] = make_float2(re.y, im.y);
         }
@@ -163,15 +168,23 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
                 part[(tid >> 5) * kTmaCT + 2 * (tid & 31) + 1] = sb;
             }
             group_sync(bar_id, NT);
-            if (tid < kTmaCT) {
-                float t = 0.f;
-                for (int w = 0; w < NT / 32; ++w) t += part[w * kTmaCT + tid];
-                mean_s[tid] = t * (1.0f / N);
+            // every thread folds the warp partials of its own channel pair (same order everywhere): no second barrier
+            float ta = 0.f, tb = 0.f;
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) {
+                ta += part[w * kTmaCT + 2 * (tid & 3)];
+                tb += part[w * kTmaCT + 2 * (tid & 3) + 1];
             }
-            group_sync(bar_id, NT);
+            mua = ta * (1.0f / N);
+            mub = tb * (1.0f / N);
+            if (tid < 4) {                                 // kept for the other tapers of this segment
+                mean_s[2 * tid] = mua;
+                mean_s[2 * tid + 1] = mub;
+            }
+        } else {
+            mua = mean_s[2 * (tid & 3)];
+            mub = mean_s[2 * (tid & 3) + 1];
         }
-        mua = mean_s[2 * (tid & 3)];
-        mub = mean_s[2 * (tid & 3) + 1];
     }
     // every thread has its raw samples in registers: the tile may now be overwritten in place
     group_sync(bar_id, NT);
