@@ -151,6 +151,91 @@ def run_cpu_reference(steps, warmup, sample_epochs=N_EPOCHS):
     return NE * NM / (ms / 1e3), ms, cores, sample
 
 
+_CPU_STAGE = {}
+
+
+def _cpu_surr_chunk(args):
+    from oracle import surrogate as osur
+    mode, idx, shifts, seed = args
+    Xw, Yw, coh_obs = _CPU_STAGE["Xw"], _CPU_STAGE["Yw"], _CPU_STAGE["coh"]
+    cs = osur.surrogate_coherence(Xw, Yw, mode, idx, shifts=shifts, seed=seed)
+    cnt, ms = osur.null_statistics(cs, coh_obs)
+    return cnt, ms
+
+
+def _cpu_cbpa_chunk(args):
+    from oracle import cbpa as ocb
+    from scipy import sparse
+    signs, thr = args
+    Xf, coo = _CPU_STAGE["Xf"], _CPU_STAGE["coo"]
+    out = []
+    for sg in signs:
+        tp = ocb.ttest_1samp_no_p(Xf * sg[:, None].astype(np.float64))
+        _, _, im = ocb.find_clusters(tp, thr, 0, coo)
+        out.append(ocb.max_stat_fixed(im, 0))
+    return out
+
+
+def run_cpu_stage_baselines(n_surr_cpu=32, n_perm_cpu=256):
+    """Oracle ports of the surrogate null and the CBPA on the host cores (bounded samples, forked workers share
+    the inputs): returns {stage: cpu_baseline dict}."""
+    import multiprocessing as mp
+    from scipy import signal, sparse
+    from scipy.stats import t as t_dist
+    from oracle import cbpa as ocb, coherence as oc, surrogate as osur
+    from multimodal_biosignal_analysis_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    out = {}
+    # spectra of config 2 (fp64), whitened once - the CPU analogue of the cached operands
+    eeg, emg = syn.make_epochs(N_EPOCHS, EPOCH, NE, NM, seed=20260102)
+    starts = syn.epoch_segment_starts(N_EPOCHS, EPOCH, NPERSEG, HOP)
+    win = signal.get_window("hann", NPERSEG)[None]
+    freqs = np.fft.rfftfreq(NPERSEG, 1 / FS)
+    sel = np.flatnonzero((freqs >= BAND[0]) & (freqs <= BAND[1]))
+    lo, hi = int(sel[0]), int(sel[-1])
+    X = oc.segment_spectra(eeg.astype(np.float64), starts, win, 1, lo, hi)[:, 0]
+    Y = oc.segment_spectra(emg.astype(np.float64), starts, win, 1, lo, hi)[:, 0]
+    _CPU_STAGE["Xw"], _ = osur.whiten(X)
+    _CPU_STAGE["Yw"], _ = osur.whiten(Y)
+    _CPU_STAGE["coh"] = oc.msc_from_spectra(X, Y)[0]
+    Xc = syn.make_cbpa_contrast(*CBPA_SHAPE)
+    adj = ocb.combine_adjacency(CBPA_SHAPE[1], ocb.delaunay_adjacency(syn.sensor_positions(CBPA_SHAPE[2])))
+    _CPU_STAGE["Xf"] = np.ascontiguousarray(Xc.reshape(CBPA_SHAPE[0], -1), dtype=np.float64)
+    _CPU_STAGE["coo"] = sparse.coo_matrix(adj)
+    thr = float(t_dist.ppf(0.975, CBPA_SHAPE[0] - 1))
+    signs = syn.make_sign_table(n_perm_cpu, CBPA_SHAPE[0], seed=42)
+    shifts = np.random.default_rng(3).integers(1, len(starts), n_surr_cpu).astype(np.int32)
+    ctx = mp.get_context("fork")
+    pool = ctx.Pool(cores) if cores > 1 else None
+    mapper = pool.map if pool else (lambda f, jobs: [f(j) for j in jobs])
+    try:
+        for mode, key in (("phase", "surrogate_null_phase"), ("shift", "surrogate_null_shift")):
+            chunks = [c for c in np.array_split(np.arange(n_surr_cpu), cores) if len(c)]
+            jobs = [(mode, c, shifts if mode == "shift" else None, 7) for c in chunks]
+            mapper(_cpu_surr_chunk, jobs[:1])                                  # warm the workers
+            t0 = time.perf_counter()
+            mapper(_cpu_surr_chunk, jobs)
+            dt = time.perf_counter() - t0
+            out[key] = {"value": n_surr_cpu / dt, "unit": "surrogates/s", "cores": cores, "kind": "port",
+                        "sample": f"oracle/surrogate.py ({mode}): {n_surr_cpu} surrogates of config 2 (64x64xF=100, "
+                                  f"L={len(starts)}) on cached whitened spectra, numpy complex128 einsum per surrogate, "
+                                  f"{cores} worker processes"}
+        chunks = [c for c in np.array_split(np.arange(n_perm_cpu), cores) if len(c)]
+        jobs = [(signs[c], thr) for c in chunks]
+        mapper(_cpu_cbpa_chunk, jobs[:1])
+        t0 = time.perf_counter()
+        mapper(_cpu_cbpa_chunk, jobs)
+        dt = time.perf_counter() - t0
+        out["cbpa"] = {"value": n_perm_cpu / dt, "unit": "permutations/s", "cores": cores, "kind": "port",
+                       "sample": f"oracle/cbpa.py (MNE algorithm: numpy t-map + scipy connected_components): "
+                                 f"{n_perm_cpu} permutations of the config 4 geometry, {cores} worker processes"}
+    finally:
+        if pool:
+            pool.terminate()
+        _CPU_STAGE.clear()
+    return out
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -511,6 +596,8 @@ def main_gpu(args):
         v, ms, cores, sample = run_cpu_reference(steps=2, warmup=1, sample_epochs=10)
         cpu = {"value": v, "unit": "pair-spectra/s", "cores": cores, "kind": "port", "sample": sample,
                "ms_per_step": ms}
+        for key, base in run_cpu_stage_baselines().items():       # CPU ports of the surrogate / CBPA stages
+            stages[key]["cpu_baseline"] = base
 
     if rank == 0:
         line = {
