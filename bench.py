@@ -176,7 +176,20 @@ def _cpu_cbpa_chunk(args):
     return out
 
 
-def run_cpu_stage_baselines(n_surr_cpu=32, n_perm_cpu=256):
+def _cpu_mt_chunk(args):
+    from oracle import coherence as oc
+    starts, lo, hi = args
+    eeg, emg, tapers = _CPU_STAGE["eeg"], _CPU_STAGE["emg"], _CPU_STAGE["tapers"]
+    n = 0
+    for s0 in starts:
+        X = oc.segment_spectra(eeg, np.array([s0]), tapers, 0, lo, hi)[0]          # (K, F, Ne), no detrend
+        Y = oc.segment_spectra(emg, np.array([s0]), tapers, 0, lo, hi)[0]
+        m, l, h = oc.jackknife_from_spectra(X, Y, 0.05)
+        n += int((m > 0.81).sum() >= 0)                                            # mask as in the GPU stage
+    return n
+
+
+def run_cpu_stage_baselines(n_surr_cpu=32, n_perm_cpu=256, n_win_cpu=32):
     """Oracle ports of the surrogate null and the CBPA on the host cores (bounded samples, forked workers share
     the inputs): returns {stage: cpu_baseline dict}."""
     import multiprocessing as mp
@@ -205,10 +218,23 @@ def run_cpu_stage_baselines(n_surr_cpu=32, n_perm_cpu=256):
     thr = float(t_dist.ppf(0.975, CBPA_SHAPE[0] - 1))
     signs = syn.make_sign_table(n_perm_cpu, CBPA_SHAPE[0], seed=42)
     shifts = np.random.default_rng(3).integers(1, len(starts), n_surr_cpu).astype(np.int32)
+    _CPU_STAGE["eeg"], _CPU_STAGE["emg"] = eeg.astype(np.float64), emg.astype(np.float64)
+    _CPU_STAGE["tapers"] = oc.dpss_tapers(NPERSEG, 3, 0.9)[0]
     ctx = mp.get_context("fork")
     pool = ctx.Pool(cores) if cores > 1 else None
     mapper = pool.map if pool else (lambda f, jobs: [f(j) for j in jobs])
     try:
+        chunks = [c for c in np.array_split(starts[:n_win_cpu], cores) if len(c)]
+        jobs = [(c, lo, hi) for c in chunks]
+        mapper(_cpu_mt_chunk, jobs[:1])
+        t0 = time.perf_counter()
+        mapper(_cpu_mt_chunk, jobs)
+        dt = time.perf_counter() - t0
+        out["multitaper_windows"] = {
+            "value": min(n_win_cpu, len(starts)) * NE * NM / dt, "unit": "pair-spectra/s (one per window)",
+            "cores": cores, "kind": "port",
+            "sample": f"oracle/coherence.py (DPSS spectra + leave-one-taper-out jackknife CI, F = {hi - lo + 1} in-band "
+                      f"bins): {min(n_win_cpu, len(starts))} of the 210 windows, {cores} worker processes"}
         for mode, key in (("phase", "surrogate_null_phase"), ("shift", "surrogate_null_shift")):
             chunks = [c for c in np.array_split(np.arange(n_surr_cpu), cores) if len(c)]
             jobs = [(mode, c, shifts if mode == "shift" else None, 7) for c in chunks]
