@@ -7,11 +7,11 @@
 //     D[(i,ci)][(j,cj)] = sum_l X[l][i].ci * Y[l][j].cj              (M = N = 128, K = L)
 // holds the four real products of every pair; the epilogue folds the 2 x 2 blocks,
 //     Re S_ij = D[(i,0)][(j,0)] + D[(i,1)][(j,1)],   Im S_ij = D[(i,0)][(j,1)] - D[(i,1)][(j,0)],
-// with one shuffle between the two TMEM lanes of a channel, then normalises with the auto-spectra.
+// with two shuffles between the two TMEM lanes of a channel, then normalises with the auto-spectra.
 // TMA stages 32 segments x 32 floats boxes (128-byte swizzle with 32-byte base, the only layout UMMA accepts for
-// MN-major TF32 operands; segments past L and channels past the last read as
-// zeros); four converter warps round the tile to TF32 in place, write the lo plane (3xTF32: lo*hi + hi*lo +
-// hi*hi) and accumulate Pxx / Pyy in a fixed order.  HBM traffic = the spectra, once.
+// MN-major TF32 operands; segments past L and channels past the last read as zeros); eight converter warps round
+// the tile to TF32 in place, write the lo plane (3xTF32: lo*hi + hi*lo + hi*hi) and accumulate Pxx / Pyy in a
+// fixed order.  HBM traffic = the spectra, once.
 //
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue,
 // warps 8-15 converters.  Stage ring: full (TMA bytes) -> conv (256 converter arrivals) -> MMAs -> empty.
