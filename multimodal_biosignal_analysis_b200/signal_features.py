@@ -10,6 +10,8 @@ all-pairs pooled estimator that feeds the surrogate null (``data_surrogation.py`
 """
 from __future__ import annotations
 
+import functools
+
 from pathlib import Path
 from typing import Literal
 
@@ -148,7 +150,7 @@ def multitaper_psd(input_array, sampling_freq: float, nw: float = 3, window_leng
     window_samples = int(window_length_sec * sampling_freq)
     hop_samples = int(window_samples * (1 - overlap_frac))
     k = int(2 * nw - 1)
-    tapers = signal.windows.dpss(M=window_samples, NW=nw, Kmax=k)
+    tapers = _dpss_raw(window_samples, nw, k)
     window_starts = np.arange(0, n_samples - window_samples, hop_samples)
     time_centers = (window_starts + window_samples / 2) / sampling_freq
     freqs = np.fft.rfftfreq(window_samples, d=1 / sampling_freq)
@@ -249,12 +251,24 @@ def apply_threshold_filtering(coherence_values, K: int, alpha: float = 0.05, n_c
     return coherence_values > IT, IT
 
 
+@functools.lru_cache(maxsize=32)
+def _dpss_raw(window_samples: int, nw: float, k: int):
+    """Un-renormalised DPSS rows as multitaper_psd uses them (signal_features.py:395), cached like _dpss."""
+    out = signal.windows.dpss(M=window_samples, NW=nw, Kmax=k)
+    out.setflags(write=False)
+    return out
+
+
+@functools.lru_cache(maxsize=32)
 def _dpss(window_samples: int, nw: float, eig_threshold: float):
-    """Tapers kept by eigenvalue and L2-normalised, signal_features.py:669-678 (host side, tiny)."""
+    """Tapers kept by eigenvalue and L2-normalised, signal_features.py:669-678.  Host side; scipy needs ~16 ms for
+    N = 4096 - more than the GPU needs for a ten-minute recording - so the (read-only) table is cached."""
     k = int(2 * nw - 1)
     tapers, eigs = signal.windows.dpss(M=window_samples, NW=nw, Kmax=k, return_ratios=True)
     kept = tapers[eigs > eig_threshold]
-    return np.stack([t / np.sqrt(np.sum(t ** 2)) for t in kept]) if len(kept) else kept
+    out = np.stack([t / np.sqrt(np.sum(t ** 2)) for t in kept]) if len(kept) else kept
+    out.setflags(write=False)
+    return out
 
 
 # ----------------------------------------------------------------------------- multitaper MSC
