@@ -165,12 +165,19 @@ def make_sign_table(n_permutations: int, n_subjects: int, seed=None, tail: int =
 
 
 def _pvalues(stats_fixed: np.ndarray, h0_fixed: np.ndarray, tail: int) -> np.ndarray:
-    if tail == -1:
-        return np.array([np.mean(h0_fixed <= s) for s in stats_fixed], dtype=np.float64)
-    if tail == 1:
-        return np.array([np.mean(h0_fixed >= s) for s in stats_fixed], dtype=np.float64)
-    a = np.abs(h0_fixed)
-    return np.array([np.mean(a >= abs(int(s))) for s in stats_fixed], dtype=np.float64)
+    """MNE's ``_pval_from_histogram`` on the integer images: exact counts / len(H0), through one sort of H0 and a
+    binary search per cluster instead of one pass over H0 per cluster (same values, float64 count / n)."""
+    stats_fixed = np.asarray(stats_fixed, dtype=np.int64)
+    n = len(h0_fixed)
+    if len(stats_fixed) == 0 or n == 0:
+        return np.zeros(len(stats_fixed), dtype=np.float64)
+    if tail == -1:                                               # #{H0 <= s}
+        cnt = np.searchsorted(np.sort(h0_fixed), stats_fixed, side="right")
+    elif tail == 1:                                              # #{H0 >= s}
+        cnt = n - np.searchsorted(np.sort(h0_fixed), stats_fixed, side="left")
+    else:                                                        # #{|H0| >= |s|}
+        cnt = n - np.searchsorted(np.sort(np.abs(h0_fixed)), np.abs(stats_fixed), side="left")
+    return cnt.astype(np.float64) / float(n)
 
 
 def permutation_cluster_1samp_test(X, threshold=None, n_permutations: int = 1024, tail: int = 0,
