@@ -95,6 +95,76 @@ __device__ __forceinline__ PairStats pair_stats(const float2 (&x)[K], const floa
     return out;
 }
 
+// Jackknife statistics of one pair from the spectra and the per-channel leave-one-taper-out factors
+// rx[k] = 1 / sqrt(sum_{m != k} |x_m|^2) (0 for a silent channel), same for ry: the auto-spectra part of every
+// replicate depends on one channel only, so it is computed once per (window, bin, channel) instead of once per pair.
+// Arithmetic and summation order are those of pair_stats<K, true>, the results are bit-identical.
+template <int K>
+__device__ __forceinline__ PairStats pair_stats_jk(const float2 (&x)[K], const float2 (&y)[K], const float (&rx)[K],
+                                                   const float (&ry)[K], float t_crit) {
+    float2 c[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        c[k] = make_float2(x[k].x * y[k].x + x[k].y * y[k].y, x[k].x * y[k].y - x[k].y * y[k].x);   // conj(x) * y
+    float pre_re[K], pre_im[K];
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pre_re[k] = a; pre_im[k] = b;
+        a += c[k].x; b += c[k].y;
+    }
+    float z[K];
+    float csum = 0.f, zsum = 0.f;
+    a = b = 0.f;
+#pragma unroll
+    for (int k = K - 1; k >= 0; --k) {
+        const float r = rx[k] * ry[k];
+        const float u = (pre_re[k] + a) * r, v = (pre_im[k] + b) * r;
+        const float ck = fminf(u * u + v * v, 1.0f);
+        z[k] = fisher_z(ck);
+        csum += ck;
+        zsum += z[k];
+        a += c[k].x; b += c[k].y;
+    }
+    const float mean = fminf(fmaxf(csum * (1.0f / K), 0.f), 1.f);
+    const float zbar = zsum * (1.0f / K);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) ss += (z[k] - zbar) * (z[k] - zbar);
+    const float se = sqrtf(ss * ((float)(K - 1) / (float)K));
+    const float zc = fisher_z(mean);
+    PairStats out;
+    out.coh = mean;
+    out.lo = fminf(inv_fisher(zc - t_crit * se), mean);
+    out.hi = fmaxf(inv_fisher(zc + t_crit * se), mean);
+    return out;
+}
+
+// leave-one-out inverse roots of the staged spectra: rs[k * n + c] for the n = Ne + Nm channels (sx then sy)
+template <int K>
+__device__ __forceinline__ void stage_loo_roots(const float2* sx, const float2* sy, float* rs, int Ne, int Nm) {
+    for (int c = threadIdx.x; c < Ne + Nm; c += blockDim.x) {
+        const float2* s = c < Ne ? sx + c : sy + (c - Ne);
+        const int n = c < Ne ? Ne : Nm;
+        float pw[K], pre[K];
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float2 v = s[k * n];
+            pw[k] = v.x * v.x + v.y * v.y;
+            pre[k] = acc;
+            acc += pw[k];
+        }
+        acc = 0.f;
+#pragma unroll
+        for (int k = K - 1; k >= 0; --k) {
+            const float loo = pre[k] + acc;
+            rs[k * (Ne + Nm) + c] = loo > 0.f ? rsqrtf(loo) : 0.f;
+            acc += pw[k];
+        }
+    }
+}
+
 template <int K>
 __device__ __forceinline__ void stage_spectra(float2* sx, float2* sy, const float2* __restrict__ X,
                                               const float2* __restrict__ Y, int w, int f, int F, int Ne,
@@ -117,6 +187,7 @@ msc_windows_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, i
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sx = reinterpret_cast<float2*>(smem_raw);
     float2* sy = sx + K * Ne;
+    float* rs = reinterpret_cast<float*>(sy + K * Nm);          // [K][Ne + Nm] leave-one-out inverse roots (JK)
     const int w = blockIdx.y;
     if (window_mask && !window_mask[w]) return;
     const int n_pairs = Ne * Nm;
@@ -125,6 +196,10 @@ msc_windows_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, i
         __syncthreads();
         stage_spectra<K>(sx, sy, X, Y, w, f, F, Ne, Nm, ldx, ldy);
         __syncthreads();
+        if (JK) {
+            stage_loo_roots<K>(sx, sy, rs, Ne, Nm);
+            __syncthreads();
+        }
         const int64_t obase = ((int64_t)w * F + f) * n_pairs;
         auto emit = [&](int p, const float2 (&x)[K], const float2 (&y)[K]) {
             const PairStats s = pair_stats<K, JK>(x, y, t_crit);
@@ -147,6 +222,24 @@ msc_windows_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, i
 #pragma unroll
                 for (int k = 0; k < K; ++k) x[k] = sx[k * Ne + i];
                 emit(i * Nm + j, x, y);
+            }
+        } else if (JK) {
+            for (int p = threadIdx.x; p < n_pairs; p += kMscThreads) {
+                const int i = p / Nm, j = p - i * Nm;
+                float2 x[K], y[K];
+                float rx[K], ry[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    x[k] = sx[k * Ne + i];
+                    y[k] = sy[k * Nm + j];
+                    rx[k] = rs[k * (Ne + Nm) + i];
+                    ry[k] = rs[k * (Ne + Nm) + Ne + j];
+                }
+                const PairStats st = pair_stats_jk<K>(x, y, rx, ry, t_crit);
+                coh[obase + p] = st.coh;
+                ci_lo[obase + p] = st.lo;
+                ci_hi[obase + p] = st.hi;
+                if (significant) significant[obase + p] = st.coh > it_threshold ? 1 : 0;
             }
         } else {
             for (int p = threadIdx.x; p < n_pairs; p += kMscThreads) {
@@ -174,6 +267,7 @@ msc_windows_maxemg_kernel(const float2* __restrict__ X, const float2* __restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sx = reinterpret_cast<float2*>(smem_raw);
     float2* sy = sx + K * Ne;
+    float* rs = reinterpret_cast<float*>(sy + K * Nm);          // [K][Ne + Nm] leave-one-out inverse roots (JK)
     const int w = blockIdx.y;
     if (window_mask && !window_mask[w]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -182,17 +276,31 @@ msc_windows_maxemg_kernel(const float2* __restrict__ X, const float2* __restrict
         __syncthreads();
         stage_spectra<K>(sx, sy, X, Y, w, f, F, Ne, Nm, ldx, ldy);
         __syncthreads();
+        if (JK) {
+            stage_loo_roots<K>(sx, sy, rs, Ne, Nm);
+            __syncthreads();
+        }
         for (int i = warp; i < Ne; i += kMscThreads / 32) {
             float2 x[K];
+            float rx[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) x[k] = sx[k * Ne + i];
+            for (int k = 0; k < K; ++k) {
+                x[k] = sx[k * Ne + i];
+                rx[k] = JK ? rs[k * (Ne + Nm) + i] : 0.f;
+            }
             float best = -1.f, blo = 0.f, bhi = 0.f;
             int bj = 0x7fffffff;
             for (int j = lane; j < Nm; j += 32) {
                 float2 y[K];
+                float ry[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) y[k] = sy[k * Nm + j];
-                const PairStats s = pair_stats<K, JK>(x, y, t_crit);
+                for (int k = 0; k < K; ++k) {
+                    y[k] = sy[k * Nm + j];
+                    ry[k] = JK ? rs[k * (Ne + Nm) + Ne + j] : 0.f;
+                }
+                PairStats s;
+                if (JK) s = pair_stats_jk<K>(x, y, rx, ry, t_crit);
+                else s = pair_stats<K, false>(x, y, t_crit);
                 float val = s.coh;
                 if (zero_nonsig && !(s.coh > it_threshold)) val = 0.f;
                 if (val > best) { best = val; blo = s.lo; bhi = s.hi; bj = j; }
@@ -220,7 +328,7 @@ static int launch_msc(bool maxemg, const float2* X, const float2* Y, int W, int 
                       int64_t ldx, int64_t ldy, const uint8_t* mask, int jk, float t_crit, float it,
                       int zero_nonsig, float* o0, float* o1, float* o2, void* o3, cudaStream_t st) {
     dim3 grid((F + kFreqPerBlock - 1) / kFreqPerBlock, W);
-    const size_t smem = sizeof(float2) * K * (Ne + Nm);
+    const size_t smem = (sizeof(float2) + sizeof(float)) * K * (Ne + Nm);      // spectra + leave-one-out roots
     if (!maxemg) {
         if (jk)
             msc_windows_kernel<K, true><<<grid, kMscThreads, smem, st>>>(
@@ -248,7 +356,7 @@ static int dispatch_msc(bool maxemg, const float* X, const float* Y, int W, int 
                 "cmc_msc_windows: bad shape W=%d F=%d Ne=%d Nm=%d", W, F, Ne, Nm);
     CMC_REQUIRE(!jk || (o1 && o2), "cmc_msc_windows: jackknife needs ci_lo and ci_hi");
     CMC_REQUIRE(!jk || K >= 2, "cmc_msc_windows: jackknife needs K >= 2 tapers");
-    CMC_REQUIRE((size_t)K * (Ne + Nm) * sizeof(float2) <= 48 * 1024,
+    CMC_REQUIRE((size_t)K * (Ne + Nm) * (sizeof(float2) + sizeof(float)) <= 48 * 1024,
                 "cmc_msc_windows: K * (Ne + Nm) too large for the staging buffer");
     CMC_REQUIRE(W <= 65535, "cmc_msc_windows: more than 65535 windows per call");
     if (W == 0) return CMC_OK;
