@@ -394,6 +394,7 @@ def main_gpu(args):
     sB.wait_stream(cur)
     with torch.cuda.stream(sA):
         t_begin.record()
+    host_t0 = time.perf_counter()
     for i in range(steps):
         gA, gB, res = graphs[i % N_ROTATE]
         with torch.cuda.stream(sA):
@@ -409,6 +410,7 @@ def main_gpu(args):
                 b_start[i].record()
             gB.replay()
             b_done[i].record()
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / steps      # must stay below ms_per_step
     with torch.cuda.stream(sB):
         t_end.record()                                  # stream B finishes last (its last graph waits for stream A)
     cur.wait_stream(sA)
@@ -642,6 +644,7 @@ def main_gpu(args):
                                         f"{serial_ms_per_step:.4f} ms); inside the two-stream timed region the spans "
                                         f"overlap (K1 {k1_ms_pipe:.4f} ms, K2 {k2_ms_pipe:.4f} ms incl. waiting for SMs)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "stages": stages,
+            "host_enqueue_ms_per_step": host_enqueue_ms,
         }
         print(json.dumps(line))
     if world > 1:
