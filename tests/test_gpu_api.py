@@ -275,3 +275,20 @@ def test_welch_coherence_sweep_matches_item_by_item(cuda_device):
         for g, r in zip(got, ref):
             np.testing.assert_array_equal(g, r)
     assert list(sf.welch_coherence_sweep([], fs)) == []
+
+
+def test_sharded_nulls_and_cbpa_identical_on_two_gpus(cuda_device):
+    """torchrun with 2 ranks (NCCL): frequency-sharded and surrogate-sharded nulls and the index-sharded CBPA
+    return exactly the single-GPU results (scripts/check_multi_gpu.py).  Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "scripts", "check_multi_gpu.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "identical to one GPU: True" in r.stdout
