@@ -105,23 +105,40 @@ template <> struct Plan<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8;  
 template <> struct Plan<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; };
 
 
+// Read-only table of float2 entries: global memory through the read-only path, or a copy a persistent kernel staged
+// in shared memory (`s` = shared-window byte address of entry 0; loads then cost a shared-memory round trip instead
+// of an L1 / L2 one).
+template <bool SMEM>
+struct Tab {
+    const float2* g;
+    uint32_t s;
+    __device__ __forceinline__ float2 operator()(int i) const {
+        if (SMEM) {
+            float2 v;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(s + 8u * (uint32_t)i));
+            return v;
+        }
+        return __ldg(g + i);
+    }
+};
+
 // the same twiddles applied to two channels held by one thread (table loads and powers shared)
-template <int R>
-__device__ __forceinline__ void apply_twiddles2(float2 (&v)[R], float2 (&u)[R], const float2* __restrict__ tw, int base) {
+template <int R, class TW>
+__device__ __forceinline__ void apply_twiddles2(float2 (&v)[R], float2 (&u)[R], const TW& tw, int base) {
     float2 w[R];
-    w[1] = __ldg(tw + base);
+    w[1] = tw(base);
     if (R >= 4) {
-        w[2] = __ldg(tw + 2 * base);
+        w[2] = tw(2 * base);
         w[3] = cmul(w[1], w[2]);
     }
     if (R >= 8) {
-        w[4] = __ldg(tw + 4 * base);
+        w[4] = tw(4 * base);
         w[5] = cmul(w[4], w[1]);
         w[6] = cmul(w[4], w[2]);
         w[7] = cmul(w[4], w[3]);
     }
     if (R >= 16) {
-        w[8] = __ldg(tw + 8 * base);
+        w[8] = tw(8 * base);
 #pragma unroll
         for (int r = 1; r < 8; ++r) w[8 + r] = cmul(w[8], w[r]);
     }

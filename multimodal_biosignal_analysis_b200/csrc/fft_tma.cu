@@ -57,8 +57,8 @@ __device__ __forceinline__ uint32_t pt_off(int p, int cp) {
 
 // Row swizzle p -> p ^ ((p >> 4) & 1) commutes with adding multiples of 32 rows, so it is applied once per
 // butterfly (all strides used after the first pass are multiples of 32 rows for M >= 512).
-template <int M, int R, int NS>
-__device__ __forceinline__ void pass_pair(uint32_t sbuf, const float2* __restrict__ twM, int tid, int bar_id) {
+template <int M, int R, int NS, class TW>
+__device__ __forceinline__ void pass_pair(uint32_t sbuf, const TW& twM, int tid, int bar_id) {
     constexpr int NT = M / 4;
     constexpr int B = kPtsPerThread / R;
     constexpr int STRIDE = M / R;
@@ -115,17 +115,23 @@ struct NoPoll {
     __device__ __forceinline__ void operator()() const {}
 };
 
-template <int M, bool SWZ, class Poll>
+// TAB: the window rows, twM and the requested entries of twN have been staged in shared memory at `tab_s`
+// (layout: twM [M], twN [F], windows [n_win][N] floats); otherwise they are read from global memory.
+template <int M, bool SWZ, class Poll, bool TAB = false>
 __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, float* part, float* mean_s, int tid, int bar_id, int kw,
                                              int seg, int c0, int n_ch, const float* __restrict__ windows, int n_win,
                                              int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
-                                             const float2* __restrict__ twM, const float2* __restrict__ twN) {
+                                             const float2* __restrict__ twM_g, const float2* __restrict__ twN_g,
+                                             uint32_t tab_s = 0) {
+    const Tab<TAB> twM{twM_g, tab_s};
+    const Tab<TAB> twN{twN_g, tab_s + 8u * (uint32_t)(M - bin_lo)};                       // indexed by the bin number
+    const Tab<TAB> win2{reinterpret_cast<const float2*>(windows + (int64_t)kw * (2 * M)),
+                        tab_s + 8u * (uint32_t)(M + F) + 4u * (uint32_t)(kw * 2 * M)};    // pairs (w[2p], w[2p+1])
     constexpr int N = 2 * M;
     constexpr int NT = M / 4;
     constexpr int R0 = Plan<M>::R0, R1 = Plan<M>::R1, R2 = Plan<M>::R2;
     constexpr int B0 = kPtsPerThread / R0;
     constexpr int S0 = M / R0;
-    const float* win = windows + (int64_t)kw * N;
     K1_TICK_INIT;
     float2 va[B0][R0], vb[B0][R0];
 #pragma unroll
@@ -196,7 +202,7 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
         const int cp = q & 3, j = q >> 2;
 #pragma unroll
         for (int r = 0; r < R0; ++r) {
-            const float2 w = __ldg(reinterpret_cast<const float2*>(win + 2 * (j + r * S0)));
+            const float2 w = win2(j + r * S0);
             va[b][r] = make_float2((va[b][r].x - mua) * w.x, (va[b][r].y - mua) * w.y);
             vb[b][r] = make_float2((vb[b][r].x - mub) * w.x, (vb[b][r].y - mub) * w.y);
         }
@@ -223,7 +229,7 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
         const int b = bin_lo + bi;
         const float4 A = lds128(sbuf + pt_off(b & (M - 1), cp));
         const float4 Bz = lds128(sbuf + pt_off((M - b) & (M - 1), cp));
-        const float2 w = __ldg(twN + b);
+        const float2 w = twN(b);
         float2 X[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -338,7 +344,7 @@ __device__ __forceinline__ void worker_leave(TileCounter* ctr, int tid) {
     }
 }
 
-template <int M>
+template <int M, bool TAB>
 __global__ void __launch_bounds__(M / 2, 1)
 fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch, int n_seg,
                              const int64_t* __restrict__ seg_starts, const float* __restrict__ windows, int n_win,
@@ -352,6 +358,16 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
     float* part_all = reinterpret_cast<float*>(base + 3 * kTileBytes);          // [2][NT / 32][8]
     float* mean_all = part_all + 2 * (NT / 32) * kTmaCT;                        // [2][8]
     PipeCtrl* ctl = reinterpret_cast<PipeCtrl*>(mean_all + 2 * kTmaCT);
+    // TAB: twM [M], the requested twN entries [F] and the window rows [n_win][N] live in shared memory for the whole
+    // launch (the CTA is persistent), so the per-tile table loads are shared-memory round trips
+    float2* tab = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(ctl) + ((sizeof(PipeCtrl) + 15) & ~size_t(15)));
+    const uint32_t tab_s = TAB ? smem_u32(tab) : 0u;
+    if (TAB) {
+        for (int i = threadIdx.x; i < M; i += blockDim.x) tab[i] = __ldg(twM + i);
+        for (int i = threadIdx.x; i < F; i += blockDim.x) tab[M + i] = __ldg(twN + bin_lo + i);
+        float* wtab = reinterpret_cast<float*>(tab + M + F);
+        for (int i = threadIdx.x; i < n_win * N; i += blockDim.x) wtab[i] = __ldg(windows + i);
+    }
     const int worker = threadIdx.x / NT;
     const int tid = threadIdx.x - worker * NT;
     const int bar_id = 1 + worker;
@@ -425,8 +441,9 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
                 }
             };
             poll();
-            process_tile<M, false>(poll, smem_u32(base + cur * kTileBytes), part, mean_s, tid, bar_id, kw, seg, c0, n_ch,
-                                   windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN);
+            process_tile<M, false, decltype(poll), TAB>(poll, smem_u32(base + cur * kTileBytes), part, mean_s, tid, bar_id,
+                                                        kw, seg, c0, n_ch, windows, n_win, detrend, bin_lo, F, spec,
+                                                        spec_ld, twM, twN, tab_s);
         }
         // process_tile ended with a worker barrier: the buffer is no longer read and ctl->next_* is visible
         t = ctl->next_tile[worker];
@@ -483,8 +500,13 @@ static int launch_tma_pipe(const CUtensorMap& tmap, int n_ch, const int64_t* seg
                            int n_win, int detrend, int bin_lo, int F, float2* spec, int64_t spec_ld, const float2* twM,
                            const float2* twN, cudaStream_t st) {
     constexpr int NT = M / 4;
-    const size_t smem = 1024 + 3 * (size_t)M * 64 + sizeof(float) * 2 * ((NT / 32) * kTmaCT + kTmaCT) + sizeof(PipeCtrl) + 16;
-    auto kern = fft_segments_tma_pipe_kernel<M>;
+    const size_t smem_base = 1024 + 3 * (size_t)M * 64 + sizeof(float) * 2 * ((NT / 32) * kTmaCT + kTmaCT) +
+                             sizeof(PipeCtrl) + 32;
+    // twiddles, requested split twiddles and window rows next to the tile buffers when they fit
+    const size_t tab_bytes = ((size_t)M + F) * 8 + (size_t)n_win * 2 * M * 4;
+    const bool tab = smem_base + tab_bytes <= 227 * 1024;
+    const size_t smem = smem_base + (tab ? tab_bytes : 0);
+    auto kern = tab ? fft_segments_tma_pipe_kernel<M, true> : fft_segments_tma_pipe_kernel<M, false>;
     int rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
     if (rc) return rc;
     int dev = 0, sms = 148;
