@@ -192,8 +192,9 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
             mub = mean_s[2 * (tid & 3) + 1];
         }
     }
-    // every thread has its raw samples in registers: the tile may now be overwritten in place
-    group_sync(bar_id, NT);
+    // every thread has its raw samples in registers: the tile may now be overwritten in place (the barrier of the mean
+    // reduction already says so when it ran)
+    if (!(detrend == CMC_DETREND_CONSTANT && kw == 0)) group_sync(bar_id, NT);
     K1_TICK(1);
     poll();
 #pragma unroll
