@@ -1,0 +1,165 @@
+"""Seeded random-shape sweeps through the C ABI against the oracle: channel counts, segment counts, FFT lengths,
+bin ranges, taper counts and map sizes that the hand-picked cases do not hit (odd / prime sizes, single elements,
+tile boundaries +- 1)."""
+import numpy as np
+import pytest
+import torch
+from scipy import signal
+from scipy.stats import t as t_dist
+
+from oracle import cbpa as ocb
+from oracle import coherence as oc
+from multimodal_biosignal_analysis_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_welch_pooled_coherence(cuda_device, seed):
+    """K1 (every kernel variant: TMA pipelined / TMA / LDG / direct DFT) + K2 (direct or packed path) on random shapes."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.choice([128, 256, 512, 1024, 2048, 4096, 200, 384]))
+    ne, nm = int(rng.integers(1, 71)), int(rng.integers(1, 71))
+    n_seg = int(rng.integers(1, 40))
+    hop = int(rng.integers(max(N // 4, 1), N + 1))
+    n = N + hop * (n_seg - 1) + int(rng.integers(0, 7))
+    lo = int(rng.integers(0, N // 4))
+    hi = int(rng.integers(lo, min(lo + 60, N // 2) + 1))
+    detrend = int(rng.integers(0, 2))
+    t = np.arange(n)
+    common = np.sin(2 * np.pi * (lo + 1.5) / N * t)
+    eeg = (rng.standard_normal((n, ne)) + 0.7 * common[:, None] + 3.0).astype(np.float32)
+    emg = (rng.standard_normal((n, nm)) + 0.7 * np.roll(common, 3)[:, None] - 1.0).astype(np.float32)
+    starts = (np.arange(n_seg) * hop).astype(np.int64)
+    win = signal.get_window("hann", N)
+    X = K.fft_segments(_dev(eeg), _dev(starts), _dev(win.astype(np.float32)[None]), detrend, lo, hi)[:, 0]
+    Y = K.fft_segments(_dev(emg), _dev(starts), _dev(win.astype(np.float32)[None]), detrend, lo, hi)[:, 0]
+    Xo = oc.segment_spectra(eeg.astype(np.float64), starts, win[None], detrend, lo, hi)[:, 0]
+    Yo = oc.segment_spectra(emg.astype(np.float64), starts, win[None], detrend, lo, hi)[:, 0]
+    scale = np.sqrt(np.mean(np.abs(Xo) ** 2)) + 1e-30
+    assert np.max(np.abs(X.cpu().numpy() - Xo)) / scale < 2e-5
+    res = K.csd_msc(X, Y)
+    coh, sxx, syy, _ = oc.msc_from_spectra(Xo, Yo)
+    ok = (sxx[:, :, None] > 1e-9 * sxx.max()) & (syy[:, None, :] > 1e-9 * syy.max())     # away from 0 / 0 bins
+    assert np.max(np.abs(res.coh.cpu().numpy() - coh)[ok]) < 1e-4
+    np.testing.assert_allclose(res.sxx.cpu().numpy(), sxx, rtol=3e-5, atol=1e-9 * sxx.max())
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_window_jackknife(cuda_device, seed):
+    """K1 with several taper rows + K2w (jackknife CI, mask) and the fused EMG-argmax on random shapes."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(2000 + seed)
+    N = int(rng.choice([128, 256, 512]))
+    Kt = int(rng.integers(2, 8))
+    ne, nm = int(rng.integers(1, 20)), int(rng.integers(1, 40))
+    W = int(rng.integers(1, 9))
+    n = N * (W + 1) // 2 + N
+    eeg = rng.standard_normal((n, ne)).astype(np.float32)
+    emg = (rng.standard_normal((n, nm)) + 0.5 * eeg[:, :1]).astype(np.float32)
+    starts = (np.arange(W) * (N // 2)).astype(np.int64)
+    tapers = signal.windows.dpss(N, 3.5, Kt)
+    lo, hi = 1, int(rng.integers(2, N // 4))
+    X = K.fft_segments(_dev(eeg), _dev(starts), _dev(tapers.astype(np.float32)), 0, lo, hi)
+    Y = K.fft_segments(_dev(emg), _dev(starts), _dev(tapers.astype(np.float32)), 0, lo, hi)
+    t_crit = float(t_dist.ppf(0.975, Kt - 1))
+    coh, clo, chi, _ = K.msc_windows(X, Y, None, True, t_crit, None)
+    best, blo, bhi, arg = K.msc_windows_maxemg(X, Y, None, True, t_crit, None, return_argmax=True)
+    for w in range(W):
+        Xo = oc.segment_spectra(eeg.astype(np.float64), starts[w:w + 1], tapers, 0, lo, hi)[0]
+        Yo = oc.segment_spectra(emg.astype(np.float64), starts[w:w + 1], tapers, 0, lo, hi)[0]
+        m, l, h = oc.jackknife_from_spectra(Xo, Yo, 0.05)
+        assert np.max(np.abs(coh[w].cpu().numpy() - m)) < 1e-4
+        # the CI of replicates that sit within 1e-5 of 1 is ill-conditioned in float32 (documented in DESIGN.md)
+        tame = m < 0.999
+        assert np.max(np.abs(clo[w].cpu().numpy() - l)[tame], initial=0.0) < 2e-3
+        assert np.max(np.abs(chi[w].cpu().numpy() - h)[tame], initial=0.0) < 2e-3
+        a = arg[w].cpu().numpy().astype(np.int64)
+        picked = np.take_along_axis(coh[w].cpu().numpy(), a[..., None], axis=2)[..., 0]
+        np.testing.assert_array_equal(best[w].cpu().numpy(), picked)                # gathers its own argmax
+        np.testing.assert_array_equal(picked, coh[w].cpu().numpy().max(axis=2))
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_cbpa(cuda_device, seed):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(3000 + seed)
+    n_subj = int(rng.integers(2, 40))
+    n_times, n_ch = int(rng.integers(1, 40)), int(rng.integers(3, 30))
+    tail = int(rng.choice([-1, 0, 1]))
+    adj = ocb.combine_adjacency(n_times, ocb.delaunay_adjacency(syn.sensor_positions(64)[:n_ch]))
+    X = rng.standard_normal((n_subj, n_times, n_ch)) + rng.uniform(-0.5, 0.5)
+    X[:, : max(n_times // 3, 1), : n_ch // 2] += rng.uniform(0.5, 1.5) * (1 if tail >= 0 else -1)
+    n_perm = int(rng.integers(1, 70))
+    signs = np.where(rng.random((n_perm, n_subj)) < 0.5, -1, 1).astype(np.int8)
+    thr = float(t_dist.ppf(0.975 if tail == 0 else 0.95, n_subj - 1)) * (-1 if tail == -1 else 1)
+    with np.errstate(all="ignore"):
+        ref = ocb.permutation_cluster_1samp_test(X, signs, thr, tail, adj)
+    a = adj.tocsr()
+    a.sort_indices()
+    ip, ix = _dev(a.indptr.astype(np.int32)), _dev(a.indices.astype(np.int32))
+    Xd = _dev(X.reshape(n_subj, -1))
+    t_obs, labels, mass, n = K.cbpa_observed(Xd, thr, tail, ip, ix)
+    h0 = K.cbpa_permute(Xd, _dev(signs), 0, n_perm, thr, tail, ip, ix)
+    np.testing.assert_array_equal(t_obs.cpu().numpy(), ref["t_obs"].reshape(-1))
+    np.testing.assert_array_equal(labels.cpu().numpy(), ref["labels"])
+    np.testing.assert_array_equal(mass.cpu().numpy(), ref["mass_fixed"])
+    np.testing.assert_array_equal(h0.cpu().numpy(), ref["H0_fixed"][1:])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_surrogate_nulls(cuda_device, seed):
+    """Shift (with taper groups, four-shift tiles incl. ragged last group) and phase (resident or streamed panel)
+    surrogates on random spectra against oracle/surrogate.py, plus frequency-range splits."""
+    from oracle import surrogate as osur
+    from multimodal_biosignal_analysis_b200 import kernels as K, _lib
+    rng = np.random.default_rng(4000 + seed)
+    group = int(rng.choice([1, 1, 2, 5]))
+    n_pos = int(rng.integers(2, 40))
+    L = n_pos * group
+    if seed == 7:
+        L, group, n_pos = 270, 1, 270                                   # 2L > 512: streamed phase panel
+    F, ne, nm = int(rng.integers(1, 9)), int(rng.integers(1, 70)), int(rng.integers(1, 70))
+    ne, nm = ne + (ne & 1), nm + (nm & 1)                               # even pitch: direct K2 kernel
+    Xo = (rng.standard_normal((L, F, ne)) + 1j * rng.standard_normal((L, F, ne)))
+    Yo = (rng.standard_normal((L, F, nm)) + 1j * rng.standard_normal((L, F, nm))) + 0.4 * Xo[:, :, :1]
+    Xo, Yo = Xo.astype(np.complex64), Yo.astype(np.complex64)
+    res = K.csd_msc(_dev(Xo), _dev(Yo))
+    coh_obs = res.coh.cpu().numpy().astype(np.float64)
+    Xw, _ = osur.whiten(Xo.astype(np.complex128))
+    Yw, _ = osur.whiten(Yo.astype(np.complex128))
+    n_surr = int(rng.integers(1, 50))
+    # ---- shift ----
+    shifts = rng.integers(1, n_pos, n_surr).astype(np.int32)
+    exceed, max_stat = K.surrogate_null(res, K.SURR_SHIFT, 0, n_surr, shifts=_dev(shifts), group=group)
+    cs = osur.surrogate_coherence(Xw, Yw, "shift", np.arange(n_surr), shifts=shifts, group=group)
+    tol = 6e-4                                                          # single TF32 term, short averages
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+tol)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-tol)
+    got = exceed.cpu().numpy().astype(np.int64)
+    assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 2e-3
+    # ---- phase ----
+    buf = np.zeros((4096, 2), np.float32)
+    assert _lib.load().cmc_phase_table(buf.ctypes.data) == 0
+    table = buf[:, 0] + 1j * buf[:, 1]
+    exceed_p, max_p = K.surrogate_null(res, K.SURR_PHASE, 0, n_surr, seed=seed + 1)
+    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed + 1, table=table, quantise_z=True)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+5e-5)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-5e-5)
+    got = exceed_p.cpu().numpy().astype(np.int64)
+    assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
+    assert np.max(np.abs(max_p.cpu().numpy() - ms)) < 5e-5
+    # ---- a random split of the frequency axis reproduces both nulls exactly ----
+    cut = int(rng.integers(0, F + 1))
+    for mode, kw, full_e, full_m in ((K.SURR_SHIFT, dict(shifts=_dev(shifts), group=group), exceed, max_stat),
+                                     (K.SURR_PHASE, dict(seed=seed + 1), exceed_p, max_p)):
+        e2, m_a = K.surrogate_null(res, mode, 0, n_surr, f_range=(0, cut), **kw)
+        e2, m_b = K.surrogate_null(res, mode, 0, n_surr, f_range=(cut, F), exceed=e2, **kw)
+        np.testing.assert_array_equal(e2.cpu().numpy(), full_e.cpu().numpy())
+        np.testing.assert_array_equal(torch.maximum(m_a, m_b).cpu().numpy(), full_m.cpu().numpy())
