@@ -223,6 +223,32 @@ msc_windows_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, i
                 for (int k = 0; k < K; ++k) x[k] = sx[k * Ne + i];
                 emit(i * Nm + j, x, y);
             }
+        } else if (JK && kMscThreads % Nm == 0) {
+            // the EMG column of a thread is fixed (p advances by a multiple of Nm): its spectra and leave-one-out
+            // factors stay in registers, the EEG side is a broadcast load per row
+            const int j = threadIdx.x % Nm;
+            float2 y[K];
+            float ry[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                y[k] = sy[k * Nm + j];
+                ry[k] = rs[k * (Ne + Nm) + Ne + j];
+            }
+            for (int i = threadIdx.x / Nm; i < Ne; i += kMscThreads / Nm) {
+                float2 x[K];
+                float rx[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    x[k] = sx[k * Ne + i];
+                    rx[k] = rs[k * (Ne + Nm) + i];
+                }
+                const PairStats st = pair_stats_jk<K>(x, y, rx, ry, t_crit);
+                const int64_t o = obase + i * Nm + j;
+                coh[o] = st.coh;
+                ci_lo[o] = st.lo;
+                ci_hi[o] = st.hi;
+                if (significant) significant[o] = st.coh > it_threshold ? 1 : 0;
+            }
         } else if (JK) {
             for (int p = threadIdx.x; p < n_pairs; p += kMscThreads) {
                 const int i = p / Nm, j = p - i * Nm;
