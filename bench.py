@@ -445,6 +445,7 @@ def main_gpu(args):
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
 
     # ---- end to end through the public API: pinned host buffers in, numpy coherence out ----
+    numa_node = cdist.bind_to_gpu_numa_node(local_rank) if world > 1 else None   # node-local pinned buffers per rank
     pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in host_sets]
 
     def e2e_step(i):
@@ -478,7 +479,7 @@ def main_gpu(args):
            "h2d_bytes_per_step": int(n_samples * (NE + NM) * 4), "d2h_bytes_per_step": int(F * NE * NM * 4),
            "api": "signal_features.welch_coherence_sweep(recordings, ...): one recording per step, pinned host "
                   "tensors in, numpy coherence out; upload, K1 + K2 and download of consecutive recordings overlap",
-           "single_call_ms": single_ms,
+           "single_call_ms": single_ms, "numa_node": numa_node,
            "single_call_api": "signal_features.welch_magnitude_squared_coherence(...).coherence, one blocking call "
                               "per recording"}
 

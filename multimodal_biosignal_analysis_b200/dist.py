@@ -58,3 +58,32 @@ def all_reduce_max_(t: torch.Tensor) -> torch.Tensor:
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t
+
+
+def bind_to_gpu_numa_node(device_index: int | None = None) -> int | None:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (one process per GPU): pinned host
+    buffers allocated afterwards are node-local, so several ranks streaming recordings over PCIe do not all pull
+    from one socket's memory.  Returns the node, or None when the topology cannot be read (then nothing changes)."""
+    import os
+    try:
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:                                             # no sysfs, no such attribute, not permitted, ...
+        return None
+
