@@ -646,6 +646,9 @@ def main_gpu(args):
                                         f"overlap (K1 {k1_ms_pipe:.4f} ms, K2 {k2_ms_pipe:.4f} ms incl. waiting for SMs)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "stages": stages,
             "host_enqueue_ms_per_step": host_enqueue_ms,
+            # the other two headline metrics of BASELINE.json, copied up from `stages` for convenience
+            "surrogates_per_s": stages["surrogate_null_phase"]["value"],
+            "cbpa_permutations_per_s": stages["cbpa"]["value"],
         }
         print(json.dumps(line))
     if world > 1:
