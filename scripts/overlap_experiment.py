@@ -19,12 +19,21 @@ for e, m, sp in sets:
     K.fft_segments(m, starts, win, 1, 1, 100, out=sp, ch_offset=NE)
     K.csd_msc(sp[:, 0, :, :NE], sp[:, 0, :, NE:])
 torch.cuda.synchronize()
+FORK = os.environ.get("FORK_K1") is not None      # the two K1 launches as parallel branches of the graph
+side = torch.cuda.Stream()
 graphs = []
 for e, m, sp in sets:
     gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
     with torch.cuda.graph(gA):
-        K.fft_segments(e, starts, win, 1, 1, 100, out=sp, ch_offset=0)
-        K.fft_segments(m, starts, win, 1, 1, 100, out=sp, ch_offset=NE)
+        if FORK:
+            side.wait_stream(torch.cuda.current_stream())
+            K.fft_segments(e, starts, win, 1, 1, 100, out=sp, ch_offset=0)
+            with torch.cuda.stream(side):
+                K.fft_segments(m, starts, win, 1, 1, 100, out=sp, ch_offset=NE)
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            K.fft_segments(e, starts, win, 1, 1, 100, out=sp, ch_offset=0)
+            K.fft_segments(m, starts, win, 1, 1, 100, out=sp, ch_offset=NE)
     with torch.cuda.graph(gB):
         res = K.csd_msc(sp[:, 0, :, :NE], sp[:, 0, :, NE:])
     graphs.append((gA, gB, res))
