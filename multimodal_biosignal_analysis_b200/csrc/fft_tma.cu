@@ -223,32 +223,43 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
     K1_TICK(4);
     poll();
 
-    // ---- real-FFT split for the requested bins; 2 channels = 16 bytes per lane ----
+    // ---- real-FFT split for the requested bins.  One item = (bin, half of the channel tile): two channel pairs
+    // with independent loads and arithmetic, so that the F * 2 items of a band-limited request fit one round of
+    // the worker's threads instead of a full round plus a mostly idle one ----
     float2* out = spec + ((int64_t)(seg * n_win + kw) * F) * spec_ld + c0;
-    for (int q = tid; q < F * 4; q += NT) {
-        const int cp = q & 3, bi = q >> 2;
+    for (int q = tid; q < F * 2; q += NT) {
+        const int half = q & 1, bi = q >> 1;
         const int b = bin_lo + bi;
-        const float4 A = lds128(sbuf + pt_off(b & (M - 1), cp));
-        const float4 Bz = lds128(sbuf + pt_off((M - b) & (M - 1), cp));
         const float2 w = twN(b);
-        float2 X[2];
+        float4 A[2], Bz[2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float ax = h ? A.z : A.x, ay = h ? A.w : A.y, bx = h ? Bz.z : Bz.x, by = h ? Bz.w : Bz.y;
-            const float2 E = make_float2(0.5f * (ax + bx), 0.5f * (ay - by));
-            const float2 O = make_float2(0.5f * (ax - bx), 0.5f * (ay + by));
-            const float2 T = cmul(w, O);
-            X[h] = make_float2(E.x + T.y, E.y - T.x);
-            if (b == 0 || b == M) X[h].y = 0.f;
-            if (detrend == CMC_DETREND_POST_TAPER && b == 0) X[h].x = 0.f;
+        for (int u = 0; u < 2; ++u) {
+            A[u] = lds128(sbuf + pt_off(b & (M - 1), 2 * half + u));
+            Bz[u] = lds128(sbuf + pt_off((M - b) & (M - 1), 2 * half + u));
         }
-        float2* o = out + (int64_t)bi * spec_ld + 2 * cp;
-        const int c = c0 + 2 * cp;
-        if (c + 1 < n_ch && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-            *reinterpret_cast<float4*>(o) = make_float4(X[0].x, X[0].y, X[1].x, X[1].y);
-        } else {
-            if (c < n_ch) o[0] = X[0];
-            if (c + 1 < n_ch) o[1] = X[1];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int cp = 2 * half + u;
+            float2 X[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float ax = h ? A[u].z : A[u].x, ay = h ? A[u].w : A[u].y;
+                const float bx = h ? Bz[u].z : Bz[u].x, by = h ? Bz[u].w : Bz[u].y;
+                const float2 E = make_float2(0.5f * (ax + bx), 0.5f * (ay - by));
+                const float2 O = make_float2(0.5f * (ax - bx), 0.5f * (ay + by));
+                const float2 T = cmul(w, O);
+                X[h] = make_float2(E.x + T.y, E.y - T.x);
+                if (b == 0 || b == M) X[h].y = 0.f;
+                if (detrend == CMC_DETREND_POST_TAPER && b == 0) X[h].x = 0.f;
+            }
+            float2* o = out + (int64_t)bi * spec_ld + 2 * cp;
+            const int c = c0 + 2 * cp;
+            if (c + 1 < n_ch && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                *reinterpret_cast<float4*>(o) = make_float4(X[0].x, X[0].y, X[1].x, X[1].y);
+            } else {
+                if (c < n_ch) o[0] = X[0];
+                if (c + 1 < n_ch) o[1] = X[1];
+            }
         }
     }
     group_sync(bar_id, NT);

@@ -38,6 +38,8 @@ for e, m, sp in sets:
         res = K.csd_msc(sp[:, 0, :, :NE], sp[:, 0, :, NE:])
     graphs.append((gA, gB, res))
 sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+sA2 = torch.cuda.Stream()
+ALT = os.environ.get("ALT_K1") is not None        # K1 graphs of even / odd steps on two streams
 steps = 400
 
 def run(overlap):
@@ -49,9 +51,10 @@ def run(overlap):
         t0.record()
     for i in range(steps):
         gA, gB, _ = graphs[i % NR]
-        with torch.cuda.stream(sA):
+        sK1 = sA2 if (ALT and overlap and (i & 1)) else sA
+        with torch.cuda.stream(sK1):
             if overlap and i >= NR:
-                sA.wait_event(evB[i - NR])          # the slot's spectra are free again
+                sK1.wait_event(evB[i - NR])         # the slot's spectra are free again
             gA.replay()
             evA[i].record()
         with torch.cuda.stream(sB if overlap else sA):
