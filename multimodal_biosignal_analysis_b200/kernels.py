@@ -161,7 +161,9 @@ def _pooled_dims(X, Y):
 
 
 class PooledCsd:
-    """Result of the tensor-core CSD pass; keeps (or can rebuild) the operands of the surrogate null."""
+    """Result of the tensor-core CSD pass; keeps (or can rebuild) the operands of the surrogate null.  Until the
+    operand planes exist the object holds on to the spectra it was computed from (they are what the planes are
+    built from on the first surrogate call)."""
 
     def __init__(self, coh, sxx, syy, sxy, ws, dims, pending=None):
         self.coh, self.sxx, self.syy, self.sxy, self.ws, self.dims = coh, sxx, syy, sxy, ws, dims

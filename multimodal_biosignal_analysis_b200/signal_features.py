@@ -823,15 +823,18 @@ def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, 
         slot["d2h"].synchronize()
         return slot["out"].numpy(), freqs[lo:hi + 1]
 
-    submit(first, 0)
-    i = 0
-    for item in it:
-        i += 1
-        submit(item, i)                                           # item i is in flight while item i - 1 is handed out
-        yield collect(i - 1)
-    yield collect(i)
-    cur.wait_stream(s_comp)
-    cur.wait_stream(s_down)
+    try:
+        submit(first, 0)
+        i = 0
+        for item in it:
+            i += 1
+            submit(item, i)                                       # item i is in flight while item i - 1 is handed out
+            yield collect(i - 1)
+        yield collect(i)
+    finally:
+        # also when the consumer stops early: nothing of this sweep may still be running when its buffers are freed
+        for st in (s_up, s_comp, s_down):
+            st.synchronize()
 
 
 def local_neighbor_coherence(data, neighbor_mapping, sampling_freq: float, nperseg: int = 256) -> float:

@@ -292,3 +292,19 @@ def test_sharded_nulls_and_cbpa_identical_on_two_gpus(cuda_device):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "identical to one GPU: True" in r.stdout
+
+
+def test_welch_coherence_sweep_can_be_abandoned(cuda_device):
+    """Stopping the sweep early (generator closed with an item still in flight) drains its streams before the
+    buffers go away; a following call is unaffected."""
+    import torch
+    from multimodal_biosignal_analysis_b200 import signal_features as sf, synthetic as syn
+    recs = [syn.make_epochs(2, 2048, 6, 8, seed=80 + k) for k in range(4)]
+    ref = sf.welch_magnitude_squared_coherence(*recs[0], 512.0, nperseg=256).coherence
+    gen = sf.welch_coherence_sweep(recs, 512.0, nperseg=256)
+    first, _ = next(gen)
+    first = first.copy()
+    gen.close()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(first, ref)
+    np.testing.assert_array_equal(sf.welch_magnitude_squared_coherence(*recs[0], 512.0, nperseg=256).coherence, ref)
