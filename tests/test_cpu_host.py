@@ -316,3 +316,15 @@ def test_cbpa_contrast_front_end():
     np.testing.assert_allclose(d, np.nanmean(np.stack(cyc["Happy"]), 0) - np.nanmean(np.stack(cyc["Silence"]), 0))
     cfg.min_cycles_per_condition = 4
     assert cb.phase_contrast_from_cycles(cfg, cyc) is None
+
+
+def test_abi_header_is_plain_c():
+    """include/cmc.h is the FFI boundary: it must compile as C99 (and C++) on its own."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cmc.h")
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    if shutil.which("g++"):
+        subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-x", "c++", hdr], check=True)
