@@ -10,6 +10,8 @@ import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libcmc_b200.so")
+# developer switch for A/B runs of instrumented or alternative builds (same ABI)
+LIB_PATH = os.environ.get("CMC_B200_LIB", LIB_PATH)
 
 _lib = None
 
