@@ -216,6 +216,66 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
     group_sync(bar_id, NT);
     K1_TICK(2);
     poll();
+    // ---- band-limited request: when every requested bin lies below the stride NSL = M / RL of the last pass, that
+    // pass only has to produce output 0 of butterfly b (Z[b]) and output RL - 1 of butterfly NSL - b (Z[M - b]).
+    // Both are plain twiddled sums of RL inputs, so the pass, its barrier, its stores and the reload of the split
+    // collapse into one step: item = (bin, channel pair), Z[b] = sum_r W_M^(r b) y[b + r NSL] and
+    // Z[M - b] = sum_r conj(W_M^(r b)) y[NSL - b + r NSL] accumulated with FMAs straight into the split.
+    // (Pairing bins b and NSL - b in one item reads every row once instead of ~1.6 times but leaves one long item
+    // per thread: 50.2 us against 48.7 us for this form, config 2.) ----
+    constexpr int RL = R2 > 1 ? R2 : R1;
+    constexpr int NSL = M / RL;
+    float2* out = spec + ((int64_t)(seg * n_win + kw) * F) * spec_ld + c0;
+    if (RL > 1 && bin_lo + F <= NSL) {
+        if (R2 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(sbuf, twM, tid, bar_id);
+        K1_TICK(3);
+        poll();
+        for (int q = tid; q < F * 4; q += NT) {
+            const int cp = q & 3, bi = q >> 2;
+            const int b = bin_lo + bi;
+            const int kk = (NSL - b) & (NSL - 1);
+            const uint32_t pa = sbuf + pt_off(b, cp), pb = sbuf + pt_off(kk, cp);
+            float4 A = lds128(pa), Bz = lds128(pb);
+#pragma unroll
+            for (int r = 1; r < RL; ++r) {
+                const float2 w = twM(r * b);
+                const float4 ya = lds128(NSL % 32 == 0 ? pa + (uint32_t)(r * NSL) * 64u : sbuf + pt_off(b + r * NSL, cp));
+                const float4 yb = lds128(NSL % 32 == 0 ? pb + (uint32_t)(r * NSL) * 64u : sbuf + pt_off(kk + r * NSL, cp));
+                A.x = fmaf(-w.y, ya.y, fmaf(w.x, ya.x, A.x));
+                A.y = fmaf(w.y, ya.x, fmaf(w.x, ya.y, A.y));
+                A.z = fmaf(-w.y, ya.w, fmaf(w.x, ya.z, A.z));
+                A.w = fmaf(w.y, ya.z, fmaf(w.x, ya.w, A.w));
+                Bz.x = fmaf(w.y, yb.y, fmaf(w.x, yb.x, Bz.x));
+                Bz.y = fmaf(-w.y, yb.x, fmaf(w.x, yb.y, Bz.y));
+                Bz.z = fmaf(w.y, yb.w, fmaf(w.x, yb.z, Bz.z));
+                Bz.w = fmaf(-w.y, yb.z, fmaf(w.x, yb.w, Bz.w));
+            }
+            const float2 w = twN(b);
+            float2 X[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float ax = h ? A.z : A.x, ay = h ? A.w : A.y;
+                const float bx = h ? Bz.z : Bz.x, by = h ? Bz.w : Bz.y;
+                const float2 E = make_float2(0.5f * (ax + bx), 0.5f * (ay - by));
+                const float2 O = make_float2(0.5f * (ax - bx), 0.5f * (ay + by));
+                const float2 T = cmul(w, O);
+                X[h] = make_float2(E.x + T.y, E.y - T.x);
+                if (b == 0) X[h].y = 0.f;
+                if (detrend == CMC_DETREND_POST_TAPER && b == 0) X[h].x = 0.f;
+            }
+            float2* o = out + (int64_t)bi * spec_ld + 2 * cp;
+            const int c = c0 + 2 * cp;
+            if (c + 1 < n_ch && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                *reinterpret_cast<float4*>(o) = make_float4(X[0].x, X[0].y, X[1].x, X[1].y);
+            } else {
+                if (c < n_ch) o[0] = X[0];
+                if (c + 1 < n_ch) o[1] = X[1];
+            }
+        }
+        group_sync(bar_id, NT);
+        K1_TICK(5);
+        return;
+    }
     if (R1 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(sbuf, twM, tid, bar_id);
     K1_TICK(3);
     poll();
@@ -226,7 +286,6 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
     // ---- real-FFT split for the requested bins.  One item = (bin, half of the channel tile): two channel pairs
     // with independent loads and arithmetic, so that the F * 2 items of a band-limited request fit one round of
     // the worker's threads instead of a full round plus a mostly idle one ----
-    float2* out = spec + ((int64_t)(seg * n_win + kw) * F) * spec_ld + c0;
     for (int q = tid; q < F * 2; q += NT) {
         const int half = q & 1, bi = q >> 1;
         const int b = bin_lo + bi;
