@@ -651,8 +651,9 @@ def main_gpu(args):
             "data": "synthetic", "config": workload_config(),
             "roofline": {"bound": "hbm", "kernel": "fft_segments_tma_pipe_kernel<1024> (K1, one launch per modality)",
                          "achieved": k1_gbs, "peak": hbm, "unit": "GB/s", "frac": k1_gbs / hbm,
-                         # dram__bytes_read + dram__bytes_write of one K1 launch, ncu --set full (profiles/r01b_k1_tma.md)
-                         "traffic": 70.5e6, "peak_source": peak_src,
+                         # dram__bytes_read + dram__bytes_write of one K1 launch, ncu --set full (profiles/r01b_k1_tma.md,
+                         # addendum 8: 63.0 MB read + 4.0 MB written inside the window, the rest of the output still in L2)
+                         "traffic": 67.0e6, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": k1_ms,
                          "k2_ms_per_step": k2_ms, "k1_share_of_step": 2 * k1_ms / (2 * k1_ms + k2_ms),
                          "timing_note": "launch_ms / k2_ms_per_step: CUDA events around the same kernels replayed back "
