@@ -514,18 +514,18 @@ def main_gpu(args):
     barrier()
     surr_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
     n_distinct = len(np.unique(shifts))
-    flop = 2.0 * 128 * 64 * 2 * L * F * n_distinct                       # executed TF32 flop
+    flop = 3 * 2.0 * 128 * 64 * 2 * L * F * n_distinct                   # executed TF32 flop (three terms)
     stages["surrogate_null_shift"] = {
         "metric": "surrogates_per_s", "value": N_SURR / (surr_ms / 1e3), "unit": "surrogates/s",
         "ms": surr_ms, "scaling": "replicated",
         "config": f"config 3: {N_SURR} circular-shift surrogates of one 64x64xF=100 subject-condition; distinct shifts are "
-                  f"deduplicated on the device ({n_distinct} of L={L}), four of them share one TF32 tcgen05 tile "
+                  f"deduplicated on the device ({n_distinct} of L={L}), four of them share one 3xTF32 tcgen05 tile "
                   f"(N = 256), so the cost does not grow beyond {L - 1} CSD passes (10,000 surrogates take the same "
                   f"time); every rank runs it for its own subject-condition",
         "roofline": {"bound": "tensor", "achieved": flop / (surr_ms * 1e-3) / 1e12, "peak": bf16 / 2,
                      "unit": "TFLOP/s", "frac": flop / (surr_ms * 1e-3) / 1e12 / (bf16 / 2),
-                     "note": "executed TF32 flop of the distinct-shift passes (M=128 x N=256 tiles; bound by the "
-                             "per-output epilogue on 4 warps); TF32 peak taken as half the measured dense bf16 figure"},
+                     "note": "executed TF32 flop of the distinct-shift passes (M=128 x N=256 tiles, three error-compensated "
+                             "TF32 terms per product); TF32 peak taken as half the measured dense bf16 figure"},
     }
 
     # ---- stage: phase-randomised surrogates (config 3 count per rank-shard of config 5's 10,000) ----
@@ -548,17 +548,17 @@ def main_gpu(args):
     barrier()
     ph_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
     kpb = ((2 * L + 63) // 64) * 64
-    ph_flop = 2.0 * n_phase * (2 * NE * NM) * kpb * (fe - fb)              # executed bf16 flop on this rank
+    ph_flop = 2.0 * n_phase * (2 * NE * NM) * kpb * (fe - fb)              # executed fp16 flop on this rank
     stages["surrogate_null_phase"] = {
         "metric": "surrogates_per_s", "value": n_phase / (ph_ms / 1e3), "unit": "surrogates/s", "ms": ph_ms,
         "scaling": "strong",
         "config": f"config 5 count: {n_phase} phase-randomised surrogates of one 64x64xF=100 subject-condition "
-                  f"with the frequency axis sharded over {world} rank(s) (Philox phases + bf16 Z operands generated in "
+                  f"with the frequency axis sharded over {world} rank(s) (Philox phases + fp16 Z operands generated in "
                   f"the timed region; "
                   f"counts summed, max-stat max-reduced over ranks)",
         "roofline": {"bound": "tensor", "achieved": ph_flop / (ph_ms * 1e-3) / 1e12, "peak": bf16,
                      "unit": "TFLOP/s", "frac": ph_flop / (ph_ms * 1e-3) / 1e12 / bf16,
-                     "note": "executed bf16 flop (K padded to 64) vs measured dense bf16 peak"},
+                     "note": "executed fp16 flop (kind::f16, K padded to 64) vs the measured dense bf16 peak (same rate)"},
     }
 
     # ---- stage: the reference's production estimator - per-window multitaper MSC with jackknife CI ----

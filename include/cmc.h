@@ -48,7 +48,7 @@ extern "C" {
 
 #define CMC_SURR_SHIFT 0
 #define CMC_SURR_PHASE 1
-#define CMC_PHASE_TABLE_BITS 12  /* phase surrogates index a 4096-entry bf16 table */
+#define CMC_PHASE_TABLE_BITS 12  /* phase surrogates draw one of 4096 unit-circle phases exp(2 pi i a / 4096) */
 #define CMC_FIX_SHIFT 30         /* cluster masses: int64 sums of rint(t * 2^30) */
 #define CMC_T_CLAMP 65536.0
 
@@ -96,7 +96,8 @@ CMC_API int cmc_psd_from_spectra(const float* spec, int W, int K, int F, int n_c
  *   jackknife   0: coh = clip(|Sxy|^2 / (Sxx Syy), 0, 1)
  *               1: coh = leave-one-taper-out mean, ci_lo / ci_hi = Student-t CI in
  *                  Fisher-z space with critical value t_crit = t.ppf(1 - alpha/2, K-1)
- *   it_threshold  >= 0: significant = coh > it_threshold;  < 0: `significant` unused
+ *   it_threshold  >= 0: significant = coh > it_threshold;  < 0: `significant` unused;  NaN (degenerate
+ *                 Beta(K-2, K-2) for K <= 2 tapers): mask written as all zeros, like `coh > nan` in numpy
  *   coh, ci_lo, ci_hi [W][F][Ne][Nm] float32;  significant [W][F][Ne][Nm] uint8
  * ---------------------------------------------------------------------------------- */
 CMC_API int cmc_msc_windows(const float* X, const float* Y, int W, int K, int F, int Ne, int Nm,
@@ -162,15 +163,19 @@ CMC_API int cmc_csd_operands(const float* X, const float* Y, int L, int F, int N
  *   mode CMC_SURR_PHASE: one phase per surrogate, segment and frequency, shared by all EMG
  *        channels: table index = word (f & 3) of Philox4x32-10(key = seed, counter =
  *        (s, l, f >> 2, s >> 32)) >> 20; s runs over GLOBAL indices [s_begin, s_end) so
- *        results do not depend on how surrogates are sharded.  BF16 tensor-core GEMM with
- *        the phase panel resident in shared memory for 2 L <= 512, streamed with the B
- *        tiles for longer segment axes (2 L <= 12288).
+ *        results do not depend on how surrogates are sharded.  FP16 tensor-core GEMM (FP32
+ *        accumulation; operands prescaled into the FP16 range; error-compensated hi/lo
+ *        operand split for L <= 85 so that every surrogate coherence stays within 1e-4 of the
+ *        float64 definition) with the phase panel resident in shared memory for K <= 512,
+ *        streamed with the B tiles for longer segment axes (2 L <= 12288).
+ *   Both modes: three-term TF32 (shift) / FP16 (phase) products, FP32 accumulation in TMEM.
  *   coh_obs  [F][Ne][Nm]  observed coherence to compare against
  *   exceed   [F][Ne][Nm]  uint32, += #{s : C_s >= coh_obs}   (caller zero-initialises)
  *   max_stat [s_end - s_begin] float32 max over (f, i, j) of C_s
  *   ws2 scratch of cmc_surrogate_workspace_bytes()
  * ---------------------------------------------------------------------------------- */
-/* host copy of the phase table P[a] = (bf16(cos), bf16(sin)) of 2 pi a / 4096 as float pairs [4096][2] */
+/* host copy of the FP16-rounded phase table (fp16(cos), fp16(sin)) of 2 pi a / 4096 the phase GEMM multiplies
+ * with, as float pairs [4096][2] (diagnostics of the operand rounding; the definition uses the exact phases) */
 CMC_API int cmc_phase_table(float* out_host);
 CMC_API int64_t cmc_surrogate_workspace_bytes(int L, int F, int Ne, int Nm, int mode, int64_t n_surr);
 CMC_API int cmc_surrogate_null(void* ws, int L, int F, int Ne, int Nm, int mode, int group,

@@ -13,12 +13,13 @@ constexpr int kTileN = 64;
 // splits of the spectra; the normalisation by the auto-spectra happens in the GEMM epilogues.
 //   A_hi / A_lo [F][MT*128][KP]  rows r < 64: X of channel mt*64 + r, rows 64 + r: i * X
 //   B_hi / B_lo [F][NT*64][KP]   rows: Y
-//   B_dbl / B_odd [F][NT*64][LB] shift-surrogate views, built on demand: [Y | Y | 0..] and the same advanced by
-//                                one complex element (TMA boxes must start 16-byte aligned)
+//   B_dbl / B_odd [F][NT*64][LB] shift-surrogate views of B_hi, built on demand: [Y | Y | 0..] and the same advanced
+//                                by one complex element (TMA boxes must start 16-byte aligned);
+//   B_dbl_lo / B_odd_lo          the same views of B_lo (second and third term of the 3xTF32 shift contraction)
 struct CsdLayout {
     int L, F, Ne, Nm, MT, NT, KP, LB;
     int64_t a_elems, b_elems, bs_elems;          // floats per plane
-    int64_t off_pxx, off_pyy, off_ahi, off_alo, off_bhi, off_blo, off_bdbl, off_bodd, total;
+    int64_t off_pxx, off_pyy, off_ahi, off_alo, off_bhi, off_blo, off_bdbl, off_bodd, off_bdbl_lo, off_bodd_lo, total;
 };
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -42,6 +43,8 @@ inline CsdLayout csd_layout(int L, int F, int Ne, int Nm) {
     y.off_blo = o; o = align_up(o + y.b_elems * 4, 1024);
     y.off_bdbl = o; o = align_up(o + y.bs_elems * 4, 1024);
     y.off_bodd = o; o = align_up(o + y.bs_elems * 4, 1024);
+    y.off_bdbl_lo = o; o = align_up(o + y.bs_elems * 4, 1024);
+    y.off_bodd_lo = o; o = align_up(o + y.bs_elems * 4, 1024);
     y.total = o;
     return y;
 }

@@ -1,5 +1,13 @@
 // K3 (phase mode): phase-randomised surrogate null as ONE dense GEMM per frequency on the tensor
-// cores (tcgen05.mma kind::f16, BF16 inputs, FP32 accumulation in TMEM).
+// cores (tcgen05.mma kind::f16, FP16 inputs, FP32 accumulation in TMEM).
+//
+// Operand precision.  The definition (oracle/surrogate.py) uses exact unit-circle phases and unquantised
+// cross-products; this kernel rounds both to FP16 (11-bit significand - kind::f16 runs FP16 and BF16 at the same
+// rate, FP16 rounds 8 x finer).  Whitened cross-products obey |Z| <= 1, so a fixed 2^14 prescale keeps them in
+// the normal FP16 range down to 2^-28.  The rounding moves a surrogate coherence by <~ 3.5e-3 / L (measured
+// maximum over 2e5 samples), i.e. <= 4e-5 for L > 85.  Shorter averages (L <= kPhSplitMaxL) run the error-compensated
+// three-term split instead - operands hi + lo = 22 bits, A' = [P_hi | P_hi | P_lo], B' = [Z_hi | Z_lo | Z_hi]
+// concatenated along K (K' = 6 L <= 512 still fits the resident panel) - so every L stays inside the 1e-4 gate.
 //
 // Surrogate s rotates every EMG spectrum by one phase per (segment l, frequency f), shared by all EMG
 // channels:  S_s[i][j] = sum_l conj(Xh[l][i]) Yh[l][j] P[s][l]  (Xh, Yh whitened, P on the unit circle).
@@ -16,7 +24,7 @@
 // two 256-column TMEM accumulators overlap the epilogue with the next tile's MMAs.
 #include "csd_layout.cuh"
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <map>
 #include <mutex>
@@ -29,13 +37,16 @@ using namespace tc;
 constexpr int kPhM = 128;            // surrogates per panel
 constexpr int kPhPairs = 128;        // pairs per B tile
 constexpr int kPhN = 2 * kPhPairs;   // B tile rows (re-forms then im-forms)
-constexpr int kPhKB = 64;            // bf16 per k-block = 128 bytes
+constexpr int kPhKB = 64;            // fp16 per k-block = 128 bytes
 constexpr int kPhStages = 3;             // B ring of the resident-panel variant
 constexpr int kPhStagesStream = 4;       // (A block + B block) ring of the streamed-panel variant
 constexpr int kPhABytes = kPhM * 128;    // 16 KB: one k-block of the A panel
 constexpr int kPhBBytes = kPhN * 128;    // 32 KB: one k-block of a B tile
 constexpr int kPhThreads = 256;
 constexpr int kPhaseN = 1 << CMC_PHASE_TABLE_BITS;
+constexpr float kZScale = 16384.0f;                      // 2^14 prescale of the whitened cross-products
+constexpr float kZUnscaleSq = 1.0f / (16384.0f * 16384.0f);
+constexpr int kPhSplitMaxL = 85;                        // 6 L <= 512: the three-term operands still fit the resident panel
 
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -50,14 +61,26 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
-static uint16_t host_bf16_rne(float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
+// float -> IEEE binary16 bits, round to nearest even (|x| <= 1: no overflow handling needed beyond inf)
+static uint16_t host_f16_rne(float x) {
+    return __half_as_ushort(__float2half_rn(x));
+}
+static float host_f16_to_float(uint16_t h) {
+    return __half2float(__ushort_as_half(h));
 }
 
-// per-device table P[a] = (bf16(cos), bf16(sin)) of 2 pi a / 4096, packed as two bf16 in a uint32
+// per-device tables [2][4096]: P_hi[a] = (fp16(cos), fp16(sin)) of 2 pi a / 4096 packed as two fp16 in a uint32,
+// followed by P_lo[a] = fp16(P[a] - P_hi[a]) (second operand term of the short-L split)
+static void host_phase_entry(int a, uint32_t* hi, uint32_t* lo) {
+    const double ang = 6.283185307179586476925286766559 * a / kPhaseN;
+    const double c = cos(ang), sn = sin(ang);
+    const uint16_t ch = host_f16_rne((float)c), sh = host_f16_rne((float)sn);
+    *hi = (uint32_t)ch | ((uint32_t)sh << 16);
+    const uint16_t cl = host_f16_rne((float)(c - (double)host_f16_to_float(ch)));
+    const uint16_t sl = host_f16_rne((float)(sn - (double)host_f16_to_float(sh)));
+    *lo = (uint32_t)cl | ((uint32_t)sl << 16);
+}
+
 static int get_phase_table(const uint32_t** table) {
     static std::mutex mu;
     static std::map<int, uint32_t*> cache;
@@ -67,11 +90,8 @@ static int get_phase_table(const uint32_t** table) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(dev);
     if (it == cache.end()) {
-        std::vector<uint32_t> h(kPhaseN);
-        for (int a = 0; a < kPhaseN; ++a) {
-            const double ang = 6.283185307179586476925286766559 * a / kPhaseN;
-            h[a] = (uint32_t)host_bf16_rne((float)cos(ang)) | ((uint32_t)host_bf16_rne((float)sin(ang)) << 16);
-        }
+        std::vector<uint32_t> h(2 * kPhaseN);
+        for (int a = 0; a < kPhaseN; ++a) host_phase_entry(a, &h[a], &h[kPhaseN + a]);
         uint32_t* d = nullptr;
         rc = check_cuda(cudaMalloc(&d, h.size() * 4), "cudaMalloc(phase table)");
         if (rc) return rc;
@@ -83,10 +103,11 @@ static int get_phase_table(const uint32_t** table) {
     return CMC_OK;
 }
 
-// A operand: Phi[f][s_local][k] (bf16, K-major, row length KPb); one thread = (s, l, group of 4 frequencies)
+// A operand: Phi[f][s_local][k] (fp16, K-major, row length KPb); one thread = (s, complex column, group of 4
+// frequencies).  Complex column lp = term * L + l: terms 0 / 1 carry P_hi, term 2 carries P_lo (nterms = 1 or 3).
 __global__ void __launch_bounds__(256)
 phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_begin, int n_local, int S_pad, int L,
-                 int F, int f_lo, int KPb, __nv_bfloat16* __restrict__ A) {
+                 int nterms, int F, int f_lo, int KPb, __half* __restrict__ A) {
     // frequencies [f_lo, f_lo + F) of the GLOBAL axis land in rows [0, F) of A; f_lo need not be a multiple of 4
     const int lp = blockIdx.x * blockDim.x + threadIdx.x;      // complex column index, covers [0, KPb / 2)
     const int s = blockIdx.y;                                   // local surrogate row, covers [0, S_pad)
@@ -94,15 +115,17 @@ phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_be
     const int fg = blockIdx.z;                                  // frequency group of 4, relative to fg0
     if (lp >= KPb / 2) return;
     uint32_t vals[4] = {0u, 0u, 0u, 0u};
-    if (s < n_local && lp < L) {
+    if (s < n_local && lp < nterms * L) {
+        const int term = lp / L, l = lp - term * L;
+        const uint32_t* tab = table + (term == 2 ? kPhaseN : 0);
         const uint64_t sg = (uint64_t)(s_begin + s);
         // counter = (surrogate, segment, GLOBAL frequency group, surrogate >> 32): word q is frequency 4 fg + q
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)sg, (uint32_t)lp, (uint32_t)(fg0 + fg), (uint32_t)(sg >> 32)),
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)sg, (uint32_t)l, (uint32_t)(fg0 + fg), (uint32_t)(sg >> 32)),
                                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-        vals[0] = __ldg(table + (r.x >> (32 - CMC_PHASE_TABLE_BITS)));
-        vals[1] = __ldg(table + (r.y >> (32 - CMC_PHASE_TABLE_BITS)));
-        vals[2] = __ldg(table + (r.z >> (32 - CMC_PHASE_TABLE_BITS)));
-        vals[3] = __ldg(table + (r.w >> (32 - CMC_PHASE_TABLE_BITS)));
+        vals[0] = __ldg(tab + (r.x >> (32 - CMC_PHASE_TABLE_BITS)));
+        vals[1] = __ldg(tab + (r.y >> (32 - CMC_PHASE_TABLE_BITS)));
+        vals[2] = __ldg(tab + (r.z >> (32 - CMC_PHASE_TABLE_BITS)));
+        vals[3] = __ldg(tab + (r.w >> (32 - CMC_PHASE_TABLE_BITS)));
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -112,24 +135,22 @@ phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_be
     }
 }
 
-// B operand: Z re-/im-form rows (bf16, K-major) from the whitened 3xTF32 operands left by cmc_csd_msc.
-// grid (F, Ne); block 256: the thread block holds Xh row i in shared memory and sweeps j.
+// B operand: 2^14 Z re-/im-form rows (fp16, K-major) from the whitened 3xTF32 operands left by cmc_csd_msc.
+// grid (F, Ne); block 256: the thread block holds Xh row i in shared memory and sweeps j.  Complex column
+// lp = term * L + l: terms 0 / 2 carry Z_hi = fp16(2^14 Z), term 1 carries Z_lo = fp16(2^14 Z - Z_hi).
 __global__ void __launch_bounds__(256)
 z_gen_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo, const float* __restrict__ Bhi,
              const float* __restrict__ Blo, const float* __restrict__ pxx, const float* __restrict__ pyy, int L, int Ne,
-             int Nm, int MT, int NT, int KP, int LB, int KPb, int R_pad, __nv_bfloat16* __restrict__ Z) {
-    extern __shared__ float2 xs[];                      // [KPb / 2] complex Xh[l][i]
+             int Nm, int MT, int NT, int KP, int LB, int KPb, int R_pad, int nterms, __half* __restrict__ Z) {
+    extern __shared__ float2 xs[];                      // [L] complex Xh[l][i]
     const int f = blockIdx.x, i = blockIdx.y;
     const int half = KPb / 2;
     const float* ah = Ahi + ((int64_t)(f * MT + (i >> 6)) * kTileM + (i & 63)) * KP;
     const float* al = Alo + ((int64_t)(f * MT + (i >> 6)) * kTileM + (i & 63)) * KP;
     const float px = pxx[(int64_t)f * Ne + i];
-    const float sx = px > 0.f ? rsqrtf(px) : 0.f;                // whitening: Xh = X / sqrt(Pxx)
-    for (int l = threadIdx.x; l < half; l += blockDim.x) {
-        float2 v = make_float2(0.f, 0.f);
-        if (l < L) v = make_float2((ah[2 * l] + al[2 * l]) * sx, (ah[2 * l + 1] + al[2 * l + 1]) * sx);
-        xs[l] = v;
-    }
+    const float sx = px > 0.f ? rsqrtf(px) * kZScale : 0.f;      // whitening: Xh = X / sqrt(Pxx), times the prescale
+    for (int l = threadIdx.x; l < L; l += blockDim.x)
+        xs[l] = make_float2((ah[2 * l] + al[2 * l]) * sx, (ah[2 * l + 1] + al[2 * l + 1]) * sx);
     __syncthreads();
     for (int j = 0; j < Nm; ++j) {
         const float* bh = Bhi + ((int64_t)(f * NT + (j >> 6)) * kTileN + (j & 63)) * LB;
@@ -140,18 +161,27 @@ z_gen_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo, const
         const int64_t row_re = (int64_t)f * R_pad + (p / kPhPairs) * kPhN + (p % kPhPairs);
         uint32_t* zre = reinterpret_cast<uint32_t*>(Z + row_re * KPb);
         uint32_t* zim = reinterpret_cast<uint32_t*>(Z + (row_re + kPhPairs) * KPb);
-        for (int l = threadIdx.x; l < half; l += blockDim.x) {
-            float zr = 0.f, zi = 0.f;
-            if (l < L) {
+        for (int lp = threadIdx.x; lp < half; lp += blockDim.x) {
+            __half2 re = __floats2half2_rn(0.f, 0.f), im = re;
+            if (lp < nterms * L) {
+                const int term = lp / L, l = lp - term * L;
                 const float2 x = xs[l];
                 const float yr = (bh[2 * l] + bl[2 * l]) * sy, yi = (bh[2 * l + 1] + bl[2 * l + 1]) * sy;
-                zr = x.x * yr + x.y * yi;          // conj(x) * y
-                zi = x.x * yi - x.y * yr;
+                float zr = x.x * yr + x.y * yi;          // conj(x) * y (prescaled through sx)
+                float zi = x.x * yi - x.y * yr;
+                const __half hr = __float2half_rn(zr), hi = __float2half_rn(zi);
+                if (term == 1) {                           // second operand term: what the FP16 rounding lost
+                    zr -= __half2float(hr);
+                    zi -= __half2float(hi);
+                    re = __floats2half2_rn(zr, -zi);
+                    im = __floats2half2_rn(zi, zr);
+                } else {
+                    re = __halves2half2(hr, __hneg(hi));
+                    im = __halves2half2(hi, hr);
+                }
             }
-            const __nv_bfloat162 re = __floats2bfloat162_rn(zr, -zi);
-            const __nv_bfloat162 im = __floats2bfloat162_rn(zi, zr);
-            zre[l] = *reinterpret_cast<const uint32_t*>(&re);
-            zim[l] = *reinterpret_cast<const uint32_t*>(&im);
+            zre[lp] = *reinterpret_cast<const uint32_t*>(&re);
+            zim[lp] = *reinterpret_cast<const uint32_t*>(&im);
         }
     }
 }
@@ -248,7 +278,7 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kPhM, kPhN);
+            constexpr uint32_t idesc = make_idesc_f16(kPhM, kPhN);
             int stage = 0;
             uint32_t phase = 0, a_phase = 0, it = 0;
             for (int pn = blockIdx.x; pn < n_panels; pn += gridDim.x) {
@@ -269,7 +299,7 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                         const uint32_t b0 = smem_u32(sB + stage * kStageBytes + kBOff);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_bf16(d, make_smem_desc_k_sw128(a0 + k * 32), make_smem_desc_k_sw128(b0 + k * 32),
+                            umma_f16(d, make_smem_desc_k_sw128(a0 + k * 32), make_smem_desc_k_sw128(b0 + k * 32),
                                       idesc, (kb | k) != 0 ? 1u : 0u);
                         umma_commit(&bars->empty[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -309,7 +339,7 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const float a = __uint_as_float(re[c]), b = __uint_as_float(im[c]);
-                        const float cv = fminf(a * a + b * b, 1.0f);
+                        const float cv = fminf((a * a + b * b) * kZUnscaleSq, 1.0f);
                         const bool hit = s_ok && (cv >= cobs_s[ch * 32 + c]);
                         const uint32_t bal = __ballot_sync(0xffffffffu, hit);
                         mine = (lane == c) ? __popc(bal) : mine;
@@ -339,13 +369,14 @@ __global__ void phase_gather_kernel(const uint32_t* __restrict__ max_u, int64_t 
 }
 
 struct PhaseLayout {
-    int KPb, KB, S_pad, MT, n_pairs, n_pairs_pad, R_pad, NT, f_chunk;
+    int KPb, KB, S_pad, MT, n_pairs, n_pairs_pad, R_pad, NT, f_chunk, nterms;
     int64_t off_max, off_A, off_Z, total;
 };
 
 static PhaseLayout phase_layout(int L, int F, int Ne, int Nm, int64_t n_surr) {
     PhaseLayout y;
-    y.KPb = (int)align_up(2 * (int64_t)L, kPhKB);
+    y.nterms = L <= kPhSplitMaxL ? 3 : 1;
+    y.KPb = (int)align_up(2 * (int64_t)L * y.nterms, kPhKB);
     y.KB = y.KPb / kPhKB;
     y.S_pad = (int)align_up(n_surr > 0 ? n_surr : 1, kPhM);
     y.MT = y.S_pad / kPhM;
@@ -394,8 +425,8 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
     const unsigned char* w = static_cast<const unsigned char*>(ws);
     unsigned char* w2 = static_cast<unsigned char*>(ws2);
     uint32_t* max_u = reinterpret_cast<uint32_t*>(w2 + y.off_max);
-    __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(w2 + y.off_A);
-    __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w2 + y.off_Z);
+    __half* A = reinterpret_cast<__half*>(w2 + y.off_A);
+    __half* Z = reinterpret_cast<__half*>(w2 + y.off_Z);
     rc = check_cuda(cudaMemsetAsync(max_u, 0, (size_t)y.S_pad * 4, st), "memset(max_u)");
     if (rc) return rc;
     auto gemm = stream_a ? phase_gemm_kernel<true> : phase_gemm_kernel<false>;
@@ -412,20 +443,20 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
         }
         // Philox counters use GLOBAL frequency groups of 4; a chunk may start inside a group
         phase_gen_kernel<<<dim3((y.KPb / 2 + 255) / 256, y.S_pad, ((f0 + fc - 1) >> 2) - (f0 >> 2) + 1), 256, 0, st>>>(
-            table, seed, s_begin, (int)n, y.S_pad, L, fc, f0, y.KPb, A);
+            table, seed, s_begin, (int)n, y.S_pad, L, y.nterms, fc, f0, y.KPb, A);
         CMC_CHECK_LAUNCH("phase_gen_kernel");
-        z_gen_kernel<<<dim3(fc, Ne), 256, (size_t)y.KPb * 4, st>>>(
+        z_gen_kernel<<<dim3(fc, Ne), 256, (size_t)L * 8, st>>>(
             reinterpret_cast<const float*>(w + cy.off_ahi) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_alo) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_bhi) + (int64_t)f0 * cy.NT * kTileN * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_blo) + (int64_t)f0 * cy.NT * kTileN * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_pxx) + (int64_t)f0 * Ne,
             reinterpret_cast<const float*>(w + cy.off_pyy) + (int64_t)f0 * Nm, L, Ne, Nm, cy.MT, cy.NT, cy.KP, cy.KP,
-            y.KPb, y.R_pad, Z);
+            y.KPb, y.R_pad, y.nterms, Z);
         CMC_CHECK_LAUNCH("z_gen_kernel");
         CUtensorMap mA, mB;
-        if ((rc = make_kmajor_map(&mA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y.KPb, (int64_t)fc * y.S_pad, kPhM))) return rc;
-        if ((rc = make_kmajor_map(&mB, Z, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y.KPb, (int64_t)fc * y.R_pad, kPhN))) return rc;
+        if ((rc = make_kmajor_map(&mA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y.KPb, (int64_t)fc * y.S_pad, kPhM))) return rc;
+        if ((rc = make_kmajor_map(&mB, Z, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y.KPb, (int64_t)fc * y.R_pad, kPhN))) return rc;
         PhaseParams p{};
         p.F = fc; p.MT = y.MT; p.NT = y.NT; p.KB = y.KB; p.n_local = (int)n; p.n_pairs = y.n_pairs;
         p.S_pad = y.S_pad; p.R_pad = y.R_pad;
@@ -443,15 +474,14 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
 
 }  // namespace cmc
 
-// host copy of the phase table as float pairs (cos, sin): lets callers / tests reproduce the surrogates
+// host copy of the kernel's FP16 phase table as float pairs (cos, sin): diagnostics of the operand rounding
 extern "C" CMC_API int cmc_phase_table(float* out_host /* [4096][2] */) {
     if (!out_host) return CMC_EINVAL;
     for (int a = 0; a < cmc::kPhaseN; ++a) {
-        const double ang = 6.283185307179586476925286766559 * a / cmc::kPhaseN;
-        const uint32_t c = (uint32_t)cmc::host_bf16_rne((float)cos(ang)) << 16;
-        const uint32_t s = (uint32_t)cmc::host_bf16_rne((float)sin(ang)) << 16;
-        memcpy(out_host + 2 * a, &c, 4);
-        memcpy(out_host + 2 * a + 1, &s, 4);
+        uint32_t hi, lo;
+        cmc::host_phase_entry(a, &hi, &lo);
+        out_host[2 * a] = cmc::host_f16_to_float((uint16_t)(hi & 0xFFFFu));
+        out_host[2 * a + 1] = cmc::host_f16_to_float((uint16_t)(hi >> 16));
     }
     return CMC_OK;
 }

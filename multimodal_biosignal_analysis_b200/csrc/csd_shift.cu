@@ -1,14 +1,15 @@
-// K3 (shift mode), batched: four circular-shift surrogates per tensor-core tile.
+// K3 (shift mode), batched: four circular-shift surrogates per tensor-core tile, error-compensated 3xTF32.
 //
 // One tile = (frequency, 64 x 64 channel tile, group of four distinct shifts).  The A operand ([X; i X], 128 rows,
-// K-major, single TF32 term) is staged ONCE per k-block and contracted against four views of the doubled B rows
-// (B_dbl / B_odd of csd_layout.cuh) read at four K offsets - four TMA boxes that land as one 256-row B tile, one
-// tcgen05.mma of N = 256 per k-step: half the operand bytes per surrogate (48 KB instead of 4 x 24 KB per k-block).
-// Epilogue per shift: coherence from the 64-column slice, exceedance counts weighted by the shift's multiplicity
-// (shared-memory counters flushed once per channel tile), per-shift running maximum.  The one-shift-per-tile
-// kernel (csd_gemm_kernel<1>, 1.00 ms for config 3) turned out to be bound by that epilogue, not by the fetch:
-// batching alone gave 0.93 ms; keeping the normalisation factors and the observed coherence of the channel tile
-// in shared memory for all its shifts (instead of two rsqrt and three global loads per output) gave 0.44 ms.
+// K-major, TF32 hi and lo planes) is staged ONCE per k-block and contracted against four views of the doubled B rows
+// (B_dbl / B_odd and their lo-plane twins, csd_layout.cuh) read at four K offsets - TMA boxes that land as one
+// 256-row B tile per plane, three tcgen05.mma of N = 256 per k-step (lo*hi + hi*lo + hi*hi, small terms first): the
+// surrogate coherences carry the same ~2e-6 error as the observed pass, so exceedance counts are compared against
+// the fp64 definition inside the +-1e-4 band of the north star instead of the 4e-4 .. 2e-3 a single TF32 term gave.
+// Stage = {A_hi, A_lo, 4 x B_hi, 4 x B_lo} = 96 KB, two stages.  Epilogue per shift: coherence from the 64-column
+// slice, exceedance counts weighted by the shift's multiplicity, per-shift running maximum; the observed coherence
+// and the counters of a thread's 32 fixed (i, j) positions live in REGISTERS for all shifts of a channel tile
+// (one-shift-per-tile with global loads per output: 1.00 ms for config 3; shared-memory tables: 0.44 ms).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "csd_layout.cuh"
@@ -18,10 +19,12 @@ namespace cmc {
 using namespace tc;
 
 constexpr int kShQ = 4;                                   // shifts per tile
-constexpr int kShStages = 3;
-constexpr int kShABytes = kTileM * kKBlock * 4;           // 16 KB
-constexpr int kShBBytes = kTileN * kKBlock * 4;           // 8 KB per shift
-constexpr int kShStageBytes = kShABytes + kShQ * kShBBytes;   // 48 KB
+constexpr int kShStages = 2;
+constexpr int kShABytes = kTileM * kKBlock * 4;           // 16 KB per plane
+constexpr int kShBBytes = kTileN * kKBlock * 4;           // 8 KB per shift and plane
+constexpr int kShBOff = 2 * kShABytes;                    // B_hi views
+constexpr int kShBLoOff = kShBOff + kShQ * kShBBytes;     // B_lo views
+constexpr int kShStageBytes = 2 * kShABytes + 2 * kShQ * kShBBytes;   // 96 KB
 constexpr int kShPitch = kTileN + 1;
 constexpr int kShThreads = 256;
 
@@ -72,15 +75,15 @@ struct __align__(8) ShBarriers {
 };
 
 __global__ void __launch_bounds__(kShThreads, 1)
-csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mBdbl,
-                  const __grid_constant__ CUtensorMap mBodd, const ShiftParams p) {
+csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mAlo,
+                  const __grid_constant__ CUtensorMap mBdbl, const __grid_constant__ CUtensorMap mBodd,
+                  const __grid_constant__ CUtensorMap mBdblLo, const __grid_constant__ CUtensorMap mBoddLo,
+                  const ShiftParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    unsigned char* sS = base;                                                         // [kShStages][48 KB]
+    unsigned char* sS = base;                                                         // [kShStages][96 KB]
     float* stage_tile = reinterpret_cast<float*>(sS + kShStages * kShStageBytes);     // [128][65]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(stage_tile + kTileM * kShPitch);      // [64 * 64]
-    float* obs = reinterpret_cast<float*>(cnt + 64 * 64);                              // [64 * 64] observed coherence
-    float* scale = obs + 64 * 64;                                                      // [128] 1/sqrt(Pxx), 1/sqrt(Pyy)
+    float* scale = stage_tile + kTileM * kShPitch;                                    // [128] 1/sqrt(Pxx), 1/sqrt(Pyy)
     ShBarriers* bars = reinterpret_cast<ShBarriers*>(scale + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,8 +101,11 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
         }
         fence_barrier_init();
         tma_prefetch_desc(&mA);
+        tma_prefetch_desc(&mAlo);
         tma_prefetch_desc(&mBdbl);
         tma_prefetch_desc(&mBodd);
+        tma_prefetch_desc(&mBdblLo);
+        tma_prefetch_desc(&mBoddLo);
     }
     if (warp == 2) {
         tmem_alloc(&bars->tmem_base, 512);
@@ -111,23 +117,27 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
-        // ===================== TMA producer: lane 0 owns the barriers, lanes 0-4 issue one box each =====================
+        // ===================== TMA producer: lane 0 owns the barriers, lanes 0-9 issue one box each =====================
+        // lanes 0 / 1: A_hi / A_lo; lanes 2-5: B_hi view of shift q = lane - 2; lanes 6-9: B_lo view of shift q = lane - 6
         int stage = 0;
         uint32_t phase = 0;
         for (long long t = t0; t < t1; ++t) {
             const ShTile c = sh_decode(t, p);
             uint32_t mult[kShQ];
             if (!sh_mults(p, c.g, mult)) continue;
-            // lanes 1-4: B view of shift q = lane - 1 (a TMA box must start 16-byte aligned: offsets = 2 (mod 4) floats
-            // read the copy of the B rows that is pre-shifted by one complex element)
+            // a TMA box must start 16-byte aligned: offsets = 2 (mod 4) floats read the copy of the B rows that is
+            // pre-shifted by one complex element
             int off = 0;
             bool odd = false;
-            if (lane >= 1 && lane <= kShQ) {
-                const int sh = c.g * kShQ + lane - 1;
+            const int qb = lane >= 2 ? (lane - 2) & 3 : 0;
+            if (lane >= 2 && lane < 2 + 2 * kShQ) {
+                const int sh = c.g * kShQ + qb;
                 off = sh < p.n_pos ? p.shift_off[sh] : 0;
                 odd = (off & 2) != 0;
                 off -= odd ? 2 : 0;
             }
+            const bool lo_plane = lane >= 2 + kShQ;
+            const CUtensorMap* bmap = lo_plane ? (odd ? &mBoddLo : &mBdblLo) : (odd ? &mBodd : &mBdbl);
             const int arow = (c.f * p.MT + c.mt) * kTileM;
             const int brow = (c.f * p.NT + c.nt) * kTileN;
             for (int kb = 0; kb < p.KB; ++kb) {
@@ -137,10 +147,10 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                     mbar_arrive_expect_tx(&bars->full[stage], kShStageBytes);
                 }
                 __syncwarp();
-                if (lane == 0)
-                    tma_load_2d(st, &mA, &bars->full[stage], kb * kKBlock, arow);
-                else if (lane <= kShQ)
-                    tma_load_2d(st + kShABytes + (lane - 1) * kShBBytes, odd ? &mBodd : &mBdbl, &bars->full[stage],
+                if (lane < 2)
+                    tma_load_2d(st + lane * kShABytes, lane ? &mAlo : &mA, &bars->full[stage], kb * kKBlock, arow);
+                else if (lane < 2 + 2 * kShQ)
+                    tma_load_2d(st + (lo_plane ? kShBLoOff : kShBOff) + qb * kShBBytes, bmap, &bars->full[stage],
                                 off + kb * kKBlock, brow);
                 if (++stage == kShStages) { stage = 0; phase ^= 1; }
             }
@@ -164,9 +174,15 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t s0 = smem_u32(sS + stage * kShStageBytes);
 #pragma unroll
-                    for (int k = 0; k < kKBlock / 8; ++k)
-                        umma_tf32(d, make_smem_desc_k_sw128(s0 + k * 32), make_smem_desc_k_sw128(s0 + kShABytes + k * 32),
-                                  idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < kKBlock / 8; ++k) {
+                        const uint64_t dah = make_smem_desc_k_sw128(s0 + k * 32);
+                        const uint64_t dal = make_smem_desc_k_sw128(s0 + kShABytes + k * 32);
+                        const uint64_t dbh = make_smem_desc_k_sw128(s0 + kShBOff + k * 32);
+                        const uint64_t dbl = make_smem_desc_k_sw128(s0 + kShBLoOff + k * 32);
+                        umma_tf32(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);      // small terms first
+                        umma_tf32(d, dah, dbl, idesc, 1u);
+                        umma_tf32(d, dah, dbh, idesc, 1u);
+                    }
                     umma_commit(&bars->empty[stage]);
                     if (++stage == kShStages) { stage = 0; phase ^= 1; }
                 }
@@ -178,16 +194,21 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
         // ===================== epilogue warps =====================
         const int q4 = warp - 4;                 // TMEM lane quadrant of this warp
         const int te = threadIdx.x - 128;        // 0..127
-        for (int n = 0; n < 32; ++n) cnt[te + 128 * n] = 0;
+        // thread te owns the pairs idx = te + 128 n (il = idx >> 6, jl = idx & 63), n = 0..31, of every channel tile
+        float obs[32];
+        uint32_t cnt[32];
+#pragma unroll
+        for (int n = 0; n < 32; ++n) cnt[n] = 0;
         long long key = -1;
         int kf = 0, kmt = 0, knt = 0;
         uint32_t it = 0;
         auto flush = [&]() {
+#pragma unroll
             for (int n = 0; n < 32; ++n) {
-                const int idx = te + 128 * n, i = kmt * 64 + (idx >> 6), j = knt * 64 + (idx & 63);
-                if (cnt[idx] && i < p.Ne && j < p.Nm)
-                    atomicAdd(&p.exceed[((long long)kf * p.Ne + i) * p.Nm + j], cnt[idx]);
-                cnt[idx] = 0;
+                const int idx = te + 128 * n;
+                if (cnt[n])         // out-of-range pairs never count (their threshold is unreachable)
+                    atomicAdd(&p.exceed[((long long)kf * p.Ne + kmt * 64 + (idx >> 6)) * p.Nm + knt * 64 + (idx & 63)], cnt[n]);
+                cnt[n] = 0;
             }
         };
         for (long long t = t0; t < t1; ++t) {
@@ -200,6 +221,7 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                 key = k2; kf = c.f; kmt = c.mt; knt = c.nt;
                 // per channel tile: normalisation factors and the observed coherence, once for all its shifts
                 // (out-of-range pairs get an unreachable threshold, so they never count and never raise the maximum)
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's readers of scale[] are done
                 {
                     const bool is_x = te < 64;
                     const int ch = (is_x ? c.mt : c.nt) * 64 + (te & 63);
@@ -208,9 +230,10 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                         pw = __ldg((is_x ? p.pxx : p.pyy) + (long long)c.f * (is_x ? p.Ne : p.Nm) + ch);
                     scale[te] = pw > 0.f ? rsqrtf(pw) : 0.f;
                 }
+#pragma unroll
                 for (int n = 0; n < 32; ++n) {
                     const int idx = te + 128 * n, i = c.mt * 64 + (idx >> 6), j = c.nt * 64 + (idx & 63);
-                    obs[idx] = (i < p.Ne && j < p.Nm) ? __ldg(p.coh_obs + ((long long)c.f * p.Ne + i) * p.Nm + j) : 2.0f;
+                    obs[n] = (i < p.Ne && j < p.Nm) ? __ldg(p.coh_obs + ((long long)c.f * p.Ne + i) * p.Nm + j) : 2.0f;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -233,7 +256,8 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 float vmax = 0.f;
-#pragma unroll 4
+                const uint32_t mq = mult[q];
+#pragma unroll
                 for (int n = 0; n < 32; ++n) {
                     const int idx = te + 128 * n;
                     const int il = idx >> 6, jl = idx & 63;
@@ -241,7 +265,7 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                     const float a = stage_tile[il * kShPitch + jl] * sc;
                     const float b = stage_tile[(64 + il) * kShPitch + jl] * sc;
                     const float cval = fminf(a * a + b * b, 1.0f);
-                    if (cval >= obs[idx]) cnt[idx] += mult[q];
+                    cnt[n] += cval >= obs[n] ? mq : 0u;
                     vmax = fmaxf(vmax, cval);
                 }
                 const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
@@ -264,12 +288,15 @@ csd_shift4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
 int launch_shift4(const CsdLayout& y, unsigned char* ws, int f_begin, int f_end, int Ne, int Nm, int n_pos,
                   const int32_t* shift_off, const uint32_t* shift_mult, const float* coh_obs, uint32_t* exceed,
                   uint32_t* max_u, cudaStream_t st) {
-    CUtensorMap mA, mBdbl, mBodd;
+    CUtensorMap mA, mAlo, mBdbl, mBodd, mBdblLo, mBoddLo;
     int rc;
     const int64_t arows = (int64_t)y.F * y.MT * kTileM, brows = (int64_t)y.F * y.NT * kTileN;
     if ((rc = make_operand_map(&mA, reinterpret_cast<float*>(ws + y.off_ahi), y.KP, arows, kTileM))) return rc;
+    if ((rc = make_operand_map(&mAlo, reinterpret_cast<float*>(ws + y.off_alo), y.KP, arows, kTileM))) return rc;
     if ((rc = make_operand_map(&mBdbl, reinterpret_cast<float*>(ws + y.off_bdbl), y.LB, brows, kTileN))) return rc;
     if ((rc = make_operand_map(&mBodd, reinterpret_cast<float*>(ws + y.off_bodd), y.LB, brows, kTileN))) return rc;
+    if ((rc = make_operand_map(&mBdblLo, reinterpret_cast<float*>(ws + y.off_bdbl_lo), y.LB, brows, kTileN))) return rc;
+    if ((rc = make_operand_map(&mBoddLo, reinterpret_cast<float*>(ws + y.off_bodd_lo), y.LB, brows, kTileN))) return rc;
     ShiftParams p{};
     p.F = f_end - f_begin; p.f0 = f_begin; p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock;
     p.n_pos = n_pos; p.n_groups = (n_pos + kShQ - 1) / kShQ;
@@ -278,7 +305,7 @@ int launch_shift4(const CsdLayout& y, unsigned char* ws, int f_begin, int f_end,
     p.pyy = reinterpret_cast<const float*>(ws + y.off_pyy);
     p.coh_obs = coh_obs; p.exceed = exceed; p.max_u = max_u;
     p.total_tiles = (long long)p.F * y.MT * y.NT * p.n_groups;
-    const size_t smem = 1024 + (size_t)kShStages * kShStageBytes + sizeof(float) * kTileM * kShPitch + 2 * 64 * 64 * 4 + 128 * 4 +
+    const size_t smem = 1024 + (size_t)kShStages * kShStageBytes + sizeof(float) * kTileM * kShPitch + 128 * 4 +
                         sizeof(ShBarriers) + 16;
     rc = ensure_smem_attr(reinterpret_cast<const void*>(csd_shift4_kernel), smem);
     if (rc) return rc;
@@ -286,7 +313,7 @@ int launch_shift4(const CsdLayout& y, unsigned char* ws, int f_begin, int f_end,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long grid = p.total_tiles < sms ? p.total_tiles : sms;
-    csd_shift4_kernel<<<(unsigned)grid, kShThreads, smem, st>>>(mA, mBdbl, mBodd, p);
+    csd_shift4_kernel<<<(unsigned)grid, kShThreads, smem, st>>>(mA, mAlo, mBdbl, mBodd, mBdblLo, mBoddLo, p);
     CMC_CHECK_LAUNCH("csd_shift4_kernel");
     return CMC_OK;
 }

@@ -17,8 +17,8 @@
 // The observed pass is error-compensated 3xTF32 (hi*hi + hi*lo + lo*hi with hi = tf32(x), lo = tf32(x - hi)):
 // every pipeline stage carries the four tiles A_hi, A_lo, B_hi, B_lo of one k-block, so each operand byte is
 // fetched once; |dC| ~ 2e-6 and the pass stays HBM bound.
-// Shift surrogates read the B operand at K offset 2 * shift * group from a doubled row [Y | Y | 0...] - a TMA
-// coordinate, no data movement - and use a single TF32 term.
+// Shift surrogates (csd_shift.cu) read the B operand at K offset 2 * shift * group from a doubled row
+// [Y | Y | 0...] - a TMA coordinate, no data movement - with the same three TF32 terms.
 //
 // Pipeline per CTA (persistent over a contiguous tile range): warp 0 = TMA producer, warp 1 = MMA issuer (one
 // thread), warp 2 = TMEM allocator, warps 4-7 = epilogue.  mbarrier ring of smem stages (full/empty), 2 TMEM
@@ -31,73 +31,59 @@ namespace cmc {
 
 using namespace tc;
 
-constexpr int kMaxStages = 4;
+constexpr int kStages = 3;                      // {A_hi, A_lo, B_hi, B_lo} = 48 KB each (a 4th stage measured no gain)
 constexpr int kABytes = kTileM * kKBlock * 4;   // 16 KB
 constexpr int kBBytes = kTileN * kKBlock * 4;   // 8 KB
+constexpr int kStageBytes = 2 * (kABytes + kBBytes);
 constexpr int kStagePitch = kTileN + 1;         // padded staging row (floats)
 constexpr int kGemmThreads = 256;
 
 struct CsdParams {
-    int F, MT, NT, Ne, Nm, KB, nterms, n_shift;
-    int f0;                       // first frequency of the processed range (tiles cover [f0, f0 + F))
-    const int32_t* shift_off;     // [n_shift] K offset (floats) into the doubled B rows, or null
-    const uint32_t* shift_mult;   // [n_shift] surrogates that use this shift (0 = skip), or null
-    float* coh;                   // EPI 0 out [F][Ne][Nm]
-    float2* sxy;                  // EPI 0 optional out
-    const float* pxx;             // [F][Ne] auto-spectra (for sxy)
+    int F, MT, NT, Ne, Nm, KB;
+    float* coh;                   // out [F][Ne][Nm]
+    float2* sxy;                  // optional out
+    const float* pxx;             // [F][Ne] auto-spectra
     const float* pyy;             // [F][Nm]
-    const float* coh_obs;         // EPI 1 in
-    uint32_t* exceed;             // EPI 1 in/out [F][Ne][Nm]
-    uint32_t* max_u;              // EPI 1 out [n_shift] float bits
-    long long total_tiles;
+    long long total_tiles;        // F * MT * NT
 };
 
 struct TileCoord {
-    int f, mt, nt, sh;
+    int f, mt, nt;
 };
 __device__ __forceinline__ TileCoord decode_tile(long long t, const CsdParams& p) {
     TileCoord c;
-    c.sh = (int)(t % p.n_shift);
-    long long r = t / p.n_shift;
-    c.nt = (int)(r % p.NT);
-    r /= p.NT;
+    c.nt = (int)(t % p.NT);
+    const long long r = t / p.NT;
     c.mt = (int)(r % p.MT);
-    c.f = p.f0 + (int)(r / p.MT);
+    c.f = (int)(r / p.MT);
     return c;
 }
 
 struct __align__(8) GemmBarriers {
-    uint64_t full[kMaxStages];
-    uint64_t empty[kMaxStages];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
 };
 
-template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
-                const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-                const __grid_constant__ CUtensorMap mBodd, const CsdParams p) {
+                const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo, const CsdParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    // EPI 0 (3xTF32): 3 stages of {A_hi, A_lo, B_hi, B_lo} = 48 KB (a 4th stage measured no gain); EPI 1 (one term):
-    // 4 stages of {A_hi, B} = 24 KB
-    constexpr int kStages = EPI == 0 ? 3 : 4;
-    constexpr int kStageBytes = EPI == 0 ? 2 * (kABytes + kBBytes) : (kABytes + kBBytes);
     unsigned char* sS = base;                                   // [kStages][kStageBytes]
     float* stage_tile = reinterpret_cast<float*>(sS + kStages * kStageBytes);      // [128][65]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(stage_tile + kTileM * kStagePitch);  // [64*64] (EPI 1)
-    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(cnt + (EPI == 1 ? 64 * 64 : 0));
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(stage_tile + kTileM * kStagePitch);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t0 = p.total_tiles * blockIdx.x / gridDim.x;
     const long long t1 = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMaxStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
@@ -125,12 +111,6 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
             uint32_t phase = 0;
             for (long long t = t0; t < t1; ++t) {
                 const TileCoord c = decode_tile(t, p);
-                if (p.shift_mult && p.shift_mult[c.sh] == 0) continue;
-                // TMA needs a 16-byte aligned box start: offsets = 2 (mod 4) floats read the copy of
-                // the B rows that is pre-shifted by one complex element
-                int off = p.shift_off ? p.shift_off[c.sh] : 0;
-                const bool odd = (off & 2) != 0;
-                off -= odd ? 2 : 0;
                 const int arow = (c.f * p.MT + c.mt) * kTileM;
                 const int brow = (c.f * p.NT + c.nt) * kTileN;
                 for (int kb = 0; kb < p.KB; ++kb) {
@@ -138,13 +118,9 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
                     tma_load_2d(st, &mAhi, &bars->full[stage], kb * kKBlock, arow);
-                    if (EPI == 0) {
-                        tma_load_2d(st + kABytes, &mAlo, &bars->full[stage], kb * kKBlock, arow);
-                        tma_load_2d(st + 2 * kABytes, &mBhi, &bars->full[stage], kb * kKBlock, brow);
-                        tma_load_2d(st + 2 * kABytes + kBBytes, &mBlo, &bars->full[stage], kb * kKBlock, brow);
-                    } else {
-                        tma_load_2d(st + kABytes, odd ? &mBodd : &mBhi, &bars->full[stage], off + kb * kKBlock, brow);
-                    }
+                    tma_load_2d(st + kABytes, &mAlo, &bars->full[stage], kb * kKBlock, arow);
+                    tma_load_2d(st + 2 * kABytes, &mBhi, &bars->full[stage], kb * kKBlock, brow);
+                    tma_load_2d(st + 2 * kABytes + kBBytes, &mBlo, &bars->full[stage], kb * kKBlock, brow);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -157,8 +133,6 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
             uint32_t phase = 0;
             uint32_t it = 0;
             for (long long t = t0; t < t1; ++t) {
-                const TileCoord c = decode_tile(t, p);
-                if (p.shift_mult && p.shift_mult[c.sh] == 0) continue;
                 const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
                 mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
                 tc_fence_after();
@@ -167,21 +141,14 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
                     const uint32_t s0 = smem_u32(sS + stage * kStageBytes);
-                    if (EPI == 0) {
-                        const uint32_t ahi = s0, alo = s0 + kABytes, bhi = s0 + 2 * kABytes, blo = bhi + kBBytes;
+                    const uint32_t ahi = s0, alo = s0 + kABytes, bhi = s0 + 2 * kABytes, blo = bhi + kBBytes;
 #pragma unroll
-                        for (int k = 0; k < kKBlock / 8; ++k) {
-                            const uint64_t dah = make_smem_desc_k_sw128(ahi + k * 32), dal = make_smem_desc_k_sw128(alo + k * 32);
-                            const uint64_t dbh = make_smem_desc_k_sw128(bhi + k * 32), dbl = make_smem_desc_k_sw128(blo + k * 32);
-                            umma_tf32(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);      // small terms first
-                            umma_tf32(d, dah, dbl, idesc, 1u);
-                            umma_tf32(d, dah, dbh, idesc, 1u);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kKBlock / 8; ++k)
-                            umma_tf32(d, make_smem_desc_k_sw128(s0 + k * 32), make_smem_desc_k_sw128(s0 + kABytes + k * 32),
-                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < kKBlock / 8; ++k) {
+                        const uint64_t dah = make_smem_desc_k_sw128(ahi + k * 32), dal = make_smem_desc_k_sw128(alo + k * 32);
+                        const uint64_t dbh = make_smem_desc_k_sw128(bhi + k * 32), dbl = make_smem_desc_k_sw128(blo + k * 32);
+                        umma_tf32(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);      // small terms first
+                        umma_tf32(d, dah, dbl, idesc, 1u);
+                        umma_tf32(d, dah, dbh, idesc, 1u);
                     }
                     umma_commit(&bars->empty[stage]);      // frees the smem slot when these MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -194,29 +161,9 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
         // ===================== epilogue warps =====================
         const int q = warp - 4;                  // TMEM lane quadrant of this warp
         const int te = threadIdx.x - 128;        // 0..127
-        if (EPI == 1)
-            for (int n = 0; n < 32; ++n) cnt[te + 128 * n] = 0;
-        long long key = -1;
-        int kf = 0, kmt = 0, knt = 0;
         uint32_t it = 0;
         for (long long t = t0; t < t1; ++t) {
             const TileCoord c = decode_tile(t, p);
-            const uint32_t mult = p.shift_mult ? p.shift_mult[c.sh] : 1u;
-            if (mult == 0) continue;
-            if (EPI == 1) {
-                const long long k2 = ((long long)c.f * p.MT + c.mt) * p.NT + c.nt;
-                if (k2 != key) {
-                    if (key >= 0) {
-                        for (int n = 0; n < 32; ++n) {
-                            const int idx = te + 128 * n, i = kmt * 64 + (idx >> 6), j = knt * 64 + (idx & 63);
-                            if (cnt[idx] && i < p.Ne && j < p.Nm)
-                                atomicAdd(&p.exceed[((long long)kf * p.Ne + i) * p.Nm + j], cnt[idx]);
-                            cnt[idx] = 0;
-                        }
-                    }
-                    key = k2; kf = c.f; kmt = c.mt; knt = c.nt;
-                }
-            }
             const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
             mbar_wait(&bars->tmem_full[acc], accphase);
             tc_fence_after();
@@ -235,7 +182,6 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
                 row[32 + cidx] = __uint_as_float(r1[cidx]);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            float vmax = 0.f;
 #pragma unroll 4
             for (int n = 0; n < 32; ++n) {
                 const int idx = te + 128 * n;
@@ -248,30 +194,13 @@ csd_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant_
                     // |S|^2 / (Pxx Pyy) as |S / sqrt(Pxx) / sqrt(Pyy)|^2: no overflow, zero-power channels give 0
                     const float sc = (px > 0.f && py > 0.f) ? rsqrtf(px) * rsqrtf(py) : 0.f;
                     const float a = re * sc, b = im * sc;
-                    const float cval = fminf(a * a + b * b, 1.0f);
                     const long long o = ((long long)c.f * p.Ne + i) * p.Nm + j;
-                    if (EPI == 0) {
-                        p.coh[o] = cval;
-                        if (p.sxy) p.sxy[o] = make_float2(re, im);
-                    } else {
-                        if (cval >= __ldg(p.coh_obs + o)) cnt[idx] += mult;
-                        vmax = fmaxf(vmax, cval);
-                    }
+                    p.coh[o] = fminf(a * a + b * b, 1.0f);
+                    if (p.sxy) p.sxy[o] = make_float2(re, im);
                 }
-            }
-            if (EPI == 1) {
-                const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
-                if (lane == 0) atomicMax(&p.max_u[c.sh], m);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             ++it;
-        }
-        if (EPI == 1 && key >= 0) {
-            for (int n = 0; n < 32; ++n) {
-                const int idx = te + 128 * n, i = kmt * 64 + (idx >> 6), j = knt * 64 + (idx & 63);
-                if (cnt[idx] && i < p.Ne && j < p.Nm)
-                    atomicAdd(&p.exceed[((long long)kf * p.Ne + i) * p.Nm + j], cnt[idx]);
-            }
         }
     }
     tc_fence_before();
@@ -352,54 +281,47 @@ pack_fused_kernel(const float2* __restrict__ X, int64_t ldx, int Ne, const float
     }
 }
 
-// Shift-surrogate views of the B operand: Bdbl[k] = Bhi[k mod 2L] for k < 4L (else 0), Bodd[k] = Bdbl[k + 2].
-// One thread per complex column; grid (ceil(LB / 2 / 256), rows).
+// Shift-surrogate views of the B operand: Bdbl[k] = B[k mod 2L] for k < 4L (else 0), Bodd[k] = Bdbl[k + 2], for
+// both TF32 planes (blockIdx.z = 0: B_hi, 1: B_lo).  One thread per complex column; grid (rows, ceil(LB / 2 / 256), 2).
 __global__ void __launch_bounds__(256)
-shift_operand_kernel(const float* __restrict__ Bhi, int L, int KP, int LB, float* __restrict__ Bdbl,
-                     float* __restrict__ Bodd) {
-    const int lp = blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t row = blockIdx.y;
+shift_operand_kernel(const float* __restrict__ Bhi, const float* __restrict__ Blo, int L, int KP, int LB,
+                     float* __restrict__ Bdbl, float* __restrict__ Bodd, float* __restrict__ BdblLo,
+                     float* __restrict__ BoddLo) {
+    const int lp = blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t row = blockIdx.x;                       // rows on the x axis: F * NT * 64 may exceed 65,535
     if (lp >= LB / 2) return;
-    const float2* src = reinterpret_cast<const float2*>(Bhi + row * KP);
+    const bool lo = blockIdx.z != 0;
+    const float2* src = reinterpret_cast<const float2*>((lo ? Blo : Bhi) + row * KP);
     const float2 z = make_float2(0.f, 0.f);
     const float2 a = lp < 2 * L ? src[lp % L] : z;
     const float2 b = lp + 1 < 2 * L ? src[(lp + 1) % L] : z;
-    reinterpret_cast<float2*>(Bdbl + row * LB)[lp] = a;
-    reinterpret_cast<float2*>(Bodd + row * LB)[lp] = b;
+    reinterpret_cast<float2*>((lo ? BdblLo : Bdbl) + row * LB)[lp] = a;
+    reinterpret_cast<float2*>((lo ? BoddLo : Bodd) + row * LB)[lp] = b;
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static size_t gemm_smem_bytes(int epi) {
-    const size_t stages = epi == 0 ? 3 * 2 * (kABytes + kBBytes) : 4 * (kABytes + kBBytes);
-    return 1024 + stages + sizeof(float) * kTileM * kStagePitch + (epi == 1 ? 64 * 64 * 4 : 0) + sizeof(GemmBarriers) + 16;
+static size_t gemm_smem_bytes() {
+    return 1024 + (size_t)kStages * kStageBytes + sizeof(float) * kTileM * kStagePitch + sizeof(GemmBarriers) + 16;
 }
 
-template <int EPI>
 static int launch_gemm(const CsdLayout& y, unsigned char* ws, CsdParams p, cudaStream_t st) {
-    CUtensorMap mAhi, mAlo, mBhi, mBlo, mBodd;
+    CUtensorMap mAhi, mAlo, mBhi, mBlo;
     int rc;
     const int64_t arows = (int64_t)y.F * y.MT * kTileM, brows = (int64_t)y.F * y.NT * kTileN;
     if ((rc = make_operand_map(&mAhi, reinterpret_cast<float*>(ws + y.off_ahi), y.KP, arows, kTileM))) return rc;
     if ((rc = make_operand_map(&mAlo, reinterpret_cast<float*>(ws + y.off_alo), y.KP, arows, kTileM))) return rc;
-    if (EPI == 0) {
-        if ((rc = make_operand_map(&mBhi, reinterpret_cast<float*>(ws + y.off_bhi), y.KP, brows, kTileN))) return rc;
-        if ((rc = make_operand_map(&mBlo, reinterpret_cast<float*>(ws + y.off_blo), y.KP, brows, kTileN))) return rc;
-        mBodd = mBhi;
-    } else {
-        if ((rc = make_operand_map(&mBhi, reinterpret_cast<float*>(ws + y.off_bdbl), y.LB, brows, kTileN))) return rc;
-        if ((rc = make_operand_map(&mBodd, reinterpret_cast<float*>(ws + y.off_bodd), y.LB, brows, kTileN))) return rc;
-        mBlo = mBhi;
-    }
-    const size_t smem = gemm_smem_bytes(EPI);
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(csd_gemm_kernel<EPI>), smem);
+    if ((rc = make_operand_map(&mBhi, reinterpret_cast<float*>(ws + y.off_bhi), y.KP, brows, kTileN))) return rc;
+    if ((rc = make_operand_map(&mBlo, reinterpret_cast<float*>(ws + y.off_blo), y.KP, brows, kTileN))) return rc;
+    const size_t smem = gemm_smem_bytes();
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(csd_gemm_kernel), smem);
     if (rc) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long grid = p.total_tiles < sms ? p.total_tiles : sms;
-    csd_gemm_kernel<EPI><<<(unsigned)grid, kGemmThreads, smem, st>>>(mAhi, mAlo, mBhi, mBlo, mBodd, p);
+    csd_gemm_kernel<<<(unsigned)grid, kGemmThreads, smem, st>>>(mAhi, mAlo, mBhi, mBlo, p);
     CMC_CHECK_LAUNCH("csd_gemm_kernel");
     return CMC_OK;
 }
@@ -490,10 +412,10 @@ extern "C" int cmc_csd_msc(const float* X, const float* Y, int L, int F, int Ne,
         reinterpret_cast<float*>(w + y.off_bhi), reinterpret_cast<float*>(w + y.off_blo), pxx, pyy, sxx, syy);
     CMC_CHECK_LAUNCH("pack_fused_kernel");
     CsdParams p{};
-    p.F = F; p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock; p.nterms = 3; p.n_shift = 1;
+    p.F = F; p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock;
     p.coh = coh; p.sxy = reinterpret_cast<float2*>(sxy); p.pxx = pxx; p.pyy = pyy;
     p.total_tiles = (long long)F * y.MT * y.NT;
-    return launch_gemm<0>(y, w, p, st);
+    return launch_gemm(y, w, p, st);
 }
 
 extern "C" int64_t cmc_csd_workspace_bytes_min(int F, int Ne, int Nm) {
@@ -587,24 +509,13 @@ extern "C" int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, 
     shift_hist_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(shifts, n, n_pos, group, mult, off);
     CMC_CHECK_LAUNCH("shift_hist_kernel");
     // doubled / advanced views of the B operand (rebuilt per call: ~10 us against milliseconds of GEMM)
-    shift_operand_kernel<<<dim3((y.LB / 2 + 255) / 256, (unsigned)((int64_t)F * y.NT * kTileN)), 256, 0, st>>>(
-        reinterpret_cast<const float*>(w + y.off_bhi), L, y.KP, y.LB, reinterpret_cast<float*>(w + y.off_bdbl),
-        reinterpret_cast<float*>(w + y.off_bodd));
+    shift_operand_kernel<<<dim3((unsigned)((int64_t)F * y.NT * kTileN), (y.LB / 2 + 255) / 256, 2), 256, 0, st>>>(
+        reinterpret_cast<const float*>(w + y.off_bhi), reinterpret_cast<const float*>(w + y.off_blo), L, y.KP, y.LB,
+        reinterpret_cast<float*>(w + y.off_bdbl), reinterpret_cast<float*>(w + y.off_bodd),
+        reinterpret_cast<float*>(w + y.off_bdbl_lo), reinterpret_cast<float*>(w + y.off_bodd_lo));
     CMC_CHECK_LAUNCH("shift_operand_kernel");
-    static const bool one_per_tile = getenv("CMC_SHIFT_NO_BATCH") != nullptr;
-    if (!one_per_tile) {
-        // four shifts share one staged A tile (csd_shift.cu)
-        rc = launch_shift4(y, w, f_begin, f_end, Ne, Nm, n_pos, off, mult, coh_obs, exceed, max_u, st);
-    } else {
-        CsdParams p{};
-        p.F = f_end - f_begin; p.f0 = f_begin;
-        p.MT = y.MT; p.NT = y.NT; p.Ne = Ne; p.Nm = Nm; p.KB = y.KP / kKBlock; p.nterms = 1; p.n_shift = n_pos;
-        p.shift_off = off; p.shift_mult = mult; p.coh_obs = coh_obs; p.exceed = exceed; p.max_u = max_u;
-        p.pxx = reinterpret_cast<const float*>(w + y.off_pxx);
-        p.pyy = reinterpret_cast<const float*>(w + y.off_pyy);
-        p.total_tiles = (long long)(f_end - f_begin) * y.MT * y.NT * n_pos;
-        rc = launch_gemm<1>(y, w, p, st);
-    }
+    // four shifts share one staged A tile, three TF32 terms per product (csd_shift.cu)
+    rc = launch_shift4(y, w, f_begin, f_end, Ne, Nm, n_pos, off, mult, coh_obs, exceed, max_u, st);
     if (rc) return rc;
     shift_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shifts, n, n_pos, max_u, max_stat);
     CMC_CHECK_LAUNCH("shift_gather_kernel");

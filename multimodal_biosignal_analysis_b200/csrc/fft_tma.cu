@@ -11,7 +11,9 @@
 // Shared-memory rows are XOR-swizzled so that all butterfly strides are bank-conflict free.
 #include "fft_common.cuh"
 
-#include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "tc_common.cuh"
 #include "csd_layout.cuh"
 #include <stdlib.h>
@@ -394,15 +396,43 @@ struct PipeCtrl {
 };
 
 // Tiles beyond the first one of every worker are claimed from a device-wide counter, so workers that start late
-// (their SM was still busy with another kernel) or run slower simply take fewer tiles.  One slot per launch in
-// flight; the last worker to leave resets its slot, so a slot is reusable by the next stream-ordered launch (and by
-// CUDA-graph replays, whose kernel arguments are frozen).
+// (their SM was still busy with another kernel) or run slower simply take fewer tiles.  The last worker to leave
+// resets the counter, so it is reusable by the next STREAM-ORDERED launch (and by CUDA-graph replays, whose kernel
+// arguments are frozen).  Two launches that may overlap must never share a counter: eager launches own one slot per
+// (device, stream) - launches of one stream are ordered - and every launch recorded during stream capture gets a
+// fresh slot of its own (parallel graph branches, graphs replayed beside eager work); when a pool runs out the
+// launch uses the fixed tile stride instead (tile_counter_for).
 struct TileCounter {
     unsigned next;           // tiles claimed so far beyond the 2 * gridDim.x initial ones
     unsigned done;           // workers that have left the kernel
 };
-constexpr int kTileCounterSlots = 64;
-__device__ TileCounter g_tile_counters[kTileCounterSlots];
+constexpr int kTileCounterEagerSlots = 64;       // distinct (device, stream) pairs with a claim counter
+constexpr int kTileCounterCaptureSlots = 960;   // kernel nodes recorded into CUDA graphs
+__device__ TileCounter g_tile_counters[kTileCounterEagerSlots + kTileCounterCaptureSlots];
+
+// Host side of the rule above.  Returns nullptr (= fixed stride) when no private counter is available.
+static TileCounter* tile_counter_for(int dev, cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, int> eager;      // (device, stream) -> slot
+    static std::map<int, int> n_eager, n_capture;                  // per device
+    TileCounter* slots = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void**>(&slots), g_tile_counters) != cudaSuccess) return nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cap != cudaStreamCaptureStatusNone) {
+        int& n = n_capture[dev];
+        if (n >= kTileCounterCaptureSlots) return nullptr;
+        return slots + kTileCounterEagerSlots + n++;
+    }
+    auto it = eager.find({dev, st});
+    if (it == eager.end()) {
+        int& n = n_eager[dev];
+        if (n >= kTileCounterEagerSlots) return nullptr;
+        it = eager.emplace(std::make_pair(dev, st), n++).first;
+    }
+    return slots + it->second;
+}
 
 __device__ __forceinline__ void worker_leave(TileCounter* ctr, int tid) {
     if (tid == 0 && ctr) {
@@ -585,13 +615,9 @@ static int launch_tma_pipe(const CUtensorMap& tmap, int n_ch, const int64_t* seg
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT);
     const long long grid = (tiles + 1) / 2 < sms ? (tiles + 1) / 2 : sms;
-    // one counter slot per launch in flight (round robin; zero-initialised device memory, reset by the kernel)
-    static std::atomic<unsigned> next_slot{0};
-    TileCounter* slots = nullptr;
-    rc = check_cuda(cudaGetSymbolAddress(reinterpret_cast<void**>(&slots), g_tile_counters), "cudaGetSymbolAddress");
-    if (rc) return rc;
+    // claim counter private to this launch's stream / graph node (zero-initialised device memory, reset by the kernel)
     static const bool static_tiles = getenv("CMC_FFT_STATIC_TILES") != nullptr;      // fixed stride instead of claims
-    TileCounter* ctr = static_tiles ? nullptr : slots + next_slot.fetch_add(1) % kTileCounterSlots;
+    TileCounter* ctr = static_tiles ? nullptr : tile_counter_for(dev, st);
     kern<<<(unsigned)grid, 2 * NT, smem, st>>>(tmap, n_ch, n_seg, seg_starts, windows, n_win, detrend, bin_lo, F, spec,
                                                spec_ld, twM, twN, ctr);
     CMC_CHECK_LAUNCH("fft_segments_tma_pipe_kernel");

@@ -411,7 +411,7 @@ extern "C" int cmc_msc_windows(const float* X, const float* Y, int W, int K, int
                                float* coh, float* ci_lo, float* ci_hi, uint8_t* significant,
                                void* stream) {
     return cmc::dispatch_msc(false, X, Y, W, K, F, Ne, Nm, ldx, ldy, window_mask, jackknife, t_crit,
-                             it_threshold, 0, coh, ci_lo, ci_hi, it_threshold >= 0.f ? significant : nullptr,
+                             it_threshold, 0, coh, ci_lo, ci_hi, !(it_threshold < 0.f) ? significant : nullptr,   // NaN: all-false mask
                              stream);
 }
 

@@ -101,8 +101,8 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// same with BF16 inputs (kind::f16, K = 16 per instruction)
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// same with 16-bit inputs (kind::f16: FP16 or BF16 as the instruction descriptor says, K = 16 per instruction)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n"
@@ -176,6 +176,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// instruction descriptor: FP16 x FP16 -> FP32 (a_format = b_format = 0), both operands K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 __device__ __forceinline__ float to_tf32(float x) {

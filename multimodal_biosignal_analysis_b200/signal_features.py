@@ -727,8 +727,9 @@ def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, 
     three CUDA streams - upload of item i + 1, K1 + K2 of item i and download of item i - 1 overlap - so a sweep runs
     at the speed of the PCIe upload instead of the sum of the three.  Items must be time-first
     ``(n_samples, n_channels)`` float32; pinned host tensors (``torch.Tensor.pin_memory()``) upload asynchronously,
-    anything else is staged through a pinned buffer first (one extra host copy).  The yielded coherence array is
-    only valid until the next-but-one item is requested (two host buffers rotate); copy it to keep it."""
+    anything else is staged through a pinned buffer first (one extra host copy).  The yielded coherence array stays
+    valid while the NEXT item is fetched and is overwritten when the one after that is requested (three buffer
+    sets rotate: one uploading, one computing / downloading, one in the caller's hands); copy it to keep it longer."""
     it = iter(recordings)
     try:
         first = next(it)
@@ -759,8 +760,9 @@ def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, 
     wd = torch.from_numpy(signal.get_window(window, nperseg).astype(np.float32)[None]).to(dev)
     L = len(segment_starts)
     ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)                    # even channel pitch for K2's TMA
+    n_slots = 3
     slots = []
-    for _ in range(2):
+    for _ in range(n_slots):
         slots.append(dict(
             eeg=torch.empty((n, ne), dtype=torch.float32, device=dev),
             emg=torch.empty((n, nm), dtype=torch.float32, device=dev),
@@ -788,7 +790,7 @@ def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, 
         return buf
 
     def submit(item, i):
-        slot = slots[i % 2]
+        slot = slots[i % n_slots]
         eeg, emg = item
         if tuple(eeg.shape) != (n, ne) or tuple(emg.shape) != (n, nm):
             raise ValueError("all recordings of a sweep must have the shape of the first one")
@@ -819,7 +821,7 @@ def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, 
         slot["res"] = res
 
     def collect(i):
-        slot = slots[i % 2]
+        slot = slots[i % n_slots]
         slot["d2h"].synchronize()
         return slot["out"].numpy(), freqs[lo:hi + 1]
 

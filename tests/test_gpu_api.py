@@ -275,6 +275,13 @@ def test_welch_coherence_sweep_matches_item_by_item(cuda_device):
         for g, r in zip(got, ref):
             np.testing.assert_array_equal(g, r)
     assert list(sf.welch_coherence_sweep([], fs)) == []
+    # documented lifetime: item i stays valid while item i + 1 is fetched (no copy taken here)
+    held = None
+    for k, (coh, _) in enumerate(sf.welch_coherence_sweep(pinned, fs, nperseg=nper, freq_band=(2, 60))):
+        if held is not None:
+            torch.cuda.synchronize()                              # everything submitted so far has landed
+            np.testing.assert_array_equal(held, ref[k - 1])
+        held = coh
 
 
 def test_sharded_nulls_and_cbpa_identical_on_two_gpus(cuda_device):

@@ -1,7 +1,8 @@
-"""GPU parity: K2 (tcgen05 pooled CSD -> MSC) and K3 (shift-surrogate null) vs the fp64 oracle.
-Coherence tolerance 1e-4 absolute (north star).  Surrogate coherences come from a single TF32 term
-(|dC| ~ 4e-4 |S| / sqrt(L)), so exceedance counts must lie inside the band obtained by moving the
-oracle's comparison by +-1e-4 (counts are exact whenever no surrogate falls that close to C_obs)."""
+"""GPU parity: K2 (tcgen05 pooled CSD -> MSC) and K3 (surrogate nulls) vs the fp64 oracle.
+Coherence tolerance 1e-4 absolute (north star) - for the observed pass AND for every surrogate coherence, against
+the UNQUANTISED float64 definition of oracle/surrogate.py (shift: 3xTF32 contraction; phase: FP16 operands with
+FP32 accumulation).  Exceedance counts must lie inside the band obtained by moving the oracle's comparison by
++-SURR_TOL (counts are exact whenever no surrogate falls that close to C_obs)."""
 import numpy as np
 import pytest
 import torch
@@ -13,6 +14,7 @@ from multimodal_biosignal_analysis_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 COH_TOL = 1e-4
+SURR_TOL = 1e-4          # per-surrogate max statistic and count bands vs the unquantised fp64 definition
 
 
 def _dev(a, dtype=None):
@@ -97,14 +99,14 @@ def test_shift_surrogates_match_oracle(cuda_device):
     Yw, _ = osur.whiten(Yo)
     cs = osur.surrogate_coherence(Xw, Yw, "shift", np.arange(n_surr), shifts=shifts)
     coh_obs = res.coh.cpu().numpy().astype(np.float64)
-    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+1e-4)
-    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-1e-4)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+SURR_TOL)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-SURR_TOL)
     got = exceed.cpu().numpy().astype(np.int64)
     assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
     exact, _ = osur.null_statistics(cs, coh_obs, tol=0.0)
-    assert np.mean(got != exact) < 0.02                      # and almost always equal the exact count
-    # single TF32 term: |dC| ~ 2 |S| 4e-4 / sqrt(L); with L = 42 and C_max ~ 0.3 that is ~1.5e-4
-    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 4e-4
+    assert np.mean(got != exact) < 0.002                     # and almost always equal the exact count
+    # 3xTF32: the surrogate coherences are as accurate as the observed pass
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 2e-5
     # sharding invariance: two halves accumulate to the same counts
     e2, m_a = K.surrogate_null(res, K.SURR_SHIFT, 0, 30, shifts=_dev(shifts[:30]))
     e2, m_b = K.surrogate_null(res, K.SURR_SHIFT, 30, 60, shifts=_dev(shifts[30:]), exceed=e2)
@@ -134,11 +136,11 @@ def test_shift_surrogates_multitaper_groups(cuda_device):
     Yw, _ = osur.whiten(Yo)
     cs = osur.surrogate_coherence(Xw, Yw, "shift", np.arange(25), shifts=shifts, group=Kt)
     coh_obs = res.coh.cpu().numpy().astype(np.float64)
-    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+1e-4)
-    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-1e-4)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+SURR_TOL)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-SURR_TOL)
     got = exceed.cpu().numpy().astype(np.int64)
     assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
-    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 1e-4
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 2e-5
 
 
 def _phase_table_from_lib():
@@ -150,10 +152,10 @@ def _phase_table_from_lib():
 
 @pytest.mark.parametrize("ne,nm,n_surr,F_hi", [(20, 70, 150, 12), (64, 64, 130, 6), (3, 5, 40, 9)])
 def test_phase_surrogates_match_oracle(cuda_device, ne, nm, n_surr, F_hi):
-    """BF16 tensor-core GEMM vs the fp64 oracle.  Against the definition the kernel implements (cross-
-    products quantised to bf16, oracle/surrogate.py) counts sit inside a +-2e-5 band and the max statistic
-    agrees to 2e-5; against the unquantised fp64 sum the max statistic stays within 1e-3.  The surrogate
-    index is global, so shards reproduce the unsharded run exactly."""
+    """FP16 tensor-core GEMM vs the UNQUANTISED fp64 definition (exact unit-circle phases, float64
+    cross-products): counts sit inside the +-1e-4 band and every per-surrogate max statistic agrees to 1e-4;
+    the kernel's deviation is attributed by the FP16 emulation of the oracle (2e-6 = accumulation order).
+    The surrogate index is global, so shards reproduce the unsharded run exactly."""
     from multimodal_biosignal_analysis_b200 import kernels as K
     N, hop, ep, n_epochs = 512, 256, 2048, 6
     eeg, emg = syn.make_epochs(n_epochs, ep, ne, nm, seed=31)
@@ -162,21 +164,21 @@ def test_phase_surrogates_match_oracle(cuda_device, ne, nm, n_surr, F_hi):
     res = K.csd_msc(X, Y)
     seed = 0x1234ABCD5678
     exceed, max_stat = K.surrogate_null(res, K.SURR_PHASE, 0, n_surr, seed=seed)
-    table = _phase_table_from_lib()
-    np.testing.assert_array_equal(table, osur.phase_table())
+    np.testing.assert_array_equal(_phase_table_from_lib(), osur.kernel_phase_table())
     Xo, Yo = _oracle_spectra(eeg, emg, starts, N, 1, F_hi)
     Xw, _ = osur.whiten(Xo)
     Yw, _ = osur.whiten(Yo)
-    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed, table=table, quantise_z=True)
+    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed)      # the definition
     coh_obs = res.coh.cpu().numpy().astype(np.float64)
-    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+2e-5)
-    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-2e-5)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+SURR_TOL)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-SURR_TOL)
     got = exceed.cpu().numpy().astype(np.int64)
     assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
-    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 2e-5
-    cs_exact = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(min(n_surr, 40)), seed=seed, table=table)
-    ms_exact = cs_exact.reshape(cs_exact.shape[0], -1).max(axis=1)
-    assert np.max(np.abs(max_stat.cpu().numpy()[:len(ms_exact)] - ms_exact)) < 1e-3
+    exact, _ = osur.null_statistics(cs, coh_obs, tol=0.0)
+    assert np.mean(got != exact) < 0.005
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < SURR_TOL
+    # L = 42 <= 85 segments: the error-compensated operand split runs - far inside the gate
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 1e-5
     half = n_surr // 2
     e2, m_a = K.surrogate_null(res, K.SURR_PHASE, 0, half, seed=seed)
     e2, m_b = K.surrogate_null(res, K.SURR_PHASE, half, n_surr, seed=seed, exceed=e2)
@@ -204,7 +206,8 @@ def test_phase_surrogate_null_is_calibrated(cuda_device):
 
 def test_phase_surrogates_long_segment_axis_streams_the_panel(cuda_device):
     """L = 300 segments (2L = 600 > 512): the phase panel no longer fits in shared memory and is streamed with
-    the B tiles; same definition, same tolerances, and shards still reproduce the unsharded run."""
+    the B tiles; single-term FP16 operands (L > 85), same definition, same 1e-4 gate - the deviation is the operand
+    rounding the oracle can emulate - and shards still reproduce the unsharded run."""
     from multimodal_biosignal_analysis_b200 import kernels as K
     rng = np.random.default_rng(77)
     N, L, ne, nm, n_surr = 64, 300, 5, 70, 150
@@ -217,17 +220,18 @@ def test_phase_surrogates_long_segment_axis_streams_the_panel(cuda_device):
     res = K.csd_msc(X, Y)
     seed = 99
     exceed, max_stat = K.surrogate_null(res, K.SURR_PHASE, 0, n_surr, seed=seed)
-    table = _phase_table_from_lib()
     Xo, Yo = _oracle_spectra(eeg, emg, starts, N, 2, 10)
     Xw, _ = osur.whiten(Xo)
     Yw, _ = osur.whiten(Yo)
-    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed, table=table, quantise_z=True)
+    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed)
     coh_obs = res.coh.cpu().numpy().astype(np.float64)
-    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+2e-5)
-    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-2e-5)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+SURR_TOL)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-SURR_TOL)
     got = exceed.cpu().numpy().astype(np.int64)
     assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
-    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 2e-5
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < SURR_TOL
+    cs_emul = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(40), seed=seed, emulate_fp16=True)
+    assert np.max(np.abs(max_stat.cpu().numpy()[:40] - cs_emul.reshape(40, -1).max(axis=1))) < 5e-6
     e2, m_a = K.surrogate_null(res, K.SURR_PHASE, 0, 70, seed=seed)
     e2, m_b = K.surrogate_null(res, K.SURR_PHASE, 70, n_surr, seed=seed, exceed=e2)
     np.testing.assert_array_equal(e2.cpu().numpy(), exceed.cpu().numpy())

@@ -117,7 +117,7 @@ def test_fuzz_surrogate_nulls(cuda_device, seed):
     """Shift (with taper groups, four-shift tiles incl. ragged last group) and phase (resident or streamed panel)
     surrogates on random spectra against oracle/surrogate.py, plus frequency-range splits."""
     from oracle import surrogate as osur
-    from multimodal_biosignal_analysis_b200 import kernels as K, _lib
+    from multimodal_biosignal_analysis_b200 import kernels as K
     rng = np.random.default_rng(4000 + seed)
     group = int(rng.choice([1, 1, 2, 5]))
     n_pos = int(rng.integers(2, 40))
@@ -138,23 +138,20 @@ def test_fuzz_surrogate_nulls(cuda_device, seed):
     shifts = rng.integers(1, n_pos, n_surr).astype(np.int32)
     exceed, max_stat = K.surrogate_null(res, K.SURR_SHIFT, 0, n_surr, shifts=_dev(shifts), group=group)
     cs = osur.surrogate_coherence(Xw, Yw, "shift", np.arange(n_surr), shifts=shifts, group=group)
-    tol = 6e-4                                                          # single TF32 term, short averages
+    tol = 1e-4                                                          # north-star gate vs the fp64 definition
     lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+tol)
     hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-tol)
     got = exceed.cpu().numpy().astype(np.int64)
     assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
-    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 2e-3
-    # ---- phase ----
-    buf = np.zeros((4096, 2), np.float32)
-    assert _lib.load().cmc_phase_table(buf.ctypes.data) == 0
-    table = buf[:, 0] + 1j * buf[:, 1]
+    assert np.max(np.abs(max_stat.cpu().numpy() - ms)) < 2e-5           # 3xTF32
+    # ---- phase: unquantised definition (exact phases, float64 products) ----
     exceed_p, max_p = K.surrogate_null(res, K.SURR_PHASE, 0, n_surr, seed=seed + 1)
-    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed + 1, table=table, quantise_z=True)
-    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+5e-5)
-    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-5e-5)
+    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed + 1)
+    lo_cnt, _ = osur.null_statistics(cs, coh_obs, tol=+tol)
+    hi_cnt, ms = osur.null_statistics(cs, coh_obs, tol=-tol)
     got = exceed_p.cpu().numpy().astype(np.int64)
     assert np.all(got >= lo_cnt) and np.all(got <= hi_cnt)
-    assert np.max(np.abs(max_p.cpu().numpy() - ms)) < 5e-5
+    assert np.max(np.abs(max_p.cpu().numpy() - ms)) < (1e-5 if L <= 85 else tol)
     # ---- a random split of the frequency axis reproduces both nulls exactly ----
     cut = int(rng.integers(0, F + 1))
     for mode, kw, full_e, full_m in ((K.SURR_SHIFT, dict(shifts=_dev(shifts), group=group), exceed, max_stat),
