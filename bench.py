@@ -40,6 +40,22 @@ N_PERM_TOTAL = 10000         # config 5 permutation count (sharded over ranks)
 CBPA_SHAPE = (20, 100, 64)   # config 4
 
 
+def _k1_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed `ncu --set full` export
+    (profiled offline, NOT measured in this run; null when the file is absent)."""
+    path = os.path.join(ROOT, "profiles", "k1_dram_traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"bytes": float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]),
+                "source": f"profiled offline: profiles/k1_dram_traffic.json ({d.get('source', '')})"}
+    except Exception:
+        return {"bytes": None, "source": "no ncu export committed"}
+
+
+K1_TRAFFIC_PROFILED = _k1_traffic()
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -535,8 +551,8 @@ def main_gpu(args):
     fb, fe = cdist.shard_range(F, rank, world)
     def phase_null():
         ex_p, ms_p = K.surrogate_null(res, K.SURR_PHASE, 0, n_phase, seed=7, f_range=(fb, fe))
-        cdist.all_reduce_sum_(ex_p)                                # exceedance histogram (disjoint bins)
-        return ex_p, cdist.all_reduce_max_(ms_p)                   # per-surrogate max statistic
+        # one all-gather carries every rank's slice of the counts together with its per-surrogate maxima
+        return cdist.all_gather_frequency_slices(ex_p, ms_p, (fb, fe))
 
     for _ in range(2):                                             # warm-up includes the collectives
         phase_null()
@@ -555,7 +571,7 @@ def main_gpu(args):
         "config": f"config 5 count: {n_phase} phase-randomised surrogates of one 64x64xF=100 subject-condition "
                   f"with the frequency axis sharded over {world} rank(s) (Philox phases + fp16 Z operands generated in "
                   f"the timed region; "
-                  f"counts summed, max-stat max-reduced over ranks)",
+                  f"count slices and per-surrogate maxima exchanged with ONE all-gather)",
         "roofline": {"bound": "tensor", "achieved": ph_flop / (ph_ms * 1e-3) / 1e12, "peak": bf16,
                      "unit": "TFLOP/s", "frac": ph_flop / (ph_ms * 1e-3) / 1e12 / bf16,
                      "note": "executed fp16 flop (kind::f16, K padded to 64) vs the measured dense bf16 peak (same rate)"},
@@ -621,7 +637,9 @@ def main_gpu(args):
     fp64_ops = n_tests_c * (4 * n_subj_c - 2 + 4)
     cbpa_tops = fp64_ops * (pe - pb) / (cbpa_ms * 1e-3) / 1e12
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-    fp64_peak = n_sm * 64 * 1.965e9 / 1e12           # FP64 instructions: 64 lanes / SM / clock at the 1965 MHz boost clock
+    sm_clock_hz = torch.cuda.get_device_properties(dev).clock_rate * 1e3 if hasattr(
+        torch.cuda.get_device_properties(dev), "clock_rate") else 1.965e9
+    fp64_peak = n_sm * 64 * sm_clock_hz / 1e12       # FP64 instructions: 64 lanes / SM / clock at the device's boost clock
     stages["cbpa"] = {
         "metric": "cbpa_permutations_per_s", "value": N_PERM_TOTAL / (cbpa_ms / 1e3), "unit": "permutations/s",
         "ms": cbpa_ms, "scaling": "strong",
@@ -633,6 +651,121 @@ def main_gpu(args):
                              "in numpy) vs the FP64 issue rate of 148 SMs x 64 lanes x 1965 MHz; X (1 MB) is L2 "
                              "resident, DRAM traffic is negligible"},
     }
+
+    # ---- stage: BASELINE config 5 as one pipeline through the public API (numpy / pinned host in, numpy out) ----
+    # 20 subjects x 4 conditions = 80 subject-conditions dealt round-robin over the ranks (no collective while they
+    # run); per unit upload -> K1 x 2 -> K2 -> operand planes -> 10,000-surrogate phase null -> download of coherence,
+    # counts and maxima, uploads / downloads of neighbouring units overlapped; then one all-reduce of the (F, Ne)
+    # EMG-max maps and the 10,000-permutation CBPA of the condition contrast (permutations sharded, H0 all-gathered).
+    from multimodal_biosignal_analysis_b200 import sweep as csweep
+    n_subj5, conds5 = 20, ("happy", "sad", "calm", "silence")
+    units5 = {(f"S{s_:02d}", c_): pinned[(4 * s_ + k_) % N_ROTATE]
+              for s_ in range(n_subj5) for k_, c_ in enumerate(conds5)}
+
+    def run_cfg5(units, n_surr=10000, n_perm=N_PERM_TOTAL):
+        return csweep.cmc_surrogate_cbpa_sweep(units, FS, nperseg=NPERSEG, freq_band=BAND, segment_starts=starts_h,
+                                               n_surrogates=n_surr, mode="phase", seed=11, n_permutations=n_perm,
+                                               contrasts=[("happy", "silence")])
+
+    small = {k: v for k, v in list(units5.items())[: 4 * max(world, 2)]}
+    run_cfg5(small)                                                # warm-up: allocator, NCCL, CBPA tables
+    barrier()
+    t0 = time.perf_counter()
+    out5 = run_cfg5(units5)
+    barrier()
+    cfg5_s = max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3
+    n_units5 = len(units5)
+    # the unit stage alone on THIS rank's share (device events around one more pass over 8 resident units)
+    e0.record()
+    for _ in range(8):
+        K.surrogate_null(res, K.SURR_PHASE, 0, 10000, seed=3)
+    e1.record()
+    torch.cuda.synchronize()
+    null_ms = e0.elapsed_time(e1) / 8
+    stages["config5_sweep"] = {
+        "metric": "subject_conditions_per_s", "value": n_units5 / cfg5_s, "unit": "subject-conditions/s",
+        "seconds_total": cfg5_s, "ms_per_unit_wall": cfg5_s * 1e3 * world / n_units5, "scaling": "strong",
+        "surrogates_per_s_e2e": n_units5 * 10000 / cfg5_s,
+        "pair_spectra_per_s_e2e": n_units5 * NE * NM / cfg5_s,
+        "null_kernel_ms_per_unit": null_ms,
+        "h2d_bytes_per_unit": int(n_samples * (NE + NM) * 4),
+        "d2h_bytes_per_unit": int(F * NE * NM * 8 + 10000 * 4),
+        "n_units": n_units5, "n_surrogates": 10000, "n_permutations": N_PERM_TOTAL,
+        "n_clusters": int(len(out5["cbpa"][("happy", "silence")]["cluster_pv"])),
+        "config": "BASELINE config 5 end to end, wall clock: sweep.cmc_surrogate_cbpa_sweep(units, ...) - 80 "
+                  "subject-conditions (20 subjects x 4 conditions, 64x64 channels, 30 epochs x 4 s, pinned float32 host "
+                  "tensors in, numpy out) dealt round-robin over the ranks, each with a 10,000-surrogate phase null, "
+                  "then the 10,000-permutation CBPA of one condition contrast (20 x 100 x 64) sharded over the ranks",
+        "api": "multimodal_biosignal_analysis_b200.sweep.cmc_surrogate_cbpa_sweep",
+    }
+    if world == 1:
+        # what a caller holding the reference's arrays pays: pageable numpy float32 / float64 (np.load output) are
+        # converted into pinned staging buffers by host threads before the upload
+        n_small = 8
+        for label, conv in (("numpy_float32_pageable", lambda a: a), ("numpy_float64_pageable", lambda a: a.astype(np.float64))):
+            hs = [(conv(a), conv(b)) for a, b in host_sets[:2]]
+            us = {(f"S{s_:02d}", c_): hs[(2 * s_ + k_) % 2] for s_ in range(n_small // 2) for k_, c_ in enumerate(conds5[:2])}
+            csweep.cmc_surrogate_cbpa_sweep({k: us[k] for k in list(us)[:2]}, FS, nperseg=NPERSEG, freq_band=BAND,
+                                            segment_starts=starts_h, n_surrogates=10000, seed=11, contrasts=[])
+            t0 = time.perf_counter()
+            csweep.cmc_surrogate_cbpa_sweep(us, FS, nperseg=NPERSEG, freq_band=BAND, segment_starts=starts_h,
+                                            n_surrogates=10000, seed=11, contrasts=[])
+            stages["config5_sweep"][f"ms_per_unit_wall_{label}"] = (time.perf_counter() - t0) * 1e3 / len(us)
+            del hs, us
+
+    # ---- stage: BASELINE config 1 (the reference's own CPU-runnable case): one EEG x one bipolar EMG channel ----
+    eeg1, emg1 = syn.make_recording(122880, 1, 2, seed=1)
+    bip1 = np.ascontiguousarray(emg1[:, :1] - emg1[:, 1:2])
+    for _ in range(3):
+        c1 = sf.welch_magnitude_squared_coherence(eeg1, bip1, FS, nperseg=1024).coherence
+    t0 = time.perf_counter()
+    for _ in range(20):
+        c1 = sf.welch_magnitude_squared_coherence(eeg1, bip1, FS, nperseg=1024).coherence
+    cfg1_ms = (time.perf_counter() - t0) * 1e3 / 20
+    stages["config1_welch_pair"] = {
+        "metric": "pair_spectra_per_s", "value": 1.0 / (cfg1_ms / 1e3), "unit": "pair-spectra/s", "ms": cfg1_ms,
+        "scaling": "replicated",
+        "config": "BASELINE config 1: C3 x one bipolar EMG channel, 60 s @ 2048 Hz, nperseg 1024 (L = 239, F = 513): one "
+                  "blocking welch_magnitude_squared_coherence call, numpy in, numpy out (launch / PCIe latency bound)"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from scipy import signal as ssig
+        x64, y64 = eeg1[:, 0].astype(np.float64), bip1[:, 0].astype(np.float64)
+        ssig.coherence(x64, y64, fs=FS, nperseg=1024)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            _, cref1 = ssig.coherence(x64, y64, fs=FS, nperseg=1024)
+        sc_ms = (time.perf_counter() - t0) * 1e3 / 20
+        stages["config1_welch_pair"]["cpu_baseline"] = {
+            "value": 1.0 / (sc_ms / 1e3), "unit": "pair-spectra/s", "cores": 1, "kind": "reference",
+            "sample": "scipy.signal.coherence(fs=2048, nperseg=1024) - the reference's own CPU path for this config "
+                      "(preprocessing.py:1228-1230) - 20 repetitions, one core",
+            "max_abs_diff_vs_gpu": float(np.max(np.abs(c1[:, 0, 0] - cref1)))}
+
+    # ---- stage: the production call of the reference workflow (subject_feature_extraction_workflow.py:58-69) ----
+    n_prod = int(FS) * 600
+    g = torch.Generator(device=dev).manual_seed(5)
+    eeg_p = torch.randn((n_prod, 11), device=dev, generator=g)
+    emg_p = torch.randn((n_prod, 64), device=dev, generator=g)
+
+    def prod():
+        return sf.multitaper_magnitude_squared_coherence(eeg_p, emg_p, FS, window_length_sec=2.0, use_jackknife=True,
+                                                         reduce_emg=True, zero_nonsignificant=True, freq_band=(1, 100))
+    for _ in range(2):
+        rp = prod()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        rp = prod()
+    torch.cuda.synchronize()
+    prod_ms = (time.perf_counter() - t0) * 1e3 / 5
+    w_prod = int(rp["coherence_raw"].shape[0])
+    stages["production_multitaper"] = {
+        "metric": "window_pair_spectra_per_s", "value": w_prod * 11 * 64 * world / (prod_ms / 1e3),
+        "unit": "pair-spectra/s (one per window)", "ms": prod_ms, "windows": w_prod, "scaling": "weak",
+        "config": "production geometry: 10-minute recording, 11 EEG x 64 EMG channels, N = 4096 / hop 2048, K = 5 DPSS "
+                  "tapers, jackknife CI + significance zeroing + EMG-argmax fused (compute_task_wise_aggregated_cmc "
+                  "semantics), 1-100 Hz, device-resident input, wall clock of the blocking call"}
+    del eeg_p, emg_p, rp
 
     # ---- CPU baseline (rank 0, N = 1): oracle port on a bounded sample ----
     cpu = None
@@ -653,7 +786,8 @@ def main_gpu(args):
                          "achieved": k1_gbs, "peak": hbm, "unit": "GB/s", "frac": k1_gbs / hbm,
                          # dram__bytes_read + dram__bytes_write of one K1 launch, ncu --set full (profiles/r01b_k1_tma.md,
                          # addendum 8: 63.0 MB read + 4.0 MB written inside the window, the rest of the output still in L2)
-                         "traffic": 67.0e6, "peak_source": peak_src,
+                         "traffic": K1_TRAFFIC_PROFILED["bytes"], "traffic_source": K1_TRAFFIC_PROFILED["source"],
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": k1_ms,
                          "k2_ms_per_step": k2_ms, "k1_share_of_step": 2 * k1_ms / (2 * k1_ms + k2_ms),
                          "timing_note": "launch_ms / k2_ms_per_step: CUDA events around the same kernels replayed back "
@@ -665,6 +799,7 @@ def main_gpu(args):
             # the other two headline metrics of BASELINE.json, copied up from `stages` for convenience
             "surrogates_per_s": stages["surrogate_null_phase"]["value"],
             "cbpa_permutations_per_s": stages["cbpa"]["value"],
+            "config5_sweep_seconds": stages["config5_sweep"]["seconds_total"],
         }
         print(json.dumps(line))
     if world > 1:

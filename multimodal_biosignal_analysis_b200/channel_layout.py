@@ -34,3 +34,32 @@ def _in_area(ch: str, abbr: str) -> bool:
 EEG_CHANNELS_BY_AREA = {label: [ch for ch in EEG_CHANNELS if _in_area(ch, abbr)] for label, abbr in _AREAS}
 EEG_CHANNEL_IND_DICT = {ch: ind for ind, ch in enumerate(EEG_CHANNELS)}
 EMG_CHANNELS = [f"EMG{i:02d}" for i in range(64)]
+
+# 2-D sensor layout of the cap (data; same coordinates as ``EEG_POSITIONS`` of the reference's
+# ``src/pipeline/visualizations.py:61-131``, to 4 decimals).  The layout is left / right symmetric: midline and
+# left-hemisphere (odd) sites are listed, even sites mirror them.  ``cbpa.run_cbpa`` derives its default spatial
+# adjacency from these positions (Delaunay neighbours) when no MNE montage is available.
+_MIDLINE_Y = {"Fpz": 0.602, "AFz": 0.42, "Fz": 0.252, "FCz": 0.126, "Cz": 0.0, "CPz": -0.126, "Pz": -0.252,
+              "POz": -0.42}
+_LEFT_XY = {
+    "Fp1": (0.165, 0.56), "AF7": (0.308, 0.49), "AF3": (0.154, 0.448), "F9": (0.506, 0.455), "F7": (0.41, 0.385),
+    "F3": (0.22, 0.294), "F1": (0.11, 0.266), "FT9": (0.594, 0.238), "FT7": (0.484, 0.196), "FC5": (0.3685, 0.168),
+    "FC3": (0.253, 0.147), "FC1": (0.1293, 0.133), "T9": (0.64, 0.0), "T7": (0.53, 0.0), "C5": (0.4125, 0.0),
+    "C3": (0.275, 0.0), "C1": (0.1375, 0.0), "TP9": (0.6, -0.24), "TP7": (0.484, -0.196), "CP5": (0.3685, -0.168),
+    "CP3": (0.253, -0.147), "CP1": (0.1293, -0.133), "P9": (0.47, -0.42), "P7": (0.37, -0.355), "P3": (0.22, -0.294),
+    "P1": (0.11, -0.266), "PO7": (0.308, -0.49), "O1": (0.165, -0.56),
+}
+
+
+def _positions() -> dict:
+    import re
+    pos = {ch: (0.0, y) for ch, y in _MIDLINE_Y.items()}
+    for ch, (ax, y) in _LEFT_XY.items():
+        area, num = re.fullmatch(r"([A-Za-z]+)(\d+)", ch).groups()
+        pos[ch] = (-ax, y)
+        pos[f"{area}{int(num) + 1}"] = (ax, y)
+    return {ch: pos[ch] for ch in EEG_CHANNELS}
+
+
+EEG_POSITIONS = _positions()
+assert len(EEG_POSITIONS) == 64

@@ -116,7 +116,7 @@ phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_be
     if (lp >= KPb / 2) return;
     uint32_t vals[4] = {0u, 0u, 0u, 0u};
     if (s < n_local && lp < nterms * L) {
-        const int term = lp / L, l = lp - term * L;
+        const int term = nterms == 1 ? 0 : lp / L, l = lp - term * L;
         const uint32_t* tab = table + (term == 2 ? kPhaseN : 0);
         const uint64_t sg = (uint64_t)(s_begin + s);
         // counter = (surrogate, segment, GLOBAL frequency group, surrogate >> 32): word q is frequency 4 fg + q
@@ -138,10 +138,11 @@ phase_gen_kernel(const uint32_t* __restrict__ table, uint64_t seed, int64_t s_be
 // B operand: 2^14 Z re-/im-form rows (fp16, K-major) from the whitened 3xTF32 operands left by cmc_csd_msc.
 // grid (F, Ne); block 256: the thread block holds Xh row i in shared memory and sweeps j.  Complex column
 // lp = term * L + l: terms 0 / 2 carry Z_hi = fp16(2^14 Z), term 1 carries Z_lo = fp16(2^14 Z - Z_hi).
+template <int NTERMS>
 __global__ void __launch_bounds__(256)
 z_gen_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo, const float* __restrict__ Bhi,
              const float* __restrict__ Blo, const float* __restrict__ pxx, const float* __restrict__ pyy, int L, int Ne,
-             int Nm, int MT, int NT, int KP, int LB, int KPb, int R_pad, int nterms, __half* __restrict__ Z) {
+             int Nm, int MT, int NT, int KP, int LB, int KPb, int R_pad, __half* __restrict__ Z) {
     extern __shared__ float2 xs[];                      // [L] complex Xh[l][i]
     const int f = blockIdx.x, i = blockIdx.y;
     const int half = KPb / 2;
@@ -163,8 +164,8 @@ z_gen_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo, const
         uint32_t* zim = reinterpret_cast<uint32_t*>(Z + (row_re + kPhPairs) * KPb);
         for (int lp = threadIdx.x; lp < half; lp += blockDim.x) {
             __half2 re = __floats2half2_rn(0.f, 0.f), im = re;
-            if (lp < nterms * L) {
-                const int term = lp / L, l = lp - term * L;
+            if (lp < NTERMS * L) {
+                const int term = NTERMS == 1 ? 0 : lp / L, l = lp - term * L;
                 const float2 x = xs[l];
                 const float yr = (bh[2 * l] + bl[2 * l]) * sy, yi = (bh[2 * l + 1] + bl[2 * l + 1]) * sy;
                 float zr = x.x * yr + x.y * yi;          // conj(x) * y (prescaled through sx)
@@ -445,14 +446,14 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
         phase_gen_kernel<<<dim3((y.KPb / 2 + 255) / 256, y.S_pad, ((f0 + fc - 1) >> 2) - (f0 >> 2) + 1), 256, 0, st>>>(
             table, seed, s_begin, (int)n, y.S_pad, L, y.nterms, fc, f0, y.KPb, A);
         CMC_CHECK_LAUNCH("phase_gen_kernel");
-        z_gen_kernel<<<dim3(fc, Ne), 256, (size_t)L * 8, st>>>(
+        (y.nterms == 3 ? z_gen_kernel<3> : z_gen_kernel<1>)<<<dim3(fc, Ne), 256, (size_t)L * 8, st>>>(
             reinterpret_cast<const float*>(w + cy.off_ahi) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_alo) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_bhi) + (int64_t)f0 * cy.NT * kTileN * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_blo) + (int64_t)f0 * cy.NT * kTileN * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_pxx) + (int64_t)f0 * Ne,
             reinterpret_cast<const float*>(w + cy.off_pyy) + (int64_t)f0 * Nm, L, Ne, Nm, cy.MT, cy.NT, cy.KP, cy.KP,
-            y.KPb, y.R_pad, y.nterms, Z);
+            y.KPb, y.R_pad, Z);
         CMC_CHECK_LAUNCH("z_gen_kernel");
         CUtensorMap mA, mB;
         if ((rc = make_kmajor_map(&mA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y.KPb, (int64_t)fc * y.S_pad, kPhM))) return rc;

@@ -108,11 +108,14 @@ def _plan(n_surrogates: int, n_freqs: int, shard: str):
 
 
 def _finish(pooled, exceed_d: torch.Tensor, max_local: torch.Tensor, n_surrogates: int, alpha: float,
-            by_frequency: bool = False):
-    cdist.all_reduce_sum_(exceed_d)                              # disjoint bins (or disjoint surrogates): a sum
+            by_frequency: bool = False, f_range=None):
     if by_frequency:
-        max_stat = cdist.all_reduce_max_(max_local)              # every rank holds all surrogates of its bins
+        # ranks own disjoint bin slices and all surrogates of them: ONE all-gather moves every rank's slice of the
+        # counts together with its per-surrogate maxima (instead of an all-reduce over the whole (F, Ne, Nm) array
+        # plus a second max-reduction)
+        exceed_d, max_stat = cdist.all_gather_frequency_slices(exceed_d, max_local, f_range)
     else:
+        cdist.all_reduce_sum_(exceed_d)                          # disjoint surrogates: counts add up
         max_stat = cdist.all_gather_ranges(max_local, n_surrogates)
     exceed = exceed_d.cpu().numpy().astype(np.int64)
     ms = max_stat.cpu().numpy()
@@ -150,7 +153,7 @@ def circular_shift_surrogate_null(pooled, n_surrogates: int = 1000, seed: int | 
     exceed, max_local = K.surrogate_null(csd, K.SURR_SHIFT, begin, end,
                                          shifts=torch.from_numpy(shifts[begin:end]).to(dev), group=pooled.group,
                                          f_range=f_range)
-    return _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq)
+    return _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq, f_range)
 
 
 def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int = 0, alpha: float = 0.05,
@@ -161,4 +164,69 @@ def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int 
     csd = pooled.device_result
     begin, end, f_range, by_freq = _plan(n_surrogates, csd.dims[1], shard)
     exceed, max_local = K.surrogate_null(csd, K.SURR_PHASE, begin, end, seed=seed, f_range=f_range)
-    return _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq)
+    return _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq, f_range)
+
+
+def surrogate_null_sweep(recordings, sampling_freq: float, nperseg: int = 256, noverlap: int | None = None,
+                         window: str = "hann", detrend: str | bool = "constant",
+                         freq_band: tuple[float, float] | None = None, segment_starts=None,
+                         n_surrogates: int = 1000, mode: str = "phase", seed: int = 0, alpha: float = 0.05,
+                         unit_indices=None):
+    """Welch coherence + surrogate null of MANY recordings of equal shape - the subject-condition sweep of BASELINE
+    config 5 (reference loop: ``src/subject_feature_extraction_workflow.py:37``, per-subject CMC call ``:246-255``).
+
+    Generator: per ``(eeg, emg)`` item, in order, a dict with ``coherence`` (F, Ne, Nm) float32, ``exceed``
+    (#{s : C_s >= C_obs}, int32), ``p_values`` (float64), ``max_stat`` (n_surrogates,) float32, ``threshold_fwe``
+    (the (1 - alpha) quantile of ``max_stat``), ``freqs`` and ``unit`` (the item's global index).  Per item the device
+    runs K1 (both modalities) -> K2 -> operand planes -> the whole null; upload of item i + 1 and download of item
+    i - 1 overlap with it on separate streams (``signal_features._RecordingPipeline``), so a sweep is GPU-bound as
+    long as one null outlasts one upload.  Arrays stay valid while the next item is fetched (copy to keep longer).
+
+    Item u draws its surrogates from ``seed + unit_indices[u]`` (default: its position in ``recordings``), so a
+    rank that is handed ``recordings[rank::world]`` with ``unit_indices=range(rank, n, world)`` reproduces exactly
+    what a single process computes for those items - units shard over ranks with NO collective."""
+    from . import signal_features as sf
+    if mode not in ("phase", "shift"):
+        raise ValueError("mode must be 'phase' or 'shift'")
+    first, it = sf._first_item(recordings)
+    if first is None:
+        return
+    dev = sf._device()
+    n, ne, nm = int(first[0].shape[0]), int(first[0].shape[1]), int(first[1].shape[1])
+    starts_h, win, dmode, lo, hi, freqs = sf._welch_plan(n, sampling_freq, nperseg, noverlap, window, detrend,
+                                                         freq_band, segment_starts)
+    F, L = hi - lo + 1, len(starts_h)
+    if mode == "shift" and L < 2:
+        raise ValueError("circular shift surrogates need at least two segments")
+    starts_d = torch.as_tensor(starts_h).to(dev)
+    wd = torch.from_numpy(win).to(dev)
+    ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)
+    units = iter(unit_indices) if unit_indices is not None else None
+    unit_of = {}
+
+    def compute(slot, i):
+        u = int(next(units)) if units is not None else i
+        unit_of[i] = u
+        if "X" not in slot:
+            slot["X"] = torch.empty((L, 1, F, ne_p), dtype=torch.complex64, device=dev)
+            slot["Y"] = torch.empty((L, 1, F, nm_p), dtype=torch.complex64, device=dev)
+        K.fft_segments(slot["eeg"], starts_d, wd, dmode, lo, hi, out=slot["X"], ch_offset=0)
+        K.fft_segments(slot["emg"], starts_d, wd, dmode, lo, hi, out=slot["Y"], ch_offset=0)
+        csd = K.csd_msc(slot["X"].view(L, F, ne_p)[:, :, :ne], slot["Y"].view(L, F, nm_p)[:, :, :nm])
+        if mode == "phase":
+            exceed, max_stat = K.surrogate_null(csd, K.SURR_PHASE, 0, n_surrogates, seed=seed + u)
+        else:
+            sh = np.random.default_rng(seed + u).integers(1, L, n_surrogates).astype(np.int32)
+            exceed, max_stat = K.surrogate_null(csd, K.SURR_SHIFT, 0, n_surrogates,
+                                                shifts=torch.from_numpy(sh).to(dev, non_blocking=True))
+        return {"coherence": csd.coh, "exceed": exceed, "max_stat": max_stat}
+
+    pipe = sf._RecordingPipeline(n, ne, nm, {"coherence": ((F, ne, nm), torch.float32),
+                                             "exceed": ((F, ne, nm), torch.int32),
+                                             "max_stat": ((n_surrogates,), torch.float32)}, compute)
+    for k, out in enumerate(pipe.run(first, it)):
+        ms = out["max_stat"]
+        yield {"coherence": out["coherence"], "exceed": out["exceed"],
+               "p_values": (1.0 + out["exceed"]) / (1.0 + n_surrogates), "max_stat": ms,
+               "threshold_fwe": float(np.quantile(ms, 1.0 - alpha)) if n_surrogates else float("nan"),
+               "n_surrogates": n_surrogates, "freqs": freqs[lo:hi + 1], "unit": unit_of[k]}

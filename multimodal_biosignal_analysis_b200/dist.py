@@ -46,6 +46,39 @@ def all_gather_ranges(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat([out[r * width: r * width + (e - b)] for r, (b, e) in enumerate(sizes)])
 
 
+def all_gather_frequency_slices(exceed: torch.Tensor, max_local: torch.Tensor, f_range) -> tuple:
+    """Combine a null whose FREQUENCY axis is split with ``shard_range(F)``: rank r owns ``exceed[f_b:f_e]`` and the
+    maxima of all surrogates over those bins.  One all-gather carries [slice of the counts | float bits of the
+    maxima] of every rank; returns (full counts (in place), element-wise max over the ranks' maxima)."""
+    rank, ws = world()
+    if ws == 1:
+        return exceed, max_local
+    F = exceed.shape[0]
+    per_bin = exceed[0].numel()
+    sizes = [shard_range(F, r, ws) for r in range(ws)]
+    width = max(e - b for b, e in sizes)
+    n_s = max_local.numel()
+    fb, fe = (int(f_range[0]), int(f_range[1])) if f_range is not None else sizes[rank]
+    mine = torch.zeros(width * per_bin + n_s, dtype=torch.int32, device=exceed.device)
+    mine[: (fe - fb) * per_bin] = exceed[fb:fe].reshape(-1).view(torch.int32)
+    mine[width * per_bin:] = max_local.contiguous().view(torch.int32)
+    out = torch.empty(ws * mine.numel(), dtype=torch.int32, device=exceed.device)
+    dist.all_gather_into_tensor(out, mine)
+    out = out.view(ws, mine.numel())
+    flat = exceed.view(F, per_bin)
+    for r, (b, e) in enumerate(sizes):
+        flat[b:e] = out[r, : (e - b) * per_bin].view(e - b, per_bin).view(exceed.dtype)
+    max_stat = out[:, width * per_bin:].view(torch.float32).max(dim=0).values
+    return exceed, max_stat
+
+
+def round_robin(n: int, rank: int | None = None, world_size: int | None = None) -> range:
+    """Indices of range(n) owned by ``rank`` when independent units (subject-conditions) are dealt out in turn."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    return range(rank, n, world_size)
+
+
 def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     _, ws = world()
     if ws > 1:

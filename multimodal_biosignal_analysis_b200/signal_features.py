@@ -717,29 +717,122 @@ def welch_magnitude_squared_coherence(eeg_array, emg_array, sampling_freq: float
                             eeg_axis, emg_axis)
 
 
-def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, noverlap: int | None = None,
-                          window: str = "hann", detrend: str | bool = "constant",
-                          freq_band: tuple[float, float] | None = None, segment_starts=None):
-    """Welch coherence of MANY recordings of equal shape (the subject-condition sweep of the workflows): a
-    generator that yields ``(coherence (F, Ne, Nm) float32 numpy, freqs)`` per ``(eeg, emg)`` item, in order.
+class _RecordingPipeline:
+    """Streams recordings of equal shape through the device: upload of item i + 1, compute of item i and download of
+    item i - 1 overlap on three CUDA streams, three buffer sets rotate (one uploading, one computing / downloading,
+    one in the caller's hands).  ``compute(slot, index)`` is called on the compute stream with ``slot["eeg"]``,
+    ``slot["emg"]`` resident (float32 (n, channels)) and returns ``{name: device tensor}`` matching ``out_specs``
+    (``{name: (shape, torch dtype)}``); ``slot`` is a dict the callback may keep per-slot scratch in.
 
-    Same arithmetic as :func:`welch_magnitude_squared_coherence` item by item, but the items are pipelined over
-    three CUDA streams - upload of item i + 1, K1 + K2 of item i and download of item i - 1 overlap - so a sweep runs
-    at the speed of the PCIe upload instead of the sum of the three.  Items must be time-first
-    ``(n_samples, n_channels)`` float32; pinned host tensors (``torch.Tensor.pin_memory()``) upload asynchronously,
-    anything else is staged through a pinned buffer first (one extra host copy).  The yielded coherence array stays
-    valid while the NEXT item is fetched and is overwritten when the one after that is requested (three buffer
-    sets rotate: one uploading, one computing / downloading, one in the caller's hands); copy it to keep it longer."""
-    it = iter(recordings)
-    try:
-        first = next(it)
-    except StopIteration:
-        return
-    dev = _device()
-    eeg0, emg0 = first
-    n, ne, nm = int(eeg0.shape[0]), int(eeg0.shape[1]), int(emg0.shape[1])
-    if int(emg0.shape[0]) != n:
-        raise ValueError("EEG and EMG must have same number of samples")
+    Items are ``(eeg, emg)``, time-first.  Pinned float32 host tensors upload asynchronously as they are; CUDA tensors
+    are used in place; anything else (numpy, pageable, float64, ...) is converted into a pinned staging buffer first
+    by a few host threads (numpy releases the GIL for the copy) - the extra host pass the reference's callers pay
+    when they hand over what ``np.load`` returned."""
+
+    N_SLOTS = 3
+    _pool = None
+
+    def __init__(self, n: int, ne: int, nm: int, out_specs: dict, compute, stage_threads: int = 4):
+        self.n, self.ne, self.nm, self.compute, self.stage_threads = n, ne, nm, compute, stage_threads
+        dev = _device()
+        self.slots = []
+        for _ in range(self.N_SLOTS):
+            self.slots.append(dict(
+                eeg=torch.empty((n, ne), dtype=torch.float32, device=dev),
+                emg=torch.empty((n, nm), dtype=torch.float32, device=dev),
+                out={k: torch.empty(shape, dtype=dt).pin_memory() for k, (shape, dt) in out_specs.items()},
+                stage=None, h2d=None, comp=None, d2h=None, res=None, src=None))
+        self.s_up, self.s_comp, self.s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        for st in (self.s_up, self.s_comp, self.s_down):
+            st.wait_stream(cur)
+
+    @classmethod
+    def _threads(cls):
+        if cls._pool is None:
+            import concurrent.futures as cf
+            cls._pool = cf.ThreadPoolExecutor(max_workers=8, thread_name_prefix="cmc-stage")
+        return cls._pool
+
+    def _host_f32(self, a, slot, key):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a
+            if a.dtype == torch.float32 and a.is_pinned() and a.is_contiguous():
+                return a
+            a = a.numpy()
+        if slot["stage"] is None:
+            slot["stage"] = {"eeg": torch.empty((self.n, self.ne), dtype=torch.float32).pin_memory(),
+                             "emg": torch.empty((self.n, self.nm), dtype=torch.float32).pin_memory()}
+        buf = slot["stage"][key]
+        dst, src = buf.numpy(), np.asarray(a)
+        nt = self.stage_threads if src.size >= (1 << 20) else 1
+        if nt <= 1:
+            np.copyto(dst, src, casting="same_kind")
+        else:
+            edges = np.linspace(0, self.n, nt + 1).astype(np.int64)
+            futs = [self._threads().submit(np.copyto, dst[b:e], src[b:e], "same_kind")
+                    for b, e in zip(edges[:-1], edges[1:]) if e > b]
+            for f in futs:
+                f.result()
+        return buf
+
+    def _submit(self, item, i):
+        slot = self.slots[i % self.N_SLOTS]
+        eeg, emg = item
+        if tuple(eeg.shape) != (self.n, self.ne) or tuple(emg.shape) != (self.n, self.nm):
+            raise ValueError("all recordings of a sweep must have the shape of the first one")
+        if slot["comp"] is not None:                              # the slot's previous item has been transformed
+            self.s_up.wait_event(slot["comp"])
+        if slot["stage"] is not None and slot["h2d"] is not None:
+            slot["h2d"].synchronize()                             # staging buffer still being read by the copy engine
+        he, hm = self._host_f32(eeg, slot, "eeg"), self._host_f32(emg, slot, "emg")
+        slot["src"] = (he, hm)                                    # keep the sources alive until the copy has run
+        with torch.cuda.stream(self.s_up):
+            slot["eeg"].copy_(he, non_blocking=True)
+            slot["emg"].copy_(hm, non_blocking=True)
+            slot["h2d"] = torch.cuda.Event()
+            slot["h2d"].record()
+        with torch.cuda.stream(self.s_comp):
+            self.s_comp.wait_event(slot["h2d"])
+            if slot["d2h"] is not None:
+                self.s_comp.wait_event(slot["d2h"])               # previous results of this slot have left the device
+            res = self.compute(slot, i)
+            slot["comp"] = torch.cuda.Event()
+            slot["comp"].record()
+        with torch.cuda.stream(self.s_down):
+            self.s_down.wait_event(slot["comp"])
+            for k, t in res.items():
+                slot["out"][k].copy_(t, non_blocking=True)
+                t.record_stream(self.s_down)
+            slot["d2h"] = torch.cuda.Event()
+            slot["d2h"].record()
+        slot["res"] = res
+
+    def _collect(self, i):
+        slot = self.slots[i % self.N_SLOTS]
+        slot["d2h"].synchronize()
+        return {k: t.numpy() for k, t in slot["out"].items()}
+
+    def run(self, first, rest):
+        """Generator over ``[first] + rest``: yields the dict of host arrays of every item, in order.  An array
+        stays valid while the NEXT item is fetched and is overwritten when the one after that is requested."""
+        try:
+            self._submit(first, 0)
+            i = 0
+            for item in rest:
+                i += 1
+                self._submit(item, i)                             # item i is in flight while item i - 1 is handed out
+                yield self._collect(i - 1)
+            yield self._collect(i)
+        finally:
+            # also when the consumer stops early: nothing of this sweep may still be running when its buffers are freed
+            for st in (self.s_up, self.s_comp, self.s_down):
+                st.synchronize()
+
+
+def _welch_plan(n: int, sampling_freq: float, nperseg: int, noverlap, window: str, detrend, freq_band, segment_starts):
+    """Shared argument handling of the Welch entry points: (segment_starts, window row, detrend mode, lo, hi, freqs)."""
     if noverlap is None:
         noverlap = nperseg // 2
     if segment_starts is None:
@@ -754,89 +847,60 @@ def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, 
         if len(sel) == 0:
             raise ValueError(f"freq_band {freq_band} selects no frequency bin")
         lo, hi = int(sel[0]), int(sel[-1])
-    F = hi - lo + 1
     K.check_segments(segment_starts, nperseg, n)
-    starts_d = torch.as_tensor(np.asarray(segment_starts, dtype=np.int64)).to(dev)
-    wd = torch.from_numpy(signal.get_window(window, nperseg).astype(np.float32)[None]).to(dev)
-    L = len(segment_starts)
-    ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)                    # even channel pitch for K2's TMA
-    n_slots = 3
-    slots = []
-    for _ in range(n_slots):
-        slots.append(dict(
-            eeg=torch.empty((n, ne), dtype=torch.float32, device=dev),
-            emg=torch.empty((n, nm), dtype=torch.float32, device=dev),
-            X=torch.empty((L, 1, F, ne_p), dtype=torch.complex64, device=dev),
-            Y=torch.empty((L, 1, F, nm_p), dtype=torch.complex64, device=dev),
-            out=torch.empty((F, ne, nm), dtype=torch.float32).pin_memory(),
-            stage=None, h2d=None, comp=None, d2h=None, res=None))
-    s_up, s_comp, s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    cur = torch.cuda.current_stream()
-    for st in (s_up, s_comp, s_down):
-        st.wait_stream(cur)
+    win = signal.get_window(window, nperseg).astype(np.float32)[None]
+    return np.asarray(segment_starts, dtype=np.int64), win, dmode, lo, hi, freqs
 
-    def host_f32(a, slot, key):
-        if isinstance(a, torch.Tensor):
-            if a.is_cuda:
-                return a
-            if a.dtype == torch.float32 and a.is_pinned() and a.is_contiguous():
-                return a
-            a = a.numpy()
-        if slot["stage"] is None:
-            slot["stage"] = {"eeg": torch.empty((n, ne), dtype=torch.float32).pin_memory(),
-                             "emg": torch.empty((n, nm), dtype=torch.float32).pin_memory()}
-        buf = slot["stage"][key]
-        np.copyto(buf.numpy(), np.asarray(a), casting="same_kind")
-        return buf
 
-    def submit(item, i):
-        slot = slots[i % n_slots]
-        eeg, emg = item
-        if tuple(eeg.shape) != (n, ne) or tuple(emg.shape) != (n, nm):
-            raise ValueError("all recordings of a sweep must have the shape of the first one")
-        if slot["comp"] is not None:                              # the slot's previous item has been transformed
-            s_up.wait_event(slot["comp"])
-        if slot["stage"] is not None and slot["h2d"] is not None:
-            slot["h2d"].synchronize()                             # staging buffer still being read by the copy engine
-        with torch.cuda.stream(s_up):
-            slot["eeg"].copy_(host_f32(eeg, slot, "eeg"), non_blocking=True)
-            slot["emg"].copy_(host_f32(emg, slot, "emg"), non_blocking=True)
-            slot["h2d"] = torch.cuda.Event()
-            slot["h2d"].record()
-        with torch.cuda.stream(s_comp):
-            s_comp.wait_event(slot["h2d"])
-            if slot["d2h"] is not None:
-                s_comp.wait_event(slot["d2h"])                    # previous result of this slot has left the device
-            K.fft_segments(slot["eeg"], starts_d, wd, dmode, lo, hi, out=slot["X"], ch_offset=0)
-            K.fft_segments(slot["emg"], starts_d, wd, dmode, lo, hi, out=slot["Y"], ch_offset=0)
-            res = K.csd_msc(slot["X"].view(L, F, ne_p)[:, :, :ne], slot["Y"].view(L, F, nm_p)[:, :, :nm])
-            slot["comp"] = torch.cuda.Event()
-            slot["comp"].record()
-        with torch.cuda.stream(s_down):
-            s_down.wait_event(slot["comp"])
-            slot["out"].copy_(res.coh, non_blocking=True)
-            res.coh.record_stream(s_down)
-            slot["d2h"] = torch.cuda.Event()
-            slot["d2h"].record()
-        slot["res"] = res
-
-    def collect(i):
-        slot = slots[i % n_slots]
-        slot["d2h"].synchronize()
-        return slot["out"].numpy(), freqs[lo:hi + 1]
-
+def _first_item(recordings):
+    it = iter(recordings)
     try:
-        submit(first, 0)
-        i = 0
-        for item in it:
-            i += 1
-            submit(item, i)                                       # item i is in flight while item i - 1 is handed out
-            yield collect(i - 1)
-        yield collect(i)
-    finally:
-        # also when the consumer stops early: nothing of this sweep may still be running when its buffers are freed
-        for st in (s_up, s_comp, s_down):
-            st.synchronize()
+        first = next(it)
+    except StopIteration:
+        return None, it
+    eeg0, emg0 = first
+    if int(emg0.shape[0]) != int(eeg0.shape[0]):
+        raise ValueError("EEG and EMG must have same number of samples")
+    return first, it
+
+
+def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, noverlap: int | None = None,
+                          window: str = "hann", detrend: str | bool = "constant",
+                          freq_band: tuple[float, float] | None = None, segment_starts=None):
+    """Welch coherence of MANY recordings of equal shape (the subject-condition sweep of the workflows): a
+    generator that yields ``(coherence (F, Ne, Nm) float32 numpy, freqs)`` per ``(eeg, emg)`` item, in order.
+
+    Same arithmetic as :func:`welch_magnitude_squared_coherence` item by item, but the items are pipelined over
+    three CUDA streams - upload of item i + 1, K1 + K2 of item i and download of item i - 1 overlap - so a sweep runs
+    at the speed of the PCIe upload instead of the sum of the three.  Items must be time-first
+    ``(n_samples, n_channels)``; pinned float32 host tensors (``torch.Tensor.pin_memory()``) upload asynchronously,
+    anything else is staged through a pinned buffer first (one extra host pass).  The yielded coherence array stays
+    valid while the NEXT item is fetched and is overwritten when the one after that is requested (three buffer
+    sets rotate: one uploading, one computing / downloading, one in the caller's hands); copy it to keep it longer."""
+    first, it = _first_item(recordings)
+    if first is None:
+        return
+    dev = _device()
+    n, ne, nm = int(first[0].shape[0]), int(first[0].shape[1]), int(first[1].shape[1])
+    starts_h, win, dmode, lo, hi, freqs = _welch_plan(n, sampling_freq, nperseg, noverlap, window, detrend, freq_band,
+                                                       segment_starts)
+    F, L = hi - lo + 1, len(starts_h)
+    starts_d = torch.as_tensor(starts_h).to(dev)
+    wd = torch.from_numpy(win).to(dev)
+    ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)                    # even channel pitch for K2's TMA
+
+    def compute(slot, i):
+        if "X" not in slot:
+            slot["X"] = torch.empty((L, 1, F, ne_p), dtype=torch.complex64, device=dev)
+            slot["Y"] = torch.empty((L, 1, F, nm_p), dtype=torch.complex64, device=dev)
+        K.fft_segments(slot["eeg"], starts_d, wd, dmode, lo, hi, out=slot["X"], ch_offset=0)
+        K.fft_segments(slot["emg"], starts_d, wd, dmode, lo, hi, out=slot["Y"], ch_offset=0)
+        res = K.csd_msc(slot["X"].view(L, F, ne_p)[:, :, :ne], slot["Y"].view(L, F, nm_p)[:, :, :nm])
+        return {"coherence": res.coh}
+
+    pipe = _RecordingPipeline(n, ne, nm, {"coherence": ((F, ne, nm), torch.float32)}, compute)
+    for out in pipe.run(first, it):
+        yield out["coherence"], freqs[lo:hi + 1]
 
 
 def local_neighbor_coherence(data, neighbor_mapping, sampling_freq: float, nperseg: int = 256) -> float:

@@ -104,8 +104,15 @@ def _gloo_worker(rank, world, port, q):
     mx = torch.tensor([0.1 * (rank + 1), 0.5 - 0.1 * rank], dtype=torch.float32)
     cd.all_reduce_max_(mx)
     s0b, s1b, f_range_b, by_freq_b = ds._plan(7, 1, "auto")          # fewer bins than ranks: split the surrogates
+    # one all-gather of [count slice | maxima bits]: uneven slices (3 + 2 bins), 2 x 3 pairs, 4 surrogates
+    ex = torch.zeros((5, 2, 3), dtype=torch.int32)
+    ex[f_range[0]:f_range[1]] = 100 * (rank + 1) + torch.arange((f_range[1] - f_range[0]) * 6, dtype=torch.int32).view(-1, 2, 3)
+    ml = torch.tensor([0.1, 0.9, 0.3, 0.0], dtype=torch.float32) if rank == 0 else \
+        torch.tensor([0.2, 0.8, 0.3, 0.5], dtype=torch.float32)
+    ex_full, ms = cd.all_gather_frequency_slices(ex, ml, f_range)
     q.put((rank, full.tolist(), cnt.tolist(), (s0, s1, f_range, by_freq), [round(float(v), 6) for v in mx],
-           (s0b, s1b, f_range_b, by_freq_b)))
+           (s0b, s1b, f_range_b, by_freq_b), ex_full.reshape(-1).tolist(), [round(float(v), 6) for v in ms],
+           list(cd.round_robin(7))))
     dist.destroy_process_group()
 
 
@@ -121,7 +128,10 @@ def test_two_rank_sharding_over_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, full, cnt, plan, mx, plan_b in out:
+    want_ex = [100 + i for i in range(18)] + [200 + i for i in range(12)]
+    for rank, full, cnt, plan, mx, plan_b, ex_full, ms, rr in out:
+        assert ex_full == want_ex and ms == [0.2, 0.9, 0.3, 0.5]
+        assert rr == ([0, 2, 4, 6] if rank == 0 else [1, 3, 5])
         assert full == [10 * i for i in range(11)]
         assert cnt == [3, 3, 3, 3]
         assert plan == (0, 7, (0, 3) if rank == 0 else (3, 5), True)
