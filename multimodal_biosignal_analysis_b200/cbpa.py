@@ -330,22 +330,226 @@ def phase_contrast_from_cycles(cfg: CBPAConfig, cycles_by_condition: dict) -> np
     return np.nanmean(np.stack(a, axis=0), axis=0) - np.nanmean(np.stack(b, axis=0), axis=0)
 
 
+# ----------------------------------------------------------------------------- data loading (cbpa.py:282-432)
+def _load_subject_data(cfg: CBPAConfig, subject_ind: int):
+    """Stored spectrogram + enriched log of one subject (cbpa.py:282-350): ``(spectrogram (n_windows, n_freqs,
+    n_channels), freqs, timestamps (tz-aware DatetimeIndex, one per window centre), log_df)``.  Left-handed subjects
+    carry the mirrored CMC channel subset in their file names."""
+    import pandas as pd
+    from . import experiment_log as xlog
+    from .signal_features import fetch_stored_spectrograms, mirror_eeg_channel_list
+    data = Path(cfg.data_root) / "data"
+    feat_dir = data / "precomputed_features" / f"subject_{subject_ind:02}"
+    exp_dir = data / "experiment_results" / f"subject_{subject_ind:02}"
+    handedness = xlog.fetch_personal_data(exp_dir, False)["Dominant hand"]
+    log_df = xlog.fetch_enriched_log_frame(exp_dir, verbose=False)
+    log_df.index = xlog.make_timezone_aware(log_df.index)
+    qtc_start, qtc_end = xlog.get_qtc_measurement_start_end(log_df, False)
+    if cfg.modality == "CMC":
+        subset = (mirror_eeg_channel_list(CMC_EEG_CHANNEL_SUBSET, input_is_left=True) if handedness == "Left"
+                  else CMC_EEG_CHANNEL_SUBSET)
+        file_id = [cfg.modality_file_id, f"Channels_{'_'.join(subset)}"]
+        expected_ch = len(CMC_EEG_CHANNEL_SUBSET)
+    else:
+        file_id, expected_ch = cfg.modality_file_id, None
+    spectrogram, times, freqs = fetch_stored_spectrograms(feat_dir, modality=cfg.modality, file_identifier=file_id,
+                                                          expected_n_channels=expected_ch)
+    times_arr = np.asarray(times, dtype=np.float64)
+    if cfg.use_stretched_window_timestamps:
+        half = 0.5 * (cfg.cmc_time_window_sec if cfg.modality == "CMC" else cfg.psd_time_window_sec)
+        timestamps = xlog.add_time_index(start_timestamp=qtc_start + pd.Timedelta(seconds=half),
+                                         end_timestamp=qtc_end - pd.Timedelta(seconds=half),
+                                         n_timesteps=len(times_arr))
+    else:
+        # window centres are stored as seconds since the measurement start; non-finite centres (outside-task
+        # slots) become NaT and never match a trial span
+        timestamps = pd.DatetimeIndex([qtc_start + pd.Timedelta(seconds=float(sec)) if np.isfinite(sec) else pd.NaT
+                                       for sec in times_arr])
+    return spectrogram, freqs, xlog.make_timezone_aware(timestamps), log_df
+
+
+def _get_trial_spans(log_df) -> dict:
+    """{trial_id: (start, end)} with the default latency / transient cut-off (cbpa.py:354-361)."""
+    from . import experiment_log as xlog
+    return xlog.get_all_task_start_ends(log_df, "dict")
+
+
+def _common_time_grid_from_spans(cfg: CBPAConfig, trial_spans: dict, overlap_ratio=.5) -> np.ndarray:
+    """Within-trial time grid at the spectrogram step, from the first trial's duration (cbpa.py:364-378)."""
+    import pandas as pd
+    tw = cfg.psd_time_window_sec if cfg.modality == "PSD" else cfg.cmc_time_window_sec
+    first_start, first_end = next(iter(trial_spans.values()))
+    dur = (pd.Timestamp(first_end) - pd.Timestamp(first_start)).total_seconds()
+    n_times = max(1, int(dur / (tw * overlap_ratio)))
+    return np.arange(n_times) * (tw * overlap_ratio)
+
+
+def _band_power_per_trial(cfg: CBPAConfig, band_power: np.ndarray, timestamps, trial_spans: dict,
+                          target_n_times: int | None):
+    """(n_trials, n_times, n_channels) slices at native resolution, trials of another length linearly resampled
+    onto ``target_n_times`` points (default: the modal length) - cbpa.py:381-432."""
+    import warnings
+    import pandas as pd
+    slices, ids = [], []
+    for trial_id, (t_start, t_end) in trial_spans.items():
+        slc = band_power[np.asarray((timestamps >= t_start) & (timestamps < t_end))]
+        if slc.shape[0] == 0:
+            warnings.warn(f"  [WARN] Trial {trial_id}: no spectrogram windows found in span. Skipping.")
+            continue
+        slices.append(slc)
+        ids.append(trial_id)
+    if not slices:
+        raise RuntimeError("No trial windows found — check timestamp alignment.")
+    if target_n_times is None:
+        target_n_times = int(pd.Series([x.shape[0] for x in slices]).mode().iloc[0])
+    n_ch = slices[0].shape[-1]
+    result = np.full((len(slices), target_n_times, n_ch), np.nan)
+    dst_x = np.linspace(0, 1, target_n_times)
+    for i, slc in enumerate(slices):
+        if slc.shape[0] == target_n_times:
+            result[i] = slc
+        else:
+            src_x = np.linspace(0, 1, slc.shape[0])
+            for ch in range(n_ch):
+                result[i, :, ch] = np.interp(dst_x, src_x, slc[:, ch])
+    return result, ids
+
+
+STATS_FRAME_SEG_SUFFIX: str = "1seg"
+
+
+def load_stats_frame(data_root):
+    """Newest ``Combined Statistics 1seg`` CSV - the single source of trial-level condition labels (cbpa.py:445-492)."""
+    import pandas as pd
+    feature_dir = Path(data_root) / "data" / "precomputed_features"
+    try:
+        csv_path = filemgmt.most_recent_file(feature_dir, ".csv", [f"Combined Statistics {STATS_FRAME_SEG_SUFFIX}"])
+    except (ValueError, FileNotFoundError):
+        raise FileNotFoundError(
+            f"\n[CBPA] Required statistics frame not found in:\n  {feature_dir}\n"
+            f"Expected a file matching 'Combined Statistics {STATS_FRAME_SEG_SUFFIX}' with extension '.csv'.\n"
+            f"Please run the main statistical_workflow.py pipeline first (with n_within_trial_segments=1) to "
+            f"generate it.")
+    df = pd.read_csv(csv_path)
+    missing = {"Subject ID", "Trial ID", "Category or Silence", "Perceived Category", "Music Listening"} - set(df.columns)
+    if missing:
+        raise ValueError(f"[CBPA] Statistics frame is missing required columns: {missing}\n  Loaded from: {csv_path}")
+    print(f"  [stats frame] Loaded: {Path(csv_path).name}  ({len(df)} rows, {df['Subject ID'].nunique()} subjects, "
+          f"{df['Trial ID'].nunique()} unique trial IDs)")
+    return df
+
+
+def get_trial_condition_map(stats_df, subject_id: int, condition_column: str) -> dict:
+    """Trial ID -> condition label (None for NaN) of one subject, cbpa.py:495-529."""
+    import pandas as pd
+    subj = stats_df[stats_df["Subject ID"] == subject_id]
+    if subj.empty:
+        raise ValueError(f"[CBPA] Subject {subject_id} not found in statistics frame. "
+                         f"Available subjects: {sorted(stats_df['Subject ID'].unique())}")
+    out = {}
+    for _, row in subj.iterrows():
+        val = row.get(condition_column, None)
+        out[int(row["Trial ID"])] = None if pd.isna(val) else str(val)
+    return out
+
+
 # ----------------------------------------------------------------------------- runner
 def build_contrast_array(cfg: CBPAConfig):
-    """Per-subject A - B contrast (n_subj, n_times, n_ch) from the stored spectrogram files
-    (cbpa.py:733-942).  The loaders are pandas / experiment-log glue of the reference
-     and are not rebuilt here: pass ``contrast=(X, ch_names, time_grid)``
-    to ``run_cbpa`` or assign a callable to ``cbpa.build_contrast_array``."""
-    raise NotImplementedError(
-        "build_contrast_array needs the reference's experiment-log loaders; pass contrast=(X, ch_names, "
-        "time_grid) to run_cbpa")
+    """Per-subject A - B contrast ``X (n_subjects, n_times, n_channels)``, channel names and the time (seconds) or
+    phase (degrees) grid from the stored spectrogram files, the enriched logs and the Combined Statistics frame -
+    cbpa.py:733-942.  Subjects whose files fail to load, who are missing from the statistics frame or lack one of
+    the two conditions are skipped with a warning (which lowers the degrees of freedom of the threshold)."""
+    import warnings
+    stats_df = load_stats_frame(cfg.data_root)
+    subjects = sorted(stats_df["Subject ID"].astype(int).unique())
+    if cfg.exclude_subjects:
+        print(f"  [Exclusions] Skipping subjects: {cfg.exclude_subjects}")
+        subjects = [s for s in subjects if s not in cfg.exclude_subjects]
+    print(f"  [subjects] Running on {len(subjects)} subjects: {subjects}")
+    if cfg.modality == "CMC":
+        # stored CMC spectrograms already hold the motor subset: never index them with 64-channel indices
+        ch_indices = None
+        ch_names_out = cfg.channels if cfg.channels is not None else CMC_EEG_CHANNEL_SUBSET
+    elif cfg.channels is not None:
+        ch_indices, ch_names_out = [EEG_CHANNEL_IND_DICT[ch] for ch in cfg.channels], cfg.channels
+    else:
+        ch_indices, ch_names_out = None, EEG_CHANNELS
+    time_grid, n_times_ref = None, None
+    if cfg.use_phase_normalization:
+        time_grid = np.linspace(0, 360, cfg.n_phase_bins, endpoint=False)
+        n_times_ref = cfg.n_phase_bins
+    diffs = []
+    for subj in subjects:
+        print(f"  Subject {subj:02} — loading...")
+        try:
+            spectrogram, freqs, timestamps, log_df = _load_subject_data(cfg, subj)
+        except Exception as exc:
+            warnings.warn(f"Subject {subj:02}: load failed ({exc}). Skipping.")
+            continue
+        try:
+            cond_map = get_trial_condition_map(stats_df, subj, cfg.condition_column)
+        except ValueError as exc:
+            warnings.warn(str(exc) + " Skipping.")
+            continue
+        spans = {int(k): v for k, v in _get_trial_spans(log_df).items()}
+        missing = set(spans) - set(cond_map)
+        if missing:
+            warnings.warn(f"Subject {subj:02}: trial IDs {missing} present in log_df but missing from stats frame. "
+                          f"These trials will be skipped.")
+        if time_grid is None:
+            time_grid = _common_time_grid_from_spans(cfg, spans, overlap_ratio=cfg.overlap_ratio)
+            n_times_ref = len(time_grid)
+        band_power = _extract_band_power(cfg, spectrogram, freqs, ch_indices)
+        if cfg.use_phase_normalization:
+            cycles = _band_power_per_phase(cfg, band_power, timestamps, spans, cond_map, log_df,
+                                           min_cycle_coverage_ratio=.8)
+            cyc_a, cyc_b = cycles.get(cfg.condition_A, []), cycles.get(cfg.condition_B, [])
+            short = [(c, len(x)) for c, x in ((cfg.condition_A, cyc_a), (cfg.condition_B, cyc_b))
+                     if len(x) < cfg.min_cycles_per_condition]
+            if short:
+                warnings.warn(f"Subject {subj:02}: only {short[0][1]} valid cycles for '{short[0][0]}' "
+                              f"(min={cfg.min_cycles_per_condition}). Skipping.")
+                continue
+            diffs.append(phase_contrast_from_cycles(cfg, cycles))
+            print(f"    → {len(cyc_a)} cycles '{cfg.condition_A}', {len(cyc_b)} cycles '{cfg.condition_B}'")
+            continue
+        trial_data, trial_ids = _band_power_per_trial(cfg, band_power, timestamps, spans, n_times_ref)
+        idx_a = [i for i, t in enumerate(trial_ids) if cond_map.get(t) == cfg.condition_A]
+        idx_b = [i for i, t in enumerate(trial_ids) if cond_map.get(t) == cfg.condition_B]
+        empty = [c for c, idx in ((cfg.condition_A, idx_a), (cfg.condition_B, idx_b)) if len(idx) == 0]
+        if empty:
+            warnings.warn(f"Subject {subj:02}: no trials found for '{empty[0]}' in '{cfg.condition_column}'. Skipping.")
+            continue
+        diffs.append(np.nanmean(trial_data[idx_a], axis=0) - np.nanmean(trial_data[idx_b], axis=0))
+        print(f"    → {len(idx_a)} trials '{cfg.condition_A}', {len(idx_b)} trials '{cfg.condition_B}'")
+    if not diffs:
+        raise RuntimeError("[CBPA] No valid subjects produced a contrast. "
+                           "Check data paths, subject IDs, and condition labels.")
+    X = np.stack(diffs, axis=0)
+    print(f"\n  Contrast array built: {X.shape}  "
+          f"[{X.shape[0]} subjects × {X.shape[1]} time pts × {X.shape[2]} channels]")
+    return X, ch_names_out, time_grid
+
+
+def default_spatial_adjacency(ch_names):
+    """Stand-in for ``find_ch_adjacency(_build_mne_info(ch_names))`` (cbpa.py:200-243) without MNE: Delaunay
+    neighbours of the cap layout ``channel_layout.EEG_POSITIONS`` (reference ``visualizations.py:61-131``) restricted
+    to ``ch_names``.  MNE triangulates the standard_1020 montage instead, so the edge set can differ in detail;
+    pass ``spatial_adjacency=`` to ``run_cbpa`` to use an exact one."""
+    from .channel_layout import EEG_POSITIONS
+    unknown = [c for c in ch_names if c not in EEG_POSITIONS]
+    if unknown:
+        raise ValueError(f"no sensor position for channels {unknown}; pass spatial_adjacency=")
+    return find_ch_adjacency_from_positions(np.array([EEG_POSITIONS[c] for c in ch_names], dtype=np.float64))
 
 
 def run_cbpa(cfg: CBPAConfig, cluster_rows_accumulator: list[dict] | None = None, *, contrast=None,
              spatial_adjacency=None, signs: np.ndarray | None = None) -> dict:
-    """Full CBPA for one contrast, cbpa.py:985-1067.  Returns the reference's result dict
-    (keys t_obs, t_thresh, clusters, cluster_pv, H0, good_cluster_inds, ch_names, time_grid, cfg,
-    n_valid_subjects).  ``spatial_adjacency``: channel adjacency matrix or (n_ch, 2) positions."""
+    """Full CBPA for one contrast, cbpa.py:985-1067: ``run_cbpa(cfg, cluster_rows_accumulator)`` as the reference
+    calls it.  Returns the reference's result dict (keys t_obs, t_thresh, clusters, cluster_pv, H0,
+    good_cluster_inds, ch_names, time_grid, cfg, n_valid_subjects).  Keyword-only extras (defaults reproduce the
+    reference's behaviour): ``contrast=(X, ch_names, time_grid)`` skips the file loading, ``spatial_adjacency``
+    (matrix or (n_ch, 2) positions) replaces the layout-derived channel adjacency, ``signs`` fixes the sign table."""
     filemgmt.assert_dir(cfg.output_dir)
     _print_header(cfg)
     X, ch_names, time_grid = contrast if contrast is not None else build_contrast_array(cfg)
@@ -360,7 +564,7 @@ def run_cbpa(cfg: CBPAConfig, cluster_rows_accumulator: list[dict] | None = None
           f"(α = {cfg.alpha_cluster_forming}, tail = {cfg.tail})")
     rng = np.random.default_rng(cfg.seed)
     if spatial_adjacency is None:
-        raise ValueError("spatial_adjacency (matrix or 2-D sensor positions) is required without MNE")
+        spatial_adjacency = default_spatial_adjacency(list(ch_names))
     adjacency = _build_adjacency(spatial_adjacency, n_times)
     if cfg.use_phase_normalization:
         adjacency = _add_phase_wraparound(adjacency, n_times, n_ch, np.asarray(time_grid))
@@ -386,7 +590,20 @@ def run_cbpa(cfg: CBPAConfig, cluster_rows_accumulator: list[dict] | None = None
                    n_valid_subjects=n_subj)
     _save_results(results, cfg, cluster_rows_accumulator=cluster_rows_accumulator,
                   save_per_run_cluster_csv=(cluster_rows_accumulator is None))
+    if cfg.save_plots or cfg.show_plots:
+        _plot_results(results, cfg)
     return results
+
+
+def _plot_results(results: dict, cfg: CBPAConfig) -> None:
+    """cbpa.py:1064-1065 hands the result dict to ``visualizations.plot_cbpa_results`` (matplotlib, out of scope of
+    this package): use the reference's plotting module when it is importable, otherwise say so once and go on."""
+    try:
+        import importlib
+        viz = importlib.import_module("src.pipeline.visualizations")
+        viz.plot_cbpa_results(results, cfg)
+    except Exception as exc:                                       # no reference tree / no matplotlib backend
+        print(f"  [plots] skipped ({type(exc).__name__}): plotting lives in the reference's visualizations module")
 
 
 def _cluster_mask(cluster, n_times: int, n_ch: int) -> np.ndarray:

@@ -492,9 +492,8 @@ def max_cmc_spectrograms_over_channels(cmc_array, cmc_array_lower_ci=None, cmc_a
 
 
 def _build_task_window_mask(time_centers_sec, log_frame, pre_buffer_sec: float, post_buffer_sec: float):
-    """signal_features.py:842-895.  The trial-log parsing lives in the reference's pandas glue
-    (``data_integration``, out of scope); it is resolved lazily so that the reference's own module
-    (or test doubles patched onto this module) supplies it."""
+    """signal_features.py:842-895.  The trial-log readers come from ``experiment_log`` through the
+    ``data_integration`` namespace below (test doubles may be patched onto it)."""
     import pandas as pd
     measurement_start, _ = data_integration.get_qtc_measurement_start_end(log_frame)
     measurement_start_aware = pd.Timestamp(measurement_start)
@@ -513,28 +512,13 @@ def _build_task_window_mask(time_centers_sec, log_frame, pre_buffer_sec: float, 
     return mask
 
 
-def _reference_glue(name: str):
-    """The trial-log parsers are pandas / experiment-log glue of the reference
-    (``src/pipeline/data_integration.py:717,766``), outside this package's scope: delegate to the
-    reference's module when it is importable, otherwise fail when CALLED (not at import)."""
-    def call(*args, **kwargs):
-        import importlib
-        try:
-            mod = importlib.import_module("src.pipeline.data_integration")
-        except Exception as exc:
-            raise ImportError(
-                f"log_frame handling needs the reference's src.pipeline.data_integration.{name} "
-                "(pandas glue, out of scope of this package); pass window masks instead") from exc
-        return getattr(mod, name)(*args, **kwargs)
-    call.__name__ = name
-    return call
-
-
 class _DataIntegrationShim:
-    """Namespace with the two functions ``_build_task_window_mask`` needs; tests and callers may
-    replace them (``monkeypatch.setattr(features.data_integration, ...)`` as the reference's tests do)."""
-    get_all_task_start_ends = staticmethod(_reference_glue("get_all_task_start_ends"))
-    get_qtc_measurement_start_end = staticmethod(_reference_glue("get_qtc_measurement_start_end"))
+    """Namespace with the two trial-log readers ``_build_task_window_mask`` needs (restated in
+    ``experiment_log.py`` after ``src/pipeline/data_integration.py:717,766``); tests and callers may replace them
+    (``monkeypatch.setattr(features.data_integration, ...)`` as the reference's tests do)."""
+    from . import experiment_log as _log
+    get_all_task_start_ends = staticmethod(_log.get_all_task_start_ends)
+    get_qtc_measurement_start_end = staticmethod(_log.get_qtc_measurement_start_end)
 
 
 data_integration = _DataIntegrationShim()
@@ -731,6 +715,17 @@ class _RecordingPipeline:
 
     N_SLOTS = 3
     _pool = None
+    _pinned_free: dict = {}          # (shape, dtype) -> idle pinned host tensors; cudaHostAlloc of a 126 MB
+    # recording costs tens of milliseconds, so the buffers of a finished sweep are kept for the next one
+
+    @classmethod
+    def _pinned(cls, shape, dtype):
+        free = cls._pinned_free.get((tuple(shape), dtype))
+        return free.pop() if free else torch.empty(tuple(shape), dtype=dtype).pin_memory()
+
+    @classmethod
+    def _release(cls, t):
+        cls._pinned_free.setdefault((tuple(t.shape), t.dtype), []).append(t)
 
     def __init__(self, n: int, ne: int, nm: int, out_specs: dict, compute, stage_threads: int = 4):
         self.n, self.ne, self.nm, self.compute, self.stage_threads = n, ne, nm, compute, stage_threads
@@ -740,7 +735,7 @@ class _RecordingPipeline:
             self.slots.append(dict(
                 eeg=torch.empty((n, ne), dtype=torch.float32, device=dev),
                 emg=torch.empty((n, nm), dtype=torch.float32, device=dev),
-                out={k: torch.empty(shape, dtype=dt).pin_memory() for k, (shape, dt) in out_specs.items()},
+                out={k: self._pinned(shape, dt) for k, (shape, dt) in out_specs.items()},
                 stage=None, h2d=None, comp=None, d2h=None, res=None, src=None))
         self.s_up, self.s_comp, self.s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
         cur = torch.cuda.current_stream()
@@ -762,8 +757,8 @@ class _RecordingPipeline:
                 return a
             a = a.numpy()
         if slot["stage"] is None:
-            slot["stage"] = {"eeg": torch.empty((self.n, self.ne), dtype=torch.float32).pin_memory(),
-                             "emg": torch.empty((self.n, self.nm), dtype=torch.float32).pin_memory()}
+            slot["stage"] = {"eeg": self._pinned((self.n, self.ne), torch.float32),
+                             "emg": self._pinned((self.n, self.nm), torch.float32)}
         buf = slot["stage"][key]
         dst, src = buf.numpy(), np.asarray(a)
         nt = self.stage_threads if src.size >= (1 << 20) else 1
@@ -829,6 +824,12 @@ class _RecordingPipeline:
             # also when the consumer stops early: nothing of this sweep may still be running when its buffers are freed
             for st in (self.s_up, self.s_comp, self.s_down):
                 st.synchronize()
+            # staging buffers go back to the pool; the OUTPUT buffers do not - the caller may still hold views of them
+            for slot in self.slots:
+                if slot["stage"] is not None:
+                    for t in slot["stage"].values():
+                        self._release(t)
+                    slot["stage"] = None
 
 
 def _welch_plan(n: int, sampling_freq: float, nperseg: int, noverlap, window: str, detrend, freq_band, segment_starts):

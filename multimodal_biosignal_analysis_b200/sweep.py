@@ -23,13 +23,7 @@ from scipy.stats import t as t_dist
 from . import cbpa as cb
 from . import data_surrogation as dsur
 from . import dist as cdist
-from .channel_layout import EEG_CHANNELS, EEG_POSITIONS
-
-
-def default_spatial_adjacency(ch_names=None):
-    """Delaunay neighbours of the cap layout (``channel_layout.EEG_POSITIONS``) for the listed channels."""
-    names = list(EEG_CHANNELS if ch_names is None else ch_names)
-    return cb.find_ch_adjacency_from_positions(np.array([EEG_POSITIONS[c] for c in names], dtype=np.float64))
+from .channel_layout import EEG_CHANNELS
 
 
 def cmc_surrogate_cbpa_sweep(units, sampling_freq: float, nperseg: int = 2048, noverlap: int | None = None,
@@ -111,7 +105,7 @@ def cmc_surrogate_cbpa_sweep(units, sampling_freq: float, nperseg: int = 2048, n
     if spatial_adjacency is None and contrasts:
         if n_e != len(EEG_CHANNELS):
             raise ValueError("spatial_adjacency is required unless the EEG array holds the 64 channels of the cap")
-        spatial_adjacency = default_spatial_adjacency()
+        spatial_adjacency = cb.default_spatial_adjacency(EEG_CHANNELS)
     out_cbpa = {}
     for cond_a, cond_b in contrasts:
         subj = [s for s in subjects if (s, cond_a) in index and (s, cond_b) in index]

@@ -160,10 +160,43 @@ def main():
         IT_K7_a01=sf.compute_cmc_independence_threshold(7, 0.01),
         fisher_in=np.linspace(0, 1, 11), fisher_out=sf.fisher_atanh_transform(np.linspace(0, 1, 11)),
         inv_in=np.linspace(-3, 3, 13), inv_out=sf.inverse_fisher_atanh(np.linspace(-3, 3, 13)))
+    contrast_golden()
     print("golden vectors written to", OUT)
     for fn in sorted(os.listdir(OUT)):
         print(f"  {fn:28s} {os.path.getsize(os.path.join(OUT, fn)) / 1024:8.1f} KiB")
 
 
+def contrast_golden():
+    """X / channel names / grid of the reference's ``cbpa.build_contrast_array`` (cbpa.py:733-942) on the synthetic
+    study of tests/cbpa_fixture.py.  The reference module imports mne and matplotlib at the top; neither is touched
+    by the contrast front-end, so they are replaced by inert stubs for the import."""
+    import tempfile
+    import warnings
+    from unittest.mock import MagicMock
+    for name in ("mne", "mne.stats", "mne.channels", "mne.io", "matplotlib", "matplotlib.pyplot",
+                 "src.pipeline.visualizations"):
+        sys.modules.setdefault(name, MagicMock())
+    import src.pipeline.cbpa as ref_cbpa          # noqa: E402  (load_reference() put /root/reference on sys.path)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cbpa_fixture as fx                      # noqa: E402
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        root = fx.build_study(os.path.join(tmp, "study"))
+        for name, cfg in fx.configs(ref_cbpa, root, os.path.join(tmp, "out")).items():
+            with warnings.catch_warnings(record=True) as w:
+                warnings.simplefilter("always")
+                X, ch, grid = ref_cbpa.build_contrast_array(cfg)
+            out[f"X_{name}"] = X
+            out[f"ch_{name}"] = np.array(list(ch))
+            out[f"grid_{name}"] = np.asarray(grid)
+            out[f"n_warnings_{name}"] = len([x for x in w if "Skipping" in str(x.message)])
+            print(f"  contrast {name}: X {X.shape}, {out[f'n_warnings_{name}']} skip warnings")
+    np.savez_compressed(os.path.join(OUT, "contrast.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "contrast":
+        load_reference()
+        contrast_golden()
+    else:
+        main()

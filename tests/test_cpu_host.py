@@ -338,3 +338,56 @@ def test_abi_header_is_plain_c():
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
     if shutil.which("g++"):
         subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-x", "c++", hdr], check=True)
+
+
+def test_build_contrast_array_matches_reference_golden(tmp_path):
+    """cbpa.build_contrast_array (reference cbpa.py:733-942 incl. _load_subject_data :282-350) on the synthetic study
+    of tests/cbpa_fixture.py equals, bit for bit, what the UNMODIFIED reference returned for the same files
+    (tests/golden/contrast.npz, written by scripts/make_golden.py): CMC clock-time, CMC phase-normalised and PSD
+    contrasts, with a left-handed subject (mirrored file names), an excluded trial, a subject without condition A
+    and a subject without files (both skipped with a warning)."""
+    import warnings
+    import cbpa_fixture as fx
+    from conftest import golden
+    from multimodal_biosignal_analysis_b200 import cbpa as cb
+    g = golden("contrast.npz")
+    root = fx.build_study(tmp_path / "study")
+    for name, cfg in fx.configs(cb, root, tmp_path / "out").items():
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            X, ch, grid = cb.build_contrast_array(cfg)
+        np.testing.assert_array_equal(X, g[f"X_{name}"])
+        assert list(ch) == [str(c) for c in g[f"ch_{name}"]]
+        np.testing.assert_array_equal(np.asarray(grid), g[f"grid_{name}"])
+        assert len([x for x in w if "Skipping" in str(x.message)]) == int(g[f"n_warnings_{name}"])
+    # the statistics frame is a hard requirement
+    with pytest.raises(FileNotFoundError):
+        cb.build_contrast_array(cb.CBPAConfig(data_root=tmp_path / "nowhere"))
+
+
+def test_experiment_log_readers(tmp_path):
+    """experiment_log.py restates data_integration.get_qtc_measurement_start_end / get_all_task_start_ends
+    (reference data_integration.py:604-955): trigger latency, Actual Start Trigger override, excluded trials."""
+    import pandas as pd
+    import cbpa_fixture as fx
+    from multimodal_biosignal_analysis_b200 import experiment_log as xlog
+    root = fx.build_study(tmp_path / "study", n_subjects=3)
+    log = xlog.fetch_enriched_log_frame(root / "data" / "experiment_results" / "subject_03", verbose=False)
+    assert log.index.tz is not None
+    start, end = xlog.get_qtc_measurement_start_end(log, verbose=False)
+    assert start == (fx.T0 + pd.Timedelta(seconds=2.75)).tz_localize("UTC")
+    spans = xlog.get_all_task_start_ends(log)
+    assert 4 not in spans and len(spans) == fx.N_TRIALS - 1             # trial 4 is marked for exclusion
+    t0, t1 = spans[0]                                                   # music trial: rows with a Task Frequency
+    assert t0 == (fx.T0 + pd.Timedelta(seconds=fx.LEAD_SEC + 2 + 3.25)).tz_localize("UTC")
+    assert t1 == (fx.T0 + pd.Timedelta(seconds=fx.LEAD_SEC + fx.TRIAL_SEC - 1 + 3.25 - 2.0)).tz_localize("UTC")
+    log2 = log.copy()
+    log2.loc[log2.index[7], "Event"] = "Actual Start Trigger"
+    s2, _ = xlog.get_qtc_measurement_start_end(log2, verbose=False)
+    assert s2 == log2.index[7]                                          # no latency on the override
+    log2.loc[log2.index[9], "Event"] = "Start Trigger"
+    with pytest.raises(ValueError):
+        xlog.get_qtc_measurement_start_end(log2, verbose=False)
+    assert xlog.fetch_personal_data(root / "data" / "experiment_results" / "subject_02")["Dominant hand"] == "Left"
+    idx = xlog.add_time_index(start, end, n_timesteps=5)
+    assert len(idx) == 5 and idx[0] == start and idx[-1] == end

@@ -315,3 +315,50 @@ def test_welch_coherence_sweep_can_be_abandoned(cuda_device):
     torch.cuda.synchronize()
     np.testing.assert_array_equal(first, ref)
     np.testing.assert_array_equal(sf.welch_magnitude_squared_coherence(*recs[0], 512.0, nperseg=256).coherence, ref)
+
+
+def test_run_batch_unchanged_call_on_stored_files(cuda_device, tmp_path):
+    """The call of the reference's statistics workflow (statistics_RQ_A_post_hoc_testing_workflow.py:136-172, 465):
+    ``run_batch(CONTRASTS)`` with nothing but CBPAConfig objects.  The contrast comes from stored spectrogram files
+    (tests/cbpa_fixture.py; X is pinned to the reference by tests/test_cpu_host.py), the channel adjacency from the
+    cap layout, the permutations run on the GPU; result dict, .npz and CSVs follow cbpa.py:1051-1056, 1076-1185 and
+    the statistics equal the MNE-algorithm oracle for the same sign table."""
+    import pandas as pd
+    import cbpa_fixture as fx
+    from oracle import cbpa as ocb
+    from multimodal_biosignal_analysis_b200 import cbpa as cb
+    root = fx.build_study(tmp_path / "study")
+    cfgs = fx.configs(cb, root, tmp_path / "out")
+    contrasts = [cfgs["cmc_clock"], cfgs["cmc_phase"]]
+    all_results, combined = cb.run_batch(contrasts)
+    assert len(all_results) == 2
+    for cfg, res in zip(contrasts, all_results):
+        assert set(res) == {"t_obs", "t_thresh", "clusters", "cluster_pv", "H0", "good_cluster_inds", "ch_names",
+                            "time_grid", "cfg", "n_valid_subjects"}
+        X, ch, grid = cb.build_contrast_array(cfg)
+        n_subj, n_times, n_ch = X.shape
+        assert res["n_valid_subjects"] == n_subj == 4 and res["t_obs"].shape == (n_times, n_ch)
+        assert list(res["ch_names"]) == fx.CMC_SUBSET and res["H0"].shape == (cfg.n_permutations,)
+        adj = cb.combine_adjacency(n_times, cb.default_spatial_adjacency(fx.CMC_SUBSET))
+        if cfg.use_phase_normalization:
+            adj = cb._add_phase_wraparound(adj, n_times, n_ch, np.asarray(grid))
+        signs = cb.make_sign_table(cfg.n_permutations, n_subj, np.random.default_rng(cfg.seed), cfg.tail)
+        with np.errstate(all="ignore"):
+            ref = ocb.permutation_cluster_1samp_test(X, signs, float(res["t_thresh"]), cfg.tail, adj)
+        np.testing.assert_array_equal(res["t_obs"], ref["t_obs"])
+        np.testing.assert_array_equal(res["cluster_pv"], ref["cluster_pv"])
+        np.testing.assert_array_equal(res["H0"], ref["H0"])
+        assert len(res["clusters"]) == len(ref["clusters"])
+        for a, b in zip(res["clusters"], ref["clusters"]):
+            np.testing.assert_array_equal(a, b)
+    out = tmp_path / "out"
+    names = sorted(p.name for p in out.iterdir())
+    assert sum(n.endswith("cmc clock.npz") for n in names) == 1 and sum(n.endswith("cmc phase_t_obs.csv") for n in names) == 1
+    comb = [n for n in names if "CBPA Combined Cluster Summary" in n]
+    assert len(comb) == 1
+    df = pd.read_csv(out / comb[0])
+    assert len(df) == sum(len(r["clusters"]) for r in all_results) == len(combined)
+    assert {"hypothesis", "cluster_index", "p_value", "significant", "peak_t", "n_channels", "channels"} <= set(df.columns)
+    # run_cbpa(cfg) alone writes its own per-run cluster summary
+    cb.run_cbpa(cfgs["psd_alpha"])
+    assert any(n.name.endswith("psd alpha_cluster_summary.csv") for n in out.iterdir())

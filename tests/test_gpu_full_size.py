@@ -114,7 +114,10 @@ def test_cfg3_full_size_all_surrogates_vs_fp64_on_channel_subset(cfg2, mode):
     n_diff = int((got != exact).sum())
     print(f"cfg3 {mode}: {n_diff} of {got.size} cells differ from the exact fp64 count "
           f"(max |d count| {int(np.abs(got - exact).max())} of {n_surr})")
-    assert n_diff <= got.size * 0.15 and np.abs(got - exact).max() <= 3
+    # one near tie moves a count by the multiplicity of that surrogate: 1 for phases, the number of surrogates that
+    # drew the same shift (1,000 draws from L - 1 = 209 shifts) for the shift null
+    worst = 3 if mode == "phase" else 3 * int(np.bincount(shifts).max())
+    assert n_diff <= got.size * 0.15 and np.abs(got - exact).max() <= worst
     # the same subset as its own 8 x 8 problem: per-surrogate max statistic vs fp64
     sub = K.csd_msc(_subset_spectra(eeg, starts, ie), _subset_spectra(emg, starts, im))
     _, ms = K.surrogate_null(sub, kmode, 0, n_surr, **kw)
