@@ -193,6 +193,20 @@ CMC_API int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, int
                              const float* coh_obs, uint32_t* exceed, float* max_stat,
                              void* ws2, int64_t ws2_bytes, void* stream);
 
+/* Per-pair null histograms of the phase surrogates [s_begin, s_end) (north star: "null histograms"; they give the
+ * per-pair significance thresholds of BASELINE config 3 - the reference's stand-in is apply_threshold_filtering,
+ * signal_features.py:581-604).  A surrogate coherence C of pair (i, j) at frequency f lands in bin
+ *     floor((sqrt(C) - bin_lo[f][i][j]) * bin_scale[f][i][j])           (not counted outside [0, n_bins))
+ * with bin_lo = NULL read as 0 and bin_scale = NULL as n_bins, i.e. n_bins uniform bins on the |coherency| axis;
+ * per-pair (lo, scale) arrays zoom into a sub-range in a second pass.  Same surrogates as cmc_surrogate_null for
+ * the same (seed, s, l, f); counts are ADDED to hist, so chunks of the surrogate range accumulate.
+ *   hist [F][Ne][Nm][n_bins] uint32 (caller zero-initialises), 2 <= n_bins <= 128; ws / ws2 as for
+ *   cmc_surrogate_null (mode CMC_SURR_PHASE only; CMC_SURR_SHIFT returns CMC_EUNSUPPORTED). */
+CMC_API int cmc_surrogate_null_hist(void* ws, int L, int F, int Ne, int Nm, int mode, uint64_t seed,
+                            int64_t s_begin, int64_t s_end, int f_begin, int f_end, int n_bins,
+                            const float* bin_lo, const float* bin_scale, uint32_t* hist,
+                            void* ws2, int64_t ws2_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K4  cluster-based permutation test: sign-flip t-map -> threshold -> connected-component
  * labelling over a CSR adjacency -> cluster mass -> signed max statistic.  Replaces the

@@ -364,6 +364,165 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------ per-pair null histograms
+// Same GEMM with the loops swapped: CTA work unit = one (frequency, 128-pair tile), inner loop over ALL surrogate
+// panels, so the histograms of the unit's 128 pairs live in shared memory for the whole null and leave the SM once
+// ([128][n_bins] uint32, n_bins <= 128).  The pair tile no longer fits next to the panel, so both operands stream:
+// every ring stage carries the A k-block (16 KB) next to the B k-block (32 KB); B is re-read per panel from L2.
+// Bin of a surrogate coherence C: floor((sqrt(C) - lo[pair]) * scale[pair]); values outside [0, n_bins) are not
+// counted (lo = 0, scale = n_bins: uniform bins on the |coherency| axis; a second pass zooms into the bin pair that
+// brackets a quantile - data_surrogation.py).  One CTA owns a (frequency, pair tile) for the whole launch, so the
+// flush is a plain read-add-write and successive launches (surrogate chunks, zoom passes on a cleared array) add up.
+constexpr int kPhHistStages = 3;
+constexpr int kPhHistMaxBins = 128;
+
+struct PhaseHistParams {
+    int F, MT, NT, KB, n_local, n_pairs, S_pad, R_pad, n_bins;
+    const float* bin_lo;       // [F][n_pairs] or null (0)
+    const float* bin_scale;    // [F][n_pairs] or null (n_bins)
+    uint32_t* hist;            // [F][n_pairs][n_bins]
+};
+
+__global__ void __launch_bounds__(kPhThreads, 1)
+phase_hist_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
+                  const PhaseHistParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    constexpr int kStageBytes = kPhABytes + kPhBBytes;
+    unsigned char* sB = base;                                                      // [kPhHistStages][48 KB]
+    uint32_t* hist_s = reinterpret_cast<uint32_t*>(sB + kPhHistStages * kStageBytes);   // [128][n_bins]
+    float* lo_s = reinterpret_cast<float*>(hist_s + kPhPairs * p.n_bins);          // [128]
+    float* sc_s = lo_s + kPhPairs;                                                 // [128]
+    PhaseBarriers* bars = reinterpret_cast<PhaseBarriers*>(sc_s + kPhPairs);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_units = p.F * p.NT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPhHistStages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars->tmem_full[a], 1);
+            mbar_init(&bars->tmem_empty[a], 4);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&mA);
+        tma_prefetch_desc(&mB);
+    }
+    if (warp == 2) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {                                          // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int un = blockIdx.x; un < n_units; un += gridDim.x) {
+                const int f = un / p.NT, nt = un - f * p.NT;
+                for (int mt = 0; mt < p.MT; ++mt)
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(&bars->empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+                        unsigned char* st = sB + stage * kStageBytes;
+                        tma_load_2d(st, &mA, &bars->full[stage], kb * kPhKB, f * p.S_pad + mt * kPhM);
+                        tma_load_2d(st + kPhABytes, &mB, &bars->full[stage], kb * kPhKB, f * p.R_pad + nt * kPhN);
+                        if (++stage == kPhHistStages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                          // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc_f16(kPhM, kPhN);
+            int stage = 0;
+            uint32_t phase = 0, it = 0;
+            for (int un = blockIdx.x; un < n_units; un += gridDim.x)
+                for (int mt = 0; mt < p.MT; ++mt) {
+                    const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
+                    mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + acc * kPhN;
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(&bars->full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(sB + stage * kStageBytes);
+                        const uint32_t b0 = a0 + kPhABytes;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(d, make_smem_desc_k_sw128(a0 + k * 32), make_smem_desc_k_sw128(b0 + k * 32), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(&bars->empty[stage]);
+                        if (++stage == kPhHistStages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&bars->tmem_full[acc]);
+                    ++it;
+                }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: lane = surrogate row of the panel, columns = the unit's 128 pairs =====
+        const int q = warp - 4;
+        const int te = threadIdx.x - 128;
+        const float nb = (float)p.n_bins;
+        uint32_t it = 0;
+        for (int un = blockIdx.x; un < n_units; un += gridDim.x) {
+            const int f = un / p.NT, nt = un - f * p.NT;
+            const int pair_t = nt * kPhPairs + te;
+            const bool pair_ok = pair_t < p.n_pairs;
+            lo_s[te] = (pair_ok && p.bin_lo) ? __ldg(p.bin_lo + (int64_t)f * p.n_pairs + pair_t) : 0.f;
+            sc_s[te] = (pair_ok && p.bin_scale) ? __ldg(p.bin_scale + (int64_t)f * p.n_pairs + pair_t) : nb;
+            for (int i = te; i < kPhPairs * p.n_bins; i += 128) hist_s[i] = 0u;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int mt = 0; mt < p.MT; ++mt) {
+                const bool s_ok = mt * kPhM + te < p.n_local;
+                const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
+                mbar_wait(&bars->tmem_full[acc], accphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * kPhN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t re[32], im[32];
+                    tmem_ld_32x32(taddr + ch * 32, re);
+                    tmem_ld_32x32(taddr + kPhPairs + ch * 32, im);
+                    tmem_ld_wait();
+                    if (s_ok) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float a = __uint_as_float(re[c]), b = __uint_as_float(im[c]);
+                            // |coherency| in [0, 1): C = 1 is binned with the largest float below 1
+                            const float v = fminf(sqrtf((a * a + b * b) * kZUnscaleSq), 0.99999994f);
+                            const float x = (v - lo_s[ch * 32 + c]) * sc_s[ch * 32 + c];
+                            // x >= 0 first: the float -> int conversion of a negative value must not wrap into range
+                            if (x >= 0.f && x < nb) atomicAdd(&hist_s[(ch * 32 + c) * p.n_bins + (int)x], 1u);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+                ++it;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // flush: rows of padding pairs (beyond n_pairs) hold counts of the zero rows of Z and are dropped
+            const int rows = min(kPhPairs, p.n_pairs - nt * kPhPairs);
+            uint32_t* g = p.hist + ((int64_t)f * p.n_pairs + (int64_t)nt * kPhPairs) * p.n_bins;
+            for (int i = te; i < rows * p.n_bins; i += 128) {
+                const uint32_t v = hist_s[i];
+                if (v) g[i] += v;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 __global__ void phase_gather_kernel(const uint32_t* __restrict__ max_u, int64_t n, float* __restrict__ max_stat) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) max_stat[i] = __uint_as_float(max_u[i]);
@@ -403,39 +562,26 @@ int64_t phase_workspace_bytes(int L, int F, int Ne, int Nm, int64_t n_surr) {
     return phase_layout(L, F, Ne, Nm, n_surr).total;
 }
 
-int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
-                         int f_begin, int f_end, const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2,
-                         int64_t ws2_bytes, cudaStream_t st) {
-    const int64_t n = s_end - s_begin;
+// Operand generation + GEMM launch per frequency chunk, shared by the exceedance null and the histogram pass.
+// `launch(fc, f0, mA, mB, y)` enqueues the GEMM kernel of one chunk.
+template <typename Launch>
+static int phase_run(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t n, int f_begin,
+                     int f_end, void* ws2, int64_t ws2_bytes, cudaStream_t st, const PhaseLayout& y, Launch launch) {
     CMC_REQUIRE(n < (1ll << 31) - 256, "cmc_surrogate_null: too many surrogates in one call");
     const CsdLayout cy = csd_layout(L, F, Ne, Nm);
-    const PhaseLayout y = phase_layout(L, F, Ne, Nm, n);
     if (ws2_bytes < y.total) {
         set_error("cmc_surrogate_null: workspace %lld < %lld bytes", (long long)ws2_bytes, (long long)y.total);
         return CMC_EWORKSPACE;
     }
     CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws2) & 255) == 0, "cmc_surrogate_null: workspace must be 256-byte aligned");
-    const size_t tail_bytes = kPhPairs * 8 + sizeof(PhaseBarriers) + 16;
-    size_t smem = 1024 + (size_t)y.KB * kPhABytes + kPhStages * kPhBBytes + tail_bytes;
-    const bool stream_a = smem > 227 * 1024;                    // 2L > 512: the panel no longer fits next to the ring
-    if (stream_a) smem = 1024 + (size_t)kPhStagesStream * (kPhABytes + kPhBBytes) + tail_bytes;
-    CMC_REQUIRE((size_t)y.KPb * 4 <= 48 * 1024, "cmc_surrogate_null: L=%d too long (2L <= 12288)", L);
+    CMC_REQUIRE((size_t)L * 8 <= 48 * 1024, "cmc_surrogate_null: L=%d too long (2L <= 12288)", L);
     const uint32_t* table;
     int rc = get_phase_table(&table);
     if (rc) return rc;
     const unsigned char* w = static_cast<const unsigned char*>(ws);
     unsigned char* w2 = static_cast<unsigned char*>(ws2);
-    uint32_t* max_u = reinterpret_cast<uint32_t*>(w2 + y.off_max);
     __half* A = reinterpret_cast<__half*>(w2 + y.off_A);
     __half* Z = reinterpret_cast<__half*>(w2 + y.off_Z);
-    rc = check_cuda(cudaMemsetAsync(max_u, 0, (size_t)y.S_pad * 4, st), "memset(max_u)");
-    if (rc) return rc;
-    auto gemm = stream_a ? phase_gemm_kernel<true> : phase_gemm_kernel<false>;
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(gemm), smem);
-    if (rc) return rc;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     for (int f0 = f_begin; f0 < f_end; f0 += y.f_chunk) {
         const int fc = f_end - f0 < y.f_chunk ? f_end - f0 : y.f_chunk;
         if (y.n_pairs_pad != y.n_pairs) {
@@ -458,19 +604,82 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
         CUtensorMap mA, mB;
         if ((rc = make_kmajor_map(&mA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y.KPb, (int64_t)fc * y.S_pad, kPhM))) return rc;
         if ((rc = make_kmajor_map(&mB, Z, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y.KPb, (int64_t)fc * y.R_pad, kPhN))) return rc;
-        PhaseParams p{};
-        p.F = fc; p.MT = y.MT; p.NT = y.NT; p.KB = y.KB; p.n_local = (int)n; p.n_pairs = y.n_pairs;
-        p.S_pad = y.S_pad; p.R_pad = y.R_pad;
-        p.coh_obs = coh_obs + (int64_t)f0 * y.n_pairs;
-        p.exceed = exceed + (int64_t)f0 * y.n_pairs;
-        p.max_u = max_u;
-        const int n_panels = fc * y.MT;
-        gemm<<<n_panels < sms ? n_panels : sms, kPhThreads, smem, st>>>(mA, mB, p);
-        CMC_CHECK_LAUNCH("phase_gemm_kernel");
+        if ((rc = launch(fc, f0, mA, mB))) return rc;
     }
+    return CMC_OK;
+}
+
+static int sm_count() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
+                         int f_begin, int f_end, const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2,
+                         int64_t ws2_bytes, cudaStream_t st) {
+    const int64_t n = s_end - s_begin;
+    const PhaseLayout y = phase_layout(L, F, Ne, Nm, n);
+    const size_t tail_bytes = kPhPairs * 8 + sizeof(PhaseBarriers) + 16;
+    size_t smem = 1024 + (size_t)y.KB * kPhABytes + kPhStages * kPhBBytes + tail_bytes;
+    const bool stream_a = smem > 227 * 1024;                    // K > 512: the panel no longer fits next to the ring
+    if (stream_a) smem = 1024 + (size_t)kPhStagesStream * (kPhABytes + kPhBBytes) + tail_bytes;
+    auto gemm = stream_a ? phase_gemm_kernel<true> : phase_gemm_kernel<false>;
+    int rc = ensure_smem_attr(reinterpret_cast<const void*>(gemm), smem);
+    if (rc) return rc;
+    if (ws2_bytes < y.total) {
+        set_error("cmc_surrogate_null: workspace %lld < %lld bytes", (long long)ws2_bytes, (long long)y.total);
+        return CMC_EWORKSPACE;
+    }
+    uint32_t* max_u = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(ws2) + y.off_max);
+    rc = check_cuda(cudaMemsetAsync(max_u, 0, (size_t)y.S_pad * 4, st), "memset(max_u)");
+    if (rc) return rc;
+    const int sms = sm_count();
+    rc = phase_run(ws, L, F, Ne, Nm, seed, s_begin, n, f_begin, f_end, ws2, ws2_bytes, st, y,
+                   [&](int fc, int f0, const CUtensorMap& mA, const CUtensorMap& mB) -> int {
+                       PhaseParams p{};
+                       p.F = fc; p.MT = y.MT; p.NT = y.NT; p.KB = y.KB; p.n_local = (int)n; p.n_pairs = y.n_pairs;
+                       p.S_pad = y.S_pad; p.R_pad = y.R_pad;
+                       p.coh_obs = coh_obs + (int64_t)f0 * y.n_pairs;
+                       p.exceed = exceed + (int64_t)f0 * y.n_pairs;
+                       p.max_u = max_u;
+                       const int n_panels = fc * y.MT;
+                       gemm<<<n_panels < sms ? n_panels : sms, kPhThreads, smem, st>>>(mA, mB, p);
+                       CMC_CHECK_LAUNCH("phase_gemm_kernel");
+                       return CMC_OK;
+                   });
+    if (rc) return rc;
     phase_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(max_u, n, max_stat);
     CMC_CHECK_LAUNCH("phase_gather_kernel");
     return CMC_OK;
+}
+
+int phase_surrogate_hist(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
+                         int f_begin, int f_end, int n_bins, const float* bin_lo, const float* bin_scale,
+                         uint32_t* hist, void* ws2, int64_t ws2_bytes, cudaStream_t st) {
+    const int64_t n = s_end - s_begin;
+    CMC_REQUIRE(n_bins >= 2 && n_bins <= kPhHistMaxBins, "cmc_surrogate_null_hist: n_bins must be in [2, %d]",
+                kPhHistMaxBins);
+    const PhaseLayout y = phase_layout(L, F, Ne, Nm, n);
+    const size_t smem = 1024 + (size_t)kPhHistStages * (kPhABytes + kPhBBytes) + (size_t)kPhPairs * n_bins * 4 +
+                        kPhPairs * 8 + sizeof(PhaseBarriers) + 16;
+    int rc = ensure_smem_attr(reinterpret_cast<const void*>(phase_hist_kernel), smem);
+    if (rc) return rc;
+    const int sms = sm_count();
+    return phase_run(ws, L, F, Ne, Nm, seed, s_begin, n, f_begin, f_end, ws2, ws2_bytes, st, y,
+                     [&](int fc, int f0, const CUtensorMap& mA, const CUtensorMap& mB) -> int {
+                         PhaseHistParams p{};
+                         p.F = fc; p.MT = y.MT; p.NT = y.NT; p.KB = y.KB; p.n_local = (int)n; p.n_pairs = y.n_pairs;
+                         p.S_pad = y.S_pad; p.R_pad = y.R_pad; p.n_bins = n_bins;
+                         p.bin_lo = bin_lo ? bin_lo + (int64_t)f0 * y.n_pairs : nullptr;
+                         p.bin_scale = bin_scale ? bin_scale + (int64_t)f0 * y.n_pairs : nullptr;
+                         p.hist = hist + (int64_t)f0 * y.n_pairs * n_bins;
+                         const int n_units = fc * y.NT;
+                         phase_hist_kernel<<<n_units < sms ? n_units : sms, kPhThreads, smem, st>>>(mA, mB, p);
+                         CMC_CHECK_LAUNCH("phase_hist_kernel");
+                         return CMC_OK;
+                     });
 }
 
 }  // namespace cmc

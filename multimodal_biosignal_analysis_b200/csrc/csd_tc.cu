@@ -381,6 +381,10 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
                          int f_begin, int f_end, const float* coh_obs, uint32_t* exceed, float* max_stat, void* ws2,
                          int64_t ws2_bytes, cudaStream_t st);
 
+int phase_surrogate_hist(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
+                         int f_begin, int f_end, int n_bins, const float* bin_lo, const float* bin_scale,
+                         uint32_t* hist, void* ws2, int64_t ws2_bytes, cudaStream_t st);
+
 }  // namespace cmc
 
 extern "C" int64_t cmc_csd_workspace_bytes(int L, int F, int Ne, int Nm) {
@@ -520,4 +524,23 @@ extern "C" int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, 
     shift_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shifts, n, n_pos, max_u, max_stat);
     CMC_CHECK_LAUNCH("shift_gather_kernel");
     return CMC_OK;
+}
+
+extern "C" int cmc_surrogate_null_hist(void* ws, int L, int F, int Ne, int Nm, int mode, uint64_t seed,
+                                       int64_t s_begin, int64_t s_end, int f_begin, int f_end, int n_bins,
+                                       const float* bin_lo, const float* bin_scale, uint32_t* hist, void* ws2,
+                                       int64_t ws2_bytes, void* stream) {
+    using namespace cmc;
+    CMC_REQUIRE(ws && hist && ws2, "cmc_surrogate_null_hist: null pointer");
+    CMC_REQUIRE(s_end >= s_begin, "cmc_surrogate_null_hist: bad surrogate range");
+    CMC_REQUIRE(0 <= f_begin && f_begin <= f_end && f_end <= F, "cmc_surrogate_null_hist: bad frequency range [%d, %d)",
+                f_begin, f_end);
+    if (mode != CMC_SURR_PHASE) {
+        set_error("cmc_surrogate_null_hist: histograms are built for phase surrogates only (a shift null has at most "
+                  "L - 1 distinct values per pair)");
+        return CMC_EUNSUPPORTED;
+    }
+    if (s_end == s_begin || f_begin == f_end) return CMC_OK;
+    return phase_surrogate_hist(ws, L, F, Ne, Nm, seed, s_begin, s_end, f_begin, f_end, n_bins, bin_lo, bin_scale, hist,
+                                ws2, ws2_bytes, static_cast<cudaStream_t>(stream));
 }

@@ -241,6 +241,37 @@ def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: 
     return exceed, max_stat
 
 
+def surrogate_null_hist(csd: PooledCsd, s_begin: int, s_end: int, seed: int = 0, n_bins: int = 128,
+                        bin_lo: torch.Tensor | None = None, bin_scale: torch.Tensor | None = None,
+                        hist: torch.Tensor | None = None, f_range: tuple[int, int] | None = None) -> torch.Tensor:
+    """Per-pair histograms of the phase surrogates [s_begin, s_end): int32 (F, Ne, Nm, n_bins), accumulated into
+    ``hist`` when given.  Bin = floor((sqrt(C_s) - bin_lo) * bin_scale) with per-pair float32 (F, Ne, Nm) arrays
+    (defaults 0 and n_bins: uniform bins on the |coherency| axis); values outside [0, n_bins) are not counted."""
+    L, F, Ne, Nm = csd.dims
+    dev = csd.coh.device
+    lib = _lib.load()
+    csd.ensure_operands()
+    if hist is None:
+        hist = torch.zeros((F, Ne, Nm, n_bins), dtype=torch.int32, device=dev)
+    elif hist.shape != (F, Ne, Nm, n_bins) or not hist.is_contiguous():
+        raise ValueError("hist must be contiguous (F, Ne, Nm, n_bins)")
+    for t, name in ((bin_lo, "bin_lo"), (bin_scale, "bin_scale")):
+        if t is not None:
+            _need_cuda(t, name, torch.float32)
+            if t.shape != (F, Ne, Nm) or not t.is_contiguous():
+                raise ValueError(f"{name} must be contiguous (F, Ne, Nm)")
+    ws2_bytes = int(lib.cmc_surrogate_workspace_bytes(L, F, Ne, Nm, SURR_PHASE, s_end - s_begin))
+    if ws2_bytes < 0:
+        _lib.check(ws2_bytes, "cmc_surrogate_workspace_bytes")
+    ws2 = torch.empty(max(ws2_bytes, 16), dtype=torch.uint8, device=dev)
+    f_begin, f_end = (0, F) if f_range is None else (int(f_range[0]), int(f_range[1]))
+    rc = lib.cmc_surrogate_null_hist(csd.ws.data_ptr(), L, F, Ne, Nm, SURR_PHASE, seed, s_begin, s_end, f_begin, f_end,
+                                     n_bins, _lib.ptr(bin_lo), _lib.ptr(bin_scale), hist.data_ptr(), ws2.data_ptr(),
+                                     ws2_bytes, _lib.current_stream())
+    _lib.check(rc, "cmc_surrogate_null_hist")
+    return hist
+
+
 # ----------------------------------------------------------------------------- K4
 def _cbpa_args(X, indptr, indices):
     _need_cuda(X, "X", torch.float64)

@@ -338,7 +338,8 @@ def test_run_batch_unchanged_call_on_stored_files(cuda_device, tmp_path):
         X, ch, grid = cb.build_contrast_array(cfg)
         n_subj, n_times, n_ch = X.shape
         assert res["n_valid_subjects"] == n_subj == 4 and res["t_obs"].shape == (n_times, n_ch)
-        assert list(res["ch_names"]) == fx.CMC_SUBSET and res["H0"].shape == (cfg.n_permutations,)
+        # 4 subjects, two-tailed: all 2^3 - 1 = 7 sign patterns fit into 64 permutations -> exact test, like MNE
+        assert list(res["ch_names"]) == fx.CMC_SUBSET and res["H0"].shape == (8,)
         adj = cb.combine_adjacency(n_times, cb.default_spatial_adjacency(fx.CMC_SUBSET))
         if cfg.use_phase_normalization:
             adj = cb._add_phase_wraparound(adj, n_times, n_ch, np.asarray(grid))

@@ -333,3 +333,54 @@ def test_direct_path_segment_count_edges(cuda_device, L, ne, nm, F):
     assert torch.max(torch.abs(got.sxy.to(torch.complex128) - sxy) / torch.sqrt(sxx[:, :, None] * syy[:, None, :])).item() < 1e-5
     torch.testing.assert_close(got.sxx.double(), sxx, rtol=1e-5, atol=0)
     torch.testing.assert_close(got.syy.double(), syy, rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("n_epochs,passes,tol", [(6, 2, 1e-4), (6, 3, 1e-5), (14, 3, 1e-4)])
+def test_per_pair_null_thresholds_match_fp64_quantiles(cuda_device, n_epochs, passes, tol):
+    """BASELINE config 3 "significance thresholds": the per-pair (1 - alpha) quantile of the phase-surrogate null from
+    the device histograms (cmc_surrogate_null_hist, zoom passes) against np.quantile over the fp64 surrogate
+    coherences of oracle/surrogate.py; the first-pass histograms against np.histogram of the same stack.
+    n_epochs = 6: L = 42 (error-compensated operands); n_epochs = 14: L = 98 (single FP16 term)."""
+    from multimodal_biosignal_analysis_b200 import kernels as K, data_surrogation as ds
+    N, hop, ep, ne, nm, n_surr, seed, alpha = 512, 256, 2048, 6, 10, 300, 21, 0.05
+    eeg, emg = syn.make_epochs(n_epochs, ep, ne, nm, seed=77)
+    emg[:, 0] += 0.7 * eeg[:, 0]                                     # one strongly coupled pair (large |S| terms)
+    starts = syn.epoch_segment_starts(n_epochs, ep, N, hop)
+    X, Y = _welch_spectra(eeg, emg, starts, N, 2, 13)
+    res = K.csd_msc(X, Y)
+    Xo, Yo = _oracle_spectra(eeg, emg, starts, N, 2, 13)
+    Xw, _ = osur.whiten(Xo)
+    Yw, _ = osur.whiten(Yo)
+    cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed)          # (S, F, Ne, Nm) fp64
+    want = np.quantile(cs, 1.0 - alpha, axis=0)
+    thr, hist = ds.null_quantile_thresholds(res, n_surr, seed, 1.0 - alpha, passes=passes, n_bins=128)
+    got = thr.cpu().numpy()
+    err = np.abs(got - want)
+    assert err.max() < tol, f"max threshold error {err.max():.2e}"
+    # first-pass histograms: 128 uniform bins on the |coherency| axis; only values within rounding of an edge move
+    h = hist.cpu().numpy().astype(np.int64)
+    assert h.shape == cs.shape[1:] + (128,) and np.all(h.sum(axis=-1) == n_surr)
+    bins = np.minimum((np.sqrt(cs) * 128).astype(np.int64), 127)
+    ref = np.zeros_like(h)
+    f_i, e_i, m_i = np.meshgrid(*[np.arange(k) for k in cs.shape[1:]], indexing="ij")
+    for s in range(n_surr):
+        np.add.at(ref, (f_i, e_i, m_i, bins[s]), 1)
+    assert np.abs(h - ref).sum() <= 0.004 * n_surr * ref[..., 0].size
+    assert np.abs(np.cumsum(h, -1) - np.cumsum(ref, -1)).max() <= 2
+    # chunks of the surrogate range accumulate to the same histogram
+    h2 = K.surrogate_null_hist(res, 0, 170, seed=seed)
+    h2 = K.surrogate_null_hist(res, 170, n_surr, seed=seed, hist=h2)
+    np.testing.assert_array_equal(h2.cpu().numpy(), hist.cpu().numpy())
+    # public API: thresholds + significance mask next to the exceedance p-values
+    class _P:                                                        # the slice of PooledCoherence the API reads
+        device_result, coherence, freqs = res, res.coh, np.arange(res.coh.shape[0])
+    out = ds.phase_randomised_surrogate_null(_P, n_surr, seed=seed, alpha=alpha, thresholds=True,
+                                             threshold_passes=passes)
+    np.testing.assert_allclose(out["threshold"], got, rtol=0, atol=1e-7)
+    coh = res.coh.cpu().numpy()
+    np.testing.assert_array_equal(out["significant"], coh > out["threshold"])
+    # a pair above its threshold has few exceedances, and vice versa (alpha n = 15 of 300; ties at the edge excluded)
+    clear = np.abs(coh - out["threshold"]) > 1e-3
+    assert np.all((out["exceed"][clear & out["significant"]] <= 15))
+    assert np.all((out["exceed"][clear & ~out["significant"]] >= 15))
+    assert out["significant"][:, 0, 0].all()
