@@ -164,8 +164,8 @@ def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int 
     Philox4x32-10(seed; s, l, f) so any sharding of the surrogate index gives the same null.
 
     ``thresholds=True`` adds the per-pair significance thresholds of BASELINE config 3: ``threshold[f, i, j]`` =
-    the (1 - alpha) quantile (numpy's linear definition) of the pair's own null coherences, from per-pair null
-    histograms accumulated on the device (:func:`null_quantile_thresholds`), and ``significant = coherence >
+    the (1 - alpha) quantile (order statistic, numpy ``method="higher"``) of the pair's own null coherences, from
+    per-pair null histograms accumulated on the device (:func:`null_quantile_thresholds`), and ``significant = coherence >
     threshold`` - the surrogate counterpart of the reference's analytic ``apply_threshold_filtering``
     (signal_features.py:581-604).  ``return_hist=True`` also returns the first-pass histograms
     (``null_hist`` (F, Ne, Nm, hist_bins) over uniform |coherency| bins, ``null_hist_edges``)."""
@@ -188,25 +188,26 @@ def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int 
 
 def null_quantile_thresholds(csd, n_surrogates: int, seed: int, q: float, passes: int = 2, n_bins: int = 128,
                              shard: str = "auto"):
-    """Per-pair q-quantile of the phase-surrogate null, ``np.quantile(C_s[:, f, i, j], q)`` for every (f, i, j),
-    without ever materialising the (n_surrogates, F, Ne, Nm) stack: pass 1 histograms every pair's |coherency|
-    into ``n_bins`` uniform bins; every further pass re-runs the null with per-pair bins zoomed into the two
-    neighbouring bins that hold the order statistics x[k], x[k + 1] bracketing the quantile (k = floor(q (n - 1))),
-    so after p passes they are known to +-(2 / n_bins)^p / 4 on the |coherency| axis (p = 2, 128 bins: a threshold
-    error <= 1.3e-4 sqrt(C), i.e. ~2e-5 at typical null levels; p = 3 is exact to 1e-6).  Each pass costs one GEMM
-    sweep of the null (``cmc_surrogate_null_hist``).  Multi-rank: ranks split the frequency axis and the threshold
-    slices are summed.  Returns (threshold float32 (F, Ne, Nm) CUDA tensor, first-pass histogram)."""
+    """Per-pair q-quantile of the phase-surrogate null for every (f, i, j) without ever materialising the
+    (n_surrogates, F, Ne, Nm) stack.  The quantile is an ORDER STATISTIC of the pair's surrogate coherences,
+    ``np.quantile(C_s[:, f, i, j], q, method="higher")`` = the k-th smallest with k = ceil(q (n - 1)) - the
+    conservative choice for a significance threshold (at most (1 - q) n surrogates lie above it) and an actually
+    observed null value.  Pass 1 histograms every pair's |coherency| into ``n_bins`` uniform bins; every further
+    pass re-runs the null with per-pair bins zoomed into the bin that holds the k-th value, so after p passes it is
+    known to +-n_bins^-p / 2 on the |coherency| axis (p = 2, 128 bins: threshold error <= 6.2e-5 sqrt(C); p = 3:
+    5e-7).  Each pass costs one GEMM sweep of the null (``cmc_surrogate_null_hist``).  Multi-rank: ranks split the
+    frequency axis and the threshold slices are summed.  Returns (threshold float32 (F, Ne, Nm) CUDA tensor,
+    first-pass histogram int32 (F, Ne, Nm, n_bins))."""
     if passes < 1:
         raise ValueError("passes must be >= 1")
     L, F, Ne, Nm = csd.dims
     dev = csd.coh.device
     n = int(n_surrogates)
+    if n < 1:
+        raise ValueError("n_surrogates must be >= 1")
     _, _, f_range, by_freq = _plan(n, F, shard if shard != "surrogate" else "frequency")
     fb, fe = f_range if by_freq else (0, F)
-    h = q * (n - 1)
-    k0 = int(np.floor(h))
-    frac = float(h - k0)
-    k1 = min(k0 + 1, n - 1)
+    k = min(int(np.ceil(q * (n - 1) - 1e-9)), n - 1)        # 0-based rank of the order statistic
     lo = torch.zeros((F, Ne, Nm), dtype=torch.float32, device=dev)
     width = 1.0                                              # window [lo, lo + width) on the |coherency| axis
     below = torch.zeros((F, Ne, Nm), dtype=torch.int32, device=dev)      # surrogates below the window
@@ -218,21 +219,16 @@ def null_quantile_thresholds(csd, n_surrogates: int, seed: int, q: float, passes
         if first is None:
             first = hist
         cum = torch.cumsum(hist, dim=-1, dtype=torch.int32) + below[..., None]
-        b0 = (cum > k0).to(torch.uint8).argmax(dim=-1)                       # bin of x[k0] (0 when never reached)
-        found1 = cum[..., -1] > k1
-        b1 = torch.where(found1, (cum > k1).to(torch.uint8).argmax(dim=-1), torch.full_like(b0, n_bins))
+        b = (cum > k).to(torch.uint8).argmax(dim=-1)                         # bin of the k-th smallest value
         bw = width / n_bins
         if p + 1 < passes:
-            prev = torch.gather(cum, -1, (b0 - 1).clamp(min=0)[..., None])[..., 0]
-            below = torch.where(b0 > 0, prev, below)
-            lo = lo + b0.to(torch.float32) * bw
-            width = 2.0 * bw
-            del cum, hist
-    x0 = lo + (b0.to(torch.float32) + 0.5) * bw
-    # x[k0 + 1] beyond the window: its lower bound is the window's upper edge
-    x1 = torch.where(found1, lo + (b1.to(torch.float32) + 0.5) * bw, lo + width)
-    c0, c1 = x0 * x0, x1 * x1
-    thr = (c0 + frac * (c1 - c0)).clamp(max=1.0)
+            prev = torch.gather(cum, -1, (b - 1).clamp(min=0)[..., None])[..., 0]
+            below = torch.where(b > 0, prev, below)
+            lo = lo + b.to(torch.float32) * bw
+            width = bw
+        del cum
+    x = lo + (b.to(torch.float32) + 0.5) * bw if passes > 1 else (b.to(torch.float32) + 0.5) * bw
+    thr = (x * x).clamp(max=1.0)
     if by_freq:
         mask = torch.zeros(F, dtype=torch.bool, device=dev)
         mask[fb:fe] = True

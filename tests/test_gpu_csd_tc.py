@@ -335,7 +335,7 @@ def test_direct_path_segment_count_edges(cuda_device, L, ne, nm, F):
     torch.testing.assert_close(got.syy.double(), syy, rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("n_epochs,passes,tol", [(6, 2, 1e-4), (6, 3, 1e-5), (14, 3, 1e-4)])
+@pytest.mark.parametrize("n_epochs,passes,tol", [(6, 2, 6e-5), (6, 3, 5e-6), (14, 3, 1e-4)])
 def test_per_pair_null_thresholds_match_fp64_quantiles(cuda_device, n_epochs, passes, tol):
     """BASELINE config 3 "significance thresholds": the per-pair (1 - alpha) quantile of the phase-surrogate null from
     the device histograms (cmc_surrogate_null_hist, zoom passes) against np.quantile over the fp64 surrogate
@@ -352,7 +352,7 @@ def test_per_pair_null_thresholds_match_fp64_quantiles(cuda_device, n_epochs, pa
     Xw, _ = osur.whiten(Xo)
     Yw, _ = osur.whiten(Yo)
     cs = osur.surrogate_coherence(Xw, Yw, "phase", np.arange(n_surr), seed=seed)          # (S, F, Ne, Nm) fp64
-    want = np.quantile(cs, 1.0 - alpha, axis=0)
+    want = np.quantile(cs, 1.0 - alpha, axis=0, method="higher")
     thr, hist = ds.null_quantile_thresholds(res, n_surr, seed, 1.0 - alpha, passes=passes, n_bins=128)
     got = thr.cpu().numpy()
     err = np.abs(got - want)
