@@ -223,8 +223,11 @@ CMC_API int cmc_surrogate_null_hist(void* ws, int L, int F, int Ne, int Nm, int 
  * k = k-th cluster in MNE order: t > thr clusters first, each group by smallest flat
  * index) and per-cluster masses (caller sizes mass_fixed / mass_f64 to n_tests).
  *   ws     scratch of cmc_cbpa_workspace_bytes() for BOTH calls, 16-byte aligned: labelling
- *          scratch plus a re-tiled copy of X (rebuilt on every call; calls sharing a stream
- *          may share one workspace)
+ *          scratch plus a re-tiled copy of X (calls sharing a stream may share one workspace).
+ *          cmc_cbpa_permute accepts X == NULL when ws still holds the tiled copy written by an
+ *          earlier cmc_cbpa_observed / cmc_cbpa_permute call for the same data: the re-tile pass
+ *          is then skipped.  Permutations beyond a CTA's first are claimed from a device counter
+ *          kept in ws, so ragged permutation costs balance themselves.
  * ---------------------------------------------------------------------------------- */
 CMC_API int64_t cmc_cbpa_workspace_bytes(int n_subj, int n_tests);
 CMC_API int cmc_cbpa_permute(const double* X, int n_subj, int n_tests,

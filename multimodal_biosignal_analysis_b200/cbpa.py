@@ -216,10 +216,12 @@ def permutation_cluster_1samp_test(X, threshold=None, n_permutations: int = 1024
     Xd = torch.from_numpy(Xf).to(dev)
     indptr = torch.from_numpy(adj.indptr.astype(np.int32)).to(dev)
     indices = torch.from_numpy(adj.indices.astype(np.int32)).to(dev)
-    t_obs_d, labels_d, mass_d, n_clusters = K.cbpa_observed(Xd, threshold, tail, indptr, indices)
+    ws = K.cbpa_workspace(Xd)                                    # both calls share the re-tiled copy of X
+    t_obs_d, labels_d, mass_d, n_clusters = K.cbpa_observed(Xd, threshold, tail, indptr, indices, ws=ws)
     n_rows = signs.shape[0]
     begin, end = cdist.shard_range(n_rows)
-    h0_local = K.cbpa_permute(Xd, torch.from_numpy(signs).to(dev), begin, end, threshold, tail, indptr, indices)
+    h0_local = K.cbpa_permute(Xd, torch.from_numpy(signs).to(dev), begin, end, threshold, tail, indptr, indices,
+                              ws=ws, tiled=True)
     h0_perm = cdist.all_gather_ranges(h0_local, n_rows).cpu().numpy()
     mass = mass_d.cpu().numpy()
     if n_clusters:

@@ -176,7 +176,7 @@ cbpa_kernel(const double* __restrict__ XT, int n_subj, int n_tests, const int8_t
             int64_t n_perm, double thr, int tail, const int32_t* __restrict__ indptr,
             const int32_t* __restrict__ indices, long long* __restrict__ h0,
             double* __restrict__ t_obs, int32_t* __restrict__ root_out, long long* __restrict__ mass_out,
-            int list_cap) {
+            int list_cap, unsigned* __restrict__ claim) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     long long* mass = reinterpret_cast<long long*>(smem_raw);                 // [n_tests]
     int* parent = reinterpret_cast<int*>(mass + n_tests);                      // [n_tests]
@@ -187,14 +187,18 @@ cbpa_kernel(const double* __restrict__ XT, int n_subj, int n_tests, const int8_t
     __shared__ long long red_abs[kCbpaThreads / 32];
     __shared__ long long red_val[kCbpaThreads / 32];
     __shared__ int n_supra;
+    __shared__ long long next_p;
     const int tid = threadIdx.x;
 
 #ifdef CMC_CBPA_PROFILE
     long long tick_ = clock64();
 #endif
-    for (int64_t p = blockIdx.x; p < n_perm; p += gridDim.x) {
+    // the first permutation of a CTA is static, every further one is claimed from a device counter (zeroed by the
+    // host before the launch): CTAs that drew cheap permutations (few supra-threshold nodes) take more of them
+    for (int64_t p = blockIdx.x; p < n_perm;) {
         __syncthreads();
         CBPA_TICK(0);
+        if (tid == 0) next_p = claim ? (long long)gridDim.x + atomicAdd(claim, 1u) : (long long)p + gridDim.x;
         for (int s = tid; s < n_subj; s += kCbpaThreads) {
             const int sv = OBSERVED ? 1 : (int)signs[p * n_subj + s];
             sg[s] = (double)sv;
@@ -319,6 +323,7 @@ cbpa_kernel(const double* __restrict__ XT, int n_subj, int n_tests, const int8_t
             h0[p] = best_abs < 0 ? 0 : best_val;
         }
         CBPA_TICK(4);
+        p = next_p;                 // written before this iteration's first barrier, read after its last one
     }
 }
 
@@ -381,9 +386,8 @@ static int cbpa_list_cap(int n_subj, int n_tests) {
     return (int)(cap < (size_t)n_tests ? cap : (size_t)n_tests);
 }
 
-static int cbpa_check(const double* X, int n_subj, int n_tests, const int32_t* indptr, const int32_t* indices,
-                      int tail, double thr) {
-    CMC_REQUIRE(X && indptr && indices, "cmc_cbpa: null pointer");
+static int cbpa_check(int n_subj, int n_tests, const int32_t* indptr, const int32_t* indices, int tail, double thr) {
+    CMC_REQUIRE(indptr && indices, "cmc_cbpa: null pointer");
     CMC_REQUIRE(n_subj >= 2, "cmc_cbpa: need at least 2 subjects");
     CMC_REQUIRE(n_tests >= 1 && n_tests <= kCbpaMaxTests, "cmc_cbpa: n_tests=%d outside [1, %d]", n_tests,
                 kCbpaMaxTests);
@@ -406,7 +410,9 @@ namespace cmc {
 static int64_t cbpa_labels_bytes(int n_tests) {
     return ((int64_t)n_tests * 16 + 256 + 255) & ~255LL;           // root int32 + rank int32 + mass_root int64 per test
 }
-// Re-tiles X into the workspace (after the labelling scratch) and returns the tiled copy.
+// Re-tiles X into the workspace (after the labelling scratch) and returns the tiled copy.  X == nullptr: the
+// workspace already holds the tiled copy of an earlier call on the same data (cmc_cbpa_observed followed by
+// cmc_cbpa_permute on one stream), only the pointer is returned.
 static int cbpa_tile(const double* X, int n_subj, int n_tests, void* ws, int64_t ws_bytes, cudaStream_t st,
                      const double** XT, const char* who) {
     if (!ws || ws_bytes < cmc_cbpa_workspace_bytes(n_subj, n_tests)) {
@@ -416,10 +422,12 @@ static int cbpa_tile(const double* X, int n_subj, int n_tests, void* ws, int64_t
     }
     CMC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "%s: workspace must be 16-byte aligned", who);
     double* xt = reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + cbpa_labels_bytes(n_tests));
-    const int64_t total = (((int64_t)n_tests + 31) & ~31LL) * n_subj;
-    const int64_t blocks = (total + 255) / 256;
-    cbpa_tile_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(X, n_subj, n_tests, xt);
-    CMC_CHECK_LAUNCH("cbpa_tile_kernel");
+    if (X) {
+        const int64_t total = (((int64_t)n_tests + 31) & ~31LL) * n_subj;
+        const int64_t blocks = (total + 255) / 256;
+        cbpa_tile_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(X, n_subj, n_tests, xt);
+        CMC_CHECK_LAUNCH("cbpa_tile_kernel");
+    }
     *XT = xt;
     return CMC_OK;
 }
@@ -435,7 +443,7 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
                                 const int32_t* indptr, const int32_t* indices, int64_t* h0_fixed,
                                 void* ws, int64_t ws_bytes, void* stream) {
     using namespace cmc;
-    int rc = cbpa_check(X, n_subj, n_tests, indptr, indices, tail, thr);
+    int rc = cbpa_check(n_subj, n_tests, indptr, indices, tail, thr);
     if (rc) return rc;
     CMC_REQUIRE(signs && h0_fixed && p_end >= p_begin, "cmc_cbpa_permute: bad permutation range");
     const int64_t n_perm = p_end - p_begin;
@@ -450,7 +458,7 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
     const size_t smem = cbpa_smem_bytes(n_subj, n_tests, list_cap);
     // exact subject count as a template parameter for the usual group sizes, generic loop otherwise
     using KernT = void (*)(const double*, int, int, const int8_t*, int64_t, double, int, const int32_t*,
-                           const int32_t*, long long*, double*, int32_t*, long long*, int);
+                           const int32_t*, long long*, double*, int32_t*, long long*, int, unsigned*);
     KernT kern = cbpa_kernel<false, 0>;
     switch (n_subj) {
 #define CMC_CBPA_CASE(n) case n: kern = cbpa_kernel<false, n>; break;
@@ -468,9 +476,14 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCbpaThreads, smem);
     if (per_sm < 1) per_sm = 1;
     const int64_t grid = n_perm < (int64_t)sms * per_sm ? n_perm : (int64_t)sms * per_sm;
+    // permutation claim counter: the first word of the labelling scratch (unused by this call)
+    unsigned* claim = static_cast<unsigned*>(ws);
+    static const bool static_split = getenv("CMC_CBPA_STATIC_SPLIT") != nullptr;
+    if (static_split) claim = nullptr;
+    else if ((rc = check_cuda(cudaMemsetAsync(claim, 0, 4, static_cast<cudaStream_t>(stream)), "memset(claim)"))) return rc;
     kern<<<(unsigned)grid, kCbpaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         XT, n_subj, n_tests, signs + p_begin * n_subj, n_perm, thr, tail, indptr, indices,
-        reinterpret_cast<long long*>(h0_fixed), nullptr, nullptr, nullptr, list_cap);
+        reinterpret_cast<long long*>(h0_fixed), nullptr, nullptr, nullptr, list_cap, claim);
     CMC_CHECK_LAUNCH("cbpa_kernel<perm>");
     return CMC_OK;
 }
@@ -480,9 +493,9 @@ extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, doubl
                                  int32_t* labels, int64_t* mass_fixed, double* mass_f64,
                                  int32_t* n_clusters, void* ws, int64_t ws_bytes, void* stream) {
     using namespace cmc;
-    int rc = cbpa_check(X, n_subj, n_tests, indptr, indices, tail, thr);
+    int rc = cbpa_check(n_subj, n_tests, indptr, indices, tail, thr);
     if (rc) return rc;
-    CMC_REQUIRE(t_obs && labels && mass_fixed && mass_f64 && n_clusters, "cmc_cbpa_observed: null pointer");
+    CMC_REQUIRE(X && t_obs && labels && mass_fixed && mass_f64 && n_clusters, "cmc_cbpa_observed: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const double* XT = nullptr;
     rc = cbpa_tile(X, n_subj, n_tests, ws, ws_bytes, st, &XT, "cmc_cbpa_observed");
@@ -495,7 +508,7 @@ extern "C" int cmc_cbpa_observed(const double* X, int n_subj, int n_tests, doubl
     rc = ensure_smem_attr(reinterpret_cast<const void*>(cbpa_kernel<true, 0>), smem);
     if (rc) return rc;
     cbpa_kernel<true, 0><<<1, kCbpaThreads, smem, st>>>(XT, n_subj, n_tests, nullptr, 1, thr, tail, indptr,
-                                                     indices, h0_tmp, t_obs, root, mass_root, 0);
+                                                     indices, h0_tmp, t_obs, root, mass_root, 0, nullptr);
     CMC_CHECK_LAUNCH("cbpa_kernel<observed>");
     cbpa_label_kernel<<<1, 1024, 0, st>>>(root, mass_root, n_tests, labels,
                                            reinterpret_cast<long long*>(mass_fixed), mass_f64, n_clusters, rank);

@@ -285,14 +285,22 @@ def _cbpa_args(X, indptr, indices):
     return n_subj, n_tests
 
 
-def cbpa_observed(X: torch.Tensor, thr: float, tail: int, indptr: torch.Tensor, indices: torch.Tensor):
+def cbpa_workspace(X: torch.Tensor) -> torch.Tensor:
+    """Scratch for the CBPA calls on X; pass it to both calls to share the re-tiled copy of X."""
+    n_subj, n_tests = X.shape
+    return torch.empty(int(_lib.load().cmc_cbpa_workspace_bytes(n_subj, n_tests)), dtype=torch.uint8, device=X.device)
+
+
+def cbpa_observed(X: torch.Tensor, thr: float, tail: int, indptr: torch.Tensor, indices: torch.Tensor,
+                  ws: torch.Tensor | None = None):
     """Observed clustering: (t_obs f64 (n_tests,), labels int32, mass_fixed int64 (n_clusters,),
-    n_clusters).  Synchronises once to read the cluster count."""
+    n_clusters).  Synchronises once to read the cluster count.  Leaves the tiled copy of X in ``ws``."""
     n_subj, n_tests = _cbpa_args(X, indptr, indices)
     dev = X.device
     lib = _lib.load()
-    ws_bytes = int(lib.cmc_cbpa_workspace_bytes(n_subj, n_tests))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if ws is None:
+        ws = cbpa_workspace(X)
+    ws_bytes = ws.numel()
     t_obs = torch.empty(n_tests, dtype=torch.float64, device=dev)
     labels = torch.empty(n_tests, dtype=torch.int32, device=dev)
     mass_fixed = torch.zeros(n_tests, dtype=torch.int64, device=dev)
@@ -308,8 +316,11 @@ def cbpa_observed(X: torch.Tensor, thr: float, tail: int, indptr: torch.Tensor, 
 
 
 def cbpa_permute(X: torch.Tensor, signs: torch.Tensor, p_begin: int, p_end: int, thr: float, tail: int,
-                 indptr: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
-    """Max-cluster statistic (int64 fixed point) of permutations [p_begin, p_end) of the sign table."""
+                 indptr: torch.Tensor, indices: torch.Tensor, ws: torch.Tensor | None = None,
+                 tiled: bool = False) -> torch.Tensor:
+    """Max-cluster statistic (int64 fixed point) of permutations [p_begin, p_end) of the sign table.
+    ``tiled=True``: ``ws`` already holds the tiled copy of X (left by :func:`cbpa_observed` or an earlier call on
+    the same stream), the re-tile pass is skipped."""
     n_subj, n_tests = _cbpa_args(X, indptr, indices)
     _need_cuda(signs, "signs", torch.int8)
     if signs.dim() != 2 or signs.shape[1] != n_subj or not signs.is_contiguous():
@@ -318,9 +329,12 @@ def cbpa_permute(X: torch.Tensor, signs: torch.Tensor, p_begin: int, p_end: int,
         raise ValueError("permutation range outside the sign table")
     h0 = torch.empty(p_end - p_begin, dtype=torch.int64, device=X.device)
     lib = _lib.load()
-    ws_bytes = int(lib.cmc_cbpa_workspace_bytes(n_subj, n_tests))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
-    rc = lib.cmc_cbpa_permute(X.data_ptr(), n_subj, n_tests, signs.data_ptr(), p_begin, p_end, float(thr),
+    if tiled and ws is None:
+        raise ValueError("tiled=True needs the workspace that holds the tiled copy")
+    if ws is None:
+        ws = cbpa_workspace(X)
+    ws_bytes = ws.numel()
+    rc = lib.cmc_cbpa_permute(None if tiled else X.data_ptr(), n_subj, n_tests, signs.data_ptr(), p_begin, p_end, float(thr),
                               int(tail), indptr.data_ptr(), indices.data_ptr(), h0.data_ptr(), ws.data_ptr(),
                               ws_bytes, _lib.current_stream())
     _lib.check(rc, "cmc_cbpa_permute")
