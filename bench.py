@@ -514,283 +514,284 @@ def main_gpu(args):
            "single_call_api": "signal_features.welch_magnitude_squared_coherence(...).coherence, one blocking call "
                               "per recording"}
 
-    # ---- stage: surrogate null (config 3: 1,000 circular-shift surrogates on the cached spectra) ----
     stages = {}
-    shifts = np.random.default_rng(3).integers(1, L, N_SURR).astype(np.int32)
-    shifts_d = torch.from_numpy(shifts).to(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_rep = 3
-    for _ in range(2):
-        K.surrogate_null(res, K.SURR_SHIFT, 0, N_SURR, shifts=shifts_d)
-    barrier()
-    e0.record()
-    for _ in range(n_rep):
-        ex_s, ms_s = K.surrogate_null(res, K.SURR_SHIFT, 0, N_SURR, shifts=shifts_d)
-    e1.record()
-    barrier()
-    surr_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
-    n_distinct = len(np.unique(shifts))
-    flop = 3 * 2.0 * 128 * 64 * 2 * L * F * n_distinct                   # executed TF32 flop (three terms)
-    stages["surrogate_null_shift"] = {
-        "metric": "surrogates_per_s", "value": N_SURR / (surr_ms / 1e3), "unit": "surrogates/s",
-        "ms": surr_ms, "scaling": "replicated",
-        "config": f"config 3: {N_SURR} circular-shift surrogates of one 64x64xF=100 subject-condition; distinct shifts are "
-                  f"deduplicated on the device ({n_distinct} of L={L}), four of them share one 3xTF32 tcgen05 tile "
-                  f"(N = 256), so the cost does not grow beyond {L - 1} CSD passes (10,000 surrogates take the same "
-                  f"time); every rank runs it for its own subject-condition",
-        "roofline": {"bound": "tensor", "achieved": flop / (surr_ms * 1e-3) / 1e12, "peak": bf16 / 2,
-                     "unit": "TFLOP/s", "frac": flop / (surr_ms * 1e-3) / 1e12 / (bf16 / 2),
-                     "note": "executed TF32 flop of the distinct-shift passes (M=128 x N=256 tiles, three error-compensated "
-                             "TF32 terms per product); TF32 peak taken as half the measured dense bf16 figure"},
-    }
+    if not args.skip_stages:
+        # ---- stage: surrogate null (config 3: 1,000 circular-shift surrogates on the cached spectra) ----
+        shifts = np.random.default_rng(3).integers(1, L, N_SURR).astype(np.int32)
+        shifts_d = torch.from_numpy(shifts).to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_rep = 3
+        for _ in range(2):
+            K.surrogate_null(res, K.SURR_SHIFT, 0, N_SURR, shifts=shifts_d)
+        barrier()
+        e0.record()
+        for _ in range(n_rep):
+            ex_s, ms_s = K.surrogate_null(res, K.SURR_SHIFT, 0, N_SURR, shifts=shifts_d)
+        e1.record()
+        barrier()
+        surr_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
+        n_distinct = len(np.unique(shifts))
+        flop = 3 * 2.0 * 128 * 64 * 2 * L * F * n_distinct                   # executed TF32 flop (three terms)
+        stages["surrogate_null_shift"] = {
+            "metric": "surrogates_per_s", "value": N_SURR / (surr_ms / 1e3), "unit": "surrogates/s",
+            "ms": surr_ms, "scaling": "replicated",
+            "config": f"config 3: {N_SURR} circular-shift surrogates of one 64x64xF=100 subject-condition; distinct shifts are "
+                      f"deduplicated on the device ({n_distinct} of L={L}), four of them share one 3xTF32 tcgen05 tile "
+                      f"(N = 256), so the cost does not grow beyond {L - 1} CSD passes (10,000 surrogates take the same "
+                      f"time); every rank runs it for its own subject-condition",
+            "roofline": {"bound": "tensor", "achieved": flop / (surr_ms * 1e-3) / 1e12, "peak": bf16 / 2,
+                         "unit": "TFLOP/s", "frac": flop / (surr_ms * 1e-3) / 1e12 / (bf16 / 2),
+                         "note": "executed TF32 flop of the distinct-shift passes (M=128 x N=256 tiles, three error-compensated "
+                                 "TF32 terms per product); TF32 peak taken as half the measured dense bf16 figure"},
+        }
 
-    # ---- stage: phase-randomised surrogates (config 3 count per rank-shard of config 5's 10,000) ----
-    n_phase = 10000
-    # one null shared by the ranks: every rank runs all surrogates on its slice of the frequency axis, so
-    # operand generation, phases and contraction all shrink with the rank count (data_surrogation._plan)
-    fb, fe = cdist.shard_range(F, rank, world)
-    def phase_null():
-        ex_p, ms_p = K.surrogate_null(res, K.SURR_PHASE, 0, n_phase, seed=7, f_range=(fb, fe))
-        # one all-gather carries every rank's slice of the counts together with its per-surrogate maxima
-        return cdist.all_gather_frequency_slices(ex_p, ms_p, (fb, fe))
+        # ---- stage: phase-randomised surrogates (config 3 count per rank-shard of config 5's 10,000) ----
+        n_phase = 10000
+        # one null shared by the ranks: every rank runs all surrogates on its slice of the frequency axis, so
+        # operand generation, phases and contraction all shrink with the rank count (data_surrogation._plan)
+        fb, fe = cdist.shard_range(F, rank, world)
+        def phase_null():
+            ex_p, ms_p = K.surrogate_null(res, K.SURR_PHASE, 0, n_phase, seed=7, f_range=(fb, fe))
+            # one all-gather carries every rank's slice of the counts together with its per-surrogate maxima
+            return cdist.all_gather_frequency_slices(ex_p, ms_p, (fb, fe))
 
-    for _ in range(2):                                             # warm-up includes the collectives
-        phase_null()
-    barrier()
-    e0.record()
-    for _ in range(n_rep):
-        ex_p, ms_all = phase_null()
-    e1.record()
-    barrier()
-    ph_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
-    kpb = ((2 * L + 63) // 64) * 64
-    ph_flop = 2.0 * n_phase * (2 * NE * NM) * kpb * (fe - fb)              # executed fp16 flop on this rank
-    stages["surrogate_null_phase"] = {
-        "metric": "surrogates_per_s", "value": n_phase / (ph_ms / 1e3), "unit": "surrogates/s", "ms": ph_ms,
-        "scaling": "strong",
-        "config": f"config 5 count: {n_phase} phase-randomised surrogates of one 64x64xF=100 subject-condition "
-                  f"with the frequency axis sharded over {world} rank(s) (Philox phases + fp16 Z operands generated in "
-                  f"the timed region; "
-                  f"count slices and per-surrogate maxima exchanged with ONE all-gather)",
-        "roofline": {"bound": "tensor", "achieved": ph_flop / (ph_ms * 1e-3) / 1e12, "peak": bf16,
-                     "unit": "TFLOP/s", "frac": ph_flop / (ph_ms * 1e-3) / 1e12 / bf16,
-                     "note": "executed fp16 flop (kind::f16, K padded to 64) vs the measured dense bf16 peak (same rate)"},
-    }
+        for _ in range(2):                                             # warm-up includes the collectives
+            phase_null()
+        barrier()
+        e0.record()
+        for _ in range(n_rep):
+            ex_p, ms_all = phase_null()
+        e1.record()
+        barrier()
+        ph_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
+        kpb = ((2 * L + 63) // 64) * 64
+        ph_flop = 2.0 * n_phase * (2 * NE * NM) * kpb * (fe - fb)              # executed fp16 flop on this rank
+        stages["surrogate_null_phase"] = {
+            "metric": "surrogates_per_s", "value": n_phase / (ph_ms / 1e3), "unit": "surrogates/s", "ms": ph_ms,
+            "scaling": "strong",
+            "config": f"config 5 count: {n_phase} phase-randomised surrogates of one 64x64xF=100 subject-condition "
+                      f"with the frequency axis sharded over {world} rank(s) (Philox phases + fp16 Z operands generated in "
+                      f"the timed region; "
+                      f"count slices and per-surrogate maxima exchanged with ONE all-gather)",
+            "roofline": {"bound": "tensor", "achieved": ph_flop / (ph_ms * 1e-3) / 1e12, "peak": bf16,
+                         "unit": "TFLOP/s", "frac": ph_flop / (ph_ms * 1e-3) / 1e12 / bf16,
+                         "note": "executed fp16 flop (kind::f16, K padded to 64) vs the measured dense bf16 peak (same rate)"},
+        }
 
-    # ---- stage: config 3 with per-pair significance thresholds (null histograms, two zoom passes) ----
-    class _Pooled:                                                 # the slice of PooledCoherence the null API reads
-        device_result, coherence, freqs, group = res, res.coh, freqs[lo:hi + 1], 1
-    for _ in range(2):
-        dsur.phase_randomised_surrogate_null(_Pooled, N_SURR, seed=3, thresholds=True)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(n_rep):
-        null3 = dsur.phase_randomised_surrogate_null(_Pooled, N_SURR, seed=3, thresholds=True)
-    barrier()
-    thr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_rep
-    stages["surrogate_thresholds_cfg3"] = {
-        "metric": "surrogates_per_s", "value": N_SURR / (thr_ms / 1e3), "unit": "surrogates/s", "ms": thr_ms,
-        "scaling": "strong" if world > 1 else "replicated",
-        "significant_pairs": int(null3["significant"].sum()),
-        "config": f"config 3: {N_SURR} phase-randomised surrogates per pair of one 64x64xF=100 subject-condition -> "
-                  "exceedance p-values, family-wise threshold AND per-pair (1 - alpha) thresholds from device-side "
-                  "null histograms (128 bins, two zoom passes = three GEMM sweeps in total); wall clock of "
-                  "data_surrogation.phase_randomised_surrogate_null(..., thresholds=True) incl. the download of "
-                  "counts, maxima and thresholds"}
+        # ---- stage: config 3 with per-pair significance thresholds (null histograms, two zoom passes) ----
+        import types
+        _Pooled = types.SimpleNamespace(device_result=res, coherence=res.coh, freqs=freqs[lo:hi + 1], group=1)
+        for _ in range(2):
+            dsur.phase_randomised_surrogate_null(_Pooled, N_SURR, seed=3, thresholds=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_rep):
+            null3 = dsur.phase_randomised_surrogate_null(_Pooled, N_SURR, seed=3, thresholds=True)
+        barrier()
+        thr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_rep
+        stages["surrogate_thresholds_cfg3"] = {
+            "metric": "surrogates_per_s", "value": N_SURR / (thr_ms / 1e3), "unit": "surrogates/s", "ms": thr_ms,
+            "scaling": "strong" if world > 1 else "replicated",
+            "significant_pairs": int(null3["significant"].sum()),
+            "config": f"config 3: {N_SURR} phase-randomised surrogates per pair of one 64x64xF=100 subject-condition -> "
+                      "exceedance p-values, family-wise threshold AND per-pair (1 - alpha) thresholds from device-side "
+                      "null histograms (128 bins, two zoom passes = three GEMM sweeps in total); wall clock of "
+                      "data_surrogation.phase_randomised_surrogate_null(..., thresholds=True) incl. the download of "
+                      "counts, maxima and thresholds"}
 
-    # ---- stage: the reference's production estimator - per-window multitaper MSC with jackknife CI ----
-    from multimodal_biosignal_analysis_b200.signal_features import _dpss
-    tapers = torch.from_numpy(_dpss(NPERSEG, 3, 0.9).astype(np.float32)).to(dev)
-    Kt = tapers.shape[0]
-    t_crit = float(t_dist.ppf(0.975, Kt - 1))
-    eeg_d, emg_d = dev_sets[0]
+        # ---- stage: the reference's production estimator - per-window multitaper MSC with jackknife CI ----
+        from multimodal_biosignal_analysis_b200.signal_features import _dpss
+        tapers = torch.from_numpy(_dpss(NPERSEG, 3, 0.9).astype(np.float32)).to(dev)
+        Kt = tapers.shape[0]
+        t_crit = float(t_dist.ppf(0.975, Kt - 1))
+        eeg_d, emg_d = dev_sets[0]
 
-    def mt_step():
-        Xw = K.fft_segments(eeg_d, starts, tapers, K.DETREND_NONE, lo, hi)
-        Yw = K.fft_segments(emg_d, starts, tapers, K.DETREND_NONE, lo, hi)
-        return K.msc_windows(Xw, Yw, None, True, t_crit, 0.81)
+        def mt_step():
+            Xw = K.fft_segments(eeg_d, starts, tapers, K.DETREND_NONE, lo, hi)
+            Yw = K.fft_segments(emg_d, starts, tapers, K.DETREND_NONE, lo, hi)
+            return K.msc_windows(Xw, Yw, None, True, t_crit, 0.81)
 
-    for _ in range(3):
-        mt_step()                                     # warm the allocator: 1.1 GB of outputs per call
-    barrier()
-    e0.record()
-    for _ in range(n_rep):
-        mt_step()
-    e1.record()
-    barrier()
-    mt_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
-    mt_bytes = n_samples * (NE + NM) * 4 + L * F * NE * NM * 13 + 2 * L * Kt * F * (NE + NM) * 8
-    stages["multitaper_windows"] = {
-        "metric": "window_pair_spectra_per_s", "value": L * NE * NM * world / (mt_ms / 1e3),
-        "unit": "pair-spectra/s (one per window)", "ms": mt_ms, "scaling": "weak",
-        "config": f"multitaper variant of config 2: {L} windows of {NPERSEG} samples, K={Kt} DPSS tapers, 64x64 pairs, "
-                  f"F={F} in-band bins, jackknife CI + independence mask (signal_features.py:619-839 semantics); "
-                  f"outputs (W,F,64,64) x (3 float32 + 1 mask) stay in HBM",
-        "roofline": {"bound": "hbm", "achieved": mt_bytes / (mt_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                     "frac": mt_bytes / (mt_ms * 1e-3) / 1e9 / hbm,
-                     "note": "algorithmic bytes = recordings once + spectra write/read + 13 B per (window, bin, pair)"},
-    }
+        for _ in range(3):
+            mt_step()                                     # warm the allocator: 1.1 GB of outputs per call
+        barrier()
+        e0.record()
+        for _ in range(n_rep):
+            mt_step()
+        e1.record()
+        barrier()
+        mt_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
+        mt_bytes = n_samples * (NE + NM) * 4 + L * F * NE * NM * 13 + 2 * L * Kt * F * (NE + NM) * 8
+        stages["multitaper_windows"] = {
+            "metric": "window_pair_spectra_per_s", "value": L * NE * NM * world / (mt_ms / 1e3),
+            "unit": "pair-spectra/s (one per window)", "ms": mt_ms, "scaling": "weak",
+            "config": f"multitaper variant of config 2: {L} windows of {NPERSEG} samples, K={Kt} DPSS tapers, 64x64 pairs, "
+                      f"F={F} in-band bins, jackknife CI + independence mask (signal_features.py:619-839 semantics); "
+                      f"outputs (W,F,64,64) x (3 float32 + 1 mask) stay in HBM",
+            "roofline": {"bound": "hbm", "achieved": mt_bytes / (mt_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": mt_bytes / (mt_ms * 1e-3) / 1e9 / hbm,
+                         "note": "algorithmic bytes = recordings once + spectra write/read + 13 B per (window, bin, pair)"},
+        }
 
-    # ---- stage: CBPA permutations (config 4 geometry, config 5 count sharded over the ranks) ----
-    from multimodal_biosignal_analysis_b200.cbpa import combine_adjacency, find_ch_adjacency_from_positions
-    adj = combine_adjacency(CBPA_SHAPE[1], find_ch_adjacency_from_positions(syn.sensor_positions(CBPA_SHAPE[2])))
-    adj.sort_indices()
-    Xc = syn.make_cbpa_contrast(*CBPA_SHAPE)
-    signs = syn.make_sign_table(N_PERM_TOTAL, CBPA_SHAPE[0], seed=42)
-    thr = float(t_dist.ppf(0.975, CBPA_SHAPE[0] - 1))
-    Xd = torch.from_numpy(np.ascontiguousarray(Xc.reshape(CBPA_SHAPE[0], -1))).to(dev)
-    indptr = torch.from_numpy(adj.indptr.astype(np.int32)).to(dev)
-    indices = torch.from_numpy(adj.indices.astype(np.int32)).to(dev)
-    sd = torch.from_numpy(signs).to(dev)
-    pb, pe = cdist.shard_range(N_PERM_TOTAL, rank, world)
-    ws_c = K.cbpa_workspace(Xd)
-    K.cbpa_observed(Xd, thr, 0, indptr, indices, ws=ws_c)          # observed clustering; leaves the tiled X in ws_c
-    for _ in range(2):                                             # warm-up includes the collective
-        cdist.all_gather_ranges(K.cbpa_permute(Xd, sd, pb, pe, thr, 0, indptr, indices, ws=ws_c, tiled=True),
-                                N_PERM_TOTAL)
-    barrier()
-    e0.record()
-    for _ in range(n_rep):
-        h0 = cdist.all_gather_ranges(K.cbpa_permute(Xd, sd, pb, pe, thr, 0, indptr, indices, ws=ws_c, tiled=True),
-                                     N_PERM_TOTAL)
-    e1.record()
-    barrier()
-    cbpa_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
-    # the t-map is the dominant pass and lives in the FP64 pipe: numpy's operation order costs 4 n_subj - 2
-    # adds/multiplies + 4 divisions/square root per test, none of them fusable; X is L2 resident
-    n_subj_c, n_tests_c = CBPA_SHAPE[0], CBPA_SHAPE[1] * CBPA_SHAPE[2]
-    fp64_ops = n_tests_c * (4 * n_subj_c - 2 + 4)
-    cbpa_tops = fp64_ops * (pe - pb) / (cbpa_ms * 1e-3) / 1e12
-    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-    sm_clock_hz = torch.cuda.get_device_properties(dev).clock_rate * 1e3 if hasattr(
-        torch.cuda.get_device_properties(dev), "clock_rate") else 1.965e9
-    fp64_peak = n_sm * 64 * sm_clock_hz / 1e12       # FP64 instructions: 64 lanes / SM / clock at the device's boost clock
-    stages["cbpa"] = {
-        "metric": "cbpa_permutations_per_s", "value": N_PERM_TOTAL / (cbpa_ms / 1e3), "unit": "permutations/s",
-        "ms": cbpa_ms, "scaling": "strong",
-        "config": f"config 4 geometry (20 subj x 100 x 64 = 6400 tests, {adj.nnz} nnz adjacency), "
-                  f"{N_PERM_TOTAL} sign-flip permutations sharded over {world} rank(s), H0 all-gathered",
-        "roofline": {"bound": "fp64", "achieved": cbpa_tops, "peak": fp64_peak, "unit": "Tinstr/s",
-                     "frac": cbpa_tops / fp64_peak,
-                     "note": "algorithmic FP64 operations of the sign-flip t-map (4 n_subj + 2 per test, unfused as "
-                             "in numpy) vs the FP64 issue rate of 148 SMs x 64 lanes x 1965 MHz; X (1 MB) is L2 "
-                             "resident, DRAM traffic is negligible"},
-    }
+        # ---- stage: CBPA permutations (config 4 geometry, config 5 count sharded over the ranks) ----
+        from multimodal_biosignal_analysis_b200.cbpa import combine_adjacency, find_ch_adjacency_from_positions
+        adj = combine_adjacency(CBPA_SHAPE[1], find_ch_adjacency_from_positions(syn.sensor_positions(CBPA_SHAPE[2])))
+        adj.sort_indices()
+        Xc = syn.make_cbpa_contrast(*CBPA_SHAPE)
+        signs = syn.make_sign_table(N_PERM_TOTAL, CBPA_SHAPE[0], seed=42)
+        thr = float(t_dist.ppf(0.975, CBPA_SHAPE[0] - 1))
+        Xd = torch.from_numpy(np.ascontiguousarray(Xc.reshape(CBPA_SHAPE[0], -1))).to(dev)
+        indptr = torch.from_numpy(adj.indptr.astype(np.int32)).to(dev)
+        indices = torch.from_numpy(adj.indices.astype(np.int32)).to(dev)
+        sd = torch.from_numpy(signs).to(dev)
+        pb, pe = cdist.shard_range(N_PERM_TOTAL, rank, world)
+        ws_c = K.cbpa_workspace(Xd)
+        K.cbpa_observed(Xd, thr, 0, indptr, indices, ws=ws_c)          # observed clustering; leaves the tiled X in ws_c
+        for _ in range(2):                                             # warm-up includes the collective
+            cdist.all_gather_ranges(K.cbpa_permute(Xd, sd, pb, pe, thr, 0, indptr, indices, ws=ws_c, tiled=True),
+                                    N_PERM_TOTAL)
+        barrier()
+        e0.record()
+        for _ in range(n_rep):
+            h0 = cdist.all_gather_ranges(K.cbpa_permute(Xd, sd, pb, pe, thr, 0, indptr, indices, ws=ws_c, tiled=True),
+                                         N_PERM_TOTAL)
+        e1.record()
+        barrier()
+        cbpa_ms = max_over_ranks(e0.elapsed_time(e1)) / n_rep
+        # the t-map is the dominant pass and lives in the FP64 pipe: numpy's operation order costs 4 n_subj - 2
+        # adds/multiplies + 4 divisions/square root per test, none of them fusable; X is L2 resident
+        n_subj_c, n_tests_c = CBPA_SHAPE[0], CBPA_SHAPE[1] * CBPA_SHAPE[2]
+        fp64_ops = n_tests_c * (4 * n_subj_c - 2 + 4)
+        cbpa_tops = fp64_ops * (pe - pb) / (cbpa_ms * 1e-3) / 1e12
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_clock_hz = torch.cuda.get_device_properties(dev).clock_rate * 1e3 if hasattr(
+            torch.cuda.get_device_properties(dev), "clock_rate") else 1.965e9
+        fp64_peak = n_sm * 64 * sm_clock_hz / 1e12       # FP64 instructions: 64 lanes / SM / clock at the device's boost clock
+        stages["cbpa"] = {
+            "metric": "cbpa_permutations_per_s", "value": N_PERM_TOTAL / (cbpa_ms / 1e3), "unit": "permutations/s",
+            "ms": cbpa_ms, "scaling": "strong",
+            "config": f"config 4 geometry (20 subj x 100 x 64 = 6400 tests, {adj.nnz} nnz adjacency), "
+                      f"{N_PERM_TOTAL} sign-flip permutations sharded over {world} rank(s), H0 all-gathered",
+            "roofline": {"bound": "fp64", "achieved": cbpa_tops, "peak": fp64_peak, "unit": "Tinstr/s",
+                         "frac": cbpa_tops / fp64_peak,
+                         "note": "algorithmic FP64 operations of the sign-flip t-map (4 n_subj + 2 per test, unfused as "
+                                 "in numpy) vs the FP64 issue rate of 148 SMs x 64 lanes x 1965 MHz; X (1 MB) is L2 "
+                                 "resident, DRAM traffic is negligible"},
+        }
 
-    # ---- stage: BASELINE config 5 as one pipeline through the public API (numpy / pinned host in, numpy out) ----
-    # 20 subjects x 4 conditions = 80 subject-conditions dealt round-robin over the ranks (no collective while they
-    # run); per unit upload -> K1 x 2 -> K2 -> operand planes -> 10,000-surrogate phase null -> download of coherence,
-    # counts and maxima, uploads / downloads of neighbouring units overlapped; then one all-reduce of the (F, Ne)
-    # EMG-max maps and the 10,000-permutation CBPA of the condition contrast (permutations sharded, H0 all-gathered).
-    from multimodal_biosignal_analysis_b200 import sweep as csweep
-    n_subj5, conds5 = 20, ("happy", "sad", "calm", "silence")
-    units5 = {(f"S{s_:02d}", c_): pinned[(4 * s_ + k_) % N_ROTATE]
-              for s_ in range(n_subj5) for k_, c_ in enumerate(conds5)}
+        # ---- stage: BASELINE config 5 as one pipeline through the public API (numpy / pinned host in, numpy out) ----
+        # 20 subjects x 4 conditions = 80 subject-conditions dealt round-robin over the ranks (no collective while they
+        # run); per unit upload -> K1 x 2 -> K2 -> operand planes -> 10,000-surrogate phase null -> download of coherence,
+        # counts and maxima, uploads / downloads of neighbouring units overlapped; then one all-reduce of the (F, Ne)
+        # EMG-max maps and the 10,000-permutation CBPA of the condition contrast (permutations sharded, H0 all-gathered).
+        from multimodal_biosignal_analysis_b200 import sweep as csweep
+        n_subj5, conds5 = 20, ("happy", "sad", "calm", "silence")
+        units5 = {(f"S{s_:02d}", c_): pinned[(4 * s_ + k_) % N_ROTATE]
+                  for s_ in range(n_subj5) for k_, c_ in enumerate(conds5)}
 
-    def run_cfg5(units, n_surr=10000, n_perm=N_PERM_TOTAL):
-        return csweep.cmc_surrogate_cbpa_sweep(units, FS, nperseg=NPERSEG, freq_band=BAND, segment_starts=starts_h,
-                                               n_surrogates=n_surr, mode="phase", seed=11, n_permutations=n_perm,
-                                               contrasts=[("happy", "silence")])
+        def run_cfg5(units, n_surr=10000, n_perm=N_PERM_TOTAL):
+            return csweep.cmc_surrogate_cbpa_sweep(units, FS, nperseg=NPERSEG, freq_band=BAND, segment_starts=starts_h,
+                                                   n_surrogates=n_surr, mode="phase", seed=11, n_permutations=n_perm,
+                                                   contrasts=[("happy", "silence")])
 
-    small = {k: v for k, v in list(units5.items())[: 4 * max(world, 2)]}
-    run_cfg5(small)                                                # warm-up: allocator, NCCL, CBPA tables
-    barrier()
-    t0 = time.perf_counter()
-    out5 = run_cfg5(units5)
-    barrier()
-    cfg5_s = max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3
-    n_units5 = len(units5)
-    # the unit stage alone on THIS rank's share (device events around one more pass over 8 resident units)
-    e0.record()
-    for _ in range(8):
-        K.surrogate_null(res, K.SURR_PHASE, 0, 10000, seed=3)
-    e1.record()
-    torch.cuda.synchronize()
-    null_ms = e0.elapsed_time(e1) / 8
-    stages["config5_sweep"] = {
-        "metric": "subject_conditions_per_s", "value": n_units5 / cfg5_s, "unit": "subject-conditions/s",
-        "seconds_total": cfg5_s, "ms_per_unit_wall": cfg5_s * 1e3 * world / n_units5, "scaling": "strong",
-        "surrogates_per_s_e2e": n_units5 * 10000 / cfg5_s,
-        "pair_spectra_per_s_e2e": n_units5 * NE * NM / cfg5_s,
-        "null_kernel_ms_per_unit": null_ms,
-        "h2d_bytes_per_unit": int(n_samples * (NE + NM) * 4),
-        "d2h_bytes_per_unit": int(F * NE * NM * 8 + 10000 * 4),
-        "n_units": n_units5, "n_surrogates": 10000, "n_permutations": N_PERM_TOTAL,
-        "n_clusters": int(len(out5["cbpa"][("happy", "silence")]["cluster_pv"])),
-        "config": "BASELINE config 5 end to end, wall clock: sweep.cmc_surrogate_cbpa_sweep(units, ...) - 80 "
-                  "subject-conditions (20 subjects x 4 conditions, 64x64 channels, 30 epochs x 4 s, pinned float32 host "
-                  "tensors in, numpy out) dealt round-robin over the ranks, each with a 10,000-surrogate phase null, "
-                  "then the 10,000-permutation CBPA of one condition contrast (20 x 100 x 64) sharded over the ranks",
-        "api": "multimodal_biosignal_analysis_b200.sweep.cmc_surrogate_cbpa_sweep",
-    }
-    if world == 1:
-        # what a caller holding the reference's arrays pays: pageable numpy float32 / float64 (np.load output) are
-        # converted into pinned staging buffers by host threads before the upload
-        n_small = 8
-        for label, conv in (("numpy_float32_pageable", lambda a: a), ("numpy_float64_pageable", lambda a: a.astype(np.float64))):
-            hs = [(conv(a), conv(b)) for a, b in host_sets[:2]]
-            us = {(f"S{s_:02d}", c_): hs[(2 * s_ + k_) % 2] for s_ in range(n_small // 2) for k_, c_ in enumerate(conds5[:2])}
-            csweep.cmc_surrogate_cbpa_sweep({k: us[k] for k in list(us)[:2]}, FS, nperseg=NPERSEG, freq_band=BAND,
-                                            segment_starts=starts_h, n_surrogates=10000, seed=11, contrasts=[])
-            t0 = time.perf_counter()
-            csweep.cmc_surrogate_cbpa_sweep(us, FS, nperseg=NPERSEG, freq_band=BAND, segment_starts=starts_h,
-                                            n_surrogates=10000, seed=11, contrasts=[])
-            stages["config5_sweep"][f"ms_per_unit_wall_{label}"] = (time.perf_counter() - t0) * 1e3 / len(us)
-            del hs, us
+        small = {k: v for k, v in list(units5.items())[: 4 * max(world, 2)]}
+        run_cfg5(small)                                                # warm-up: allocator, NCCL, CBPA tables
+        barrier()
+        t0 = time.perf_counter()
+        out5 = run_cfg5(units5)
+        barrier()
+        cfg5_s = max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3
+        n_units5 = len(units5)
+        # the unit stage alone on THIS rank's share (device events around one more pass over 8 resident units)
+        e0.record()
+        for _ in range(8):
+            K.surrogate_null(res, K.SURR_PHASE, 0, 10000, seed=3)
+        e1.record()
+        torch.cuda.synchronize()
+        null_ms = e0.elapsed_time(e1) / 8
+        stages["config5_sweep"] = {
+            "metric": "subject_conditions_per_s", "value": n_units5 / cfg5_s, "unit": "subject-conditions/s",
+            "seconds_total": cfg5_s, "ms_per_unit_wall": cfg5_s * 1e3 * world / n_units5, "scaling": "strong",
+            "surrogates_per_s_e2e": n_units5 * 10000 / cfg5_s,
+            "pair_spectra_per_s_e2e": n_units5 * NE * NM / cfg5_s,
+            "null_kernel_ms_per_unit": null_ms,
+            "h2d_bytes_per_unit": int(n_samples * (NE + NM) * 4),
+            "d2h_bytes_per_unit": int(F * NE * NM * 8 + 10000 * 4),
+            "n_units": n_units5, "n_surrogates": 10000, "n_permutations": N_PERM_TOTAL,
+            "n_clusters": int(len(out5["cbpa"][("happy", "silence")]["cluster_pv"])),
+            "config": "BASELINE config 5 end to end, wall clock: sweep.cmc_surrogate_cbpa_sweep(units, ...) - 80 "
+                      "subject-conditions (20 subjects x 4 conditions, 64x64 channels, 30 epochs x 4 s, pinned float32 host "
+                      "tensors in, numpy out) dealt round-robin over the ranks, each with a 10,000-surrogate phase null, "
+                      "then the 10,000-permutation CBPA of one condition contrast (20 x 100 x 64) sharded over the ranks",
+            "api": "multimodal_biosignal_analysis_b200.sweep.cmc_surrogate_cbpa_sweep",
+        }
+        if world == 1:
+            # what a caller holding the reference's arrays pays: pageable numpy float32 / float64 (np.load output) are
+            # converted into pinned staging buffers by host threads before the upload
+            n_small = 8
+            for label, conv in (("numpy_float32_pageable", lambda a: a), ("numpy_float64_pageable", lambda a: a.astype(np.float64))):
+                hs = [(conv(a), conv(b)) for a, b in host_sets[:2]]
+                us = {(f"S{s_:02d}", c_): hs[(2 * s_ + k_) % 2] for s_ in range(n_small // 2) for k_, c_ in enumerate(conds5[:2])}
+                csweep.cmc_surrogate_cbpa_sweep({k: us[k] for k in list(us)[:2]}, FS, nperseg=NPERSEG, freq_band=BAND,
+                                                segment_starts=starts_h, n_surrogates=10000, seed=11, contrasts=[])
+                t0 = time.perf_counter()
+                csweep.cmc_surrogate_cbpa_sweep(us, FS, nperseg=NPERSEG, freq_band=BAND, segment_starts=starts_h,
+                                                n_surrogates=10000, seed=11, contrasts=[])
+                stages["config5_sweep"][f"ms_per_unit_wall_{label}"] = (time.perf_counter() - t0) * 1e3 / len(us)
+                del hs, us
 
-    # ---- stage: BASELINE config 1 (the reference's own CPU-runnable case): one EEG x one bipolar EMG channel ----
-    eeg1, emg1 = syn.make_recording(122880, 1, 2, seed=1)
-    bip1 = np.ascontiguousarray(emg1[:, :1] - emg1[:, 1:2])
-    for _ in range(3):
-        c1 = sf.welch_magnitude_squared_coherence(eeg1, bip1, FS, nperseg=1024).coherence
-    t0 = time.perf_counter()
-    for _ in range(20):
-        c1 = sf.welch_magnitude_squared_coherence(eeg1, bip1, FS, nperseg=1024).coherence
-    cfg1_ms = (time.perf_counter() - t0) * 1e3 / 20
-    stages["config1_welch_pair"] = {
-        "metric": "pair_spectra_per_s", "value": 1.0 / (cfg1_ms / 1e3), "unit": "pair-spectra/s", "ms": cfg1_ms,
-        "scaling": "replicated",
-        "config": "BASELINE config 1: C3 x one bipolar EMG channel, 60 s @ 2048 Hz, nperseg 1024 (L = 239, F = 513): one "
-                  "blocking welch_magnitude_squared_coherence call, numpy in, numpy out (launch / PCIe latency bound)"}
-    if rank == 0 and world == 1 and not args.no_cpu:
-        from scipy import signal as ssig
-        x64, y64 = eeg1[:, 0].astype(np.float64), bip1[:, 0].astype(np.float64)
-        ssig.coherence(x64, y64, fs=FS, nperseg=1024)
+        # ---- stage: BASELINE config 1 (the reference's own CPU-runnable case): one EEG x one bipolar EMG channel ----
+        eeg1, emg1 = syn.make_recording(122880, 1, 2, seed=1)
+        bip1 = np.ascontiguousarray(emg1[:, :1] - emg1[:, 1:2])
+        for _ in range(3):
+            c1 = sf.welch_magnitude_squared_coherence(eeg1, bip1, FS, nperseg=1024).coherence
         t0 = time.perf_counter()
         for _ in range(20):
-            _, cref1 = ssig.coherence(x64, y64, fs=FS, nperseg=1024)
-        sc_ms = (time.perf_counter() - t0) * 1e3 / 20
-        stages["config1_welch_pair"]["cpu_baseline"] = {
-            "value": 1.0 / (sc_ms / 1e3), "unit": "pair-spectra/s", "cores": 1, "kind": "reference",
-            "sample": "scipy.signal.coherence(fs=2048, nperseg=1024) - the reference's own CPU path for this config "
-                      "(preprocessing.py:1228-1230) - 20 repetitions, one core",
-            "max_abs_diff_vs_gpu": float(np.max(np.abs(c1[:, 0, 0] - cref1)))}
+            c1 = sf.welch_magnitude_squared_coherence(eeg1, bip1, FS, nperseg=1024).coherence
+        cfg1_ms = (time.perf_counter() - t0) * 1e3 / 20
+        stages["config1_welch_pair"] = {
+            "metric": "pair_spectra_per_s", "value": 1.0 / (cfg1_ms / 1e3), "unit": "pair-spectra/s", "ms": cfg1_ms,
+            "scaling": "replicated",
+            "config": "BASELINE config 1: C3 x one bipolar EMG channel, 60 s @ 2048 Hz, nperseg 1024 (L = 239, F = 513): one "
+                      "blocking welch_magnitude_squared_coherence call, numpy in, numpy out (launch / PCIe latency bound)"}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from scipy import signal as ssig
+            x64, y64 = eeg1[:, 0].astype(np.float64), bip1[:, 0].astype(np.float64)
+            ssig.coherence(x64, y64, fs=FS, nperseg=1024)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                _, cref1 = ssig.coherence(x64, y64, fs=FS, nperseg=1024)
+            sc_ms = (time.perf_counter() - t0) * 1e3 / 20
+            stages["config1_welch_pair"]["cpu_baseline"] = {
+                "value": 1.0 / (sc_ms / 1e3), "unit": "pair-spectra/s", "cores": 1, "kind": "reference",
+                "sample": "scipy.signal.coherence(fs=2048, nperseg=1024) - the reference's own CPU path for this config "
+                          "(preprocessing.py:1228-1230) - 20 repetitions, one core",
+                "max_abs_diff_vs_gpu": float(np.max(np.abs(c1[:, 0, 0] - cref1)))}
 
-    # ---- stage: the production call of the reference workflow (subject_feature_extraction_workflow.py:58-69) ----
-    n_prod = int(FS) * 600
-    g = torch.Generator(device=dev).manual_seed(5)
-    eeg_p = torch.randn((n_prod, 11), device=dev, generator=g)
-    emg_p = torch.randn((n_prod, 64), device=dev, generator=g)
+        # ---- stage: the production call of the reference workflow (subject_feature_extraction_workflow.py:58-69) ----
+        n_prod = int(FS) * 600
+        g = torch.Generator(device=dev).manual_seed(5)
+        eeg_p = torch.randn((n_prod, 11), device=dev, generator=g)
+        emg_p = torch.randn((n_prod, 64), device=dev, generator=g)
 
-    def prod():
-        return sf.multitaper_magnitude_squared_coherence(eeg_p, emg_p, FS, window_length_sec=2.0, use_jackknife=True,
-                                                         reduce_emg=True, zero_nonsignificant=True, freq_band=(1, 100))
-    for _ in range(2):
-        rp = prod()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        rp = prod()
-    torch.cuda.synchronize()
-    prod_ms = (time.perf_counter() - t0) * 1e3 / 5
-    w_prod = int(rp["coherence_raw"].shape[0])
-    stages["production_multitaper"] = {
-        "metric": "window_pair_spectra_per_s", "value": w_prod * 11 * 64 * world / (prod_ms / 1e3),
-        "unit": "pair-spectra/s (one per window)", "ms": prod_ms, "windows": w_prod, "scaling": "weak",
-        "config": "production geometry: 10-minute recording, 11 EEG x 64 EMG channels, N = 4096 / hop 2048, K = 5 DPSS "
-                  "tapers, jackknife CI + significance zeroing + EMG-argmax fused (compute_task_wise_aggregated_cmc "
-                  "semantics), 1-100 Hz, device-resident input, wall clock of the blocking call"}
-    del eeg_p, emg_p, rp
+        def prod():
+            return sf.multitaper_magnitude_squared_coherence(eeg_p, emg_p, FS, window_length_sec=2.0, use_jackknife=True,
+                                                             reduce_emg=True, zero_nonsignificant=True, freq_band=(1, 100))
+        for _ in range(2):
+            rp = prod()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            rp = prod()
+        torch.cuda.synchronize()
+        prod_ms = (time.perf_counter() - t0) * 1e3 / 5
+        w_prod = int(rp["coherence_raw"].shape[0])
+        stages["production_multitaper"] = {
+            "metric": "window_pair_spectra_per_s", "value": w_prod * 11 * 64 * world / (prod_ms / 1e3),
+            "unit": "pair-spectra/s (one per window)", "ms": prod_ms, "windows": w_prod, "scaling": "weak",
+            "config": "production geometry: 10-minute recording, 11 EEG x 64 EMG channels, N = 4096 / hop 2048, K = 5 DPSS "
+                      "tapers, jackknife CI + significance zeroing + EMG-argmax fused (compute_task_wise_aggregated_cmc "
+                      "semantics), 1-100 Hz, device-resident input, wall clock of the blocking call"}
+        del eeg_p, emg_p, rp
 
     # ---- CPU baseline (rank 0, N = 1): oracle port on a bounded sample ----
     cpu = None
@@ -798,8 +799,9 @@ def main_gpu(args):
         v, ms, cores, sample = run_cpu_reference(steps=2, warmup=1, sample_epochs=10)
         cpu = {"value": v, "unit": "pair-spectra/s", "cores": cores, "kind": "port", "sample": sample,
                "ms_per_step": ms}
-        for key, base in run_cpu_stage_baselines().items():       # CPU ports of the surrogate / CBPA stages
-            stages[key]["cpu_baseline"] = base
+        if stages:
+            for key, base in run_cpu_stage_baselines().items():   # CPU ports of the surrogate / CBPA stages
+                stages[key]["cpu_baseline"] = base
 
     if rank == 0:
         line = {
@@ -822,9 +824,9 @@ def main_gpu(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "stages": stages,
             "host_enqueue_ms_per_step": host_enqueue_ms,
             # the other two headline metrics of BASELINE.json, copied up from `stages` for convenience
-            "surrogates_per_s": stages["surrogate_null_phase"]["value"],
-            "cbpa_permutations_per_s": stages["cbpa"]["value"],
-            "config5_sweep_seconds": stages["config5_sweep"]["seconds_total"],
+            "surrogates_per_s": stages.get("surrogate_null_phase", {}).get("value"),
+            "cbpa_permutations_per_s": stages.get("cbpa", {}).get("value"),
+            "config5_sweep_seconds": stages.get("config5_sweep", {}).get("seconds_total"),
         }
         print(json.dumps(line))
     if world > 1:
@@ -838,6 +840,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--skip-stages", action="store_true",
+                    help="headline metric only (profiling runs): no surrogate / CBPA / sweep stages")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

@@ -634,7 +634,7 @@ int fft_segments_tma(const float* x, int64_t n_samples, int n_ch, int64_t ld, co
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
     // SWIZZLE_64B with a 32-byte inner box faults on sm_100 (illegal memory access, found on hardware with
-    // scripts/debug_fft.py), so the raw tile is loaded unswizzled: first-pass reads are then 2-way bank
+    // a probe script in round 1), so the raw tile is loaded unswizzled: first-pass reads are then 2-way bank
     // conflicted (4 instead of 2 wavefronts per request), every other access is conflict free.
     constexpr bool swz = false;
     CUtensorMap tmap;

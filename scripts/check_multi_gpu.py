@@ -39,6 +39,37 @@ h_all = K.cbpa_permute(Xd, sd, 0, len(signs), thr, 0, ip, ix)
 b, e = cd.shard_range(len(signs))
 h_sh = cd.all_gather_ranges(K.cbpa_permute(Xd, sd, b, e, thr, 0, ip, ix), len(signs))
 ok &= bool(torch.equal(h_all, h_sh))
+# per-pair thresholds: ranks split the frequency axis of the histogram passes
+thr1, hist1 = ds.null_quantile_thresholds(csd, n, 5, 0.95, passes=2, shard="surrogate" if world == 1 else "auto")
+ref_thr = None
+if True:
+    # single-GPU reference without collectives: run the passes on the whole axis by hand
+    import multimodal_biosignal_analysis_b200.dist as _cd
+    saved = _cd.world
+    _cd.world = lambda: (0, 1)
+    try:
+        ref_thr, ref_hist = ds.null_quantile_thresholds(csd, n, 5, 0.95, passes=2)
+    finally:
+        _cd.world = saved
+ok &= bool(torch.equal(thr1, ref_thr)) and bool(torch.equal(hist1, ref_hist))
+# subject-condition sweep: units dealt round-robin, maps all-reduced, CBPA sharded == the same call on one rank
+from multimodal_biosignal_analysis_b200 import sweep
+units = {}
+for s_ in range(5):
+    for c_ in ("A", "B"):
+        units[(s_, c_)] = syn.make_epochs(3, 2048, 8, 6, seed=500 + 10 * s_ + (c_ == "B"))
+adj_sp = cb.find_ch_adjacency_from_positions(syn.sensor_positions(64)[:8])
+kw = dict(nperseg=512, freq_band=(4, 60), n_surrogates=64, seed=9, spatial_adjacency=adj_sp, n_permutations=120)
+multi = sweep.cmc_surrogate_cbpa_sweep(units, 1024.0, **kw)
+_cd.world = lambda: (0, 1)
+try:
+    single = sweep.cmc_surrogate_cbpa_sweep(units, 1024.0, **kw)
+finally:
+    _cd.world = saved
+ok &= np.array_equal(multi["cmc"], single["cmc"]) and np.array_equal(multi["n_significant_pairs"], single["n_significant_pairs"])
+ok &= np.allclose(multi["threshold_fwe"], single["threshold_fwe"], rtol=1e-6)
+ra, rb = multi["cbpa"][("A", "B")], single["cbpa"][("A", "B")]
+ok &= np.array_equal(ra["H0"], rb["H0"]) and np.array_equal(ra["cluster_pv"], rb["cluster_pv"]) and np.array_equal(ra["t_obs"], rb["t_obs"])
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
