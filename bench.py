@@ -306,7 +306,7 @@ def workload_config():
                         "per step per GPU",
             "l2_policy": f"inputs larger than L2: {N_ROTATE} resident recordings (126 MB each) rotated per step",
             "parallelism": "one subject-condition per rank per step, no data-path collective",
-            "pipelining": "the EEG and EMG K1 launches of a step are parallel graph branches; consecutive steps overlap on "
+            "pipelining": "one K1 launch per step transforms the EEG and the EMG array; consecutive steps overlap on "
                           "two streams: K2 of step i runs beside K1 of step i + 1"}
 
 
@@ -363,8 +363,7 @@ def main_gpu(args):
     def step(i):
         eeg_d, emg_d = dev_sets[i % N_ROTATE]
         spec = specs[i % N_ROTATE]
-        K.fft_segments(eeg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=spec, ch_offset=0)
-        K.fft_segments(emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=spec, ch_offset=NE)
+        K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, spec[..., :NE], spec[..., NE:])
         return K.csd_msc(spec[:, 0, :, :NE], spec[:, 0, :, NE:])
 
     for i in range(warmup):
@@ -383,13 +382,9 @@ def main_gpu(args):
         gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(gA):
-            # the two K1 launches are independent: parallel branches of the graph, so the CTAs of the second start
-            # on the SMs the first one's tail leaves idle (claimed tiles balance the rest)
-            side.wait_stream(torch.cuda.current_stream())
-            K.fft_segments(eeg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=spec, ch_offset=0)
-            with torch.cuda.stream(side):
-                K.fft_segments(emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=spec, ch_offset=NE)
-            torch.cuda.current_stream().wait_stream(side)
+            # ONE K1 launch transforms both modalities (tiles of the EEG and of the EMG array share the persistent CTAs
+            # and the claim counter: one prologue and one tail instead of two)
+            K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, spec[..., :NE], spec[..., NE:])
         with torch.cuda.graph(gB):
             res_r = K.csd_msc(spec[:, 0, :, :NE], spec[:, 0, :, NE:])
         launches_per_step = _lib.launch_count() - n0
@@ -445,7 +440,7 @@ def main_gpu(args):
     ms_per_step = total_ms / steps
     value = NE * NM * world / (ms_per_step / 1e3)
     # spans seen inside the pipelined region (kernels of consecutive steps overlap, so they are not additive)
-    k1_ms_pipe = float(np.mean([a_start[i].elapsed_time(a_done[i]) for i in a_start])) / 2.0
+    k1_ms_pipe = float(np.mean([a_start[i].elapsed_time(a_done[i]) for i in a_start]))
     k2_ms_pipe = float(np.mean([b_start[i].elapsed_time(b_done[i]) for i in b_start]))
     # per-kernel durations for the roofline: the same kernels replayed back to back on ONE stream right after the timed
     # region (graphs with the two K1 launches in sequence), CUDA events between them (same process, same clocks,
@@ -455,8 +450,8 @@ def main_gpu(args):
         eeg_d, emg_d = dev_sets[r]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            K.fft_segments(eeg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=specs[r], ch_offset=0)
-            K.fft_segments(emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, out=specs[r], ch_offset=NE)
+            K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, specs[r][..., :NE],
+                                specs[r][..., NE:])
         serial_graphs.append(g)
     n_serial = min(steps, 128)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_serial)]
@@ -467,11 +462,11 @@ def main_gpu(args):
         graphs[i % N_ROTATE][1].replay()
         ev[i][2].record()
     torch.cuda.synchronize()
-    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev])) / 2.0      # per K1 launch
+    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))            # the K1 launch (both modalities)
     k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     serial_ms_per_step = float(np.mean([e[0].elapsed_time(e[2]) for e in ev]))
     n_samples = N_EPOCHS * EPOCH
-    k1_bytes = n_samples * NE * 4 + L * F * NE * 8                              # per launch (one modality)
+    k1_bytes = n_samples * (NE + NM) * 4 + L * F * (NE + NM) * 8                # per launch (both modalities)
     hbm, bf16, peak_src = peaks()
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
 
@@ -809,14 +804,14 @@ def main_gpu(args):
             "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT), tf32x3 -> f32 accumulate (CSD)",
             "data": "synthetic", "config": workload_config(),
-            "roofline": {"bound": "hbm", "kernel": "fft_segments_tma_pipe_kernel<1024> (K1, one launch per modality)",
+            "roofline": {"bound": "hbm", "kernel": "fft_segments_tma_pipe_kernel<1024> (K1, ONE launch for the EEG and the EMG array)",
                          "achieved": k1_gbs, "peak": hbm, "unit": "GB/s", "frac": k1_gbs / hbm,
                          # dram__bytes_read + dram__bytes_write of one K1 launch, ncu --set full (profiles/r01b_k1_tma.md,
                          # addendum 8: 63.0 MB read + 4.0 MB written inside the window, the rest of the output still in L2)
                          "traffic": K1_TRAFFIC_PROFILED["bytes"], "traffic_source": K1_TRAFFIC_PROFILED["source"],
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(k1_bytes), "launch_ms": k1_ms,
-                         "k2_ms_per_step": k2_ms, "k1_share_of_step": 2 * k1_ms / (2 * k1_ms + k2_ms),
+                         "k2_ms_per_step": k2_ms, "k1_share_of_step": k1_ms / (k1_ms + k2_ms),
                          "timing_note": "launch_ms / k2_ms_per_step: CUDA events around the same kernels replayed back "
                                         "to back on one stream right after the timed region (serial step "
                                         f"{serial_ms_per_step:.4f} ms); inside the two-stream timed region the spans "

@@ -77,6 +77,16 @@ CMC_API int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int64_
                      int bin_lo, int bin_hi,
                      float* spec, int64_t spec_ld, void* stream);
 
+/* The same for TWO recordings of equal length that share segments, windows and bins (EEG and EMG of one
+ * subject-condition): one launch of the pipelined kernel when both arrays qualify for its TMA path (N = 512, 1024,
+ * 2048; channel pitches multiples of 4 floats, 16-byte aligned bases), otherwise two cmc_fft_segments calls - the
+ * results are identical either way.  spec1 / spec2 use the row pitch spec_ld (e.g. two channel ranges of one array). */
+CMC_API int cmc_fft_segments_pair(const float* x1, int n_ch1, int64_t ld1, float* spec1,
+                          const float* x2, int n_ch2, int64_t ld2, float* spec2,
+                          int64_t n_samples, const int64_t* seg_starts, int n_seg,
+                          const float* windows, int n_win, int N, int detrend,
+                          int bin_lo, int bin_hi, int64_t spec_ld, void* stream);
+
 /* Power spectra from segment spectra: out[w][f][c] = base_scale * dbl(f) * mean_k |spec[w][k][f][c]|^2, with
  * dbl(f) = 2 for bins strictly inside (0, N/2) when one_sided != 0 (scipy density convention), optionally
  * followed by log10(|.| + 1e-10).  Replaces signal.periodogram + mean over tapers of multitaper_psd
@@ -201,11 +211,14 @@ CMC_API int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, int
  * per-pair (lo, scale) arrays zoom into a sub-range in a second pass.  Same surrogates as cmc_surrogate_null for
  * the same (seed, s, l, f); counts are ADDED to hist, so chunks of the surrogate range accumulate.
  *   hist [F][Ne][Nm][n_bins] uint32 (caller zero-initialises), 2 <= n_bins <= 128; ws / ws2 as for
- *   cmc_surrogate_null (mode CMC_SURR_PHASE only; CMC_SURR_SHIFT returns CMC_EUNSUPPORTED). */
+ *   cmc_surrogate_null (mode CMC_SURR_PHASE only; CMC_SURR_SHIFT returns CMC_EUNSUPPORTED).
+ *   reuse_operands != 0: ws2 still holds the phase panel and cross-product rows that an earlier
+ *   cmc_surrogate_null[_range / _hist] call generated for the SAME ws, seed, surrogate range and frequency range
+ *   (e.g. the exceedance pass, or the previous zoom pass): their generation is skipped. */
 CMC_API int cmc_surrogate_null_hist(void* ws, int L, int F, int Ne, int Nm, int mode, uint64_t seed,
                             int64_t s_begin, int64_t s_end, int f_begin, int f_end, int n_bins,
                             const float* bin_lo, const float* bin_scale, uint32_t* hist,
-                            void* ws2, int64_t ws2_bytes, void* stream);
+                            void* ws2, int64_t ws2_bytes, int reuse_operands, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K4  cluster-based permutation test: sign-flip t-map -> threshold -> connected-component

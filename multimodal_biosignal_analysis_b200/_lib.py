@@ -23,6 +23,8 @@ _SIGNATURES = {
     "cmc_launch_count": (_i64, []),
     "cmc_fft_segments": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32,
                                    _vp, _i64, _vp]),
+    "cmc_fft_segments_pair": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i32, _i64, _vp, _i64, _vp, _i32, _vp, _i32, _i32,
+                                        _i32, _i32, _i32, _i64, _vp]),
     "cmc_psd_from_spectra": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _f32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "cmc_msc_windows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i32, _f32, _f32,
                                   _vp, _vp, _vp, _vp, _vp]),
@@ -40,7 +42,7 @@ _SIGNATURES = {
     "cmc_surrogate_null_range": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _u64, _i64, _i64, _i32, _i32,
                                            _vp, _vp, _vp, _vp, _i64, _vp]),
     "cmc_surrogate_null_hist": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _u64, _i64, _i64, _i32, _i32, _i32,
-                                          _vp, _vp, _vp, _vp, _i64, _vp]),
+                                          _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "cmc_cbpa_workspace_bytes": (_i64, [_i32, _i32]),
     "cmc_cbpa_permute": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _i64, _f64, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cmc_cbpa_observed": (C.c_int, [_vp, _i32, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,

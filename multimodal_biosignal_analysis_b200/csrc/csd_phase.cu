@@ -390,10 +390,11 @@ phase_hist_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     constexpr int kStageBytes = kPhABytes + kPhBBytes;
     unsigned char* sB = base;                                                      // [kPhHistStages][48 KB]
-    uint32_t* hist_s = reinterpret_cast<uint32_t*>(sB + kPhHistStages * kStageBytes);   // [128][n_bins]
-    float* lo_s = reinterpret_cast<float*>(hist_s + kPhPairs * p.n_bins);          // [128]
-    float* sc_s = lo_s + kPhPairs;                                                 // [128]
-    PhaseBarriers* bars = reinterpret_cast<PhaseBarriers*>(sc_s + kPhPairs);
+    uint32_t* hist_s = reinterpret_cast<uint32_t*>(sB + kPhHistStages * kStageBytes);   // [128][n_bins + 1]
+    const int hp = p.n_bins + 1;                  // padded histogram row: lanes that hit the same bin of 32 different
+                                                  // pairs fall into 32 different banks
+    float* stage_s = reinterpret_cast<float*>(hist_s + kPhPairs * hp);            // [128][33] transposition tile
+    PhaseBarriers* bars = reinterpret_cast<PhaseBarriers*>(stage_s + kPhM * 33);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = p.F * p.NT;
@@ -465,54 +466,72 @@ phase_hist_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                 }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: lane = surrogate row of the panel, columns = the unit's 128 pairs =====
+        // ===== epilogue: TMEM lane = surrogate row of the panel, columns = the unit's 128 pairs =====
+        // All 32 lanes of a warp hold the SAME pair in a given column, and under the null their values crowd into a
+        // few bins: binning straight from the accumulator layout serialises on same-address shared-memory atomics
+        // (3.5 ms per 1,024 surrogates, tensor pipe 10 % busy).  So every 32-column chunk is transposed through a
+        // padded shared tile first: thread (column c = te % 32, row block te / 32) then walks 32 surrogates of ONE
+        // pair, the lanes of a warp update 32 different histogram rows, and only the four row blocks of a column
+        // still meet in an atomic.
         const int q = warp - 4;
         const int te = threadIdx.x - 128;
         const float nb = (float)p.n_bins;
+        const int tc_col = te & 31, tc_rb = te >> 5;            // transposed role: column of the chunk, row block
         uint32_t it = 0;
         for (int un = blockIdx.x; un < n_units; un += gridDim.x) {
             const int f = un / p.NT, nt = un - f * p.NT;
-            const int pair_t = nt * kPhPairs + te;
-            const bool pair_ok = pair_t < p.n_pairs;
-            lo_s[te] = (pair_ok && p.bin_lo) ? __ldg(p.bin_lo + (int64_t)f * p.n_pairs + pair_t) : 0.f;
-            sc_s[te] = (pair_ok && p.bin_scale) ? __ldg(p.bin_scale + (int64_t)f * p.n_pairs + pair_t) : nb;
-            for (int i = te; i < kPhPairs * p.n_bins; i += 128) hist_s[i] = 0u;
+            // bin origin / scale of the four pairs this thread bins (column tc_col of every 32-column chunk)
+            float lo_r[4], sc_r[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const int pair_t = nt * kPhPairs + ch * 32 + tc_col;
+                const bool pair_ok = pair_t < p.n_pairs;
+                lo_r[ch] = (pair_ok && p.bin_lo) ? __ldg(p.bin_lo + (int64_t)f * p.n_pairs + pair_t) : 0.f;
+                sc_r[ch] = (pair_ok && p.bin_scale) ? __ldg(p.bin_scale + (int64_t)f * p.n_pairs + pair_t) : nb;
+            }
+            for (int i = te; i < kPhPairs * hp; i += 128) hist_s[i] = 0u;
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int mt = 0; mt < p.MT; ++mt) {
-                const bool s_ok = mt * kPhM + te < p.n_local;
+                const int n_rows = min(kPhM, p.n_local - mt * kPhM);      // valid surrogate rows of this panel
                 const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
                 mbar_wait(&bars->tmem_full[acc], accphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * kPhN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
+#pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                     uint32_t re[32], im[32];
                     tmem_ld_32x32(taddr + ch * 32, re);
                     tmem_ld_32x32(taddr + kPhPairs + ch * 32, im);
                     tmem_ld_wait();
-                    if (s_ok) {
+                    float* row = stage_s + te * 33;
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float a = __uint_as_float(re[c]), b = __uint_as_float(im[c]);
-                            // |coherency| in [0, 1): C = 1 is binned with the largest float below 1
-                            const float v = fminf(sqrtf((a * a + b * b) * kZUnscaleSq), 0.99999994f);
-                            const float x = (v - lo_s[ch * 32 + c]) * sc_s[ch * 32 + c];
-                            // x >= 0 first: the float -> int conversion of a negative value must not wrap into range
-                            if (x >= 0.f && x < nb) atomicAdd(&hist_s[(ch * 32 + c) * p.n_bins + (int)x], 1u);
-                        }
+                    for (int c = 0; c < 32; ++c) {
+                        const float a = __uint_as_float(re[c]), b = __uint_as_float(im[c]);
+                        // |coherency| in [0, 1): C = 1 is binned with the largest float below 1
+                        row[c] = fminf(sqrtf((a * a + b * b) * kZUnscaleSq), 0.99999994f);
                     }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const float lo = lo_r[ch], sc = sc_r[ch];
+                    uint32_t* hrow = hist_s + (ch * 32 + tc_col) * hp;
+                    const int r_end = min(32, n_rows - tc_rb * 32);
+#pragma unroll 4
+                    for (int r = 0; r < r_end; ++r) {
+                        const float x = (stage_s[(tc_rb * 32 + r) * 33 + tc_col] - lo) * sc;
+                        // x >= 0 first: the float -> int conversion of a negative value must not wrap into range
+                        if (x >= 0.f && x < nb) atomicAdd(hrow + (int)x, 1u);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");         // the tile is rewritten by the next chunk
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
                 ++it;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
             // flush: rows of padding pairs (beyond n_pairs) hold counts of the zero rows of Z and are dropped
             const int rows = min(kPhPairs, p.n_pairs - nt * kPhPairs);
             uint32_t* g = p.hist + ((int64_t)f * p.n_pairs + (int64_t)nt * kPhPairs) * p.n_bins;
             for (int i = te; i < rows * p.n_bins; i += 128) {
-                const uint32_t v = hist_s[i];
+                const uint32_t v = hist_s[(i / p.n_bins) * hp + (i % p.n_bins)];
                 if (v) g[i] += v;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -563,10 +582,13 @@ int64_t phase_workspace_bytes(int L, int F, int Ne, int Nm, int64_t n_surr) {
 }
 
 // Operand generation + GEMM launch per frequency chunk, shared by the exceedance null and the histogram pass.
-// `launch(fc, f0, mA, mB, y)` enqueues the GEMM kernel of one chunk.
+// `launch(fc, f0, mA, mB, y)` enqueues the GEMM kernel of one chunk.  `reuse`: ws2 still holds the phase panel and
+// the Z rows that an earlier call generated for the SAME (ws, seed, surrogate range, frequency range) - honoured
+// when the range is one chunk (otherwise only the last chunk's operands survive and everything is regenerated).
 template <typename Launch>
 static int phase_run(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t n, int f_begin,
-                     int f_end, void* ws2, int64_t ws2_bytes, cudaStream_t st, const PhaseLayout& y, Launch launch) {
+                     int f_end, void* ws2, int64_t ws2_bytes, cudaStream_t st, const PhaseLayout& y, bool reuse,
+                     Launch launch) {
     CMC_REQUIRE(n < (1ll << 31) - 256, "cmc_surrogate_null: too many surrogates in one call");
     const CsdLayout cy = csd_layout(L, F, Ne, Nm);
     if (ws2_bytes < y.total) {
@@ -582,17 +604,18 @@ static int phase_run(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed
     unsigned char* w2 = static_cast<unsigned char*>(ws2);
     __half* A = reinterpret_cast<__half*>(w2 + y.off_A);
     __half* Z = reinterpret_cast<__half*>(w2 + y.off_Z);
+    const bool keep = reuse && f_end - f_begin <= y.f_chunk;
     for (int f0 = f_begin; f0 < f_end; f0 += y.f_chunk) {
         const int fc = f_end - f0 < y.f_chunk ? f_end - f0 : y.f_chunk;
-        if (y.n_pairs_pad != y.n_pairs) {
+        if (!keep && y.n_pairs_pad != y.n_pairs) {
             rc = check_cuda(cudaMemsetAsync(Z, 0, (size_t)fc * y.R_pad * y.KPb * 2, st), "memset(Z)");
             if (rc) return rc;
         }
         // Philox counters use GLOBAL frequency groups of 4; a chunk may start inside a group
-        phase_gen_kernel<<<dim3((y.KPb / 2 + 255) / 256, y.S_pad, ((f0 + fc - 1) >> 2) - (f0 >> 2) + 1), 256, 0, st>>>(
+        if (!keep) phase_gen_kernel<<<dim3((y.KPb / 2 + 255) / 256, y.S_pad, ((f0 + fc - 1) >> 2) - (f0 >> 2) + 1), 256, 0, st>>>(
             table, seed, s_begin, (int)n, y.S_pad, L, y.nterms, fc, f0, y.KPb, A);
         CMC_CHECK_LAUNCH("phase_gen_kernel");
-        (y.nterms == 3 ? z_gen_kernel<3> : z_gen_kernel<1>)<<<dim3(fc, Ne), 256, (size_t)L * 8, st>>>(
+        if (!keep) (y.nterms == 3 ? z_gen_kernel<3> : z_gen_kernel<1>)<<<dim3(fc, Ne), 256, (size_t)L * 8, st>>>(
             reinterpret_cast<const float*>(w + cy.off_ahi) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_alo) + (int64_t)f0 * cy.MT * kTileM * cy.KP,
             reinterpret_cast<const float*>(w + cy.off_bhi) + (int64_t)f0 * cy.NT * kTileN * cy.KP,
@@ -636,7 +659,7 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
     rc = check_cuda(cudaMemsetAsync(max_u, 0, (size_t)y.S_pad * 4, st), "memset(max_u)");
     if (rc) return rc;
     const int sms = sm_count();
-    rc = phase_run(ws, L, F, Ne, Nm, seed, s_begin, n, f_begin, f_end, ws2, ws2_bytes, st, y,
+    rc = phase_run(ws, L, F, Ne, Nm, seed, s_begin, n, f_begin, f_end, ws2, ws2_bytes, st, y, false,
                    [&](int fc, int f0, const CUtensorMap& mA, const CUtensorMap& mB) -> int {
                        PhaseParams p{};
                        p.F = fc; p.MT = y.MT; p.NT = y.NT; p.KB = y.KB; p.n_local = (int)n; p.n_pairs = y.n_pairs;
@@ -657,17 +680,17 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
 
 int phase_surrogate_hist(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
                          int f_begin, int f_end, int n_bins, const float* bin_lo, const float* bin_scale,
-                         uint32_t* hist, void* ws2, int64_t ws2_bytes, cudaStream_t st) {
+                         uint32_t* hist, void* ws2, int64_t ws2_bytes, bool reuse, cudaStream_t st) {
     const int64_t n = s_end - s_begin;
     CMC_REQUIRE(n_bins >= 2 && n_bins <= kPhHistMaxBins, "cmc_surrogate_null_hist: n_bins must be in [2, %d]",
                 kPhHistMaxBins);
     const PhaseLayout y = phase_layout(L, F, Ne, Nm, n);
-    const size_t smem = 1024 + (size_t)kPhHistStages * (kPhABytes + kPhBBytes) + (size_t)kPhPairs * n_bins * 4 +
-                        kPhPairs * 8 + sizeof(PhaseBarriers) + 16;
+    const size_t smem = 1024 + (size_t)kPhHistStages * (kPhABytes + kPhBBytes) + (size_t)kPhPairs * (n_bins + 1) * 4 +
+                        (size_t)kPhM * 33 * 4 + sizeof(PhaseBarriers) + 16;
     int rc = ensure_smem_attr(reinterpret_cast<const void*>(phase_hist_kernel), smem);
     if (rc) return rc;
     const int sms = sm_count();
-    return phase_run(ws, L, F, Ne, Nm, seed, s_begin, n, f_begin, f_end, ws2, ws2_bytes, st, y,
+    return phase_run(ws, L, F, Ne, Nm, seed, s_begin, n, f_begin, f_end, ws2, ws2_bytes, st, y, reuse,
                      [&](int fc, int f0, const CUtensorMap& mA, const CUtensorMap& mB) -> int {
                          PhaseHistParams p{};
                          p.F = fc; p.MT = y.MT; p.NT = y.NT; p.KB = y.KB; p.n_local = (int)n; p.n_pairs = y.n_pairs;

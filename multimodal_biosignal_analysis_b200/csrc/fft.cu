@@ -247,7 +247,8 @@ static int get_full_twiddles(int N, const float2** tw) {
 
 int fft_segments_tma(const float* x, int64_t n_samples, int n_ch, int64_t ld, const int64_t* seg_starts, int n_seg,
                      const float* windows, int n_win, int N, int detrend, int bin_lo, int F, float2* spec,
-                     int64_t spec_ld, const float2* twM, const float2* twN, cudaStream_t st);
+                     int64_t spec_ld, const float2* twM, const float2* twN, cudaStream_t st, const float* x2 = nullptr,
+                     int n_ch2 = 0, int64_t ld2 = 0, float2* spec2 = nullptr);
 
 }  // namespace cmc
 
@@ -307,4 +308,37 @@ extern "C" int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int
     }
 #undef CMC_FFT_CASE
     return CMC_EUNSUPPORTED;
+}
+
+// Two recordings of equal length that share the segment table, the window rows and the bin range (the EEG and the
+// EMG array of one subject-condition) in ONE launch of the pipelined K1 kernel when both qualify for it; any other
+// case runs as two cmc_fft_segments calls with identical results.  spec1 / spec2 share the row pitch spec_ld
+// (typically two channel ranges of one [n_seg][n_win][F][spec_ld] array).
+extern "C" int cmc_fft_segments_pair(const float* x1, int n_ch1, int64_t ld1, float* spec1,
+                                     const float* x2, int n_ch2, int64_t ld2, float* spec2,
+                                     int64_t n_samples, const int64_t* seg_starts, int n_seg,
+                                     const float* windows, int n_win, int N, int detrend,
+                                     int bin_lo, int bin_hi, int64_t spec_ld, void* stream) {
+    using namespace cmc;
+    CMC_REQUIRE(x1 && x2 && seg_starts && windows && spec1 && spec2, "cmc_fft_segments_pair: null pointer");
+    const bool fast = n_seg > 0 && n_ch1 >= 1 && n_ch2 >= 1 && ld1 >= n_ch1 && ld2 >= n_ch2 && spec_ld >= n_ch1 &&
+                      spec_ld >= n_ch2 && n_win >= 1 && detrend >= 0 && detrend <= 2 && bin_lo >= 0 &&
+                      bin_hi >= bin_lo && bin_hi <= N / 2 && (N == 512 || N == 1024 || N == 2048) &&
+                      (reinterpret_cast<uintptr_t>(windows) & 7) == 0 && (reinterpret_cast<uintptr_t>(spec1) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(spec2) & 7) == 0;
+    static const bool no_pair = getenv("CMC_FFT_NO_PAIR") != nullptr || getenv("CMC_FFT_NO_TMA") != nullptr;
+    if (fast && !no_pair) {
+        const float2 *twM, *twN;
+        int rc = get_twiddles(N, &twM, &twN);
+        if (rc) return rc;
+        rc = fft_segments_tma(x1, n_samples, n_ch1, ld1, seg_starts, n_seg, windows, n_win, N, detrend, bin_lo,
+                              bin_hi - bin_lo + 1, reinterpret_cast<float2*>(spec1), spec_ld, twM, twN,
+                              static_cast<cudaStream_t>(stream), x2, n_ch2, ld2, reinterpret_cast<float2*>(spec2));
+        if (rc != 1) return rc;
+    }
+    int rc = cmc_fft_segments(x1, n_samples, n_ch1, ld1, seg_starts, n_seg, windows, n_win, N, detrend, bin_lo, bin_hi,
+                              spec1, spec_ld, stream);
+    if (rc) return rc;
+    return cmc_fft_segments(x2, n_samples, n_ch2, ld2, seg_starts, n_seg, windows, n_win, N, detrend, bin_lo, bin_hi,
+                            spec2, spec_ld, stream);
 }

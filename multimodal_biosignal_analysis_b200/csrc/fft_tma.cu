@@ -445,9 +445,18 @@ __device__ __forceinline__ void worker_leave(TileCounter* ctr, int tid) {
     }
 }
 
+// The kernel serves ONE or TWO recordings that share the segment table, the window rows and the bin range (EEG and
+// EMG of one subject-condition): a tile index runs over (segment, channel tile of recording 0 | 1), so the two
+// modalities share one launch - one prologue, one tail of partly idle SMs, one claim counter - instead of two.
+struct PipeSecond {
+    int n_ch;                // channels of the second recording (0 = none)
+    float2* spec;            // its output base (channel 0 of the second recording)
+};
+
 template <int M, bool TAB>
 __global__ void __launch_bounds__(M / 2, 1)
-fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch, int n_seg,
+fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap2,
+                             int n_ch, const PipeSecond second, int n_seg,
                              const int64_t* __restrict__ seg_starts, const float* __restrict__ windows, int n_win,
                              int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
                              const float2* __restrict__ twM, const float2* __restrict__ twN, TileCounter* ctr) {
@@ -474,9 +483,16 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
     const int bar_id = 1 + worker;
     float* part = part_all + worker * (NT / 32) * kTmaCT;
     float* mean_s = mean_all + worker * kTmaCT;
-    const int n_ct = (n_ch + kTmaCT - 1) / kTmaCT;
+    const int n_ct0 = (n_ch + kTmaCT - 1) / kTmaCT;
+    const int n_ct = n_ct0 + (second.n_ch + kTmaCT - 1) / kTmaCT;
     const long long total = (long long)n_seg * n_ct;
     long long t = 2ll * blockIdx.x + worker;   // first tile is static, the rest come from the counter
+    // tile -> (recording, first channel): channel tiles [0, n_ct0) belong to the first recording
+    auto tile_map = [&](long long tile, int& c0) -> const CUtensorMap* {
+        const int ct = (int)(tile % n_ct);
+        c0 = (ct < n_ct0 ? ct : ct - n_ct0) * kTmaCT;
+        return ct < n_ct0 ? &tmap : &tmap2;
+    };
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < 3; ++b) {
@@ -487,6 +503,7 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
         ctl->next_buf[0] = ctl->next_buf[1] = -1;
         fence_barrier_init();
         tma_prefetch_desc(&tmap);
+        if (second.n_ch) tma_prefetch_desc(&tmap2);
     }
     __syncthreads();
     if (t >= total) {                          // this worker has no tile; buffer 2 stays with the other worker
@@ -498,13 +515,19 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
     unsigned cur_parity = 0;
     long long tn = total, tnn = total;         // thread 0 of the worker: tiles claimed for the next two rounds
     if (tid == 0) {
-        issue_tile_tma<M>(base + cur * kTileBytes, &tmap, &ctl->full[cur], (int)(t % n_ct) * kTmaCT,
-                          (int)seg_starts[t / n_ct]);
+        int c0f;
+        const CUtensorMap* mf = tile_map(t, c0f);
+        issue_tile_tma<M>(base + cur * kTileBytes, mf, &ctl->full[cur], c0f, (int)seg_starts[t / n_ct]);
         ctl->fills[cur] = 1;
         tn = ctr ? 2ll * gridDim.x + atomicAdd(&ctr->next, 1u) : t + 2ll * gridDim.x;
     }
     while (true) {
-        const int seg = (int)(t / n_ct), c0 = (int)(t % n_ct) * kTmaCT;
+        const int seg = (int)(t / n_ct);
+        int c0;
+        const CUtensorMap* cur_map = tile_map(t, c0);
+        const bool is2 = cur_map == &tmap2;
+        const int cur_nch = is2 ? second.n_ch : n_ch;
+        float2* cur_spec = is2 ? second.spec : spec;
         if (tid == 0) {
             ctl->next_tile[worker] = tn;       // read by the whole worker after the tile's last barrier
             // claim one round ahead: the atomic's round trip hides behind this tile
@@ -514,7 +537,7 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
             if (kw > 0 && tid == 0) {          // the in-place transform consumed the raw tile: fetch it again
                 cur_parity = ctl->fills[cur] & 1;
                 ctl->fills[cur] += 1;
-                issue_tile_tma<M>(base + cur * kTileBytes, &tmap, &ctl->full[cur], c0, (int)seg_starts[seg]);
+                issue_tile_tma<M>(base + cur * kTileBytes, cur_map, &ctl->full[cur], c0, (int)seg_starts[seg]);
             }
             if (kw > 0) {
                 group_sync(bar_id, NT);
@@ -535,15 +558,16 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
                     if (fb >= 0) {
                         ctl->next_parity[worker] = ctl->fills[fb] & 1;
                         ctl->fills[fb] += 1;
-                        issue_tile_tma<M>(base + fb * kTileBytes, &tmap, &ctl->full[fb], (int)(tn % n_ct) * kTmaCT,
-                                          (int)seg_starts[tn / n_ct]);
+                        int c0n;
+                        const CUtensorMap* mn = tile_map(tn, c0n);
+                        issue_tile_tma<M>(base + fb * kTileBytes, mn, &ctl->full[fb], c0n, (int)seg_starts[tn / n_ct]);
                         ctl->next_buf[worker] = fb;
                     }
                 }
             };
             poll();
             process_tile<M, false, decltype(poll), TAB>(poll, smem_u32(base + cur * kTileBytes), part, mean_s, tid, bar_id,
-                                                        kw, seg, c0, n_ch, windows, n_win, detrend, bin_lo, F, spec,
+                                                        kw, seg, c0, cur_nch, windows, n_win, detrend, bin_lo, F, cur_spec,
                                                         spec_ld, twM, twN, tab_s);
         }
         // process_tile ended with a worker barrier: the buffer is no longer read and ctl->next_* is visible
@@ -572,8 +596,9 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
             // no prefetch happened (the other worker held the idle buffer): reload in place
             if (tid == 0) {
                 ctl->fills[cur] += 1;
-                issue_tile_tma<M>(base + cur * kTileBytes, &tmap, &ctl->full[cur], (int)(t % n_ct) * kTmaCT,
-                                  (int)seg_starts[t / n_ct]);
+                int c0r;
+                const CUtensorMap* mr = tile_map(t, c0r);
+                issue_tile_tma<M>(base + cur * kTileBytes, mr, &ctl->full[cur], c0r, (int)seg_starts[t / n_ct]);
             }
             group_sync(bar_id, NT);
             cur_parity = (ctl->fills[cur] - 1) & 1;
@@ -597,7 +622,8 @@ static int launch_tma(const CUtensorMap& tmap, int n_ch, const int64_t* seg_star
 }
 
 template <int M>
-static int launch_tma_pipe(const CUtensorMap& tmap, int n_ch, const int64_t* seg_starts, int n_seg, const float* windows,
+static int launch_tma_pipe(const CUtensorMap& tmap, int n_ch, const CUtensorMap& tmap2, const PipeSecond& second,
+                           const int64_t* seg_starts, int n_seg, const float* windows,
                            int n_win, int detrend, int bin_lo, int F, float2* spec, int64_t spec_ld, const float2* twM,
                            const float2* twN, cudaStream_t st) {
     constexpr int NT = M / 4;
@@ -613,53 +639,76 @@ static int launch_tma_pipe(const CUtensorMap& tmap, int n_ch, const int64_t* seg
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT);
+    const long long tiles = (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT + (second.n_ch + kTmaCT - 1) / kTmaCT);
     const long long grid = (tiles + 1) / 2 < sms ? (tiles + 1) / 2 : sms;
     // claim counter private to this launch's stream / graph node (zero-initialised device memory, reset by the kernel)
     static const bool static_tiles = getenv("CMC_FFT_STATIC_TILES") != nullptr;      // fixed stride instead of claims
     TileCounter* ctr = static_tiles ? nullptr : tile_counter_for(dev, st);
-    kern<<<(unsigned)grid, 2 * NT, smem, st>>>(tmap, n_ch, n_seg, seg_starts, windows, n_win, detrend, bin_lo, F, spec,
-                                               spec_ld, twM, twN, ctr);
+    kern<<<(unsigned)grid, 2 * NT, smem, st>>>(tmap, tmap2, n_ch, second, n_seg, seg_starts, windows, n_win, detrend,
+                                               bin_lo, F, spec, spec_ld, twM, twN, ctr);
     CMC_CHECK_LAUNCH("fft_segments_tma_pipe_kernel");
     return CMC_OK;
 }
 
-// Returns 1 when the request does not qualify for the TMA path (caller falls back to fft_segments_kernel).
-int fft_segments_tma(const float* x, int64_t n_samples, int n_ch, int64_t ld, const int64_t* seg_starts, int n_seg,
-                     const float* windows, int n_win, int N, int detrend, int bin_lo, int F, float2* spec,
-                     int64_t spec_ld, const float2* twM, const float2* twN, cudaStream_t st) {
-    if (N != 512 && N != 1024 && N != 2048 && N != 4096) return 1;
-    if ((ld & 3) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 || n_samples >= (1ll << 31)) return 1;
+static bool tma_layout_ok(const float* x, int64_t n_samples, int64_t ld) {
+    return (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && n_samples < (1ll << 31);
+}
+
+static int make_recording_map(CUtensorMap* tmap, const float* x, int64_t n_samples, int n_ch, int64_t ld) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
     // SWIZZLE_64B with a 32-byte inner box faults on sm_100 (illegal memory access, found on hardware with
     // a probe script in round 1), so the raw tile is loaded unswizzled: first-pass reads are then 2-way bank
     // conflicted (4 instead of 2 wavefronts per request), every other access is conflict free.
-    constexpr bool swz = false;
-    CUtensorMap tmap;
     cuuint64_t dims[2] = {(cuuint64_t)n_ch, (cuuint64_t)n_samples};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
     cuuint32_t box[2] = {(cuuint32_t)kTmaCT, 256u};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(recording) failed with CUresult %d", (int)r);
         return CMC_ECUDA;
     }
+    return CMC_OK;
+}
+
+// Returns 1 when the request does not qualify for the TMA path (caller falls back to fft_segments_kernel).
+// x2 != nullptr: a second recording (n_ch2 channels, pitch ld2, same length / segments / windows / bins) transformed
+// by the same launch into spec2; only the pipelined kernel takes pairs (returns 1 otherwise, the caller then issues
+// two single calls).
+int fft_segments_tma(const float* x, int64_t n_samples, int n_ch, int64_t ld, const int64_t* seg_starts, int n_seg,
+                     const float* windows, int n_win, int N, int detrend, int bin_lo, int F, float2* spec,
+                     int64_t spec_ld, const float2* twM, const float2* twN, cudaStream_t st, const float* x2, int n_ch2,
+                     int64_t ld2, float2* spec2) {
+    if (N != 512 && N != 1024 && N != 2048 && N != 4096) return 1;
+    if (!tma_layout_ok(x, n_samples, ld)) return 1;
+    if (x2 && (!tma_layout_ok(x2, n_samples, ld2) || N == 4096)) return 1;
+    CUtensorMap tmap, tmap2;
+    int rc = make_recording_map(&tmap, x, n_samples, n_ch, ld);
+    if (rc) return rc;
+    PipeSecond second{0, nullptr};
+    if (x2) {
+        if ((rc = make_recording_map(&tmap2, x2, n_samples, n_ch2, ld2))) return rc;
+        second.n_ch = n_ch2;
+        second.spec = spec2;
+    } else {
+        tmap2 = tmap;
+    }
     // pipelined persistent kernel whenever three tiles fit into shared memory (N <= 2048) and there is enough work
     static const bool no_pipe = getenv("CMC_FFT_NO_PIPE") != nullptr;
-    if (!no_pipe && (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT) >= 64) {
+    const long long n_tiles = (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT + (second.n_ch + kTmaCT - 1) / kTmaCT);
+    if (!no_pipe && n_tiles >= 64) {
         switch (N) {
-            case 512:  return launch_tma_pipe<256>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
-            case 1024: return launch_tma_pipe<512>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
-            case 2048: return launch_tma_pipe<1024>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            case 512:  return launch_tma_pipe<256>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            case 1024: return launch_tma_pipe<512>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            case 2048: return launch_tma_pipe<1024>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
             default: break;
         }
     }
+    if (x2) return 1;
     switch (N) {
         case 512: return launch_tma<256, false>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
         case 1024: return launch_tma<512, false>(tmap, n_ch, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);

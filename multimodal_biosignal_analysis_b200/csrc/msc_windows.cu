@@ -14,18 +14,42 @@ namespace cmc {
 constexpr int kMscThreads = 256;
 constexpr int kFreqPerBlock = 4;
 
-// The transcendental epilogue dominates this kernel (6 Fisher transforms + 2 inverse transforms per output), so
-// both use the MUFU-backed intrinsics: __logf is within 2^-21.4 absolute on [0.5, 2] and 3 ulp elsewhere, __expf
-// within 2 ulp of exp on the range used - z errors ~1e-6, far inside the 1e-4 gate on coherence / CI bounds.
+// The transcendental epilogue dominates this kernel (6 Fisher transforms + 2 inverse transforms per output) and the
+// kernel is issue bound, so both are written on the bare MUFU approximations with flush-to-zero (no denormal can
+// occur: the arguments are clamped into [6e-8, 3.4e7]) - the default __logf / __expf / sqrtf expansions carry a
+// denormal rescue and a Newton step per call, which doubled the instruction count of an output (431 -> ~220):
+//   z(c)   = 0.5 ln((1 + c) / (1 - c)) = (ln 2 / 2) * lg2((1 + c) * rcp(1 - c))      RCP + LG2, 2 ulp each
+//   z^-1   = tanh(z)^2,  tanh(z) = 1 - 2 * rcp(ex2(2 z log2 e) + 1)                   EX2 + RCP
+// z errors ~3e-7 relative, far inside the 1e-4 gate on coherence / CI bounds.
+__device__ __forceinline__ float mufu_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float fisher_z(float c) {
     // signal_features.py:459-462 with the clip bounds representable in float32
     c = fminf(fmaxf(c, 1e-10f), 0.99999994f);
-    return 0.5f * (__logf(1.0f + c) - __logf(1.0f - c));
+    return 0.34657359028f * mufu_lg2((1.0f + c) * mufu_rcp(1.0f - c));
 }
 __device__ __forceinline__ float inv_fisher(float z) {
     // tanh(z)^2 with tanh(z) = 1 - 2 / (exp(2 z) + 1); |z| is capped where tanh saturates in float32
-    const float e = __expf(2.0f * fminf(fmaxf(z, -12.0f), 12.0f));
-    const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
+    const float e = mufu_ex2(2.88539008178f * fminf(fmaxf(z, -12.0f), 12.0f));
+    const float t = fmaf(-2.0f, mufu_rcp(e + 1.0f), 1.0f);
     return t * t;
 }
 __device__ __forceinline__ float msc_ratio(float re, float im, float sxx, float syy) {
@@ -87,7 +111,7 @@ __device__ __forceinline__ PairStats pair_stats(const float2 (&x)[K], const floa
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) ss += (z[k] - zbar) * (z[k] - zbar);
-    const float se = sqrtf(ss * ((float)(K - 1) / (float)K));
+    const float se = mufu_sqrt(ss * ((float)(K - 1) / (float)K));
     const float zc = fisher_z(mean);
     out.coh = mean;
     out.lo = fminf(inv_fisher(zc - t_crit * se), mean);
@@ -131,7 +155,7 @@ __device__ __forceinline__ PairStats pair_stats_jk(const float2 (&x)[K], const f
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) ss += (z[k] - zbar) * (z[k] - zbar);
-    const float se = sqrtf(ss * ((float)(K - 1) / (float)K));
+    const float se = mufu_sqrt(ss * ((float)(K - 1) / (float)K));
     const float zc = fisher_z(mean);
     PairStats out;
     out.coh = mean;

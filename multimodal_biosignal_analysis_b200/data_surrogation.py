@@ -171,7 +171,8 @@ def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int 
     (``null_hist`` (F, Ne, Nm, hist_bins) over uniform |coherency| bins, ``null_hist_edges``)."""
     csd = pooled.device_result
     begin, end, f_range, by_freq = _plan(n_surrogates, csd.dims[1], shard)
-    exceed, max_local = K.surrogate_null(csd, K.SURR_PHASE, begin, end, seed=seed, f_range=f_range)
+    exceed, max_local = K.surrogate_null(csd, K.SURR_PHASE, begin, end, seed=seed, f_range=f_range,
+                                         keep_phase_operands=(thresholds or return_hist) and (begin, end) == (0, n_surrogates))
     out = _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq, f_range)
     if thresholds or return_hist:
         thr, hist = null_quantile_thresholds(csd, n_surrogates, seed, 1.0 - alpha, passes=threshold_passes,
@@ -215,7 +216,8 @@ def null_quantile_thresholds(csd, n_surrogates: int, seed: int, q: float, passes
     for p in range(passes):
         scale = torch.full((F, Ne, Nm), n_bins / width, dtype=torch.float32, device=dev)
         hist = K.surrogate_null_hist(csd, 0, n, seed=seed, n_bins=n_bins, bin_lo=lo if p else None,
-                                     bin_scale=scale if p else None, f_range=(fb, fe))
+                                     bin_scale=scale if p else None, f_range=(fb, fe),
+                                     keep_operands=p + 1 < passes)
         if first is None:
             first = hist
         cum = torch.cumsum(hist, dim=-1, dtype=torch.int32) + below[..., None]
@@ -278,12 +280,12 @@ def surrogate_null_sweep(recordings, sampling_freq: float, nperseg: int = 256, n
     def compute(slot, i):
         u = int(next(units)) if units is not None else i
         unit_of[i] = u
-        if "X" not in slot:
-            slot["X"] = torch.empty((L, 1, F, ne_p), dtype=torch.complex64, device=dev)
-            slot["Y"] = torch.empty((L, 1, F, nm_p), dtype=torch.complex64, device=dev)
-        K.fft_segments(slot["eeg"], starts_d, wd, dmode, lo, hi, out=slot["X"], ch_offset=0)
-        K.fft_segments(slot["emg"], starts_d, wd, dmode, lo, hi, out=slot["Y"], ch_offset=0)
-        csd = K.csd_msc(slot["X"].view(L, F, ne_p)[:, :, :ne], slot["Y"].view(L, F, nm_p)[:, :, :nm])
+        if "S" not in slot:
+            slot["S"] = torch.empty((L, 1, F, ne_p + nm_p), dtype=torch.complex64, device=dev)
+        sp = slot["S"]
+        K.fft_segments_pair(slot["eeg"], slot["emg"], starts_d, wd, dmode, lo, hi, sp[..., :ne], sp[..., ne_p:ne_p + nm])
+        flat = sp.view(L, F, ne_p + nm_p)
+        csd = K.csd_msc(flat[:, :, :ne], flat[:, :, ne_p:ne_p + nm])
         if mode == "phase":
             exceed, max_stat = K.surrogate_null(csd, K.SURR_PHASE, 0, n_surrogates, seed=seed + u)
         else:

@@ -69,6 +69,35 @@ def fft_segments(x: torch.Tensor, seg_starts: torch.Tensor, windows: torch.Tenso
     return out
 
 
+def fft_segments_pair(x1: torch.Tensor, x2: torch.Tensor, seg_starts: torch.Tensor, windows: torch.Tensor,
+                      detrend: int, bin_lo: int, bin_hi: int, out1: torch.Tensor, out2: torch.Tensor) -> None:
+    """Spectra of two recordings of equal length (EEG, EMG) in one K1 launch: ``out1`` / ``out2`` are complex64
+    (n_seg, K, F, C_i) tensors or channel-range views of one (n_seg, K, F, C_total) array (same row pitch)."""
+    for t, name in ((x1, "x1"), (x2, "x2")):
+        _need_cuda(t, name, torch.float32)
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError(f"{name} must be (n_samples, n_ch) with contiguous channels")
+    if x1.shape[0] != x2.shape[0]:
+        raise ValueError("both recordings must have the same number of samples")
+    _need_cuda(seg_starts, "seg_starts", torch.int64)
+    _need_cuda(windows, "windows", torch.float32)
+    windows, seg_starts = windows.contiguous(), seg_starts.contiguous()
+    K, N = windows.shape
+    n_seg, F = seg_starts.numel(), bin_hi - bin_lo + 1
+    for o, x, name in ((out1, x1, "out1"), (out2, x2, "out2")):
+        _need_cuda(o, name, torch.complex64)
+        if o.shape != (n_seg, K, F, x.shape[1]) or o.stride(3) != 1 or o.stride(1) != F * o.stride(2) or \
+                o.stride(0) != K * F * o.stride(2):
+            raise ValueError(f"{name} must be (n_seg, K, F, n_ch) with unit channel stride and dense leading axes")
+    if out1.stride(2) != out2.stride(2):
+        raise ValueError("out1 and out2 must share the row pitch")
+    rc = _lib.load().cmc_fft_segments_pair(x1.data_ptr(), x1.shape[1], x1.stride(0), out1.data_ptr(),
+                                           x2.data_ptr(), x2.shape[1], x2.stride(0), out2.data_ptr(),
+                                           x1.shape[0], seg_starts.data_ptr(), n_seg, windows.data_ptr(), K, N, detrend,
+                                           bin_lo, bin_hi, out1.stride(2), _lib.current_stream())
+    _lib.check(rc, "cmc_fft_segments_pair")
+
+
 def psd_from_spectra(spec: torch.Tensor, base_scale: float, one_sided: bool, bin_lo: int, N: int,
                      log_scale: bool) -> torch.Tensor:
     """(W, K, F, C) complex64 spectra -> (W, F, C) float32 power spectra (mean over axis 1)."""
@@ -169,6 +198,9 @@ class PooledCsd:
         self.coh, self.sxx, self.syy, self.sxy, self.ws, self.dims = coh, sxx, syy, sxy, ws, dims
         # (X, Y, ldx, ldy) while the operand planes of ws are not filled yet
         self._pending = pending
+        # ((seed, s_begin, s_end, f_begin, f_end), workspace) of the last phase null whose generated operands (phase
+        # panel + cross-product rows) were kept for the histogram passes
+        self.phase_ops = None
 
     def ensure_operands(self) -> None:
         """Fill the TF32 operand planes the surrogate kernels read (no-op when already present)."""
@@ -213,7 +245,7 @@ def csd_msc(X: torch.Tensor, Y: torch.Tensor, want_sxy: bool = False, keep_opera
 
 def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: torch.Tensor | None = None,
                    group: int = 1, seed: int = 0, exceed: torch.Tensor | None = None,
-                   f_range: tuple[int, int] | None = None):
+                   f_range: tuple[int, int] | None = None, keep_phase_operands: bool = False):
     """Surrogates [s_begin, s_end) against csd.coh: returns (exceed uint32 (F,Ne,Nm) accumulated,
     max_stat float32 (s_end - s_begin,)).  ``f_range = (f_begin, f_end)`` restricts the null to those
     frequency bins: exceed is only updated there and max_stat is the maximum over the range."""
@@ -238,12 +270,15 @@ def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: 
                                       s_end, f_begin, f_end, csd.coh.data_ptr(), exceed.data_ptr(),
                                       max_stat.data_ptr(), ws2.data_ptr(), ws2_bytes, _lib.current_stream())
     _lib.check(rc, "cmc_surrogate_null_range")
+    if mode == SURR_PHASE:
+        csd.phase_ops = ((int(seed), int(s_begin), int(s_end), f_begin, f_end), ws2) if keep_phase_operands else None
     return exceed, max_stat
 
 
 def surrogate_null_hist(csd: PooledCsd, s_begin: int, s_end: int, seed: int = 0, n_bins: int = 128,
                         bin_lo: torch.Tensor | None = None, bin_scale: torch.Tensor | None = None,
-                        hist: torch.Tensor | None = None, f_range: tuple[int, int] | None = None) -> torch.Tensor:
+                        hist: torch.Tensor | None = None, f_range: tuple[int, int] | None = None,
+                        keep_operands: bool = False) -> torch.Tensor:
     """Per-pair histograms of the phase surrogates [s_begin, s_end): int32 (F, Ne, Nm, n_bins), accumulated into
     ``hist`` when given.  Bin = floor((sqrt(C_s) - bin_lo) * bin_scale) with per-pair float32 (F, Ne, Nm) arrays
     (defaults 0 and n_bins: uniform bins on the |coherency| axis); values outside [0, n_bins) are not counted."""
@@ -263,12 +298,17 @@ def surrogate_null_hist(csd: PooledCsd, s_begin: int, s_end: int, seed: int = 0,
     ws2_bytes = int(lib.cmc_surrogate_workspace_bytes(L, F, Ne, Nm, SURR_PHASE, s_end - s_begin))
     if ws2_bytes < 0:
         _lib.check(ws2_bytes, "cmc_surrogate_workspace_bytes")
-    ws2 = torch.empty(max(ws2_bytes, 16), dtype=torch.uint8, device=dev)
     f_begin, f_end = (0, F) if f_range is None else (int(f_range[0]), int(f_range[1]))
+    # the phase panel and the cross-product rows of an earlier pass over the same surrogates are reused (and kept
+    # for the next zoom pass): they depend on (seed, surrogate range, frequency range) only
+    key = (int(seed), int(s_begin), int(s_end), f_begin, f_end)
+    reuse = csd.phase_ops is not None and csd.phase_ops[0] == key and csd.phase_ops[1].numel() >= ws2_bytes
+    ws2 = csd.phase_ops[1] if reuse else torch.empty(max(ws2_bytes, 16), dtype=torch.uint8, device=dev)
     rc = lib.cmc_surrogate_null_hist(csd.ws.data_ptr(), L, F, Ne, Nm, SURR_PHASE, seed, s_begin, s_end, f_begin, f_end,
                                      n_bins, _lib.ptr(bin_lo), _lib.ptr(bin_scale), hist.data_ptr(), ws2.data_ptr(),
-                                     ws2_bytes, _lib.current_stream())
+                                     ws2.numel(), int(reuse), _lib.current_stream())
     _lib.check(rc, "cmc_surrogate_null_hist")
+    csd.phase_ops = (key, ws2) if keep_operands else None
     return hist
 
 

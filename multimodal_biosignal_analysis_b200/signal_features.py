@@ -668,15 +668,15 @@ def pooled_coherence(eeg_array, emg_array, sampling_freq: float, segment_starts,
     starts_d = torch.as_tensor(np.asarray(segment_starts, dtype=np.int64)).to(dev)
     wd = torch.from_numpy(windows).to(dev)
     # K2 contracts the spectra as K1 writes them (no pack pass); its TMA needs an even channel pitch, so odd
-    # channel counts get one padding column.  The operand planes of the surrogate nulls are built on demand.
-    def spectra(sig):
-        n_ch = sig.shape[1]
-        out = torch.empty((len(segment_starts), n_win, hi - lo + 1, n_ch + (n_ch & 1)), dtype=torch.complex64,
-                          device=dev)
-        K.fft_segments(sig, starts_d, wd, detrend, lo, hi, out=out, ch_offset=0)
-        return out.view(-1, out.shape[2], out.shape[3])[:, :, :n_ch]
-
-    csd = K.csd_msc(spectra(_to_device_f32(eeg_array)), spectra(_to_device_f32(emg_array)))
+    # channel counts get one padding column.  Both modalities land in ONE array (EEG columns, then EMG columns) so
+    # that one K1 launch transforms them together.  The operand planes of the surrogate nulls are built on demand.
+    eeg_d, emg_d = _to_device_f32(eeg_array), _to_device_f32(emg_array)
+    ne, nm = eeg_d.shape[1], emg_d.shape[1]
+    ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)
+    spec = torch.empty((len(segment_starts), n_win, hi - lo + 1, ne_p + nm_p), dtype=torch.complex64, device=dev)
+    K.fft_segments_pair(eeg_d, emg_d, starts_d, wd, detrend, lo, hi, spec[..., :ne], spec[..., ne_p:ne_p + nm])
+    flat = spec.view(-1, spec.shape[2], spec.shape[3])
+    csd = K.csd_msc(flat[:, :, :ne], flat[:, :, ne_p:ne_p + nm])
     return PooledCoherence(csd, freqs[lo:hi + 1], n_win, host)
 
 
@@ -891,12 +891,12 @@ def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, 
     ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)                    # even channel pitch for K2's TMA
 
     def compute(slot, i):
-        if "X" not in slot:
-            slot["X"] = torch.empty((L, 1, F, ne_p), dtype=torch.complex64, device=dev)
-            slot["Y"] = torch.empty((L, 1, F, nm_p), dtype=torch.complex64, device=dev)
-        K.fft_segments(slot["eeg"], starts_d, wd, dmode, lo, hi, out=slot["X"], ch_offset=0)
-        K.fft_segments(slot["emg"], starts_d, wd, dmode, lo, hi, out=slot["Y"], ch_offset=0)
-        res = K.csd_msc(slot["X"].view(L, F, ne_p)[:, :, :ne], slot["Y"].view(L, F, nm_p)[:, :, :nm])
+        if "S" not in slot:
+            slot["S"] = torch.empty((L, 1, F, ne_p + nm_p), dtype=torch.complex64, device=dev)
+        sp = slot["S"]
+        K.fft_segments_pair(slot["eeg"], slot["emg"], starts_d, wd, dmode, lo, hi, sp[..., :ne], sp[..., ne_p:ne_p + nm])
+        flat = sp.view(L, F, ne_p + nm_p)
+        res = K.csd_msc(flat[:, :, :ne], flat[:, :, ne_p:ne_p + nm])
         return {"coherence": res.coh}
 
     pipe = _RecordingPipeline(n, ne, nm, {"coherence": ((F, ne, nm), torch.float32)}, compute)

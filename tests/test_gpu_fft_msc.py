@@ -240,3 +240,29 @@ def test_fft_segments_pipelined_kernel_many_tiles(cuda_device, N):
     a = K.fft_segments(_dev(x), _dev(starts), _dev(wins[:1]), 1, 2, 90)
     b = K.fft_segments(_dev(x), _dev(starts), _dev(wins[:1]), 1, 2, 90)
     assert torch.equal(torch.view_as_real(a), torch.view_as_real(b))
+
+
+@pytest.mark.parametrize("N,ne,nm,n_seg,n_win", [(2048, 64, 64, 12, 1), (512, 11, 70, 9, 1), (1024, 8, 5, 7, 3),
+                                                   (512, 3, 3, 2, 1), (4096, 8, 8, 3, 1), (256, 6, 9, 4, 1)])
+def test_fft_segments_pair_is_bit_identical_to_two_launches(cuda_device, N, ne, nm, n_seg, n_win):
+    """cmc_fft_segments_pair: EEG and EMG in ONE launch of the pipelined K1 kernel (tiles of both recordings share
+    the persistent CTAs) - and its fall-back to two launches for sizes / layouts outside that kernel - give exactly
+    the spectra of two cmc_fft_segments calls, written into channel ranges of one array."""
+    import torch
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(N + ne)
+    n = N * (n_seg + 1) // 2 + N
+    x1 = torch.as_tensor(rng.standard_normal((n, ne)).astype(np.float32) + 3.0).cuda()
+    x2 = torch.as_tensor(rng.standard_normal((n, nm)).astype(np.float32) - 1.0).cuda()
+    starts = torch.as_tensor((np.arange(n_seg) * (N // 2)).astype(np.int64)).cuda()
+    win = torch.as_tensor(rng.random((n_win, N)).astype(np.float32)).cuda()
+    for lo, hi in ((1, min(100, N // 2)), (0, N // 2)):
+        F = hi - lo + 1
+        ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)
+        joint = torch.zeros((n_seg, n_win, F, ne_p + nm_p), dtype=torch.complex64, device="cuda")
+        K.fft_segments_pair(x1, x2, starts, win, 1, lo, hi, joint[..., :ne], joint[..., ne_p:ne_p + nm])
+        a = K.fft_segments(x1, starts, win, 1, lo, hi)
+        b = K.fft_segments(x2, starts, win, 1, lo, hi)
+        assert torch.equal(joint[..., :ne], a) and torch.equal(joint[..., ne_p:ne_p + nm], b)
+        if ne & 1:
+            assert torch.all(joint[..., ne] == 0)                  # padding columns are never written
