@@ -602,9 +602,9 @@ def main_gpu(args):
         eeg_d, emg_d = dev_sets[0]
 
         def mt_step():
-            Xw = K.fft_segments(eeg_d, starts, tapers, K.DETREND_NONE, lo, hi)
-            Yw = K.fft_segments(emg_d, starts, tapers, K.DETREND_NONE, lo, hi)
-            return K.msc_windows(Xw, Yw, None, True, t_crit, 0.81)
+            S = torch.empty((L, Kt, F, NE + NM), dtype=torch.complex64, device=dev)
+            K.fft_segments_pair(eeg_d, emg_d, starts, tapers, K.DETREND_NONE, lo, hi, S[..., :NE], S[..., NE:])
+            return K.msc_windows(S[..., :NE], S[..., NE:], None, True, t_crit, 0.81)
 
         for _ in range(3):
             mt_step()                                     # warm the allocator: 1.1 GB of outputs per call

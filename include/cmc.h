@@ -206,19 +206,29 @@ CMC_API int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, int
 /* Per-pair null histograms of the phase surrogates [s_begin, s_end) (north star: "null histograms"; they give the
  * per-pair significance thresholds of BASELINE config 3 - the reference's stand-in is apply_threshold_filtering,
  * signal_features.py:581-604).  A surrogate coherence C of pair (i, j) at frequency f lands in bin
- *     floor((sqrt(C) - bin_lo[f][i][j]) * bin_scale[f][i][j])           (not counted outside [0, n_bins))
- * with bin_lo = NULL read as 0 and bin_scale = NULL as n_bins, i.e. n_bins uniform bins on the |coherency| axis;
- * per-pair (lo, scale) arrays zoom into a sub-range in a second pass.  Same surrogates as cmc_surrogate_null for
- * the same (seed, s, l, f); counts are ADDED to hist, so chunks of the surrogate range accumulate.
- *   hist [F][Ne][Nm][n_bins] uint32 (caller zero-initialises), 2 <= n_bins <= 128; ws / ws2 as for
- *   cmc_surrogate_null (mode CMC_SURR_PHASE only; CMC_SURR_SHIFT returns CMC_EUNSUPPORTED).
+ *     floor((C - bin_lo[f][i][j]) * bin_scale[f][i][j])
+ * of the pair's histogram; values under the window (negative bin) only raise below[f][i][j], values over it are
+ * dropped.  bin_lo = NULL reads as 0 and bin_scale = NULL as n_bins, i.e. n_bins uniform bins over [0, 1]; per-pair
+ * (lo, scale) arrays place / zoom the window (a quantile search resolves the upper tail only, which keeps most
+ * surrogates out of the histogram - and out of the shared-memory atomics).  Same surrogates as cmc_surrogate_null
+ * for the same (seed, s, l, f); counts are ADDED to hist / below, so chunks of the surrogate range accumulate.
+ *   hist  [F][Ne][Nm][n_bins] uint32 (caller zero-initialises), 2 <= n_bins <= 128
+ *   below [F][Ne][Nm] uint32 or NULL (caller zero-initialises)
+ *   ws / ws2 as for cmc_surrogate_null (mode CMC_SURR_PHASE only; CMC_SURR_SHIFT returns CMC_EUNSUPPORTED).
  *   reuse_operands != 0: ws2 still holds the phase panel and cross-product rows that an earlier
  *   cmc_surrogate_null[_range / _hist] call generated for the SAME ws, seed, surrogate range and frequency range
  *   (e.g. the exceedance pass, or the previous zoom pass): their generation is skipped. */
 CMC_API int cmc_surrogate_null_hist(void* ws, int L, int F, int Ne, int Nm, int mode, uint64_t seed,
                             int64_t s_begin, int64_t s_end, int f_begin, int f_end, int n_bins,
-                            const float* bin_lo, const float* bin_scale, uint32_t* hist,
+                            const float* bin_lo, const float* bin_scale, uint32_t* hist, uint32_t* below,
                             void* ws2, int64_t ws2_bytes, int reuse_operands, void* stream);
+
+/* Rank selection in the histograms above: for every row of hist [n_rows][n_bins] the first bin whose running count,
+ * started at below[row], exceeds k (the bin of the value of 0-based rank k among the counted and the `below` values);
+ * below[row] is replaced by the count below that bin.  bin_out = -1: the rank lies under the window (below > k),
+ * bin_out = n_bins: over it (the counts never reach k).  Drives the zoom passes of the per-pair quantiles. */
+CMC_API int cmc_hist_select(const uint32_t* hist, int64_t n_rows, int n_bins, int k, int32_t* below, int32_t* bin_out,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K4  cluster-based permutation test: sign-flip t-map -> threshold -> connected-component

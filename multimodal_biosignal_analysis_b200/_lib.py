@@ -42,7 +42,8 @@ _SIGNATURES = {
     "cmc_surrogate_null_range": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _u64, _i64, _i64, _i32, _i32,
                                            _vp, _vp, _vp, _vp, _i64, _vp]),
     "cmc_surrogate_null_hist": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _u64, _i64, _i64, _i32, _i32, _i32,
-                                          _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+                                          _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "cmc_hist_select": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "cmc_cbpa_workspace_bytes": (_i64, [_i32, _i32]),
     "cmc_cbpa_permute": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _i64, _f64, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cmc_cbpa_observed": (C.c_int, [_vp, _i32, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,

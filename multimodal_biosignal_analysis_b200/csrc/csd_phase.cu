@@ -369,21 +369,26 @@ phase_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
 // panels, so the histograms of the unit's 128 pairs live in shared memory for the whole null and leave the SM once
 // ([128][n_bins] uint32, n_bins <= 128).  The pair tile no longer fits next to the panel, so both operands stream:
 // every ring stage carries the A k-block (16 KB) next to the B k-block (32 KB); B is re-read per panel from L2.
-// Bin of a surrogate coherence C: floor((sqrt(C) - lo[pair]) * scale[pair]); values outside [0, n_bins) are not
-// counted (lo = 0, scale = n_bins: uniform bins on the |coherency| axis; a second pass zooms into the bin pair that
-// brackets a quantile - data_surrogation.py).  One CTA owns a (frequency, pair tile) for the whole launch, so the
-// flush is a plain read-add-write and successive launches (surrogate chunks, zoom passes on a cleared array) add up.
+// Bin of a surrogate coherence C: floor((C - lo[pair]) * scale[pair]); values under the window only raise the pair's
+// `below` counter, values over it are dropped (lo = 0, scale = n_bins: uniform bins over [0, 1]).  Per-pair windows
+// are what makes the pass cheap: a quantile search only has to resolve the upper tail of each pair's null, so the
+// ~80-90 % of the surrogates that fall under the window cost a register increment instead of a shared-memory atomic
+// (measured: the atomics alone were half of a full-range pass).  data_surrogation.py places the first window from
+// the null's analytic mean and zooms with further passes.  One CTA owns a (frequency, pair tile) for the whole
+// launch, so the flush is a plain read-add-write and successive launches (surrogate chunks) add up.
 constexpr int kPhHistStages = 3;
 constexpr int kPhHistMaxBins = 128;
+constexpr int kPhHistThreads = 384;      // TMA / MMA / TMEM-allocator warps + TWO epilogue warpgroups
 
 struct PhaseHistParams {
     int F, MT, NT, KB, n_local, n_pairs, S_pad, R_pad, n_bins;
     const float* bin_lo;       // [F][n_pairs] or null (0)
     const float* bin_scale;    // [F][n_pairs] or null (n_bins)
     uint32_t* hist;            // [F][n_pairs][n_bins]
+    uint32_t* below;           // [F][n_pairs] surrogates under the window, or null
 };
 
-__global__ void __launch_bounds__(kPhThreads, 1)
+__global__ void __launch_bounds__(kPhHistThreads, 1)
 phase_hist_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
                   const PhaseHistParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -393,8 +398,9 @@ phase_hist_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     uint32_t* hist_s = reinterpret_cast<uint32_t*>(sB + kPhHistStages * kStageBytes);   // [128][n_bins + 1]
     const int hp = p.n_bins + 1;                  // padded histogram row: lanes that hit the same bin of 32 different
                                                   // pairs fall into 32 different banks
-    float* stage_s = reinterpret_cast<float*>(hist_s + kPhPairs * hp);            // [128][33] transposition tile
-    PhaseBarriers* bars = reinterpret_cast<PhaseBarriers*>(stage_s + kPhM * 33);
+    float* lo_s = reinterpret_cast<float*>(hist_s + kPhPairs * hp);               // [128] window origin per pair
+    float* sc_s = lo_s + kPhPairs;                                                 // [128] bins per unit of coherence
+    PhaseBarriers* bars = reinterpret_cast<PhaseBarriers*>(sc_s + kPhPairs);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = p.F * p.NT;
@@ -467,32 +473,37 @@ phase_hist_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM lane = surrogate row of the panel, columns = the unit's 128 pairs =====
-        // All 32 lanes of a warp hold the SAME pair in a given column, and under the null their values crowd into a
-        // few bins: binning straight from the accumulator layout serialises on same-address shared-memory atomics
-        // (3.5 ms per 1,024 surrogates, tensor pipe 10 % busy).  So every 32-column chunk is transposed through a
-        // padded shared tile first: thread (column c = te % 32, row block te / 32) then walks 32 surrogates of ONE
-        // pair, the lanes of a warp update 32 different histogram rows, and only the four row blocks of a column
-        // still meet in an atomic.
-        const int q = warp - 4;
-        const int te = threadIdx.x - 128;
+        // All 32 lanes of a warp hold the SAME pair in a given column.  With a window that keeps most of the null
+        // under it, a column costs one ballot for the `below` counter (accumulated by lane c for column c, as in
+        // the exceedance kernel) and a shared-memory atomic only for the few lanes whose value lies inside the window,
+        // so the same-address serialisation that made full-range binning slow (half of the pass) hardly occurs.
+        // The ~16 instructions per column run with one warp per scheduler, i.e. latency bound: TWO epilogue
+        // warpgroups take the two TMEM accumulators in turn (warps 4-7: even tile-panels, warps 8-11: odd ones), each
+        // with two MMA periods per panel; both add into the same shared histograms.
+        // Measured per 1,000 surrogates of config 3 (one pass, operands reused): full-range binning from this layout
+        // 4.4 ms; every 32-column chunk transposed through shared memory so that a thread walks 32 surrogates of one
+        // pair 2.9 ms; windows + ballot counters 2.5 ms; + the second warpgroup 1.7 ms (GEMM floor of this loop
+        // order, both operands streamed from L2: 0.6 ms).
+        const int wg = (warp - 4) >> 2;                         // epilogue warpgroup 0 / 1
+        const int q = warp & 3;                                 // TMEM lane quadrant this warp may read
+        const int te = q * 32 + lane;                           // accumulator lane = surrogate row of the panel
+        const int t256 = threadIdx.x - 128;                     // 0..255 over both warpgroups
         const float nb = (float)p.n_bins;
-        const int tc_col = te & 31, tc_rb = te >> 5;            // transposed role: column of the chunk, row block
         uint32_t it = 0;
         for (int un = blockIdx.x; un < n_units; un += gridDim.x) {
             const int f = un / p.NT, nt = un - f * p.NT;
-            // bin origin / scale of the four pairs this thread bins (column tc_col of every 32-column chunk)
-            float lo_r[4], sc_r[4];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const int pair_t = nt * kPhPairs + ch * 32 + tc_col;
+            if (t256 < kPhPairs) {
+                const int pair_t = nt * kPhPairs + t256;
                 const bool pair_ok = pair_t < p.n_pairs;
-                lo_r[ch] = (pair_ok && p.bin_lo) ? __ldg(p.bin_lo + (int64_t)f * p.n_pairs + pair_t) : 0.f;
-                sc_r[ch] = (pair_ok && p.bin_scale) ? __ldg(p.bin_scale + (int64_t)f * p.n_pairs + pair_t) : nb;
+                lo_s[t256] = (pair_ok && p.bin_lo) ? __ldg(p.bin_lo + (int64_t)f * p.n_pairs + pair_t) : 0.f;
+                sc_s[t256] = (pair_ok && p.bin_scale) ? __ldg(p.bin_scale + (int64_t)f * p.n_pairs + pair_t) : nb;
             }
-            for (int i = te; i < kPhPairs * hp; i += 128) hist_s[i] = 0u;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int mt = 0; mt < p.MT; ++mt) {
-                const int n_rows = min(kPhM, p.n_local - mt * kPhM);      // valid surrogate rows of this panel
+            for (int i = t256; i < kPhPairs * hp; i += 256) hist_s[i] = 0u;
+            uint32_t below_r[4] = {0u, 0u, 0u, 0u};              // lane c: surrogates of this warp under the window
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // of column ch * 32 + c
+            for (int mt = 0; mt < p.MT; ++mt, ++it) {
+                if ((int)(it & 1) != wg) continue;
+                const bool s_ok = mt * kPhM + te < p.n_local;
                 const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
                 mbar_wait(&bars->tmem_full[acc], accphase);
                 tc_fence_after();
@@ -503,43 +514,87 @@ phase_hist_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                     tmem_ld_32x32(taddr + ch * 32, re);
                     tmem_ld_32x32(taddr + kPhPairs + ch * 32, im);
                     tmem_ld_wait();
-                    float* row = stage_s + te * 33;
+                    uint32_t mine = 0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const float a = __uint_as_float(re[c]), b = __uint_as_float(im[c]);
-                        // |coherency| in [0, 1): C = 1 is binned with the largest float below 1
-                        row[c] = fminf(sqrtf((a * a + b * b) * kZUnscaleSq), 0.99999994f);
+                        const float cv = fminf((a * a + b * b) * kZUnscaleSq, 1.0f);
+                        const float x = (cv - lo_s[ch * 32 + c]) * sc_s[ch * 32 + c];
+                        const uint32_t bal = __ballot_sync(0xffffffffu, s_ok && x < 0.f);
+                        mine = (lane == c) ? __popc(bal) : mine;
+                        if (s_ok && x >= 0.f && x < nb) atomicAdd(hist_s + (ch * 32 + c) * hp + (int)x, 1u);
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const float lo = lo_r[ch], sc = sc_r[ch];
-                    uint32_t* hrow = hist_s + (ch * 32 + tc_col) * hp;
-                    const int r_end = min(32, n_rows - tc_rb * 32);
-#pragma unroll 4
-                    for (int r = 0; r < r_end; ++r) {
-                        const float x = (stage_s[(tc_rb * 32 + r) * 33 + tc_col] - lo) * sc;
-                        // x >= 0 first: the float -> int conversion of a negative value must not wrap into range
-                        if (x >= 0.f && x < nb) atomicAdd(hrow + (int)x, 1u);
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");         // the tile is rewritten by the next chunk
+                    below_r[ch] += mine;
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
-                ++it;
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             // flush: rows of padding pairs (beyond n_pairs) hold counts of the zero rows of Z and are dropped
+            // (reductions without a return value: no dependent global load per entry; only this CTA touches the
+            // unit's rows during the launch, other launches are stream-ordered)
             const int rows = min(kPhPairs, p.n_pairs - nt * kPhPairs);
             uint32_t* g = p.hist + ((int64_t)f * p.n_pairs + (int64_t)nt * kPhPairs) * p.n_bins;
-            for (int i = te; i < rows * p.n_bins; i += 128) {
-                const uint32_t v = hist_s[(i / p.n_bins) * hp + (i % p.n_bins)];
-                if (v) g[i] += v;
+            for (int r = t256 >> 7; r < rows; r += 2)
+                for (int b = t256 & 127; b < p.n_bins; b += 128) {
+                    const uint32_t v = hist_s[r * hp + b];
+                    if (v) atomicAdd(g + r * p.n_bins + b, v);
+                }
+            if (p.below) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int pc = nt * kPhPairs + ch * 32 + lane;
+                    if (pc < p.n_pairs && below_r[ch]) atomicAdd(p.below + (int64_t)f * p.n_pairs + pc, below_r[ch]);
+                }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Rank selection in per-row histograms: for every row (= one (f, i, j) pair) the bin that holds the value of 0-based
+// rank k - the first bin whose running count, started at below[row], exceeds k - and the count below that bin.
+// bin -1: the rank lies under the window (below > k); bin n_bins: over it (the counts never reach k; below is then
+// the total).  One warp per row, coalesced reads, shuffle scan.
+__global__ void __launch_bounds__(256)
+hist_select_kernel(const uint32_t* __restrict__ hist, int64_t n_rows, int n_bins, int k, int32_t* __restrict__ below,
+                   int32_t* __restrict__ bin_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const uint32_t* h = hist + row * n_bins;
+    int run = below[row];
+    if (run > k) {
+        if (lane == 0) bin_out[row] = -1;
+        return;
+    }
+    int found_bin = n_bins, found_below = -1;
+    for (int b0 = 0; b0 < n_bins && found_below < 0; b0 += 32) {
+        const int b = b0 + lane;
+        const int v = b < n_bins ? (int)h[b] : 0;
+        int inc = v;                                           // inclusive scan over the 32 bins of this step
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, b < n_bins && run + inc > k);
+        if (hit) {
+            const int l = __ffs(hit) - 1;
+            found_bin = b0 + l;
+            found_below = run + __shfl_sync(0xffffffffu, inc - v, l);
+        } else {
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    if (lane == 0) {
+        bin_out[row] = found_bin;
+        below[row] = found_below >= 0 ? found_below : run;
+    }
 }
 
 __global__ void phase_gather_kernel(const uint32_t* __restrict__ max_u, int64_t n, float* __restrict__ max_stat) {
@@ -680,13 +735,13 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
 
 int phase_surrogate_hist(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
                          int f_begin, int f_end, int n_bins, const float* bin_lo, const float* bin_scale,
-                         uint32_t* hist, void* ws2, int64_t ws2_bytes, bool reuse, cudaStream_t st) {
+                         uint32_t* hist, uint32_t* below, void* ws2, int64_t ws2_bytes, bool reuse, cudaStream_t st) {
     const int64_t n = s_end - s_begin;
     CMC_REQUIRE(n_bins >= 2 && n_bins <= kPhHistMaxBins, "cmc_surrogate_null_hist: n_bins must be in [2, %d]",
                 kPhHistMaxBins);
     const PhaseLayout y = phase_layout(L, F, Ne, Nm, n);
     const size_t smem = 1024 + (size_t)kPhHistStages * (kPhABytes + kPhBBytes) + (size_t)kPhPairs * (n_bins + 1) * 4 +
-                        (size_t)kPhM * 33 * 4 + sizeof(PhaseBarriers) + 16;
+                        kPhPairs * 8 + sizeof(PhaseBarriers) + 16;
     int rc = ensure_smem_attr(reinterpret_cast<const void*>(phase_hist_kernel), smem);
     if (rc) return rc;
     const int sms = sm_count();
@@ -695,17 +750,30 @@ int phase_surrogate_hist(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
                          PhaseHistParams p{};
                          p.F = fc; p.MT = y.MT; p.NT = y.NT; p.KB = y.KB; p.n_local = (int)n; p.n_pairs = y.n_pairs;
                          p.S_pad = y.S_pad; p.R_pad = y.R_pad; p.n_bins = n_bins;
+                         p.below = below ? below + (int64_t)f0 * y.n_pairs : nullptr;
                          p.bin_lo = bin_lo ? bin_lo + (int64_t)f0 * y.n_pairs : nullptr;
                          p.bin_scale = bin_scale ? bin_scale + (int64_t)f0 * y.n_pairs : nullptr;
                          p.hist = hist + (int64_t)f0 * y.n_pairs * n_bins;
                          const int n_units = fc * y.NT;
-                         phase_hist_kernel<<<n_units < sms ? n_units : sms, kPhThreads, smem, st>>>(mA, mB, p);
+                         phase_hist_kernel<<<n_units < sms ? n_units : sms, kPhHistThreads, smem, st>>>(mA, mB, p);
                          CMC_CHECK_LAUNCH("phase_hist_kernel");
                          return CMC_OK;
                      });
 }
 
 }  // namespace cmc
+
+extern "C" CMC_API int cmc_hist_select(const uint32_t* hist, int64_t n_rows, int n_bins, int k, int32_t* below,
+                                       int32_t* bin_out, void* stream) {
+    using namespace cmc;
+    CMC_REQUIRE(hist && below && bin_out, "cmc_hist_select: null pointer");
+    CMC_REQUIRE(n_rows >= 0 && n_bins >= 1 && k >= 0, "cmc_hist_select: bad shape");
+    if (n_rows == 0) return CMC_OK;
+    hist_select_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, n_rows, n_bins, k,
+                                                                                                  below, bin_out);
+    CMC_CHECK_LAUNCH("hist_select_kernel");
+    return CMC_OK;
+}
 
 // host copy of the kernel's FP16 phase table as float pairs (cos, sin): diagnostics of the operand rounding
 extern "C" CMC_API int cmc_phase_table(float* out_host /* [4096][2] */) {

@@ -383,7 +383,7 @@ int phase_surrogate_null(const void* ws, int L, int F, int Ne, int Nm, uint64_t 
 
 int phase_surrogate_hist(const void* ws, int L, int F, int Ne, int Nm, uint64_t seed, int64_t s_begin, int64_t s_end,
                          int f_begin, int f_end, int n_bins, const float* bin_lo, const float* bin_scale,
-                         uint32_t* hist, void* ws2, int64_t ws2_bytes, bool reuse, cudaStream_t st);
+                         uint32_t* hist, uint32_t* below, void* ws2, int64_t ws2_bytes, bool reuse, cudaStream_t st);
 
 }  // namespace cmc
 
@@ -528,8 +528,8 @@ extern "C" int cmc_surrogate_null_range(void* ws, int L, int F, int Ne, int Nm, 
 
 extern "C" int cmc_surrogate_null_hist(void* ws, int L, int F, int Ne, int Nm, int mode, uint64_t seed,
                                        int64_t s_begin, int64_t s_end, int f_begin, int f_end, int n_bins,
-                                       const float* bin_lo, const float* bin_scale, uint32_t* hist, void* ws2,
-                                       int64_t ws2_bytes, int reuse_operands, void* stream) {
+                                       const float* bin_lo, const float* bin_scale, uint32_t* hist, uint32_t* below,
+                                       void* ws2, int64_t ws2_bytes, int reuse_operands, void* stream) {
     using namespace cmc;
     CMC_REQUIRE(ws && hist && ws2, "cmc_surrogate_null_hist: null pointer");
     CMC_REQUIRE(s_end >= s_begin, "cmc_surrogate_null_hist: bad surrogate range");
@@ -542,5 +542,5 @@ extern "C" int cmc_surrogate_null_hist(void* ws, int L, int F, int Ne, int Nm, i
     }
     if (s_end == s_begin || f_begin == f_end) return CMC_OK;
     return phase_surrogate_hist(ws, L, F, Ne, Nm, seed, s_begin, s_end, f_begin, f_end, n_bins, bin_lo, bin_scale, hist,
-                                ws2, ws2_bytes, reuse_operands != 0, static_cast<cudaStream_t>(stream));
+                                below, ws2, ws2_bytes, reuse_operands != 0, static_cast<cudaStream_t>(stream));
 }

@@ -157,8 +157,9 @@ def circular_shift_surrogate_null(pooled, n_surrogates: int = 1000, seed: int | 
 
 
 def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int = 0, alpha: float = 0.05,
-                                    shard: str = "auto", thresholds: bool = False, threshold_passes: int = 2,
-                                    hist_bins: int = 128, return_hist: bool = False) -> dict:
+                                    shard: str = "auto", thresholds: bool = False, threshold_passes: int = 3,
+                                    hist_bins: int = 128, return_hist: bool = False,
+                                    hist_range: tuple[float, float] = (0.0, 1.0)) -> dict:
     """Phase-randomised surrogates: every EMG spectrum is rotated by one random phase per
     (surrogate, segment, frequency), shared by all EMG channels; phases come from
     Philox4x32-10(seed; s, l, f) so any sharding of the surrogate index gives the same null.
@@ -167,38 +168,54 @@ def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int 
     the (1 - alpha) quantile (order statistic, numpy ``method="higher"``) of the pair's own null coherences, from
     per-pair null histograms accumulated on the device (:func:`null_quantile_thresholds`), and ``significant = coherence >
     threshold`` - the surrogate counterpart of the reference's analytic ``apply_threshold_filtering``
-    (signal_features.py:581-604).  ``return_hist=True`` also returns the first-pass histograms
-    (``null_hist`` (F, Ne, Nm, hist_bins) over uniform |coherency| bins, ``null_hist_edges``)."""
+    (signal_features.py:581-604).  ``return_hist=True`` also returns every pair's null histogram over ``hist_range``
+    (``null_hist`` (F, Ne, Nm, hist_bins) uniform coherence bins, ``null_hist_edges``, ``null_hist_below`` = the
+    surrogates under the range; those over it are not counted)."""
     csd = pooled.device_result
     begin, end, f_range, by_freq = _plan(n_surrogates, csd.dims[1], shard)
     exceed, max_local = K.surrogate_null(csd, K.SURR_PHASE, begin, end, seed=seed, f_range=f_range,
                                          keep_phase_operands=(thresholds or return_hist) and (begin, end) == (0, n_surrogates))
     out = _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq, f_range)
-    if thresholds or return_hist:
-        thr, hist = null_quantile_thresholds(csd, n_surrogates, seed, 1.0 - alpha, passes=threshold_passes,
-                                             n_bins=hist_bins, shard=shard)
+    if thresholds:
+        thr, _ = null_quantile_thresholds(csd, n_surrogates, seed, 1.0 - alpha, passes=threshold_passes, shard=shard)
         thr_h = thr.cpu().numpy().astype(np.float64)
         out["threshold"] = thr_h
         coh = pooled.coherence
         out["significant"] = (coh.cpu().numpy() if isinstance(coh, torch.Tensor) else coh) > thr_h
-        if return_hist:
-            out["null_hist"] = hist.cpu().numpy()
-            out["null_hist_edges"] = np.linspace(0.0, 1.0, hist_bins + 1) ** 2       # in coherence units
+    if return_hist:
+        lo_h, hi_h = float(hist_range[0]), float(hist_range[1])
+        F, Ne, Nm = csd.dims[1:]
+        fb, fe = f_range if by_freq else (0, F)
+        lo_t = torch.full((F, Ne, Nm), lo_h, dtype=torch.float32, device=csd.coh.device)
+        sc_t = torch.full((F, Ne, Nm), hist_bins / (hi_h - lo_h), dtype=torch.float32, device=csd.coh.device)
+        hist, below = K.surrogate_null_hist(csd, 0, n_surrogates, seed=seed, n_bins=hist_bins, bin_lo=lo_t,
+                                            bin_scale=sc_t, f_range=(fb, fe))
+        if by_freq:
+            cdist.all_reduce_sum_(hist)
+            cdist.all_reduce_sum_(below)
+        out["null_hist"] = hist.cpu().numpy()
+        out["null_hist_below"] = below.cpu().numpy()
+        out["null_hist_edges"] = np.linspace(lo_h, hi_h, hist_bins + 1)
     return out
 
 
-def null_quantile_thresholds(csd, n_surrogates: int, seed: int, q: float, passes: int = 2, n_bins: int = 128,
+def null_quantile_thresholds(csd, n_surrogates: int, seed: int, q: float, passes: int = 3, n_bins: int = 128,
                              shard: str = "auto"):
     """Per-pair q-quantile of the phase-surrogate null for every (f, i, j) without ever materialising the
     (n_surrogates, F, Ne, Nm) stack.  The quantile is an ORDER STATISTIC of the pair's surrogate coherences,
     ``np.quantile(C_s[:, f, i, j], q, method="higher")`` = the k-th smallest with k = ceil(q (n - 1)) - the
     conservative choice for a significance threshold (at most (1 - q) n surrogates lie above it) and an actually
-    observed null value.  Pass 1 histograms every pair's |coherency| into ``n_bins`` uniform bins; every further
-    pass re-runs the null with per-pair bins zoomed into the bin that holds the k-th value, so after p passes it is
-    known to +-n_bins^-p / 2 on the |coherency| axis (p = 2, 128 bins: threshold error <= 6.2e-5 sqrt(C); p = 3:
-    5e-7).  Each pass costs one GEMM sweep of the null (``cmc_surrogate_null_hist``).  Multi-rank: ranks split the
-    frequency axis and the threshold slices are summed.  Returns (threshold float32 (F, Ne, Nm) CUDA tensor,
-    first-pass histogram int32 (F, Ne, Nm, n_bins))."""
+    observed null value.
+
+    Every pass re-runs the null GEMM with a per-pair window of ``n_bins`` bins (``cmc_surrogate_null_hist``):
+    surrogates under the window are only counted, those inside are histogrammed, ``cmc_hist_select`` finds the bin
+    of rank k and the next pass zooms into that bin (or into the part of [0, 1] under / over the window when the
+    rank fell outside).  The first window is placed from the analytic mean m of the null, E[C_s] = sum_l |Z_l|^2
+    (an approximately exponential null has its q-quantile at -m ln(1 - q)): [0.5, 0.5 + 16 / -ln(1 - q)] x that
+    value, so that ~80 % of the surrogates stay under it.  After p passes a well-placed pair is resolved to
+    16 m / n_bins^p (3 passes, 128 bins, m = 0.005: 4e-8), a misplaced one to n_bins^-(p - 1).  Multi-rank: ranks
+    split the frequency axis and the threshold slices are summed.  Returns (threshold float32 (F, Ne, Nm) CUDA
+    tensor, dict with the last window: lo, width, hist, below)."""
     if passes < 1:
         raise ValueError("passes must be >= 1")
     L, F, Ne, Nm = csd.dims
@@ -206,38 +223,36 @@ def null_quantile_thresholds(csd, n_surrogates: int, seed: int, q: float, passes
     n = int(n_surrogates)
     if n < 1:
         raise ValueError("n_surrogates must be >= 1")
+    if not 0.0 < q < 1.0:
+        raise ValueError("q must lie in (0, 1)")
     _, _, f_range, by_freq = _plan(n, F, shard if shard != "surrogate" else "frequency")
     fb, fe = f_range if by_freq else (0, F)
     k = min(int(np.ceil(q * (n - 1) - 1e-9)), n - 1)        # 0-based rank of the order statistic
-    lo = torch.zeros((F, Ne, Nm), dtype=torch.float32, device=dev)
-    width = 1.0                                              # window [lo, lo + width) on the |coherency| axis
-    below = torch.zeros((F, Ne, Nm), dtype=torch.int32, device=dev)      # surrogates below the window
-    first = None
+    m = csd.null_mean()
+    qhat = m * float(-np.log1p(-q))
+    lo = (0.5 * qhat).clamp(max=1.0)
+    width = (16.0 * m).clamp(min=1e-12)
+    width = torch.minimum(width, (1.0 - lo).clamp(min=1e-12))
     for p in range(passes):
-        scale = torch.full((F, Ne, Nm), n_bins / width, dtype=torch.float32, device=dev)
-        hist = K.surrogate_null_hist(csd, 0, n, seed=seed, n_bins=n_bins, bin_lo=lo if p else None,
-                                     bin_scale=scale if p else None, f_range=(fb, fe),
-                                     keep_operands=p + 1 < passes)
-        if first is None:
-            first = hist
-        cum = torch.cumsum(hist, dim=-1, dtype=torch.int32) + below[..., None]
-        b = (cum > k).to(torch.uint8).argmax(dim=-1)                         # bin of the k-th smallest value
+        scale = (float(n_bins) / width).contiguous()
+        hist, below = K.surrogate_null_hist(csd, 0, n, seed=seed, n_bins=n_bins, bin_lo=lo.contiguous(),
+                                            bin_scale=scale, f_range=(fb, fe), keep_operands=p + 1 < passes)
+        last = dict(lo=lo, width=width, hist=hist, below=below.clone())
+        b = K.hist_select(hist, k, below)                    # bin of rank k; below <- count under that bin
         bw = width / n_bins
+        under, over = b < 0, b >= n_bins
+        x = torch.where(under, lo, torch.where(over, lo + width, lo + (b.to(torch.float32) + 0.5) * bw))
         if p + 1 < passes:
-            prev = torch.gather(cum, -1, (b - 1).clamp(min=0)[..., None])[..., 0]
-            below = torch.where(b > 0, prev, below)
-            lo = lo + b.to(torch.float32) * bw
-            width = bw
-        del cum
-    x = lo + (b.to(torch.float32) + 0.5) * bw if passes > 1 else (b.to(torch.float32) + 0.5) * bw
-    thr = (x * x).clamp(max=1.0)
+            new_lo = torch.where(under, torch.zeros_like(lo), torch.where(over, lo + width, lo + b.to(torch.float32) * bw))
+            new_w = torch.where(under, lo, torch.where(over, 1.0 - (lo + width), bw))
+            lo, width = new_lo.clamp(0.0, 1.0), new_w.clamp(min=1e-12)
+    thr = x.clamp(0.0, 1.0)
     if by_freq:
         mask = torch.zeros(F, dtype=torch.bool, device=dev)
         mask[fb:fe] = True
         thr = torch.where(mask[:, None, None], thr, torch.zeros_like(thr))
         cdist.all_reduce_sum_(thr)
-        cdist.all_reduce_sum_(first)
-    return thr, first
+    return thr, last
 
 
 def surrogate_null_sweep(recordings, sampling_freq: float, nperseg: int = 256, noverlap: int | None = None,

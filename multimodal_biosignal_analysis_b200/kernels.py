@@ -201,6 +201,19 @@ class PooledCsd:
         # ((seed, s_begin, s_end, f_begin, f_end), workspace) of the last phase null whose generated operands (phase
         # panel + cross-product rows) were kept for the histogram passes
         self.phase_ops = None
+        self._xy = None             # the spectra the coherence was computed from (null_mean)
+
+    def null_mean(self) -> torch.Tensor:
+        """E[C_s] of the phase-randomised null per (f, i, j): sum_l |Xw_l|^2 |Yw_l|^2 for whitened spectra (the
+        cross terms of |sum_l Z_l e^{i phi_l}|^2 vanish in expectation).  float32 (F, Ne, Nm)."""
+        if self._xy is None:
+            raise RuntimeError("the spectra of this result are not available")
+        X, Y = self._xy
+        px = X.real.square() + X.imag.square()
+        py = Y.real.square() + Y.imag.square()
+        wx = torch.where(self.sxx > 0, 1.0 / self.sxx, torch.zeros_like(self.sxx))
+        wy = torch.where(self.syy > 0, 1.0 / self.syy, torch.zeros_like(self.syy))
+        return torch.einsum("lfi,lfj->fij", px * wx[None], py * wy[None]).contiguous()
 
     def ensure_operands(self) -> None:
         """Fill the TF32 operand planes the surrogate kernels read (no-op when already present)."""
@@ -240,7 +253,9 @@ def csd_msc(X: torch.Tensor, Y: torch.Tensor, want_sxy: bool = False, keep_opera
     rc = fn(X.data_ptr(), Y.data_ptr(), L, F, Ne, Nm, ldx, ldy, coh.data_ptr(), sxx.data_ptr(), syy.data_ptr(),
             _lib.ptr(sxy), ws.data_ptr(), ws_bytes, _lib.current_stream())
     _lib.check(rc, "cmc_csd_coherence" if direct else "cmc_csd_msc")
-    return PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm), pending=(X, Y, ldx, ldy) if direct else None)
+    out = PooledCsd(coh, sxx, syy, sxy, ws, (L, F, Ne, Nm), pending=(X, Y, ldx, ldy) if direct else None)
+    out._xy = (X, Y)
+    return out
 
 
 def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: torch.Tensor | None = None,
@@ -278,10 +293,11 @@ def surrogate_null(csd: PooledCsd, mode: int, s_begin: int, s_end: int, shifts: 
 def surrogate_null_hist(csd: PooledCsd, s_begin: int, s_end: int, seed: int = 0, n_bins: int = 128,
                         bin_lo: torch.Tensor | None = None, bin_scale: torch.Tensor | None = None,
                         hist: torch.Tensor | None = None, f_range: tuple[int, int] | None = None,
-                        keep_operands: bool = False) -> torch.Tensor:
-    """Per-pair histograms of the phase surrogates [s_begin, s_end): int32 (F, Ne, Nm, n_bins), accumulated into
-    ``hist`` when given.  Bin = floor((sqrt(C_s) - bin_lo) * bin_scale) with per-pair float32 (F, Ne, Nm) arrays
-    (defaults 0 and n_bins: uniform bins on the |coherency| axis); values outside [0, n_bins) are not counted."""
+                        keep_operands: bool = False, below: torch.Tensor | None = None):
+    """Per-pair histograms of the phase surrogates [s_begin, s_end): returns (hist int32 (F, Ne, Nm, n_bins), below
+    int32 (F, Ne, Nm)), accumulated into ``hist`` / ``below`` when given.  Bin = floor((C_s - bin_lo) * bin_scale)
+    with per-pair float32 (F, Ne, Nm) arrays (defaults 0 and n_bins: uniform bins over [0, 1]); values under the
+    window are counted in ``below``, values over it are dropped."""
     L, F, Ne, Nm = csd.dims
     dev = csd.coh.device
     lib = _lib.load()
@@ -290,6 +306,10 @@ def surrogate_null_hist(csd: PooledCsd, s_begin: int, s_end: int, seed: int = 0,
         hist = torch.zeros((F, Ne, Nm, n_bins), dtype=torch.int32, device=dev)
     elif hist.shape != (F, Ne, Nm, n_bins) or not hist.is_contiguous():
         raise ValueError("hist must be contiguous (F, Ne, Nm, n_bins)")
+    if below is None:
+        below = torch.zeros((F, Ne, Nm), dtype=torch.int32, device=dev)
+    elif below.shape != (F, Ne, Nm) or not below.is_contiguous() or below.dtype != torch.int32:
+        raise ValueError("below must be contiguous int32 (F, Ne, Nm)")
     for t, name in ((bin_lo, "bin_lo"), (bin_scale, "bin_scale")):
         if t is not None:
             _need_cuda(t, name, torch.float32)
@@ -305,11 +325,26 @@ def surrogate_null_hist(csd: PooledCsd, s_begin: int, s_end: int, seed: int = 0,
     reuse = csd.phase_ops is not None and csd.phase_ops[0] == key and csd.phase_ops[1].numel() >= ws2_bytes
     ws2 = csd.phase_ops[1] if reuse else torch.empty(max(ws2_bytes, 16), dtype=torch.uint8, device=dev)
     rc = lib.cmc_surrogate_null_hist(csd.ws.data_ptr(), L, F, Ne, Nm, SURR_PHASE, seed, s_begin, s_end, f_begin, f_end,
-                                     n_bins, _lib.ptr(bin_lo), _lib.ptr(bin_scale), hist.data_ptr(), ws2.data_ptr(),
-                                     ws2.numel(), int(reuse), _lib.current_stream())
+                                     n_bins, _lib.ptr(bin_lo), _lib.ptr(bin_scale), hist.data_ptr(), below.data_ptr(),
+                                     ws2.data_ptr(), ws2.numel(), int(reuse), _lib.current_stream())
     _lib.check(rc, "cmc_surrogate_null_hist")
     csd.phase_ops = (key, ws2) if keep_operands else None
-    return hist
+    return hist, below
+
+
+def hist_select(hist: torch.Tensor, k: int, below: torch.Tensor) -> torch.Tensor:
+    """Bin of the value of 0-based rank ``k`` in every histogram ``hist[..., :]`` whose counts start at ``below``
+    (int32, same leading shape; updated in place to the count below the returned bin).  Returns int32 bins; -1 =
+    the rank lies under the window, n_bins = over it."""
+    _need_cuda(hist, "hist", torch.int32)
+    _need_cuda(below, "below", torch.int32)
+    if not hist.is_contiguous() or not below.is_contiguous() or below.shape != hist.shape[:-1]:
+        raise ValueError("hist must be contiguous (..., n_bins) and below contiguous (...)")
+    out = torch.empty_like(below)
+    rc = _lib.load().cmc_hist_select(hist.data_ptr(), below.numel(), hist.shape[-1], int(k), below.data_ptr(),
+                                     out.data_ptr(), _lib.current_stream())
+    _lib.check(rc, "cmc_hist_select")
+    return out
 
 
 # ----------------------------------------------------------------------------- K4

