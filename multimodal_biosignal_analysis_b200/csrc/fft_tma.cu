@@ -46,35 +46,42 @@ __device__ __forceinline__ void group_sync(int id, int n) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
-template <bool SWZ>
+// CP = channel pairs per tile row: 4 (tiles of 8 channels, 32-byte raw rows) or 2 (tiles of 4 channels, 16-byte raw
+// rows - half-size tiles for the four-worker pipeline).
+template <bool SWZ, int CP = 4>
 __device__ __forceinline__ uint32_t raw_off(int n, int cp) {
-    const uint32_t lin = (uint32_t)n * 32u + (uint32_t)cp * 8u;
-    return SWZ ? (lin ^ (((lin >> 7) & 3u) << 4)) : lin;
+    const uint32_t lin = (uint32_t)n * (8u * CP) + (uint32_t)cp * 8u;
+    return (SWZ && CP == 4) ? (lin ^ (((lin >> 7) & 3u) << 4)) : lin;
 }
-// byte offset of complex point p (channel pair cp) in the interleaved work layout: 64-byte rows, rows of odd
-// 16-row groups swapped pairwise so that first-pass stores (row stride 16) spread over all banks
+// byte offset of complex point p (channel pair cp) in the interleaved work layout: rows of CP * 16 bytes; the low
+// row bits are XOR-ed with the 16-row group index so that first-pass stores (row stride 16) spread over all banks:
+// one bit for 64-byte rows (two rows per 128 bytes), two bits for 32-byte rows (four rows per 128 bytes).  The
+// swizzle commutes with adding multiples of kSwzPeriod rows.
+template <int CP = 4>
 __device__ __forceinline__ uint32_t pt_off(int p, int cp) {
-    return (uint32_t)(p ^ ((p >> 4) & 1)) * 64u + (uint32_t)cp * 16u;
+    return (uint32_t)(p ^ ((p >> 4) & (CP == 4 ? 1 : 3))) * (16u * CP) + (uint32_t)cp * 16u;
 }
+template <int CP> struct SwzPeriod { static constexpr int value = CP == 4 ? 32 : 64; };
 
-// Row swizzle p -> p ^ ((p >> 4) & 1) commutes with adding multiples of 32 rows, so it is applied once per
-// butterfly (all strides used after the first pass are multiples of 32 rows for M >= 512).
-template <int M, int R, int NS, class TW>
+// The row swizzle commutes with adding multiples of SwzPeriod rows, so it is applied once per butterfly whenever the
+// pass stride is such a multiple (all strides after the first pass for M >= 512 with 8-channel tiles).
+template <int M, int R, int NS, int CP, class TW>
 __device__ __forceinline__ void pass_pair(uint32_t sbuf, const TW& twM, int tid, int bar_id) {
-    constexpr int NT = M / 4;
+    constexpr int NT = M * CP / 16;
     constexpr int B = kPtsPerThread / R;
     constexpr int STRIDE = M / R;
-    constexpr bool kHoist = (STRIDE % 32 == 0) && (NS % 32 == 0 || NS >= 32);
+    constexpr int P = SwzPeriod<CP>::value;
+    constexpr uint32_t RB = 16u * CP;              // bytes per point row
     float2 va[B][R], vb[B][R];
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const int q = tid + b * NT;
-        const int cp = q & 3, j = q >> 2;
-        const uint32_t base = sbuf + pt_off(j, cp);
+        const int cp = q & (CP - 1), j = q / CP;
+        const uint32_t base = sbuf + pt_off<CP>(j, cp);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const float4 t = lds128(STRIDE % 32 == 0 ? base + (uint32_t)(r * STRIDE) * 64u
-                                                     : sbuf + pt_off(j + r * STRIDE, cp));
+            const float4 t = lds128(STRIDE % P == 0 ? base + (uint32_t)(r * STRIDE) * RB
+                                                    : sbuf + pt_off<CP>(j + r * STRIDE, cp));
             va[b][r] = make_float2(t.x, t.y);
             vb[b][r] = make_float2(t.z, t.w);
         }
@@ -87,21 +94,20 @@ __device__ __forceinline__ void pass_pair(uint32_t sbuf, const TW& twM, int tid,
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const int q = tid + b * NT;
-        const int cp = q & 3, j = q >> 2;
+        const int cp = q & (CP - 1), j = q / CP;
         const int k = j % NS;
         const int j0 = (j / NS) * (NS * R) + k;
-        const uint32_t base = sbuf + pt_off(j0, cp);
+        const uint32_t base = sbuf + pt_off<CP>(j0, cp);
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            sts128(NS % 32 == 0 ? base + (uint32_t)(r * NS) * 64u : sbuf + pt_off(j0 + r * NS, cp),
+            sts128(NS % P == 0 ? base + (uint32_t)(r * NS) * RB : sbuf + pt_off<CP>(j0 + r * NS, cp),
                    make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
     }
     group_sync(bar_id, NT);
-    (void)kHoist;
 }
 
 // Transforms the raw tile that sits at `sbuf` (N rows x 8 channels, written by TMA) in place and writes the
-// requested bins of window row `kw`.  Executed by the NT = M / 4 threads that synchronise on barrier `bar_id`.
+// requested bins of window row `kw`.  Executed by the NT = M * CP / 16 threads that synchronise on barrier `bar_id`.
 #ifdef CMC_K1_PROFILE
 // instrumented build only: per-phase clock64() totals of thread 0 of worker 0 of every CTA
 __device__ unsigned long long g_k1_cycles[8];
@@ -119,7 +125,7 @@ struct NoPoll {
 
 // TAB: the window rows, twM and the requested entries of twN have been staged in shared memory at `tab_s`
 // (layout: twM [M], twN [F], windows [n_win][N] floats); otherwise they are read from global memory.
-template <int M, bool SWZ, class Poll, bool TAB = false>
+template <int M, bool SWZ, class Poll, bool TAB = false, int CP = 4>
 __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, float* part, float* mean_s, int tid, int bar_id, int kw,
                                              int seg, int c0, int n_ch, const float* __restrict__ windows, int n_win,
                                              int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
@@ -130,7 +136,10 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
     const Tab<TAB> win2{reinterpret_cast<const float2*>(windows + (int64_t)kw * (2 * M)),
                         tab_s + 8u * (uint32_t)(M + F) + 4u * (uint32_t)(kw * 2 * M)};    // pairs (w[2p], w[2p+1])
     constexpr int N = 2 * M;
-    constexpr int NT = M / 4;
+    constexpr int NT = M * CP / 16;
+    constexpr int CT = 2 * CP;
+    constexpr int P = SwzPeriod<CP>::value;
+    constexpr uint32_t RB = 16u * CP;
     constexpr int R0 = Plan<M>::R0, R1 = Plan<M>::R1, R2 = Plan<M>::R2;
     constexpr int B0 = kPtsPerThread / R0;
     constexpr int S0 = M / R0;
@@ -139,15 +148,16 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
 #pragma unroll
     for (int b = 0; b < B0; ++b) {
         const int q = tid + b * NT;
-        const int cp = q & 3, j = q >> 2;
-        // rows are 32 bytes and a lane group of four owns one row, so a half-warp that read the even rows of four
-        // consecutive points would hit only half of the banks; every other point pair reads its odd row first
-        const int sw = (j >> 1) & 1;
+        const int cp = q & (CP - 1), j = q / CP;
+        // raw rows are CP * 8 bytes and a lane group of CP owns one row, so a half-warp that read the even rows of
+        // consecutive points would hit only half of the banks: every other group of 8 / CP points reads its odd
+        // row first
+        const int sw = (j >> (CP == 4 ? 1 : 2)) & 1;
 #pragma unroll
         for (int r = 0; r < R0; ++r) {
             const int n0 = 2 * (j + r * S0);
-            const float2 first = lds64(sbuf + raw_off<SWZ>(n0 + sw, cp));
-            const float2 second = lds64(sbuf + raw_off<SWZ>(n0 + 1 - sw, cp));
+            const float2 first = lds64(sbuf + raw_off<SWZ, CP>(n0 + sw, cp));
+            const float2 second = lds64(sbuf + raw_off<SWZ, CP>(n0 + 1 - sw, cp));
             const float2 re = sw ? second : first;                      // x[2p][c], x[2p][c+1]
             const float2 im = sw ? first : second;                      // x[2p+1][c], x[2p+1][c+1]
             va[b][r] = make_float2(re.x, im.x);
@@ -165,33 +175,33 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
                     sa += va[b][r].x + va[b][r].y;
                     sb += vb[b][r].x + vb[b][r].y;
                 }
-            // lanes with equal (lane & 3) hold the same channel pair: fixed-order butterfly reduction
+            // lanes with equal (lane % CP) hold the same channel pair: fixed-order butterfly reduction
 #pragma unroll
-            for (int off = 16; off >= 4; off >>= 1) {
+            for (int off = 16; off >= CP; off >>= 1) {
                 sa += __shfl_xor_sync(0xffffffffu, sa, off);
                 sb += __shfl_xor_sync(0xffffffffu, sb, off);
             }
-            if ((tid & 31) < 4) {
-                part[(tid >> 5) * kTmaCT + 2 * (tid & 31)] = sa;
-                part[(tid >> 5) * kTmaCT + 2 * (tid & 31) + 1] = sb;
+            if ((tid & 31) < CP) {
+                part[(tid >> 5) * CT + 2 * (tid & 31)] = sa;
+                part[(tid >> 5) * CT + 2 * (tid & 31) + 1] = sb;
             }
             group_sync(bar_id, NT);
             // every thread folds the warp partials of its own channel pair (same order everywhere): no second barrier
             float ta = 0.f, tb = 0.f;
 #pragma unroll
             for (int w = 0; w < NT / 32; ++w) {
-                ta += part[w * kTmaCT + 2 * (tid & 3)];
-                tb += part[w * kTmaCT + 2 * (tid & 3) + 1];
+                ta += part[w * CT + 2 * (tid & (CP - 1))];
+                tb += part[w * CT + 2 * (tid & (CP - 1)) + 1];
             }
             mua = ta * (1.0f / N);
             mub = tb * (1.0f / N);
-            if (tid < 4) {                                 // kept for the other tapers of this segment
+            if (tid < CP) {                                // kept for the other tapers of this segment
                 mean_s[2 * tid] = mua;
                 mean_s[2 * tid + 1] = mub;
             }
         } else {
-            mua = mean_s[2 * (tid & 3)];
-            mub = mean_s[2 * (tid & 3) + 1];
+            mua = mean_s[2 * (tid & (CP - 1))];
+            mub = mean_s[2 * (tid & (CP - 1)) + 1];
         }
     }
     // every thread has its raw samples in registers: the tile may now be overwritten in place (the barrier of the mean
@@ -202,7 +212,7 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
 #pragma unroll
     for (int b = 0; b < B0; ++b) {
         const int q = tid + b * NT;
-        const int cp = q & 3, j = q >> 2;
+        const int cp = q & (CP - 1), j = q / CP;
 #pragma unroll
         for (int r = 0; r < R0; ++r) {
             const float2 w = win2(j + r * S0);
@@ -213,7 +223,7 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
         dft<R0>(vb[b]);
 #pragma unroll
         for (int r = 0; r < R0; ++r)
-            sts128(sbuf + pt_off(j * R0 + r, cp), make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
+            sts128(sbuf + pt_off<CP>(j * R0 + r, cp), make_float4(va[b][r].x, va[b][r].y, vb[b][r].x, vb[b][r].y));
     }
     group_sync(bar_id, NT);
     K1_TICK(2);
@@ -229,20 +239,20 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
     constexpr int NSL = M / RL;
     float2* out = spec + ((int64_t)(seg * n_win + kw) * F) * spec_ld + c0;
     if (RL > 1 && bin_lo + F <= NSL) {
-        if (R2 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(sbuf, twM, tid, bar_id);
+        if (R2 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0, CP>(sbuf, twM, tid, bar_id);
         K1_TICK(3);
         poll();
-        for (int q = tid; q < F * 4; q += NT) {
-            const int cp = q & 3, bi = q >> 2;
+        for (int q = tid; q < F * CP; q += NT) {
+            const int cp = q & (CP - 1), bi = q / CP;
             const int b = bin_lo + bi;
             const int kk = (NSL - b) & (NSL - 1);
-            const uint32_t pa = sbuf + pt_off(b, cp), pb = sbuf + pt_off(kk, cp);
+            const uint32_t pa = sbuf + pt_off<CP>(b, cp), pb = sbuf + pt_off<CP>(kk, cp);
             float4 A = lds128(pa), Bz = lds128(pb);
 #pragma unroll
             for (int r = 1; r < RL; ++r) {
                 const float2 w = twM(r * b);
-                const float4 ya = lds128(NSL % 32 == 0 ? pa + (uint32_t)(r * NSL) * 64u : sbuf + pt_off(b + r * NSL, cp));
-                const float4 yb = lds128(NSL % 32 == 0 ? pb + (uint32_t)(r * NSL) * 64u : sbuf + pt_off(kk + r * NSL, cp));
+                const float4 ya = lds128(NSL % P == 0 ? pa + (uint32_t)(r * NSL) * RB : sbuf + pt_off<CP>(b + r * NSL, cp));
+                const float4 yb = lds128(NSL % P == 0 ? pb + (uint32_t)(r * NSL) * RB : sbuf + pt_off<CP>(kk + r * NSL, cp));
                 A.x = fmaf(-w.y, ya.y, fmaf(w.x, ya.x, A.x));
                 A.y = fmaf(w.y, ya.x, fmaf(w.x, ya.y, A.y));
                 A.z = fmaf(-w.y, ya.w, fmaf(w.x, ya.z, A.z));
@@ -278,25 +288,25 @@ __device__ __forceinline__ void process_tile(const Poll& poll, uint32_t sbuf, fl
         K1_TICK(5);
         return;
     }
-    if (R1 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0>(sbuf, twM, tid, bar_id);
+    if (R1 > 1) pass_pair<M, (R1 > 1 ? R1 : 2), R0, CP>(sbuf, twM, tid, bar_id);
     K1_TICK(3);
     poll();
-    if (R2 > 1) pass_pair<M, (R2 > 1 ? R2 : 2), R0 * R1>(sbuf, twM, tid, bar_id);
+    if (R2 > 1) pass_pair<M, (R2 > 1 ? R2 : 2), R0 * R1, CP>(sbuf, twM, tid, bar_id);
     K1_TICK(4);
     poll();
 
     // ---- real-FFT split for the requested bins.  One item = (bin, half of the channel tile): two channel pairs
     // with independent loads and arithmetic, so that the F * 2 items of a band-limited request fit one round of
     // the worker's threads instead of a full round plus a mostly idle one ----
-    for (int q = tid; q < F * 2; q += NT) {
-        const int half = q & 1, bi = q >> 1;
+    for (int q = tid; q < F * (CP / 2); q += NT) {
+        const int half = q % (CP / 2), bi = q / (CP / 2);
         const int b = bin_lo + bi;
         const float2 w = twN(b);
         float4 A[2], Bz[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            A[u] = lds128(sbuf + pt_off(b & (M - 1), 2 * half + u));
-            Bz[u] = lds128(sbuf + pt_off((M - b) & (M - 1), 2 * half + u));
+            A[u] = lds128(sbuf + pt_off<CP>(b & (M - 1), 2 * half + u));
+            Bz[u] = lds128(sbuf + pt_off<CP>((M - b) & (M - 1), 2 * half + u));
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -338,13 +348,14 @@ namespace cmc {
 #endif
 
 // one thread: raw tile of (segment start, channel tile) -> shared memory, N rows of 32 bytes in boxes of 256 rows
-template <int M>
+template <int M, int CP = 4>
 __device__ __forceinline__ void issue_tile_tma(unsigned char* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int start) {
     constexpr int N = 2 * M;
+    constexpr int ROW = 8 * CP;                // bytes per raw row
     fence_proxy_async();                       // earlier generic-proxy accesses before async-proxy writes
-    mbar_arrive_expect_tx(bar, N * 32);
+    mbar_arrive_expect_tx(bar, N * ROW);
 #pragma unroll 1
-    for (int i = 0; i < N / 256; ++i) tma_load_2d(dst + i * 256 * 32, tmap, bar, c0, start + i * 256);
+    for (int i = 0; i < N / 256; ++i) tma_load_2d(dst + i * 256 * ROW, tmap, bar, c0, start + i * 256);
 }
 
 // Basic kernel: one CTA per (segment, channel tile), 2 CTAs per SM.
@@ -380,19 +391,23 @@ fft_segments_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n_ch,
     }
 }
 
-// Pipelined kernel: one persistent CTA per SM with TWO workers of NT threads and THREE tile buffers.  Each worker
-// transforms its current tile while the free buffer receives the next tile of whichever worker claims it first;
-// when a worker moves on to its prefetched buffer it hands the old one back.  The basic kernel serialises the
-// TMA wait and the butterflies inside a CTA (53.9 us = 0.75 x (40.6 compute + 25.4 load), profiles/r01b); here the
-// load of tile t + 1 overlaps the transform of tile t.  At most one prefetch is outstanding at any time (3 buffers,
-// 2 in use), so a single-slot free list suffices.
-struct PipeCtrl {
-    uint64_t full[3];
-    int free_buf;            // index of the idle buffer or -1
-    unsigned fills[3];       // number of TMA fills issued into each buffer (parity of the next wait)
-    int next_buf[2];         // per worker: prefetched buffer or -1
-    unsigned next_parity[2];
-    long long next_tile[2];  // per worker: tile claimed for the next round
+// Pipelined kernel: one persistent CTA per SM with NW workers of NT threads and NW + NW / 2 tile buffers.  Each worker
+// transforms its current tile while an idle buffer receives the next tile of whichever worker claims it first; when
+// a worker moves on to its prefetched buffer it hands the old one back.  The basic kernel serialises the TMA wait
+// and the butterflies inside a CTA (53.9 us = 0.75 x (40.6 compute + 25.4 load), profiles/r01b); here the load of
+// tile t + 1 overlaps the transform of tile t.
+//   CP = 4: tiles of 8 channels (64 KB at N = 2048), two 256-thread workers, three buffers, one prefetch in flight;
+//   CP = 2: tiles of 4 channels (32 KB), FOUR 128-thread workers, six buffers, two prefetches in flight - the
+//           worker barriers span 4 warps instead of 8 and three other workers can issue while one waits
+//           (profiles/r01b addendum 8: barrier stalls 1.9 and load waits 0.6 cycles per issued instruction).
+template <int NB>
+struct PipeCtrlT {
+    uint64_t full[NB];
+    unsigned free_mask;      // bit b set: buffer b is idle
+    unsigned fills[NB];      // number of TMA fills issued into each buffer (parity of the next wait)
+    int next_buf[4];         // per worker: prefetched buffer or -1
+    unsigned next_parity[4];
+    long long next_tile[4];  // per worker: tile claimed for the next round
 };
 
 // Tiles beyond the first one of every worker are claimed from a device-wide counter, so workers that start late
@@ -403,7 +418,7 @@ struct PipeCtrl {
 // fresh slot of its own (parallel graph branches, graphs replayed beside eager work); when a pool runs out the
 // launch uses the fixed tile stride instead (tile_counter_for).
 struct TileCounter {
-    unsigned next;           // tiles claimed so far beyond the 2 * gridDim.x initial ones
+    unsigned next;           // tiles claimed so far beyond the initial (workers per CTA) * gridDim.x ones
     unsigned done;           // workers that have left the kernel
 };
 constexpr int kTileCounterEagerSlots = 64;       // distinct (device, stream) pairs with a claim counter
@@ -434,10 +449,10 @@ static TileCounter* tile_counter_for(int dev, cudaStream_t st) {
     return slots + it->second;
 }
 
-__device__ __forceinline__ void worker_leave(TileCounter* ctr, int tid) {
+__device__ __forceinline__ void worker_leave(TileCounter* ctr, int tid, int n_workers) {
     if (tid == 0 && ctr) {
         __threadfence();
-        if (atomicAdd(&ctr->done, 1u) == 2u * gridDim.x - 1u) {   // every worker has claimed its last tile
+        if (atomicAdd(&ctr->done, 1u) == (unsigned)n_workers * gridDim.x - 1u) {   // every worker has claimed its last tile
             ctr->next = 0u;
             ctr->done = 0u;
             __threadfence();
@@ -453,74 +468,94 @@ struct PipeSecond {
     float2* spec;            // its output base (channel 0 of the second recording)
 };
 
-template <int M, bool TAB>
-__global__ void __launch_bounds__(M / 2, 1)
+__device__ __forceinline__ int claim_free(unsigned* mask) {
+    unsigned m = *reinterpret_cast<volatile unsigned*>(mask);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        const unsigned old = atomicAnd(mask, ~(1u << b));
+        if (old & (1u << b)) return b;
+        m = old & ~(1u << b);
+    }
+    return -1;
+}
+
+template <int M, bool TAB, int CP>
+__global__ void __launch_bounds__((M * CP / 16) * (8 / CP), 1)
 fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap2,
                              int n_ch, const PipeSecond second, int n_seg,
                              const int64_t* __restrict__ seg_starts, const float* __restrict__ windows, int n_win,
                              int detrend, int bin_lo, int F, float2* __restrict__ spec, int64_t spec_ld,
                              const float2* __restrict__ twM, const float2* __restrict__ twN, TileCounter* ctr) {
     constexpr int N = 2 * M;
-    constexpr int NT = M / 4;                  // threads per worker
-    constexpr int kTileBytes = N * 32;
+    constexpr int CT = 2 * CP;
+    constexpr int NT = M * CP / 16;            // threads per worker
+    constexpr int NW = 8 / CP;                 // workers per CTA (NW * NT = M / 2 threads)
+    constexpr int NB = NW + NW / 2;            // tile buffers
+    constexpr int kTileBytes = N * CT * 4;
+    using PipeCtrl = PipeCtrlT<NB>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    float* part_all = reinterpret_cast<float*>(base + 3 * kTileBytes);          // [2][NT / 32][8]
-    float* mean_all = part_all + 2 * (NT / 32) * kTmaCT;                        // [2][8]
-    PipeCtrl* ctl = reinterpret_cast<PipeCtrl*>(mean_all + 2 * kTmaCT);
+    float* part_all = reinterpret_cast<float*>(base + NB * kTileBytes);         // [NW][NT / 32][CT]
+    float* mean_all = part_all + NW * (NT / 32) * CT;                           // [NW][CT]
+    PipeCtrl* ctl = reinterpret_cast<PipeCtrl*>(mean_all + NW * CT);
     // TAB: twM [M], the requested twN entries [F] and the window rows [n_win][N] live in shared memory for the whole
     // launch (the CTA is persistent), so the per-tile table loads are shared-memory round trips
     float2* tab = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(ctl) + ((sizeof(PipeCtrl) + 15) & ~size_t(15)));
     const uint32_t tab_s = TAB ? smem_u32(tab) : 0u;
+    const int worker = threadIdx.x / NT;
+    const int tid = threadIdx.x - worker * NT;
+    const int bar_id = 1 + worker;
+    float* part = part_all + worker * (NT / 32) * CT;
+    float* mean_s = mean_all + worker * CT;
+    const int n_ct0 = (n_ch + CT - 1) / CT;
+    const int n_ct = n_ct0 + (second.n_ch + CT - 1) / CT;
+    const long long total = (long long)n_seg * n_ct;
+    const long long first_wave = (long long)NW * gridDim.x;   // tiles handed out statically
+    long long t = (long long)NW * blockIdx.x + worker;        // first tile is static, the rest come from the counter
+    // tile -> (recording, first channel): channel tiles [0, n_ct0) belong to the first recording
+    auto tile_map = [&](long long tile, int& c0) -> const CUtensorMap* {
+        const int ct = (int)(tile % n_ct);
+        c0 = (ct < n_ct0 ? ct : ct - n_ct0) * CT;
+        return ct < n_ct0 ? &tmap : &tmap2;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NB; ++b) {
+            mbar_init(&ctl->full[b], 1);
+            ctl->fills[b] = 0;
+        }
+        ctl->free_mask = ((1u << NB) - 1u) & ~((1u << NW) - 1u);     // buffers NW .. NB - 1 start idle
+        for (int w = 0; w < NW; ++w) ctl->next_buf[w] = -1;
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap);
+        if (second.n_ch) tma_prefetch_desc(&tmap2);
+        // the first tile of every worker is on its way before the tables are staged
+        for (int w = 0; w < NW; ++w) {
+            const long long tw = (long long)NW * blockIdx.x + w;
+            if (tw < total) {
+                int c0f;
+                const CUtensorMap* mf = tile_map(tw, c0f);
+                issue_tile_tma<M, CP>(base + w * kTileBytes, mf, &ctl->full[w], c0f, (int)seg_starts[tw / n_ct]);
+                ctl->fills[w] = 1;
+            }
+        }
+    }
     if (TAB) {
         for (int i = threadIdx.x; i < M; i += blockDim.x) tab[i] = __ldg(twM + i);
         for (int i = threadIdx.x; i < F; i += blockDim.x) tab[M + i] = __ldg(twN + bin_lo + i);
         float* wtab = reinterpret_cast<float*>(tab + M + F);
         for (int i = threadIdx.x; i < n_win * N; i += blockDim.x) wtab[i] = __ldg(windows + i);
     }
-    const int worker = threadIdx.x / NT;
-    const int tid = threadIdx.x - worker * NT;
-    const int bar_id = 1 + worker;
-    float* part = part_all + worker * (NT / 32) * kTmaCT;
-    float* mean_s = mean_all + worker * kTmaCT;
-    const int n_ct0 = (n_ch + kTmaCT - 1) / kTmaCT;
-    const int n_ct = n_ct0 + (second.n_ch + kTmaCT - 1) / kTmaCT;
-    const long long total = (long long)n_seg * n_ct;
-    long long t = 2ll * blockIdx.x + worker;   // first tile is static, the rest come from the counter
-    // tile -> (recording, first channel): channel tiles [0, n_ct0) belong to the first recording
-    auto tile_map = [&](long long tile, int& c0) -> const CUtensorMap* {
-        const int ct = (int)(tile % n_ct);
-        c0 = (ct < n_ct0 ? ct : ct - n_ct0) * kTmaCT;
-        return ct < n_ct0 ? &tmap : &tmap2;
-    };
-
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < 3; ++b) {
-            mbar_init(&ctl->full[b], 1);
-            ctl->fills[b] = 0;
-        }
-        ctl->free_buf = 2;
-        ctl->next_buf[0] = ctl->next_buf[1] = -1;
-        fence_barrier_init();
-        tma_prefetch_desc(&tmap);
-        if (second.n_ch) tma_prefetch_desc(&tmap2);
-    }
     __syncthreads();
-    if (t >= total) {                          // this worker has no tile; buffer 2 stays with the other worker
-        worker_leave(ctr, tid);
+    if (t >= total) {                          // this worker has no tile; its buffer stays unused
+        worker_leave(ctr, tid, NW);
         return;
     }
 
     int cur = worker;
     unsigned cur_parity = 0;
     long long tn = total, tnn = total;         // thread 0 of the worker: tiles claimed for the next two rounds
-    if (tid == 0) {
-        int c0f;
-        const CUtensorMap* mf = tile_map(t, c0f);
-        issue_tile_tma<M>(base + cur * kTileBytes, mf, &ctl->full[cur], c0f, (int)seg_starts[t / n_ct]);
-        ctl->fills[cur] = 1;
-        tn = ctr ? 2ll * gridDim.x + atomicAdd(&ctr->next, 1u) : t + 2ll * gridDim.x;
-    }
+    if (tid == 0) tn = ctr ? first_wave + atomicAdd(&ctr->next, 1u) : t + first_wave;
     while (true) {
         const int seg = (int)(t / n_ct);
         int c0;
@@ -531,13 +566,13 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __g
         if (tid == 0) {
             ctl->next_tile[worker] = tn;       // read by the whole worker after the tile's last barrier
             // claim one round ahead: the atomic's round trip hides behind this tile
-            tnn = !ctr ? tn + 2ll * gridDim.x : (tn < total ? 2ll * gridDim.x + atomicAdd(&ctr->next, 1u) : total);
+            tnn = !ctr ? tn + first_wave : (tn < total ? first_wave + atomicAdd(&ctr->next, 1u) : total);
         }
         for (int kw = 0; kw < n_win; ++kw) {
             if (kw > 0 && tid == 0) {          // the in-place transform consumed the raw tile: fetch it again
                 cur_parity = ctl->fills[cur] & 1;
                 ctl->fills[cur] += 1;
-                issue_tile_tma<M>(base + cur * kTileBytes, cur_map, &ctl->full[cur], c0, (int)seg_starts[seg]);
+                issue_tile_tma<M, CP>(base + cur * kTileBytes, cur_map, &ctl->full[cur], c0, (int)seg_starts[seg]);
             }
             if (kw > 0) {
                 group_sync(bar_id, NT);
@@ -550,34 +585,34 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __g
 #ifdef CMC_K1_PROFILE
             if (tid == 0 && worker == 0) atomicAdd(&g_k1_cycles[0], (unsigned long long)(clock64() - w0_));
 #endif
-            // thread 0 of the worker tries to claim the idle buffer for the worker's next tile - here and again after
-            // every pass barrier, so that a buffer released by the other worker mid-tile is picked up at once
+            // thread 0 of the worker tries to claim an idle buffer for the worker's next tile - here and again after
+            // every pass barrier, so that a buffer released by another worker mid-tile is picked up at once
             auto poll = [&]() {
                 if (tid == 0 && kw == n_win - 1 && tn < total && ctl->next_buf[worker] < 0) {
-                    const int fb = atomicExch(&ctl->free_buf, -1);
+                    const int fb = claim_free(&ctl->free_mask);
                     if (fb >= 0) {
                         ctl->next_parity[worker] = ctl->fills[fb] & 1;
                         ctl->fills[fb] += 1;
                         int c0n;
                         const CUtensorMap* mn = tile_map(tn, c0n);
-                        issue_tile_tma<M>(base + fb * kTileBytes, mn, &ctl->full[fb], c0n, (int)seg_starts[tn / n_ct]);
+                        issue_tile_tma<M, CP>(base + fb * kTileBytes, mn, &ctl->full[fb], c0n, (int)seg_starts[tn / n_ct]);
                         ctl->next_buf[worker] = fb;
                     }
                 }
             };
             poll();
-            process_tile<M, false, decltype(poll), TAB>(poll, smem_u32(base + cur * kTileBytes), part, mean_s, tid, bar_id,
-                                                        kw, seg, c0, cur_nch, windows, n_win, detrend, bin_lo, F, cur_spec,
-                                                        spec_ld, twM, twN, tab_s);
+            process_tile<M, false, decltype(poll), TAB, CP>(poll, smem_u32(base + cur * kTileBytes), part, mean_s, tid,
+                                                            bar_id, kw, seg, c0, cur_nch, windows, n_win, detrend, bin_lo,
+                                                            F, cur_spec, spec_ld, twM, twN, tab_s);
         }
         // process_tile ended with a worker barrier: the buffer is no longer read and ctl->next_* is visible
         t = ctl->next_tile[worker];
         if (t >= total) {
             if (tid == 0) {
                 __threadfence_block();
-                atomicCAS(&ctl->free_buf, -1, cur);                // let the other worker prefetch into it
+                atomicOr(&ctl->free_mask, 1u << cur);              // let another worker prefetch into it
             }
-            worker_leave(ctr, tid);
+            worker_leave(ctr, tid, NW);
             break;
         }
         tn = tnn;
@@ -588,17 +623,17 @@ fft_segments_tma_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __g
             if (tid == 0) {
                 ctl->next_buf[worker] = -1;
                 __threadfence_block();
-                atomicCAS(&ctl->free_buf, -1, cur);                // hand the old buffer back
+                atomicOr(&ctl->free_mask, 1u << cur);              // hand the old buffer back
             }
             cur = nb;
             cur_parity = np;
         } else {
-            // no prefetch happened (the other worker held the idle buffer): reload in place
+            // no prefetch happened (the other workers held the idle buffers): reload in place
             if (tid == 0) {
                 ctl->fills[cur] += 1;
                 int c0r;
                 const CUtensorMap* mr = tile_map(t, c0r);
-                issue_tile_tma<M>(base + cur * kTileBytes, mr, &ctl->full[cur], c0r, (int)seg_starts[t / n_ct]);
+                issue_tile_tma<M, CP>(base + cur * kTileBytes, mr, &ctl->full[cur], c0r, (int)seg_starts[t / n_ct]);
             }
             group_sync(bar_id, NT);
             cur_parity = (ctl->fills[cur] - 1) & 1;
@@ -621,31 +656,31 @@ static int launch_tma(const CUtensorMap& tmap, int n_ch, const int64_t* seg_star
     return CMC_OK;
 }
 
-template <int M>
+template <int M, int CP>
 static int launch_tma_pipe(const CUtensorMap& tmap, int n_ch, const CUtensorMap& tmap2, const PipeSecond& second,
                            const int64_t* seg_starts, int n_seg, const float* windows,
                            int n_win, int detrend, int bin_lo, int F, float2* spec, int64_t spec_ld, const float2* twM,
                            const float2* twN, cudaStream_t st) {
-    constexpr int NT = M / 4;
-    const size_t smem_base = 1024 + 3 * (size_t)M * 64 + sizeof(float) * 2 * ((NT / 32) * kTmaCT + kTmaCT) +
-                             sizeof(PipeCtrl) + 32;
+    constexpr int CT = 2 * CP, NT = M * CP / 16, NW = 8 / CP, NB = NW + NW / 2;
+    const size_t smem_base = 1024 + (size_t)NB * (2 * M) * CT * 4 + sizeof(float) * NW * ((NT / 32) * CT + CT) +
+                             sizeof(PipeCtrlT<NB>) + 32;
     // twiddles, requested split twiddles and window rows next to the tile buffers when they fit
     const size_t tab_bytes = ((size_t)M + F) * 8 + (size_t)n_win * 2 * M * 4;
     const bool tab = smem_base + tab_bytes <= 227 * 1024;
     const size_t smem = smem_base + (tab ? tab_bytes : 0);
-    auto kern = tab ? fft_segments_tma_pipe_kernel<M, true> : fft_segments_tma_pipe_kernel<M, false>;
+    auto kern = tab ? fft_segments_tma_pipe_kernel<M, true, CP> : fft_segments_tma_pipe_kernel<M, false, CP>;
     int rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
     if (rc) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT + (second.n_ch + kTmaCT - 1) / kTmaCT);
-    const long long grid = (tiles + 1) / 2 < sms ? (tiles + 1) / 2 : sms;
+    const long long tiles = (long long)n_seg * ((n_ch + CT - 1) / CT + (second.n_ch + CT - 1) / CT);
+    const long long grid = (tiles + NW - 1) / NW < sms ? (tiles + NW - 1) / NW : sms;
     // claim counter private to this launch's stream / graph node (zero-initialised device memory, reset by the kernel)
     static const bool static_tiles = getenv("CMC_FFT_STATIC_TILES") != nullptr;      // fixed stride instead of claims
     TileCounter* ctr = static_tiles ? nullptr : tile_counter_for(dev, st);
-    kern<<<(unsigned)grid, 2 * NT, smem, st>>>(tmap, tmap2, n_ch, second, n_seg, seg_starts, windows, n_win, detrend,
-                                               bin_lo, F, spec, spec_ld, twM, twN, ctr);
+    kern<<<(unsigned)grid, NW * NT, smem, st>>>(tmap, tmap2, n_ch, second, n_seg, seg_starts, windows, n_win, detrend,
+                                                bin_lo, F, spec, spec_ld, twM, twN, ctr);
     CMC_CHECK_LAUNCH("fft_segments_tma_pipe_kernel");
     return CMC_OK;
 }
@@ -654,7 +689,7 @@ static bool tma_layout_ok(const float* x, int64_t n_samples, int64_t ld) {
     return (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && n_samples < (1ll << 31);
 }
 
-static int make_recording_map(CUtensorMap* tmap, const float* x, int64_t n_samples, int n_ch, int64_t ld) {
+static int make_recording_map(CUtensorMap* tmap, const float* x, int64_t n_samples, int n_ch, int64_t ld, int ct) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
@@ -663,7 +698,7 @@ static int make_recording_map(CUtensorMap* tmap, const float* x, int64_t n_sampl
     // conflicted (4 instead of 2 wavefronts per request), every other access is conflict free.
     cuuint64_t dims[2] = {(cuuint64_t)n_ch, (cuuint64_t)n_samples};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kTmaCT, 256u};
+    cuuint32_t box[2] = {(cuuint32_t)ct, 256u};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -686,25 +721,34 @@ int fft_segments_tma(const float* x, int64_t n_samples, int n_ch, int64_t ld, co
     if (N != 512 && N != 1024 && N != 2048 && N != 4096) return 1;
     if (!tma_layout_ok(x, n_samples, ld)) return 1;
     if (x2 && (!tma_layout_ok(x2, n_samples, ld2) || N == 4096)) return 1;
+    // CMC_FFT_CT4=1: four half-size workers for N = 2048 (tiles of 4 channels).  Measured 93.8 us against 90.1 us for
+    // the default two 8-channel workers on config 2 (both modalities in one launch): twice the tiles, 16-byte TMA
+    // rows and half-width output stores cost more than the cheaper barriers and the second prefetch gain.
+    static const bool ct4 = getenv("CMC_FFT_CT4") != nullptr;
+    static const bool no_pipe = getenv("CMC_FFT_NO_PIPE") != nullptr;
+    const int ct = (N == 2048 && ct4 && !no_pipe) ? 4 : kTmaCT;
+    const long long n_tiles = (long long)n_seg * ((n_ch + ct - 1) / ct + (x2 ? (n_ch2 + ct - 1) / ct : 0));
+    const bool pipe = !no_pipe && N <= 2048 && n_tiles >= 64 * (kTmaCT / ct);
     CUtensorMap tmap, tmap2;
-    int rc = make_recording_map(&tmap, x, n_samples, n_ch, ld);
+    int rc = make_recording_map(&tmap, x, n_samples, n_ch, ld, pipe ? ct : kTmaCT);
     if (rc) return rc;
     PipeSecond second{0, nullptr};
     if (x2) {
-        if ((rc = make_recording_map(&tmap2, x2, n_samples, n_ch2, ld2))) return rc;
+        if (!pipe) return 1;
+        if ((rc = make_recording_map(&tmap2, x2, n_samples, n_ch2, ld2, ct))) return rc;
         second.n_ch = n_ch2;
         second.spec = spec2;
     } else {
         tmap2 = tmap;
     }
-    // pipelined persistent kernel whenever three tiles fit into shared memory (N <= 2048) and there is enough work
-    static const bool no_pipe = getenv("CMC_FFT_NO_PIPE") != nullptr;
-    const long long n_tiles = (long long)n_seg * ((n_ch + kTmaCT - 1) / kTmaCT + (second.n_ch + kTmaCT - 1) / kTmaCT);
-    if (!no_pipe && n_tiles >= 64) {
+    // pipelined persistent kernel whenever the tile buffers fit into shared memory (N <= 2048) and there is enough work
+    if (pipe) {
         switch (N) {
-            case 512:  return launch_tma_pipe<256>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
-            case 1024: return launch_tma_pipe<512>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
-            case 2048: return launch_tma_pipe<1024>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            case 512:  return launch_tma_pipe<256, 4>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            case 1024: return launch_tma_pipe<512, 4>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+            case 2048:
+                if (ct == 4) return launch_tma_pipe<1024, 2>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
+                return launch_tma_pipe<1024, 4>(tmap, n_ch, tmap2, second, seg_starts, n_seg, windows, n_win, detrend, bin_lo, F, spec, spec_ld, twM, twN, st);
             default: break;
         }
     }
