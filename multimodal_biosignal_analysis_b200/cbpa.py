@@ -180,6 +180,20 @@ def _pvalues(stats_fixed: np.ndarray, h0_fixed: np.ndarray, tail: int) -> np.nda
     return cnt.astype(np.float64) / float(n)
 
 
+class DeviceAdjacency:
+    """A sparse adjacency already converted to sorted CSR int32 on the current CUDA device.  Pass it as
+    ``adjacency=`` to skip the per-call conversion / upload (``sweep.py`` prepares it while the unit stage runs)."""
+
+    def __init__(self, adjacency):
+        adj = sparse.csr_matrix(adjacency)
+        adj.sort_indices()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.shape = adj.shape
+        self.nnz = adj.nnz
+        self.indptr = torch.from_numpy(adj.indptr.astype(np.int32)).to(dev)
+        self.indices = torch.from_numpy(adj.indices.astype(np.int32)).to(dev)
+
+
 def permutation_cluster_1samp_test(X, threshold=None, n_permutations: int = 1024, tail: int = 0,
                                    adjacency=None, n_jobs=None, seed=None, out_type: str = "indices",
                                    verbose=None, *, signs: np.ndarray | None = None, return_details: bool = False):
@@ -202,10 +216,9 @@ def permutation_cluster_1samp_test(X, threshold=None, n_permutations: int = 1024
         threshold = float(t_dist.ppf(1 - p, n_subj - 1)) * (-1 if tail == -1 else 1)
     if (tail < 0 and threshold > 0) or (tail > 0 and threshold < 0) or (tail == 0 and threshold < 0):
         raise ValueError(f"incompatible tail and threshold signs, got {tail} and {threshold}")
-    adj = sparse.csr_matrix(adjacency)
-    if adj.shape != (n_tests, n_tests):
-        raise ValueError(f"adjacency must be ({n_tests}, {n_tests}), got {adj.shape}")
-    adj.sort_indices()
+    adj = adjacency if isinstance(adjacency, DeviceAdjacency) else DeviceAdjacency(adjacency)
+    if tuple(adj.shape) != (n_tests, n_tests):
+        raise ValueError(f"adjacency must be ({n_tests}, {n_tests}), got {tuple(adj.shape)}")
     if signs is None:
         signs = make_sign_table(n_permutations, n_subj, seed, tail)
     signs = np.ascontiguousarray(signs, dtype=np.int8)
@@ -214,8 +227,7 @@ def permutation_cluster_1samp_test(X, threshold=None, n_permutations: int = 1024
 
     dev = torch.device("cuda", torch.cuda.current_device())
     Xd = torch.from_numpy(Xf).to(dev)
-    indptr = torch.from_numpy(adj.indptr.astype(np.int32)).to(dev)
-    indices = torch.from_numpy(adj.indices.astype(np.int32)).to(dev)
+    indptr, indices = adj.indptr, adj.indices
     ws = K.cbpa_workspace(Xd)                                    # both calls share the re-tiled copy of X
     t_obs_d, labels_d, mass_d, n_clusters = K.cbpa_observed(Xd, threshold, tail, indptr, indices, ws=ws)
     n_rows = signs.shape[0]

@@ -58,6 +58,16 @@ def cmc_surrogate_cbpa_sweep(units, sampling_freq: float, nperseg: int = 2048, n
         item = units[keys[u]]
         return item() if callable(item) else item
 
+    # group-level inputs that do not depend on the data (channel adjacency -> lattice adjacency -> device CSR, sign
+    # table) are prepared by a host thread while the unit stage keeps the GPU busy
+    subjects = list(dict.fromkeys(k[0] for k in keys))
+    conditions = list(dict.fromkeys(k[1] for k in keys))
+    if contrasts is None:
+        contrasts = [(conditions[0], conditions[1])] if len(conditions) >= 2 else []
+    index = {k: u for u, k in enumerate(keys)}
+    prep = _GroupPrep(contrasts, subjects, index, load(0), sampling_freq, nperseg, freq_band, spatial_adjacency,
+                      n_permutations, tail, cbpa_seed, signs)
+
     cmc = None
     thr = np.zeros(n_units, dtype=np.float64)
     nsig = np.zeros(n_units, dtype=np.float64)
@@ -96,29 +106,17 @@ def cmc_surrogate_cbpa_sweep(units, sampling_freq: float, nperseg: int = 2048, n
             freqs = f if freq_band is None else f[(f >= freq_band[0]) & (f <= freq_band[1])]
 
     # ---- group level: A - B contrast per subject -> CBPA over (frequency, EEG channel) ----
-    subjects = list(dict.fromkeys(k[0] for k in keys))
-    conditions = list(dict.fromkeys(k[1] for k in keys))
-    if contrasts is None:
-        contrasts = [(conditions[0], conditions[1])] if len(conditions) >= 2 else []
-    index = {k: u for u, k in enumerate(keys)}
-    n_f, n_e = cmc.shape[1], cmc.shape[2]
-    if spatial_adjacency is None and contrasts:
-        if n_e != len(EEG_CHANNELS):
-            raise ValueError("spatial_adjacency is required unless the EEG array holds the 64 channels of the cap")
-        spatial_adjacency = cb.default_spatial_adjacency(EEG_CHANNELS)
     out_cbpa = {}
+    adjacency = prep.result()
     for cond_a, cond_b in contrasts:
-        subj = [s for s in subjects if (s, cond_a) in index and (s, cond_b) in index]
-        if len(subj) < 2:
-            raise ValueError(f"contrast {cond_a!r} - {cond_b!r}: fewer than two subjects have both conditions")
+        subj = prep.subjects_of[(cond_a, cond_b)]
         X = np.stack([cmc[index[(s, cond_a)]].astype(np.float64) - cmc[index[(s, cond_b)]].astype(np.float64)
                       for s in subj])
         q = alpha_cluster_forming / 2 if tail == 0 else alpha_cluster_forming
         t_thresh = float(t_dist.ppf(1.0 - q, df=len(subj) - 1)) * (-1.0 if tail == -1 else 1.0)
-        adjacency = cb.combine_adjacency(n_f, spatial_adjacency)
         t_obs, clusters, pv, H0 = cb.spatio_temporal_cluster_1samp_test(
-            X, threshold=t_thresh, n_permutations=n_permutations, tail=tail, adjacency=adjacency,
-            seed=np.random.default_rng(cbpa_seed), out_type="mask", signs=signs)
+            X, threshold=t_thresh, n_permutations=n_permutations, tail=tail, adjacency=adjacency, out_type="mask",
+            signs=prep.signs[(cond_a, cond_b)])
         out_cbpa[(cond_a, cond_b)] = dict(t_obs=t_obs, clusters=clusters, cluster_pv=pv, H0=H0, t_thresh=t_thresh,
                                           subjects=subj, X=X)
     out = dict(keys=keys, freqs=freqs, cmc=cmc, threshold_fwe=thr, n_significant_pairs=nsig.astype(np.int64),
@@ -132,3 +130,47 @@ def _map_shape(first_item, sampling_freq, nperseg, freq_band):
     f = np.fft.rfftfreq(nperseg, d=1 / sampling_freq)
     n_f = len(f) if freq_band is None else int(((f >= freq_band[0]) & (f <= freq_band[1])).sum())
     return n_f, int(first_item[0].shape[1])
+
+
+class _GroupPrep:
+    """Everything the CBPA needs besides the contrast itself, built on a host thread: which subjects enter each
+    contrast, the (frequency x channel) lattice adjacency as device CSR, and the sign tables (``cbpa.make_sign_table``
+    with ``default_rng(cbpa_seed)``, exactly what ``permutation_cluster_1samp_test`` would draw)."""
+
+    def __init__(self, contrasts, subjects, index, first_item, sampling_freq, nperseg, freq_band, spatial_adjacency,
+                 n_permutations, tail, cbpa_seed, signs):
+        import threading
+        self.subjects_of, self.signs = {}, {}
+        for cond_a, cond_b in contrasts:
+            subj = [s for s in subjects if (s, cond_a) in index and (s, cond_b) in index]
+            if len(subj) < 2:
+                raise ValueError(f"contrast {cond_a!r} - {cond_b!r}: fewer than two subjects have both conditions")
+            self.subjects_of[(cond_a, cond_b)] = subj
+        n_f, n_e = _map_shape(first_item, sampling_freq, nperseg, freq_band)
+        if contrasts and spatial_adjacency is None and n_e != len(EEG_CHANNELS):
+            raise ValueError("spatial_adjacency is required unless the EEG array holds the 64 channels of the cap")
+        self._adj, self._err = None, None
+        device = torch.cuda.current_device()
+
+        def work():
+            try:
+                torch.cuda.set_device(device)
+                sp = spatial_adjacency if spatial_adjacency is not None else cb.default_spatial_adjacency(EEG_CHANNELS)
+                self._adj = cb.DeviceAdjacency(cb.combine_adjacency(n_f, sp))
+                for key, subj in self.subjects_of.items():
+                    self.signs[key] = signs if signs is not None else cb.make_sign_table(
+                        n_permutations, len(subj), np.random.default_rng(cbpa_seed), tail)
+            except Exception as exc:                              # noqa: BLE001 - re-raised by result()
+                self._err = exc
+
+        self._thread = None
+        if contrasts:
+            self._thread = threading.Thread(target=work, name="cmc-group-prep", daemon=True)
+            self._thread.start()
+
+    def result(self):
+        if self._thread is not None:
+            self._thread.join()
+        if self._err is not None:
+            raise self._err
+        return self._adj

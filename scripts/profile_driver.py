@@ -1,5 +1,5 @@
 """Every kernel of the hot path once at its BASELINE size, for `ncu --set full` (scripts/profile_r2.sh):
-config 2 (K1 x 2, K2 direct), config 3 (shift null, phase null of 1,024 surrogates, per-pair histogram pass),
+config 2 (K1 for both modalities, K2 direct), config 3 (shift null, phase null of 1,024 surrogates, per-pair histogram pass),
 the per-window multitaper estimator (K2w, 210 windows x 5 tapers), config 4 CBPA (1,184 permutations = 4 per CTA)."""
 import os
 import sys
@@ -22,19 +22,20 @@ win = torch.from_numpy(signal.get_window("hann", 2048).astype(np.float32)[None])
 L = len(starts_h)
 spec = torch.empty((L, 1, 100, 128), dtype=torch.complex64, device=dev)
 for _ in range(2):                                  # first pass warms tables / attributes, second one is profiled
-    K.fft_segments(eeg_d, starts, win, K.DETREND_CONSTANT, 1, 100, out=spec, ch_offset=0)
-    K.fft_segments(emg_d, starts, win, K.DETREND_CONSTANT, 1, 100, out=spec, ch_offset=64)
+    K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, 1, 100, spec[..., :64], spec[..., 64:])
     res = K.csd_msc(spec[:, 0, :, :64], spec[:, 0, :, 64:])
     shifts = torch.from_numpy(np.random.default_rng(3).integers(1, L, 1000).astype(np.int32)).to(dev)
     K.surrogate_null(res, K.SURR_SHIFT, 0, 1000, shifts=shifts)
     K.surrogate_null(res, K.SURR_PHASE, 0, 1024, seed=7)
-    K.surrogate_null_hist(res, 0, 1024, seed=7, n_bins=128)
+    m_ = res.null_mean()                            # the first window of the per-pair threshold search
+    K.surrogate_null_hist(res, 0, 1024, seed=7, n_bins=128, bin_lo=(1.5 * m_).contiguous(),
+                          bin_scale=(128.0 / (16.0 * m_).clamp(min=1e-12)).contiguous())
     tapers = torch.from_numpy(_dpss(2048, 3, 0.9).astype(np.float32)).to(dev)
-    Xw = K.fft_segments(eeg_d, starts, tapers, K.DETREND_NONE, 1, 100)
-    Yw = K.fft_segments(emg_d, starts, tapers, K.DETREND_NONE, 1, 100)
-    K.msc_windows(Xw, Yw, None, True, float(t_dist.ppf(0.975, 4)), 0.81)
-    K.msc_windows_maxemg(Xw, Yw, None, True, float(t_dist.ppf(0.975, 4)), 0.81, True, False)
-    del Xw, Yw
+    S = torch.empty((L, tapers.shape[0], 100, 128), dtype=torch.complex64, device=dev)
+    K.fft_segments_pair(eeg_d, emg_d, starts, tapers, K.DETREND_NONE, 1, 100, S[..., :64], S[..., 64:])
+    K.msc_windows(S[..., :64], S[..., 64:], None, True, float(t_dist.ppf(0.975, 4)), 0.81)
+    K.msc_windows_maxemg(S[..., :64], S[..., 64:], None, True, float(t_dist.ppf(0.975, 4)), 0.81, True, False)
+    del S
     adj = cb.combine_adjacency(100, cb.find_ch_adjacency_from_positions(syn.sensor_positions(64))).tocsr()
     adj.sort_indices()
     Xc = torch.from_numpy(np.ascontiguousarray(syn.make_cbpa_contrast(20, 100, 64).reshape(20, -1))).to(dev)

@@ -161,3 +161,38 @@ def test_cbpa_subject_counts_and_ragged_maps(cuda_device, n_subj, n_times, n_ch)
     np.testing.assert_array_equal(labels, ref["labels"])
     np.testing.assert_array_equal(mass, ref["mass_fixed"])
     np.testing.assert_array_equal(h0, ref["H0_fixed"][1:])
+
+
+def test_cbpa_lockfree_labelling_is_deterministic_under_repetition(cuda_device):
+    """compute-sanitizer (racecheck) is closed on the GPU pool, so the lock-free shared-memory union-find
+    (csrc/cbpa.cu: atomicCAS hooks, atomic fixed-point masses, permutations claimed from a device counter) is
+    checked the other way round: a race would show as run-to-run variation, so 40 repetitions of the same 1,500
+    permutations - whole range, ragged sub-ranges, shared and private workspaces - must agree bit for bit with each
+    other and with the oracle on a sample."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(99)
+    n_subj, n_times, n_ch = 14, 60, 64
+    adj = ocb.combine_adjacency(n_times, ocb.delaunay_adjacency(syn.sensor_positions(n_ch)))
+    X = rng.standard_normal((n_subj, n_times, n_ch)) + 0.35          # many supra-threshold nodes, large clusters
+    signs = syn.make_sign_table(1500, n_subj, seed=5)
+    thr = t_dist.ppf(0.975, n_subj - 1)
+    indptr, indices = _csr(adj)
+    Xd = torch.as_tensor(np.ascontiguousarray(X.reshape(n_subj, -1))).cuda()
+    sd = torch.as_tensor(signs).cuda()
+    ws = K.cbpa_workspace(Xd)
+    K.cbpa_observed(Xd, thr, 0, indptr, indices, ws=ws)
+    first = K.cbpa_permute(Xd, sd, 0, 1500, thr, 0, indptr, indices, ws=ws, tiled=True).cpu().numpy()
+    for rep in range(40):
+        if rep % 3 == 0:
+            got = K.cbpa_permute(Xd, sd, 0, 1500, thr, 0, indptr, indices, ws=ws, tiled=True).cpu().numpy()
+        elif rep % 3 == 1:
+            got = K.cbpa_permute(Xd, sd, 0, 1500, thr, 0, indptr, indices).cpu().numpy()
+        else:
+            cut = int(rng.integers(1, 1499))
+            got = np.concatenate([K.cbpa_permute(Xd, sd, 0, cut, thr, 0, indptr, indices).cpu().numpy(),
+                                  K.cbpa_permute(Xd, sd, cut, 1500, thr, 0, indptr, indices).cpu().numpy()])
+        np.testing.assert_array_equal(got, first)
+    pick = np.arange(0, 1500, 100)
+    with np.errstate(all="ignore"):
+        ref = ocb.permutation_cluster_1samp_test(X, signs[pick], thr, 0, adj)
+    np.testing.assert_array_equal(first[pick], ref["H0_fixed"][1:])
