@@ -87,6 +87,35 @@ CMC_API int cmc_fft_segments_pair(const float* x1, int n_ch1, int64_t ld1, float
                           const float* windows, int n_win, int N, int detrend,
                           int bin_lo, int bin_hi, int64_t spec_ld, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * K1t  band-limited hann-windowed Welch spectra on the tensor cores.
+ * The reference's Welch path is scipy.signal.coherence with its defaults (preprocessing.py:1228-1230): periodic
+ * hann window, noverlap = nperseg / 2, detrend = 'constant'; its callers keep a narrow band (1 - 100 Hz).  For that
+ * case the spectra are computed WITHOUT an FFT: one BF16 x 3 tcgen05 GEMM per half block of N / 2 samples against a
+ * constant (cos, -sin) table gives the rectangular-window half-block sums P_h[b]; the epilogue applies the hann
+ * window as the three-tap filter 1/2 R[b] - 1/4 (R[b-1] + R[b+1]) and adds the two halves of every segment
+ * (R_s[b] = P_h[b] + (-1)^b P_{h+1}[b]).  Every sample is transformed once although segments overlap by half, and
+ * only the requested bins are computed.  Output identical in meaning to cmc_fft_segments(.., windows = periodic
+ * hann, n_win = 1, ..) to ~1e-5 of the spectrum's rms (BF16 hi + lo operands, FP32 accumulation).
+ *
+ * A plan holds what depends on the segment table, N and the band only: the half-block list (segments that overlap
+ * their predecessor by exactly N / 2 share a half block; any other segment simply costs two) and the table.
+ *   seg_starts_host [n_seg]  int64 on the HOST
+ *   N % 128 == 0, 256 <= N <= 16384; at most 102 bins, bin_hi + 2 <= N / 2; otherwise CMC_EUNSUPPORTED
+ *     (the caller then uses cmc_fft_segments)
+ * cmc_welch_hann_plan_create allocates a few MB of device memory for the plan and synchronises the device once;
+ * destroy frees it.  cmc_welch_hann_spectra is asynchronous on `stream` and may be captured into a CUDA graph.
+ *   x1 [n_samples][ld1], x2 [n_samples][ld2] (x2 may be NULL)   float32 recordings, 16-byte aligned rows
+ *   spec1 / spec2 [n_seg][F][spec_ld] complex64, channel c of recording i at spec_i[..][c]
+ * ---------------------------------------------------------------------------------- */
+CMC_API int cmc_welch_hann_plan_create(const int64_t* seg_starts_host, int n_seg, int N, int bin_lo, int bin_hi,
+                               void** plan_out);
+CMC_API int cmc_welch_hann_plan_destroy(void* plan);
+CMC_API int cmc_welch_hann_plan_info(const void* plan, int* n_half_blocks, int* n_segments, int* n_bins);
+CMC_API int cmc_welch_hann_spectra(const void* plan, const float* x1, int n_ch1, int64_t ld1, float* spec1,
+                           const float* x2, int n_ch2, int64_t ld2, float* spec2, int64_t n_samples,
+                           int detrend, int64_t spec_ld, void* stream);
+
 /* Power spectra from segment spectra: out[w][f][c] = base_scale * dbl(f) * mean_k |spec[w][k][f][c]|^2, with
  * dbl(f) = 2 for bins strictly inside (0, N/2) when one_sided != 0 (scipy density convention), optionally
  * followed by log10(|.| + 1e-10).  Replaces signal.periodogram + mean over tapers of multitaper_psd

@@ -25,6 +25,10 @@ _SIGNATURES = {
                                    _vp, _i64, _vp]),
     "cmc_fft_segments_pair": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i32, _i64, _vp, _i64, _vp, _i32, _vp, _i32, _i32,
                                         _i32, _i32, _i32, _i64, _vp]),
+    "cmc_welch_hann_plan_create": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(C.c_void_p)]),
+    "cmc_welch_hann_plan_destroy": (C.c_int, [_vp]),
+    "cmc_welch_hann_plan_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cmc_welch_hann_spectra": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i32, _i64, _vp, _i64, _i32, _i64, _vp]),
     "cmc_psd_from_spectra": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _f32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "cmc_msc_windows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i32, _f32, _f32,
                                   _vp, _vp, _vp, _vp, _vp]),

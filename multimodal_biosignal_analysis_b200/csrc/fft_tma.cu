@@ -16,6 +16,7 @@
 #include <utility>
 #include "tc_common.cuh"
 #include "csd_layout.cuh"
+#include "tile_counter.cuh"
 #include <stdlib.h>
 
 namespace cmc {
@@ -417,16 +418,12 @@ struct PipeCtrlT {
 // (device, stream) - launches of one stream are ordered - and every launch recorded during stream capture gets a
 // fresh slot of its own (parallel graph branches, graphs replayed beside eager work); when a pool runs out the
 // launch uses the fixed tile stride instead (tile_counter_for).
-struct TileCounter {
-    unsigned next;           // tiles claimed so far beyond the initial (workers per CTA) * gridDim.x ones
-    unsigned done;           // workers that have left the kernel
-};
 constexpr int kTileCounterEagerSlots = 64;       // distinct (device, stream) pairs with a claim counter
 constexpr int kTileCounterCaptureSlots = 960;   // kernel nodes recorded into CUDA graphs
 __device__ TileCounter g_tile_counters[kTileCounterEagerSlots + kTileCounterCaptureSlots];
 
 // Host side of the rule above.  Returns nullptr (= fixed stride) when no private counter is available.
-static TileCounter* tile_counter_for(int dev, cudaStream_t st) {
+TileCounter* tile_counter_for(int dev, cudaStream_t st) {
     static std::mutex mu;
     static std::map<std::pair<int, cudaStream_t>, int> eager;      // (device, stream) -> slot
     static std::map<int, int> n_eager, n_capture;                  // per device

@@ -98,6 +98,67 @@ def fft_segments_pair(x1: torch.Tensor, x2: torch.Tensor, seg_starts: torch.Tens
     _lib.check(rc, "cmc_fft_segments_pair")
 
 
+class WelchHannPlan:
+    """Half-block plan of the tensor-core Welch kernel (``cmc_welch_hann_*``): periodic hann window, one window row,
+    band of at most 102 bins.  Built from the HOST segment table; ``spectra`` enqueues on the current stream."""
+
+    def __init__(self, seg_starts_host, N: int, bin_lo: int, bin_hi: int):
+        import ctypes as C
+        import numpy as np
+        starts = np.ascontiguousarray(np.asarray(seg_starts_host, dtype=np.int64))
+        handle = C.c_void_p()
+        lib = _lib.load()
+        rc = lib.cmc_welch_hann_plan_create(starts.ctypes.data, int(starts.size), int(N), int(bin_lo), int(bin_hi),
+                                            C.byref(handle))
+        _lib.check(rc, "cmc_welch_hann_plan_create")
+        self._handle, self._lib = handle, lib
+        self.N, self.bin_lo, self.bin_hi, self.n_seg = int(N), int(bin_lo), int(bin_hi), int(starts.size)
+        self.device = torch.cuda.current_device()
+        nh = C.c_int()
+        lib.cmc_welch_hann_plan_info(handle, C.byref(nh), None, None)
+        self.n_half_blocks = int(nh.value)
+
+    @staticmethod
+    def supports(N: int, bin_lo: int, bin_hi: int) -> bool:
+        b0 = max(bin_lo - 1, 0)
+        return (N % 128 == 0 and 256 <= N <= 16384 and bin_hi + 1 - b0 <= 103 and b0 + 104 <= N // 2
+                and 0 <= bin_lo <= bin_hi)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                self._lib.cmc_welch_hann_plan_destroy(h)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self._handle = None
+
+    def spectra(self, x1: torch.Tensor, out1: torch.Tensor, x2: torch.Tensor | None = None,
+                out2: torch.Tensor | None = None, detrend: int = DETREND_CONSTANT) -> None:
+        """Spectra of the plan's segments for one recording or for two of equal length (EEG, EMG): ``out*`` are
+        complex64 (n_seg, 1, F, C_i) or (n_seg, F, C_i) tensors / channel-range views that share the row pitch."""
+        F = self.bin_hi - self.bin_lo + 1
+        pairs = [(x1, out1, "1")] + ([(x2, out2, "2")] if x2 is not None else [])
+        for x, o, name in pairs:
+            _need_cuda(x, "x" + name, torch.float32)
+            _need_cuda(o, "out" + name, torch.complex64)
+            if x.dim() != 2 or x.stride(1) != 1:
+                raise ValueError(f"x{name} must be (n_samples, n_ch) with contiguous channels")
+            if o.dim() == 4:
+                if o.shape[1] != 1:
+                    raise ValueError("the tensor-core Welch kernel takes one window row")
+                o = o[:, 0]
+            if o.shape != (self.n_seg, F, x.shape[1]) or o.stride(2) != 1 or o.stride(0) != F * o.stride(1):
+                raise ValueError(f"out{name} must be (n_seg, F, n_ch) with unit channel stride and dense leading axes")
+        if x2 is not None and (x1.shape[0] != x2.shape[0] or out1.stride(-2) != out2.stride(-2)):
+            raise ValueError("both recordings need the same length and both outputs the same row pitch")
+        rc = self._lib.cmc_welch_hann_spectra(self._handle, x1.data_ptr(), x1.shape[1], x1.stride(0), out1.data_ptr(),
+                                              _lib.ptr(x2), 0 if x2 is None else x2.shape[1],
+                                              0 if x2 is None else x2.stride(0), _lib.ptr(out2), x1.shape[0],
+                                              int(detrend), out1.stride(-2), _lib.current_stream())
+        _lib.check(rc, "cmc_welch_hann_spectra")
+
+
 def psd_from_spectra(spec: torch.Tensor, base_scale: float, one_sided: bool, bin_lo: int, N: int,
                      log_scale: bool) -> torch.Tensor:
     """(W, K, F, C) complex64 spectra -> (W, F, C) float32 power spectra (mean over axis 1)."""

@@ -16,4 +16,6 @@ $NCU --set full --clock-control none --import-source on --launch-skip "$half" -o
     python scripts/profile_driver.py > "$out/r02_ncu_full.log" 2>&1
 $NCU -i "$out/prof_r2_all.ncu-rep" --page raw --csv > "$out/r02_ncu_full_raw.csv" 2>/dev/null
 $NCU -i "$out/prof_r2_all.ncu-rep" --page details --csv > "$out/r02_ncu_full_details.csv" 2>/dev/null
+# the report itself (~150 MB) exceeds what gpurun copies back: keep the CSV exports only
+rm -f "$out/prof_r2_all.ncu-rep"
 echo "launches: $n (profiled the last $((n - half)))"
