@@ -40,20 +40,19 @@ N_PERM_TOTAL = 10000         # config 5 permutation count (sharded over ranks)
 CBPA_SHAPE = (20, 100, 64)   # config 4
 
 
-def _k1_traffic():
+def _k1_traffic(kind="tc"):
     """dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed `ncu --set full` export
-    (profiled offline, NOT measured in this run; null when the file is absent)."""
+    (profiled offline, NOT measured in this run; null when the file is absent).  kind: "tc" | "fft"."""
     path = os.path.join(ROOT, "profiles", "k1_dram_traffic.json")
     try:
         with open(path) as fh:
-            d = json.load(fh)
+            d = json.load(fh)[kind]
         return {"bytes": float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]),
                 "source": f"profiled offline: profiles/k1_dram_traffic.json ({d.get('source', '')})"}
     except Exception:
         return {"bytes": None, "source": "no ncu export committed"}
 
 
-K1_TRAFFIC_PROFILED = _k1_traffic()
 
 
 def peaks():
@@ -360,10 +359,24 @@ def main_gpu(args):
         dev_sets.append((torch.from_numpy(eeg).to(dev), torch.from_numpy(emg).to(dev)))
     specs = [torch.empty((L, 1, F, NE + NM), dtype=torch.complex64, device=dev) for _ in range(N_ROTATE)]
 
+    # K1: hann / 50 % overlap / narrow band = the tensor-core half-block kernel (cmc_welch_hann_spectra); --k1 fft
+    # times the FFT kernel (cmc_fft_segments_pair) instead.  The plan is built once, outside every timed region.
+    k1_plan = None if args.k1 == "fft" else K.hann_plan_for(starts_h, NPERSEG, lo, hi)
+    K1_TRAFFIC_PROFILED = _k1_traffic("tc" if k1_plan is not None else "fft")
+    k1_name = ("dft_hann_tc_kernel (K1t, tcgen05 BF16x3 half-block DFT, ONE launch for the EEG and the EMG array)"
+               if k1_plan is not None else
+               "fft_segments_tma_pipe_kernel<1024> (K1, ONE launch for the EEG and the EMG array)")
+
+    def k1(eeg_d, emg_d, spec):
+        if k1_plan is not None:
+            k1_plan.spectra(eeg_d, spec[..., :NE], emg_d, spec[..., NE:], detrend=K.DETREND_CONSTANT)
+        else:
+            K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, spec[..., :NE], spec[..., NE:])
+
     def step(i):
         eeg_d, emg_d = dev_sets[i % N_ROTATE]
         spec = specs[i % N_ROTATE]
-        K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, spec[..., :NE], spec[..., NE:])
+        k1(eeg_d, emg_d, spec)
         return K.csd_msc(spec[:, 0, :, :NE], spec[:, 0, :, NE:])
 
     for i in range(warmup):
@@ -384,7 +397,7 @@ def main_gpu(args):
         with torch.cuda.graph(gA):
             # ONE K1 launch transforms both modalities (tiles of the EEG and of the EMG array share the persistent CTAs
             # and the claim counter: one prologue and one tail instead of two)
-            K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, spec[..., :NE], spec[..., NE:])
+            k1(eeg_d, emg_d, spec)
         with torch.cuda.graph(gB):
             res_r = K.csd_msc(spec[:, 0, :, :NE], spec[:, 0, :, NE:])
         launches_per_step = _lib.launch_count() - n0
@@ -450,8 +463,7 @@ def main_gpu(args):
         eeg_d, emg_d = dev_sets[r]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, lo, hi, specs[r][..., :NE],
-                                specs[r][..., NE:])
+            k1(eeg_d, emg_d, specs[r])
         serial_graphs.append(g)
     n_serial = min(steps, 128)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_serial)]
@@ -804,7 +816,7 @@ def main_gpu(args):
             "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT), tf32x3 -> f32 accumulate (CSD)",
             "data": "synthetic", "config": workload_config(),
-            "roofline": {"bound": "hbm", "kernel": "fft_segments_tma_pipe_kernel<1024> (K1, ONE launch for the EEG and the EMG array)",
+            "roofline": {"bound": "hbm", "kernel": k1_name,
                          "achieved": k1_gbs, "peak": hbm, "unit": "GB/s", "frac": k1_gbs / hbm,
                          # dram__bytes_read + dram__bytes_write of one K1 launch, ncu --set full (profiles/r01b_k1_tma.md,
                          # addendum 8: 63.0 MB read + 4.0 MB written inside the window, the rest of the output still in L2)
@@ -835,6 +847,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--k1", default="tc", choices=["tc", "fft"],
+                    help="K1 of the headline step: tensor-core half-block DFT (default) or the FFT kernel")
     ap.add_argument("--skip-stages", action="store_true",
                     help="headline metric only (profiling runs): no surrogate / CBPA / sweep stages")
     args = ap.parse_args()

@@ -38,6 +38,8 @@
 
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <math.h>
+#include <stdlib.h>
 #include <numeric>
 #include <vector>
 
@@ -47,20 +49,26 @@ using namespace tc;
 
 constexpr int kDtThreads = 512;
 constexpr int kDtConvThreads = 256;                          // warps 8-15
-constexpr int kDtStages = 2;
-constexpr int kDtKB = 64;                                    // samples per k-block (128 bytes of BF16)
+constexpr int kDtStagesA = 3;                                // raw tile / A operand ring
+constexpr int kDtStagesB = 2;                                // W k-block ring
+constexpr int kDtKB = 64;                                    // samples per k-block: 128-byte BF16 rows (SWIZZLE_128B).  32 (64-byte rows,
+                                                             // SWIZZLE_64B, rings of 5 + 4) is also implemented and measured: same speed
+constexpr int kDtRowB = kDtKB * 2;                           // bytes per operand row of a k-block
+constexpr int kDtSpt = kDtKB / 2;                            // samples per converter thread and k-block
 constexpr int kDtM = 128;                                    // channels per unit (two 64-channel groups)
 constexpr int kDtBins = 104;                                 // accumulator bins
 constexpr int kDtCols = 2 * kDtBins;                         // 208 accumulator columns (re, im interleaved)
 constexpr int kDtPlaneA = kDtM * kDtKB * 2;                  // 16 KB: one BF16 plane of the A k-block
 constexpr int kDtABytes = 2 * kDtPlaneA;                     // 32 KB = the raw FP32 tile [64][128]
-constexpr int kDtPlaneB = kDtCols * kDtKB * 2;               // 26 KB: one BF16 plane of the W k-block
-constexpr int kDtStageBytes = kDtABytes + 2 * kDtPlaneB;     // 84 KB
+constexpr int kDtPlaneB = kDtCols * kDtKB * 2;               // one BF16 plane of the W k-block
+constexpr int kDtBBytes = 2 * kDtPlaneB;                     // 52 KB
 constexpr int kDtChainCap = 32;                              // segments per chain (bounds the drift y = x - c sees)
+constexpr int kDtPrefetch = 4;                               // k-blocks the L2 prefetch of the raw tiles runs ahead
+constexpr int kDtSlots = 4;                                  // units whose per-channel offsets are alive at once
 
 struct DtItem {           // one half block
     int x_row;            // first sample
-    int c_row;            // sample whose value is subtracted before the BF16 split (first sample of the chain)
+    int c_row;            // sample whose value is subtracted first (first sample of the chain: exact for b != 0)
     int seg_a;            // segment whose FIRST half this is, or -1
     int seg_b;            // segment whose SECOND half this is, or -1
     int phase;            // 0: emissions are stores, 1: emissions are adds
@@ -69,6 +77,7 @@ struct DtItem {           // one half block
 
 struct DtParams {
     const DtItem* items;
+    const float* e1im;             // [104] Im of E1[b] = sum_{n < N/2} exp(-2 pi i b n / N) for odd b (Re = 1), 0 for even b
     int n_items, n_gp;             // half blocks, channel-group pairs per half block (units = n_items * n_gp)
     int n_store_units;             // units with phase 0 (they come first)
     int KB, N, bin_lo, F, b0, detrend;
@@ -79,17 +88,43 @@ struct DtParams {
     float2* spec[2];
     long long spec_ld;
     TileCounter* ctr;
+    int pf;                        // k-blocks the L2 prefetch of the raw tiles runs ahead (0 = off)
+    int dbg;                       // developer switches (CMC_DT_DBG): 1 no conversion, 2 no MMAs, 4 no emissions, 8 no W loads after the first two
 };
 
 struct __align__(8) DtBarriers {
-    uint64_t full[kDtStages];
-    uint64_t conv[kDtStages];
-    uint64_t empty[kDtStages];
+    uint64_t full_a[kDtStagesA];
+    uint64_t conv[kDtStagesA];
+    uint64_t empty_a[kDtStagesA];
+    uint64_t full_b[kDtStagesB];
+    uint64_t empty_b[kDtStagesB];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
 };
+
+// UMMA shared-memory descriptor of a K-major BF16 operand k-block: rows of kDtRowB bytes, 8-row swizzle atoms
+__device__ __forceinline__ uint64_t dt_desc(uint32_t smem_addr) {
+    if (kDtKB == 64) return make_smem_desc_k_sw128(smem_addr);
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);          // start address  [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                             // leading byte offset (ignored)
+    d |= static_cast<uint64_t>(512 >> 4) << 32;                      // stride byte offset: 8 rows x 64 bytes
+    d |= static_cast<uint64_t>(1) << 46;                             // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(4) << 61;                             // SWIZZLE_64B
+    return d;
+}
+
+// developer trace (CMC_DT_DBG & 32): globaltimer stamps of CTA 0, read back with cmc_dbg_dt_trace
+__device__ unsigned long long g_dt_trace[64];
+__device__ __forceinline__ void dt_stamp(const DtParams& p, int slot) {
+    if ((p.dbg & 32) && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_dt_trace[slot] = t;
+    }
+}
 
 __device__ __forceinline__ float dt_lds32(uint32_t a) {
     float v;
@@ -110,6 +145,11 @@ __device__ __forceinline__ void dt_emit(float2* o, float re, float im, int add) 
     else
         asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(re), "f"(im) : "memory");
 }
+__device__ __forceinline__ void dt_prefetch_l2(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
 // BF16 hi / lo split of two values: hi = rn(v), lo = rn(v - hi); element 0 in the low half-word
 __device__ __forceinline__ void dt_split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
@@ -126,20 +166,116 @@ __device__ __forceinline__ void dt_group(const DtParams& p, int g, int& rec, int
     else { rec = 0; c0 = p.n_grp0 * 64; }
 }
 
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void dt_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// tcgen05.wait::ld that the compiler cannot move uses of `r` across (the registers are operands of the wait)
+__device__ __forceinline__ void dt_tmem_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+// P[j] += ch * E1[b0 + j] for the 8 bins of accumulator chunk cq; e1s[j] = (1, Im E1) for odd bins, (0, 0) for even
+__device__ __forceinline__ void dt_fixup(uint32_t (&v)[16], int cq, float ch, const float2* e1s) {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const float2 e = e1s[8 * cq + jj];
+        v[2 * jj] = __float_as_uint(fmaf(ch, e.x, __uint_as_float(v[2 * jj])));
+        v[2 * jj + 1] = __float_as_uint(fmaf(ch, e.y, __uint_as_float(v[2 * jj + 1])));
+    }
+}
+
+// Three-tap hann over the 104 accumulator bins of one TMEM lane and the two emissions of the half block: a rolled
+// loop over 8-bin chunks (the fully unrolled form was 100 KB of straight-line code and ran at instruction-fetch
+// speed: 15 - 25 us per unit).  oA / oB point at output bin j = 0 of the two target segments (or are null).
+template <bool ADD>
+__device__ __forceinline__ void dt_epilogue_bins(uint32_t taddr, float chh, const float2* e1s, int j_lo, int j_hi,
+                                                 float dc_add, bool dc_is_bin0, bool dc_zero_all, bool post_taper,
+                                                 float sgn_even, float2* oA, float2* oB, long long ld, bool no_emit) {
+    uint32_t cur[16], nxt[16];
+    dt_tmem_ld16(taddr, cur);
+    dt_tmem_wait16(cur);
+    dt_fixup(cur, 0, chh, e1s);
+    float pm_re = 0.f, pm_im = 0.f;              // P[j - 1] of the first bin of the chunk
+    if (dc_is_bin0) {                            // accumulator bin 0 is the DC bin
+        cur[0] = dc_zero_all ? 0u : __float_as_uint(__uint_as_float(cur[0]) + dc_add);
+        cur[1] = 0u;
+        pm_re = __uint_as_float(cur[2]);         // P[-1] = conj(P[1])
+        pm_im = -__uint_as_float(cur[3]);
+    }
+    constexpr int kChunks = kDtBins / 8;         // 13
+    auto bin = [&](int cq, int jj) {
+        const int j = 8 * cq + jj;
+        const float pc_re = __uint_as_float(cur[2 * jj]), pc_im = __uint_as_float(cur[2 * jj + 1]);
+        const float pp_re = __uint_as_float(jj < 7 ? cur[2 * jj + 2] : nxt[0]);
+        const float pp_im = __uint_as_float(jj < 7 ? cur[2 * jj + 3] : nxt[1]);
+        const float qm_re = jj > 0 ? __uint_as_float(cur[2 * jj - 2]) : pm_re;
+        const float qm_im = jj > 0 ? __uint_as_float(cur[2 * jj - 1]) : pm_im;
+        const float s_re = 0.25f * (qm_re + pp_re), s_im = 0.25f * (qm_im + pp_im);
+        float a_re = fmaf(0.5f, pc_re, -s_re), a_im = fmaf(0.5f, pc_im, -s_im);
+        const float sg = (jj & 1) ? -sgn_even : sgn_even;                 // (-1)^b of the second-half emission
+        float b_re = sg * fmaf(0.5f, pc_re, s_re), b_im = sg * fmaf(0.5f, pc_im, s_im);
+        if (jj == 0 && cq == 0 && dc_is_bin0 && post_taper) a_re = b_re = 0.f;   // periodogram: DC bin zeroed
+        if (j >= j_lo && j < j_hi && !no_emit) {
+            if (oA) dt_emit(oA, a_re, a_im, ADD);
+            if (oB) dt_emit(oB, b_re, b_im, ADD);
+        }
+        if (oA) oA += ld;
+        if (oB) oB += ld;
+    };
+#pragma unroll 1
+    for (int cq = 0; cq < kChunks; ++cq) {
+        // the load of the next chunk is in flight while bins 0 - 6 of this one are emitted
+        if (cq < kChunks - 1) dt_tmem_ld16(taddr + 16 * (cq + 1), nxt);
+#pragma unroll
+        for (int jj = 0; jj < 7; ++jj) bin(cq, jj);
+        if (cq < kChunks - 1) {
+            dt_tmem_wait16(nxt);
+            dt_fixup(nxt, cq + 1, chh, e1s);
+        }
+        bin(cq, 7);
+        pm_re = __uint_as_float(cur[14]);
+        pm_im = __uint_as_float(cur[15]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+    }
+}
+
 __global__ void __launch_bounds__(kDtThreads, 1)
 dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant__ CUtensorMap mX1,
                    const __grid_constant__ CUtensorMap mW, const DtParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    DtBarriers* bars = reinterpret_cast<DtBarriers*>(base + kDtStages * kDtStageBytes);
+    unsigned char* sA = base;                                        // [kDtStagesA][32 KB]
+    unsigned char* sB = base + kDtStagesA * kDtABytes;               // [kDtStagesB][52 KB]
+    float* csum = reinterpret_cast<float*>(sB + kDtStagesB * kDtBBytes);   // [2][128] partial sums of the first k-block
+    float* coff = csum + 2 * kDtM;                                   // [kDtSlots][128] per-unit channel offsets c_h
+    float2* e1s = reinterpret_cast<float2*>(coff + kDtSlots * kDtM); // [112] E1 of the accumulator bins (odd bins only)
+    DtBarriers* bars = reinterpret_cast<DtBarriers*>(e1s + 112);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = p.n_items * p.n_gp;
+    if (threadIdx.x == 0) dt_stamp(p, 0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kDtStages; ++s) {
-            mbar_init(&bars->full[s], 1);
+        for (int s = 0; s < kDtStagesA; ++s) {
+            mbar_init(&bars->full_a[s], 1);
             mbar_init(&bars->conv[s], kDtConvThreads);
-            mbar_init(&bars->empty[s], 1);
+            mbar_init(&bars->empty_a[s], 1);
+        }
+        for (int s = 0; s < kDtStagesB; ++s) {
+            mbar_init(&bars->full_b[s], 1);
+            mbar_init(&bars->empty_b[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tmem_full[a], 1);
@@ -154,32 +290,57 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + 112) {
+        const int j = threadIdx.x - 128;
+        const bool odd = j < kDtBins && ((p.b0 + j) & 1);
+        e1s[j] = odd ? make_float2(1.0f, __ldg(p.e1im + j)) : make_float2(0.f, 0.f);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    if (threadIdx.x == 0) dt_stamp(p, 1);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (raw tiles and W k-blocks on separate rings) =====================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const DtItem it = p.items[u / p.n_gp];
                 const int gp = u % p.n_gp;
                 int ra, ca, rb, cb;
                 dt_group(p, 2 * gp, ra, ca);
                 dt_group(p, 2 * gp + 1, rb, cb);
+                const CUtensorMap* ma = ra ? &mX1 : &mX0;
+                const CUtensorMap* mb = rb ? &mX1 : &mX0;
+                for (int kb = 0; kb < p.pf && kb < p.KB; ++kb) {      // raw tiles come from HBM: warm L2 ahead
+                    dt_prefetch_l2(ma, ca, it.x_row + kb * kDtKB);
+                    dt_prefetch_l2(mb, cb, it.x_row + kb * kDtKB);
+                }
                 for (int kb = 0; kb < p.KB; ++kb) {
-                    mbar_wait(&bars->empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&bars->full[stage], kDtStageBytes);
-                    unsigned char* st = base + stage * kDtStageBytes;
                     const int row = it.x_row + kb * kDtKB;
-                    tma_load_2d(st, ra ? &mX1 : &mX0, &bars->full[stage], ca, row);
-                    tma_load_2d(st + kDtPlaneA, rb ? &mX1 : &mX0, &bars->full[stage], cb, row);
-                    tma_load_2d(st + kDtABytes, &mW, &bars->full[stage], kb * kDtKB, 0);
-                    tma_load_2d(st + kDtABytes + kDtPlaneB, &mW, &bars->full[stage], kb * kDtKB, kDtCols);
-                    if (++stage == kDtStages) { stage = 0; phase ^= 1; }
+                    if (p.pf && kb + p.pf < p.KB) {
+                        dt_prefetch_l2(ma, ca, row + p.pf * kDtKB);
+                        dt_prefetch_l2(mb, cb, row + p.pf * kDtKB);
+                    }
+                    mbar_wait(&bars->empty_a[sa], pa ^ 1);
+                    if (u == (int)blockIdx.x && kb < 16) dt_stamp(p, 2 + kb);
+                    mbar_arrive_expect_tx(&bars->full_a[sa], kDtABytes);
+                    unsigned char* st = sA + sa * kDtABytes;
+                    tma_load_2d(st, ma, &bars->full_a[sa], ca, row);
+                    tma_load_2d(st + kDtPlaneA, mb, &bars->full_a[sa], cb, row);
+                    if (++sa == kDtStagesA) { sa = 0; pa ^= 1; }
+                    mbar_wait(&bars->empty_b[sb], pb ^ 1);
+                    if ((p.dbg & 8) && (u != (int)blockIdx.x || kb >= kDtStagesB)) {
+                        mbar_arrive(&bars->full_b[sb]);            // timing experiment: stale W, no load
+                    } else {
+                        mbar_arrive_expect_tx(&bars->full_b[sb], kDtBBytes);
+                        unsigned char* sw = sB + sb * kDtBBytes;
+                        tma_load_2d(sw, &mW, &bars->full_b[sb], kb * kDtKB, 0);
+                        tma_load_2d(sw + kDtPlaneB, &mW, &bars->full_b[sb], kb * kDtKB, kDtCols);
+                    }
+                    if (++sb == kDtStagesB) { sb = 0; pb ^= 1; }
                 }
             }
         }
@@ -187,41 +348,45 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
         // ===================== MMA issuer (single thread) =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(kDtM, kDtCols);
-            int stage = 0;
-            uint32_t phase = 0, n = 0;
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0, n = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
                 mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * 256;
                 for (int kb = 0; kb < p.KB; ++kb) {
-                    mbar_wait(&bars->full[stage], phase);          // W planes (async proxy) have landed
-                    mbar_wait(&bars->conv[stage], phase);          // A planes written by the converters
+                    mbar_wait(&bars->full_b[sb], pb);              // W planes (async proxy) have landed
+                    mbar_wait(&bars->conv[sa], pa);                // A planes written by the converters
+                    if (u == (int)blockIdx.x && kb < 16) dt_stamp(p, 18 + kb);
                     tc_fence_after();
-                    const uint32_t ahi = smem_u32(base + stage * kDtStageBytes), alo = ahi + kDtPlaneA;
-                    const uint32_t bhi = ahi + kDtABytes, blo = bhi + kDtPlaneB;
+                    const uint32_t ahi = smem_u32(sA + sa * kDtABytes), alo = ahi + kDtPlaneA;
+                    const uint32_t bhi = smem_u32(sB + sb * kDtBBytes), blo = bhi + kDtPlaneB;
 #pragma unroll
                     for (int k = 0; k < kDtKB / 16; ++k) {
-                        const uint64_t dah = make_smem_desc_k_sw128(ahi + k * 32), dal = make_smem_desc_k_sw128(alo + k * 32);
-                        const uint64_t dbh = make_smem_desc_k_sw128(bhi + k * 32), dbl = make_smem_desc_k_sw128(blo + k * 32);
+                        if (p.dbg & 2) break;
+                        const uint64_t dah = dt_desc(ahi + k * 32), dal = dt_desc(alo + k * 32);
+                        const uint64_t dbh = dt_desc(bhi + k * 32), dbl = dt_desc(blo + k * 32);
                         umma_f16(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);      // small terms first
                         umma_f16(d, dah, dbl, idesc, 1u);
                         umma_f16(d, dah, dbh, idesc, 1u);
                     }
-                    umma_commit(&bars->empty[stage]);
-                    if (++stage == kDtStages) { stage = 0; phase ^= 1; }
+                    umma_commit(&bars->empty_a[sa]);
+                    umma_commit(&bars->empty_b[sb]);
+                    if (++sa == kDtStagesA) { sa = 0; pa ^= 1; }
+                    if (++sb == kDtStagesB) { sb = 0; pb ^= 1; }
                 }
                 umma_commit(&bars->tmem_full[acc]);
                 ++n;
             }
         }
     } else if (warp >= 8) {
-        // ===================== converters: y = x - c, BF16 hi / lo planes in place =====================
+        // ===================== converters: y = x - c0 - c_h, BF16 hi / lo planes in place =====================
         const int t = threadIdx.x - 256;
         const int m = t & 127;                   // A row = channel of the unit
         const int g = t >> 7;                    // samples 32 g .. 32 g + 31 of the k-block
-        int stage = 0;
-        uint32_t phase = 0;
+        int sa = 0;
+        uint32_t pa = 0, n = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const DtItem it = p.items[u / p.n_gp];
             const int gp = u % p.n_gp;
@@ -230,31 +395,57 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
             const int ch = c0 + (m & 63);
             const float* xr = rec ? p.x[1] : p.x[0];
             const long long ldr = rec ? p.ld[1] : p.ld[0];
-            const float c = ch < (rec ? p.n_ch[1] : p.n_ch[0]) ? __ldg(xr + (long long)it.c_row * ldr + ch) : 0.f;
+            // c0: first sample of the chain (the same for both halves of every segment, so it drops out of every bin
+            // but DC).  c_h: mean of the half block's first 64 samples of x - c0, added back in the epilogue; it keeps
+            // the 1 / b leakage of a half-block mean out of the accumulators.
+            float c = ch < (rec ? p.n_ch[1] : p.n_ch[0]) ? __ldg(xr + (long long)it.c_row * ldr + ch) : 0.f;
             for (int kb = 0; kb < p.KB; ++kb) {
-                mbar_wait(&bars->full[stage], phase);
-                const uint32_t sb = smem_u32(base + stage * kDtStageBytes);
-                const uint32_t src = sb + (uint32_t)((m >> 6) * kDtPlaneA + (m & 63) * 4 + g * 32 * 256);
-                float v[32];
+                mbar_wait(&bars->full_a[sa], pa);
+                if (t == 0 && u == (int)blockIdx.x && kb < 16) dt_stamp(p, 34 + kb);
+                if (p.dbg & 1) {
+                    mbar_arrive(&bars->conv[sa]);
+                    if (++sa == kDtStagesA) { sa = 0; pa ^= 1; }
+                    continue;
+                }
+                const uint32_t sbase = smem_u32(sA + sa * kDtABytes);
+                const uint32_t src = sbase + (uint32_t)((m >> 6) * kDtPlaneA + (m & 63) * 4 + g * kDtSpt * 256);
+                float v[kDtSpt];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = dt_lds32(src + i * 256) - c;
+                for (int i = 0; i < kDtSpt; ++i) v[i] = dt_lds32(src + i * 256) - c;
+                if (kb == 0) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kDtSpt; ++i) s += v[i];
+                    csum[g * kDtM + m] = s;
+                }
                 asm volatile("bar.sync 2, 256;" ::: "memory");       // every raw value is in a register
-                const uint32_t row = sb + (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+                if (kb == 0) {
+                    const float chh = (csum[m] + csum[kDtM + m]) * (1.0f / kDtKB);
+                    if (g == 0) coff[(n & (kDtSlots - 1)) * kDtM + m] = chh;
+                    c += chh;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                    for (int i = 0; i < kDtSpt; ++i) v[i] -= chh;
+                }
+                // K-major row of channel m: 8-row atoms; 16-byte chunk index XOR (row & 7) for 128-byte rows
+                // (SWIZZLE_128B), XOR ((row >> 1) & 3) for 64-byte rows (SWIZZLE_64B)
+                const uint32_t row = sbase + (uint32_t)((m >> 3) * (8 * kDtRowB) + (m & 7) * kDtRowB);
+                const int sw = kDtKB == 64 ? (m & 7) : ((m >> 1) & 3);
+#pragma unroll
+                for (int q = 0; q < kDtSpt / 8; ++q) {
                     uint4 hi, lo;
                     dt_split2(v[8 * q], v[8 * q + 1], hi.x, lo.x);
                     dt_split2(v[8 * q + 2], v[8 * q + 3], hi.y, lo.y);
                     dt_split2(v[8 * q + 4], v[8 * q + 5], hi.z, lo.z);
                     dt_split2(v[8 * q + 6], v[8 * q + 7], hi.w, lo.w);
-                    const uint32_t off = (uint32_t)(((4 * g + q) ^ (m & 7)) << 4);     // 128-byte swizzle
+                    const uint32_t off = (uint32_t)((((kDtSpt / 8) * g + q) ^ sw) << 4);
                     dt_sts128(row + off, hi);
                     dt_sts128(row + kDtPlaneA + off, lo);
                 }
                 fence_proxy_async();             // generic-proxy writes -> visible to the MMA's async-proxy reads
-                mbar_arrive(&bars->conv[stage]);
-                if (++stage == kDtStages) { stage = 0; phase ^= 1; }
+                mbar_arrive(&bars->conv[sa]);
+                if (++sa == kDtStagesA) { sa = 0; pa ^= 1; }
             }
+            ++n;
         }
     } else if (warp >= 4) {
         // ===================== epilogue: three-tap hann, two emissions per half block =====================
@@ -272,12 +463,14 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
             float2* sp = rec ? p.spec[1] : p.spec[0];
             float2* outA = (valid && it.seg_a >= 0) ? sp + (long long)it.seg_a * p.F * p.spec_ld + ch : nullptr;
             float2* outB = (valid && it.seg_b >= 0) ? sp + (long long)it.seg_b * p.F * p.spec_ld + ch : nullptr;
-            float dc_fix = 0.f;                  // (N / 2) c: what y = x - c removed from P[0]
+            float c_first = 0.f;                 // c0 of this channel (only the DC bin of the non-detrended modes needs it)
             if (p.b0 == 0 && p.detrend != CMC_DETREND_CONSTANT && valid)
-                dc_fix = 0.5f * (float)p.N * __ldg((rec ? p.x[1] : p.x[0]) + (long long)it.c_row * (rec ? p.ld[1] : p.ld[0]) + ch);
+                c_first = __ldg((rec ? p.x[1] : p.x[0]) + (long long)it.c_row * (rec ? p.ld[1] : p.ld[0]) + ch);
             const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
             mbar_wait(&bars->tmem_full[acc], accphase);
+            if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 50);
             tc_fence_after();
+            const float chh = coff[(n & (kDtSlots - 1)) * kDtM + m];
             if (it.phase) {
                 // adds may only start once every store of the launch is visible
                 if (lane == 0) {
@@ -293,56 +486,23 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
                 __syncwarp();
             }
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
-            uint32_t cur[32], nxt[32];
-            tmem_ld_32x32(taddr, cur);
-            tmem_ld_wait();
-            if (p.b0 == 0) {                     // accumulator bin 0 is the DC bin
-                if (p.detrend == CMC_DETREND_CONSTANT) cur[0] = 0u;      // segment mean removed: R[0] = 0
-                else cur[0] = __float_as_uint(__uint_as_float(cur[0]) + dc_fix);
-                cur[1] = 0u;
-            }
-            float pm_re = 0.f, pm_im = 0.f;      // P[j - 1] of the first bin of the chunk
-#pragma unroll
-            for (int cq = 0; cq < 7; ++cq) {
-                if (cq < 6) {
-                    tmem_ld_32x32(taddr + 32 * (cq + 1), nxt);
-                    tmem_ld_wait();
-                }
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    const int j = 16 * cq + jj;
-                    if (j >= kDtBins - 1) break;                           // bin 103 has no right neighbour
-                    const int b = p.b0 + j;
-                    const float pc_re = __uint_as_float(cur[2 * jj]), pc_im = __uint_as_float(cur[2 * jj + 1]);
-                    const float pp_re = __uint_as_float(jj < 15 ? cur[2 * jj + 2] : nxt[0]);
-                    const float pp_im = __uint_as_float(jj < 15 ? cur[2 * jj + 3] : nxt[1]);
-                    float qm_re = jj > 0 ? __uint_as_float(cur[2 * jj - 2]) : pm_re;
-                    float qm_im = jj > 0 ? __uint_as_float(cur[2 * jj - 1]) : pm_im;
-                    if (j == 0 && p.b0 == 0) { qm_re = pp_re; qm_im = -pp_im; }   // P[-1] = conj(P[1])
-                    if (b >= p.bin_lo && b < p.bin_lo + p.F) {
-                        const float s_re = 0.25f * (qm_re + pp_re), s_im = 0.25f * (qm_im + pp_im);
-                        float a_re = 0.5f * pc_re - s_re, a_im = 0.5f * pc_im - s_im;
-                        float b_re = 0.5f * pc_re + s_re, b_im = 0.5f * pc_im + s_im;
-                        if (b & 1) { b_re = -b_re; b_im = -b_im; }
-                        if (b == 0) {
-                            a_im = b_im = 0.f;
-                            if (p.detrend == CMC_DETREND_POST_TAPER) a_re = b_re = 0.f;
-                        }
-                        const long long o = (long long)(b - p.bin_lo) * p.spec_ld;
-                        if (outA) dt_emit(outA + o, a_re, a_im, it.phase);
-                        if (outB) dt_emit(outB + o, b_re, b_im, it.phase);
-                    }
-                }
-                pm_re = __uint_as_float(cur[30]);
-                pm_im = __uint_as_float(cur[31]);
-                if (cq < 6) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
-                }
-            }
+            const int j_lo = p.bin_lo - p.b0;
+            const long long back = (long long)j_lo * p.spec_ld;                   // oA / oB address accumulator bin 0
+            const bool dc0 = p.b0 == 0;
+            const float dc_add = 0.5f * (float)p.N * (c_first + chh);
+            const float sgn_even = (p.b0 & 1) ? -1.0f : 1.0f;
+            if (it.phase)
+                dt_epilogue_bins<true>(taddr, chh, e1s, j_lo, j_lo + p.F, dc_add, dc0, p.detrend == CMC_DETREND_CONSTANT,
+                                       p.detrend == CMC_DETREND_POST_TAPER, sgn_even, outA ? outA - back : nullptr,
+                                       outB ? outB - back : nullptr, p.spec_ld, (p.dbg & 4) != 0);
+            else
+                dt_epilogue_bins<false>(taddr, chh, e1s, j_lo, j_lo + p.F, dc_add, dc0, p.detrend == CMC_DETREND_CONSTANT,
+                                        p.detrend == CMC_DETREND_POST_TAPER, sgn_even, outA ? outA - back : nullptr,
+                                        outB ? outB - back : nullptr, p.spec_ld, (p.dbg & 4) != 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);   // accumulator may be overwritten
+            if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 51);
             if (!it.phase) {
                 __threadfence();                 // this thread's stores before the warp's arrival
                 __syncwarp();
@@ -354,6 +514,7 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (threadIdx.x == 0) dt_stamp(p, 52);
     if (threadIdx.x == 0) {
         // the last CTA to leave hands the counter back at zero (stream-ordered launches and graph replays reuse it)
         __threadfence();
@@ -385,6 +546,7 @@ struct WelchHannPlan {
     int dev, N, bin_lo, F, b0, KB, n_seg, n_items, n_store;
     long long max_row_end;
     DtItem* d_items;
+    float* d_e1im;
     __nv_bfloat16* d_W;
     CUtensorMap mW;
 };
@@ -402,6 +564,25 @@ static int make_raw_map(CUtensorMap* m, const float* x, int64_t n_samples, int n
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(recording, tensor-core DFT) failed with CUresult %d", (int)r);
+        return CMC_ECUDA;
+    }
+    return CMC_OK;
+}
+
+// W planes [2 * 208][Kw] BF16, K-major: box = one k-block (kDtKB elements) x 208 rows, swizzle = row bytes
+static int make_w_map(CUtensorMap* m, const __nv_bfloat16* W, int Kw) {
+    EncodeTiledFn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)Kw, (cuuint64_t)(2 * kDtCols)};
+    cuuint64_t strides[1] = {(cuuint64_t)Kw * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kDtKB, (cuuint32_t)kDtCols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(W), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, kDtKB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(W table) failed with CUresult %d", (int)r);
         return CMC_ECUDA;
     }
     return CMC_OK;
@@ -460,12 +641,21 @@ extern "C" int cmc_welch_hann_plan_create(const int64_t* seg_starts_host, int n_
     pl->n_items = (int)items.size();
     pl->n_store = (int)std::count_if(items.begin(), items.end(), [](const DtItem& a) { return a.phase == 0; });
     pl->max_row_end = max_end;
-    pl->d_items = nullptr; pl->d_W = nullptr;
+    pl->d_items = nullptr; pl->d_W = nullptr; pl->d_e1im = nullptr;
+    // E1[b] = sum_{n < N/2} exp(-2 pi i b n / N) = 1 - i cot(pi b / N) for odd b (0 for even b != 0)
+    std::vector<float> e1(kDtBins, 0.f);
+    for (int j = 0; j < kDtBins; ++j) {
+        const int b = b0 + j;
+        if (b & 1) e1[j] = (float)(-1.0 / tan(3.14159265358979323846 * (double)b / (double)N));
+    }
     int rc = check_cuda(cudaGetDevice(&pl->dev), "cudaGetDevice");
     const int Kw = N / 2;
     if (!rc) rc = check_cuda(cudaMalloc(&pl->d_items, items.size() * sizeof(DtItem)), "cudaMalloc(plan items)");
     if (!rc) rc = check_cuda(cudaMemcpy(pl->d_items, items.data(), items.size() * sizeof(DtItem), cudaMemcpyHostToDevice),
                              "cudaMemcpy(plan items)");
+    if (!rc) rc = check_cuda(cudaMalloc(&pl->d_e1im, kDtBins * sizeof(float)), "cudaMalloc(plan E1)");
+    if (!rc) rc = check_cuda(cudaMemcpy(pl->d_e1im, e1.data(), kDtBins * sizeof(float), cudaMemcpyHostToDevice),
+                             "cudaMemcpy(plan E1)");
     if (!rc) rc = check_cuda(cudaMalloc(&pl->d_W, (size_t)2 * kDtCols * Kw * sizeof(__nv_bfloat16)), "cudaMalloc(plan W)");
     if (!rc) {
         dft_w_table_kernel<<<dim3((Kw + 127) / 128, kDtCols), 128>>>(pl->d_W, Kw, N, b0);
@@ -473,9 +663,10 @@ extern "C" int cmc_welch_hann_plan_create(const int64_t* seg_starts_host, int n_
         rc = check_cuda(cudaGetLastError(), "dft_w_table_kernel");
     }
     if (!rc) rc = check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize(plan)");
-    if (!rc) rc = make_kmajor_map(&pl->mW, pl->d_W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Kw, 2 * kDtCols, kDtCols);
+    if (!rc) rc = make_w_map(&pl->mW, pl->d_W, Kw);
     if (rc) {
         cudaFree(pl->d_items);
+        cudaFree(pl->d_e1im);
         cudaFree(pl->d_W);
         delete pl;
         return rc;
@@ -484,10 +675,15 @@ extern "C" int cmc_welch_hann_plan_create(const int64_t* seg_starts_host, int n_
     return CMC_OK;
 }
 
+extern "C" CMC_API int cmc_dbg_dt_trace(unsigned long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, cmc::g_dt_trace, sizeof(unsigned long long) * 64);
+}
+
 extern "C" int cmc_welch_hann_plan_destroy(void* plan) {
     if (!plan) return CMC_OK;
     auto* pl = static_cast<WelchHannPlan*>(plan);
     cudaFree(pl->d_items);
+    cudaFree(pl->d_e1im);
     cudaFree(pl->d_W);
     delete pl;
     return CMC_OK;
@@ -536,6 +732,7 @@ extern "C" int cmc_welch_hann_spectra(const void* plan, const float* x1, int n_c
     else m1 = m0;
     DtParams p{};
     p.items = pl->d_items;
+    p.e1im = pl->d_e1im;
     p.n_items = pl->n_items;
     p.n_grp0 = (n_ch1 + 63) / 64;
     const int n_grp = p.n_grp0 + (n_ch2 + 63) / 64;
@@ -549,7 +746,10 @@ extern "C" int cmc_welch_hann_spectra(const void* plan, const float* x1, int n_c
     p.spec[1] = reinterpret_cast<float2*>(n_ch2 ? spec2 : spec1);
     p.spec_ld = spec_ld;
     p.ctr = ctr;
-    const size_t smem = 1024 + (size_t)kDtStages * kDtStageBytes + sizeof(DtBarriers) + 16;
+    { const char* e = getenv("CMC_DT_DBG"); p.dbg = e ? atoi(e) : 0; }
+    { const char* e = getenv("CMC_DT_PF"); p.pf = e ? atoi(e) : kDtPrefetch; }
+    const size_t smem = 1024 + (size_t)kDtStagesA * kDtABytes + (size_t)kDtStagesB * kDtBBytes +
+                        (2 + kDtSlots) * kDtM * sizeof(float) + 112 * sizeof(float2) + sizeof(DtBarriers) + 16;
     rc = ensure_smem_attr(reinterpret_cast<const void*>(dft_hann_tc_kernel), smem);
     if (rc) return rc;
     const long long n_units = (long long)p.n_items * p.n_gp;

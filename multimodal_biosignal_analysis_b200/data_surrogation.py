@@ -288,6 +288,7 @@ def surrogate_null_sweep(recordings, sampling_freq: float, nperseg: int = 256, n
         raise ValueError("circular shift surrogates need at least two segments")
     starts_d = torch.as_tensor(starts_h).to(dev)
     wd = torch.from_numpy(win).to(dev)
+    is_hann = sf._is_periodic_hann(win)
     ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)
     units = iter(unit_indices) if unit_indices is not None else None
     unit_of = {}
@@ -298,7 +299,8 @@ def surrogate_null_sweep(recordings, sampling_freq: float, nperseg: int = 256, n
         if "S" not in slot:
             slot["S"] = torch.empty((L, 1, F, ne_p + nm_p), dtype=torch.complex64, device=dev)
         sp = slot["S"]
-        K.fft_segments_pair(slot["eeg"], slot["emg"], starts_d, wd, dmode, lo, hi, sp[..., :ne], sp[..., ne_p:ne_p + nm])
+        K.welch_spectra_pair(slot["eeg"], slot["emg"], starts_h, starts_d, wd, is_hann, dmode, lo, hi, sp[..., :ne],
+                             sp[..., ne_p:ne_p + nm])
         flat = sp.view(L, F, ne_p + nm_p)
         csd = K.csd_msc(flat[:, :, :ne], flat[:, :, ne_p:ne_p + nm])
         if mode == "phase":

@@ -159,6 +159,48 @@ class WelchHannPlan:
         _lib.check(rc, "cmc_welch_hann_spectra")
 
 
+_HANN_PLANS: dict = {}
+_HANN_PLANS_MAX = 16
+
+
+def hann_plan_for(seg_starts_host, N: int, bin_lo: int, bin_hi: int) -> "WelchHannPlan | None":
+    """Cached :class:`WelchHannPlan` of a host segment table, or None when the tensor-core kernel does not take the
+    request (band too wide, N not a multiple of 128, ``CMC_WELCH_FFT=1``)."""
+    import os
+    import numpy as np
+    if os.environ.get("CMC_WELCH_FFT") or not WelchHannPlan.supports(N, bin_lo, bin_hi):
+        return None
+    starts = np.ascontiguousarray(np.asarray(seg_starts_host, dtype=np.int64))
+    if starts.size == 0:
+        return None
+    key = (torch.cuda.current_device(), int(N), int(bin_lo), int(bin_hi), starts.size, hash(starts.tobytes()))
+    plan = _HANN_PLANS.get(key)
+    if plan is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                                   # plan creation allocates and synchronises
+        if len(_HANN_PLANS) >= _HANN_PLANS_MAX:
+            _HANN_PLANS.pop(next(iter(_HANN_PLANS)))
+        plan = _HANN_PLANS[key] = WelchHannPlan(starts, N, bin_lo, bin_hi)
+    return plan
+
+
+def welch_spectra_pair(x1: torch.Tensor, x2: torch.Tensor, seg_starts_host, seg_starts: torch.Tensor,
+                       windows: torch.Tensor, window_is_hann: bool, detrend: int, bin_lo: int, bin_hi: int,
+                       out1: torch.Tensor, out2: torch.Tensor) -> str:
+    """Spectra of two recordings (EEG, EMG) for the Welch entry points.  A single periodic-hann window row over a
+    narrow band goes through the tensor-core half-block kernel (``cmc_welch_hann_spectra``), everything else through
+    the FFT kernel (``cmc_fft_segments_pair``).  Returns the name of the path taken."""
+    N = int(windows.shape[-1])
+    use_tc = (window_is_hann and windows.shape[0] == 1 and x1.shape[1] + x2.shape[1] >= 64
+              and x1.stride(0) % 4 == 0 and x2.stride(0) % 4 == 0 and x1.data_ptr() % 16 == 0 and x2.data_ptr() % 16 == 0)
+    plan = hann_plan_for(seg_starts_host, N, bin_lo, bin_hi) if use_tc else None
+    if plan is not None:
+        plan.spectra(x1, out1, x2, out2, detrend=detrend)
+        return "tensor-core"
+    fft_segments_pair(x1, x2, seg_starts, windows, detrend, bin_lo, bin_hi, out1, out2)
+    return "fft"
+
+
 def psd_from_spectra(spec: torch.Tensor, base_scale: float, one_sided: bool, bin_lo: int, N: int,
                      log_scale: bool) -> torch.Tensor:
     """(W, K, F, C) complex64 spectra -> (W, F, C) float32 power spectra (mean over axis 1)."""

@@ -642,6 +642,15 @@ class PooledCoherence:
         return self._csd.dims[0]
 
 
+def _is_periodic_hann(windows) -> bool:
+    """Whether ``windows`` is ONE row equal to scipy's default Welch window (periodic hann, float32): the case the
+    tensor-core Welch kernel computes without an FFT."""
+    w = np.atleast_2d(np.asarray(windows))
+    if w.shape[0] != 1:
+        return False
+    return bool(np.array_equal(w[0].astype(np.float32), signal.get_window("hann", w.shape[1]).astype(np.float32)))
+
+
 def pooled_coherence(eeg_array, emg_array, sampling_freq: float, segment_starts, windows,
                      detrend: int = K.DETREND_CONSTANT, freq_band: tuple[float, float] | None = None,
                      eeg_axis: Literal[0, 1] = 0, emg_axis: Literal[0, 1] = 0) -> PooledCoherence:
@@ -674,7 +683,8 @@ def pooled_coherence(eeg_array, emg_array, sampling_freq: float, segment_starts,
     ne, nm = eeg_d.shape[1], emg_d.shape[1]
     ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)
     spec = torch.empty((len(segment_starts), n_win, hi - lo + 1, ne_p + nm_p), dtype=torch.complex64, device=dev)
-    K.fft_segments_pair(eeg_d, emg_d, starts_d, wd, detrend, lo, hi, spec[..., :ne], spec[..., ne_p:ne_p + nm])
+    K.welch_spectra_pair(eeg_d, emg_d, segment_starts, starts_d, wd, _is_periodic_hann(windows), detrend, lo, hi,
+                         spec[..., :ne], spec[..., ne_p:ne_p + nm])
     flat = spec.view(-1, spec.shape[2], spec.shape[3])
     csd = K.csd_msc(flat[:, :, :ne], flat[:, :, ne_p:ne_p + nm])
     return PooledCoherence(csd, freqs[lo:hi + 1], n_win, host)
@@ -888,13 +898,15 @@ def welch_coherence_sweep(recordings, sampling_freq: float, nperseg: int = 256, 
     F, L = hi - lo + 1, len(starts_h)
     starts_d = torch.as_tensor(starts_h).to(dev)
     wd = torch.from_numpy(win).to(dev)
+    is_hann = _is_periodic_hann(win)
     ne_p, nm_p = ne + (ne & 1), nm + (nm & 1)                    # even channel pitch for K2's TMA
 
     def compute(slot, i):
         if "S" not in slot:
             slot["S"] = torch.empty((L, 1, F, ne_p + nm_p), dtype=torch.complex64, device=dev)
         sp = slot["S"]
-        K.fft_segments_pair(slot["eeg"], slot["emg"], starts_d, wd, dmode, lo, hi, sp[..., :ne], sp[..., ne_p:ne_p + nm])
+        K.welch_spectra_pair(slot["eeg"], slot["emg"], starts_h, starts_d, wd, is_hann, dmode, lo, hi, sp[..., :ne],
+                             sp[..., ne_p:ne_p + nm])
         flat = sp.view(L, F, ne_p + nm_p)
         res = K.csd_msc(flat[:, :, :ne], flat[:, :, ne_p:ne_p + nm])
         return {"coherence": res.coh}

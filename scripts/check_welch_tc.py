@@ -30,7 +30,7 @@ def oracle_spec(x, starts, N, detrend, lo, hi):
     return out
 
 
-def case(name, eeg, emg, starts, N, lo, hi, detrend, tol=3e-5):
+def case(name, eeg, emg, starts, N, lo, hi, detrend, tol=6e-5):
     starts = np.asarray(starts, dtype=np.int64)
     F = hi - lo + 1
     ne = eeg.shape[1]

@@ -391,3 +391,20 @@ def test_experiment_log_readers(tmp_path):
     assert xlog.fetch_personal_data(root / "data" / "experiment_results" / "subject_02")["Dominant hand"] == "Left"
     idx = xlog.add_time_index(start, end, n_timesteps=5)
     assert len(idx) == 5 and idx[0] == start and idx[-1] == end
+
+
+def test_welch_tensor_core_path_selection_is_host_logic():
+    """Which Welch requests go to the tensor-core half-block kernel (cmc_welch_hann_*) is decided on the host."""
+    from scipy import signal
+    from multimodal_biosignal_analysis_b200 import kernels as K, signal_features as sf
+    assert sf._is_periodic_hann(signal.get_window("hann", 2048)[None])
+    assert sf._is_periodic_hann(signal.get_window("hann", 512).astype(np.float32))
+    assert not sf._is_periodic_hann(signal.windows.hann(2048, sym=True)[None])          # symmetric hann: not scipy's default
+    assert not sf._is_periodic_hann(signal.get_window("hamming", 2048)[None])
+    assert not sf._is_periodic_hann(np.stack([signal.get_window("hann", 256)] * 2))     # more than one window row
+    assert K.WelchHannPlan.supports(2048, 1, 100)          # BASELINE config 2: 1 - 100 Hz of nperseg 2048
+    assert K.WelchHannPlan.supports(2048, 0, 101) and K.WelchHannPlan.supports(2048, 40, 141)
+    assert not K.WelchHannPlan.supports(2048, 0, 103)      # more than 102 bins (+ two neighbours) per accumulator
+    assert not K.WelchHannPlan.supports(2048, 1, 1024)     # full band: the FFT kernel's job
+    assert not K.WelchHannPlan.supports(1000, 1, 50) and not K.WelchHannPlan.supports(128, 1, 20)
+    assert not K.WelchHannPlan.supports(256, 60, 100)      # would reach the Nyquist bin

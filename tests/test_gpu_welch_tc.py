@@ -1,0 +1,171 @@
+"""GPU parity of the tensor-core Welch kernel (cmc_welch_hann_*: half-block BF16x3 tcgen05 DFT, hann as a three-tap
+epilogue) through the C ABI against the fp64 oracle.
+
+Gates: spectra within 1.2e-4 of the channel's spectral rms (operands carry 16 significand bits; the FFT kernel sits
+at 2e-6), coherence computed from them within 1e-5 of the fp64 coherence (north star: 1e-4), bit-identical results
+from run to run and from a CUDA-graph replay, and every detrend convention / band edge / channel layout the FFT
+kernel takes.  What scipy.signal.coherence does per pair (preprocessing.py:1228-1230) is the ground truth."""
+import numpy as np
+import pytest
+import torch
+from scipy import signal
+
+from oracle import coherence as oc
+
+pytestmark = pytest.mark.gpu
+
+SPEC_TOL = 1.2e-4
+
+
+def _dev(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def _oracle_spectra(x, starts, N, detrend, lo, hi):
+    win = signal.get_window("hann", N)[None]
+    return oc.segment_spectra(x.astype(np.float64), np.asarray(starts), win, detrend, lo, hi)[:, 0]
+
+
+def _run(K, plan, eeg, emg, F, detrend=1):
+    ne = eeg.shape[1]
+    nm = 0 if emg is None else emg.shape[1]
+    spec = torch.full((plan.n_seg, 1, F, ne + nm), float("nan"), dtype=torch.complex64, device="cuda")
+    if emg is None:
+        plan.spectra(_dev(eeg), spec, detrend=detrend)
+    else:
+        plan.spectra(_dev(eeg), spec[..., :ne], _dev(emg), spec[..., ne:], detrend=detrend)
+    torch.cuda.synchronize()
+    return spec
+
+
+def _rel_err(got, ref):
+    rms = np.sqrt(np.mean(np.abs(ref) ** 2, axis=(0, 1), keepdims=True)) + 1e-30
+    return float(np.max(np.abs(got - ref) / rms))
+
+
+@pytest.mark.parametrize("detrend,lo,hi", [(1, 1, 100), (0, 1, 100), (2, 0, 99), (1, 0, 101), (1, 40, 141), (0, 0, 50)])
+def test_spectra_match_oracle_config2_epochs(cuda_device, detrend, lo, hi):
+    from multimodal_biosignal_analysis_b200 import kernels as K, synthetic as syn
+    eeg, emg = syn.make_epochs(3, 8192, 64, 64, seed=1)
+    starts = syn.epoch_segment_starts(3, 8192, 2048, 1024)
+    plan = K.WelchHannPlan(starts, 2048, lo, hi)
+    assert plan.n_half_blocks == 24                       # 8 half blocks per epoch instead of 2 x 7
+    got = _run(K, plan, eeg, emg, hi - lo + 1, detrend)[:, 0].cpu().numpy()
+    ref = _oracle_spectra(np.concatenate([eeg, emg], axis=1), starts, 2048, detrend, lo, hi)
+    assert not np.isnan(got.view(np.float32)).any()
+    assert _rel_err(got, ref) < SPEC_TOL
+
+
+def test_mixed_chains_odd_channel_counts(cuda_device):
+    """Isolated segments, short chains, unsorted starts, 12 + 60 channels (rows of the unit left empty)."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal((20000, 12)).astype(np.float32)
+    m = rng.standard_normal((20000, 60)).astype(np.float32)
+    starts = np.array([0, 512, 1024, 5000, 5512, 9000, 3000, 3512, 4024, 18976], dtype=np.int64)
+    plan = K.WelchHannPlan(starts, 1024, 1, 50)
+    assert plan.n_half_blocks == 15
+    got = _run(K, plan, e, m, 50)[:, 0].cpu().numpy()
+    ref = _oracle_spectra(np.concatenate([e, m], axis=1), starts, 1024, 1, 1, 50)
+    assert _rel_err(got, ref) < SPEC_TOL
+
+
+@pytest.mark.parametrize("n_ch,N,lo,hi", [(128, 512, 2, 60), (200, 4096, 1, 100), (64, 256, 1, 20)])
+def test_single_recording(cuda_device, n_ch, N, lo, hi):
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(n_ch)
+    x = rng.standard_normal((3 * N + 1000, n_ch)).astype(np.float32)
+    starts = np.arange(0, x.shape[0] - N, N // 2, dtype=np.int64)
+    plan = K.WelchHannPlan(starts, N, lo, hi)
+    got = _run(K, plan, x, None, hi - lo + 1)[:, 0].cpu().numpy()
+    ref = _oracle_spectra(x, starts, N, 1, lo, hi)
+    assert _rel_err(got, ref) < SPEC_TOL
+
+
+def test_dc_offset_and_drift_no_worse_than_fft(cuda_device):
+    """A DC level of 1000 sigma plus a ramp: float32 input quantisation bounds both kernels; the tensor-core path
+    (chain offset removed exactly before the BF16 split) must stay at the FFT kernel's error level."""
+    from multimodal_biosignal_analysis_b200 import kernels as K, synthetic as syn
+    eeg, emg = syn.make_epochs(3, 8192, 64, 64, seed=1)
+    starts = syn.epoch_segment_starts(3, 8192, 2048, 1024)
+    t = np.arange(eeg.shape[0], dtype=np.float32)[:, None]
+    eeg = (eeg + 1000.0 + 0.01 * t).astype(np.float32)
+    emg = (emg - 300.0).astype(np.float32)
+    plan = K.WelchHannPlan(starts, 2048, 1, 100)
+    got = _run(K, plan, eeg, emg, 100)[:, 0].cpu().numpy()
+    ref = _oracle_spectra(np.concatenate([eeg, emg], axis=1), starts, 2048, 1, 1, 100)
+    win = _dev(signal.get_window("hann", 2048).astype(np.float32)[None])
+    fft = torch.empty((len(starts), 1, 100, 128), dtype=torch.complex64, device="cuda")
+    K.fft_segments_pair(_dev(eeg), _dev(emg), _dev(starts), win, 1, 1, 100, fft[..., :64], fft[..., 64:])
+    e_tc, e_fft = _rel_err(got, ref), _rel_err(fft[:, 0].cpu().numpy(), ref)
+    assert e_tc < max(2.0 * e_fft, SPEC_TOL)
+
+
+def test_config2_full_size_coherence_and_determinism(cuda_device):
+    """BASELINE config 2 at full size: coherence from the tensor-core spectra vs fp64, 1e-5; two launches and a
+    CUDA-graph replay are bit-identical (store-then-add emission is order independent)."""
+    from multimodal_biosignal_analysis_b200 import kernels as K, synthetic as syn
+    eeg, emg = syn.make_epochs(30, 8192, 64, 64, seed=20260102)
+    starts = syn.epoch_segment_starts(30, 8192, 2048, 1024)
+    plan = K.WelchHannPlan(starts, 2048, 1, 100)
+    assert plan.n_half_blocks == 240
+    e_d, m_d = _dev(eeg), _dev(emg)
+    spec = torch.empty((210, 1, 100, 128), dtype=torch.complex64, device="cuda")
+    plan.spectra(e_d, spec[..., :64], m_d, spec[..., 64:])
+    torch.cuda.synchronize()
+    got = spec[:, 0].cpu().numpy()
+    ref = _oracle_spectra(np.concatenate([eeg, emg], axis=1), starts, 2048, 1, 1, 100)
+    assert _rel_err(got, ref) < SPEC_TOL
+    c_ref = oc.msc_from_spectra(ref[:, :, :64], ref[:, :, 64:])[0]
+    c_got = oc.msc_from_spectra(got[:, :, :64].astype(np.complex128), got[:, :, 64:].astype(np.complex128))[0]
+    assert np.max(np.abs(c_ref - c_got)) < 1e-5
+    again = torch.empty_like(spec)
+    plan.spectra(e_d, again[..., :64], m_d, again[..., 64:])
+    g = torch.cuda.CUDAGraph()
+    graphed = torch.empty_like(spec)
+    with torch.cuda.graph(g):
+        plan.spectra(e_d, graphed[..., :64], m_d, graphed[..., 64:])
+    graphed.zero_()
+    g.replay()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(again.view(torch.float32), spec.view(torch.float32))
+    assert torch.equal(graphed.view(torch.float32), spec.view(torch.float32))
+
+
+def test_public_api_takes_the_tensor_core_path(cuda_device, monkeypatch):
+    """welch_magnitude_squared_coherence on 64 x 64 channels: same coherence (1e-4 vs the fp64 oracle) whichever K1
+    runs, the hann / band-limited call goes through the tensor cores, another window through the FFT kernel."""
+    from multimodal_biosignal_analysis_b200 import kernels as K, signal_features as sf, synthetic as syn
+    eeg, emg = syn.make_epochs(4, 8192, 64, 64, seed=9)
+    starts = syn.epoch_segment_starts(4, 8192, 2048, 1024)
+    taken = []
+    orig = K.welch_spectra_pair
+    monkeypatch.setattr(K, "welch_spectra_pair", lambda *a, **k: taken.append(orig(*a, **k)) or taken[-1])
+    tc = sf.welch_magnitude_squared_coherence(eeg, emg, 2048.0, nperseg=2048, freq_band=(1, 100), segment_starts=starts)
+    monkeypatch.setenv("CMC_WELCH_FFT", "1")
+    fft = sf.welch_magnitude_squared_coherence(eeg, emg, 2048.0, nperseg=2048, freq_band=(1, 100), segment_starts=starts)
+    monkeypatch.delenv("CMC_WELCH_FFT")
+    ham = sf.welch_magnitude_squared_coherence(eeg, emg, 2048.0, nperseg=2048, window="hamming", freq_band=(1, 100),
+                                               segment_starts=starts)
+    assert taken == ["tensor-core", "fft", "fft"]
+    ref = _oracle_spectra(np.concatenate([eeg, emg], axis=1), starts, 2048, 1, 1, 100)
+    c_ref = oc.msc_from_spectra(ref[:, :, :64], ref[:, :, 64:])[0]
+    assert np.max(np.abs(tc.coherence - c_ref)) < 1e-4
+    assert np.max(np.abs(fft.coherence - c_ref)) < 1e-4
+    assert np.max(np.abs(tc.coherence - fft.coherence)) < 2e-5
+    assert ham.coherence.shape == tc.coherence.shape
+
+
+def test_unsupported_requests_are_refused(cuda_device):
+    from multimodal_biosignal_analysis_b200 import _lib, kernels as K
+    assert not K.WelchHannPlan.supports(2048, 1, 200)          # band wider than 102 bins
+    assert not K.WelchHannPlan.supports(1000, 1, 50)           # N not a multiple of 128
+    assert K.hann_plan_for(np.arange(0, 4096, 1024), 2048, 1, 200) is None
+    with pytest.raises(_lib.CmcError, match="outside the tensor-core kernel"):
+        K.WelchHannPlan(np.arange(0, 4096, 1024), 2048, 1, 200)
+    plan = K.WelchHannPlan(np.array([0, 1024], dtype=np.int64), 2048, 1, 100)
+    x = torch.zeros((2048, 64), device="cuda")               # too short for the second segment
+    out = torch.empty((2, 100, 64), dtype=torch.complex64, device="cuda")
+    with pytest.raises(_lib.CmcError, match="outside the recording"):
+        plan.spectra(x, out)
