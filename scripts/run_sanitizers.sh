@@ -14,5 +14,6 @@ run() {  # name tool families...
 run all memcheck
 run k4 racecheck k4
 run k1 racecheck k1
+run k1t racecheck k1t
 run k2k3 racecheck k2 k3
 run k2w racecheck k2w

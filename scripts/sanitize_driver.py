@@ -37,6 +37,17 @@ if want("k1"):
             assert torch.isfinite(torch.view_as_real(s)).all()
     print("k1 ok")
 
+if want("k1t"):
+    # tensor-core Welch kernel: 12 + 60 channels (two partly empty 64-channel groups), mixed chains, both emission phases
+    e = d(rng.standard_normal((6000, 12)).astype(np.float32))
+    m = d(rng.standard_normal((6000, 60)).astype(np.float32))
+    st = np.array([0, 256, 512, 3000, 5400], dtype=np.int64)
+    plan = K.WelchHannPlan(st, 512, 1, 40)
+    out = torch.empty((len(st), 1, 40, 72), dtype=torch.complex64, device=dev)
+    plan.spectra(e, out[..., :12], m, out[..., 12:])
+    assert torch.isfinite(torch.view_as_real(out)).all()
+    print("k1t ok")
+
 if want("k2") or want("k3") or want("k2w"):
     L, F, ne, nm = 24, 6, 12, 70
     X = d((rng.standard_normal((L, F, ne)) + 1j * rng.standard_normal((L, F, ne))).astype(np.complex64))
