@@ -542,6 +542,9 @@ def main_gpu(args):
         stages["surrogate_null_shift"] = {
             "metric": "surrogates_per_s", "value": N_SURR / (surr_ms / 1e3), "unit": "surrogates/s",
             "ms": surr_ms, "scaling": "replicated",
+            # what the kernel actually contracts: one CSD pass per DISTINCT shift (the p-value resolution of a shift
+            # null is 1 / (L - 1) however many surrogates are drawn)
+            "distinct_shifts": int(n_distinct), "csd_passes_per_s": n_distinct / (surr_ms / 1e3),
             "config": f"config 3: {N_SURR} circular-shift surrogates of one 64x64xF=100 subject-condition; distinct shifts are "
                       f"deduplicated on the device ({n_distinct} of L={L}), four of them share one 3xTF32 tcgen05 tile "
                       f"(N = 256), so the cost does not grow beyond {L - 1} CSD passes (10,000 surrogates take the same "

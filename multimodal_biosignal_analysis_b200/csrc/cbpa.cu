@@ -445,7 +445,9 @@ extern "C" int cmc_cbpa_permute(const double* X, int n_subj, int n_tests, const 
     using namespace cmc;
     int rc = cbpa_check(n_subj, n_tests, indptr, indices, tail, thr);
     if (rc) return rc;
-    CMC_REQUIRE(signs && h0_fixed && p_end >= p_begin, "cmc_cbpa_permute: bad permutation range");
+    CMC_REQUIRE(p_end >= p_begin, "cmc_cbpa_permute: bad permutation range");
+    if (p_end == p_begin) return CMC_OK;
+    CMC_REQUIRE(signs && h0_fixed, "cmc_cbpa_permute: null pointer");
     const int64_t n_perm = p_end - p_begin;
     if (n_perm == 0) return CMC_OK;
     const double* XT = nullptr;

@@ -506,6 +506,8 @@ def cbpa_permute(X: torch.Tensor, signs: torch.Tensor, p_begin: int, p_end: int,
     if not (0 <= p_begin <= p_end <= signs.shape[0]):
         raise ValueError("permutation range outside the sign table")
     h0 = torch.empty(p_end - p_begin, dtype=torch.int64, device=X.device)
+    if p_end == p_begin:                        # a rank whose shard of a short (exact) sign table is empty
+        return h0
     lib = _lib.load()
     if tiled and ws is None:
         raise ValueError("tiled=True needs the workspace that holds the tiled copy")

@@ -196,3 +196,21 @@ def test_cbpa_lockfree_labelling_is_deterministic_under_repetition(cuda_device):
     with np.errstate(all="ignore"):
         ref = ocb.permutation_cluster_1samp_test(X, signs[pick], thr, 0, adj)
     np.testing.assert_array_equal(first[pick], ref["H0_fixed"][1:])
+
+
+def test_empty_permutation_shard(cuda_device):
+    """A rank whose slice of a short (exact-enumeration) sign table is empty - 2 subjects have ONE sign pattern, two
+    ranks share it - must get an empty H0 slice back, not an error (found by the 2-GPU bench of config 5)."""
+    from multimodal_biosignal_analysis_b200 import cbpa as cb, kernels as K, synthetic as syn
+    X = syn.make_cbpa_contrast(2, 6, 16, seed=4)
+    signs = cb.make_sign_table(1000, 2, seed=1, tail=0)
+    assert signs.shape == (1, 2)
+    adj = cb.combine_adjacency(6, cb.find_ch_adjacency_from_positions(syn.sensor_positions(64)[:16])).tocsr()
+    adj.sort_indices()
+    Xd = torch.from_numpy(np.ascontiguousarray(X.reshape(2, -1))).cuda()
+    ip = torch.from_numpy(adj.indptr.astype(np.int32)).cuda()
+    ix = torch.from_numpy(adj.indices.astype(np.int32)).cuda()
+    sd = torch.from_numpy(signs).cuda()
+    h_empty = K.cbpa_permute(Xd, sd, 1, 1, 12.7, 0, ip, ix)
+    h_one = K.cbpa_permute(Xd, sd, 0, 1, 12.7, 0, ip, ix)
+    assert h_empty.numel() == 0 and h_one.numel() == 1
