@@ -324,6 +324,10 @@ def main_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line: whatever libraries print on fd 1 (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -817,7 +821,9 @@ def main_gpu(args):
         line = {
             "metric": "pair_spectra_per_s", "value": value, "unit": "pair-spectra/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT), tf32x3 -> f32 accumulate (CSD)",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ("bf16x3 -> f32 accumulate (K1t DFT), " if k1_plan is not None else "f32 (FFT), ") +
+                     "tf32x3 -> f32 accumulate (CSD)",
             "data": "synthetic", "config": workload_config(),
             "roofline": {"bound": "hbm", "kernel": k1_name,
                          "achieved": k1_gbs, "peak": hbm, "unit": "GB/s", "frac": k1_gbs / hbm,
@@ -838,7 +844,8 @@ def main_gpu(args):
             "cbpa_permutations_per_s": stages.get("cbpa", {}).get("value"),
             "config5_sweep_seconds": stages.get("config5_sweep", {}).get("seconds_total"),
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
