@@ -51,6 +51,7 @@ constexpr int kDtThreads = 512;
 constexpr int kDtConvThreads = 256;                          // warps 8-15
 constexpr int kDtStagesA = 3;                                // raw tile / A operand ring
 constexpr int kDtStagesB = 2;                                // W k-block ring
+constexpr int kDtStagesBPair = 4;                            // W ring of the CTA-pair variant (each CTA stages half a k-block)
 constexpr int kDtKB = 64;                                    // samples per k-block: 128-byte BF16 rows (SWIZZLE_128B).  32 (64-byte rows,
                                                              // SWIZZLE_64B, rings of 5 + 4) is also implemented and measured: same speed
 constexpr int kDtRowB = kDtKB * 2;                           // bytes per operand row of a k-block
@@ -96,8 +97,8 @@ struct __align__(8) DtBarriers {
     uint64_t full_a[kDtStagesA];
     uint64_t conv[kDtStagesA];
     uint64_t empty_a[kDtStagesA];
-    uint64_t full_b[kDtStagesB];
-    uint64_t empty_b[kDtStagesB];
+    uint64_t full_b[kDtStagesBPair];
+    uint64_t empty_b[kDtStagesBPair];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
@@ -114,6 +115,59 @@ __device__ __forceinline__ uint64_t dt_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(1) << 46;                             // descriptor version (Blackwell)
     d |= static_cast<uint64_t>(4) << 61;                             // SWIZZLE_64B
     return d;
+}
+
+// ------------------------------------------------------------------ CTA pair (cta_group::2) primitives
+__device__ __forceinline__ uint32_t dt_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `addr` (a shared::cta window address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dt_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dt_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void dt_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier of the pair's LEADER (cluster address `mbar`)
+__device__ __forceinline__ void dt_tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t mbar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void dt_umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all earlier MMAs of this thread have completed) on the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void dt_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void dt_tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dt_tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 // developer trace (CMC_DT_DBG & 32): globaltimer stamps of CTA 0, read back with cmc_dbg_dt_trace
@@ -252,34 +306,49 @@ __device__ __forceinline__ void dt_epilogue_bins(uint32_t taddr, float chh, cons
     }
 }
 
+// PAIR: two CTAs of a cluster (one TPC) run their units in lockstep as ONE tcgen05.mma.cta_group::2 of M = 256: each
+// CTA converts its own raw tile (A rows of its unit) and stages HALF of the W k-block (104 of the 208 rows); the
+// tensor cores of the pair share the two halves.  Per CTA and k-block that is 26 KB instead of 52 KB of W written by
+// TMA and 39 KB instead of 78 KB of W read by the tensor core - the main loop is bound by shared-memory bandwidth.
+// The leader (cluster rank 0) issues the MMAs; its barriers collect the pair's arrivals (conv: 512 converter threads,
+// full_b: the bytes of both halves, tmem_empty: 8 epilogue warps); tcgen05.commit multicasts to both CTAs.
+template <bool PAIR>
 __global__ void __launch_bounds__(kDtThreads, 1)
 dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant__ CUtensorMap mX1,
                    const __grid_constant__ CUtensorMap mW, const DtParams p) {
+    constexpr int kStagesB = PAIR ? kDtStagesBPair : kDtStagesB;
+    constexpr int kPlaneB = PAIR ? kDtPlaneB / 2 : kDtPlaneB;       // W rows this CTA stages per plane and k-block
+    constexpr int kBBytes = 2 * kPlaneB;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                        // [kDtStagesA][32 KB]
-    unsigned char* sB = base + kDtStagesA * kDtABytes;               // [kDtStagesB][52 KB]
-    float* csum = reinterpret_cast<float*>(sB + kDtStagesB * kDtBBytes);   // [2][128] partial sums of the first k-block
+    unsigned char* sB = base + kDtStagesA * kDtABytes;               // [kStagesB][kBBytes]
+    float* csum = reinterpret_cast<float*>(sB + kStagesB * kBBytes); // [2][128] partial sums of the first k-block
     float* coff = csum + 2 * kDtM;                                   // [kDtSlots][128] per-unit channel offsets c_h
     float2* e1s = reinterpret_cast<float2*>(coff + kDtSlots * kDtM); // [112] E1 of the accumulator bins (odd bins only)
     DtBarriers* bars = reinterpret_cast<DtBarriers*>(e1s + 112);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = p.n_items * p.n_gp;
+    const uint32_t rank = PAIR ? dt_cta_rank() : 0u;                 // 0 = leader of the pair
+    // rounds of this CTA (pair): q = q0, q0 + q_step, ...; its unit in round q is 2 q + rank (PAIR) or q
+    const int q0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int q_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_rounds = PAIR ? (n_units + 1) / 2 : n_units;
     if (threadIdx.x == 0) dt_stamp(p, 0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kDtStagesA; ++s) {
             mbar_init(&bars->full_a[s], 1);
-            mbar_init(&bars->conv[s], kDtConvThreads);
+            mbar_init(&bars->conv[s], PAIR ? 2 * kDtConvThreads : kDtConvThreads);
             mbar_init(&bars->empty_a[s], 1);
         }
-        for (int s = 0; s < kDtStagesB; ++s) {
+        for (int s = 0; s < kStagesB; ++s) {
             mbar_init(&bars->full_b[s], 1);
             mbar_init(&bars->empty_b[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tmem_full[a], 1);
-            mbar_init(&bars->tmem_empty[a], 4);
+            mbar_init(&bars->tmem_empty[a], PAIR ? 8 : 4);
         }
         fence_barrier_init();
         tma_prefetch_desc(&mX0);
@@ -287,8 +356,11 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
         tma_prefetch_desc(&mW);
     }
     if (warp == 2) {
-        tmem_alloc(&bars->tmem_base, 512);
-        tmem_relinquish();
+        if (PAIR) dt_tmem_alloc_pair(&bars->tmem_base, 512);
+        else {
+            tmem_alloc(&bars->tmem_base, 512);
+            tmem_relinquish();
+        }
     }
     if (threadIdx.x >= 128 && threadIdx.x < 128 + 112) {
         const int j = threadIdx.x - 128;
@@ -297,6 +369,7 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) dt_cluster_sync();                 // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     if (threadIdx.x == 0) dt_stamp(p, 1);
@@ -306,51 +379,59 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
         if (lane == 0) {
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const DtItem it = p.items[u / p.n_gp];
+            for (int q = q0; q < n_rounds; q += q_step) {
+                const int u = PAIR ? 2 * q + (int)rank : q;
+                const bool live = u < n_units;                       // the last pair may run one empty unit
+                const DtItem it = p.items[(live ? u : 0) / p.n_gp];
                 const int gp = u % p.n_gp;
                 int ra, ca, rb, cb;
                 dt_group(p, 2 * gp, ra, ca);
                 dt_group(p, 2 * gp + 1, rb, cb);
                 const CUtensorMap* ma = ra ? &mX1 : &mX0;
                 const CUtensorMap* mb = rb ? &mX1 : &mX0;
-                for (int kb = 0; kb < p.pf && kb < p.KB; ++kb) {      // raw tiles come from HBM: warm L2 ahead
-                    dt_prefetch_l2(ma, ca, it.x_row + kb * kDtKB);
-                    dt_prefetch_l2(mb, cb, it.x_row + kb * kDtKB);
-                }
                 for (int kb = 0; kb < p.KB; ++kb) {
                     const int row = it.x_row + kb * kDtKB;
-                    if (p.pf && kb + p.pf < p.KB) {
+                    if (live && p.pf && kb + p.pf < p.KB) {          // optional L2 prefetch (CMC_DT_PF)
                         dt_prefetch_l2(ma, ca, row + p.pf * kDtKB);
                         dt_prefetch_l2(mb, cb, row + p.pf * kDtKB);
                     }
                     mbar_wait(&bars->empty_a[sa], pa ^ 1);
-                    if (u == (int)blockIdx.x && kb < 16) dt_stamp(p, 2 + kb);
-                    mbar_arrive_expect_tx(&bars->full_a[sa], kDtABytes);
-                    unsigned char* st = sA + sa * kDtABytes;
-                    tma_load_2d(st, ma, &bars->full_a[sa], ca, row);
-                    tma_load_2d(st + kDtPlaneA, mb, &bars->full_a[sa], cb, row);
+                    if (q == q0 && kb < 16) dt_stamp(p, 2 + kb);
+                    if (live) {
+                        mbar_arrive_expect_tx(&bars->full_a[sa], kDtABytes);
+                        unsigned char* st = sA + sa * kDtABytes;
+                        tma_load_2d(st, ma, &bars->full_a[sa], ca, row);
+                        tma_load_2d(st + kDtPlaneA, mb, &bars->full_a[sa], cb, row);
+                    } else {
+                        mbar_arrive(&bars->full_a[sa]);
+                    }
                     if (++sa == kDtStagesA) { sa = 0; pa ^= 1; }
                     mbar_wait(&bars->empty_b[sb], pb ^ 1);
-                    if ((p.dbg & 8) && (u != (int)blockIdx.x || kb >= kDtStagesB)) {
+                    unsigned char* sw = sB + sb * kBBytes;
+                    if (PAIR) {
+                        // both CTAs load their half of the W k-block; the bytes of both are counted on the leader's barrier
+                        if (rank == 0) mbar_arrive_expect_tx(&bars->full_b[sb], 2 * kBBytes);
+                        const uint32_t lead_bar = dt_mapa(smem_u32(&bars->full_b[sb]), 0);
+                        dt_tma_load_2d_pair(sw, &mW, lead_bar, kb * kDtKB, (int)rank * (kDtCols / 2));
+                        dt_tma_load_2d_pair(sw + kPlaneB, &mW, lead_bar, kb * kDtKB, kDtCols + (int)rank * (kDtCols / 2));
+                    } else if ((p.dbg & 8) && (q != q0 || kb >= kStagesB)) {
                         mbar_arrive(&bars->full_b[sb]);            // timing experiment: stale W, no load
                     } else {
-                        mbar_arrive_expect_tx(&bars->full_b[sb], kDtBBytes);
-                        unsigned char* sw = sB + sb * kDtBBytes;
+                        mbar_arrive_expect_tx(&bars->full_b[sb], kBBytes);
                         tma_load_2d(sw, &mW, &bars->full_b[sb], kb * kDtKB, 0);
-                        tma_load_2d(sw + kDtPlaneB, &mW, &bars->full_b[sb], kb * kDtKB, kDtCols);
+                        tma_load_2d(sw + kPlaneB, &mW, &bars->full_b[sb], kb * kDtKB, kDtCols);
                     }
-                    if (++sb == kDtStagesB) { sb = 0; pb ^= 1; }
+                    if (++sb == kStagesB) { sb = 0; pb ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kDtM, kDtCols);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kDtM : kDtM, kDtCols);
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0, n = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            for (int q = q0; q < n_rounds; q += q_step) {
                 const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
                 mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
                 tc_fence_after();
@@ -358,25 +439,37 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(&bars->full_b[sb], pb);              // W planes (async proxy) have landed
                     mbar_wait(&bars->conv[sa], pa);                // A planes written by the converters
-                    if (u == (int)blockIdx.x && kb < 16) dt_stamp(p, 18 + kb);
+                    if (q == q0 && kb < 16) dt_stamp(p, 18 + kb);
                     tc_fence_after();
                     const uint32_t ahi = smem_u32(sA + sa * kDtABytes), alo = ahi + kDtPlaneA;
-                    const uint32_t bhi = smem_u32(sB + sb * kDtBBytes), blo = bhi + kDtPlaneB;
+                    const uint32_t bhi = smem_u32(sB + sb * kBBytes), blo = bhi + kPlaneB;
 #pragma unroll
                     for (int k = 0; k < kDtKB / 16; ++k) {
                         if (p.dbg & 2) break;
                         const uint64_t dah = dt_desc(ahi + k * 32), dal = dt_desc(alo + k * 32);
                         const uint64_t dbh = dt_desc(bhi + k * 32), dbl = dt_desc(blo + k * 32);
-                        umma_f16(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);      // small terms first
-                        umma_f16(d, dah, dbl, idesc, 1u);
-                        umma_f16(d, dah, dbh, idesc, 1u);
+                        if (PAIR) {
+                            dt_umma_f16_pair(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+                            dt_umma_f16_pair(d, dah, dbl, idesc, 1u);
+                            dt_umma_f16_pair(d, dah, dbh, idesc, 1u);
+                        } else {
+                            umma_f16(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);      // small terms first
+                            umma_f16(d, dah, dbl, idesc, 1u);
+                            umma_f16(d, dah, dbh, idesc, 1u);
+                        }
                     }
-                    umma_commit(&bars->empty_a[sa]);
-                    umma_commit(&bars->empty_b[sb]);
+                    if (PAIR) {
+                        dt_commit_pair(&bars->empty_a[sa]);
+                        dt_commit_pair(&bars->empty_b[sb]);
+                    } else {
+                        umma_commit(&bars->empty_a[sa]);
+                        umma_commit(&bars->empty_b[sb]);
+                    }
                     if (++sa == kDtStagesA) { sa = 0; pa ^= 1; }
-                    if (++sb == kDtStagesB) { sb = 0; pb ^= 1; }
+                    if (++sb == kStagesB) { sb = 0; pb ^= 1; }
                 }
-                umma_commit(&bars->tmem_full[acc]);
+                if (PAIR) dt_commit_pair(&bars->tmem_full[acc]);
+                else umma_commit(&bars->tmem_full[acc]);
                 ++n;
             }
         }
@@ -387,8 +480,10 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
         const int g = t >> 7;                    // samples 32 g .. 32 g + 31 of the k-block
         int sa = 0;
         uint32_t pa = 0, n = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const DtItem it = p.items[u / p.n_gp];
+        for (int q = q0; q < n_rounds; q += q_step) {
+            const int u = PAIR ? 2 * q + (int)rank : q;
+            const bool live = u < n_units;
+            const DtItem it = p.items[(live ? u : 0) / p.n_gp];
             const int gp = u % p.n_gp;
             int rec, c0;
             dt_group(p, 2 * gp + (m >> 6), rec, c0);
@@ -401,9 +496,10 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
             float c = ch < (rec ? p.n_ch[1] : p.n_ch[0]) ? __ldg(xr + (long long)it.c_row * ldr + ch) : 0.f;
             for (int kb = 0; kb < p.KB; ++kb) {
                 mbar_wait(&bars->full_a[sa], pa);
-                if (t == 0 && u == (int)blockIdx.x && kb < 16) dt_stamp(p, 34 + kb);
-                if (p.dbg & 1) {
-                    mbar_arrive(&bars->conv[sa]);
+                if (t == 0 && q == q0 && kb < 16) dt_stamp(p, 34 + kb);
+                if ((p.dbg & 1) || !live) {
+                    if (PAIR) dt_arrive_cluster(dt_mapa(smem_u32(&bars->conv[sa]), 0));
+                    else mbar_arrive(&bars->conv[sa]);
                     if (++sa == kDtStagesA) { sa = 0; pa ^= 1; }
                     continue;
                 }
@@ -442,7 +538,8 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
                     dt_sts128(row + kDtPlaneA + off, lo);
                 }
                 fence_proxy_async();             // generic-proxy writes -> visible to the MMA's async-proxy reads
-                mbar_arrive(&bars->conv[sa]);
+                if (PAIR) dt_arrive_cluster(dt_mapa(smem_u32(&bars->conv[sa]), 0));    // the leader issues the pair's MMAs
+                else mbar_arrive(&bars->conv[sa]);
                 if (++sa == kDtStagesA) { sa = 0; pa ^= 1; }
             }
             ++n;
@@ -453,13 +550,15 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
         const int m = threadIdx.x - 128;         // accumulator lane = channel of the unit
         uint32_t n = 0;
         const unsigned store_target = 4u * (unsigned)p.n_store_units;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const DtItem it = p.items[u / p.n_gp];
+        for (int q = q0; q < n_rounds; q += q_step) {
+            const int u = PAIR ? 2 * q + (int)rank : q;
+            const bool live = u < n_units;
+            const DtItem it = p.items[(live ? u : 0) / p.n_gp];
             const int gp = u % p.n_gp;
             int rec, c0;
             dt_group(p, 2 * gp + (m >> 6), rec, c0);
             const int ch = c0 + (m & 63);
-            const bool valid = ch < (rec ? p.n_ch[1] : p.n_ch[0]);
+            const bool valid = live && ch < (rec ? p.n_ch[1] : p.n_ch[0]);
             float2* sp = rec ? p.spec[1] : p.spec[0];
             float2* outA = (valid && it.seg_a >= 0) ? sp + (long long)it.seg_a * p.F * p.spec_ld + ch : nullptr;
             float2* outB = (valid && it.seg_b >= 0) ? sp + (long long)it.seg_b * p.F * p.spec_ld + ch : nullptr;
@@ -468,10 +567,10 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
                 c_first = __ldg((rec ? p.x[1] : p.x[0]) + (long long)it.c_row * (rec ? p.ld[1] : p.ld[0]) + ch);
             const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
             mbar_wait(&bars->tmem_full[acc], accphase);
-            if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 50);
+            if (m == 0 && q == q0) dt_stamp(p, 50);
             tc_fence_after();
             const float chh = coff[(n & (kDtSlots - 1)) * kDtM + m];
-            if (it.phase) {
+            if (live && it.phase) {
                 // adds may only start once every store of the launch is visible
                 if (lane == 0) {
                     const long long t0 = clock64();
@@ -501,9 +600,12 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
                                         outB ? outB - back : nullptr, p.spec_ld, (p.dbg & 4) != 0);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);   // accumulator may be overwritten
-            if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 51);
-            if (!it.phase) {
+            if (lane == 0) {                                      // accumulator may be overwritten
+                if (PAIR) dt_arrive_cluster(dt_mapa(smem_u32(&bars->tmem_empty[acc]), 0));
+                else mbar_arrive(&bars->tmem_empty[acc]);
+            }
+            if (m == 0 && q == q0) dt_stamp(p, 51);
+            if (live && !it.phase) {
                 __threadfence();                 // this thread's stores before the warp's arrival
                 __syncwarp();
                 if (lane == 0) atomicAdd(&p.ctr->next, 1u);
@@ -513,7 +615,11 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (PAIR) dt_cluster_sync();                 // no arrival on the peer's barriers is in flight when a CTA leaves
+    if (warp == 2) {
+        if (PAIR) dt_tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
     if (threadIdx.x == 0) dt_stamp(p, 52);
     if (threadIdx.x == 0) {
         // the last CTA to leave hands the counter back at zero (stream-ordered launches and graph replays reuse it)
@@ -548,7 +654,8 @@ struct WelchHannPlan {
     DtItem* d_items;
     float* d_e1im;
     __nv_bfloat16* d_W;
-    CUtensorMap mW;
+    CUtensorMap mW;          // box = 208 rows: one CTA stages a whole W k-block
+    CUtensorMap mW_half;     // box = 104 rows: each CTA of a pair stages half of it
 };
 
 static int make_raw_map(CUtensorMap* m, const float* x, int64_t n_samples, int n_ch, int64_t ld) {
@@ -570,13 +677,13 @@ static int make_raw_map(CUtensorMap* m, const float* x, int64_t n_samples, int n
 }
 
 // W planes [2 * 208][Kw] BF16, K-major: box = one k-block (kDtKB elements) x 208 rows, swizzle = row bytes
-static int make_w_map(CUtensorMap* m, const __nv_bfloat16* W, int Kw) {
+static int make_w_map(CUtensorMap* m, const __nv_bfloat16* W, int Kw, int box_rows = kDtCols) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)Kw, (cuuint64_t)(2 * kDtCols)};
     cuuint64_t strides[1] = {(cuuint64_t)Kw * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kDtKB, (cuuint32_t)kDtCols};
+    cuuint32_t box[2] = {(cuuint32_t)kDtKB, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(W), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, kDtKB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -664,6 +771,7 @@ extern "C" int cmc_welch_hann_plan_create(const int64_t* seg_starts_host, int n_
     }
     if (!rc) rc = check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize(plan)");
     if (!rc) rc = make_w_map(&pl->mW, pl->d_W, Kw);
+    if (!rc) rc = make_w_map(&pl->mW_half, pl->d_W, Kw, kDtCols / 2);
     if (rc) {
         cudaFree(pl->d_items);
         cudaFree(pl->d_e1im);
@@ -748,13 +856,41 @@ extern "C" int cmc_welch_hann_spectra(const void* plan, const float* x1, int n_c
     p.ctr = ctr;
     { const char* e = getenv("CMC_DT_DBG"); p.dbg = e ? atoi(e) : 0; }
     { const char* e = getenv("CMC_DT_PF"); p.pf = e ? atoi(e) : kDtPrefetch; }
-    const size_t smem = 1024 + (size_t)kDtStagesA * kDtABytes + (size_t)kDtStagesB * kDtBBytes +
-                        (2 + kDtSlots) * kDtM * sizeof(float) + 112 * sizeof(float2) + sizeof(DtBarriers) + 16;
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(dft_hann_tc_kernel), smem);
-    if (rc) return rc;
     const long long n_units = (long long)p.n_items * p.n_gp;
-    const unsigned grid = (unsigned)(n_units < sms ? n_units : sms);
-    dft_hann_tc_kernel<<<grid, kDtThreads, smem, st>>>(m0, m1, pl->mW, p);
+    // CMC_DT_PAIR=1: CTA pairs (tcgen05 cta_group::2) share every W k-block.  Bit-identical results; measured SLOWER
+    // (77 us against 54 us for config 2: the pair's barrier round trips lengthen every stage cycle by ~2 us while the
+    // raw / A ring, which bounds the loop, is no deeper), so it is not the default.
+    const bool pair = getenv("CMC_DT_PAIR") != nullptr && kDtKB == 64 && sms >= 2;
+    const size_t smem = 1024 + (size_t)kDtStagesA * kDtABytes +
+                        (pair ? (size_t)kDtStagesBPair * (kDtBBytes / 2) : (size_t)kDtStagesB * kDtBBytes) +
+                        (2 + kDtSlots) * kDtM * sizeof(float) + 112 * sizeof(float2) + sizeof(DtBarriers) + 16;
+    if (pair) {
+        auto kern = dft_hann_tc_kernel<true>;
+        rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
+        if (rc) return rc;
+        const long long n_rounds = (n_units + 1) / 2;
+        const long long pairs = n_rounds < sms / 2 ? n_rounds : sms / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(kDtThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, m0, m1, pl->mW_half, p), "cudaLaunchKernelEx(dft_hann_tc_kernel<pair>)");
+        if (rc) return rc;
+    } else {
+        auto kern = dft_hann_tc_kernel<false>;
+        rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
+        if (rc) return rc;
+        const unsigned grid = (unsigned)(n_units < sms ? n_units : sms);
+        kern<<<grid, kDtThreads, smem, st>>>(m0, m1, pl->mW, p);
+    }
     CMC_CHECK_LAUNCH("dft_hann_tc_kernel");
     return CMC_OK;
 }

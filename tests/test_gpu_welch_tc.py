@@ -169,3 +169,26 @@ def test_unsupported_requests_are_refused(cuda_device):
     out = torch.empty((2, 100, 64), dtype=torch.complex64, device="cuda")
     with pytest.raises(_lib.CmcError, match="outside the recording"):
         plan.spectra(x, out)
+
+
+def test_cta_pair_variant_is_bit_identical(cuda_device, monkeypatch):
+    """CMC_DT_PAIR=1 runs the same units as tcgen05 cta_group::2 pairs (M = 256, each CTA stages half of W): same
+    accumulation order per output, so the spectra must be bit-identical - including an odd number of units (one
+    empty unit in the last pair) and partly empty channel groups."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(3)
+    e = rng.standard_normal((9000, 20)).astype(np.float32)
+    m = rng.standard_normal((9000, 64)).astype(np.float32)
+    starts = np.array([0, 512, 1024, 1536, 4000, 6000, 6512], dtype=np.int64)      # 5 + 2 + 3 = 10 half blocks ...
+    plan = K.WelchHannPlan(starts, 1024, 1, 60)
+    starts_odd = starts[:-1]                                                          # ... and 5 + 2 + 2 = 9
+    plan_odd = K.WelchHannPlan(starts_odd, 1024, 1, 60)
+    assert plan.n_half_blocks == 10 and plan_odd.n_half_blocks == 9
+    for pl in (plan, plan_odd):
+        monkeypatch.delenv("CMC_DT_PAIR", raising=False)
+        single = _run(K, pl, e, m, 60)
+        monkeypatch.setenv("CMC_DT_PAIR", "1")
+        paired = _run(K, pl, e, m, 60)
+        monkeypatch.delenv("CMC_DT_PAIR")
+        assert not torch.isnan(torch.view_as_real(paired)).any()
+        assert torch.equal(single.view(torch.float32), paired.view(torch.float32))
