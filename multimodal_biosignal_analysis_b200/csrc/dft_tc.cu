@@ -78,7 +78,9 @@ struct DtItem {           // one half block
 
 struct DtParams {
     const DtItem* items;
-    const float* e1im;             // [104] Im of E1[b] = sum_{n < N/2} exp(-2 pi i b n / N) for odd b (Re = 1), 0 for even b
+    const float* e1im;             // [104] unfolded kernel: Im of E1[b] = sum_{n < N/2} exp(-2 pi i b n / N) for odd b (Re = 1),
+                                   // 0 for even b; folded kernel: E1c[b] = sum_{k < N/4} 2 cos(theta_b (k + 1/2))
+    const float* rot;              // [104][2] folded kernel: (cos phi_b, sin phi_b), phi_b = theta_b (N/4 - 1/2)
     int n_items, n_gp;             // half blocks, channel-group pairs per half block (units = n_items * n_gp)
     int n_store_units;             // units with phase 0 (they come first)
     int KB, N, bin_lo, F, b0, detrend;
@@ -203,6 +205,21 @@ __device__ __forceinline__ void dt_prefetch_l2(const CUtensorMap* m, int c0, int
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
                  "r"(c0), "r"(c1)
                  : "memory");
+}
+// predicated emission (no branch): `on` != 0 -> store or add
+template <bool ADD>
+__device__ __forceinline__ void dt_emit_if(float2* o, float re, float im, int on) {
+    if (ADD)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %3, 0;\n@p red.global.add.v2.f32 [%0], {%1, %2};\n}\n"
+                     ::"l"(o), "f"(re), "f"(im), "r"(on) : "memory");
+    else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %3, 0;\n@p st.global.v2.f32 [%0], {%1, %2};\n}\n"
+                     ::"l"(o), "f"(re), "f"(im), "r"(on) : "memory");
+}
+__device__ __forceinline__ float4 dt_lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
 }
 // BF16 hi / lo split of two values: hi = rn(v), lo = rn(v - hi); element 0 in the low half-word
 __device__ __forceinline__ void dt_split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
@@ -632,6 +649,432 @@ dft_hann_tc_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constan
     }
 }
 
+// ====================================================================================================================
+// K1t, folded form (default).  About its centre a half block splits into an even and an odd part,
+//     P_h[b] = e^{-i phi_b} (Cp[b] - i Sm[b]),   phi_b = theta_b (N/4 - 1/2),   theta_b = 2 pi b / N,
+//     Cp[b] = sum_{k < N/4} (y[N/4 + k] + y[N/4 - 1 - k]) cos(theta_b (k + 1/2)),
+//     Sm[b] = sum_{k < N/4} (y[N/4 + k] - y[N/4 - 1 - k]) sin(theta_b (k + 1/2)),
+// so the converters fold the raw tile (one add, one subtract per sample pair, in FP32, before the BF16 split) and the
+// GEMM runs over K = N / 4 with the cos table for the sums and the sin table for the differences: two MMAs of N = 112
+// instead of one of N = 208 over twice the K - half the tensor work and half the table bytes per sample.  The
+// epilogue rotates (Cp, Sm) by phi_b (four FMAs per bin) and continues as the unfolded kernel does.  Stages carry 32
+// folded samples (64 raw): raw tile / A planes 32 KB (sum hi, lo, difference hi, lo; 64-byte rows, SWIZZLE_64B),
+// table k-block 28 KB; rings of 4 + 3 stages hold 256 / 192 raw samples in flight against 192 / 128 before.
+constexpr int kFdKB = 32;                                    // folded samples per k-block (64-byte BF16 rows)
+constexpr int kFdRows = 112;                                 // table rows / accumulator columns per set (104 bins + 8 zero rows)
+constexpr int kFdStagesL = 2;                                // raw (landing) ring
+constexpr int kFdStagesA = 2;                                // operand ring (A planes)
+constexpr int kFdStagesB = 3;                                // table ring
+constexpr int kFdPlaneA = kDtM * kFdKB * 2;                  // 8 KB
+constexpr int kFdABytes = 4 * kFdPlaneA;                     // 32 KB: sum hi, sum lo, difference hi, difference lo
+constexpr int kFdPlaneB = kFdRows * kFdKB * 2;               // 7 KB: one set of one plane
+constexpr int kFdBBytes = 4 * kFdPlaneB;                     // 28 KB: [hi: cos rows, sin rows][lo: cos rows, sin rows]
+constexpr int kFdSpt = kFdKB / 2;                            // folded samples per converter thread and k-block
+
+struct __align__(8) FdBarriers {
+    uint64_t full_l[kFdStagesL];     // raw tile landed (TMA bytes)
+    uint64_t empty_l[kFdStagesL];    // raw tile read into registers by all 8 converter warps
+    uint64_t conv[kFdStagesA];       // A planes written (8 converter warps)
+    uint64_t empty_a[kFdStagesA];    // A planes consumed (MMA commit)
+    uint64_t full_b[kFdStagesB];
+    uint64_t empty_b[kFdStagesB];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+// K-major BF16 operand k-block with 64-byte rows: 8-row atoms of 512 bytes, SWIZZLE_64B
+__device__ __forceinline__ uint64_t fd_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;
+    return d;
+}
+
+// 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void fd_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// (Cp, Sm) of the 8 bins of chunk cq -> (Re P, Im P) with the odd-bin constant added back: Cp += ch * E1c, then the
+// rotation by phi.  tab_s: shared-window address of the (cos phi, sin phi, E1c, -) table.
+__device__ __forceinline__ void fd_load_rotate(uint32_t taddr, int cq, float (&re)[8], float (&im)[8], float ch,
+                                               uint32_t tab_s) {
+    uint32_t cp[8], sm[8];
+    fd_tmem_ld8(taddr + 8 * cq, cp);
+    fd_tmem_ld8(taddr + kFdRows + 8 * cq, sm);
+    tmem_ld_wait();
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const float4 t = dt_lds_f4(tab_s + 16u * (uint32_t)(8 * cq + jj));
+        const float c = fmaf(ch, t.z, __uint_as_float(cp[jj]));
+        const float s = __uint_as_float(sm[jj]);
+        re[jj] = fmaf(t.x, c, -t.y * s);
+        im[jj] = -fmaf(t.y, c, t.x * s);
+    }
+}
+
+// oA / oB: output pointers of accumulator bin 0 (any valid address when the emission is off), on_a / on_b: emission on
+template <bool ADD>
+__device__ __forceinline__ void fd_epilogue_bins(uint32_t taddr, float chh, uint32_t tab_s, int j_lo, int j_hi,
+                                                 float dc_add, bool dc_is_bin0, bool dc_zero_all, bool post_taper,
+                                                 float sgn_even, float2* oA, float2* oB, int on_a, int on_b, long long ld) {
+    float cre[8], cim[8], nre[8] = {}, nim[8] = {};
+    fd_load_rotate(taddr, 0, cre, cim, chh, tab_s);
+    float pm_re = 0.f, pm_im = 0.f;              // P[j - 1] of the first bin of the chunk
+    if (dc_is_bin0) {                            // accumulator bin 0 is the DC bin
+        cre[0] = dc_zero_all ? 0.f : cre[0] + dc_add;
+        cim[0] = 0.f;
+        pm_re = cre[1];                          // P[-1] = conj(P[1])
+        pm_im = -cim[1];
+    }
+    constexpr int kChunks = kDtBins / 8;         // 13
+#pragma unroll 1
+    for (int cq = 0; cq < kChunks; ++cq) {
+        if (cq < kChunks - 1) fd_load_rotate(taddr, cq + 1, nre, nim, chh, tab_s);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = 8 * cq + jj;
+            const float pp_re = jj < 7 ? cre[jj < 7 ? jj + 1 : 7] : nre[0];
+            const float pp_im = jj < 7 ? cim[jj < 7 ? jj + 1 : 7] : nim[0];
+            const float qm_re = jj > 0 ? cre[jj > 0 ? jj - 1 : 0] : pm_re;
+            const float qm_im = jj > 0 ? cim[jj > 0 ? jj - 1 : 0] : pm_im;
+            const float s_re = 0.25f * (qm_re + pp_re), s_im = 0.25f * (qm_im + pp_im);
+            float a_re = fmaf(0.5f, cre[jj], -s_re), a_im = fmaf(0.5f, cim[jj], -s_im);
+            const float sg = (jj & 1) ? -sgn_even : sgn_even;                 // (-1)^b of the second-half emission
+            float b_re = sg * fmaf(0.5f, cre[jj], s_re), b_im = sg * fmaf(0.5f, cim[jj], s_im);
+            if (jj == 0 && cq == 0 && dc_is_bin0 && post_taper) a_re = b_re = 0.f;   // periodogram: DC bin zeroed
+            const int in_band = (j >= j_lo && j < j_hi) ? 1 : 0;
+            dt_emit_if<ADD>(oA, a_re, a_im, in_band & on_a);
+            dt_emit_if<ADD>(oB, b_re, b_im, in_band & on_b);
+            oA += ld;
+            oB += ld;
+        }
+        pm_re = cre[7];
+        pm_im = cim[7];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            cre[i] = nre[i];
+            cim[i] = nim[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kDtThreads, 1)
+dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant__ CUtensorMap mX1,
+                     const __grid_constant__ CUtensorMap mW, const DtParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    // the raw tiles land in their own ring: the converters need no barrier between reading a tile and writing the
+    // planes (in place, all 256 threads had to meet in the middle of every k-block and the eight warps ran in lockstep)
+    unsigned char* sL = base;                                        // [kFdStagesL][32 KB] raw FP32 tiles
+    unsigned char* sA = sL + kFdStagesL * kFdABytes;                 // [kFdStagesA][32 KB] BF16 planes
+    unsigned char* sB = sA + kFdStagesA * kFdABytes;                 // [kFdStagesB][28 KB]
+    float* csum = reinterpret_cast<float*>(sB + kFdStagesB * kFdBBytes);   // [2][128] partial sums of the first k-block
+    float* coff = csum + 2 * kDtM;                                   // [kDtSlots][128] per-unit channel offsets c_h
+    float4* tab = reinterpret_cast<float4*>(coff + kDtSlots * kDtM); // [112] (cos phi, sin phi, E1c, 0) per accumulator bin
+    FdBarriers* bars = reinterpret_cast<FdBarriers*>(tab + kFdRows);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_units = p.n_items * p.n_gp;
+    const int q4 = p.N / 4;
+    if (threadIdx.x == 0) dt_stamp(p, 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kFdStagesL; ++s) {
+            mbar_init(&bars->full_l[s], 1);
+            mbar_init(&bars->empty_l[s], kDtConvThreads / 32);
+        }
+        for (int s = 0; s < kFdStagesA; ++s) {
+            mbar_init(&bars->conv[s], kDtConvThreads / 32);
+            mbar_init(&bars->empty_a[s], 1);
+        }
+        for (int s = 0; s < kFdStagesB; ++s) {
+            mbar_init(&bars->full_b[s], 1);
+            mbar_init(&bars->empty_b[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars->tmem_full[a], 1);
+            mbar_init(&bars->tmem_empty[a], 4);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&mX0);
+        tma_prefetch_desc(&mX1);
+        tma_prefetch_desc(&mW);
+    }
+    if (warp == 2) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + kFdRows) {
+        const int j = threadIdx.x - 128;
+        tab[j] = j < kDtBins ? make_float4(__ldg(p.rot + 2 * j), __ldg(p.rot + 2 * j + 1), __ldg(p.e1im + j), 0.f)
+                             : make_float4(1.f, 0.f, 0.f, 0.f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    if (threadIdx.x == 0) dt_stamp(p, 1);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const DtItem it = p.items[u / p.n_gp];
+                const int gp = u % p.n_gp;
+                int ra, ca, rb, cb;
+                dt_group(p, 2 * gp, ra, ca);
+                dt_group(p, 2 * gp + 1, rb, cb);
+                const CUtensorMap* ma = ra ? &mX1 : &mX0;
+                const CUtensorMap* mb = rb ? &mX1 : &mX0;
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    // forward tile: samples N/4 + 32 kb ...; mirrored tile: samples N/4 - 32 (kb + 1) ... (read backwards)
+                    const int row_f = it.x_row + q4 + kb * kFdKB;
+                    const int row_r = it.x_row + q4 - (kb + 1) * kFdKB;
+                    mbar_wait(&bars->empty_l[sa], pa ^ 1);
+                    if (u == (int)blockIdx.x && kb < 16) dt_stamp(p, 2 + kb);
+                    mbar_arrive_expect_tx(&bars->full_l[sa], kFdABytes);
+                    unsigned char* st = sL + sa * kFdABytes;
+                    tma_load_2d(st, ma, &bars->full_l[sa], ca, row_f);
+                    tma_load_2d(st + kFdPlaneA, mb, &bars->full_l[sa], cb, row_f);
+                    tma_load_2d(st + 2 * kFdPlaneA, ma, &bars->full_l[sa], ca, row_r);
+                    tma_load_2d(st + 3 * kFdPlaneA, mb, &bars->full_l[sa], cb, row_r);
+                    if (++sa == kFdStagesL) { sa = 0; pa ^= 1; }
+                    mbar_wait(&bars->empty_b[sb], pb ^ 1);
+                    mbar_arrive_expect_tx(&bars->full_b[sb], kFdBBytes);
+                    unsigned char* sw = sB + sb * kFdBBytes;
+                    tma_load_2d(sw, &mW, &bars->full_b[sb], kb * kFdKB, 0);                    // hi: cos rows, sin rows
+                    tma_load_2d(sw + 2 * kFdPlaneB, &mW, &bars->full_b[sb], kb * kFdKB, 2 * kFdRows);   // lo
+                    if (++sb == kFdStagesB) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kDtM, kFdRows);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0, n = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
+                mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(&bars->full_b[sb], pb);
+                    mbar_wait(&bars->conv[sa], pa);
+                    if (u == (int)blockIdx.x && kb < 16) dt_stamp(p, 18 + kb);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + sa * kFdABytes);
+                    const uint32_t b0 = smem_u32(sB + sb * kFdBBytes);
+#pragma unroll
+                    for (int set = 0; set < 2; ++set) {              // 0: sums x cos table, 1: differences x sin table
+                        const uint32_t d = tmem_base + acc * 256 + set * kFdRows;
+                        const uint32_t ahi = a0 + set * 2 * kFdPlaneA, alo = ahi + kFdPlaneA;
+                        const uint32_t bhi = b0 + set * kFdPlaneB, blo = bhi + 2 * kFdPlaneB;
+#pragma unroll
+                        for (int k = 0; k < kFdKB / 16; ++k) {
+                            const uint64_t dah = fd_desc(ahi + k * 32), dal = fd_desc(alo + k * 32);
+                            const uint64_t dbh = fd_desc(bhi + k * 32), dbl = fd_desc(blo + k * 32);
+                            umma_f16(d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);      // small terms first
+                            umma_f16(d, dah, dbl, idesc, 1u);
+                            umma_f16(d, dah, dbh, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&bars->empty_a[sa]);
+                    umma_commit(&bars->empty_b[sb]);
+                    if (++sa == kFdStagesA) { sa = 0; pa ^= 1; }
+                    if (++sb == kFdStagesB) { sb = 0; pb ^= 1; }
+                }
+                umma_commit(&bars->tmem_full[acc]);
+                ++n;
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== converters: fold, y = x - c0 - c_h, BF16 hi / lo planes in place =====================
+        const int t = threadIdx.x - 256;
+        const int m = t & 127;                   // A row = channel of the unit
+        const int g = t >> 7;                    // folded samples 16 g .. 16 g + 15 of the k-block
+        int sl = 0, sa = 0;
+        uint32_t pl = 0, pa = 0, n = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const DtItem it = p.items[u / p.n_gp];
+            const int gp = u % p.n_gp;
+            int rec, c0;
+            dt_group(p, 2 * gp + (m >> 6), rec, c0);
+            const int ch = c0 + (m & 63);
+            const float* xr = rec ? p.x[1] : p.x[0];
+            const long long ldr = rec ? p.ld[1] : p.ld[0];
+            float c = ch < (rec ? p.n_ch[1] : p.n_ch[0]) ? __ldg(xr + (long long)it.c_row * ldr + ch) : 0.f;
+            for (int kb = 0; kb < p.KB; ++kb) {
+                mbar_wait(&bars->full_l[sl], pl);
+                if (t == 0 && u == (int)blockIdx.x && kb < 16) dt_stamp(p, 34 + kb);
+                const uint32_t lbase = smem_u32(sL + sl * kFdABytes);
+                const uint32_t src_f = lbase + (uint32_t)((m >> 6) * kFdPlaneA + (m & 63) * 4 + g * kFdSpt * 256);
+                // the mirror of forward row kk is row 31 - kk of the mirrored tile
+                const uint32_t src_r = lbase + (uint32_t)(2 * kFdPlaneA + (m >> 6) * kFdPlaneA + (m & 63) * 4 +
+                                                          (kFdKB - 1 - g * kFdSpt) * 256);
+                float sum[kFdSpt], dif[kFdSpt];
+                const float c2 = 2.0f * c;
+#pragma unroll
+                for (int i = 0; i < kFdSpt; ++i) {
+                    const float f = dt_lds32(src_f + i * 256), r = dt_lds32(src_r - i * 256);
+                    sum[i] = (f + r) - c2;
+                    dif[i] = f - r;
+                }
+                __syncwarp();                    // every lane holds its samples: the raw tile may be overwritten
+                if (lane == 0) mbar_arrive(&bars->empty_l[sl]);
+                if (++sl == kFdStagesL) { sl = 0; pl ^= 1; }
+                if (kb == 0) {
+                    // c_h: mean of the 64 samples around the centre of the half block (added back in the epilogue)
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kFdSpt; ++i) s += sum[i];
+                    csum[g * kDtM + m] = s;
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    const float chh = (csum[m] + csum[kDtM + m]) * (1.0f / (2 * kFdKB));
+                    if (g == 0) coff[(n & (kDtSlots - 1)) * kDtM + m] = chh;
+                    c += chh;
+#pragma unroll
+                    for (int i = 0; i < kFdSpt; ++i) sum[i] -= 2.0f * chh;
+                    asm volatile("bar.sync 2, 256;" ::: "memory");   // csum may be rewritten by the next unit
+                }
+                mbar_wait(&bars->empty_a[sa], pa ^ 1);             // the MMAs that read these planes have completed
+                // K-major rows of 64 bytes: 8-row atoms of 512 bytes, 16-byte chunk index XOR ((row >> 1) & 3)
+                const uint32_t row = smem_u32(sA + sa * kFdABytes) + (uint32_t)((m >> 3) * 512 + (m & 7) * 64);
+                const int sw = (m >> 1) & 3;
+#pragma unroll
+                for (int q = 0; q < kFdSpt / 8; ++q) {
+                    uint4 hi, lo;
+                    const uint32_t off = (uint32_t)((((kFdSpt / 8) * g + q) ^ sw) << 4);
+                    dt_split2(sum[8 * q], sum[8 * q + 1], hi.x, lo.x);
+                    dt_split2(sum[8 * q + 2], sum[8 * q + 3], hi.y, lo.y);
+                    dt_split2(sum[8 * q + 4], sum[8 * q + 5], hi.z, lo.z);
+                    dt_split2(sum[8 * q + 6], sum[8 * q + 7], hi.w, lo.w);
+                    dt_sts128(row + off, hi);
+                    dt_sts128(row + kFdPlaneA + off, lo);
+                    dt_split2(dif[8 * q], dif[8 * q + 1], hi.x, lo.x);
+                    dt_split2(dif[8 * q + 2], dif[8 * q + 3], hi.y, lo.y);
+                    dt_split2(dif[8 * q + 4], dif[8 * q + 5], hi.z, lo.z);
+                    dt_split2(dif[8 * q + 6], dif[8 * q + 7], hi.w, lo.w);
+                    dt_sts128(row + 2 * kFdPlaneA + off, hi);
+                    dt_sts128(row + 3 * kFdPlaneA + off, lo);
+                }
+                fence_proxy_async();             // generic-proxy writes -> visible to the MMA's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->conv[sa]);       // one arrival per warp
+                if (++sa == kFdStagesA) { sa = 0; pa ^= 1; }
+            }
+            ++n;
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: rotation, three-tap hann, two emissions per half block =====================
+        const int q = warp - 4;                  // TMEM lane quadrant
+        const int m = threadIdx.x - 128;         // accumulator lane = channel of the unit
+        uint32_t n = 0;
+        const unsigned store_target = 4u * (unsigned)p.n_store_units;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const DtItem it = p.items[u / p.n_gp];
+            const int gp = u % p.n_gp;
+            int rec, c0;
+            dt_group(p, 2 * gp + (m >> 6), rec, c0);
+            const int ch = c0 + (m & 63);
+            const bool valid = ch < (rec ? p.n_ch[1] : p.n_ch[0]);
+            float2* sp = rec ? p.spec[1] : p.spec[0];
+            float2* outA = (valid && it.seg_a >= 0) ? sp + (long long)it.seg_a * p.F * p.spec_ld + ch : nullptr;
+            float2* outB = (valid && it.seg_b >= 0) ? sp + (long long)it.seg_b * p.F * p.spec_ld + ch : nullptr;
+            float c_first = 0.f;
+            if (p.b0 == 0 && p.detrend != CMC_DETREND_CONSTANT && valid)
+                c_first = __ldg((rec ? p.x[1] : p.x[0]) + (long long)it.c_row * (rec ? p.ld[1] : p.ld[0]) + ch);
+            const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
+            mbar_wait(&bars->tmem_full[acc], accphase);
+            if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 50);
+            tc_fence_after();
+            const float chh = coff[(n & (kDtSlots - 1)) * kDtM + m];
+            if (it.phase) {
+                if (lane == 0) {
+                    const long long t0 = clock64();
+                    while (dt_ld_acquire(&p.ctr->next) < store_target) {
+                        __nanosleep(64);
+                        if (clock64() - t0 > 4000000000LL) {
+                            printf("cmc: dft_hann_fold store-phase wait timed out (block %d)\n", blockIdx.x);
+                            __trap();
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+            const int j_lo = p.bin_lo - p.b0;
+            const long long back = (long long)j_lo * p.spec_ld;
+            const bool dc0 = p.b0 == 0;
+            const float dc_add = 0.5f * (float)p.N * c_first;        // the c_h part came in through E1c[0] = N / 2
+            const float sgn_even = (p.b0 & 1) ? -1.0f : 1.0f;
+            // emissions that are off (no such segment, channel out of range) keep a valid pointer and a zero predicate
+            const int on_a = (outA != nullptr && !(p.dbg & 4)) ? 1 : 0, on_b = (outB != nullptr && !(p.dbg & 4)) ? 1 : 0;
+            float2* pa_ = (outA ? outA : sp) - back;
+            float2* pb_ = (outB ? outB : sp) - back;
+            const uint32_t tab_s = smem_u32(tab);
+            if (it.phase)
+                fd_epilogue_bins<true>(taddr, chh, tab_s, j_lo, j_lo + p.F, dc_add, dc0, p.detrend == CMC_DETREND_CONSTANT,
+                                       p.detrend == CMC_DETREND_POST_TAPER, sgn_even, pa_, pb_, on_a, on_b, p.spec_ld);
+            else
+                fd_epilogue_bins<false>(taddr, chh, tab_s, j_lo, j_lo + p.F, dc_add, dc0, p.detrend == CMC_DETREND_CONSTANT,
+                                        p.detrend == CMC_DETREND_POST_TAPER, sgn_even, pa_, pb_, on_a, on_b, p.spec_ld);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+            if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 51);
+            if (!it.phase) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(&p.ctr->next, 1u);
+            }
+            ++n;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (threadIdx.x == 0) dt_stamp(p, 52);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&p.ctr->done, 1u) == gridDim.x - 1u) {
+            p.ctr->next = 0u;
+            p.ctr->done = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// Folded table: rows [plane][set][112][N/4]: set 0 = cos(theta_b (k + 1/2)), set 1 = sin(theta_b (k + 1/2)), b = b0 + j
+// for j < 104 (zero rows above); plane 0 = BF16 hi, plane 1 = lo.
+__global__ void dft_w_fold_table_kernel(__nv_bfloat16* W, int Kw, int N, int b0) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;                    // set * 112 + j
+    if (k >= Kw) return;
+    const int set = r / kFdRows, j = r - set * kFdRows;
+    double v = 0.0;
+    if (j < kDtBins) {
+        const long long q = ((long long)(b0 + j) * (2 * k + 1)) % (2LL * N);     // angle = pi q / N
+        double s, c;
+        sincospi((double)q / (double)N, &s, &c);
+        v = set ? s : c;
+    }
+    const __nv_bfloat16 hi = __double2bfloat16(v);
+    const __nv_bfloat16 lo = __double2bfloat16(v - (double)__bfloat162float(hi));
+    W[(long long)r * Kw + k] = hi;
+    W[(long long)(2 * kFdRows + r) * Kw + k] = lo;
+}
+
 // W[r][n], r = 2 j + part: part 0 = cos, part 1 = -sin of 2 pi (b0 + j) n / N; rows [0, 208) hi, [208, 416) lo
 __global__ void dft_w_table_kernel(__nv_bfloat16* W, int Kw, int N, int b0) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -656,15 +1099,20 @@ struct WelchHannPlan {
     __nv_bfloat16* d_W;
     CUtensorMap mW;          // box = 208 rows: one CTA stages a whole W k-block
     CUtensorMap mW_half;     // box = 104 rows: each CTA of a pair stages half of it
+    // folded kernel
+    __nv_bfloat16* d_Wf;     // [2 planes][2 sets][112][N / 4]
+    float* d_e1c;            // [104]
+    float* d_rot;            // [104][2]
+    CUtensorMap mWf;         // box = 32 x 224 rows (cos rows + sin rows of one plane), SWIZZLE_64B
 };
 
-static int make_raw_map(CUtensorMap* m, const float* x, int64_t n_samples, int n_ch, int64_t ld) {
+static int make_raw_map(CUtensorMap* m, const float* x, int64_t n_samples, int n_ch, int64_t ld, int box_rows = kDtKB) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)n_ch, (cuuint64_t)n_samples};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {64u, (cuuint32_t)kDtKB};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -690,6 +1138,25 @@ static int make_w_map(CUtensorMap* m, const __nv_bfloat16* W, int Kw, int box_ro
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(W table) failed with CUresult %d", (int)r);
+        return CMC_ECUDA;
+    }
+    return CMC_OK;
+}
+
+// folded table [2 * 224][N / 4] BF16: box = 32 folded samples x 224 rows (cos rows + sin rows of one plane)
+static int make_wf_map(CUtensorMap* m, const __nv_bfloat16* W, int Kw) {
+    EncodeTiledFn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)Kw, (cuuint64_t)(4 * kFdRows)};
+    cuuint64_t strides[1] = {(cuuint64_t)Kw * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kFdKB, (cuuint32_t)(2 * kFdRows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(W), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(folded W table) failed with CUresult %d", (int)r);
         return CMC_ECUDA;
     }
     return CMC_OK;
@@ -749,6 +1216,19 @@ extern "C" int cmc_welch_hann_plan_create(const int64_t* seg_starts_host, int n_
     pl->n_store = (int)std::count_if(items.begin(), items.end(), [](const DtItem& a) { return a.phase == 0; });
     pl->max_row_end = max_end;
     pl->d_items = nullptr; pl->d_W = nullptr; pl->d_e1im = nullptr;
+    pl->d_Wf = nullptr; pl->d_e1c = nullptr; pl->d_rot = nullptr;
+    // folded kernel: E1c[b] = sum_{k < N/4} 2 cos(theta_b (k + 1/2)) = sin(pi b / 2) / sin(pi b / N) (N / 2 for b = 0),
+    // rotation (cos phi_b, sin phi_b) with phi_b = theta_b (N/4 - 1/2) = pi b / 2 - pi b / N
+    std::vector<float> e1c(kDtBins, 0.f), rot(2 * kDtBins, 0.f);
+    for (int j = 0; j < kDtBins; ++j) {
+        const int b = b0 + j;
+        const double pi = 3.14159265358979323846;
+        const double quarter[4] = {0.0, 1.0, 0.0, -1.0};     // sin(pi b / 2), exact
+        e1c[j] = b == 0 ? (float)(N / 2) : (float)(quarter[b & 3] / sin(pi * (double)b / (double)N));
+        const double phi = pi * (double)(b & 3) / 2.0 - pi * (double)b / (double)N;   // pi b / 2 reduced mod 2 pi
+        rot[2 * j] = (float)cos(phi);
+        rot[2 * j + 1] = (float)sin(phi);
+    }
     // E1[b] = sum_{n < N/2} exp(-2 pi i b n / N) = 1 - i cot(pi b / N) for odd b (0 for even b != 0)
     std::vector<float> e1(kDtBins, 0.f);
     for (int j = 0; j < kDtBins; ++j) {
@@ -772,10 +1252,26 @@ extern "C" int cmc_welch_hann_plan_create(const int64_t* seg_starts_host, int n_
     if (!rc) rc = check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize(plan)");
     if (!rc) rc = make_w_map(&pl->mW, pl->d_W, Kw);
     if (!rc) rc = make_w_map(&pl->mW_half, pl->d_W, Kw, kDtCols / 2);
+    const int Kf = N / 4;
+    if (!rc) rc = check_cuda(cudaMalloc(&pl->d_e1c, kDtBins * sizeof(float)), "cudaMalloc(plan E1c)");
+    if (!rc) rc = check_cuda(cudaMemcpy(pl->d_e1c, e1c.data(), kDtBins * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy(plan E1c)");
+    if (!rc) rc = check_cuda(cudaMalloc(&pl->d_rot, 2 * kDtBins * sizeof(float)), "cudaMalloc(plan rot)");
+    if (!rc) rc = check_cuda(cudaMemcpy(pl->d_rot, rot.data(), 2 * kDtBins * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy(plan rot)");
+    if (!rc) rc = check_cuda(cudaMalloc(&pl->d_Wf, (size_t)4 * kFdRows * Kf * sizeof(__nv_bfloat16)), "cudaMalloc(plan folded W)");
+    if (!rc) {
+        dft_w_fold_table_kernel<<<dim3((Kf + 127) / 128, 2 * kFdRows), 128>>>(pl->d_Wf, Kf, N, b0);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        rc = check_cuda(cudaGetLastError(), "dft_w_fold_table_kernel");
+    }
+    if (!rc) rc = check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize(plan, folded table)");
+    if (!rc) rc = make_wf_map(&pl->mWf, pl->d_Wf, Kf);
     if (rc) {
         cudaFree(pl->d_items);
         cudaFree(pl->d_e1im);
         cudaFree(pl->d_W);
+        cudaFree(pl->d_Wf);
+        cudaFree(pl->d_e1c);
+        cudaFree(pl->d_rot);
         delete pl;
         return rc;
     }
@@ -793,6 +1289,9 @@ extern "C" int cmc_welch_hann_plan_destroy(void* plan) {
     cudaFree(pl->d_items);
     cudaFree(pl->d_e1im);
     cudaFree(pl->d_W);
+    cudaFree(pl->d_Wf);
+    cudaFree(pl->d_e1c);
+    cudaFree(pl->d_rot);
     delete pl;
     return CMC_OK;
 }
@@ -833,10 +1332,12 @@ extern "C" int cmc_welch_hann_spectra(const void* plan, const float* x1, int n_c
         set_error("cmc_welch_hann_spectra: no launch counter available (too many captured launches)");
         return CMC_EUNSUPPORTED;
     }
+    // default: the folded kernel; CMC_DT_UNFOLD=1 / CMC_DT_PAIR=1 select the unfolded forms
+    const bool fold = getenv("CMC_DT_UNFOLD") == nullptr && getenv("CMC_DT_PAIR") == nullptr;
     CUtensorMap m0, m1;
-    int rc = make_raw_map(&m0, x1, n_samples, n_ch1, ld1);
+    int rc = make_raw_map(&m0, x1, n_samples, n_ch1, ld1, fold ? kFdKB : kDtKB);
     if (rc) return rc;
-    if (n_ch2) { if ((rc = make_raw_map(&m1, x2, n_samples, n_ch2, ld2))) return rc; }
+    if (n_ch2) { if ((rc = make_raw_map(&m1, x2, n_samples, n_ch2, ld2, fold ? kFdKB : kDtKB))) return rc; }
     else m1 = m0;
     DtParams p{};
     p.items = pl->d_items;
@@ -857,6 +1358,19 @@ extern "C" int cmc_welch_hann_spectra(const void* plan, const float* x1, int n_c
     { const char* e = getenv("CMC_DT_DBG"); p.dbg = e ? atoi(e) : 0; }
     { const char* e = getenv("CMC_DT_PF"); p.pf = e ? atoi(e) : kDtPrefetch; }
     const long long n_units = (long long)p.n_items * p.n_gp;
+    if (fold) {
+        p.KB = pl->N / 4 / kFdKB;
+        p.e1im = pl->d_e1c;
+        p.rot = pl->d_rot;
+        const size_t smem_f = 1024 + (size_t)(kFdStagesL + kFdStagesA) * kFdABytes + (size_t)kFdStagesB * kFdBBytes +
+                              (2 + kDtSlots) * kDtM * sizeof(float) + kFdRows * sizeof(float4) + sizeof(FdBarriers) + 16;
+        rc = ensure_smem_attr(reinterpret_cast<const void*>(dft_hann_fold_kernel), smem_f);
+        if (rc) return rc;
+        const unsigned grid_f = (unsigned)(n_units < sms ? n_units : sms);
+        dft_hann_fold_kernel<<<grid_f, kDtThreads, smem_f, st>>>(m0, m1, pl->mWf, p);
+        CMC_CHECK_LAUNCH("dft_hann_fold_kernel");
+        return CMC_OK;
+    }
     // CMC_DT_PAIR=1: CTA pairs (tcgen05 cta_group::2) share every W k-block.  Bit-identical results; measured SLOWER
     // (77 us against 54 us for config 2: the pair's barrier round trips lengthen every stage cycle by ~2 us while the
     // raw / A ring, which bounds the loop, is no deeper), so it is not the default.

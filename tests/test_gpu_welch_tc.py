@@ -186,7 +186,9 @@ def test_cta_pair_variant_is_bit_identical(cuda_device, monkeypatch):
     assert plan.n_half_blocks == 10 and plan_odd.n_half_blocks == 9
     for pl in (plan, plan_odd):
         monkeypatch.delenv("CMC_DT_PAIR", raising=False)
+        monkeypatch.setenv("CMC_DT_UNFOLD", "1")              # the unfolded single-CTA kernel: same arithmetic as the pair
         single = _run(K, pl, e, m, 60)
+        monkeypatch.delenv("CMC_DT_UNFOLD")
         monkeypatch.setenv("CMC_DT_PAIR", "1")
         paired = _run(K, pl, e, m, 60)
         monkeypatch.delenv("CMC_DT_PAIR")
