@@ -91,12 +91,13 @@ CMC_API int cmc_fft_segments_pair(const float* x1, int n_ch1, int64_t ld1, float
  * K1t  band-limited hann-windowed Welch spectra on the tensor cores.
  * The reference's Welch path is scipy.signal.coherence with its defaults (preprocessing.py:1228-1230): periodic
  * hann window, noverlap = nperseg / 2, detrend = 'constant'; its callers keep a narrow band (1 - 100 Hz).  For that
- * case the spectra are computed WITHOUT an FFT: one BF16 x 3 tcgen05 GEMM per half block of N / 2 samples against a
- * constant (cos, -sin) table gives the rectangular-window half-block sums P_h[b]; the epilogue applies the hann
- * window as the three-tap filter 1/2 R[b] - 1/4 (R[b-1] + R[b+1]) and adds the two halves of every segment
- * (R_s[b] = P_h[b] + (-1)^b P_{h+1}[b]).  Every sample is transformed once although segments overlap by half, and
- * only the requested bins are computed.  Output identical in meaning to cmc_fft_segments(.., windows = periodic
- * hann, n_win = 1, ..) to ~1e-5 of the spectrum's rms (BF16 hi + lo operands, FP32 accumulation).
+ * case the spectra are computed WITHOUT an FFT: BF16 x 3 tcgen05 GEMMs per half block of N / 2 samples (folded about
+ * its centre: sums against a cos table, differences against a sin table, K = N / 4) give the rectangular-window
+ * half-block sums P_h[b]; the epilogue applies the hann window as the three-tap filter 1/2 R[b] - 1/4 (R[b-1] +
+ * R[b+1]) and adds the two halves of every segment (R_s[b] = P_h[b] + (-1)^b P_{h+1}[b]).  Every sample is
+ * transformed once although segments overlap by half, and only the requested bins are computed.  Output identical
+ * in meaning to cmc_fft_segments(.., windows = periodic hann, n_win = 1, ..) to ~3e-5 of the spectrum's rms (BF16
+ * hi + lo operands, FP32 accumulation).
  *
  * A plan holds what depends on the segment table, N and the band only: the half-block list (segments that overlap
  * their predecessor by exactly N / 2 share a half block; any other segment simply costs two) and the table.

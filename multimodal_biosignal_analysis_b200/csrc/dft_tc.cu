@@ -1,4 +1,6 @@
 // K1t: band-limited hann-windowed Welch spectra on the tensor cores (tcgen05.mma kind::f16, BF16 x 3).
+// This file holds the unfolded kernel (dft_hann_tc_kernel, also as CTA pairs) and, further down, the folded kernel
+// that is the default (dft_hann_fold_kernel); the header describes what both share.
 //
 // The Welch path of the reference is scipy.signal.coherence with its defaults (preprocessing.py:1228-1230): periodic
 // hann window, 50 % overlap, per-segment constant detrend - and the callers only keep a narrow band (1 - 100 Hz =
