@@ -723,15 +723,25 @@ __device__ __forceinline__ void fd_load_rotate(uint32_t taddr, int cq, float (&r
     }
 }
 
-// oA / oB: output pointers of accumulator bin 0 (any valid address when the emission is off), on_a / on_b: emission on
+// oA / oB: output pointers of accumulator bin 0 (any valid address when the emission is off), on_a / on_b: emission on.
+// Chunks [c_begin, c_end) of the 13 eight-bin chunks: the four epilogue warps take all of them, except for the LAST
+// unit of a CTA, whose epilogue nothing overlaps - there the eight converter warps (idle by then) take two thirds.
 template <bool ADD>
 __device__ __forceinline__ void fd_epilogue_bins(uint32_t taddr, float chh, uint32_t tab_s, int j_lo, int j_hi,
                                                  float dc_add, bool dc_is_bin0, bool dc_zero_all, bool post_taper,
-                                                 float sgn_even, float2* oA, float2* oB, int on_a, int on_b, long long ld) {
+                                                 float sgn_even, float2* oA, float2* oB, int on_a, int on_b, long long ld,
+                                                 int c_begin, int c_end) {
     float cre[8], cim[8], nre[8] = {}, nim[8] = {};
-    fd_load_rotate(taddr, 0, cre, cim, chh, tab_s);
     float pm_re = 0.f, pm_im = 0.f;              // P[j - 1] of the first bin of the chunk
-    if (dc_is_bin0) {                            // accumulator bin 0 is the DC bin
+    if (c_begin > 0) {
+        fd_load_rotate(taddr, c_begin - 1, cre, cim, chh, tab_s);
+        pm_re = cre[7];
+        pm_im = cim[7];
+        oA += (long long)(8 * c_begin) * ld;
+        oB += (long long)(8 * c_begin) * ld;
+    }
+    fd_load_rotate(taddr, c_begin, cre, cim, chh, tab_s);
+    if (dc_is_bin0 && c_begin == 0) {            // accumulator bin 0 is the DC bin
         cre[0] = dc_zero_all ? 0.f : cre[0] + dc_add;
         cim[0] = 0.f;
         pm_re = cre[1];                          // P[-1] = conj(P[1])
@@ -739,7 +749,7 @@ __device__ __forceinline__ void fd_epilogue_bins(uint32_t taddr, float chh, uint
     }
     constexpr int kChunks = kDtBins / 8;         // 13
 #pragma unroll 1
-    for (int cq = 0; cq < kChunks; ++cq) {
+    for (int cq = c_begin; cq < c_end; ++cq) {
         if (cq < kChunks - 1) fd_load_rotate(taddr, cq + 1, nre, nim, chh, tab_s);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
@@ -767,6 +777,52 @@ __device__ __forceinline__ void fd_epilogue_bins(uint32_t taddr, float chh, uint
             cim[i] = nim[i];
         }
     }
+}
+
+// Everything of one unit's epilogue that depends on the lane: output pointers, the DC terms, the wait for the store
+// phase, then the chunks [c_begin, c_end).  Called by the epilogue warps for every unit and by the converter warps for
+// the last unit of the CTA.
+__device__ __forceinline__ void fd_unit_epilogue(const DtParams& p, const DtItem& it, int gp, int m, int lane, uint32_t taddr,
+                                                 float chh, uint32_t tab_s, unsigned store_target, int c_begin, int c_end) {
+    int rec, c0;
+    dt_group(p, 2 * gp + (m >> 6), rec, c0);
+    const int ch = c0 + (m & 63);
+    const bool valid = ch < (rec ? p.n_ch[1] : p.n_ch[0]);
+    float2* sp = rec ? p.spec[1] : p.spec[0];
+    float2* outA = (valid && it.seg_a >= 0) ? sp + (long long)it.seg_a * p.F * p.spec_ld + ch : nullptr;
+    float2* outB = (valid && it.seg_b >= 0) ? sp + (long long)it.seg_b * p.F * p.spec_ld + ch : nullptr;
+    float c_first = 0.f;
+    if (p.b0 == 0 && p.detrend != CMC_DETREND_CONSTANT && valid && c_begin == 0)
+        c_first = __ldg((rec ? p.x[1] : p.x[0]) + (long long)it.c_row * (rec ? p.ld[1] : p.ld[0]) + ch);
+    if (it.phase) {
+        // adds may only start once every store of the launch is visible
+        if (lane == 0) {
+            const long long t0 = clock64();
+            while (dt_ld_acquire(&p.ctr->next) < store_target) {
+                __nanosleep(64);
+                if (clock64() - t0 > 4000000000LL) {
+                    printf("cmc: dft_hann_fold store-phase wait timed out (block %d)\n", blockIdx.x);
+                    __trap();
+                }
+            }
+        }
+        __syncwarp();
+    }
+    const int j_lo = p.bin_lo - p.b0;
+    const long long back = (long long)j_lo * p.spec_ld;
+    const bool dc0 = p.b0 == 0;
+    const float dc_add = 0.5f * (float)p.N * c_first;        // the c_h part came in through E1c[0] = N / 2
+    const float sgn_even = (p.b0 & 1) ? -1.0f : 1.0f;
+    // emissions that are off (no such segment, channel out of range) keep a valid pointer and a zero predicate
+    const int on_a = (outA != nullptr && !(p.dbg & 4)) ? 1 : 0, on_b = (outB != nullptr && !(p.dbg & 4)) ? 1 : 0;
+    float2* pa_ = (outA ? outA : sp) - back;
+    float2* pb_ = (outB ? outB : sp) - back;
+    if (it.phase)
+        fd_epilogue_bins<true>(taddr, chh, tab_s, j_lo, j_lo + p.F, dc_add, dc0, p.detrend == CMC_DETREND_CONSTANT,
+                               p.detrend == CMC_DETREND_POST_TAPER, sgn_even, pa_, pb_, on_a, on_b, p.spec_ld, c_begin, c_end);
+    else
+        fd_epilogue_bins<false>(taddr, chh, tab_s, j_lo, j_lo + p.F, dc_add, dc0, p.detrend == CMC_DETREND_CONSTANT,
+                                p.detrend == CMC_DETREND_POST_TAPER, sgn_even, pa_, pb_, on_a, on_b, p.spec_ld, c_begin, c_end);
 }
 
 __global__ void __launch_bounds__(kDtThreads, 1)
@@ -977,66 +1033,46 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
             }
             ++n;
         }
+        if (n > 0) {
+            // nothing is left to convert: take two thirds of the last unit's epilogue (nothing overlaps it otherwise)
+            const int u_last = (int)blockIdx.x + (int)(n - 1) * (int)gridDim.x;
+            const DtItem it = p.items[u_last / p.n_gp];
+            const uint32_t acc = (n - 1) & 1, accphase = ((n - 1) >> 1) & 1;
+            mbar_wait(&bars->tmem_full[acc], accphase);
+            tc_fence_after();
+            const float chh = coff[((n - 1) & (kDtSlots - 1)) * kDtM + m];
+            const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(((warp - 8) & 3) * 32) << 16);
+            const int c_begin = warp < 12 ? 5 : 9, c_end = warp < 12 ? 9 : kDtBins / 8;
+            fd_unit_epilogue(p, it, u_last % p.n_gp, m, lane, taddr, chh, smem_u32(tab), 4u * (unsigned)p.n_store_units,
+                             c_begin, c_end);
+            tc_fence_before();
+            if (!it.phase) __threadfence();
+            asm volatile("bar.sync 3, 384;" ::: "memory");
+        }
     } else if (warp >= 4) {
         // ===================== epilogue: rotation, three-tap hann, two emissions per half block =====================
         const int q = warp - 4;                  // TMEM lane quadrant
         const int m = threadIdx.x - 128;         // accumulator lane = channel of the unit
         uint32_t n = 0;
         const unsigned store_target = 4u * (unsigned)p.n_store_units;
+        const uint32_t tab_s = smem_u32(tab);
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const DtItem it = p.items[u / p.n_gp];
-            const int gp = u % p.n_gp;
-            int rec, c0;
-            dt_group(p, 2 * gp + (m >> 6), rec, c0);
-            const int ch = c0 + (m & 63);
-            const bool valid = ch < (rec ? p.n_ch[1] : p.n_ch[0]);
-            float2* sp = rec ? p.spec[1] : p.spec[0];
-            float2* outA = (valid && it.seg_a >= 0) ? sp + (long long)it.seg_a * p.F * p.spec_ld + ch : nullptr;
-            float2* outB = (valid && it.seg_b >= 0) ? sp + (long long)it.seg_b * p.F * p.spec_ld + ch : nullptr;
-            float c_first = 0.f;
-            if (p.b0 == 0 && p.detrend != CMC_DETREND_CONSTANT && valid)
-                c_first = __ldg((rec ? p.x[1] : p.x[0]) + (long long)it.c_row * (rec ? p.ld[1] : p.ld[0]) + ch);
+            const bool last = u + (int)gridDim.x >= n_units;         // the converter warps take chunks 5 - 12 of the last unit
             const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
             mbar_wait(&bars->tmem_full[acc], accphase);
             if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 50);
             tc_fence_after();
             const float chh = coff[(n & (kDtSlots - 1)) * kDtM + m];
-            if (it.phase) {
-                if (lane == 0) {
-                    const long long t0 = clock64();
-                    while (dt_ld_acquire(&p.ctr->next) < store_target) {
-                        __nanosleep(64);
-                        if (clock64() - t0 > 4000000000LL) {
-                            printf("cmc: dft_hann_fold store-phase wait timed out (block %d)\n", blockIdx.x);
-                            __trap();
-                        }
-                    }
-                }
-                __syncwarp();
-            }
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
-            const int j_lo = p.bin_lo - p.b0;
-            const long long back = (long long)j_lo * p.spec_ld;
-            const bool dc0 = p.b0 == 0;
-            const float dc_add = 0.5f * (float)p.N * c_first;        // the c_h part came in through E1c[0] = N / 2
-            const float sgn_even = (p.b0 & 1) ? -1.0f : 1.0f;
-            // emissions that are off (no such segment, channel out of range) keep a valid pointer and a zero predicate
-            const int on_a = (outA != nullptr && !(p.dbg & 4)) ? 1 : 0, on_b = (outB != nullptr && !(p.dbg & 4)) ? 1 : 0;
-            float2* pa_ = (outA ? outA : sp) - back;
-            float2* pb_ = (outB ? outB : sp) - back;
-            const uint32_t tab_s = smem_u32(tab);
-            if (it.phase)
-                fd_epilogue_bins<true>(taddr, chh, tab_s, j_lo, j_lo + p.F, dc_add, dc0, p.detrend == CMC_DETREND_CONSTANT,
-                                       p.detrend == CMC_DETREND_POST_TAPER, sgn_even, pa_, pb_, on_a, on_b, p.spec_ld);
-            else
-                fd_epilogue_bins<false>(taddr, chh, tab_s, j_lo, j_lo + p.F, dc_add, dc0, p.detrend == CMC_DETREND_CONSTANT,
-                                        p.detrend == CMC_DETREND_POST_TAPER, sgn_even, pa_, pb_, on_a, on_b, p.spec_ld);
+            fd_unit_epilogue(p, it, u % p.n_gp, m, lane, taddr, chh, tab_s, store_target, 0, last ? 5 : kDtBins / 8);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
             if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 51);
+            if (!it.phase) __threadfence();      // this thread's stores before the warp's arrival on the store counter
+            if (last) asm volatile("bar.sync 3, 384;" ::: "memory");   // ... and the helpers' stores (they fence too)
             if (!it.phase) {
-                __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(&p.ctr->next, 1u);
             }
