@@ -52,6 +52,18 @@ __device__ __forceinline__ float inv_fisher(float z) {
     const float t = fmaf(-2.0f, mufu_rcp(e + 1.0f), 1.0f);
     return t * t;
 }
+// The jackknife works in units of z' = 2 z / ln 2 = lg2((1 + c) / (1 - c)): exp(2 z) = 2^z', so neither direction
+// needs a multiplication by a constant, and the variance / CI half width scale along (t_crit * se is linear in z).
+// The lower clip of the reference (c >= 1e-10) moves z by < 2e-10 and is dropped; the upper clip is folded into the
+// clamp of the replicate coherence (1 - 2^-24 instead of 1: 6e-8 on a coherence).
+__device__ __forceinline__ float fisher_z2(float c) {          // c in [0, 1 - 2^-24]
+    return mufu_lg2((1.0f + c) * mufu_rcp(1.0f - c));
+}
+__device__ __forceinline__ float inv_fisher_z2(float z2) {     // tanh(z)^2 for z = z2 ln 2 / 2
+    const float e = mufu_ex2(fminf(fmaxf(z2, -34.6f), 34.6f));
+    const float t = fmaf(-2.0f, mufu_rcp(e + 1.0f), 1.0f);
+    return t * t;
+}
 __device__ __forceinline__ float msc_ratio(float re, float im, float sxx, float syy) {
     // clip(|sxy|^2 / max(sxx * syy, tiny), 0, 1) evaluated as |sxy / sqrt(sxx) / sqrt(syy)|^2 so that
     // the product of the auto-spectra cannot overflow / underflow in float32
@@ -144,23 +156,23 @@ __device__ __forceinline__ PairStats pair_stats_jk(const float2 (&x)[K], const f
     for (int k = K - 1; k >= 0; --k) {
         const float r = rx[k] * ry[k];
         const float u = (pre_re[k] + a) * r, v = (pre_im[k] + b) * r;
-        const float ck = fminf(u * u + v * v, 1.0f);
-        z[k] = fisher_z(ck);
+        const float ck = fminf(fmaf(u, u, v * v), 0.99999994f);
+        z[k] = fisher_z2(ck);
         csum += ck;
         zsum += z[k];
         a += c[k].x; b += c[k].y;
     }
-    const float mean = fminf(fmaxf(csum * (1.0f / K), 0.f), 1.f);
+    const float mean = csum * (1.0f / K);                      // every ck is in [0, 1 - 2^-24]
     const float zbar = zsum * (1.0f / K);
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) ss += (z[k] - zbar) * (z[k] - zbar);
-    const float se = mufu_sqrt(ss * ((float)(K - 1) / (float)K));
-    const float zc = fisher_z(mean);
+    for (int k = 0; k < K; ++k) ss = fmaf(z[k] - zbar, z[k] - zbar, ss);
+    const float hw = t_crit * mufu_sqrt(ss * ((float)(K - 1) / (float)K));
+    const float zc = fisher_z2(mean);
     PairStats out;
     out.coh = mean;
-    out.lo = fminf(inv_fisher(zc - t_crit * se), mean);
-    out.hi = fmaxf(inv_fisher(zc + t_crit * se), mean);
+    out.lo = fminf(inv_fisher_z2(zc - hw), mean);
+    out.hi = fmaxf(inv_fisher_z2(zc + hw), mean);
     return out;
 }
 
