@@ -415,8 +415,8 @@ def main_gpu(args):
         sampler.start()
     # dependency events for every step; timing events (start of gA / start of gB) on every 4th step only, so that
     # the per-kernel clocks do not perturb the pipeline they measure.  (One graph of 20 pipelined steps instead of
-    # per-step graphs was measured SLOWER, 56.8 against 50.2 us per step: inside the graph K2 of step j is launched
-    # ahead of K1 of step j + 1 and takes 100 SMs first, and K1's static two-round schedule then ends late.)
+    # per-step graphs was measured SLOWER, 56.8 against 50.2 us per step, and so were two steps per graph and stream,
+    # 53.7 us: K2 then takes its 100 SMs ahead of the next K1, whose static two-round schedule ends late.)
     TIMED = 4
     sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
     a_done = [torch.cuda.Event(enable_timing=(i % TIMED == 0)) for i in range(steps)]
