@@ -194,3 +194,62 @@ def test_cta_pair_variant_is_bit_identical(cuda_device, monkeypatch):
         monkeypatch.delenv("CMC_DT_PAIR")
         assert not torch.isnan(torch.view_as_real(paired)).any()
         assert torch.equal(single.view(torch.float32), paired.view(torch.float32))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_shapes_bands_chains(cuda_device, seed):
+    """Random segment length, band, channel counts, segment tables (chains of random length, isolated and duplicated
+    segments, unsorted) and detrend modes against the fp64 oracle."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.choice([256, 512, 1024, 2048, 4096, 1536, 384]))
+    half = N // 2
+    width = int(rng.integers(1, 103))
+    b0_max = half - 104
+    lo = int(rng.integers(0, max(1, min(b0_max, 300)) + 1))
+    hi = min(lo + width - 1, half - 2)
+    if hi + 1 - max(lo - 1, 0) > 103:
+        hi = max(lo - 1, 0) + 102
+    if max(lo - 1, 0) + 104 > half:
+        lo, hi = 1, min(40, half - 106)
+    assert K.WelchHannPlan.supports(N, lo, hi), (N, lo, hi)
+    n1 = int(rng.integers(1, 131))
+    n2 = int(rng.integers(0, 131))
+    ld1, ld2 = (n1 + 3) // 4 * 4, (max(n2, 1) + 3) // 4 * 4          # TMA rows need 16-byte pitches
+    starts = []
+    pos = 0
+    for _ in range(int(rng.integers(1, 6))):                          # chains
+        pos += int(rng.integers(0, 3 * N))
+        for k in range(int(rng.integers(1, 9))):
+            starts.append(pos + k * half)
+        pos = starts[-1] + N
+    if rng.random() < 0.5:
+        starts.append(starts[0])                                      # a duplicated segment
+    starts = np.array(starts, dtype=np.int64)
+    rng.shuffle(starts)
+    n = int(starts.max()) + N + int(rng.integers(0, 50))
+    scale = float(10.0 ** rng.uniform(-5, 3))                         # volts ... ADC counts
+    x1 = (scale * (rng.standard_normal((n, ld1)) + rng.uniform(-3, 3, ld1))).astype(np.float32)
+    x2 = (scale * (rng.standard_normal((n, ld2)) + rng.uniform(-3, 3, ld2))).astype(np.float32)
+    detrend = int(rng.integers(0, 3))
+    plan = K.WelchHannPlan(starts, N, lo, hi)
+    F = hi - lo + 1
+    x1d, x2d = _dev(x1)[:, :n1], _dev(x2)[:, :n2]
+    spec = torch.full((len(starts), 1, F, n1 + n2 + 3), float("nan"), dtype=torch.complex64, device="cuda")
+    if n2:
+        plan.spectra(x1d, spec[..., :n1], x2d, spec[..., n1:n1 + n2], detrend=detrend)
+    else:
+        plan.spectra(x1d, spec[..., :n1], detrend=detrend)
+    torch.cuda.synchronize()
+    got = spec[:, 0, :, :n1 + n2].cpu().numpy()
+    assert torch.isnan(spec[..., n1 + n2:].real).all()                                # nothing written past the channels
+    ref = _oracle_spectra(np.concatenate([x1[:, :n1], x2[:, :n2]], axis=1), starts, N, detrend, lo, hi)
+    assert not np.isnan(got.view(np.float32)).any()
+    if detrend != 1 and lo == 0:
+        # the DC bin of a non-detrended segment carries N/2 x mean: compare it relative to itself
+        dc = np.abs(got[:, 0] - ref[:, 0]) / (np.abs(ref[:, 0]) + 1e-30)
+        if detrend == 0:
+            assert np.max(dc) < 1e-5
+        got, ref = got[:, 1:], ref[:, 1:]
+    if got.shape[1]:
+        assert _rel_err(got, ref) < SPEC_TOL
