@@ -77,6 +77,11 @@ CMC_API int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int64_
                      int bin_lo, int bin_hi,
                      float* spec, int64_t spec_ld, void* stream);
 
+/* Creates the per-device constant tables cmc_fft_segments uses for segment length N (done on first use otherwise: a
+ * cudaMalloc and a synchronous copy, which a stream that is being captured into a CUDA graph cannot take - the first
+ * call for a new N inside a capture fails with CMC_EINVAL and says so). */
+CMC_API int cmc_fft_prepare(int N);
+
 /* The same for TWO recordings of equal length that share segments, windows and bins (EEG and EMG of one
  * subject-condition): one launch of the pipelined kernel when both arrays qualify for its TMA path (N = 512, 1024,
  * 2048; channel pitches multiples of 4 floats, 16-byte aligned bases), otherwise two cmc_fft_segments calls - the

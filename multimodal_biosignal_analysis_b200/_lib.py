@@ -23,6 +23,7 @@ _SIGNATURES = {
     "cmc_launch_count": (_i64, []),
     "cmc_fft_segments": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32,
                                    _vp, _i64, _vp]),
+    "cmc_fft_prepare": (C.c_int, [_i32]),
     "cmc_fft_segments_pair": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i32, _i64, _vp, _i64, _vp, _i32, _vp, _i32, _i32,
                                         _i32, _i32, _i32, _i64, _vp]),
     "cmc_welch_hann_plan_create": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(C.c_void_p)]),

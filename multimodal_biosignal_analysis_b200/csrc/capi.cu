@@ -40,7 +40,20 @@ int ensure_smem_attr(const void* func, size_t bytes) {
     return CMC_OK;
 }
 
-int get_twiddles(int N, const float2** twM, const float2** twN) {
+// A stream that is being captured cannot take the cudaMalloc + synchronous copy of a first-use table: fail with a
+// message that says what to do instead of breaking the capture halfway.
+int refuse_table_during_capture(cudaStream_t st, const char* what, int N) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+        set_error("%s: the table for N=%d does not exist yet and cannot be created while the stream is being captured "
+                  "into a CUDA graph - call cmc_fft_prepare(N) (or the same function once, eagerly) before the capture",
+                  what, N);
+        return CMC_EINVAL;
+    }
+    return CMC_OK;
+}
+
+int get_twiddles(int N, const float2** twM, const float2** twN, cudaStream_t st) {
     static std::mutex mu;
     static std::map<std::pair<int, int>, std::pair<float2*, float2*>> cache;
     int dev = 0;
@@ -50,6 +63,7 @@ int get_twiddles(int N, const float2** twM, const float2** twN) {
     auto key = std::make_pair(dev, N);
     auto it = cache.find(key);
     if (it == cache.end()) {
+        if ((rc = refuse_table_during_capture(st, "cmc_fft_segments", N))) return rc;
         const int M = N / 2;
         std::vector<float2> h(M + M + 1);
         const double two_pi = 6.283185307179586476925286766559;

@@ -47,6 +47,7 @@ int ensure_smem_attr(const void* func, size_t bytes);
 
 // Per-device immutable twiddle tables (created on first use, never freed/changed).
 //   twM[q] = exp(-2 pi i q / M), q in [0, M);  twN[b] = exp(-2 pi i b / N), b in [0, N/2]
-int get_twiddles(int N, const float2** twM, const float2** twN);
+int get_twiddles(int N, const float2** twM, const float2** twN, cudaStream_t st = nullptr);
+int refuse_table_during_capture(cudaStream_t st, const char* what, int N);
 
 }  // namespace cmc

@@ -219,7 +219,7 @@ dft_direct_kernel(const float* __restrict__ x, int n_ch, int64_t ld, const int64
 }
 
 // full-circle table exp(-2 pi i q / N), q in [0, N), for the direct kernel
-static int get_full_twiddles(int N, const float2** tw) {
+static int get_full_twiddles(int N, const float2** tw, cudaStream_t st = nullptr) {
     static std::mutex mu;
     static std::map<std::pair<int, int>, float2*> cache;
     int dev = 0;
@@ -229,6 +229,7 @@ static int get_full_twiddles(int N, const float2** tw) {
     auto key = std::make_pair(dev, N);
     auto it = cache.find(key);
     if (it == cache.end()) {
+        if ((rc = refuse_table_during_capture(st, "cmc_fft_segments (direct DFT)", N))) return rc;
         std::vector<float2> h(N);
         for (int q = 0; q < N; ++q) {
             const double a = -6.283185307179586476925286766559 * q / N;
@@ -271,7 +272,7 @@ extern "C" int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int
         CMC_REQUIRE(N >= 2 && N <= (1 << 20), "cmc_fft_segments: N=%d outside [2, 2^20]", N);
         CMC_REQUIRE((int64_t)n_seg * n_win <= 2147483647ll, "cmc_fft_segments: too many segments");
         const float2* tw;
-        int rc0 = get_full_twiddles(N, &tw);
+        int rc0 = get_full_twiddles(N, &tw, static_cast<cudaStream_t>(stream));
         if (rc0) return rc0;
         dft_direct_kernel<<<dim3((unsigned)(n_seg * n_win), (n_ch + 31) / 32), dim3(32, 8), 0,
                             static_cast<cudaStream_t>(stream)>>>(x, n_ch, ld, seg_starts, windows, n_win, N, detrend, bin_lo,
@@ -281,9 +282,9 @@ extern "C" int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int
         return CMC_OK;
     }
     const float2 *twM, *twN;
-    int rc = get_twiddles(N, &twM, &twN);
-    if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = get_twiddles(N, &twM, &twN, st);
+    if (rc) return rc;
     const int F = bin_hi - bin_lo + 1;
     float2* sp = reinterpret_cast<float2*>(spec);
     // fast path: TMA-staged two-channel kernel (fft_tma.cu); returns 1 when the layout does not qualify
@@ -310,6 +311,19 @@ extern "C" int cmc_fft_segments(const float* x, int64_t n_samples, int n_ch, int
     return CMC_EUNSUPPORTED;
 }
 
+// Creates the per-device tables cmc_fft_segments needs for segment length N (twiddles, or the full-circle table of the
+// direct DFT for lengths the FFT kernels do not take) so that the first call for N may happen inside a stream capture.
+extern "C" int cmc_fft_prepare(int N) {
+    using namespace cmc;
+    CMC_REQUIRE(N >= 2 && N <= (1 << 20), "cmc_fft_prepare: N=%d outside [2, 2^20]", N);
+    if (N < 128 || N > 8192 || (N & (N - 1))) {
+        const float2* tw;
+        return get_full_twiddles(N, &tw);
+    }
+    const float2 *twM, *twN;
+    return get_twiddles(N, &twM, &twN);
+}
+
 // Two recordings of equal length that share the segment table, the window rows and the bin range (the EEG and the
 // EMG array of one subject-condition) in ONE launch of the pipelined K1 kernel when both qualify for it; any other
 // case runs as two cmc_fft_segments calls with identical results.  spec1 / spec2 share the row pitch spec_ld
@@ -329,7 +343,7 @@ extern "C" int cmc_fft_segments_pair(const float* x1, int n_ch1, int64_t ld1, fl
     static const bool no_pair = getenv("CMC_FFT_NO_PAIR") != nullptr || getenv("CMC_FFT_NO_TMA") != nullptr;
     if (fast && !no_pair) {
         const float2 *twM, *twN;
-        int rc = get_twiddles(N, &twM, &twN);
+        int rc = get_twiddles(N, &twM, &twN, static_cast<cudaStream_t>(stream));
         if (rc) return rc;
         rc = fft_segments_tma(x1, n_samples, n_ch1, ld1, seg_starts, n_seg, windows, n_win, N, detrend, bin_lo,
                               bin_hi - bin_lo + 1, reinterpret_cast<float2*>(spec1), spec_ld, twM, twN,

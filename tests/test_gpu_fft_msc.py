@@ -266,3 +266,27 @@ def test_fft_segments_pair_is_bit_identical_to_two_launches(cuda_device, N, ne, 
         assert torch.equal(joint[..., :ne], a) and torch.equal(joint[..., ne_p:ne_p + nm], b)
         if ne & 1:
             assert torch.all(joint[..., ne] == 0)                  # padding columns are never written
+
+
+def test_first_use_table_inside_capture_is_refused_cleanly(cuda_device):
+    """The twiddle table of a new N cannot be created while the stream is captured (cudaMalloc + synchronous copy):
+    the call must fail with a message that names cmc_fft_prepare, and work after preparing."""
+    from multimodal_biosignal_analysis_b200 import _lib, kernels as K
+    N = 160                                      # direct-DFT length that no other test uses
+    x = torch.randn(4 * N, 8, device="cuda")
+    starts = torch.tensor([0, N], dtype=torch.int64, device="cuda")
+    win = torch.ones(1, N, device="cuda")
+    out = torch.empty((2, 1, N // 2 + 1, 8), dtype=torch.complex64, device="cuda")
+    g = torch.cuda.CUDAGraph()
+    with pytest.raises(_lib.CmcError, match="cmc_fft_prepare"):
+        with torch.cuda.graph(g):
+            K.fft_segments(x, starts, win, 0, out=out)
+    torch.cuda.synchronize()
+    assert _lib.load().cmc_fft_prepare(N) == 0
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        K.fft_segments(x, starts, win, 0, out=out)
+    g2.replay()
+    torch.cuda.synchronize()
+    ref = torch.fft.rfft(x[:N].double(), dim=0)
+    assert torch.allclose(out[0, 0].to(torch.complex128), ref, atol=1e-3)
