@@ -989,6 +989,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
                     dif[i] = f - r;
                 }
                 __syncwarp();                    // every lane holds its samples: the raw tile may be overwritten
+                if (t == 0 && u == (int)blockIdx.x && kb >= 4 && kb < 7) dt_stamp(p, 53 + (kb - 4));
                 if (lane == 0) mbar_arrive(&bars->empty_l[sl]);
                 if (++sl == kFdStagesL) { sl = 0; pl ^= 1; }
                 if (kb == 0) {
@@ -1006,6 +1007,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
                     asm volatile("bar.sync 2, 256;" ::: "memory");   // csum may be rewritten by the next unit
                 }
                 mbar_wait(&bars->empty_a[sa], pa ^ 1);             // the MMAs that read these planes have completed
+                if (t == 0 && u == (int)blockIdx.x && kb >= 4 && kb < 7) dt_stamp(p, 56 + (kb - 4));
                 // K-major rows of 64 bytes: 8-row atoms of 512 bytes, 16-byte chunk index XOR ((row >> 1) & 3)
                 const uint32_t row = smem_u32(sA + sa * kFdABytes) + (uint32_t)((m >> 3) * 512 + (m & 7) * 64);
                 const int sw = (m >> 1) & 3;
@@ -1029,6 +1031,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
                 fence_proxy_async();             // generic-proxy writes -> visible to the MMA's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->conv[sa]);       // one arrival per warp
+                if (t == 0 && u == (int)blockIdx.x && kb >= 4 && kb < 7) dt_stamp(p, 59 + (kb - 4));
                 if (++sa == kFdStagesA) { sa = 0; pa ^= 1; }
             }
             ++n;

@@ -30,3 +30,6 @@ print(f"epochs {NE}: prologue done {rel(1):.2f} us, epilogue start {rel(50):.2f}
 print("kb   tma-issue  landed   mma-issue")
 for kb in range(16):
     print(f"{kb:2d}   {rel(2 + kb):8.2f} {rel(34 + kb):8.2f} {rel(18 + kb):8.2f}")
+print("converter (kb 4-6): landed -> loads done -> planes free -> planes written")
+for i in range(3):
+    print(f"{4 + i:2d}   {rel(34 + 4 + i):8.2f} {rel(53 + i):8.2f} {rel(56 + i):8.2f} {rel(59 + i):8.2f}")
