@@ -825,6 +825,25 @@ __device__ __forceinline__ void fd_unit_epilogue(const DtParams& p, const DtItem
                                 p.detrend == CMC_DETREND_POST_TAPER, sgn_even, pa_, pb_, on_a, on_b, p.spec_ld, c_begin, c_end);
 }
 
+// MC: the two CTAs of a cluster share every table k-block.  Each CTA still runs its own units with its own MMAs
+// (cta_group::1); only the table ring is common: k-block g is loaded ONCE, by the CTA of rank g & 1, with a TMA multicast
+// that lands it in both CTAs and signals each CTA's own full_b barrier; a table stage is free when the MMAs of BOTH
+// CTAs have consumed it (tcgen05.commit multicast to both empty_b barriers, count 2).  Table traffic from L2 halves.
+__device__ __forceinline__ void fd_tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    const uint16_t mask = 3;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void fd_commit_mc(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
+template <bool MC>
 __global__ void __launch_bounds__(kDtThreads, 1)
 dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant__ CUtensorMap mX1,
                      const __grid_constant__ CUtensorMap mW, const DtParams p) {
@@ -842,6 +861,14 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = p.n_items * p.n_gp;
     const int q4 = p.N / 4;
+    const int rank = MC ? (int)dt_cta_rank() : 0;
+    // rounds of this CTA (pair): q = q0, q0 + q_step, ...; its unit in round q is 2 q + rank (MC) or q.  The last
+    // round of an odd unit count leaves the rank-1 CTA without a unit: it still takes part in the table ring.
+    const int q0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int q_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_rounds = MC ? (n_units + 1) / 2 : n_units;
+    auto unit_of = [&](int q) { return MC ? 2 * q + rank : q; };
+    auto is_last = [&](int q) { return q + q_step >= n_rounds || unit_of(q + q_step) >= n_units; };
     if (threadIdx.x == 0) dt_stamp(p, 0);
 
     if (threadIdx.x == 0) {
@@ -855,7 +882,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
         }
         for (int s = 0; s < kFdStagesB; ++s) {
             mbar_init(&bars->full_b[s], 1);
-            mbar_init(&bars->empty_b[s], 1);
+            mbar_init(&bars->empty_b[s], MC ? 2 : 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tmem_full[a], 1);
@@ -877,6 +904,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) dt_cluster_sync();                   // the peer's barriers exist before a multicast can signal them
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     if (threadIdx.x == 0) dt_stamp(p, 1);
@@ -886,8 +914,11 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
         if (lane == 0) {
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const DtItem it = p.items[u / p.n_gp];
+            int gk = 0;                                      // k-blocks of the table ring so far (same in both CTAs)
+            for (int q = q0; q < n_rounds; q += q_step) {
+                const int u = unit_of(q);
+                const bool live = u < n_units;
+                const DtItem it = p.items[(live ? u : 0) / p.n_gp];
                 const int gp = u % p.n_gp;
                 int ra, ca, rb, cb;
                 dt_group(p, 2 * gp, ra, ca);
@@ -898,20 +929,28 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
                     // forward tile: samples N/4 + 32 kb ...; mirrored tile: samples N/4 - 32 (kb + 1) ... (read backwards)
                     const int row_f = it.x_row + q4 + kb * kFdKB;
                     const int row_r = it.x_row + q4 - (kb + 1) * kFdKB;
-                    mbar_wait(&bars->empty_l[sa], pa ^ 1);
-                    if (u == (int)blockIdx.x && kb < 16) dt_stamp(p, 2 + kb);
-                    mbar_arrive_expect_tx(&bars->full_l[sa], kFdABytes);
-                    unsigned char* st = sL + sa * kFdABytes;
-                    tma_load_2d(st, ma, &bars->full_l[sa], ca, row_f);
-                    tma_load_2d(st + kFdPlaneA, mb, &bars->full_l[sa], cb, row_f);
-                    tma_load_2d(st + 2 * kFdPlaneA, ma, &bars->full_l[sa], ca, row_r);
-                    tma_load_2d(st + 3 * kFdPlaneA, mb, &bars->full_l[sa], cb, row_r);
-                    if (++sa == kFdStagesL) { sa = 0; pa ^= 1; }
-                    mbar_wait(&bars->empty_b[sb], pb ^ 1);
+                    if (live) {
+                        mbar_wait(&bars->empty_l[sa], pa ^ 1);
+                        if (q == q0 && kb < 16) dt_stamp(p, 2 + kb);
+                        mbar_arrive_expect_tx(&bars->full_l[sa], kFdABytes);
+                        unsigned char* st = sL + sa * kFdABytes;
+                        tma_load_2d(st, ma, &bars->full_l[sa], ca, row_f);
+                        tma_load_2d(st + kFdPlaneA, mb, &bars->full_l[sa], cb, row_f);
+                        tma_load_2d(st + 2 * kFdPlaneA, ma, &bars->full_l[sa], ca, row_r);
+                        tma_load_2d(st + 3 * kFdPlaneA, mb, &bars->full_l[sa], cb, row_r);
+                        if (++sa == kFdStagesL) { sa = 0; pa ^= 1; }
+                    }
+                    mbar_wait(&bars->empty_b[sb], pb ^ 1);         // MC: the MMAs of BOTH CTAs have consumed the stage
                     mbar_arrive_expect_tx(&bars->full_b[sb], kFdBBytes);
                     unsigned char* sw = sB + sb * kFdBBytes;
-                    tma_load_2d(sw, &mW, &bars->full_b[sb], kb * kFdKB, 0);                    // hi: cos rows, sin rows
-                    tma_load_2d(sw + 2 * kFdPlaneB, &mW, &bars->full_b[sb], kb * kFdKB, 2 * kFdRows);   // lo
+                    if (!MC) {
+                        tma_load_2d(sw, &mW, &bars->full_b[sb], kb * kFdKB, 0);                    // hi: cos rows, sin rows
+                        tma_load_2d(sw + 2 * kFdPlaneB, &mW, &bars->full_b[sb], kb * kFdKB, 2 * kFdRows);   // lo
+                    } else if ((gk & 1) == rank) {                 // this CTA's turn: one load feeds both CTAs
+                        fd_tma_load_2d_mc(sw, &mW, &bars->full_b[sb], kb * kFdKB, 0);
+                        fd_tma_load_2d_mc(sw + 2 * kFdPlaneB, &mW, &bars->full_b[sb], kb * kFdKB, 2 * kFdRows);
+                    }
+                    ++gk;
                     if (++sb == kFdStagesB) { sb = 0; pb ^= 1; }
                 }
             }
@@ -922,14 +961,22 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
             constexpr uint32_t idesc = make_idesc_bf16(kDtM, kFdRows);
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0, n = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            for (int q = q0; q < n_rounds; q += q_step) {
+                if (unit_of(q) >= n_units) {                 // no unit in the pair's last round: keep the table ring turning
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(&bars->full_b[sb], pb);
+                        fd_commit_mc(&bars->empty_b[sb]);
+                        if (++sb == kFdStagesB) { sb = 0; pb ^= 1; }
+                    }
+                    break;
+                }
                 const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
                 mbar_wait(&bars->tmem_empty[acc], accphase ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(&bars->full_b[sb], pb);
                     mbar_wait(&bars->conv[sa], pa);
-                    if (u == (int)blockIdx.x && kb < 16) dt_stamp(p, 18 + kb);
+                    if (q == q0 && kb < 16) dt_stamp(p, 18 + kb);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(sA + sa * kFdABytes);
                     const uint32_t b0 = smem_u32(sB + sb * kFdBBytes);
@@ -948,7 +995,8 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
                         }
                     }
                     umma_commit(&bars->empty_a[sa]);
-                    umma_commit(&bars->empty_b[sb]);
+                    if (MC) fd_commit_mc(&bars->empty_b[sb]);
+                    else umma_commit(&bars->empty_b[sb]);
                     if (++sa == kFdStagesA) { sa = 0; pa ^= 1; }
                     if (++sb == kFdStagesB) { sb = 0; pb ^= 1; }
                 }
@@ -963,7 +1011,11 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
         const int g = t >> 7;                    // folded samples 16 g .. 16 g + 15 of the k-block
         int sl = 0, sa = 0;
         uint32_t pl = 0, pa = 0, n = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        int u_last = -1;
+        for (int q = q0; q < n_rounds; q += q_step) {
+            const int u = unit_of(q);
+            if (u >= n_units) break;
+            u_last = u;
             const DtItem it = p.items[u / p.n_gp];
             const int gp = u % p.n_gp;
             int rec, c0;
@@ -974,7 +1026,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
             float c = ch < (rec ? p.n_ch[1] : p.n_ch[0]) ? __ldg(xr + (long long)it.c_row * ldr + ch) : 0.f;
             for (int kb = 0; kb < p.KB; ++kb) {
                 mbar_wait(&bars->full_l[sl], pl);
-                if (t == 0 && u == (int)blockIdx.x && kb < 16) dt_stamp(p, 34 + kb);
+                if (t == 0 && q == q0 && kb < 16) dt_stamp(p, 34 + kb);
                 const uint32_t lbase = smem_u32(sL + sl * kFdABytes);
                 const uint32_t src_f = lbase + (uint32_t)((m >> 6) * kFdPlaneA + (m & 63) * 4 + g * kFdSpt * 256);
                 // the mirror of forward row kk is row 31 - kk of the mirrored tile
@@ -989,7 +1041,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
                     dif[i] = f - r;
                 }
                 __syncwarp();                    // every lane holds its samples: the raw tile may be overwritten
-                if (t == 0 && u == (int)blockIdx.x && kb >= 4 && kb < 7) dt_stamp(p, 53 + (kb - 4));
+                if (t == 0 && q == q0 && kb >= 4 && kb < 7) dt_stamp(p, 53 + (kb - 4));
                 if (lane == 0) mbar_arrive(&bars->empty_l[sl]);
                 if (++sl == kFdStagesL) { sl = 0; pl ^= 1; }
                 if (kb == 0) {
@@ -1007,7 +1059,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
                     asm volatile("bar.sync 2, 256;" ::: "memory");   // csum may be rewritten by the next unit
                 }
                 mbar_wait(&bars->empty_a[sa], pa ^ 1);             // the MMAs that read these planes have completed
-                if (t == 0 && u == (int)blockIdx.x && kb >= 4 && kb < 7) dt_stamp(p, 56 + (kb - 4));
+                if (t == 0 && q == q0 && kb >= 4 && kb < 7) dt_stamp(p, 56 + (kb - 4));
                 // K-major rows of 64 bytes: 8-row atoms of 512 bytes, 16-byte chunk index XOR ((row >> 1) & 3)
                 const uint32_t row = smem_u32(sA + sa * kFdABytes) + (uint32_t)((m >> 3) * 512 + (m & 7) * 64);
                 const int sw = (m >> 1) & 3;
@@ -1031,14 +1083,13 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
                 fence_proxy_async();             // generic-proxy writes -> visible to the MMA's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->conv[sa]);       // one arrival per warp
-                if (t == 0 && u == (int)blockIdx.x && kb >= 4 && kb < 7) dt_stamp(p, 59 + (kb - 4));
+                if (t == 0 && q == q0 && kb >= 4 && kb < 7) dt_stamp(p, 59 + (kb - 4));
                 if (++sa == kFdStagesA) { sa = 0; pa ^= 1; }
             }
             ++n;
         }
         if (n > 0) {
             // nothing is left to convert: take two thirds of the last unit's epilogue (nothing overlaps it otherwise)
-            const int u_last = (int)blockIdx.x + (int)(n - 1) * (int)gridDim.x;
             const DtItem it = p.items[u_last / p.n_gp];
             const uint32_t acc = (n - 1) & 1, accphase = ((n - 1) >> 1) & 1;
             mbar_wait(&bars->tmem_full[acc], accphase);
@@ -1059,12 +1110,14 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
         uint32_t n = 0;
         const unsigned store_target = 4u * (unsigned)p.n_store_units;
         const uint32_t tab_s = smem_u32(tab);
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (int q = q0; q < n_rounds; q += q_step) {
+            const int u = unit_of(q);
+            if (u >= n_units) break;
             const DtItem it = p.items[u / p.n_gp];
-            const bool last = u + (int)gridDim.x >= n_units;         // the converter warps take chunks 5 - 12 of the last unit
+            const bool last = is_last(q);                            // the converter warps take chunks 5 - 12 of the last unit
             const uint32_t acc = n & 1, accphase = (n >> 1) & 1;
             mbar_wait(&bars->tmem_full[acc], accphase);
-            if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 50);
+            if (m == 0 && q == q0) dt_stamp(p, 50);
             tc_fence_after();
             const float chh = coff[(n & (kDtSlots - 1)) * kDtM + m];
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
@@ -1072,7 +1125,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
-            if (m == 0 && u == (int)blockIdx.x) dt_stamp(p, 51);
+            if (m == 0 && q == q0) dt_stamp(p, 51);
             if (!it.phase) __threadfence();      // this thread's stores before the warp's arrival on the store counter
             if (last) asm volatile("bar.sync 3, 384;" ::: "memory");   // ... and the helpers' stores (they fence too)
             if (!it.phase) {
@@ -1084,6 +1137,7 @@ dft_hann_fold_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) dt_cluster_sync();                   // no multicast into, and no commit onto, a CTA that has left
     if (warp == 2) tmem_dealloc(tmem_base, 512);
     if (threadIdx.x == 0) dt_stamp(p, 52);
     if (threadIdx.x == 0) {
@@ -1405,10 +1459,34 @@ extern "C" int cmc_welch_hann_spectra(const void* plan, const float* x1, int n_c
         p.rot = pl->d_rot;
         const size_t smem_f = 1024 + (size_t)(kFdStagesL + kFdStagesA) * kFdABytes + (size_t)kFdStagesB * kFdBBytes +
                               (2 + kDtSlots) * kDtM * sizeof(float) + kFdRows * sizeof(float4) + sizeof(FdBarriers) + 16;
-        rc = ensure_smem_attr(reinterpret_cast<const void*>(dft_hann_fold_kernel), smem_f);
+        // CMC_DT_MC=1: clusters of two CTAs share every table k-block by TMA multicast
+        if (getenv("CMC_DT_MC") != nullptr && sms >= 2) {
+            auto kern = dft_hann_fold_kernel<true>;
+            rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem_f);
+            if (rc) return rc;
+            const long long n_rounds = (n_units + 1) / 2;
+            const long long pairs = n_rounds < sms / 2 ? n_rounds : sms / 2;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(2 * pairs));
+            cfg.blockDim = dim3(kDtThreads);
+            cfg.dynamicSmemBytes = smem_f;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, m0, m1, pl->mWf, p), "cudaLaunchKernelEx(dft_hann_fold_kernel<mc>)");
+            if (rc) return rc;
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return CMC_OK;
+        }
+        rc = ensure_smem_attr(reinterpret_cast<const void*>(dft_hann_fold_kernel<false>), smem_f);
         if (rc) return rc;
         const unsigned grid_f = (unsigned)(n_units < sms ? n_units : sms);
-        dft_hann_fold_kernel<<<grid_f, kDtThreads, smem_f, st>>>(m0, m1, pl->mWf, p);
+        dft_hann_fold_kernel<false><<<grid_f, kDtThreads, smem_f, st>>>(m0, m1, pl->mWf, p);
         CMC_CHECK_LAUNCH("dft_hann_fold_kernel");
         return CMC_OK;
     }

@@ -253,3 +253,23 @@ def test_fuzz_shapes_bands_chains(cuda_device, seed):
         got, ref = got[:, 1:], ref[:, 1:]
     if got.shape[1]:
         assert _rel_err(got, ref) < SPEC_TOL
+
+
+def test_cluster_multicast_variant_is_bit_identical(cuda_device, monkeypatch):
+    """CMC_DT_MC=1: clusters of two CTAs share every table k-block by TMA multicast (each CTA keeps its own units and
+    MMAs).  Same arithmetic per output, so the spectra must be bit-identical to the default folded kernel - including an
+    odd number of units (the rank-1 CTA of the last pair only keeps the table ring turning)."""
+    from multimodal_biosignal_analysis_b200 import kernels as K
+    rng = np.random.default_rng(5)
+    e = rng.standard_normal((9000, 20)).astype(np.float32)
+    m = rng.standard_normal((9000, 64)).astype(np.float32)
+    starts = np.array([0, 512, 1024, 1536, 4000, 6000, 6512], dtype=np.int64)      # 10 half blocks
+    for st in (starts, starts[:-1]):                                                  # ... and 9
+        plan = K.WelchHannPlan(st, 1024, 1, 60)
+        monkeypatch.delenv("CMC_DT_MC", raising=False)
+        single = _run(K, plan, e, m, 60)
+        monkeypatch.setenv("CMC_DT_MC", "1")
+        shared = _run(K, plan, e, m, 60)
+        monkeypatch.delenv("CMC_DT_MC")
+        assert not torch.isnan(shared.real).any()
+        assert torch.equal(single.view(torch.float32), shared.view(torch.float32))
