@@ -21,7 +21,8 @@
 // (lo*hi + hi*lo + hi*hi, FP32 accumulation in TMEM): relative error ~1e-5 of the spectrum's rms, i.e. <= ~1e-6 on a
 // coherence - inside the 1e-4 gate.  Before the split every channel is shifted by the first sample of its chain of
 // overlapping segments (y = x - c; exact for b != 0 because both halves of a segment use the same c, undone for
-// b = 0), so a DC offset does not eat the 16 bits.
+// b = 0), so a DC offset does not eat the 16 bits, and by a short mean of the half block itself (c_h, added back per
+// odd bin in the epilogue), so the 1 / b leakage of a half-block mean does not sit in the accumulators.
 //
 // Determinism without a zero-fill.  Every output element receives exactly two contributions, from two consecutive
 // half blocks of a chain.  Half blocks of even chain position STORE, odd ones ADD (red.global.add.v2.f32); add-phase
@@ -29,10 +30,11 @@
 // in every CTA's static schedule, all CTAs are co-resident: no deadlock).  store + one add is order independent.
 //
 // Roles (512 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue (TMEM lane = channel), warps 8-15 converters.  Two 84 KB stages: the raw FP32 tile
-// [64 samples][128 channels] lands where the A operand will live; the converters read it into registers, meet at a
-// barrier and write the K-major BF16 hi / lo planes (manual 128-byte swizzle) in place; W hi / lo k-blocks arrive
-// by TMA next to it.  Two 208-column accumulators (TMEM columns 0 and 256) overlap the epilogue with the next unit.
+// warps 4-7 epilogue (TMEM lane = channel), warps 8-15 converters.  Unfolded kernel: the raw FP32 tile
+// [64 samples][128 channels] lands where the A operand will live (ring of three 32 KB stages); the converters read it
+// into registers, meet at a barrier and write the K-major BF16 hi / lo planes (manual 128-byte swizzle) in place; W
+// hi / lo k-blocks (52 KB) arrive by TMA on a ring of two.  Two 208-column accumulators (TMEM columns 0 and 256)
+// overlap the epilogue with the next unit.  The folded kernel (its own comment further down) halves K and the table.
 #include "common.cuh"
 #include "csd_layout.cuh"
 #include "tc_common.cuh"
