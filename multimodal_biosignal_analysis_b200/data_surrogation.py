@@ -148,12 +148,23 @@ def circular_shift_surrogate_null(pooled, n_surrogates: int = 1000, seed: int | 
     shifts = np.ascontiguousarray(shifts, dtype=np.int32)
     if shifts.shape != (n_surrogates,):
         raise ValueError("one shift per surrogate")
+    # only n_pos - 1 distinct surrogates exist: the smallest p-value the null can resolve is 1 / n_pos however many
+    # are drawn (the device contracts every distinct shift once and weights it with its multiplicity)
+    n_distinct = int(np.unique(shifts % n_pos).size)
+    if n_surrogates > n_pos - 1:
+        import warnings
+        warnings.warn(f"circular-shift null: {n_surrogates} surrogates drawn from only {n_pos - 1} distinct shifts "
+                      f"({n_distinct} used): p-values below {1.0 / n_pos:.3g} cannot be resolved; use the "
+                      "phase-randomised null for finer p-values", RuntimeWarning, stacklevel=2)
     begin, end, f_range, by_freq = _plan(n_surrogates, csd.dims[1], shard)
     dev = csd.coh.device
     exceed, max_local = K.surrogate_null(csd, K.SURR_SHIFT, begin, end,
                                          shifts=torch.from_numpy(shifts[begin:end]).to(dev), group=pooled.group,
                                          f_range=f_range)
-    return _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq, f_range)
+    out = _finish(pooled, exceed, max_local, n_surrogates, alpha, by_freq, f_range)
+    out["n_distinct_shifts"] = n_distinct
+    out["p_resolution"] = 1.0 / n_pos
+    return out
 
 
 def phase_randomised_surrogate_null(pooled, n_surrogates: int = 1000, seed: int = 0, alpha: float = 0.05,

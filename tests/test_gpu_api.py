@@ -151,7 +151,9 @@ def test_welch_api_and_surrogate_api(cuda_device):
     assert pc.coherence.shape == (30, 8, 12) and np.max(np.abs(pc.coherence - coh)) < 1e-4
     np.testing.assert_allclose(pc.freqs, np.arange(1, 31) * 2.0)
     del ref
-    null = ds.circular_shift_surrogate_null(pc, 200, seed=5)
+    with pytest.warns(RuntimeWarning, match="distinct shifts"):      # 28 segments: only 27 distinct surrogates exist
+        null = ds.circular_shift_surrogate_null(pc, 200, seed=5)
+    assert null["n_distinct_shifts"] <= 27 and abs(null["p_resolution"] - 1 / 28) < 1e-12
     assert null["exceed"].shape == coh.shape and null["max_stat"].shape == (200,)
     assert np.all(null["p_values"] > 0) and np.all(null["p_values"] <= 1)
     assert 0 < null["threshold_fwe"] <= 1
