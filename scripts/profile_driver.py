@@ -1,5 +1,5 @@
 """Every kernel of the hot path once at its BASELINE size, for `ncu --set full` (scripts/profile_r2.sh):
-config 2 (K1 for both modalities, K2 direct), config 3 (shift null, phase null of 1,024 surrogates, per-pair histogram pass),
+config 2 (K1t and the FFT K1 for both modalities, K2 direct), config 3 (shift null, phase null of 1,024 surrogates, per-pair histogram pass),
 the per-window multitaper estimator (K2w, 210 windows x 5 tapers), config 4 CBPA (1,184 permutations = 4 per CTA)."""
 import os
 import sys
@@ -21,7 +21,9 @@ starts = torch.from_numpy(starts_h).to(dev)
 win = torch.from_numpy(signal.get_window("hann", 2048).astype(np.float32)[None]).to(dev)
 L = len(starts_h)
 spec = torch.empty((L, 1, 100, 128), dtype=torch.complex64, device=dev)
+plan = K.WelchHannPlan(starts_h, 2048, 1, 100)     # K1t: the tensor-core Welch kernel (default K1 of the Welch path)
 for _ in range(2):                                  # first pass warms tables / attributes, second one is profiled
+    plan.spectra(eeg_d, spec[..., :64], emg_d, spec[..., 64:])
     K.fft_segments_pair(eeg_d, emg_d, starts, win, K.DETREND_CONSTANT, 1, 100, spec[..., :64], spec[..., 64:])
     res = K.csd_msc(spec[:, 0, :, :64], spec[:, 0, :, 64:])
     shifts = torch.from_numpy(np.random.default_rng(3).integers(1, L, 1000).astype(np.int32)).to(dev)
