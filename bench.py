@@ -306,7 +306,8 @@ def workload_config():
             "l2_policy": f"inputs larger than L2: {N_ROTATE} resident recordings (126 MB each) rotated per step",
             "parallelism": "one subject-condition per rank per step, no data-path collective",
             "pipelining": "one K1 launch per step transforms the EEG and the EMG array; consecutive steps overlap on "
-                          "two streams: K2 of step i runs beside K1 of step i + 1"}
+                          "two streams: K2 of step i (normal priority) runs beside K1 of step i + 1 (high priority); "
+                          "the timed region replays CUDA graphs of 20 such steps"}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -413,16 +414,42 @@ def main_gpu(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # dependency events for every step; timing events (start of gA / start of gB) on every 4th step only, so that
-    # the per-kernel clocks do not perturb the pipeline they measure.  (One graph of 20 pipelined steps instead of
-    # per-step graphs was measured SLOWER, 56.8 against 50.2 us per step, and so were two steps per graph and stream,
-    # 53.7 us: K2 then takes its 100 SMs ahead of the next K1, whose static two-round schedule ends late.)
+    # (Without the stream priorities below, one graph of 20 pipelined steps was SLOWER than per-step graphs, 56.8 against
+    # 50.2 us per step, and so were two steps per graph and stream, 53.7 us: K2 then took its 100 SMs ahead of the next
+    # K1.  Per-step graphs cost the host ~37 us per 50 us step - too close to being host bound on a slower machine.)
     TIMED = 4
-    sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
-    a_done = [torch.cuda.Event(enable_timing=(i % TIMED == 0)) for i in range(steps)]
-    b_done = [torch.cuda.Event(enable_timing=(i % TIMED == 0)) for i in range(steps)]
-    a_start = {i: torch.cuda.Event(enable_timing=True) for i in range(0, steps, TIMED)}
-    b_start = {i: torch.cuda.Event(enable_timing=True) for i in range(0, steps, TIMED)}
+    # K1 runs on a HIGH-priority stream, K2 on a normal one: when K1 of step i ends, K2 of step i and K1 of step i + 1
+    # become ready together, and K1 - 148 CTAs with a static two-round schedule - must get the SMs first; K2's 100 CTAs
+    # then start on the 56 SMs K1 leaves idle in its second round.  With --graph-steps G (default 20) the timed region
+    # replays CUDA graphs of G steps captured on those two streams (kernel nodes keep the priority of the stream they
+    # were captured on), so the host enqueues one graph per G steps; K mod G steps run through the per-step graphs.
+    sA, sB = torch.cuda.Stream(priority=-1), torch.cuda.Stream()
+    G = max(0, args.graph_steps)
+    n_big, rem = (steps // G, steps % G) if G else (0, steps)
+    big = None
+    if n_big:
+        big = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(big, stream=sA):
+            ev_b = []
+            for j in range(G):
+                if j >= N_ROTATE:
+                    sA.wait_event(ev_b[j - N_ROTATE])              # the slot's spectra buffer has been consumed
+                k1(*dev_sets[j % N_ROTATE], specs[j % N_ROTATE])
+                e = torch.cuda.Event()
+                e.record(sA)
+                sB.wait_event(e)
+                with torch.cuda.stream(sB):
+                    K.csd_msc(specs[j % N_ROTATE][:, 0, :, :NE], specs[j % N_ROTATE][:, 0, :, NE:])
+                    e2 = torch.cuda.Event()
+                    e2.record(sB)
+                    ev_b.append(e2)
+            sA.wait_stream(sB)
+        big.replay()                                               # untimed first replay
+        torch.cuda.synchronize()
+    a_done = [torch.cuda.Event(enable_timing=(i % TIMED == 0)) for i in range(rem)]
+    b_done = [torch.cuda.Event(enable_timing=(i % TIMED == 0)) for i in range(rem)]
+    a_start = {i: torch.cuda.Event(enable_timing=True) for i in range(0, rem, TIMED)}
+    b_start = {i: torch.cuda.Event(enable_timing=True) for i in range(0, rem, TIMED)}
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -432,7 +459,12 @@ def main_gpu(args):
     with torch.cuda.stream(sA):
         t_begin.record()
     host_t0 = time.perf_counter()
-    for i in range(steps):
+    with torch.cuda.stream(sA):
+        for _ in range(n_big):
+            big.replay()
+    if n_big:
+        sB.wait_stream(sA)
+    for i in range(rem):
         gA, gB, res = graphs[i % N_ROTATE]
         with torch.cuda.stream(sA):
             if i >= N_ROTATE:
@@ -448,8 +480,9 @@ def main_gpu(args):
             gB.replay()
             b_done[i].record()
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / steps      # must stay below ms_per_step
+    sB.wait_stream(sA)
     with torch.cuda.stream(sB):
-        t_end.record()                                  # stream B finishes last (its last graph waits for stream A)
+        t_end.record()                                  # stream B finishes last (it waits for stream A)
     cur.wait_stream(sA)
     cur.wait_stream(sB)
     barrier()
@@ -458,9 +491,7 @@ def main_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / steps
     value = NE * NM * world / (ms_per_step / 1e3)
-    # spans seen inside the pipelined region (kernels of consecutive steps overlap, so they are not additive)
-    k1_ms_pipe = float(np.mean([a_start[i].elapsed_time(a_done[i]) for i in a_start]))
-    k2_ms_pipe = float(np.mean([b_start[i].elapsed_time(b_done[i]) for i in b_start]))
+    del a_start, b_start
     # per-kernel durations for the roofline: right after the timed region (same process, same clocks, inputs rotated
     # the same way) two CUDA graphs, one with 2 * N_ROTATE K1 launches and one with as many K2 launches, are replayed
     # on ONE stream with CUDA events around every replay: launches of one stream do not overlap, and inside a graph no
@@ -842,8 +873,9 @@ def main_gpu(args):
                          "k2_ms_per_step": k2_ms, "k1_share_of_step": k1_ms / (k1_ms + k2_ms),
                          "timing_note": "launch_ms / k2_ms_per_step: CUDA events around graphs of 8 back-to-back launches "
                                         "of each kernel on one stream right after the timed region (serial step "
-                                        f"{serial_ms_per_step:.4f} ms); inside the two-stream timed region the spans "
-                                        f"overlap (K1 {k1_ms_pipe:.4f} ms, K2 {k2_ms_pipe:.4f} ms incl. waiting for SMs)"},
+                                        f"{serial_ms_per_step:.4f} ms); the timed region replays {n_big} graphs of {G} "
+                                        f"pipelined steps + {rem} single steps, in which kernels of neighbouring steps "
+                                        f"overlap"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "stages": stages,
             "host_enqueue_ms_per_step": host_enqueue_ms,
             # the other two headline metrics of BASELINE.json, copied up from `stages` for convenience
@@ -864,6 +896,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--graph-steps", type=int, default=20,
+                    help="steps per CUDA graph in the timed region (0: one graph pair per step)")
     ap.add_argument("--k1", default="tc", choices=["tc", "fft"],
                     help="K1 of the headline step: tensor-core half-block DFT (default) or the FFT kernel")
     ap.add_argument("--skip-stages", action="store_true",
