@@ -557,6 +557,8 @@ def main_gpu(args):
     single_ms = (time.perf_counter() - t0) * 1e3 / n_single
     e2e = {"value": NE * NM * world / (e2e_ms / 1e3), "unit": "pair-spectra/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(n_samples * (NE + NM) * 4), "d2h_bytes_per_step": int(F * NE * NM * 4),
+           "h2d_gb_per_s_per_gpu": n_samples * (NE + NM) * 4 / (e2e_ms * 1e6),
+           "bound": "host->device copy: the step is the upload of one recording over the GPU's PCIe link",
            "api": "signal_features.welch_coherence_sweep(recordings, ...): one recording per step, pinned host "
                   "tensors in, numpy coherence out; upload, K1 + K2 and download of consecutive recordings overlap",
            "single_call_ms": single_ms, "numa_node": numa_node,
