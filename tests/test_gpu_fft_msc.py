@@ -290,3 +290,39 @@ def test_first_use_table_inside_capture_is_refused_cleanly(cuda_device):
     torch.cuda.synchronize()
     ref = torch.fft.rfft(x[:N].double(), dim=0)
     assert torch.allclose(out[0, 0].to(torch.complex128), ref, atol=1e-3)
+
+
+def test_msc_windows_large_staging_and_unaligned_outputs(cuda_device):
+    """K (Ne + Nm) large enough for more than 48 KB of staged operands (opt-in shared memory), and outputs that are
+    only 4-byte aligned (scalar stores instead of the 8-byte ones): same bits as the aligned call, oracle parity."""
+    from multimodal_biosignal_analysis_b200 import kernels as K, _lib
+    rng = np.random.default_rng(11)
+    W, Kt, F, Ne, Nm = 2, 7, 3, 128, 256
+    X = (rng.standard_normal((W, Kt, F, Ne)) + 1j * rng.standard_normal((W, Kt, F, Ne))).astype(np.complex64)
+    Y = (rng.standard_normal((W, Kt, F, Nm)) + 1j * rng.standard_normal((W, Kt, F, Nm))).astype(np.complex64)
+    Y = (Y + 0.7 * X[..., :1]).astype(np.complex64)
+    Xd, Yd = _dev(X), _dev(Y)
+    t_crit = float(t_dist.ppf(0.975, Kt - 1))
+    coh, lo, hi, sig = K.msc_windows(Xd, Yd, None, True, t_crit, 0.3)
+    for w in range(W):
+        m, l, h = oc.jackknife_from_spectra(X[w].astype(np.complex128), Y[w].astype(np.complex128), 0.05)
+        assert np.max(np.abs(coh[w].cpu().numpy() - m)) < COH_TOL
+        tame = m < 0.999
+        assert np.max(np.abs(lo[w].cpu().numpy() - l)[tame]) < 2e-3
+        assert np.max(np.abs(hi[w].cpu().numpy() - h)[tame]) < 2e-3
+    best, blo, bhi, arg = K.msc_windows_maxemg(Xd, Yd, None, True, t_crit, None, return_argmax=True)
+    np.testing.assert_array_equal(best.cpu().numpy(), coh.cpu().numpy().max(axis=3))
+    np.testing.assert_array_equal(arg.cpu().numpy(), coh.cpu().numpy().argmax(axis=3))
+    # the same call through the C ABI with every output shifted by one element
+    n = W * F * Ne * Nm
+    bufs = [torch.zeros(n + 1, dtype=torch.float32, device="cuda") for _ in range(3)]
+    sbuf = torch.zeros(n + 1, dtype=torch.uint8, device="cuda")
+    lib = _lib.load()
+    rc = lib.cmc_msc_windows(Xd.data_ptr(), Yd.data_ptr(), W, Kt, F, Ne, Nm, Ne, Nm, None, 1, t_crit, 0.3,
+                             bufs[0].data_ptr() + 4, bufs[1].data_ptr() + 4, bufs[2].data_ptr() + 4,
+                             sbuf.data_ptr() + 1, _lib.current_stream())
+    _lib.check(rc, "cmc_msc_windows")
+    torch.cuda.synchronize()
+    for got, ref in zip(bufs, (coh, lo, hi)):
+        assert torch.equal(got[1:], ref.reshape(-1))
+    assert torch.equal(sbuf[1:], sig.reshape(-1))
