@@ -79,6 +79,57 @@ __device__ __forceinline__ void mn_sts128(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Epilogue of one chunk of 32 accumulator columns (16 EMG channels) for the accumulator row te = (EEG channel, re/im)
+// of this thread: fold the 2 x 2 blocks, normalise, park the coherence in the staging tile, optionally store Sxy.
+__device__ __forceinline__ void mn_fold_chunk(const MnParams& p, uint32_t taddr, int ch, const float* pwa, float* stage_tile,
+                                              int te, int mt, int nt, int f) {
+    const int il = te >> 1, odd = te & 1;
+    const float sx = pwa[128 + il];
+    const int i = mt * 64 + il;
+    const uint32_t sy_addr = smem_u32(pwa + 192);
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + ch * 32, v);
+    float sy[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float4 w = mn_lds128(sy_addr + (uint32_t)(ch * 64 + g * 16));
+        sy[4 * g] = w.x; sy[4 * g + 1] = w.y; sy[4 * g + 2] = w.z; sy[4 * g + 3] = w.w;
+    }
+    tmem_ld_wait();
+    // Both lanes of a channel pair fetch the partner's row (two independent shuffles per column pair);
+    // the even lane then finishes the even EMG channels, the odd lane the odd ones.
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        const float e = __uint_as_float(v[2 * jj]), o = __uint_as_float(v[2 * jj + 1]);
+        const float ep = __shfl_xor_sync(0xffffffffu, e, 1);
+        const float op = __shfl_xor_sync(0xffffffffu, o, 1);
+        if ((jj & 1) == odd) {
+            // rows (i, re) / (i, im): Re S = xr yr + xi yi, Im S = xr yi - xi yr
+            const float re = odd ? ep + o : e + op;
+            const float im = odd ? op - e : o - ep;
+            const int jl = ch * 16 + jj;
+            // |S|^2 / (Pxx Pyy) as |S / sqrt(Pxx) / sqrt(Pyy)|^2: no overflow, silent channels give 0
+            const float sc = sx * sy[jj];
+            const float ar = re * sc, ai = im * sc;
+            stage_tile[il * kMnPitch + jl] = fminf(ar * ar + ai * ai, 1.0f);
+            if (p.sxy) {
+                const int j = nt * 64 + jl;
+                if (i < p.Ne && j < p.Nm) p.sxy[((long long)f * p.Ne + i) * p.Nm + j] = make_float2(re, im);
+            }
+        }
+    }
+}
+// coalesced copy-out of the 64 x 64 coherence tile by n_thr threads
+__device__ __forceinline__ void mn_copy_out(const MnParams& p, const float* stage_tile, int tid, int n_thr, int mt, int nt,
+                                            int f) {
+#pragma unroll 4
+    for (int idx = tid; idx < 64 * 64; idx += n_thr) {
+        const int r = idx >> 6, c = idx & 63;
+        const int gi = mt * 64 + r, gj = nt * 64 + c;
+        if (gi < p.Ne && gj < p.Nm) p.coh[((long long)f * p.Ne + gi) * p.Nm + gj] = stage_tile[r * kMnPitch + c];
+    }
+}
+
 __global__ void __launch_bounds__(kMnThreads, 1)
 csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mY, const MnParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -247,11 +298,29 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
             mbar_arrive(&bars->pw_full[acc]);
             ++it;
         }
+        if (t1 > t0) {
+            // help with the epilogue of the last tile: warps 8-11 fold column chunk 2, warps 12-15 chunk 3 (a warp reads
+            // the TMEM lane quadrant warp % 4), then everybody copies the tile out
+            const long long t = t1 - 1;
+            const int nt = (int)(t % p.NT);
+            const long long rr = t / p.NT;
+            const int mt = (int)(rr % p.MT), f = (int)(rr / p.MT);
+            const uint32_t acc = (it - 1) & 1, accphase = ((it - 1) >> 1) & 1;
+            mbar_wait(&bars->pw_full[acc], accphase);
+            mbar_wait(&bars->tmem_full[acc], accphase);
+            asm volatile("bar.sync 4, 384;" ::: "memory");      // the epilogue warps are done with the previous tile
+            tc_fence_after();
+            const int q = warp & 3, te = q * 32 + lane;
+            const uint32_t taddr = tmem_base + acc * 128 + (static_cast<uint32_t>(q * 32) << 16);
+            mn_fold_chunk(p, taddr, warp < 12 ? 2 : 3, pw + acc * 256, stage_tile, te, mt, nt, f);
+            tc_fence_before();
+            asm volatile("bar.sync 3, 384;" ::: "memory");
+            mn_copy_out(p, stage_tile, 128 + tc_, 384, mt, nt, f);
+        }
     } else if (warp >= 4) {
         // ===================== epilogue warps =====================
         const int q = warp - 4;                  // TMEM lane quadrant of this warp
         const int te = threadIdx.x - 128;        // 0..127 = accumulator row (i, ci)
-        const int il = te >> 1;                  // EEG channel of this lane pair
         uint32_t it = 0;
         for (long long t = t0; t < t1; ++t) {
             const int nt = (int)(t % p.NT);
@@ -263,50 +332,19 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
             if (t == t0 && te == 0) K2_STAMP(40);
             tc_fence_after();
             const float* pwa = pw + acc * 256;
-            const uint32_t sy_addr = smem_u32(pwa + 192);
-            const float sx = pwa[128 + il];
-            const int i = mt * 64 + il;
-            const int odd = te & 1;
             const uint32_t taddr = tmem_base + acc * 128 + (static_cast<uint32_t>(q * 32) << 16);
+            // On the last tile of this CTA the converter warps are idle: they take the upper two column chunks and a
+            // share of the copy-out (with one tile per CTA, config 2, that shortens the launch by the fold time).
+            const bool last = t == t1 - 1;
+            if (last) asm volatile("bar.arrive 4, 384;" ::: "memory");    // the staging tile is free for the helpers
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {     // 32 accumulator columns = 16 EMG channels
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + ch * 32, v);
-                float sy[16];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const float4 w = mn_lds128(sy_addr + (uint32_t)(ch * 64 + g * 16));
-                    sy[4 * g] = w.x; sy[4 * g + 1] = w.y; sy[4 * g + 2] = w.z; sy[4 * g + 3] = w.w;
-                }
-                tmem_ld_wait();
-                // Both lanes of a channel pair fetch the partner's row (two independent shuffles per column pair);
-                // the even lane then finishes the even EMG channels, the odd lane the odd ones.
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    const float e = __uint_as_float(v[2 * jj]), o = __uint_as_float(v[2 * jj + 1]);
-                    const float ep = __shfl_xor_sync(0xffffffffu, e, 1);
-                    const float op = __shfl_xor_sync(0xffffffffu, o, 1);
-                    if ((jj & 1) == odd) {
-                        // rows (i, re) / (i, im): Re S = xr yr + xi yi, Im S = xr yi - xi yr
-                        const float re = odd ? ep + o : e + op;
-                        const float im = odd ? op - e : o - ep;
-                        const int jl = ch * 16 + jj;
-                        // |S|^2 / (Pxx Pyy) as |S / sqrt(Pxx) / sqrt(Pyy)|^2: no overflow, silent channels give 0
-                        const float sc = sx * sy[jj];
-                        const float ar = re * sc, ai = im * sc;
-                        stage_tile[il * kMnPitch + jl] = fminf(ar * ar + ai * ai, 1.0f);
-                        if (p.sxy) {
-                            const int j = nt * 64 + jl;
-                            if (i < p.Ne && j < p.Nm) p.sxy[((long long)f * p.Ne + i) * p.Nm + j] = make_float2(re, im);
-                        }
-                    }
-                }
-            }
+            for (int ch = 0; ch < (last ? 2 : 4); ++ch) mn_fold_chunk(p, taddr, ch, pwa, stage_tile, te, mt, nt, f);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);   // accumulator may be overwritten
             if (t == t0 && te == 0) K2_STAMP(41);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (last) asm volatile("bar.sync 3, 384;" ::: "memory");      // with the helping converter warps
+            else asm volatile("bar.sync 1, 128;" ::: "memory");
             {   // auto-spectra outputs (every pair tile of a row block carries the same values)
                 const bool is_x = te < 64;
                 const int c = (is_x ? mt : nt) * 64 + (te & 63);
@@ -317,15 +355,9 @@ csd_mn_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CU
                     if (user) user[o] = pwa[te];
                 }
             }
-#pragma unroll 4
-            for (int n = 0; n < 32; ++n) {       // coalesced copy-out of the 64 x 64 coherence tile
-                const int idx = te + 128 * n;
-                const int r = idx >> 6, c = idx & 63;
-                const int gi = mt * 64 + r, gj = nt * 64 + c;
-                if (gi < p.Ne && gj < p.Nm) p.coh[((long long)f * p.Ne + gi) * p.Nm + gj] = stage_tile[r * kMnPitch + c];
-            }
+            mn_copy_out(p, stage_tile, te, last ? 384 : 128, mt, nt, f);
             mbar_arrive(&bars->pw_empty[acc]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!last) asm volatile("bar.sync 1, 128;" ::: "memory");
             if (t == t0 && te == 0) K2_STAMP(42);
             ++it;
         }
