@@ -3,10 +3,11 @@
 //
 // Replaces signal_features.py:750-796 (PSD / CSD sums, raw coherence, threshold mask) and
 // jackknife_coherence_and_ci (:484-578).  The average here runs over only K (~5) tapers, so
-// this is an outer-product + transcendental epilogue bound by the HBM write of the
-// (W, F, Ne, Nm) outputs, not a GEMM: CUDA cores, one CTA per (window, frequency chunk),
-// spectra of one (window, frequency) staged in shared memory, outputs written fully
-// coalesced (the pair index i * Nm + j is the contiguous output index).
+// this is an outer product with a transcendental epilogue, not a GEMM: CUDA cores, one CTA
+// per (window, frequency chunk), spectra of one (window, frequency) staged in shared memory,
+// outputs written fully coalesced (the pair index i * Nm + j is the contiguous output index).
+// Its floor is the HBM write of the (W, F, Ne, Nm) outputs (13 bytes per pair); measured, the
+// jackknife sits on the MUFU and FMA pipes (17 MUFU per pair) at ~2.5x that floor.
 #include "common.cuh"
 
 namespace cmc {
@@ -54,8 +55,7 @@ __device__ __forceinline__ float mufu_sqrt(float x) {
 // The jackknife works in units of z' = 2 z / ln 2 = lg2((1 + c) / (1 - c)): exp(2 z) = 2^z', so neither direction
 // needs a multiplication by a constant, and the variance / CI half width scale along (t_crit * se is linear in z).
 // The lower clip of the reference (c >= 1e-10) moves z by < 2e-10 and is dropped; the upper clip is folded into the
-// clamp of the replicate coherence (1 - 2^-24 instead of 1: 6e-8 on a coherence).
-// (fisher_z2x2 / inv_fisher_z2x2 below.)
+// clamp of the replicate coherence (1 - 2^-24 instead of 1: 6e-8 on a coherence).  fisher_z2x2 / inv_fisher_z2x2 below.
 __device__ __forceinline__ float msc_ratio(float re, float im, float sxx, float syy) {
     // clip(|sxy|^2 / max(sxx * syy, tiny), 0, 1) evaluated as |sxy / sqrt(sxx) / sqrt(syy)|^2 so that
     // the product of the auto-spectra cannot overflow / underflow in float32
